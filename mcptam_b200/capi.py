@@ -1,0 +1,216 @@
+"""ctypes plumbing over the C ABI (include/mcptam_b200.h) for tests and bench.py.
+
+This is not the product: the product is libmcptam_b200.so (CUDA kernels + extern "C" layer) and the C++
+host mirror under mcptam_b200/host/.  There is no CPU fallback: if the library is missing or no GPU is
+present, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .synth import TaylorCamStruct
+
+MCP_OK = 0
+ERRORS = {-101: "MCP_ERR_INVALID", -102: "MCP_ERR_CUDA", -103: "MCP_ERR_UNSUPPORTED", -104: "MCP_ERR_NO_DEVICE",
+          -105: "MCP_ERR_NCCL", -106: "MCP_ERR_STATE"}
+
+
+class McpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "error"), code, msg))
+        self.code = code
+
+
+class BaConfig(C.Structure):
+    _fields_ = [("use_robust", C.c_int32), ("use_tukey", C.c_int32), ("verbose", C.c_int32),
+                ("max_trials_after_failure", C.c_int32), ("update_pct_limit", C.c_double),
+                ("update_rms_limit", C.c_double), ("min_sigma", C.c_double), ("device", C.c_int32), ("pad_", C.c_int32)]
+
+
+class BaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("total_trials", C.c_int32), ("converged", C.c_int32),
+                ("hit_max_iter", C.c_int32), ("n_outliers", C.c_int32), ("pad_", C.c_int32),
+                ("sigma_sq", C.c_double), ("mean_chi2", C.c_double), ("lambda_", C.c_double), ("max_cov", C.c_double),
+                ("chi2_before", C.c_double), ("chi2_after", C.c_double), ("gpu_ms", C.c_double),
+                ("kernel_launches", C.c_int32), ("pad2_", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("pad")}
+
+
+class BaTiming(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ms_select", "ms_linearize", "ms_schur", "ms_solve", "ms_backsub", "ms_control", "ms_other")] + \
+               [(n, C.c_int32) for n in ("n_select", "n_linearize", "n_schur", "n_solve", "n_backsub", "n_control", "n_other", "pad_")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("pad")}
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def lib():
+    """Loads libmcptam_b200.so (building it with nvcc if the tree is newer)."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        if not os.path.exists(path):
+            raise RuntimeError("libmcptam_b200.so is missing: the CUDA extension must be built (no CPU fallback)")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.mcp_last_error.restype = C.c_char_p
+        L.mcp_ba_default_config.argtypes = [C.POINTER(BaConfig)]
+        L.mcp_ba_create.argtypes = [C.POINTER(BaConfig), C.POINTER(C.c_void_p)]
+        L.mcp_ba_destroy.argtypes = [C.c_void_p]
+        L.mcp_ba_set_cameras.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.mcp_ba_load.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.POINTER(BaStats)]
+        L.mcp_ba_get_poses.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcp_ba_get_points.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcp_ba_get_outliers.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.mcp_ba_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_reset_state.argtypes = [C.c_void_p]
+        L.mcp_ba_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.mcp_nccl_unique_id.argtypes = [C.c_void_p]
+        L.mcp_ba_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_debug_jacobians.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcp_ba_lm_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        L.mcp_ba_get_timing.argtypes = [C.c_void_p, C.POINTER(BaTiming)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def check(rc):
+    if rc < 0:
+        raise McpError(rc, lib().mcp_last_error().decode())
+    return rc
+
+
+def cam_array(cams):
+    arr = (TaylorCamStruct * len(cams))()
+    for i, c in enumerate(cams):
+        C.memmove(C.byref(arr[i]), C.byref(c), C.sizeof(c))
+    return arr
+
+
+class BaHandle:
+    """One mcp_ba handle: load a BaProblem (mcptam_b200.synth.BaProblem-like) and run Compute."""
+
+    def __init__(self, use_robust=True, use_tukey=True, device=-1, **cfg_kw):
+        self.L = lib()
+        cfg = BaConfig()
+        self.L.mcp_ba_default_config(C.byref(cfg))
+        cfg.use_robust = int(use_robust)
+        cfg.use_tukey = int(use_tukey)
+        cfg.device = device
+        for k, v in cfg_kw.items():
+            setattr(cfg, k, v)
+        self.h = C.c_void_p()
+        check(self.L.mcp_ba_create(C.byref(cfg), C.byref(self.h)))
+        self.prob = None
+
+    def close(self):
+        if self.h:
+            self.L.mcp_ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, unique_id: bytes | None, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.L.mcp_ba_comm_init(self.h, buf, rank, world))
+
+    def load(self, prob):
+        self.prob = prob
+        self._cams = cam_array(prob.cams)
+        check(self.L.mcp_ba_set_cameras(self.h, len(prob.cams), C.cast(self._cams, C.c_void_p)))
+        k = [np.ascontiguousarray(prob.pose_Rt, np.float64), np.ascontiguousarray(prob.pose_fixed, np.uint8),
+             np.ascontiguousarray(prob.pt_xyz, np.float64), np.ascontiguousarray(prob.pt_chain, np.int32),
+             np.ascontiguousarray(prob.pt_fixed, np.uint8), np.ascontiguousarray(prob.meas_xy, np.float64),
+             np.ascontiguousarray(prob.meas_chain, np.int32), np.ascontiguousarray(prob.meas_pt, np.int32),
+             np.ascontiguousarray(prob.meas_noise, np.float64), np.ascontiguousarray(prob.meas_cam, np.int32)]
+        self._keep = k
+        check(self.L.mcp_ba_load(self.h, prob.n_pose, _p(k[0]), _p(k[1]), prob.n_pt, _p(k[2]), _p(k[3]), _p(k[4]),
+                                 prob.n_meas, _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9])))
+        self.n_pose_var = int((k[1] == 0).sum())
+        self.n_pt_var = int((k[4] == 0).sum())
+
+    def compute(self, n_iter=100, user_lambda=-1.0, abort=None):
+        st = BaStats()
+        rc = self.L.mcp_ba_compute(self.h, _p(abort) if abort is not None else None, n_iter, float(user_lambda), C.byref(st))
+        if rc < -1:
+            check(rc)
+        return rc, st
+
+    def poses(self):
+        o = np.zeros((self.prob.n_pose, 12))
+        check(self.L.mcp_ba_get_poses(self.h, _p(o)))
+        return o
+
+    def points(self):
+        o = np.zeros((self.prob.n_pt, 3))
+        check(self.L.mcp_ba_get_points(self.h, _p(o)))
+        return o
+
+    def outliers(self):
+        n = self.L.mcp_ba_get_outliers(self.h, None, 0)
+        o = np.zeros(max(n, 1), np.int32)
+        self.L.mcp_ba_get_outliers(self.h, _p(o), n)
+        return o[:n]
+
+    def set_state(self, poses, points):
+        poses = np.ascontiguousarray(poses, np.float64)
+        points = np.ascontiguousarray(points, np.float64)
+        check(self.L.mcp_ba_set_state(self.h, _p(poses), _p(points)))
+
+    def reset_state(self):
+        check(self.L.mcp_ba_reset_state(self.h))
+
+    def eval(self):
+        e = np.zeros((self.prob.n_meas, 2))
+        c = np.zeros(self.prob.n_meas)
+        check(self.L.mcp_ba_eval(self.h, _p(e), _p(c)))
+        return e, c
+
+    def jacobians(self):
+        j = np.zeros((self.prob.n_meas, 30))
+        check(self.L.mcp_ba_debug_jacobians(self.h, _p(j)))
+        return j
+
+    def lm_step(self, lam, sigma_sq=-1.0):
+        d = np.zeros(6 * self.n_pose_var + 3 * self.n_pt_var)
+        s = C.c_double()
+        r = C.c_double()
+        check(self.L.mcp_ba_lm_step(self.h, float(lam), float(sigma_sq), _p(d), C.byref(s), C.byref(r)))
+        return d, s.value, r.value
+
+    def set_profiling(self, on=True):
+        check(self.L.mcp_ba_set_profiling(self.h, int(on)))
+
+    def timing(self):
+        t = BaTiming()
+        check(self.L.mcp_ba_get_timing(self.h, C.byref(t)))
+        return t.as_dict()
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().mcp_nccl_unique_id(buf))
+    return buf.raw

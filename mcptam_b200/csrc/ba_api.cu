@@ -1,0 +1,748 @@
+// ba_api.cu — C ABI of the bundle adjuster (include/mcptam_b200.h): host marshalling of the map into the
+// flat device layout, the LM driver loop (restating g2o's SparseOptimizer::optimize around the device
+// kernels) and the NCCL exchange of the Schur-reduced camera system for point-sharded multi-GPU runs.
+//
+// Reference: ChainBundle::{AddPose,AddPoint,AddMeas,Compute,...}  src/ChainBundle.cc:1198-1488
+//            BundleAdjusterMulti::BundleAdjust (marshalling)        src/BundleAdjusterMulti.cc:55-203
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "ba_types.cuh"
+
+namespace mcp {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// launchers defined in ba_kernels.cu
+int launch_linearize(const BaDev& d, bool schur, int warps, size_t smem, cudaStream_t s);
+int launch_schur_only(const BaDev& d, int warps, size_t smem, cudaStream_t s);
+int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
+void launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s);
+void launch_tukey_flags(const BaDev& d, cudaStream_t s);
+void launch_lambda_init(const BaDev& d, cudaStream_t s);
+void launch_lambda_apply(const BaDev& d, cudaStream_t s);
+void launch_solve(const BaDev& d, cudaStream_t s);
+size_t solve_smem_bytes(int nc);
+void launch_lm_control(const BaDev& d, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
+void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s);
+void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
+void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s);
+int configure_kernels(int max_slots, int* warps_out, size_t* smem_out);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap && p) return MCP_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;          // pooled across BundleAdjust calls
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { set_last_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return MCP_ERR_CUDA; }
+    cap = want;
+    return MCP_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum Cat { C_SELECT = 0, C_LIN, C_SCHUR, C_SOLVE, C_BACKSUB, C_CONTROL, C_OTHER, C_N };
+
+}  // namespace mcp
+
+using namespace mcp;
+
+struct McpBa {
+  McpBaConfig cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<DevCam> cams;
+  bool loaded = false;
+  BaDev d;
+  int lin_warps = 8;
+  size_t lin_smem = 0;
+  // device buffers (pooled)
+  DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
+      b_meas_a, b_meas_b, b_pose[2], b_pt[2], b_chi2[2], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
+      b_pose0, b_pt0, b_tmp;
+  size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
+  BaCtrl* ctrl_host = nullptr;   // pinned
+  int* flags_host = nullptr;     // pinned, n_meas
+  size_t flags_cap = 0;
+  std::vector<int> meas_orig;    // sorted position -> original index
+  std::vector<int32_t> outliers;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  std::vector<int> part_pt, part_meas;   // world+1 boundaries
+  // profiling
+  bool profiling = false;
+  McpBaTiming timing;
+  struct Ev { int cat; cudaEvent_t a, b; };
+  std::vector<Ev> evs;
+  int launches = 0;
+  double last_chi2_init = 1.7976931348623157e308;
+};
+
+extern "C" {
+
+const char* mcp_last_error(void) { return g_err; }
+int mcp_abi_version(void) { return 1; }
+
+void mcp_ba_default_config(McpBaConfig* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->use_robust = 1;
+  c->use_tukey = 1;
+  c->max_trials_after_failure = 100;   // src/ChainBundle.cc:1133
+  c->update_pct_limit = 1e-10;         // :1134
+  c->update_rms_limit = 1e-10;         // :1135
+  c->min_sigma = 0.5;                  // :1136
+  c->device = -1;
+}
+
+int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
+{
+  if (!out) { set_last_error("mcp_ba_create: out is NULL"); return MCP_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("mcp_ba_create: no CUDA device available (this library has no CPU fallback)");
+    return MCP_ERR_NO_DEVICE;
+  }
+  McpBa* h = new McpBa();
+  if (cfg) h->cfg = *cfg; else mcp_ba_default_config(&h->cfg);
+  if (h->cfg.device >= 0) { MCP_CUDA_CHECK(cudaSetDevice(h->cfg.device)); }
+  MCP_CUDA_CHECK(cudaGetDevice(&h->device));
+  MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  MCP_CUDA_CHECK(cudaEventCreate(&h->ev0));
+  MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->ctrl_host, sizeof(BaCtrl)));
+  memset(h->ctrl_host, 0, sizeof(BaCtrl));
+  memset(&h->d, 0, sizeof(h->d));
+  memset(&h->timing, 0, sizeof(h->timing));
+  *out = h;
+  return MCP_OK;
+}
+
+int mcp_ba_destroy(McpBa* h)
+{
+  if (!h) return MCP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_meas_off, &h->b_pt_slot_off,
+                    &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_pose[0],
+                    &h->b_pose[1], &h->b_pt[0], &h->b_pt[1], &h->b_chi2[0], &h->b_chi2[1], &h->b_V, &h->b_gp, &h->b_W,
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp };
+  for (DevBuf* b : all) b->release();
+  if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+  if (h->flags_host) cudaFreeHost(h->flags_host);
+  if (h->comm) ncclCommDestroy(h->comm);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MCP_OK;
+}
+
+int mcp_ba_set_cameras(McpBa* h, int32_t n_cam, const McpTaylorCam* cams)
+{
+  if (!h || n_cam <= 0 || !cams) { set_last_error("mcp_ba_set_cameras: bad arguments"); return MCP_ERR_INVALID; }
+  h->cams.resize(n_cam);
+  for (int i = 0; i < n_cam; i++) {
+    const McpTaylorCam& s = cams[i];
+    if (s.n_inv < 2 || s.n_inv > 32) { set_last_error("camera %d: n_inv=%d out of range", i, s.n_inv); return MCP_ERR_INVALID; }
+    DevCam& c = h->cams[i];
+    memset(&c, 0, sizeof(c));
+    memcpy(c.poly, s.poly, sizeof(c.poly));
+    // mv5PolyDerivModCoeffs, src/TaylorCamera.cc:107-110
+    c.dmod[0] = -s.poly[0]; c.dmod[1] = s.poly[1]; c.dmod[2] = s.poly[2]; c.dmod[3] = 2 * s.poly[3]; c.dmod[4] = 3 * s.poly[4];
+    memcpy(c.center, s.center, sizeof(c.center));
+    memcpy(c.affine, s.affine, sizeof(c.affine));
+    memcpy(c.image_size, s.image_size, sizeof(c.image_size));
+    c.min_theta = s.min_theta; c.theta_mean = s.theta_mean; c.theta_std = s.theta_std;
+    c.n_inv = s.n_inv;
+    memcpy(c.inv, s.inv_poly, sizeof(double) * 32);
+  }
+  cudaSetDevice(h->device);
+  int rc = h->b_cams.ensure(sizeof(DevCam) * n_cam);
+  if (rc) return rc;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_cams.p, h->cams.data(), sizeof(DevCam) * n_cam, cudaMemcpyHostToDevice, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+static int upload(McpBa* h, DevBuf& b, const void* src, size_t bytes)
+{
+  int rc = b.ensure(bytes ? bytes : 16);
+  if (rc) return rc;
+  if (bytes) MCP_CUDA_CHECK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return MCP_OK;
+}
+
+static void compute_partition(McpBa* h, const std::vector<int>& pt_meas_off, int n_pt)
+{
+  // contiguous, measurement-count-balanced partition of points
+  h->part_pt.assign(h->world + 1, 0);
+  h->part_meas.assign(h->world + 1, 0);
+  const long long total = pt_meas_off[n_pt] + (long long)n_pt * 4;   // weight: measurements + per-point overhead
+  int p = 0;
+  for (int r = 1; r < h->world; r++) {
+    const long long target = total * r / h->world;
+    while (p < n_pt && (long long)pt_meas_off[p] + (long long)p * 4 < target) p++;
+    h->part_pt[r] = p;
+  }
+  h->part_pt[h->world] = n_pt;
+  for (int r = 0; r <= h->world; r++) h->part_meas[r] = pt_meas_off[h->part_pt[r]];
+}
+
+int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* pose_fixed, int32_t n_pt,
+                const double* pt_xyz, const int32_t* pt_chain, const uint8_t* pt_fixed, int32_t n_meas,
+                const double* meas_xy, const int32_t* meas_chain, const int32_t* meas_pt, const double* meas_noise,
+                const int32_t* meas_cam)
+{
+  if (!h) { set_last_error("mcp_ba_load: NULL handle"); return MCP_ERR_INVALID; }
+  if (h->cams.empty()) { set_last_error("mcp_ba_load: call mcp_ba_set_cameras first"); return MCP_ERR_STATE; }
+  if (n_pose <= 0 || n_pt < 0 || n_meas < 0 || !pose_Rt || !pose_fixed || (n_pt && (!pt_xyz || !pt_chain || !pt_fixed)) ||
+      (n_meas && (!meas_xy || !meas_chain || !meas_pt || !meas_noise || !meas_cam))) {
+    set_last_error("mcp_ba_load: bad arguments");
+    return MCP_ERR_INVALID;
+  }
+  h->loaded = false;
+  const int n_cam = (int)h->cams.size();
+  std::vector<int> pose_var(n_pose);
+  int npv = 0;
+  for (int i = 0; i < n_pose; i++) pose_var[i] = pose_fixed[i] ? -1 : npv++;
+  for (int p = 0; p < n_pt; p++) {
+    const int a = pt_chain[2 * p], b = pt_chain[2 * p + 1];
+    if (a < 0 || a >= n_pose || b >= n_pose) { set_last_error("point %d: chain index out of range", p); return MCP_ERR_INVALID; }
+    if (b >= 0 && !pose_fixed[b]) { set_last_error("point %d: movable second chain link is not supported", p); return MCP_ERR_UNSUPPORTED; }
+  }
+  for (int m = 0; m < n_meas; m++) {
+    const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
+    if (a < 0 || a >= n_pose || b >= n_pose) { set_last_error("measurement %d: chain index out of range", m); return MCP_ERR_INVALID; }
+    if (b >= 0 && !pose_fixed[b]) { set_last_error("measurement %d: movable second chain link is not supported", m); return MCP_ERR_UNSUPPORTED; }
+    if (meas_pt[m] < 0 || meas_pt[m] >= n_pt) { set_last_error("measurement %d: point index out of range", m); return MCP_ERR_INVALID; }
+    if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) { set_last_error("measurement %d: camera index out of range", m); return MCP_ERR_INVALID; }
+    if (!(meas_noise[m] > 0)) { set_last_error("measurement %d: noise must be > 0", m); return MCP_ERR_INVALID; }
+  }
+  // sort measurements by point (stable counting sort)
+  std::vector<int> pt_meas_off(n_pt + 1, 0);
+  for (int m = 0; m < n_meas; m++) pt_meas_off[meas_pt[m] + 1]++;
+  for (int p = 0; p < n_pt; p++) pt_meas_off[p + 1] += pt_meas_off[p];
+  std::vector<int> cursor(pt_meas_off.begin(), pt_meas_off.end() - 1);
+  h->meas_orig.assign(n_meas, 0);
+  for (int m = 0; m < n_meas; m++) h->meas_orig[cursor[meas_pt[m]]++] = m;
+
+  std::vector<int> pt_var(n_pt);
+  int nptv = 0;
+  for (int p = 0; p < n_pt; p++) pt_var[p] = pt_fixed[p] ? -1 : nptv++;
+  std::vector<int4> pt_info(n_pt), meas_a(n_meas), meas_b(n_meas);
+  std::vector<double2> mxy(n_meas);
+  std::vector<double> minfo(n_meas);
+  std::vector<int> pt_slot_off(n_pt + 1, 0), slot_var;
+  slot_var.reserve((size_t)n_meas + n_pt);
+  int max_slots = 1;
+  std::vector<int> tmp;
+  for (int p = 0; p < n_pt; p++) {
+    const int src0 = pt_chain[2 * p], src1 = pt_chain[2 * p + 1];
+    const int src_var = pose_var[src0];
+    bool any_src = false;
+    tmp.clear();
+    for (int q = pt_meas_off[p]; q < pt_meas_off[p + 1]; q++) {
+      const int m = h->meas_orig[q];
+      const int obs0 = meas_chain[2 * m];
+      const bool has_jac = (obs0 != src0);                 // PoseChainHelper::MoveTogether at depth 0
+      const int ov = has_jac ? pose_var[obs0] : -1;
+      const bool has_src = has_jac && src_var >= 0;
+      any_src |= has_src;
+      if (ov >= 0) tmp.push_back(ov);
+      meas_a[q] = make_int4(obs0, meas_chain[2 * m + 1], meas_cam[m], m);
+      meas_b[q] = make_int4(ov, -1, has_src ? 1 : 0, p);
+      mxy[q] = make_double2(meas_xy[2 * m], meas_xy[2 * m + 1]);
+      minfo[q] = 1.0 / std::sqrt(meas_noise[m]);          // src/ChainBundle.cc:1244-1245
+    }
+    int src_slot = -1;
+    pt_slot_off[p] = (int)slot_var.size();
+    if (pt_var[p] >= 0) {
+      if (any_src) tmp.push_back(src_var);
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      for (int v : tmp) slot_var.push_back(v);
+      const int K = (int)tmp.size();
+      max_slots = std::max(max_slots, K);
+      for (int q = pt_meas_off[p]; q < pt_meas_off[p + 1]; q++)
+        if (meas_b[q].x >= 0) meas_b[q].y = (int)(std::lower_bound(tmp.begin(), tmp.end(), meas_b[q].x) - tmp.begin());
+      if (any_src) src_slot = (int)(std::lower_bound(tmp.begin(), tmp.end(), src_var) - tmp.begin());
+    }
+    pt_info[p] = make_int4(src0, src1, src_var, src_slot);
+  }
+  pt_slot_off[n_pt] = (int)slot_var.size();
+  const int n_slots = (int)slot_var.size();
+  const int nc = 6 * npv;
+  if (solve_smem_bytes(nc) > 220 * 1024) {
+    set_last_error("mcp_ba_load: %d movable poses exceed the single-CTA solver capacity", npv);
+    return MCP_ERR_UNSUPPORTED;
+  }
+  cudaSetDevice(h->device);
+  if (configure_kernels(max_slots, &h->lin_warps, &h->lin_smem) != 0) {
+    set_last_error("mcp_ba_load: a point is observed from %d movable keyframes, more than the kernel supports", max_slots);
+    return MCP_ERR_UNSUPPORTED;
+  }
+  compute_partition(h, pt_meas_off, n_pt);
+
+  int rc;
+#define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
+  UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_meas_off, pt_meas_off);
+  UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
+  UP(h->b_meas_a, meas_a); UP(h->b_meas_b, meas_b);
+#undef UP
+  const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)std::max(n_pt, 1);
+  for (int k = 0; k < 2; k++) {
+    if ((rc = upload(h, h->b_pose[k], pose_Rt, pose_bytes))) return rc;
+    if ((rc = upload(h, h->b_pt[k], pt_xyz, sizeof(double) * 3 * (size_t)n_pt))) return rc;
+    if ((rc = h->b_chi2[k].ensure(sizeof(double) * (size_t)std::max(n_meas, 1)))) return rc;
+  }
+  if ((rc = upload(h, h->b_pose0, pose_Rt, pose_bytes))) return rc;
+  if ((rc = upload(h, h->b_pt0, pt_xyz, sizeof(double) * 3 * (size_t)n_pt))) return rc;
+  (void)pt_bytes;
+  if ((rc = h->b_V.ensure(sizeof(double) * 6 * (size_t)std::max(n_pt, 1)))) return rc;
+  if ((rc = h->b_gp.ensure(sizeof(double) * 3 * (size_t)std::max(n_pt, 1)))) return rc;
+  if ((rc = h->b_W.ensure(sizeof(double) * 18 * (size_t)std::max(n_slots, 1)))) return rc;
+  // accumulators: [H0 | gc | red(8) | Sm | rm]
+  const size_t ncp = (size_t)std::max(nc, 1);
+  h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 8; h->off_rm = h->off_Sm + ncp * ncp;
+  h->acc_doubles = h->off_rm + ncp;
+  if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
+  if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
+  if ((rc = h->b_L.ensure(sizeof(double) * ncp * ncp))) return rc;
+  if ((rc = h->b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
+  if ((rc = h->b_ctrl.ensure(sizeof(BaCtrl)))) return rc;
+  if ((rc = h->b_flags.ensure(sizeof(int) * (size_t)std::max(n_meas, 1)))) return rc;
+  if ((size_t)n_meas > h->flags_cap) {
+    if (h->flags_host) cudaFreeHost(h->flags_host);
+    h->flags_host = nullptr;
+    MCP_CUDA_CHECK(cudaMallocHost(&h->flags_host, sizeof(int) * (size_t)(n_meas + n_meas / 4 + 16)));
+    h->flags_cap = (size_t)(n_meas + n_meas / 4 + 16);
+  }
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_acc.p, 0, sizeof(double) * h->acc_doubles, h->stream));
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_dc.p, 0, sizeof(double) * ncp, h->stream));
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
+
+  BaDev& d = h->d;
+  memset(&d, 0, sizeof(d));
+  d.cams = h->b_cams.as<DevCam>();
+  d.n_pose = n_pose; d.n_pt = n_pt; d.n_meas = n_meas; d.n_pose_var = npv; d.n_pt_var = nptv; d.nc = nc;
+  d.n_slots = n_slots; d.max_slots = max_slots;
+  d.p_lo = h->part_pt[h->rank]; d.p_hi = h->part_pt[h->rank + 1];
+  d.m_lo = h->part_meas[h->rank]; d.m_hi = h->part_meas[h->rank + 1];
+  d.pose_var = h->b_pose_var.as<int>(); d.pt_info = h->b_pt_info.as<int4>(); d.pt_var = h->b_pt_var.as<int>();
+  d.pt_meas_off = h->b_pt_meas_off.as<int>(); d.pt_slot_off = h->b_pt_slot_off.as<int>(); d.slot_var = h->b_slot_var.as<int>();
+  d.meas_xy = h->b_meas_xy.as<double2>(); d.meas_info = h->b_meas_info.as<double>();
+  d.meas_a = h->b_meas_a.as<int4>(); d.meas_b = h->b_meas_b.as<int4>();
+  for (int k = 0; k < 2; k++) { d.pose[k] = h->b_pose[k].as<double>(); d.pt[k] = h->b_pt[k].as<double>(); d.chi2[k] = h->b_chi2[k].as<double>(); }
+  d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>();
+  double* acc = h->b_acc.as<double>();
+  d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
+  d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.part = h->b_part.as<double>();
+  d.ctrl = h->b_ctrl.as<BaCtrl>(); d.outlier_flags = h->b_flags.as<int>();
+
+  BaCtrl& c = *h->ctrl_host;
+  memset(&c, 0, sizeof(c));
+  c.cur = 0;
+  c.last_chi2 = 1.7976931348623157e308;   // CheckConvergedResidualAction ctor, src/ChainBundle.cc:1068
+  c.min_sigma_sq = h->cfg.min_sigma * h->cfg.min_sigma;
+  c.sigma_sq_raw = 0; c.sigma_sq_lim = c.min_sigma_sq; c.sigma_lim = h->cfg.min_sigma;
+  c.pct_limit = h->cfg.update_pct_limit; c.rms_limit = h->cfg.update_rms_limit;
+  c.max_trials = h->cfg.max_trials_after_failure; c.use_robust = h->cfg.use_robust;
+  c.dim = 6 * npv + 3 * nptv;
+  c.solve_ok = 1;
+  c.sel_n = n_meas; c.sel_rank = n_meas / 2;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->outliers.clear();
+  h->loaded = true;
+  return MCP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// driver loop
+// ------------------------------------------------------------------------------------------
+#define NCCL_CHECK(expr)                                                                     \
+  do {                                                                                       \
+    ncclResult_t _r = (expr);                                                                \
+    if (_r != ncclSuccess) { set_last_error("%s failed: %s", #expr, ncclGetErrorString(_r)); return MCP_ERR_NCCL; } \
+  } while (0)
+
+namespace {
+
+struct Prof {
+  McpBa* h; int cat; cudaEvent_t a = nullptr, b = nullptr;
+  Prof(McpBa* h_, int cat_) : h(h_), cat(cat_)
+  {
+    h->launches++;
+    if (h->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, h->stream); }
+  }
+  ~Prof() { if (h->profiling) { cudaEventRecord(b, h->stream); h->evs.push_back({ cat, a, b }); } }
+};
+
+int sync_ctrl(McpBa* h)
+{
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+int push_ctrl(McpBa* h)
+{
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.ctrl, h->ctrl_host, sizeof(BaCtrl), cudaMemcpyHostToDevice, h->stream));
+  return MCP_OK;
+}
+
+// make chi2[which] / pt[which] complete on every rank (each rank owns a contiguous range)
+int allgather_ranges(McpBa* h, double* base, const std::vector<int>& bounds, int stride)
+{
+  if (h->world == 1) return MCP_OK;
+  NCCL_CHECK(ncclGroupStart());
+  for (int r = 0; r < h->world; r++) {
+    const size_t off = (size_t)bounds[r] * stride, cnt = (size_t)(bounds[r + 1] - bounds[r]) * stride;
+    if (cnt) NCCL_CHECK(ncclBroadcast(base + off, base + off, cnt, ncclDouble, r, h->comm, h->stream));
+  }
+  NCCL_CHECK(ncclGroupEnd());
+  return MCP_OK;
+}
+
+int eval_state(McpBa* h, int which, double* err_out)
+{
+  { Prof p(h, C_BACKSUB); launch_backsub_eval(h->d, 0, which, err_out, h->stream); }
+  return MCP_OK;
+}
+
+}  // namespace
+
+static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter, double user_lambda, McpBaStats* st,
+                       bool single_step, double step_lambda, double step_sigma_sq)
+{
+  BaDev& d = h->d;
+  BaCtrl& c = *h->ctrl_host;
+  cudaStream_t s = h->stream;
+  double* acc = h->b_acc.as<double>();
+  double* red = acc + h->off_red;
+  const bool multi = h->world > 1;
+  int rc;
+  auto aborted = [&]() { return abort_flag && *abort_flag; };
+
+  if ((rc = sync_ctrl(h))) return rc;
+  c.need_lambda_init = 1; c.user_lambda = user_lambda; c.iter = 0; c.conv_mag = 0; c.conv_res = 0; c.total_trials = 0;
+  c.terminate = 0; c.qmax = 0; c.solve_ok = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0;
+  if ((rc = push_ctrl(h))) return rc;
+  h->outliers.clear();
+
+  // errors of the initial state, sigma, "BEFORE" chi2 (src/ChainBundle.cc:1317-1323)
+  eval_state(h, -1, nullptr);
+  if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
+  if (h->cfg.use_robust && !(single_step && step_sigma_sq >= 0)) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+  if (single_step && step_sigma_sq >= 0) {
+    if ((rc = sync_ctrl(h))) return rc;
+    c.sigma_sq_raw = step_sigma_sq;
+    c.sigma_sq_lim = step_sigma_sq < c.min_sigma_sq ? c.min_sigma_sq : step_sigma_sq;
+    c.sigma_lim = std::sqrt(c.sigma_sq_lim);
+    if ((rc = push_ctrl(h))) return rc;
+  }
+  if (single_step) {
+    if ((rc = sync_ctrl(h))) return rc;
+    c.lambda = step_lambda; c.need_lambda_init = 0; c.ni = 2;
+    if ((rc = push_ctrl(h))) return rc;
+  }
+  int n_bs = 0, n_lin = 0;
+  n_bs = launch_backsub_eval(d, 0, -1, nullptr, s); h->launches++;
+  { Prof p(h, C_OTHER); launch_reduce_partials(d, 0, n_bs, red, s); }
+  if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 1, ncclDouble, ncclSum, h->comm, s));
+  double chi_before = 0;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&chi_before, red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (st) st->chi2_before = chi_before;
+
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev0, s));
+  int counter = 0;
+  bool ok = true, local_abort = false;
+  for (int it = 0; it < n_iter && !local_abort && !aborted() && ok; it++) {
+    if (it > 0) {
+      if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
+      if (h->cfg.use_robust) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+    }
+    MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
+    if (c.need_lambda_init) {
+      { Prof p(h, C_LIN); n_lin = launch_linearize(d, false, h->lin_warps, h->lin_smem, s); }
+      if (multi) {
+        launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
+        NCCL_CHECK(ncclAllReduce(acc, acc, h->off_Sm, ncclDouble, ncclSum, h->comm, s));
+      }
+      { Prof p(h, C_OTHER); launch_lambda_init(d, s); }
+      if (multi) NCCL_CHECK(ncclAllReduce(d.part + PART_MAXDIAG * MAX_PARTIALS, d.part + PART_MAXDIAG * MAX_PARTIALS, 1, ncclDouble, ncclMax, h->comm, s));
+      { Prof p(h, C_OTHER); launch_lambda_apply(d, s); }
+      { Prof p(h, C_SCHUR); launch_schur_only(d, h->lin_warps, h->lin_smem, s); }
+      if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, h->acc_doubles - h->off_Sm, ncclDouble, ncclSum, h->comm, s));
+      c.need_lambda_init = 0;
+    } else {
+      { Prof p(h, C_LIN); n_lin = launch_linearize(d, true, h->lin_warps, h->lin_smem, s); }
+      if (multi) {
+        launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
+        NCCL_CHECK(ncclAllReduce(acc, acc, h->acc_doubles, ncclDouble, ncclSum, h->comm, s));
+      }
+    }
+    bool first = true;
+    for (;;) {
+      { Prof p(h, C_SOLVE); launch_solve(d, s); }
+      { Prof p(h, C_BACKSUB); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
+      if (multi) {
+        launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
+        NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3, ncclDouble, ncclSum, h->comm, s));
+      }
+      { Prof p(h, C_CONTROL); launch_lm_control(d, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
+      first = false;
+      if ((rc = sync_ctrl(h))) return rc;
+      if (single_step) break;
+      if (c.stop_trials) break;
+      if (aborted()) {
+        // the trial loop ends on terminate(); close the outer iteration bookkeeping like g2o does
+        c.iter++; c.total_trials += c.qmax; c.qmax = 0;
+        if ((rc = push_ctrl(h))) return rc;
+        break;
+      }
+      MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * (h->acc_doubles - h->off_Sm), s));
+      { Prof p(h, C_SCHUR); launch_schur_only(d, h->lin_warps, h->lin_smem, s); }
+      if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, h->acc_doubles - h->off_Sm, ncclDouble, ncclSum, h->comm, s));
+    }
+    if (single_step) return MCP_OK;
+    counter++;
+    if (c.terminate) ok = false;
+    if (c.conv_mag || c.conv_res) local_abort = true;
+  }
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev1, s));
+
+  // "AFTER" block (src/ChainBundle.cc:1338-1345): errors + sigma of the final state
+  eval_state(h, -1, nullptr);
+  if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
+  if (h->cfg.use_robust) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+  n_bs = launch_backsub_eval(d, 0, -1, nullptr, s); h->launches++;
+  launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
+  if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 1, ncclDouble, ncclSum, h->comm, s));
+  double chi_after = 0;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&chi_after, red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if ((rc = allgather_ranges(h, d.pt[c.cur], h->part_pt, 3))) return rc;
+  if ((rc = sync_ctrl(h))) return rc;
+
+  const bool converged = c.conv_mag || c.conv_res;
+  const bool abort_now = local_abort || aborted();
+  const bool external_abort = abort_now && !converged;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  if (st) {
+    st->iterations = counter; st->total_trials = c.total_trials; st->converged = converged ? 1 : 0;
+    st->hit_max_iter = (counter == n_iter) ? 1 : 0; st->sigma_sq = c.sigma_sq_raw; st->lambda = c.lambda;
+    st->chi2_after = chi_after; st->mean_chi2 = d.n_meas ? chi_after / d.n_meas : 0; st->max_cov = 1.7976931348623157e308;
+    st->gpu_ms = ms; st->kernel_launches = h->launches; st->n_outliers = 0;
+  }
+  if (counter == 0 && !external_abort) return -1;
+  if (counter == 0 && abort_now) return 0;
+
+  if (h->cfg.use_tukey && d.n_meas > 0) {        // src/ChainBundle.cc:1368-1399
+    { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 1, s); }
+    { Prof p(h, C_OTHER); launch_tukey_flags(d, s); }
+    MCP_CUDA_CHECK(cudaMemcpyAsync(h->flags_host, d.outlier_flags, sizeof(int) * (size_t)d.n_meas, cudaMemcpyDeviceToHost, s));
+    MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int q = 0; q < d.n_meas; q++) if (h->flags_host[q]) h->outliers.push_back(h->meas_orig[q]);
+    std::sort(h->outliers.begin(), h->outliers.end());
+  }
+  if (st) { st->n_outliers = (int)h->outliers.size(); st->max_cov = 0; st->kernel_launches = h->launches; }
+  return counter;
+}
+
+static void resolve_profile(McpBa* h)
+{
+  memset(&h->timing, 0, sizeof(h->timing));
+  double* ms[C_N] = { &h->timing.ms_select, &h->timing.ms_linearize, &h->timing.ms_schur, &h->timing.ms_solve,
+                      &h->timing.ms_backsub, &h->timing.ms_control, &h->timing.ms_other };
+  int32_t* cnt[C_N] = { &h->timing.n_select, &h->timing.n_linearize, &h->timing.n_schur, &h->timing.n_solve,
+                        &h->timing.n_backsub, &h->timing.n_control, &h->timing.n_other };
+  for (auto& e : h->evs) {
+    float t = 0;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&t, e.a, e.b);
+    *ms[e.cat] += t; (*cnt[e.cat])++;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  h->evs.clear();
+}
+
+int mcp_ba_compute(McpBa* h, volatile const uint8_t* abort_flag, int32_t n_iter, double user_lambda, McpBaStats* stats)
+{
+  if (!h || !h->loaded) { set_last_error("mcp_ba_compute: no problem loaded"); return MCP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  McpBaStats local;
+  if (!stats) stats = &local;
+  memset(stats, 0, sizeof(*stats));
+  h->launches = 0;
+  const int rc = run_compute(h, abort_flag, n_iter, user_lambda, stats, false, 0, 0);
+  if (h->profiling) resolve_profile(h);
+  if (rc < -1) cudaStreamSynchronize(h->stream);
+  return rc;
+}
+
+int mcp_ba_lm_step(McpBa* h, double lambda, double sigma_sq, double* delta, double* sigma_sq_used, double* robust_chi2)
+{
+  if (!h || !h->loaded) { set_last_error("mcp_ba_lm_step: no problem loaded"); return MCP_ERR_STATE; }
+  if (h->world > 1) { set_last_error("mcp_ba_lm_step: single-GPU diagnostic only"); return MCP_ERR_UNSUPPORTED; }
+  cudaSetDevice(h->device);
+  McpBaStats st;
+  memset(&st, 0, sizeof(st));
+  const int cur_before = h->ctrl_host->cur;
+  int rc = run_compute(h, nullptr, 1, -1.0, &st, true, lambda, sigma_sq);
+  if (rc) return rc;
+  BaCtrl& c = *h->ctrl_host;
+  const size_t dim = (size_t)c.dim;
+  if ((rc = h->b_tmp.ensure(sizeof(double) * (dim + 1)))) return rc;
+  // the update belongs to the pre-step lambda: restore it for the gather
+  const double lam_after = c.lambda;
+  c.lambda = lambda; c.cur = cur_before;
+  if ((rc = push_ctrl(h))) return rc;
+  launch_gather_delta(h->d, h->b_tmp.as<double>(), h->stream);
+  if (delta) MCP_CUDA_CHECK(cudaMemcpyAsync(delta, h->b_tmp.p, sizeof(double) * dim, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  (void)lam_after;
+  if (sigma_sq_used) *sigma_sq_used = c.sigma_sq_raw;
+  if (robust_chi2) *robust_chi2 = c.lin_chi;
+  // leave the estimate untouched (cur restored) and reset the LM history
+  c.last_chi2 = 1.7976931348623157e308; c.qmax = 0; c.iter = 0;
+  if ((rc = push_ctrl(h))) return rc;
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+int mcp_ba_get_poses(McpBa* h, double* out)
+{
+  if (!h || !h->loaded || !out) { set_last_error("mcp_ba_get_poses: bad arguments"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, h->d.pose[h->ctrl_host->cur], sizeof(double) * 12 * (size_t)h->d.n_pose, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+int mcp_ba_get_points(McpBa* h, double* out)
+{
+  if (!h || !h->loaded || !out) { set_last_error("mcp_ba_get_points: bad arguments"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, h->d.pt[h->ctrl_host->cur], sizeof(double) * 3 * (size_t)h->d.n_pt, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+int mcp_ba_get_outliers(McpBa* h, int32_t* idx, int32_t cap)
+{
+  if (!h) { set_last_error("mcp_ba_get_outliers: NULL handle"); return MCP_ERR_INVALID; }
+  const int n = (int)h->outliers.size();
+  if (idx && cap > 0) memcpy(idx, h->outliers.data(), sizeof(int32_t) * (size_t)std::min(n, (int)cap));
+  return n;
+}
+int mcp_ba_set_state(McpBa* h, const double* pose_Rt, const double* pt_xyz)
+{
+  if (!h || !h->loaded) { set_last_error("mcp_ba_set_state: no problem loaded"); return MCP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  const int cur = h->ctrl_host->cur;
+  for (int k = 0; k < 2; k++) {
+    if (pose_Rt) MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pose[k], pose_Rt, sizeof(double) * 12 * (size_t)h->d.n_pose, cudaMemcpyHostToDevice, h->stream));
+    if (pt_xyz && (k == cur)) MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pt[k], pt_xyz, sizeof(double) * 3 * (size_t)h->d.n_pt, cudaMemcpyHostToDevice, h->stream));
+  }
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+int mcp_ba_reset_state(McpBa* h)
+{
+  if (!h || !h->loaded) { set_last_error("mcp_ba_reset_state: no problem loaded"); return MCP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  for (int k = 0; k < 2; k++) {
+    MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pose[k], h->b_pose0.p, sizeof(double) * 12 * (size_t)h->d.n_pose, cudaMemcpyDeviceToDevice, h->stream));
+    MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pt[k], h->b_pt0.p, sizeof(double) * 3 * (size_t)h->d.n_pt, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  BaCtrl& c = *h->ctrl_host;
+  int rc;
+  if ((rc = sync_ctrl(h))) return rc;
+  c.last_chi2 = 1.7976931348623157e308; c.cur = 0;
+  if ((rc = push_ctrl(h))) return rc;
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+int mcp_ba_eval(McpBa* h, double* err_xy, double* chi2)
+{
+  if (!h || !h->loaded) { set_last_error("mcp_ba_eval: no problem loaded"); return MCP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  int rc;
+  const size_t n = (size_t)h->d.n_meas;
+  if ((rc = h->b_tmp.ensure(sizeof(double) * (2 * n + 2)))) return rc;
+  if ((rc = sync_ctrl(h))) return rc;
+  launch_backsub_eval(h->d, 0, -1, h->b_tmp.as<double>(), h->stream);
+  if ((rc = allgather_ranges(h, h->d.chi2[h->ctrl_host->cur], h->part_meas, 1))) return rc;
+  if (err_xy) MCP_CUDA_CHECK(cudaMemcpyAsync(err_xy, h->b_tmp.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> sorted(n);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(sorted.data(), h->d.chi2[h->ctrl_host->cur], sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (chi2) for (size_t q = 0; q < n; q++) chi2[h->meas_orig[q]] = sorted[q];
+  return MCP_OK;
+}
+
+int mcp_ba_debug_jacobians(McpBa* h, double* J30)
+{
+  if (!h || !h->loaded || !J30) { set_last_error("mcp_ba_debug_jacobians: bad arguments"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  int rc;
+  const size_t n = (size_t)h->d.n_meas;
+  if ((rc = h->b_tmp.ensure(sizeof(double) * (30 * n + 2)))) return rc;
+  if ((rc = sync_ctrl(h))) return rc;
+  launch_debug_jacobians(h->d, h->b_tmp.as<double>(), h->stream);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(J30, h->b_tmp.p, sizeof(double) * 30 * n, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+int mcp_ba_set_profiling(McpBa* h, int32_t enable) { if (!h) return MCP_ERR_INVALID; h->profiling = enable != 0; return MCP_OK; }
+int mcp_ba_get_timing(McpBa* h, McpBaTiming* out) { if (!h || !out) return MCP_ERR_INVALID; *out = h->timing; return MCP_OK; }
+
+int mcp_nccl_unique_id(void* out128)
+{
+  if (!out128) return MCP_ERR_INVALID;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  NCCL_CHECK(ncclGetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return MCP_OK;
+}
+
+int mcp_ba_comm_init(McpBa* h, const void* nccl_unique_id, int32_t rank, int32_t world)
+{
+  if (!h || world < 1 || rank < 0 || rank >= world) { set_last_error("mcp_ba_comm_init: bad arguments"); return MCP_ERR_INVALID; }
+  if (h->loaded) { set_last_error("mcp_ba_comm_init: must be called before mcp_ba_load"); return MCP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+  h->rank = rank; h->world = world;
+  if (world == 1) return MCP_OK;
+  if (!nccl_unique_id) { set_last_error("mcp_ba_comm_init: unique id required for world > 1"); return MCP_ERR_INVALID; }
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id, sizeof(id));
+  NCCL_CHECK(ncclCommInitRank(&h->comm, world, id, rank));
+  return MCP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1052 @@
+// ba_kernels.cu — sm_100a kernels of the ChainBundle LM bundle adjuster.
+//
+//   k_linearize<SCHUR>  one warp per map point: per-measurement TaylorCamera reprojection, 2x6 / 2x3
+//                       Jacobians (reference src/ChainBundle.cc:376-397, 449-685), robust weights
+//                       (:871-897), per-point 3x3 / 6x3 blocks in shared memory, pose-pose blocks and the
+//                       per-point Schur complement accumulated into the dense reduced camera system.
+//   k_schur_only        re-does only the Schur reduction for a new lambda (LM re-trial).
+//   k_select_sigma      exact upper median of |chi2| (radix select) -> Huber / Tukey sigma^2
+//                       (include/mcptam/MEstimator.h:109-126,194-204; src/ChainBundle.cc:810-833).
+//   k_lambda_init       g2o computeLambdaInit: 1e-5 * max diagonal.
+//   k_solve             dense Cholesky of the damped reduced camera system + pose update (:82-86).
+//   k_backsub_eval      per point back-substitution, VertexRelPoint::oplusImpl (:237-281) and the trial
+//                       error evaluation.
+//   k_lm_control        accept / reject, lambda schedule, convergence actions (:1009-1118).
+#include "ba_types.cuh"
+
+namespace mcp {
+
+// ---------------------------------------------------------------------------------------------
+// shared device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void robustify(const BaCtrl* __restrict__ c, double e2, double& rho0, double& rho1)
+{
+  if (!c->use_robust) { rho0 = e2; rho1 = 1.0; return; }
+  if (e2 <= c->sigma_sq_lim) { rho0 = fabs(e2); rho1 = 1.0; }
+  else { const double e = sqrt(e2); rho0 = 2 * c->sigma_lim * e - c->sigma_sq_lim; rho1 = c->sigma_lim / e; }
+}
+
+struct PtCtx {
+  Se3 Bs;          // source MKF pose (base from world)
+  double RCcs[9];  // rotation of the source cam-from-base link (identity for 1-link chains)
+  double pw[3];    // point in world frame
+  double qs[3];    // point in the source MKF frame
+  double prel[3];  // point in the source camera frame (the estimate)
+};
+
+__device__ __forceinline__ void load_pt_ctx(const BaDev& d, const double* __restrict__ pose, const int4 pi,
+                                            const double* prel, PtCtx& c)
+{
+  se3_load(pose + 12 * (size_t)pi.x, c.Bs);
+  c.prel[0] = prel[0]; c.prel[1] = prel[1]; c.prel[2] = prel[2];
+  if (pi.y >= 0) {
+    Se3 C;
+    se3_load(pose + 12 * (size_t)pi.y, C);
+#pragma unroll
+    for (int i = 0; i < 9; i++) c.RCcs[i] = C.R[i];
+    se3_apply_inv(C, prel, c.qs);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; i++) c.RCcs[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    c.qs[0] = prel[0]; c.qs[1] = prel[1]; c.qs[2] = prel[2];
+  }
+  se3_apply_inv(c.Bs, c.qs, c.pw);
+}
+
+// Tangent basis of VertexRelPoint (src/ChainBundle.cc:595-620): columns are the camera-frame motion of the
+// point for d_beta, d_alpha, d_rho.  M row-major 3x3.
+__device__ __forceinline__ void point_tangent(const double* p, double* M)
+{
+  const double len = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const double rho = 1.0 / len;
+  const double dir[3] = { p[0] * rho, p[1] * rho, p[2] * rho };
+  double axis[3] = { dir[1], -dir[0], 0.0 };   // dir ^ (0,0,1)
+  const double an = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  const double angle = asin(an);
+  axis[0] = axis[0] / an * angle; axis[1] = axis[1] / an * angle; axis[2] = axis[2] / an * angle;
+  double Rp[9];
+  so3_exp(axis, Rp);
+  double rpp[3];
+  m3_vec(Rp, p, rpp);
+  const double g0[3] = { 0.0, -rpp[2], rpp[1] };   // SO3 generator 0 on Rp*p
+  const double g1[3] = { rpp[2], 0.0, -rpp[0] };   // generator 1
+  double c0[3], c1[3];
+  m3t_vec(Rp, g0, c0);
+  m3t_vec(Rp, g1, c1);
+#pragma unroll
+  for (int r = 0; r < 3; r++) { M[r * 3 + 0] = c0[r]; M[r * 3 + 1] = c1[r]; M[r * 3 + 2] = -1 * p[r] / rho; }
+}
+
+// VertexRelPoint::oplusImpl (src/ChainBundle.cc:237-281)
+__device__ __forceinline__ void point_oplus(const double* est, const double* upd, double* out)
+{
+  const double dist_before = sqrt(est[0] * est[0] + est[1] * est[1] + est[2] * est[2]);
+  const double rho_before = 1.0 / dist_before;
+  const double dir[3] = { est[0] * rho_before, est[1] * rho_before, est[2] * rho_before };
+  double axis[3] = { dir[1], -dir[0], 0.0 };
+  const double an = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  const double angle = asin(an);
+  axis[0] = axis[0] / an * angle; axis[1] = axis[1] / an * angle; axis[2] = axis[2] / an * angle;
+  double Rp[9], Ru[9], M1[9], M2[9], RpT[9];
+  so3_exp(axis, Rp);
+  const double w[3] = { upd[0], upd[1], 0.0 };
+  so3_exp(w, Ru);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) RpT[i * 3 + j] = Rp[j * 3 + i];
+  m3_mul(RpT, Ru, M1);
+  m3_mul(M1, Rp, M2);
+  double c[3];
+  m3_vec(M2, dir, c);
+  const double s = 1 / (rho_before + upd[2]);
+  out[0] = s * c[0]; out[1] = s * c[1]; out[2] = s * c[2];
+  const double dist_after = sqrt(out[0] * out[0] + out[1] * out[1] + out[2] * out[2]);
+  if (dist_after > 1e5) { const double f = 1e5 / dist_after; out[0] *= f; out[1] *= f; out[2] *= f; }
+  if (dist_after < 1e-5) { const double f = 1e-5 / dist_after; out[0] *= f; out[1] *= f; out[2] *= f; }
+}
+
+// Per-measurement geometry: residual and the three 2x3 pixel-motion maps
+//   A  : motion in the observing MKF frame  -> pixel     (J_obs = -A  * Gamma(q))
+//   A2 : motion in the source MKF frame     -> pixel     (J_src = +A2 * Gamma(qs))
+//   A3 : motion in the source camera frame  -> pixel     (J_pt  = -A3 * M)
+struct MeasGeom {
+  double e[2];
+  double q[3];
+  double A[6], A2[6], A3[6];
+};
+
+template <bool WITH_JAC>
+__device__ __forceinline__ void meas_geometry(const BaDev& d, const double* __restrict__ pose, const PtCtx& c,
+                                              const int4 ma, const double2 z, MeasGeom& g)
+{
+  Se3 Bm;
+  se3_load(pose + 12 * (size_t)ma.x, Bm);
+  se3_apply(Bm, c.pw, g.q);
+  double v[3];
+  double RC[9];
+  if (ma.y >= 0) {
+    Se3 C;
+    se3_load(pose + 12 * (size_t)ma.y, C);
+    se3_apply(C, g.q, v);
+#pragma unroll
+    for (int i = 0; i < 9; i++) RC[i] = C.R[i];
+  } else {
+    v[0] = g.q[0]; v[1] = g.q[1]; v[2] = g.q[2];
+#pragma unroll
+    for (int i = 0; i < 9; i++) RC[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  double px[2], G[6];
+  cam_project(d.cams[ma.z], v, px, WITH_JAC ? G : nullptr);
+  g.e[0] = z.x - px[0];
+  g.e[1] = z.y - px[1];
+  if (WITH_JAC) {
+    // A = G * RC
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) g.A[r * 3 + k] = G[r * 3] * RC[k] + G[r * 3 + 1] * RC[3 + k] + G[r * 3 + 2] * RC[6 + k];
+    // T = A * R_Bm ; A2 = T * R_Bs^T ; A3 = A2 * R_Ccs^T
+    double T[6];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) T[r * 3 + k] = g.A[r * 3] * Bm.R[k] + g.A[r * 3 + 1] * Bm.R[3 + k] + g.A[r * 3 + 2] * Bm.R[6 + k];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) g.A2[r * 3 + k] = T[r * 3] * c.Bs.R[k * 3] + T[r * 3 + 1] * c.Bs.R[k * 3 + 1] + T[r * 3 + 2] * c.Bs.R[k * 3 + 2];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) g.A3[r * 3 + k] = g.A2[r * 3] * c.RCcs[k * 3] + g.A2[r * 3 + 1] * c.RCcs[k * 3 + 1] + g.A2[r * 3 + 2] * c.RCcs[k * 3 + 2];
+  }
+}
+
+// J (2x6, row-major) = sign * A * Gamma(q),  Gamma(q) = [ I3 | e_k x q ]  (TooN SE3 generator field)
+__device__ __forceinline__ void pose_jac(const double* A, const double* q, double sign, double* J)
+{
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const double a0 = A[r * 3], a1 = A[r * 3 + 1], a2 = A[r * 3 + 2];
+    J[r * 6 + 0] = sign * a0;
+    J[r * 6 + 1] = sign * a1;
+    J[r * 6 + 2] = sign * a2;
+    J[r * 6 + 3] = sign * (-a1 * q[2] + a2 * q[1]);
+    J[r * 6 + 4] = sign * (a0 * q[2] - a2 * q[0]);
+    J[r * 6 + 5] = sign * (-a0 * q[1] + a1 * q[0]);
+  }
+}
+
+__device__ __forceinline__ bool inv3_sym(const double* V6, double lambda, double* Vi)
+{
+  // V6 = {v00, v01, v02, v11, v12, v22}; returns inverse (full 3x3 row-major) of V + lambda I
+  const double a = V6[0] + lambda, b = V6[1], c = V6[2], dd = V6[3] + lambda, e = V6[4], f = V6[5] + lambda;
+  const double c00 = dd * f - e * e, c01 = c * e - b * f, c02 = b * e - c * dd;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double id = 1.0 / det;
+  Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id;
+  Vi[3] = Vi[1]; Vi[4] = (a * f - c * c) * id; Vi[5] = (b * c - a * e) * id;
+  Vi[6] = Vi[2]; Vi[7] = Vi[5]; Vi[8] = (a * dd - b * b) * id;
+  // SPD check (leading minors) – a failed point makes the whole solve fail, as CHOLMOD would.
+  return (a > 0) && (a * dd - b * b > 0) && (det > 0) && isfinite(id);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red /*>= 32 doubles of smem*/)
+{
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0;
+  if (wid == 0) {
+    r = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schur reduction of one point (warp-cooperative).  Wsm/Ysm: K x 18 doubles in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool schur_point(const BaDev& d, int lane, int K, const int* __restrict__ svar,
+                                            const double* V6, const double* gp, double lambda, double* Wsm, double* Ysm)
+{
+  double Vi[9];
+  const bool ok = inv3_sym(V6, lambda, Vi);
+  for (int i = lane; i < K * 18; i += 32) {
+    const int a6 = i / 3, c = i - a6 * 3;
+    const double* w = Wsm + a6 * 3;
+    Ysm[i] = w[0] * Vi[c] + w[1] * Vi[3 + c] + w[2] * Vi[6 + c];
+  }
+  __syncwarp();
+  const int nc = d.nc;
+  for (int i = lane; i < K * 6; i += 32) {
+    const int a = i / 6, r = i - a * 6;
+    const double* y = Ysm + i * 3;
+    atomicAdd(d.rm + 6 * svar[a] + r, y[0] * gp[0] + y[1] * gp[1] + y[2] * gp[2]);
+  }
+  for (int a = 0; a < K; a++) {
+    const int va = svar[a];
+    const double* Ya = Ysm + a * 18;
+    const int n = (K - a) * 36;
+    for (int i = lane; i < n; i += 32) {
+      const int bo = i / 36, rc = i - bo * 36;
+      const int r = rc / 6, c = rc - r * 6;
+      if (bo == 0 && c < r) continue;               // diagonal block: upper triangle only
+      const double* y = Ya + r * 3;
+      const double* w = Wsm + (a + bo) * 18 + c * 3;
+      atomicAdd(d.Sm + (size_t)(6 * va + r) * nc + 6 * svar[a + bo] + c, y[0] * w[0] + y[1] * w[1] + y[2] * w[2]);
+    }
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_linearize
+// ---------------------------------------------------------------------------------------------
+template <bool DO_SCHUR>
+__global__ void __launch_bounds__(256) k_linearize(BaDev d)
+{
+  extern __shared__ double smem[];
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* Wsm = smem + (size_t)wid * d.max_slots * 36;
+  double* Ysm = Wsm + (size_t)d.max_slots * 18;
+  const BaCtrl* ctrl = d.ctrl;
+  const int cur = ctrl->cur;
+  const double* __restrict__ pose = d.pose[cur];
+  const double* __restrict__ ptv = d.pt[cur];
+  const double lambda = ctrl->lambda;
+  const int nc = d.nc;
+  double chi_acc = 0.0;
+  int fail = 0;
+
+  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
+    const int4 pi = d.pt_info[p];
+    const int pvar = d.pt_var[p];
+    const double prel[3] = { ptv[3 * (size_t)p], ptv[3 * (size_t)p + 1], ptv[3 * (size_t)p + 2] };
+    PtCtx c;
+    load_pt_ctx(d, pose, pi, prel, c);
+    double M[9];
+    point_tangent(prel, M);
+    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+    const int* __restrict__ svar = d.slot_var + s0;
+    for (int i = lane; i < K * 18; i += 32) Wsm[i] = 0.0;
+    __syncwarp();
+
+    // sums over the measurements of this point
+    double P3[6] = { 0, 0, 0, 0, 0, 0 }, t3[3] = { 0, 0, 0 };
+    double Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 }, P2[6] = { 0, 0, 0, 0, 0, 0 }, t2[3] = { 0, 0, 0 };
+    const int m0 = d.pt_meas_off[p], m1 = d.pt_meas_off[p + 1];
+    for (int mb = m0; mb < m1; mb += 32) {
+      const int m = mb + lane;
+      if (m < m1) {
+        const int4 ma = d.meas_a[m];
+        const int4 mbi = d.meas_b[m];
+        const double2 z = d.meas_xy[m];
+        const double info = d.meas_info[m];
+        MeasGeom g;
+        meas_geometry<true>(d, pose, c, ma, z, g);
+        double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
+        if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;             // src/ChainBundle.cc:413-414
+        double rho0, rho1;
+        robustify(ctrl, chi2, rho0, rho1);
+        chi_acc += rho0;
+        const double w = rho1 * info;
+        const double we0 = w * g.e[0], we1 = w * g.e[1];
+        if (pvar >= 0) {
+          // P3 += w A3^T A3 ; t3 += w A3^T e
+          P3[0] += w * (g.A3[0] * g.A3[0] + g.A3[3] * g.A3[3]);
+          P3[1] += w * (g.A3[0] * g.A3[1] + g.A3[3] * g.A3[4]);
+          P3[2] += w * (g.A3[0] * g.A3[2] + g.A3[3] * g.A3[5]);
+          P3[3] += w * (g.A3[1] * g.A3[1] + g.A3[4] * g.A3[4]);
+          P3[4] += w * (g.A3[1] * g.A3[2] + g.A3[4] * g.A3[5]);
+          P3[5] += w * (g.A3[2] * g.A3[2] + g.A3[5] * g.A3[5]);
+#pragma unroll
+          for (int k = 0; k < 3; k++) t3[k] += g.A3[k] * we0 + g.A3[3 + k] * we1;
+        }
+        const bool has_src = mbi.z != 0;
+        if (has_src) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            t2[r] += g.A2[r] * we0 + g.A2[3 + r] * we1;
+            if (pvar >= 0) {
+#pragma unroll
+              for (int k = 0; k < 3; k++) Q[r * 3 + k] += w * (g.A2[r] * g.A3[k] + g.A2[3 + r] * g.A3[3 + k]);
+            }
+          }
+          P2[0] += w * (g.A2[0] * g.A2[0] + g.A2[3] * g.A2[3]);
+          P2[1] += w * (g.A2[0] * g.A2[1] + g.A2[3] * g.A2[4]);
+          P2[2] += w * (g.A2[0] * g.A2[2] + g.A2[3] * g.A2[5]);
+          P2[3] += w * (g.A2[1] * g.A2[1] + g.A2[4] * g.A2[4]);
+          P2[4] += w * (g.A2[1] * g.A2[2] + g.A2[4] * g.A2[5]);
+          P2[5] += w * (g.A2[2] * g.A2[2] + g.A2[5] * g.A2[5]);
+        }
+        const int vo = mbi.x;
+        if (vo >= 0) {
+          double Jo[12];
+          pose_jac(g.A, g.q, -1.0, Jo);
+          // H0[vo,vo] upper triangle, gc[vo]
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            atomicAdd(d.gc + 6 * vo + r, -(Jo[r] * we0 + Jo[6 + r] * we1));
+#pragma unroll
+            for (int cc = r; cc < 6; cc++)
+              atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vo + cc, w * (Jo[r] * Jo[cc] + Jo[6 + r] * Jo[6 + cc]));
+          }
+          if (pvar >= 0) {
+            // J_pt = -A3 * M ; W_obs = w Jo^T J_pt
+            double Jp[6];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+              for (int k = 0; k < 3; k++) Jp[r * 3 + k] = -(g.A3[r * 3] * M[k] + g.A3[r * 3 + 1] * M[3 + k] + g.A3[r * 3 + 2] * M[6 + k]);
+            double* Wo = Wsm + mbi.y * 18;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+              for (int k = 0; k < 3; k++) atomicAdd(Wo + r * 3 + k, w * (Jo[r] * Jp[k] + Jo[6 + r] * Jp[3 + k]));
+          }
+          if (has_src) {
+            double Js[12];
+            pose_jac(g.A2, c.qs, 1.0, Js);
+            const int vs = pi.z;
+            if (vo < vs) {
+#pragma unroll
+              for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++)
+                  atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vs + cc, w * (Jo[r] * Js[cc] + Jo[6 + r] * Js[6 + cc]));
+            } else {
+#pragma unroll
+              for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++)
+                  atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vo + cc, w * (Js[r] * Jo[cc] + Js[6 + r] * Jo[6 + cc]));
+            }
+          }
+        }
+      }
+    }
+    // warp-reduce the point sums (every lane ends up with the totals)
+#pragma unroll
+    for (int i = 0; i < 6; i++) { P3[i] = warp_sum(P3[i]); P2[i] = warp_sum(P2[i]); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { t3[i] = warp_sum(t3[i]); t2[i] = warp_sum(t2[i]); }
+#pragma unroll
+    for (int i = 0; i < 9; i++) Q[i] = warp_sum(Q[i]);
+
+    // point block: V = M^T P3 M, gp = M^T t3   (J_pt = -A3 M, b_p = -sum w J_pt^T e)
+    double V6[6] = { 0, 0, 0, 0, 0, 0 }, gp[3] = { 0, 0, 0 };
+    if (pvar >= 0) {
+      const double P[9] = { P3[0], P3[1], P3[2], P3[1], P3[3], P3[4], P3[2], P3[4], P3[5] };
+      double PM[9];
+      m3_mul(P, M, PM);
+      V6[0] = M[0] * PM[0] + M[3] * PM[3] + M[6] * PM[6];
+      V6[1] = M[0] * PM[1] + M[3] * PM[4] + M[6] * PM[7];
+      V6[2] = M[0] * PM[2] + M[3] * PM[5] + M[6] * PM[8];
+      V6[3] = M[1] * PM[1] + M[4] * PM[4] + M[7] * PM[7];
+      V6[4] = M[1] * PM[2] + M[4] * PM[5] + M[7] * PM[8];
+      V6[5] = M[2] * PM[2] + M[5] * PM[5] + M[8] * PM[8];
+      m3t_vec(M, t3, gp);
+    }
+    // source-pose blocks: U_ss = Gs^T P2 Gs, g_s = -Gs^T t2, W_src = -Gs^T (Q M)
+    const int vs = pi.z;
+    const bool any_src = (P2[0] != 0.0) || (P2[3] != 0.0) || (P2[5] != 0.0);
+    if (vs >= 0 && any_src) {
+      // Gs (3x6) = [I | o_k(qs)], o_0=(0,-q2,q1) o_1=(q2,0,-q0) o_2=(-q1,q0,0)
+      const double q0 = c.qs[0], q1 = c.qs[1], q2 = c.qs[2];
+      const double Gs[18] = { 1, 0, 0, 0, q2, -q1, 0, 1, 0, -q2, 0, q0, 0, 0, 1, q1, -q0, 0 };
+      const double P[9] = { P2[0], P2[1], P2[2], P2[1], P2[3], P2[4], P2[2], P2[4], P2[5] };
+      if (lane < 21) {
+        // upper-triangle entry (r,cc) of the 6x6
+        int r = 0, k = lane;
+        while (k >= 6 - r) { k -= 6 - r; r++; }
+        const int cc = r + k;
+        double acc = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) acc += Gs[i * 6 + r] * P[i * 3 + j] * Gs[j * 6 + cc];
+        atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vs + cc, acc);
+      } else if (lane < 27) {
+        const int r = lane - 21;
+        atomicAdd(d.gc + 6 * vs + r, -(Gs[r] * t2[0] + Gs[6 + r] * t2[1] + Gs[12 + r] * t2[2]));
+      }
+      __syncwarp();
+      if (pvar >= 0 && pi.w >= 0 && lane < 18) {
+        double X[9];
+        m3_mul(Q, M, X);
+        const int r = lane / 3, k = lane - r * 3;
+        Wsm[pi.w * 18 + lane] += -(Gs[r] * X[k] + Gs[6 + r] * X[3 + k] + Gs[12 + r] * X[6 + k]);
+      }
+    }
+    __syncwarp();
+    if (pvar >= 0) {
+      double* Wg = d.W + (size_t)s0 * 18;
+      for (int i = lane; i < K * 18; i += 32) Wg[i] = Wsm[i];
+      if (lane < 6) d.V[6 * (size_t)p + lane] = V6[lane];
+      if (lane < 3) d.gp[3 * (size_t)p + lane] = gp[lane];
+      if (DO_SCHUR) {
+        if (!schur_point(d, lane, K, svar, V6, gp, lambda, Wsm, Ysm)) fail = 1;
+      }
+    }
+    __syncwarp();
+  }
+  const double tot = block_sum(chi_acc, red);
+  if (threadIdx.x == 0) d.part[PART_CUR_CHI * MAX_PARTIALS + blockIdx.x] = tot;
+  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+}
+
+__global__ void __launch_bounds__(256) k_schur_only(BaDev d)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* Wsm = smem + (size_t)wid * d.max_slots * 36;
+  double* Ysm = Wsm + (size_t)d.max_slots * 18;
+  const double lambda = d.ctrl->lambda;
+  int fail = 0;
+  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
+    if (d.pt_var[p] < 0) continue;
+    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+    const double* Wg = d.W + (size_t)s0 * 18;
+    for (int i = lane; i < K * 18; i += 32) Wsm[i] = Wg[i];
+    double V6[6], gp[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
+    __syncwarp();
+    if (!schur_point(d, lane, K, d.slot_var + s0, V6, gp, lambda, Wsm, Ysm)) fail = 1;
+    __syncwarp();
+  }
+  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_backsub_eval: apply==1: point back-substitution + oplus into the trial buffers, then error eval of
+// the trial state.  apply==0: error eval of state `which` only.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int which_in, double* err_out)
+{
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const BaCtrl* ctrl = d.ctrl;
+  const int cur = ctrl->cur;
+  const int dst = apply ? (cur ^ 1) : (which_in < 0 ? cur : which_in);
+  const double* __restrict__ pose = d.pose[dst];
+  const double lambda = ctrl->lambda;
+  double chi_acc = 0, scale_acc = 0, sumsq_acc = 0;
+  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
+    const int4 pi = d.pt_info[p];
+    const int pvar = d.pt_var[p];
+    double pnew[3];
+    if (apply) {
+      const double* pold = d.pt[cur] + 3 * (size_t)p;
+      const double po[3] = { pold[0], pold[1], pold[2] };
+      if (pvar >= 0) {
+        const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+        const double* Wg = d.W + (size_t)s0 * 18;
+        const int* svar = d.slot_var + s0;
+        double t[3] = { 0, 0, 0 };
+        for (int i = lane; i < K * 18; i += 32) {
+          const int a = i / 18, rem = i - a * 18, r = rem / 3, k = rem - r * 3;
+          const double v = Wg[i] * d.dc[6 * svar[a] + r];
+          t[0] += (k == 0) ? v : 0.0; t[1] += (k == 1) ? v : 0.0; t[2] += (k == 2) ? v : 0.0;
+        }
+        t[0] = warp_sum(t[0]); t[1] = warp_sum(t[1]); t[2] = warp_sum(t[2]);
+        double V6[6], gp[3], Vi[9];
+#pragma unroll
+        for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
+        inv3_sym(V6, lambda, Vi);
+        const double rr[3] = { gp[0] - t[0], gp[1] - t[1], gp[2] - t[2] };
+        double dp[3];
+        m3_vec(Vi, rr, dp);
+        if (!ctrl->solve_ok) { dp[0] = dp[1] = dp[2] = 0.0; }
+        point_oplus(po, dp, pnew);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            scale_acc += dp[i] * (lambda * dp[i] + gp[i]);
+            sumsq_acc += dp[i] * dp[i];
+          }
+        }
+      } else { pnew[0] = po[0]; pnew[1] = po[1]; pnew[2] = po[2]; }
+      if (lane < 3) d.pt[dst][3 * (size_t)p + lane] = pnew[lane];
+    } else {
+      const double* pp = d.pt[dst] + 3 * (size_t)p;
+      pnew[0] = pp[0]; pnew[1] = pp[1]; pnew[2] = pp[2];
+    }
+    PtCtx c;
+    load_pt_ctx(d, pose, pi, pnew, c);
+    const int m0 = d.pt_meas_off[p], m1 = d.pt_meas_off[p + 1];
+    for (int m = m0 + lane; m < m1; m += 32) {
+      const int4 ma = d.meas_a[m];
+      MeasGeom g;
+      meas_geometry<false>(d, pose, c, ma, d.meas_xy[m], g);
+      double chi2 = d.meas_info[m] * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
+      if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;
+      d.chi2[dst][m] = chi2;
+      if (err_out) { err_out[2 * (size_t)ma.w] = g.e[0]; err_out[2 * (size_t)ma.w + 1] = g.e[1]; }
+      double rho0, rho1;
+      robustify(ctrl, chi2, rho0, rho1);
+      chi_acc += rho0;
+    }
+  }
+  const double a = block_sum(chi_acc, red);
+  const double b = block_sum(scale_acc, red);
+  const double c2 = block_sum(sumsq_acc, red);
+  if (threadIdx.x == 0) {
+    d.part[PART_TMP_CHI * MAX_PARTIALS + blockIdx.x] = a;
+    d.part[PART_SCALE * MAX_PARTIALS + blockIdx.x] = b;
+    d.part[PART_SUMSQ * MAX_PARTIALS + blockIdx.x] = c2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_select_sigma: exact element [n/2] of sorted |chi2| by MSB-first radix select, one block.
+// mode 0: Huber sigma (RecomputeNow), mode 1: Tukey sigma (outlier pass).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_select_sigma(BaDev d, int which_in, int mode)
+{
+  __shared__ unsigned hist[SEL_BINS];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank;
+  BaCtrl* ctrl = d.ctrl;
+  const int which = which_in < 0 ? ctrl->cur : which_in;
+  const double* __restrict__ v = d.chi2[which];
+  const int n = d.n_meas;
+  if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = (unsigned)(n / 2); }
+  // key = bits of |chi2| with the sign bit dropped -> 63 significant bits, digits taken MSB first
+  for (int pass = 0; pass < SEL_PASSES; pass++) {
+    const int shift = 63 - SEL_BITS * (pass + 1);        // 52, 41, 30, 19, 8, -3
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      bool match = false;
+      unsigned dig = 0;
+      if (i < n) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v[i]));
+        unsigned long long hi;
+        if (shift >= 0) { hi = key >> (shift + SEL_BITS); dig = (unsigned)(key >> shift) & (SEL_BINS - 1); }
+        else { hi = key >> (SEL_BITS + shift); dig = (unsigned)(key << (-shift)) & (SEL_BINS - 1); }
+        match = (pass == 0) || (hi == prefix);
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, match);
+      if (match) {
+        const unsigned peers = __match_any_sync(act, dig);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[dig], (unsigned)__popc(peers));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned r = s_rank, acc = 0; int b = 0;
+      for (b = 0; b < SEL_BINS; b++) { if (acc + hist[b] > r) break; acc += hist[b]; }
+      if (b >= SEL_BINS) b = SEL_BINS - 1;
+      s_rank = r - acc;
+      s_prefix = (shift >= 0) ? ((prefix << SEL_BITS) | (unsigned)b) : ((prefix << (SEL_BITS + shift)) | ((unsigned)b >> (-shift)));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double med = __longlong_as_double((long long)s_prefix);
+    const size_t denom = (size_t)n * 2 - 6;                       // size_t arithmetic as in the reference
+    double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
+    if (mode == 0) {
+      s = 1.345 * s;
+      ctrl->sigma_sq_raw = s * s;
+      ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
+      ctrl->sigma_lim = sqrt(ctrl->sigma_sq_lim);
+    } else {
+      s = 4.6851 * s;
+      double t = s * s;
+      if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq;
+      ctrl->tukey_sigma_sq = t;
+    }
+  }
+}
+
+// Tukey outlier flags (src/ChainBundle.cc:1385-1398)
+__global__ void k_tukey_flags(BaDev d)
+{
+  const double ts = d.ctrl->tukey_sigma_sq;
+  const double* __restrict__ v = d.chi2[d.ctrl->cur];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < d.n_meas; m += gridDim.x * blockDim.x) {
+    const double a = fabs(v[m]);
+    const double sq = a > ts ? 0.0 : 1.0 - (a / ts);
+    d.outlier_flags[m] = (sq * sq == 0.0) ? 1 : 0;
+  }
+}
+
+// g2o computeLambdaInit: tau * max |H_jj| over poses (H0 diagonal) and points (V diagonal)
+__global__ void __launch_bounds__(1024) k_lambda_init(BaDev d)
+{
+  __shared__ double red[32];
+  double mx = 0;
+  for (int i = threadIdx.x; i < d.nc; i += blockDim.x) mx = fmax(mx, fabs(d.H0[(size_t)i * d.nc + i]));
+  for (int p = d.p_lo + threadIdx.x; p < d.p_hi; p += blockDim.x) {
+    if (d.pt_var[p] < 0) continue;
+    const double* V = d.V + 6 * (size_t)p;
+    mx = fmax(mx, fmax(fabs(V[0]), fmax(fabs(V[3]), fabs(V[5]))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) mx = fmax(mx, red[i]);
+    d.part[PART_MAXDIAG * MAX_PARTIALS] = mx;
+  }
+}
+__global__ void k_lambda_apply(BaDev d)
+{
+  BaCtrl* c = d.ctrl;
+  if (c->need_lambda_init) {
+    c->max_diag = d.part[PART_MAXDIAG * MAX_PARTIALS];
+    c->lambda = c->user_lambda > 0 ? c->user_lambda : 1e-5 * c->max_diag;
+    c->ni = 2;
+    c->need_lambda_init = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_solve: single CTA blocked Cholesky of A = H0 + lambda I - Sm (upper triangles), solve, pose update.
+// ---------------------------------------------------------------------------------------------
+constexpr int NB = 32;
+
+__global__ void __launch_bounds__(1024) k_solve(BaDev d)
+{
+  extern __shared__ double sm[];          // panel [rows][NB+1] + tile [NB][NB+1] + vec
+  __shared__ int s_ok;
+  __shared__ double red[32];
+  BaCtrl* ctrl = d.ctrl;
+  const int n = d.nc;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const double lambda = ctrl->lambda;
+  double* L = d.L;
+  if (tid == 0) s_ok = ctrl->solve_ok;
+  // assemble lower triangle (row-major): L[i][j] = H0u[j][i] - Smu[j][i] (+lambda on the diagonal)
+  for (size_t idx = tid; idx < (size_t)n * n; idx += blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx - (size_t)i * n);
+    if (j <= i) {
+      double v = d.H0[(size_t)j * n + i] - d.Sm[(size_t)j * n + i];
+      if (i == j) v += lambda;
+      L[idx] = v;
+    }
+  }
+  __syncthreads();
+  double* panel = sm;                               // [(n - k0)][NB+1]
+  const int PLD = NB + 1;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int kb = min(NB, n - k0);
+    const int rows = n - k0;
+    double* tile = panel + (size_t)rows * PLD;      // [NB][NB+1]
+    // load panel
+    for (int idx = tid; idx < rows * kb; idx += blockDim.x) {
+      const int r = idx / kb, cc = idx - r * kb;
+      panel[r * PLD + cc] = (cc <= r || r >= kb) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
+    }
+    __syncthreads();
+    // panel -= L[k0+r][0:k0] * L[k0+c][0:k0]^T, processed in K-chunks of NB staged through `tile`
+    for (int kc = 0; kc < k0; kc += NB) {
+      for (int idx = tid; idx < kb * NB; idx += blockDim.x) {
+        const int r = idx / NB, cc = idx - r * NB;
+        tile[r * PLD + cc] = L[(size_t)(k0 + r) * n + kc + cc];
+      }
+      __syncthreads();
+      for (int r = wid; r < rows; r += nw) {
+        const double lv = L[(size_t)(k0 + r) * n + kc + lane];
+        if (lane < kb) {
+          double acc = 0;
+#pragma unroll 8
+          for (int k = 0; k < NB; k++) acc += __shfl_sync(0xffffffffu, lv, k) * tile[lane * PLD + k];
+          panel[r * PLD + lane] -= acc;
+        } else {
+#pragma unroll 8
+          for (int k = 0; k < NB; k++) (void)__shfl_sync(0xffffffffu, lv, k);
+        }
+      }
+      __syncthreads();
+    }
+    // factor the kb x kb diagonal block (warp 0, lane = row)
+    if (wid == 0) {
+      for (int j = 0; j < kb; j++) {
+        double djj = panel[j * PLD + j];
+        if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_ok = 0; djj = 1.0; }
+        const double dj = sqrt(djj);
+        __syncwarp();
+        if (lane == j) panel[j * PLD + j] = dj;
+        if (lane > j && lane < kb) panel[lane * PLD + j] /= dj;
+        __syncwarp();
+        if (lane > j && lane < kb) {
+          const double lij = panel[lane * PLD + j];
+          for (int k = j + 1; k <= lane; k++) panel[lane * PLD + k] -= lij * panel[k * PLD + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // triangular solve of the rows below: x * Ldd^T = row
+    for (int r = kb + tid; r < rows; r += blockDim.x) {
+      double* row = panel + r * PLD;
+      for (int j = 0; j < kb; j++) {
+        double s = row[j];
+        for (int k = 0; k < j; k++) s -= row[k] * panel[j * PLD + k];
+        row[j] = s / panel[j * PLD + j];
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rows * kb; idx += blockDim.x) {
+      const int r = idx / kb, cc = idx - r * kb;
+      if (cc <= r || r >= kb) L[(size_t)(k0 + r) * n + k0 + cc] = panel[r * PLD + cc];
+    }
+    __syncthreads();
+  }
+  // solve L L^T x = gc - rm, blocked: 32x32 diagonal solves by warp 0, rectangular updates by all threads
+  double* x = sm;
+  double* Ld = sm + n;                                  // [NB][NB+1]
+  for (int i = tid; i < n; i += blockDim.x) x[i] = d.gc[i] - d.rm[i];
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += NB) {                  // forward: L y = b
+    const int kb = min(NB, n - k0);
+    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
+      const int r = idx / kb, cc = idx - r * kb;
+      Ld[r * PLD + cc] = (cc <= r) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      double xi = lane < kb ? x[k0 + lane] : 0.0;
+      for (int j = 0; j < kb; j++) {
+        if (lane == j) xi /= Ld[j * PLD + j];
+        const double yj = __shfl_sync(0xffffffffu, xi, j);
+        if (lane > j && lane < kb) xi -= Ld[lane * PLD + j] * yj;
+      }
+      if (lane < kb) x[k0 + lane] = xi;
+    }
+    __syncthreads();
+    for (int i = k0 + kb + tid; i < n; i += blockDim.x) {
+      const double* Li = L + (size_t)i * n + k0;
+      double s2 = 0;
+      for (int j = 0; j < kb; j++) s2 += Li[j] * x[k0 + j];
+      x[i] -= s2;
+    }
+    __syncthreads();
+  }
+  for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {   // backward: L^T x = y
+    const int kb = min(NB, n - k0);
+    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
+      const int r = idx / kb, cc = idx - r * kb;
+      Ld[r * PLD + cc] = (cc <= r) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      double xi = lane < kb ? x[k0 + lane] : 0.0;
+      for (int j = kb - 1; j >= 0; j--) {
+        if (lane == j) xi /= Ld[j * PLD + j];
+        const double xj = __shfl_sync(0xffffffffu, xi, j);
+        if (lane < j) xi -= Ld[j * PLD + lane] * xj;
+      }
+      if (lane < kb) x[k0 + lane] = xi;
+    }
+    __syncthreads();
+    for (int i = tid; i < k0; i += blockDim.x) {
+      double s2 = 0;
+      for (int j = 0; j < kb; j++) s2 += L[(size_t)(k0 + j) * n + i] * x[k0 + j];
+      x[i] -= s2;
+    }
+    __syncthreads();
+  }
+  const int ok = s_ok;
+  double sc = 0, sq = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double xi = ok ? x[i] : 0.0;
+    d.dc[i] = xi;
+    sc += xi * (lambda * xi + d.gc[i]);
+    sq += xi * xi;
+  }
+  const double scs = block_sum(sc, red);
+  const double sqs = block_sum(sq, red);
+  if (tid == 0) { ctrl->scale = scs; ctrl->sumsq = sqs; ctrl->solve_ok = ok; }
+  __syncthreads();
+  // pose update into the trial buffer (VertexPoseSE3::oplusImpl)
+  const int cur = ctrl->cur;
+  for (int i = tid; i < d.n_pose; i += blockDim.x) {
+    Se3 T;
+    const double* src = d.pose[cur] + 12 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 9; k++) T.R[k] = src[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) T.t[k] = src[9 + k];
+    const int v = d.pose_var[i];
+    if (v >= 0) {
+      double mu[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) mu[k] = d.dc[6 * v + k];
+      Se3 E, O;
+      se3_exp(mu, E);
+      se3_mul(E, T, O);
+      T = O;
+    }
+    se3_store(d.pose[cur ^ 1] + 12 * (size_t)i, T);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_lm_control: [3P] OptimizationAlgorithmLevenberg::solve trial bookkeeping + post-iteration actions.
+// red_in != nullptr: sums already reduced (multi-GPU); else reduce the per-block partials here.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lm_control(BaDev d, int n_part_lin, int n_part_bs, const double* red_in, int first_trial)
+{
+  __shared__ double red[32];
+  double cur_chi = 0, tmp_chi = 0, sc = 0, sq = 0;
+  if (red_in) {
+    cur_chi = red_in[0]; tmp_chi = red_in[1]; sc = red_in[2]; sq = red_in[3];
+  } else {
+    double a = 0, b = 0, c = 0, e = 0;
+    for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
+    for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
+      b += d.part[PART_TMP_CHI * MAX_PARTIALS + i];
+      c += d.part[PART_SCALE * MAX_PARTIALS + i];
+      e += d.part[PART_SUMSQ * MAX_PARTIALS + i];
+    }
+    cur_chi = block_sum(a, red); tmp_chi = block_sum(b, red); sc = block_sum(c, red); sq = block_sum(e, red);
+  }
+  if (threadIdx.x != 0) return;
+  BaCtrl* c = d.ctrl;
+  if (first_trial) { c->current_chi = cur_chi; c->lin_chi = cur_chi; }
+  const double temp_raw = tmp_chi;
+  double temp_chi = temp_raw;
+  if (!c->solve_ok) temp_chi = 1.7976931348623157e308;
+  c->temp_chi = temp_raw;
+  double rho = c->current_chi - temp_chi;
+  double scale = c->scale + sc;
+  scale += 1e-3;
+  rho /= scale;
+  const double sumsq = c->sumsq + sq;
+  if (rho > 0 && isfinite(temp_chi)) {
+    const double t = 2 * rho - 1;
+    double alpha = 1. - t * t * t;
+    alpha = fmin(alpha, 2. / 3.);
+    const double sf = fmax(1. / 3., alpha);
+    c->lambda *= sf;
+    c->ni = 2;
+    c->current_chi = temp_chi;
+    c->cur ^= 1;
+    c->accepted = 1;
+  } else {
+    c->lambda *= c->ni;
+    c->ni *= 2;
+    c->accepted = 0;
+  }
+  c->rho = rho;
+  c->qmax++;
+  c->solve_ok = 1;
+  const bool again = (rho < 0) && (c->qmax < c->max_trials);
+  c->stop_trials = again ? 0 : 1;
+  if (!again) {
+    if (c->qmax == c->max_trials || rho == 0) c->terminate = 1;
+    c->iter++;
+    // CheckConvergedUpdateMagAction (src/ChainBundle.cc:1009-1047)
+    const double rms = sqrt(sumsq / c->dim);
+    if (rms < c->rms_limit) c->conv_mag = 1;
+    // CheckConvergedResidualAction (:1091-1118): robust chi2 of the errors currently held by the edges
+    const double curchi = temp_raw;
+    const double pct = (c->last_chi2 - curchi) / c->last_chi2;
+    if (pct >= 0 && pct <= c->pct_limit) c->conv_res = 1;
+    else if (curchi == 0) c->conv_res = 1;
+    c->last_chi2 = curchi;
+    c->total_trials += c->qmax;
+    c->qmax = 0;
+  }
+}
+
+// sums the per-block partials into out[0..3] = {cur_chi, tmp_chi, scale, sumsq} (multi-GPU path)
+__global__ void __launch_bounds__(256) k_reduce_partials(BaDev d, int n_part_lin, int n_part_bs, double* out)
+{
+  __shared__ double red[32];
+  double a = 0, b = 0, c = 0, e = 0;
+  for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
+  for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
+    b += d.part[PART_TMP_CHI * MAX_PARTIALS + i];
+    c += d.part[PART_SCALE * MAX_PARTIALS + i];
+    e += d.part[PART_SUMSQ * MAX_PARTIALS + i];
+  }
+  a = block_sum(a, red); b = block_sum(b, red); c = block_sum(c, red); e = block_sum(e, red);
+  if (threadIdx.x == 0) { if (n_part_lin > 0) out[0] = a; if (n_part_bs > 0) { out[1] = b; out[2] = c; out[3] = e; } }
+}
+
+// Debug: explicit Jacobians per measurement in the caller's order: Jobs(12) Jsrc(12) Jpt(6)
+__global__ void k_debug_jacobians(BaDev d, double* out)
+{
+  const int cur = d.ctrl->cur;
+  const double* pose = d.pose[cur];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < d.n_meas; m += gridDim.x * blockDim.x) {
+    const int4 ma = d.meas_a[m], mbi = d.meas_b[m];
+    const int p = mbi.w;
+    const int4 pi = d.pt_info[p];
+    const double* pp = d.pt[cur] + 3 * (size_t)p;
+    const double prel[3] = { pp[0], pp[1], pp[2] };
+    PtCtx c;
+    load_pt_ctx(d, pose, pi, prel, c);
+    MeasGeom g;
+    meas_geometry<true>(d, pose, c, ma, d.meas_xy[m], g);
+    double* o = out + 30 * (size_t)ma.w;
+    for (int i = 0; i < 30; i++) o[i] = 0;
+    if (mbi.x >= 0) pose_jac(g.A, g.q, -1.0, o);
+    if (mbi.z) pose_jac(g.A2, c.qs, 1.0, o + 12);
+    if (d.pt_var[p] >= 0) {
+      double M[9];
+      point_tangent(prel, M);
+      for (int r = 0; r < 2; r++)
+        for (int k = 0; k < 3; k++) o[24 + r * 3 + k] = -(g.A3[r * 3] * M[k] + g.A3[r * 3 + 1] * M[3 + k] + g.A3[r * 3 + 2] * M[6 + k]);
+    }
+  }
+}
+
+// gathers the full update vector (movable poses then movable points) for mcp_ba_lm_step
+__global__ void k_gather_delta(BaDev d, double* out)
+{
+  const double lambda = d.ctrl->lambda;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < d.nc; i += nt) out[i] = d.dc[i];
+  for (int p = tid; p < d.n_pt; p += nt) {
+    const int pv = d.pt_var[p];
+    if (pv < 0) continue;
+    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+    double t[3] = { 0, 0, 0 };
+    for (int a = 0; a < K; a++)
+      for (int r = 0; r < 6; r++)
+        for (int k = 0; k < 3; k++) t[k] += d.W[(size_t)(s0 + a) * 18 + r * 3 + k] * d.dc[6 * d.slot_var[s0 + a] + r];
+    double V6[6], gp[3], Vi[9];
+    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
+    inv3_sym(V6, lambda, Vi);
+    const double rr[3] = { gp[0] - t[0], gp[1] - t[1], gp[2] - t[2] };
+    double dp[3];
+    m3_vec(Vi, rr, dp);
+    for (int k = 0; k < 3; k++) out[d.nc + 3 * pv + k] = dp[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+static int per_point_grid(const BaDev& d, int warps)
+{
+  const int npts = d.p_hi - d.p_lo;
+  int g = (npts + warps - 1) / warps;
+  if (g < 1) g = 1;
+  if (g > MAX_PARTIALS) g = MAX_PARTIALS;
+  return g;
+}
+
+int launch_linearize(const BaDev& d, bool schur, int warps, size_t smem, cudaStream_t s)
+{
+  const int g = per_point_grid(d, warps);
+  if (schur) k_linearize<true><<<g, warps * 32, smem, s>>>(d);
+  else k_linearize<false><<<g, warps * 32, smem, s>>>(d);
+  return g;
+}
+int launch_schur_only(const BaDev& d, int warps, size_t smem, cudaStream_t s)
+{
+  const int g = per_point_grid(d, warps);
+  k_schur_only<<<g, warps * 32, smem, s>>>(d);
+  return g;
+}
+int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)
+{
+  const int g = per_point_grid(d, 8);
+  k_backsub_eval<<<g, 256, 0, s>>>(d, apply, which, err_out);
+  return g;
+}
+void launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s) { k_select_sigma<<<1, 1024, 0, s>>>(d, which, mode); }
+void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
+void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }
+void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
+size_t solve_smem_bytes(int nc)
+{
+  const size_t panel = (size_t)nc * (NB + 1) + (size_t)NB * (NB + 1);
+  const size_t vec = (size_t)nc + (size_t)NB * (NB + 1);
+  return sizeof(double) * (panel > vec ? panel : vec);
+}
+void launch_solve(const BaDev& d, cudaStream_t s) { k_solve<<<1, 1024, solve_smem_bytes(d.nc), s>>>(d); }
+void launch_lm_control(const BaDev& d, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
+{
+  k_lm_control<<<1, 256, 0, s>>>(d, n_lin, n_bs, red_in, first_trial);
+}
+void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s)
+{
+  k_reduce_partials<<<1, 256, 0, s>>>(d, n_lin, n_bs, out);
+}
+void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s) { k_debug_jacobians<<<148, 128, 0, s>>>(d, out); }
+void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s) { k_gather_delta<<<148, 128, 0, s>>>(d, out); }
+
+int configure_kernels(int max_slots, int* warps_out, size_t* smem_out)
+{
+  // shared memory per warp: W and Y blocks, max_slots x 18 doubles each
+  const size_t per_warp = (size_t)max_slots * 36 * sizeof(double);
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  const size_t smem = per_warp * warps;
+  if (smem > 200 * 1024) return -1;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+  if (e != cudaSuccess) return -2;
+  e = cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+  if (e != cudaSuccess) return -2;
+  e = cudaFuncSetAttribute(k_schur_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+  if (e != cudaSuccess) return -2;
+  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+  if (e != cudaSuccess) return -2;
+  *warps_out = warps;
+  *smem_out = smem;
+  return 0;
+}
+
+}  // namespace mcp

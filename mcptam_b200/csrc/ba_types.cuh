@@ -1,0 +1,81 @@
+// ba_types.cuh — device-side data layout of one bundle-adjustment problem.
+#pragma once
+
+#include "mcp_common.cuh"
+
+namespace mcp {
+
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BINS = 1 << SEL_BITS;   // 2048
+constexpr int SEL_PASSES = 6;             // 6 x 11 bits >= 63 significant bits of |chi2|
+constexpr int MAX_PARTIALS = 4096;        // per-block partial sums (grid size cap for the per-point kernels)
+
+// LM control block: lives in device memory, mirrored into pinned host memory after every trial.
+// Restates the state of g2o::OptimizationAlgorithmLevenberg + the ChainBundle actions
+// (reference src/ChainBundle.cc:904-1126).
+struct BaCtrl {
+  double lambda, ni;
+  double sigma_sq_raw, sigma_sq_lim, sigma_lim;   // RobustKernelData (src/ChainBundle.cc:810-833)
+  double current_chi, temp_chi;
+  double scale, sumsq;                            // computeScale(), sum x^2 of the last solve
+  double max_diag;
+  double last_chi2;                               // CheckConvergedResidualAction::_dLastChi2
+  double rho;
+  double min_sigma_sq, pct_limit, rms_limit, user_lambda;
+  double tukey_sigma_sq;
+  double lin_chi;     // robust chi2 at the linearisation point of the current outer iteration
+  int cur;            // index of the accepted state buffers
+  int accepted;       // last trial accepted
+  int stop_trials;    // trial loop of this outer iteration is over
+  int terminate;      // solver returned Terminate (qmax hit / rho == 0)
+  int qmax;           // trials in this outer iteration
+  int solve_ok;
+  int iter;           // outer iterations completed in this Compute
+  int conv_mag, conv_res;
+  int total_trials;
+  int max_trials, use_robust;
+  int dim;            // 6*n_pose_var + 3*n_pt_var (global)
+  int need_lambda_init;
+  int n_outliers;
+  int sel_n;          // number of values in the selection (global measurement count)
+  int sel_rank;       // n/2
+  int pad_;
+};
+
+struct BaDev {
+  const DevCam* cams;
+  int n_pose, n_pt, n_meas, n_pose_var, n_pt_var, nc, n_slots, max_slots;
+  int p_lo, p_hi;                // local point range (multi-GPU shard)
+  int m_lo, m_hi;                // local measurement range (sorted order)
+  const int* pose_var;           // [n_pose] variable index or -1
+  const int4* pt_info;           // [n_pt] {src link0 pose id, src link1 pose id | -1, src var | -1, src slot | -1}
+  const int* pt_var;             // [n_pt] point variable index or -1 (fixed)
+  const int* pt_meas_off;        // [n_pt+1]
+  const int* pt_slot_off;        // [n_pt+1]
+  const int* slot_var;           // [n_slots] pose variable of each (point, slot), ascending within a point
+  const double2* meas_xy;        // [n_meas] sorted by point
+  const double* meas_info;       // [n_meas] 1/sqrt(dNoiseSigmaSquared)
+  const int4* meas_a;            // [n_meas] {obs link0 pose id, obs link1 pose id | -1, camera, original index}
+  const int4* meas_b;            // [n_meas] {obs var | -1 (no obs Jacobian), obs slot | -1, has_src_jac, point id}
+  double* pose[2];               // [n_pose*12]
+  double* pt[2];                 // [n_pt*3]
+  double* chi2[2];               // [n_meas] signed as EdgeChainMeas::chi2
+  double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
+  double* gp;                    // [n_pt*3]
+  double* W;                     // [n_slots*18] 6x3 row-major
+  double* H0;                    // [nc*nc] upper block triangle, pose-pose normal matrix (no damping)
+  double* Sm;                    // [nc*nc] upper block triangle, sum_p W (V+lambda I)^-1 W^T
+  double* gc;                    // [nc]
+  double* rm;                    // [nc]   sum_p W (V+lambda I)^-1 g_p
+  double* dc;                    // [nc]   pose update
+  double* L;                     // [nc*nc] Cholesky factor workspace (lower, row-major)
+  double* part;                  // [8][MAX_PARTIALS] per-block partial sums
+  unsigned* hist;                // [SEL_PASSES][SEL_BINS]
+  BaCtrl* ctrl;
+  int* outlier_flags;            // [n_meas] (sorted order)
+  double* dbg;                   // optional debug output
+};
+
+enum PartialRow { PART_CUR_CHI = 0, PART_MAXDIAG = 1, PART_TMP_CHI = 2, PART_SCALE = 3, PART_SUMSQ = 4 };
+
+}  // namespace mcp

@@ -1,0 +1,391 @@
+"""Seeded synthetic maps and frames for the two hot paths.
+
+This module is data generation only (numpy): camera rigs with Taylor (Scaramuzza) parameters,
+multi-keyframe trajectories, map points, measurements, and textured 640x480 frames.  It also
+contains a numpy restatement of TaylorCamera::RefreshParams / FindInvPolyUsingRoots
+(reference src/TaylorCamera.cc:84-198, 489-604), used to fill the plain-C camera struct that
+crosses the C ABI (include/mcptam_b200.h: McpTaylorCam).
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import math
+
+import numpy as np
+
+MAX_INV_DEGREE = 30  # include/mcptam/TaylorCamera.h:74
+
+
+class TaylorCamStruct(ctypes.Structure):
+    """Memory layout shared by McpTaylorCam (include/mcptam_b200.h) and OraTaylorCam (oracle/oracle.h)."""
+
+    _fields_ = [
+        ("poly", ctypes.c_double * 5),
+        ("center", ctypes.c_double * 2),
+        ("affine", ctypes.c_double * 4),
+        ("image_size", ctypes.c_double * 2),
+        ("min_theta", ctypes.c_double),
+        ("theta_mean", ctypes.c_double),
+        ("theta_std", ctypes.c_double),
+        ("n_inv", ctypes.c_int32),
+        ("pad_", ctypes.c_int32),
+        ("inv_poly", ctypes.c_double * 32),
+    ]
+
+
+def _polyval_low_first(c, x):
+    """TaylorCamera::PolyVal (src/TaylorCamera.cc:472-485): coefficient of x^0 first."""
+    val = 0.0
+    for i in range(len(c) - 1, 0, -1):
+        val += c[i]
+        val *= x
+    return val + c[0]
+
+
+def taylor_camera(params9, calib_size=(640, 480), full_size=(640, 480), image_size=(640, 480)) -> TaylorCamStruct:
+    """numpy restatement of TaylorCamera::RefreshParams for a live (non-calibration) camera."""
+    p = np.asarray(params9, dtype=np.float64)
+    poly = np.array([p[0], 0.0, p[1], p[2], p[3]])
+    calib = np.asarray(calib_size, float)
+    full = np.asarray(full_size, float)
+    img = np.asarray(image_size, float)
+    scale = img / full
+    fs_center = np.array([p[4] - (calib[0] - full[0]) / 2, p[5] - (calib[1] - full[1]) / 2])
+    center = fs_center * scale
+    corner = np.maximum(fs_center, full - fs_center - 1)
+    largest_radius = math.sqrt(float(corner @ corner))
+    max_rho = 1.0 * largest_radius
+    min_theta = math.atan(_polyval_low_first(poly, max_rho) / max_rho)
+
+    # FindInvPolyUsingRoots (src/TaylorCamera.cc:489-604)
+    theta_start = -math.pi / 2 + 0.001
+    theta_end = math.pi / 2 - 0.001
+    step = 0.01
+    n_theta = int(math.ceil((theta_end - theta_start) / step)) + 1
+    thetas = np.empty(n_theta)
+    thetas[0] = theta_start
+    for i in range(1, n_theta):
+        thetas[i] = thetas[i - 1] + step
+    th_ok, rho_ok = [], []
+    for th in thetas:
+        coeffs_high_first = [poly[4], poly[3], poly[2], poly[1] - math.tan(th), poly[0]]
+        roots = np.roots(coeffs_high_first)
+        real = [r.real for r in roots if abs(r.imag) < 1e-12]
+        real = [r for r in real if not (r < 0.0 or r > max_rho)]
+        if len(real) == 1:
+            th_ok.append(th)
+            rho_ok.append(real[0])
+    th_ok = np.array(th_ok)
+    rho_ok = np.array(rho_ok)
+    if th_ok.size < 3:
+        raise ValueError("camera polynomial has no valid theta range")
+    mean = float(th_ok.sum() / th_ok.size)
+    shifted = th_ok - mean
+    std = math.sqrt(float(shifted @ shifted) / shifted.size)
+    x = (th_ok - mean) / std
+    inv = None
+    deg = 2
+    while deg <= MAX_INV_DEGREE:
+        V = np.vander(x, deg + 1, increasing=True)
+        a, *_ = np.linalg.lstsq(V, rho_ok, rcond=None)  # SVD back-substitution (TooN SVD::backsub)
+        err = np.abs(V @ a - rho_ok).max()
+        if err <= 1e-4:
+            inv = a
+            break
+        deg += 1
+    if inv is None:
+        raise ValueError("no inverse polynomial of degree <= %d fits to 1e-4" % MAX_INV_DEGREE)
+
+    cam = TaylorCamStruct()
+    cam.poly[:] = poly.tolist()
+    cam.center[:] = center.tolist()
+    cam.affine[:] = [scale[0] * p[6], scale[1] * p[7], scale[0] * p[8], scale[1] * 1.0]
+    cam.image_size[:] = img.tolist()
+    cam.min_theta = min_theta
+    cam.theta_mean = mean
+    cam.theta_std = std
+    cam.n_inv = len(inv)
+    for i, v in enumerate(inv):
+        cam.inv_poly[i] = float(v)
+    return cam
+
+
+def cam_project_np(cam: TaylorCamStruct, v):
+    """Vectorised TaylorCamera::Project (src/TaylorCamera.cc:202-287). v: (...,3). Returns px (...,2), invalid (...)."""
+    v = np.asarray(v, float)
+    norm = np.sqrt(v[..., 0] ** 2 + v[..., 1] ** 2)
+    safe = np.where(norm == 0, 1.0, norm)
+    theta = np.where(norm == 0, math.pi / 2, np.arctan(v[..., 2] / safe))
+    inv = np.array(cam.inv_poly[: cam.n_inv])
+    xs = (theta - cam.theta_mean) / cam.theta_std
+    rho = np.zeros_like(xs)
+    for i in range(len(inv) - 1, 0, -1):
+        rho = (rho + inv[i]) * xs
+    rho = rho + inv[0]
+    rho = np.where(norm == 0, 0.0, rho)
+    c = np.where(norm == 0, 0.0, v[..., 0] / safe)
+    s = np.where(norm == 0, 0.0, v[..., 1] / safe)
+    u, w = c * rho, s * rho
+    A = cam.affine
+    px = np.stack([A[0] * u + A[1] * w + cam.center[0], A[2] * u + A[3] * w + cam.center[1]], -1)
+    invalid = theta < cam.min_theta
+    invalid |= ~((px[..., 0] >= 0) & (px[..., 0] < cam.image_size[0]) & (px[..., 1] >= 0) & (px[..., 1] < cam.image_size[1]))
+    return px, invalid
+
+
+def cam_unproject_np(cam: TaylorCamStruct, px):
+    """TaylorCamera::UnProject (src/TaylorCamera.cc:319-346), vectorised."""
+    px = np.asarray(px, float)
+    A = np.array(cam.affine).reshape(2, 2)
+    Ai = np.linalg.inv(A)
+    d = px - np.array(cam.center)
+    uv = d @ Ai.T
+    rho = np.sqrt((uv ** 2).sum(-1))
+    poly = np.array(cam.poly)
+    z = np.zeros_like(rho)
+    for i in range(4, 0, -1):
+        z = (z + poly[i]) * rho
+    z = z + poly[0]
+    ray = np.concatenate([uv, z[..., None]], -1)
+    return ray / np.linalg.norm(ray, axis=-1, keepdims=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# SE3 helpers (numpy, generator side only)
+# ---------------------------------------------------------------------------------------------
+def so3_exp(w):
+    w = np.asarray(w, float)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + math.sin(th) / th * K + (1 - math.cos(th)) / th ** 2 * (K @ K)
+
+
+def rt_mul(a, b):
+    """(R,t) product: a*b."""
+    return a[0] @ b[0], a[0] @ b[1] + a[1]
+
+
+def rt_inv(a):
+    return a[0].T, -a[0].T @ a[1]
+
+
+def rt_pack(rt):
+    return np.concatenate([rt[0].reshape(9), rt[1].reshape(3)])
+
+
+@dataclasses.dataclass
+class BaProblem:
+    """Flat arrays of one bundle-adjustment problem — the fields the C ABI takes (mcp_ba_load)."""
+
+    cams: list            # list[TaylorCamStruct]
+    pose_Rt: np.ndarray   # (n_pose,12) row-major R then t; MKF base poses first, then cam-from-base
+    pose_fixed: np.ndarray  # (n_pose,) u8
+    pt_xyz: np.ndarray    # (n_pt,3) in source-camera frame
+    pt_chain: np.ndarray  # (n_pt,2) i32 pose ids [mkf, cam-extrinsic]
+    pt_fixed: np.ndarray  # (n_pt,) u8
+    meas_xy: np.ndarray   # (n_meas,2)
+    meas_chain: np.ndarray  # (n_meas,2) i32
+    meas_pt: np.ndarray   # (n_meas,) i32
+    meas_noise: np.ndarray  # (n_meas,) f64  = LevelScale^2  (BundleAdjusterMulti.cc:196)
+    meas_cam: np.ndarray  # (n_meas,) i32 camera model index
+    n_mkf: int = 0
+    truth_pose_Rt: np.ndarray | None = None
+    truth_pt_xyz: np.ndarray | None = None
+
+    @property
+    def n_pose(self):
+        return len(self.pose_Rt)
+
+    @property
+    def n_pt(self):
+        return len(self.pt_xyz)
+
+    @property
+    def n_meas(self):
+        return len(self.meas_pt)
+
+
+DEFAULT_TAYLOR = (250.0, -1.2e-3, 6.0e-7, -1.0e-9)  # a0, a2, a3, a4 : +z looking, ~165 deg FOV at 640x480
+
+
+def make_rig(n_cam, rng, image_size=(640, 480)):
+    """C cameras on a ring (radius 0.1 m), yaw 360/C apart, optical axis (+z) pointing outward."""
+    cams, extr = [], []
+    for c in range(n_cam):
+        a0, a2, a3, a4 = DEFAULT_TAYLOR
+        params = [a0 * (1 + 0.01 * rng.standard_normal()), a2, a3, a4,
+                  image_size[0] / 2 + 2 * rng.standard_normal(), image_size[1] / 2 + 2 * rng.standard_normal(),
+                  1.0 + 1e-3 * rng.standard_normal(), 1e-3 * rng.standard_normal(), 1e-3 * rng.standard_normal()]
+        cams.append(taylor_camera(params, image_size, image_size, image_size))
+        yaw = 2 * math.pi * c / n_cam
+        # base frame: x forward, y left, z up.  camera: z = optical axis, x right, y down.
+        fwd = np.array([math.cos(yaw), math.sin(yaw), 0.0])
+        up = np.array([0.0, 0.0, 1.0])
+        right = np.cross(fwd, up)
+        R_base_from_cam = np.stack([right, -up, fwd], 1)
+        t_base_from_cam = 0.1 * fwd
+        extr.append(rt_inv((R_base_from_cam, t_base_from_cam)))  # cam-from-base
+    return cams, extr
+
+
+def make_ba_problem(n_cam=1, n_mkf=20, n_pt=1000, seed=0, mean_track=8.0, outlier_frac=0.02,
+                    pose_sigma_t=0.02, pose_sigma_r=math.radians(0.5), depth_sigma=0.05,
+                    pix_sigma=0.5) -> BaProblem:
+    rng = np.random.default_rng(seed)
+    cams, extr = make_rig(n_cam, rng)
+    # trajectory: loop of radius 5 m, +-0.5 m vertical sine; first MKF at identity (fixed)
+    base_from_world = []
+    for m in range(n_mkf):
+        ang = 2 * math.pi * m / max(n_mkf, 1) * 0.9
+        pos = np.array([5 * math.sin(ang), 5 * (1 - math.cos(ang)), 0.5 * math.sin(2 * ang)])
+        Rwb = so3_exp([0, 0, ang]) @ so3_exp(0.05 * rng.standard_normal(3) * (m > 0))
+        base_from_world.append(rt_inv((Rwb, pos)))
+    # points: shell 3-12 m from the path
+    centre = np.array([0.0, 5.0, 0.0])
+    pts = []
+    while len(pts) < n_pt:
+        ang = rng.uniform(0, 2 * math.pi)
+        path = np.array([5 * math.sin(ang), 5 * (1 - math.cos(ang)), 0.0])
+        d = rng.standard_normal(3)
+        d /= np.linalg.norm(d)
+        pts.append(path + d * rng.uniform(3, 12))
+    pts = np.array(pts)
+    del centre
+
+    # visibility table: for each (mkf, cam): pixel + valid
+    cam_from_world = [[rt_mul(extr[c], base_from_world[m]) for c in range(n_cam)] for m in range(n_mkf)]
+    px_all = np.zeros((n_mkf, n_cam, n_pt, 2))
+    ok_all = np.zeros((n_mkf, n_cam, n_pt), bool)
+    for m in range(n_mkf):
+        for c in range(n_cam):
+            R, t = cam_from_world[m][c]
+            pc = pts @ R.T + t
+            px, invalid = cam_project_np(cams[c], pc)
+            # keep away from the exact optical axis (asin/normalize singularity) and image border
+            margin = (px[:, 0] > 8) & (px[:, 0] < cams[c].image_size[0] - 8) & (px[:, 1] > 8) & (px[:, 1] < cams[c].image_size[1] - 8)
+            off_axis = np.hypot(pc[:, 0], pc[:, 1]) > 1e-3 * np.abs(pc[:, 2])
+            px_all[m, c] = px
+            ok_all[m, c] = (~invalid) & margin & off_axis
+
+    meas_xy, meas_chain, meas_pt, meas_noise, meas_cam = [], [], [], [], []
+    pt_chain = np.zeros((n_pt, 2), np.int32)
+    pt_rel_true = np.zeros((n_pt, 3))
+    keep_pt = np.zeros(n_pt, bool)
+    level_p = np.array([0.5, 0.25, 0.15, 0.1])
+    for p in range(n_pt):
+        vis = np.argwhere(ok_all[:, :, p])
+        if len(vis) < 2:
+            continue
+        ms, cs = vis[rng.integers(len(vis))]
+        # observers: window of consecutive MKFs around the source (co-visibility is local in real maps)
+        L = max(2, int(round(rng.gamma(4.0, mean_track / 4.0))))
+        mk_vis = np.unique(vis[:, 0])
+        order = mk_vis[np.argsort(np.abs(mk_vis - ms), kind="stable")]
+        chosen = order[:L]
+        obs = []
+        for m in chosen:
+            cc = np.flatnonzero(ok_all[m, :, p])
+            if m == ms:
+                sel = [cs]
+                if len(cc) > 1 and rng.random() < 0.15:
+                    sel.append(int(rng.choice(cc[cc != cs])))
+            else:
+                sel = [int(rng.choice(cc))]
+                if len(cc) > 1 and rng.random() < 0.15:
+                    sel.append(int(rng.choice(cc[cc != sel[0]])))
+            obs += [(int(m), int(c)) for c in sel]
+        if len({m for m, _ in obs}) < 2 and len(obs) < 2:
+            continue
+        keep_pt[p] = True
+        pt_chain[p] = (ms, n_mkf + cs)
+        R, t = cam_from_world[ms][cs]
+        pt_rel_true[p] = R @ pts[p] + t
+        for m, c in obs:
+            lvl = int(rng.choice(4, p=level_p))
+            z = px_all[m, c, p] + rng.standard_normal(2) * pix_sigma * (1 << lvl)
+            if rng.random() < outlier_frac and not (m == ms and c == cs):
+                z = px_all[m, c, p] + rng.uniform(-30, 30, 2)
+            meas_xy.append(z)
+            meas_chain.append((m, n_mkf + c))
+            meas_pt.append(p)
+            meas_noise.append(float((1 << lvl) ** 2))
+            meas_cam.append(c)
+
+    # compact point indices
+    remap = -np.ones(n_pt, np.int64)
+    remap[keep_pt] = np.arange(keep_pt.sum())
+    meas_pt = remap[np.array(meas_pt, np.int64)].astype(np.int32)
+
+    truth_pose = np.array([rt_pack(x) for x in base_from_world] + [rt_pack(e) for e in extr])
+    # initial state: perturb movable MKF poses and point depths
+    init_pose = truth_pose.copy()
+    for m in range(1, n_mkf):
+        dR = so3_exp(rng.standard_normal(3) * pose_sigma_r)
+        dt = rng.standard_normal(3) * pose_sigma_t
+        R, t = base_from_world[m]
+        init_pose[m] = rt_pack((dR @ R, dR @ t + dt))
+    pose_fixed = np.zeros(n_mkf + n_cam, np.uint8)
+    pose_fixed[0] = 1
+    pose_fixed[n_mkf:] = 1
+    truth_rel = pt_rel_true[keep_pt]
+    init_rel = truth_rel * np.exp(rng.standard_normal((len(truth_rel), 1)) * depth_sigma)
+
+    return BaProblem(
+        cams=cams, pose_Rt=np.ascontiguousarray(init_pose), pose_fixed=pose_fixed,
+        pt_xyz=np.ascontiguousarray(init_rel), pt_chain=np.ascontiguousarray(pt_chain[keep_pt]),
+        pt_fixed=np.zeros(int(keep_pt.sum()), np.uint8),
+        meas_xy=np.ascontiguousarray(np.array(meas_xy)), meas_chain=np.array(meas_chain, np.int32),
+        meas_pt=meas_pt, meas_noise=np.array(meas_noise), meas_cam=np.array(meas_cam, np.int32),
+        n_mkf=n_mkf, truth_pose_Rt=truth_pose, truth_pt_xyz=truth_rel)
+
+
+BA_CONFIGS = {
+    # BASELINE.json configs[0], [1], [3]
+    "cfg1": dict(n_cam=1, n_mkf=20, n_pt=1000),
+    "cfg2": dict(n_cam=4, n_mkf=50, n_pt=10000),
+    "cfg4": dict(n_cam=8, n_mkf=125, n_pt=100000),
+    "tiny": dict(n_cam=2, n_mkf=5, n_pt=120),
+}
+
+
+def make_ba_config(name, seed=0, **kw) -> BaProblem:
+    args = dict(BA_CONFIGS[name])
+    args.update(kw)
+    return make_ba_problem(seed=seed, **args)
+
+
+# ---------------------------------------------------------------------------------------------
+# frames for the front end
+# ---------------------------------------------------------------------------------------------
+def make_frame(w=640, h=480, seed=0, n_shapes=400, shift=(0.0, 0.0)) -> np.ndarray:
+    """Multi-octave value noise + random high-contrast rectangles/discs (≈2-4 k FAST corners at L0)."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float64)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    xx = xx + shift[0]
+    yy = yy + shift[1]
+    for octave, amp in ((64, 50.0), (32, 30.0), (16, 18.0), (8, 10.0)):
+        gh, gw = h // octave + 3, w // octave + 3
+        g = rng.uniform(-1, 1, (gh, gw))
+        fx, fy = xx / octave, yy / octave
+        ix = np.clip(np.floor(fx).astype(int), 0, gw - 2)
+        iy = np.clip(np.floor(fy).astype(int), 0, gh - 2)
+        ax, ay = fx - ix, fy - iy
+        v = (g[iy, ix] * (1 - ax) + g[iy, ix + 1] * ax) * (1 - ay) + (g[iy + 1, ix] * (1 - ax) + g[iy + 1, ix + 1] * ax) * ay
+        img += amp * v
+    img += 128
+    for _ in range(n_shapes):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        val = rng.choice([20.0, 60.0, 190.0, 235.0])
+        if rng.random() < 0.6:
+            hw, hh = rng.uniform(3, 18), rng.uniform(3, 18)
+            m = (np.abs(xx - cx) < hw) & (np.abs(yy - cy) < hh)
+        else:
+            r = rng.uniform(3, 14)
+            m = (xx - cx) ** 2 + (yy - cy) ** 2 < r * r
+        img[m] = val
+    img += rng.standard_normal((h, w)) * 1.5
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

@@ -1,0 +1,432 @@
+/*
+ * fe_oracle.c — CPU restatement of the per-frame front end.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+ * PARITY UNPINNED: the reference has no golden vectors; libCVD is not available here.
+ *
+ * Follows (file:line in /root/reference):
+ *   src/KeyFrame.cc:189-190     CVD::halfSample                       [3P libCVD]  -> ora_halfsample
+ *   src/KeyFrame.cc:259-262     fast_corner_detect_10 / _score_10      [3P libCVD]  -> ora_fast10_*
+ *   src/KeyFrame.cc:264-315     histogram, adaptive threshold, mask filter         -> ora_level_corners
+ *   src/KeyFrame.cc:348-355     row LUT                                            -> ora_level_corners
+ *   src/ShiTomasi.cc:34-63      FindShiTomasiScoreAtPoint                          -> ora_shitomasi
+ *   src/PatchFinder.cc:135-182  MakeTemplateCoarseCont -> CVD::transform [3P]      -> ora_patch_template
+ *   src/PatchFinder.cc:209-223  MakeTemplateSums
+ *   src/PatchFinder.cc:229-355  FindPatchCoarse                                    -> ora_find_patch_coarse
+ *   src/PatchFinder.cc:362-470  MakeSubPixTemplate / IterateSubPix(ToConvergence)  -> ora_subpix
+ *   src/PatchFinder.cc:511-658  ZMSSDAtPoint                                       -> ora_zmssd
+ *   src/MiniPatch.cc:34-113     SSDAtPoint / FindPatch                             -> ora_minipatch_*
+ * [3P] libCVD semantics restated from libCVD release 20121025 (vision.h halfSample/transform/sample,
+ *      fast_corner.h): ring layout, strict > / < comparisons, 3 px border, raster order, truncating
+ *      2x2 mean, truncating float->byte conversion in sample().
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* [3P] CVD::halfSample generic template: truncating mean of the 2x2 block, out size = in size / 2 */
+void ora_halfsample(const uint8_t* in, int w, int h, int in_stride, uint8_t* out, int out_stride)
+{
+  const int ow = w / 2, oh = h / 2;
+  for (int y = 0; y < oh; y++) {
+    const uint8_t* r0 = in + (size_t)(2 * y) * in_stride;
+    const uint8_t* r1 = r0 + in_stride;
+    uint8_t* o = out + (size_t)y * out_stride;
+    for (int x = 0; x < ow; x++) o[x] = (uint8_t)((r0[2 * x] + r0[2 * x + 1] + r1[2 * x] + r1[2 * x + 1]) / 4);
+  }
+}
+
+/* [3P] FAST ring: radius-3 Bresenham circle, 16 pixels, clockwise from 12 o'clock
+   (image y grows downward) */
+static const int RING_DX[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
+static const int RING_DY[16] = { -3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3 };
+
+static int is_cornerN(const uint8_t* p, int stride, int b, int n_arc)
+{
+  const int c = *p;
+  for (int pol = 0; pol < 2; pol++)
+    for (int s = 0; s < 16; s++) {
+      int k;
+      for (k = 0; k < n_arc; k++) {
+        const int i = (s + k) & 15;
+        const int v = p[RING_DY[i] * stride + RING_DX[i]];
+        if (pol == 0 ? !(v > c + b) : !(v < c - b)) break;
+      }
+      if (k == n_arc) return 1;
+    }
+  return 0;
+}
+int ora_fastN_detect_bruteforce(const uint8_t* im, int w, int h, int stride, int b, int n_arc, int32_t* xy, int cap)
+{
+  int n = 0;
+  for (int y = 3; y < h - 3; y++)
+    for (int x = 3; x < w - 3; x++)
+      if (is_cornerN(im + (size_t)y * stride + x, stride, b, n_arc)) {
+        if (n < cap) { xy[2 * n] = x; xy[2 * n + 1] = y; }
+        n++;
+      }
+  return n;
+}
+int ora_fast10_detect_bruteforce(const uint8_t* im, int w, int h, int stride, int b, int32_t* xy, int cap)
+{
+  return ora_fastN_detect_bruteforce(im, w, h, stride, b, 10, xy, cap);
+}
+
+/* contiguous run of >= n set bits in a 16-bit circular mask */
+static int has_run(unsigned m, int n)
+{
+  unsigned d = m | (m << 16);
+  unsigned r = d;
+  for (int k = 1; k < n; k++) r &= (d >> k);
+  return (r & 0xFFFFu) != 0;
+}
+/* Same definition as the brute force, with the usual early rejection on the compass points. */
+int ora_fast10_detect(const uint8_t* im, int w, int h, int stride, int b, int32_t* xy, int cap)
+{
+  int n = 0;
+  int off[16];
+  for (int i = 0; i < 16; i++) off[i] = RING_DY[i] * stride + RING_DX[i];
+  for (int y = 3; y < h - 3; y++) {
+    const uint8_t* row = im + (size_t)y * stride;
+    for (int x = 3; x < w - 3; x++) {
+      const uint8_t* p = row + x;
+      const int cb = *p + b, c_b = *p - b;
+      /* any 10-arc contains one of {0,8} and one of {4,12} */
+      const int v0 = p[off[0]], v8 = p[off[8]];
+      if (!(v0 > cb || v0 < c_b || v8 > cb || v8 < c_b)) continue;
+      const int v4 = p[off[4]], v12 = p[off[12]];
+      if (!(v4 > cb || v4 < c_b || v12 > cb || v12 < c_b)) continue;
+      unsigned br = 0, dk = 0;
+      for (int i = 0; i < 16; i++) {
+        const int v = p[off[i]];
+        br |= (unsigned)(v > cb) << i;
+        dk |= (unsigned)(v < c_b) << i;
+      }
+      if (has_run(br, 10) || has_run(dk, 10)) {
+        if (n < cap) { xy[2 * n] = x; xy[2 * n + 1] = y; }
+        n++;
+      }
+    }
+  }
+  return n;
+}
+
+/* [3P] fast_corner_score_10: largest threshold t >= b for which the pixel is still a FAST-10 corner.
+   Closed form: max over arcs of (min over arc of signed difference) - 1. */
+void ora_fast10_score(const uint8_t* im, int stride, const int32_t* xy, int n, int b, int32_t* scores)
+{
+  for (int c = 0; c < n; c++) {
+    const uint8_t* p = im + (size_t)xy[2 * c + 1] * stride + xy[2 * c];
+    const int ctr = *p;
+    int d[16];
+    for (int i = 0; i < 16; i++) d[i] = p[RING_DY[i] * stride + RING_DX[i]] - ctr;
+    int best = b;
+    for (int s = 0; s < 16; s++) {
+      int mn = 255, mx = -255;
+      for (int k = 0; k < 10; k++) {
+        const int v = d[(s + k) & 15];
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+      }
+      if (mn - 1 > best) best = mn - 1;       /* all brighter than ctr + t  <=>  t < min diff */
+      if (-mx - 1 > best) best = -mx - 1;     /* all darker  than ctr - t  <=>  t < min(-diff) */
+    }
+    scores[c] = best;
+  }
+}
+/* The bisection exactly as libCVD performs it (bmin = b, bmax = 255). */
+void ora_fast10_score_bisect(const uint8_t* im, int stride, const int32_t* xy, int n, int b, int32_t* scores)
+{
+  for (int c = 0; c < n; c++) {
+    const uint8_t* p = im + (size_t)xy[2 * c + 1] * stride + xy[2 * c];
+    int bmin = b, bmax = 255, t = (bmax + bmin) / 2;
+    for (;;) {
+      if (is_cornerN(p, stride, t, 10)) bmin = t; else bmax = t;
+      if (bmin == bmax - 1 || bmin == bmax) break;
+      t = (bmin + bmax) / 2;
+    }
+    scores[c] = bmin;
+  }
+}
+
+/* src/KeyFrame.cc:247-355 for one level */
+int ora_level_corners(const uint8_t* im, int w, int h, int stride, const uint8_t* mask, int mask_stride,
+                      int adaptive, int fixed_thresh, int32_t* xy, int cap, int32_t* freq, int32_t* thresh_out,
+                      int32_t* row_lut)
+{
+  int n_keep = 0;
+  for (int t = 0; t <= 30; t++) freq[t] = 0;
+  if (adaptive) {
+    int n = ora_fast10_detect(im, w, h, stride, 5, NULL, 0);
+    int32_t* all = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(n > 0 ? n : 1));
+    int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    ora_fast10_detect(im, w, h, stride, 5, all, n);
+    ora_fast10_score(im, stride, all, n, 5, sc);
+    for (int j = 0; j < n; j++)                                   /* :264-275 */
+      for (int t = 5; t <= 30; ++t) {
+        if (sc[j] >= t) freq[t]++;
+        if (sc[j] == t) break;
+      }
+    const double target = -1 * (w * h) / 500.0;                    /* :279 */
+    int thr = 5;
+    for (int t = 5; t <= 30; ++t) {                                /* :283-300 */
+      double deriv;
+      if (t == 5) deriv = freq[t + 1] - freq[t];
+      else if (t == 30) deriv = freq[t] - freq[t - 1];
+      else deriv = (freq[t + 1] - freq[t - 1]) / 2.0;
+      thr = t;
+      if (deriv > target) break;
+    }
+    for (int j = 0; j < n; j++) {                                  /* :303-312 */
+      if (mask && mask[(size_t)all[2 * j + 1] * mask_stride + all[2 * j]] < 255) continue;
+      if (sc[j] < thr) continue;
+      if (n_keep < cap) { xy[2 * n_keep] = all[2 * j]; xy[2 * n_keep + 1] = all[2 * j + 1]; }
+      n_keep++;
+    }
+    *thresh_out = thr;
+    free(all); free(sc);
+  } else {
+    n_keep = ora_fast10_detect(im, w, h, stride, fixed_thresh, xy, cap);
+    *thresh_out = fixed_thresh;
+  }
+  if (row_lut) {                                                   /* :348-355 */
+    int v = 0;
+    const int nk = n_keep < cap ? n_keep : cap;
+    for (int y = 0; y < h; y++) {
+      while (v < nk && y > xy[2 * v + 1]) v++;
+      row_lut[y] = v;
+    }
+  }
+  return n_keep;
+}
+
+/* src/ShiTomasi.cc:34-63 */
+double ora_shitomasi(const uint8_t* im, int stride, int hb, int cx, int cy)
+{
+  double dXX = 0, dYY = 0, dXY = 0;
+  for (int y = cy - hb; y <= cy + hb; y++)
+    for (int x = cx - hb; x <= cx + hb; x++) {
+      const double dx = im[(size_t)y * stride + x + 1] - im[(size_t)y * stride + x - 1];
+      const double dy = im[(size_t)(y + 1) * stride + x] - im[(size_t)(y - 1) * stride + x];
+      dXX += dx * dx; dYY += dy * dy; dXY += dx * dy;
+    }
+  const int nPixels = (2 * hb + 1) * (2 * hb + 1);
+  dXX = dXX / (2.0 * nPixels);
+  dYY = dYY / (2.0 * nPixels);
+  dXY = dXY / (2.0 * nPixels);
+  return 0.5 * (dXX + dYY - sqrt((dXX + dYY) * (dXX + dYY) - 4 * (dXX * dYY - dXY * dXY)));
+}
+
+/* [3P] CVD::sample<byte,byte>: bilinear in double, implicit double->byte truncation */
+static uint8_t sample_u8(const uint8_t* im, int stride, double x, double y)
+{
+  const int lx = (int)x, ly = (int)y;
+  x -= lx; y -= ly;
+  const uint8_t* p = im + (size_t)ly * stride + lx;
+  const double v = (1 - y) * ((1 - x) * p[0] + x * p[1]) + y * ((1 - x) * p[stride] + x * p[stride + 1]);
+  return (uint8_t)v;
+}
+/* [3P] CVD::transform(in, out(8x8), M, inOrig, outOrig=(4,4)).  Returns number of pixels outside. */
+int ora_patch_template(const uint8_t* src, int w, int h, int stride, const double* M, double cx, double cy,
+                       uint8_t* out)
+{
+  const int ow = 8, oh = 8;
+  const double across[2] = { M[0], M[2] }, down[2] = { M[1], M[3] };
+  const double oo[2] = { 4, 4 };
+  double p0[2] = { cx - (M[0] * oo[0] + M[1] * oo[1]), cy - (M[2] * oo[0] + M[3] * oo[1]) };
+  double min_x = p0[0], min_y = p0[1], max_x = p0[0], max_y = p0[1];
+  if (across[0] < 0) min_x += ow * across[0]; else max_x += ow * across[0];
+  if (down[0] < 0) min_x += oh * down[0]; else max_x += oh * down[0];
+  if (across[1] < 0) min_y += ow * across[1]; else max_y += ow * across[1];
+  if (down[1] < 0) min_y += oh * down[1]; else max_y += oh * down[1];
+  const double cr[2] = { down[0] - ow * across[0], down[1] - ow * across[1] };
+  double p[2] = { p0[0], p0[1] };
+  if (min_x >= 0 && min_y >= 0 && max_x < w - 1 && max_y < h - 1) {
+    for (int i = 0; i < oh; ++i, p[0] += cr[0], p[1] += cr[1])
+      for (int j = 0; j < ow; ++j, p[0] += across[0], p[1] += across[1]) out[i * 8 + j] = sample_u8(src, stride, p[0], p[1]);
+    return 0;
+  }
+  const double xb = w - 1, yb = h - 1;
+  int count = 0;
+  for (int i = 0; i < oh; ++i, p[0] += cr[0], p[1] += cr[1])
+    for (int j = 0; j < ow; ++j, p[0] += across[0], p[1] += across[1]) {
+      if (0 <= p[0] && 0 <= p[1] && p[0] < xb && p[1] < yb) out[i * 8 + j] = sample_u8(src, stride, p[0], p[1]);
+      else { out[i * 8 + j] = 0; ++count; }
+    }
+  return count;
+}
+
+/* src/PatchFinder.cc:511-658 (scalar branch; the SSE branch computes the same integers) */
+int ora_zmssd(const uint8_t* im, int w, int h, int stride, const uint8_t* t, int tsum, int tsumsq, int x, int y,
+              int max_ssd)
+{
+  if (!(x >= 4 && y >= 4 && x < w - 4 && y < h - 4)) return max_ssd + 1;   /* in_image_with_border(ir, 4) */
+  int nImageSumSq = 0, nImageSum = 0, nCrossSum = 0;
+  for (int r = 0; r < 8; r++) {
+    const uint8_t* ip = im + (size_t)(y - 4 + r) * stride + (x - 4);
+    const uint8_t* tp = t + r * 8;
+    for (int c = 0; c < 8; c++) {
+      const int n = ip[c];
+      nImageSum += n; nImageSumSq += n * n; nCrossSum += n * tp[c];
+    }
+  }
+  const int SA = tsum, SB = nImageSum, N = 64;
+  return ((2 * SA * SB - SA * SA - SB * SB) / N + nImageSumSq + tsumsq - 2 * nCrossSum);
+}
+
+/* src/PatchFinder.cc:229-355.  corners in level coordinates, raster order, with row LUT. */
+int ora_find_patch_coarse(const uint8_t* im, int w, int h, int stride, const int32_t* cxy, int nc,
+                          const int32_t* lut, const uint8_t* t, int level, int px, int py, int range_in,
+                          int exhaustive, int32_t* best_xy, int32_t* score)
+{
+  const int max_ssd = 8 * 8 * 250;                               /* :44,61 */
+  int tsum = 0, tsumsq = 0;
+  for (int i = 0; i < 64; i++) { tsum += t[i]; tsumsq += t[i] * t[i]; }
+  const int ls = 1 << level;
+  px = px / ls; py = py / ls;
+  const unsigned nRange = ((unsigned)range_in + ls - 1) / ls;
+  int nTop = py - (int)nRange, nBottomPlusOne = py + (int)nRange + 1, nLeft = px - (int)nRange, nRight = px + (int)nRange;
+  *score = max_ssd + 1;
+  best_xy[0] = best_xy[1] = 0;
+  if (nTop < 0) nTop = 0;
+  if (nTop >= h) return 0;
+  if (nBottomPlusOne <= 0) return 0;
+  if (nLeft < 0) nLeft = 0;
+  if (nLeft >= w) return 0;
+  int bx = 0, by = 0, nBest = max_ssd + 1;
+  if (exhaustive) {
+    for (int y = nTop; y < nBottomPlusOne && y < h; y++)
+      for (int x = nLeft; x <= nRight && x < w; x++) {
+        if ((unsigned)((px - x) * (px - x) + (py - y) * (py - y)) > nRange * nRange) continue;
+        const int s = ora_zmssd(im, w, h, stride, t, tsum, tsumsq, x, y, max_ssd);
+        if (s < nBest) { bx = x; by = y; nBest = s; }
+      }
+  } else {
+    int i = lut[nTop];
+    const int i_end = nBottomPlusOne >= h ? nc : lut[nBottomPlusOne];
+    for (; i < i_end; i++) {
+      const int x = cxy[2 * i], y = cxy[2 * i + 1];
+      if (x < nLeft || x > nRight) continue;
+      if ((unsigned)((px - x) * (px - x) + (py - y) * (py - y)) > nRange * nRange) continue;
+      const int s = ora_zmssd(im, w, h, stride, t, tsum, tsumsq, x, y, max_ssd);
+      if (s < nBest) { bx = x; by = y; nBest = s; }
+    }
+  }
+  *score = nBest;
+  if (nBest < max_ssd) { best_xy[0] = bx; best_xy[1] = by; return 1; }
+  return 0;
+}
+
+/* [3P] TooN::Cholesky<3> (LDL^T, no square roots) and get_inverse() = backsub(Identity) */
+static void toon_chol3_inverse(const double* A, double* inv)
+{
+  double c[9];
+  memcpy(c, A, sizeof(c));
+  for (int col = 0; col < 3; col++) {
+    double inv_diag = 1;
+    for (int row = col; row < 3; row++) {
+      double val = c[row * 3 + col];
+      for (int col2 = 0; col2 < col; col2++) val -= c[col2 * 3 + col] * c[row * 3 + col2];
+      if (row == col) { c[row * 3 + col] = val; if (val == 0) goto factored; inv_diag = 1 / val; }
+      else { c[col * 3 + row] = val; c[row * 3 + col] = val * inv_diag; }
+    }
+  }
+factored:
+  for (int k = 0; k < 3; k++) {
+    double v[3] = { 0, 0, 0 }, y[3], r[3];
+    v[k] = 1;
+    for (int i = 0; i < 3; i++) { double val = v[i]; for (int j = 0; j < i; j++) val -= c[i * 3 + j] * y[j]; y[i] = val; }
+    for (int i = 0; i < 3; i++) y[i] /= c[i * 3 + i];
+    for (int i = 2; i >= 0; i--) { double val = y[i]; for (int j = i + 1; j < 3; j++) val -= c[j * 3 + i] * r[j]; r[i] = val; }
+    inv[0 * 3 + k] = r[0]; inv[1 * 3 + k] = r[1]; inv[2 * 3 + k] = r[2];
+  }
+}
+
+/* src/PatchFinder.cc:362-470 */
+int ora_subpix(const uint8_t* im, int w, int h, int stride, const uint8_t* t, int level, double* pos, int max_its)
+{
+  float jx[36], jy[36];
+  double H[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 }, Hinv[9];
+  for (int x = 1; x < 7; x++)                                     /* loop order as in :367-379 */
+    for (int y = 1; y < 7; y++) {
+      const double gx = 0.5 * (t[y * 8 + x + 1] - t[y * 8 + x - 1]);
+      const double gy = 0.5 * (t[(y + 1) * 8 + x] - t[(y - 1) * 8 + x]);
+      jx[(y - 1) * 6 + (x - 1)] = (float)gx;
+      jy[(y - 1) * 6 + (x - 1)] = (float)gy;
+      const double g[3] = { gx, gy, 1.0 };
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) H[r * 3 + c] += g[r] * g[c];
+    }
+  toon_chol3_inverse(H, Hinv);
+  double mean_diff = 0.0;
+  const int ls = 1 << level;
+  for (int it = 0; it < max_its; it++) {
+    const double cxl = (pos[0] + 0.5) / ls - 0.5, cyl = (pos[1] + 0.5) / ls - 0.5;   /* LevelNPos */
+    const int rx = (int)(cxl > 0.0 ? cxl + 0.5 : cxl - 0.5), ry = (int)(cyl > 0.0 ? cyl + 0.5 : cyl - 0.5);
+    if (!(rx >= 5 && ry >= 5 && rx < w - 5 && ry < h - 5)) return 0;                 /* border 8/2+1 */
+    const double bx = cxl - 4, by = cyl - 4;
+    double acc[3] = { 0, 0, 0 };
+    const double dX = bx - floor(bx), dY = by - floor(by);
+    const float fMixTL = (float)((1.0 - dX) * (1.0 - dY));
+    const float fMixTR = (float)((dX) * (1.0 - dY));
+    const float fMixBL = (float)((1.0 - dX) * (dY));
+    const float fMixBR = (float)((dX) * (dY));
+    const int ibx = (int)bx, iby = (int)by;
+    for (int y = 1; y < 7; y++) {
+      const uint8_t* tl = im + (size_t)(iby + y) * stride + ibx + 1;
+      for (int x = 1; x < 7; x++) {
+        const float fPixel = fMixTL * tl[0] + fMixTR * tl[1] + fMixBL * tl[stride] + fMixBR * tl[stride + 1];
+        tl++;
+        const double dDiff = fPixel - t[y * 8 + x] + mean_diff;
+        acc[0] += dDiff * jx[(y - 1) * 6 + (x - 1)];
+        acc[1] += dDiff * jy[(y - 1) * 6 + (x - 1)];
+        acc[2] += dDiff;
+      }
+    }
+    double upd[3];
+    for (int r = 0; r < 3; r++) upd[r] = Hinv[r * 3 + 0] * acc[0] + Hinv[r * 3 + 1] * acc[1] + Hinv[r * 3 + 2] * acc[2];
+    pos[0] -= upd[0] * ls;
+    pos[1] -= upd[1] * ls;
+    mean_diff -= upd[2];
+    const double u2 = upd[0] * upd[0] + upd[1] * upd[1];
+    if (u2 < 0) return 0;
+    if (u2 < 0.03 * 0.03) return 1;
+  }
+  return 0;
+}
+
+/* src/MiniPatch.cc:34-57 (9x9, mnHalfPatchSize 4, mnMaxSSD 9999) */
+int ora_minipatch_ssd(const uint8_t* im, int w, int h, int stride, const uint8_t* patch, int x, int y)
+{
+  if (!(x >= 4 && y >= 4 && x < w - 4 && y < h - 4)) return 9999 + 1;
+  int s = 0;
+  for (int r = 0; r < 9; r++) {
+    const uint8_t* ip = im + (size_t)(y - 4 + r) * stride + (x - 4);
+    for (int c = 0; c < 9; c++) { const int d = ip[c] - patch[r * 9 + c]; s += d * d; }
+  }
+  return s;
+}
+/* src/MiniPatch.cc:61-113 */
+int ora_minipatch_find(const uint8_t* im, int w, int h, int stride, const uint8_t* patch, const int32_t* cxy, int nc,
+                       const int32_t* lut, int n_lut, int range, int32_t* pos)
+{
+  int bx = 0, by = 0, nBest = 9999 + 1;
+  const int tlx = pos[0] - range, tly = pos[1] - range, brx = pos[0] + range, bry = pos[1] + range;
+  int i = 0;
+  if (!lut) { for (i = 0; i < nc; i++) if (cxy[2 * i + 1] >= tly) break; }
+  else {
+    int top = tly;
+    if (top < 0) top = 0;
+    if (top >= n_lut) top = n_lut - 1;
+    i = lut[top];
+  }
+  for (; i < nc; i++) {
+    const int x = cxy[2 * i], y = cxy[2 * i + 1];
+    if (x < tlx || x > brx) continue;
+    if (y > bry) break;
+    const int s = ora_minipatch_ssd(im, w, h, stride, patch, x, y);
+    if (s < nBest) { bx = x; by = y; nBest = s; }
+  }
+  if (nBest < 9999) { pos[0] = bx; pos[1] = by; return 1; }
+  return 0;
+}

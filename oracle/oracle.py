@@ -1,0 +1,180 @@
+"""ctypes loader for the CPU oracle (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  PARITY UNPINNED (see oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("ba_oracle.c", "fe_oracle.c", "oracle.h", "Makefile")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class BaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("total_trials", C.c_int32), ("converged", C.c_int32),
+                ("hit_max_iter", C.c_int32), ("n_outliers", C.c_int32), ("pad_", C.c_int32),
+                ("sigma_sq", C.c_double), ("mean_chi2", C.c_double), ("lambda_", C.c_double),
+                ("max_cov", C.c_double), ("chi2_before", C.c_double), ("chi2_after", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        L = _lib
+        L.ora_ba_create.restype = C.c_void_p
+        L.ora_ba_create.argtypes = [C.c_int, C.c_int]
+        L.ora_ba_destroy.argtypes = [C.c_void_p]
+        L.ora_ba_set_cameras.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ora_ba_load.argtypes = [C.c_void_p] + [C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5
+        L.ora_ba_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.POINTER(BaStats)]
+        for f in ("ora_ba_get_poses", "ora_ba_get_points", "ora_ba_set_poses", "ora_ba_set_points"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+        L.ora_ba_get_outliers.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ora_ba_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_ba_jacobians.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_ba_oplus_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ora_ba_oplus_point.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ora_ba_lm_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_huber_sigma_sq.restype = C.c_double
+        L.ora_huber_sigma_sq.argtypes = [C.c_void_p, C.c_int]
+        L.ora_tukey_sigma_sq.restype = C.c_double
+        L.ora_tukey_sigma_sq.argtypes = [C.c_void_p, C.c_int]
+        L.ora_cam_project.argtypes = [C.c_void_p] * 4
+        L.ora_cam_sphere_deriv.argtypes = [C.c_void_p] * 3
+        L.ora_cam_unproject.argtypes = [C.c_void_p] * 3
+        L.ora_se3_exp.argtypes = [C.c_void_p] * 2
+        L.ora_so3_exp.argtypes = [C.c_void_p] * 2
+        # front end
+        L.ora_halfsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        for f in ("ora_fast10_detect", "ora_fast10_detect_bruteforce"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.ora_fastN_detect_bruteforce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        for f in ("ora_fast10_score", "ora_fast10_score_bisect"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ora_level_corners.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_shitomasi.restype = C.c_double
+        L.ora_shitomasi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ora_patch_template.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.ora_zmssd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 5
+        L.ora_find_patch_coarse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+        L.ora_subpix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ora_minipatch_ssd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.ora_minipatch_find.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def cam_array(cams):
+    arr = (type(cams[0]) * len(cams))()
+    for i, c in enumerate(cams):
+        C.memmove(C.byref(arr[i]), C.byref(c), C.sizeof(c))
+    return arr
+
+
+class OracleBA:
+    """Thin object wrapper over the ora_ba_* functions."""
+
+    def __init__(self, prob, use_robust=True, use_tukey=True):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.ora_ba_create(int(use_robust), int(use_tukey)))
+        self.prob = prob
+        self._cams = cam_array(prob.cams)
+        self.L.ora_ba_set_cameras(self.h, len(prob.cams), C.cast(self._cams, C.c_void_p))
+        self._keep = [np.ascontiguousarray(prob.pose_Rt, np.float64), np.ascontiguousarray(prob.pose_fixed, np.uint8),
+                      np.ascontiguousarray(prob.pt_xyz, np.float64), np.ascontiguousarray(prob.pt_chain, np.int32),
+                      np.ascontiguousarray(prob.pt_fixed, np.uint8), np.ascontiguousarray(prob.meas_xy, np.float64),
+                      np.ascontiguousarray(prob.meas_chain, np.int32), np.ascontiguousarray(prob.meas_pt, np.int32),
+                      np.ascontiguousarray(prob.meas_noise, np.float64), np.ascontiguousarray(prob.meas_cam, np.int32)]
+        k = self._keep
+        rc = self.L.ora_ba_load(self.h, prob.n_pose, _p(k[0]), _p(k[1]), prob.n_pt, _p(k[2]), _p(k[3]), _p(k[4]),
+                                prob.n_meas, _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]))
+        if rc != 0:
+            raise RuntimeError("ora_ba_load failed: %d" % rc)
+        self.n_pose_var = int((np.asarray(prob.pose_fixed) == 0).sum())
+        self.n_pt_var = int((np.asarray(prob.pt_fixed) == 0).sum())
+
+    def __del__(self):
+        try:
+            self.L.ora_ba_destroy(self.h)
+        except Exception:
+            pass
+
+    def compute(self, n_iter=100, user_lambda=-1.0, solve_mode=0, abort=None):
+        st = BaStats()
+        ab = np.zeros(1, np.uint8) if abort is None else abort
+        rc = self.L.ora_ba_compute(self.h, _p(ab), n_iter, float(user_lambda), solve_mode, C.byref(st))
+        return rc, st
+
+    def poses(self):
+        o = np.zeros((self.prob.n_pose, 12))
+        self.L.ora_ba_get_poses(self.h, _p(o))
+        return o
+
+    def points(self):
+        o = np.zeros((self.prob.n_pt, 3))
+        self.L.ora_ba_get_points(self.h, _p(o))
+        return o
+
+    def set_state(self, poses, points):
+        poses = np.ascontiguousarray(poses, np.float64)
+        points = np.ascontiguousarray(points, np.float64)
+        self.L.ora_ba_set_poses(self.h, _p(poses))
+        self.L.ora_ba_set_points(self.h, _p(points))
+
+    def outliers(self):
+        o = np.zeros(self.prob.n_meas, np.int32)
+        n = self.L.ora_ba_get_outliers(self.h, _p(o), len(o))
+        return o[:n].copy()
+
+    def eval(self):
+        e = np.zeros((self.prob.n_meas, 2))
+        c = np.zeros(self.prob.n_meas)
+        self.L.ora_ba_eval(self.h, _p(e), _p(c))
+        return e, c
+
+    def jacobians(self, m):
+        jo = np.zeros((2, 2, 6)); js = np.zeros((2, 2, 6)); jp = np.zeros((2, 3))
+        self.L.ora_ba_jacobians(self.h, int(m), _p(jo), _p(js), _p(jp))
+        return jo, js, jp
+
+    def oplus_pose(self, i, d):
+        d = np.ascontiguousarray(d, np.float64)
+        self.L.ora_ba_oplus_pose(self.h, int(i), _p(d))
+
+    def oplus_point(self, i, d):
+        d = np.ascontiguousarray(d, np.float64)
+        self.L.ora_ba_oplus_point(self.h, int(i), _p(d))
+
+    def lm_step(self, lam, sigma_sq=-1.0, solve_mode=0):
+        d = np.zeros(6 * self.n_pose_var + 3 * self.n_pt_var)
+        s = C.c_double(); r = C.c_double()
+        rc = self.L.ora_ba_lm_step(self.h, float(lam), float(sigma_sq), solve_mode, _p(d), C.byref(s), C.byref(r))
+        return rc, d, s.value, r.value
