@@ -83,6 +83,7 @@ def lib():
         L.mcp_ba_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcp_ba_debug_jacobians.argtypes = [C.c_void_p, C.c_void_p]
         L.mcp_ba_lm_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.mcp_ba_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.mcp_ba_get_timing.argtypes = [C.c_void_p, C.POINTER(BaTiming)]
         _lib = L
@@ -200,6 +201,11 @@ class BaHandle:
         r = C.c_double()
         check(self.L.mcp_ba_lm_step(self.h, float(lam), float(sigma_sq), _p(d), C.byref(s), C.byref(r)))
         return d, s.value, r.value
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        check(self.L.mcp_ba_get_stream(self.h, C.byref(p)))
+        return int(p.value or 0)
 
     def set_profiling(self, on=True):
         check(self.L.mcp_ba_set_profiling(self.h, int(on)))

@@ -717,6 +717,7 @@ int mcp_ba_debug_jacobians(McpBa* h, double* J30)
   return MCP_OK;
 }
 
+int mcp_ba_get_stream(McpBa* h, void** out) { if (!h || !out) return MCP_ERR_INVALID; *out = (void*)h->stream; return MCP_OK; }
 int mcp_ba_set_profiling(McpBa* h, int32_t enable) { if (!h) return MCP_ERR_INVALID; h->profiling = enable != 0; return MCP_OK; }
 int mcp_ba_get_timing(McpBa* h, McpBaTiming* out) { if (!h || !out) return MCP_ERR_INVALID; *out = h->timing; return MCP_OK; }
 
