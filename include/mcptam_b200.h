@@ -147,6 +147,8 @@ typedef struct McpBaTiming {   /* accumulated over the last mcp_ba_compute, mill
   double ms_select, ms_linearize, ms_schur, ms_solve, ms_backsub, ms_control, ms_other;
   int32_t n_select, n_linearize, n_schur, n_solve, n_backsub, n_control, n_other, pad_;
 } McpBaTiming;
+/* out == NULL arms a per-task timestamp trace of the dense solver; a later call with out != NULL reads it. */
+int mcp_ba_debug_solve_trace(McpBa* h, double* out, int32_t cap_doubles);
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, for external event timing. */
 int mcp_ba_get_stream(McpBa* h, void** cuda_stream);
 int mcp_ba_set_profiling(McpBa* h, int32_t enable);   /* per-kernel CUDA events (adds sync overhead) */

@@ -83,6 +83,7 @@ def lib():
         L.mcp_ba_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcp_ba_debug_jacobians.argtypes = [C.c_void_p, C.c_void_p]
         L.mcp_ba_lm_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mcp_ba_debug_solve_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.mcp_ba_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.mcp_ba_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.mcp_ba_get_timing.argtypes = [C.c_void_p, C.POINTER(BaTiming)]
@@ -201,6 +202,14 @@ class BaHandle:
         r = C.c_double()
         check(self.L.mcp_ba_lm_step(self.h, float(lam), float(sigma_sq), _p(d), C.byref(s), C.byref(r)))
         return d, s.value, r.value
+
+    def solve_trace(self, arm=False):
+        if arm:
+            check(self.L.mcp_ba_debug_solve_trace(self.h, None, 0))
+            return None
+        o = np.zeros(8 * 2048)
+        check(self.L.mcp_ba_debug_solve_trace(self.h, _p(o), len(o)))
+        return o.reshape(-1, 8)
 
     def stream(self) -> int:
         p = C.c_void_p()

@@ -29,12 +29,15 @@ void set_last_error(const char* fmt, ...)
 int launch_linearize(const BaDev& d, bool schur, int warps, size_t smem, cudaStream_t s);
 int launch_schur_only(const BaDev& d, int warps, size_t smem, cudaStream_t s);
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
-void launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s);
+int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
 void launch_lambda_init(const BaDev& d, cudaStream_t s);
 void launch_lambda_apply(const BaDev& d, cudaStream_t s);
-void launch_solve(const BaDev& d, cudaStream_t s);
-size_t solve_smem_bytes(int nc);
+void launch_chol_solve(const BaDev& d, int epoch, int n_sms, cudaStream_t s);
+size_t chol_tiles_doubles(int nc);
+size_t chol_inv_doubles(int nc);
+size_t chol_flag_ints(int nc);
+int chol_max_n();
 void launch_lm_control(const BaDev& d, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s);
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
@@ -78,7 +81,8 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[2], b_pt[2], b_chi2[2], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel;
+  int chol_epoch = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
   BaCtrl* ctrl_host = nullptr;   // pinned
   int* flags_host = nullptr;     // pinned, n_meas
@@ -128,6 +132,7 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   if (cfg) h->cfg = *cfg; else mcp_ba_default_config(&h->cfg);
   if (h->cfg.device >= 0) { MCP_CUDA_CHECK(cudaSetDevice(h->cfg.device)); }
   MCP_CUDA_CHECK(cudaGetDevice(&h->device));
+  { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->n_sms = sms; }
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev0));
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
@@ -147,7 +152,7 @@ int mcp_ba_destroy(McpBa* h)
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_pose[0],
                     &h->b_pose[1], &h->b_pt[0], &h->b_pt[1], &h->b_chi2[0], &h->b_chi2[1], &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel };
   for (DevBuf* b : all) b->release();
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
   if (h->flags_host) cudaFreeHost(h->flags_host);
@@ -294,8 +299,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   pt_slot_off[n_pt] = (int)slot_var.size();
   const int n_slots = (int)slot_var.size();
   const int nc = 6 * npv;
-  if (solve_smem_bytes(nc) > 220 * 1024) {
-    set_last_error("mcp_ba_load: %d movable poses exceed the single-CTA solver capacity", npv);
+  if (nc > chol_max_n()) {
+    set_last_error("mcp_ba_load: %d movable poses exceed the dense solver capacity (%d rows)", npv, chol_max_n());
     return MCP_ERR_UNSUPPORTED;
   }
   cudaSetDevice(h->device);
@@ -329,7 +334,16 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   h->acc_doubles = h->off_rm + ncp;
   if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
   if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
-  if ((rc = h->b_L.ensure(sizeof(double) * ncp * ncp))) return rc;
+  if ((rc = h->b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
+  if ((rc = h->b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
+  if ((rc = h->b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
+  h->chol_epoch = 0;
+  {
+    const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1);
+    if ((rc = h->b_sel.ensure(sel_bytes))) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_sel.p, 0, sel_bytes, h->stream));
+  }
   if ((rc = h->b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
   if ((rc = h->b_ctrl.ensure(sizeof(BaCtrl)))) return rc;
   if ((rc = h->b_flags.ensure(sizeof(int) * (size_t)std::max(n_meas, 1)))) return rc;
@@ -358,7 +372,10 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>();
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
-  d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.part = h->b_part.as<double>();
+  d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
+  d.sel_state = h->b_sel.as<unsigned long long>();
+  d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
+  d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();
   d.ctrl = h->b_ctrl.as<BaCtrl>(); d.outlier_flags = h->b_flags.as<int>();
 
   BaCtrl& c = *h->ctrl_host;
@@ -454,7 +471,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   // errors of the initial state, sigma, "BEFORE" chi2 (src/ChainBundle.cc:1317-1323)
   eval_state(h, -1, nullptr);
   if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
-  if (h->cfg.use_robust && !(single_step && step_sigma_sq >= 0)) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+  if (h->cfg.use_robust && !(single_step && step_sigma_sq >= 0)) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
   if (single_step && step_sigma_sq >= 0) {
     if ((rc = sync_ctrl(h))) return rc;
     c.sigma_sq_raw = step_sigma_sq;
@@ -482,7 +499,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   for (int it = 0; it < n_iter && !local_abort && !aborted() && ok; it++) {
     if (it > 0) {
       if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
-      if (h->cfg.use_robust) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+      if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
     }
     MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
     if (c.need_lambda_init) {
@@ -506,7 +523,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     }
     bool first = true;
     for (;;) {
-      { Prof p(h, C_SOLVE); launch_solve(d, s); }
+      { Prof p(h, C_SOLVE); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
       { Prof p(h, C_BACKSUB); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
       if (multi) {
         launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
@@ -537,7 +554,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   // "AFTER" block (src/ChainBundle.cc:1338-1345): errors + sigma of the final state
   eval_state(h, -1, nullptr);
   if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
-  if (h->cfg.use_robust) { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 0, s); }
+  if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
   n_bs = launch_backsub_eval(d, 0, -1, nullptr, s); h->launches++;
   launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
   if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 1, ncclDouble, ncclSum, h->comm, s));
@@ -561,7 +578,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   if (counter == 0 && abort_now) return 0;
 
   if (h->cfg.use_tukey && d.n_meas > 0) {        // src/ChainBundle.cc:1368-1399
-    { Prof p(h, C_SELECT); launch_select_sigma(d, -1, 1, s); }
+    { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 1, s) - 1; }
     { Prof p(h, C_OTHER); launch_tukey_flags(d, s); }
     MCP_CUDA_CHECK(cudaMemcpyAsync(h->flags_host, d.outlier_flags, sizeof(int) * (size_t)d.n_meas, cudaMemcpyDeviceToHost, s));
     MCP_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -717,6 +734,26 @@ int mcp_ba_debug_jacobians(McpBa* h, double* J30)
   return MCP_OK;
 }
 
+/* Debug: per-task timestamps of the next k_chol_solve launches (8 doubles per task: i, j, t_start, t_deps, t_end, cta) */
+int mcp_ba_debug_solve_trace(McpBa* h, double* out, int32_t cap_doubles)
+{
+  if (!h || !h->loaded) return MCP_ERR_STATE;
+  cudaSetDevice(h->device);
+  const size_t nd = 8 * 2048;
+  if (!out) {   // arm
+    int rc = h->b_dbg.ensure(sizeof(double) * nd);
+    if (rc) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_dbg.p, 0, sizeof(double) * nd, h->stream));
+    h->d.dbg = h->b_dbg.as<double>();
+    return MCP_OK;
+  }
+  if (!h->d.dbg) return MCP_ERR_STATE;
+  const size_t n = std::min((size_t)cap_doubles, nd);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, h->b_dbg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->d.dbg = nullptr;
+  return MCP_OK;
+}
 int mcp_ba_get_stream(McpBa* h, void** out) { if (!h || !out) return MCP_ERR_INVALID; *out = (void*)h->stream; return MCP_OK; }
 int mcp_ba_set_profiling(McpBa* h, int32_t enable) { if (!h) return MCP_ERR_INVALID; h->profiling = enable != 0; return MCP_OK; }
 int mcp_ba_get_timing(McpBa* h, McpBaTiming* out) { if (!h || !out) return MCP_ERR_INVALID; *out = h->timing; return MCP_OK; }

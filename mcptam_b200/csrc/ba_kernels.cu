@@ -548,68 +548,90 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_select_sigma: exact element [n/2] of sorted |chi2| by MSB-first radix select, one block.
-// mode 0: Huber sigma (RecomputeNow), mode 1: Tukey sigma (outlier pass).
+// k_sel_pass: exact element [n/2] of sorted |chi2| by MSB-first radix select (6 digits of 11 bits).
+// One launch per digit, many blocks; the last block to finish a pass (ticket counter) scans the global
+// histogram, narrows (prefix, rank) for the next pass and re-arms the histogram.  The last block of the
+// last pass turns the median into the Huber (mode 0) or Tukey (mode 1) sigma^2
+// (include/mcptam/MEstimator.h:109-126,194-204; src/ChainBundle.cc:810-833, 1376-1383).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_select_sigma(BaDev d, int which_in, int mode)
+__global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pass, int mode)
 {
   __shared__ unsigned hist[SEL_BINS];
-  __shared__ unsigned long long s_prefix;
-  __shared__ unsigned s_rank;
+  __shared__ unsigned wsum[8];
+  __shared__ int s_last;
   BaCtrl* ctrl = d.ctrl;
   const int which = which_in < 0 ? ctrl->cur : which_in;
   const double* __restrict__ v = d.chi2[which];
   const int n = d.n_meas;
-  if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = (unsigned)(n / 2); }
-  // key = bits of |chi2| with the sign bit dropped -> 63 significant bits, digits taken MSB first
-  for (int pass = 0; pass < SEL_PASSES; pass++) {
-    const int shift = 63 - SEL_BITS * (pass + 1);        // 52, 41, 30, 19, 8, -3
-    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const unsigned long long prefix = s_prefix;
-    for (int base = 0; base < n; base += blockDim.x) {
-      const int i = base + threadIdx.x;
-      bool match = false;
-      unsigned dig = 0;
-      if (i < n) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v[i]));
-        unsigned long long hi;
-        if (shift >= 0) { hi = key >> (shift + SEL_BITS); dig = (unsigned)(key >> shift) & (SEL_BINS - 1); }
-        else { hi = key >> (SEL_BITS + shift); dig = (unsigned)(key << (-shift)) & (SEL_BINS - 1); }
-        match = (pass == 0) || (hi == prefix);
-      }
-      const unsigned act = __ballot_sync(0xffffffffu, match);
-      if (match) {
-        const unsigned peers = __match_any_sync(act, dig);
-        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[dig], (unsigned)__popc(peers));
-      }
+  unsigned long long* state = d.sel_state;            // [2*pass] = prefix, [2*pass+1] = rank
+  const unsigned long long prefix = pass == 0 ? 0ull : __ldcg(&state[2 * pass]);
+  const int shift = 63 - SEL_BITS * (pass + 1);       // 52, 41, 30, 19, 8, -3
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool match = false;
+    unsigned dig = 0;
+    if (i < n) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v[i]));
+      unsigned long long hi;
+      if (shift >= 0) { hi = key >> (shift + SEL_BITS); dig = (unsigned)(key >> shift) & (SEL_BINS - 1); }
+      else { hi = key >> (SEL_BITS + shift); dig = (unsigned)(key << (-shift)) & (SEL_BINS - 1); }
+      match = (pass == 0) || (hi == prefix);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned r = s_rank, acc = 0; int b = 0;
-      for (b = 0; b < SEL_BINS; b++) { if (acc + hist[b] > r) break; acc += hist[b]; }
-      if (b >= SEL_BINS) b = SEL_BINS - 1;
-      s_rank = r - acc;
-      s_prefix = (shift >= 0) ? ((prefix << SEL_BITS) | (unsigned)b) : ((prefix << (SEL_BITS + shift)) | ((unsigned)b >> (-shift)));
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double med = __longlong_as_double((long long)s_prefix);
-    const size_t denom = (size_t)n * 2 - 6;                       // size_t arithmetic as in the reference
-    double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
-    if (mode == 0) {
-      s = 1.345 * s;
-      ctrl->sigma_sq_raw = s * s;
-      ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
-      ctrl->sigma_lim = sqrt(ctrl->sigma_sq_lim);
-    } else {
-      s = 4.6851 * s;
-      double t = s * s;
-      if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq;
-      ctrl->tukey_sigma_sq = t;
+    const unsigned act = __ballot_sync(0xffffffffu, match);
+    if (match) {
+      const unsigned peers = __match_any_sync(act, dig);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[dig], (unsigned)__popc(peers));
     }
   }
+  __syncthreads();
+  unsigned* ghist = d.sel_hist + pass * SEL_BINS;
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&d.sel_done[pass], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: locate the bin holding the wanted rank ------------------------------------------
+  const unsigned rank = pass == 0 ? (unsigned)(n / 2) : (unsigned)__ldcg(&state[2 * pass + 1]);
+  unsigned loc[8], tsum = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { loc[q] = __ldcg(&ghist[threadIdx.x * 8 + q]); tsum += loc[q]; ghist[threadIdx.x * 8 + q] = 0; }
+  // exclusive scan of the 256 per-thread sums
+  unsigned incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wsum[w];
+  const unsigned excl = woff + incl - tsum;
+  if (rank >= excl && rank < excl + tsum) {
+    unsigned acc = excl; int b = 0;
+    for (b = 0; b < 8; b++) { if (acc + loc[b] > rank) break; acc += loc[b]; }
+    const unsigned bin = threadIdx.x * 8 + b;
+    const unsigned long long np = (shift >= 0) ? ((prefix << SEL_BITS) | bin) : ((prefix << (SEL_BITS + shift)) | (bin >> (-shift)));
+    if (pass + 1 < SEL_PASSES) { state[2 * (pass + 1)] = np; state[2 * (pass + 1) + 1] = rank - acc; }
+    else {
+      const double med = __longlong_as_double((long long)np);
+      const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
+      double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
+      if (mode == 0) {
+        s = 1.345 * s;
+        ctrl->sigma_sq_raw = s * s;
+        ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
+        ctrl->sigma_lim = sqrt(ctrl->sigma_sq_lim);
+      } else {
+        s = 4.6851 * s;
+        double t = s * s;
+        if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq;
+        ctrl->tukey_sigma_sq = t;
+      }
+    }
+  }
+  if (threadIdx.x == 0) d.sel_done[pass] = 0;
 }
 
 // Tukey outlier flags (src/ChainBundle.cc:1385-1398)
@@ -652,188 +674,6 @@ __global__ void k_lambda_apply(BaDev d)
     c->lambda = c->user_lambda > 0 ? c->user_lambda : 1e-5 * c->max_diag;
     c->ni = 2;
     c->need_lambda_init = 0;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_solve: single CTA blocked Cholesky of A = H0 + lambda I - Sm (upper triangles), solve, pose update.
-// ---------------------------------------------------------------------------------------------
-constexpr int NB = 32;
-
-__global__ void __launch_bounds__(1024) k_solve(BaDev d)
-{
-  extern __shared__ double sm[];          // panel [rows][NB+1] + tile [NB][NB+1] + vec
-  __shared__ int s_ok;
-  __shared__ double red[32];
-  BaCtrl* ctrl = d.ctrl;
-  const int n = d.nc;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const double lambda = ctrl->lambda;
-  double* L = d.L;
-  if (tid == 0) s_ok = ctrl->solve_ok;
-  // assemble lower triangle (row-major): L[i][j] = H0u[j][i] - Smu[j][i] (+lambda on the diagonal)
-  for (size_t idx = tid; idx < (size_t)n * n; idx += blockDim.x) {
-    const int i = (int)(idx / n), j = (int)(idx - (size_t)i * n);
-    if (j <= i) {
-      double v = d.H0[(size_t)j * n + i] - d.Sm[(size_t)j * n + i];
-      if (i == j) v += lambda;
-      L[idx] = v;
-    }
-  }
-  __syncthreads();
-  double* panel = sm;                               // [(n - k0)][NB+1]
-  const int PLD = NB + 1;
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int kb = min(NB, n - k0);
-    const int rows = n - k0;
-    double* tile = panel + (size_t)rows * PLD;      // [NB][NB+1]
-    // load panel
-    for (int idx = tid; idx < rows * kb; idx += blockDim.x) {
-      const int r = idx / kb, cc = idx - r * kb;
-      panel[r * PLD + cc] = (cc <= r || r >= kb) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
-    }
-    __syncthreads();
-    // panel -= L[k0+r][0:k0] * L[k0+c][0:k0]^T, processed in K-chunks of NB staged through `tile`
-    for (int kc = 0; kc < k0; kc += NB) {
-      for (int idx = tid; idx < kb * NB; idx += blockDim.x) {
-        const int r = idx / NB, cc = idx - r * NB;
-        tile[r * PLD + cc] = L[(size_t)(k0 + r) * n + kc + cc];
-      }
-      __syncthreads();
-      for (int r = wid; r < rows; r += nw) {
-        const double lv = L[(size_t)(k0 + r) * n + kc + lane];
-        if (lane < kb) {
-          double acc = 0;
-#pragma unroll 8
-          for (int k = 0; k < NB; k++) acc += __shfl_sync(0xffffffffu, lv, k) * tile[lane * PLD + k];
-          panel[r * PLD + lane] -= acc;
-        } else {
-#pragma unroll 8
-          for (int k = 0; k < NB; k++) (void)__shfl_sync(0xffffffffu, lv, k);
-        }
-      }
-      __syncthreads();
-    }
-    // factor the kb x kb diagonal block (warp 0, lane = row)
-    if (wid == 0) {
-      for (int j = 0; j < kb; j++) {
-        double djj = panel[j * PLD + j];
-        if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_ok = 0; djj = 1.0; }
-        const double dj = sqrt(djj);
-        __syncwarp();
-        if (lane == j) panel[j * PLD + j] = dj;
-        if (lane > j && lane < kb) panel[lane * PLD + j] /= dj;
-        __syncwarp();
-        if (lane > j && lane < kb) {
-          const double lij = panel[lane * PLD + j];
-          for (int k = j + 1; k <= lane; k++) panel[lane * PLD + k] -= lij * panel[k * PLD + j];
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // triangular solve of the rows below: x * Ldd^T = row
-    for (int r = kb + tid; r < rows; r += blockDim.x) {
-      double* row = panel + r * PLD;
-      for (int j = 0; j < kb; j++) {
-        double s = row[j];
-        for (int k = 0; k < j; k++) s -= row[k] * panel[j * PLD + k];
-        row[j] = s / panel[j * PLD + j];
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < rows * kb; idx += blockDim.x) {
-      const int r = idx / kb, cc = idx - r * kb;
-      if (cc <= r || r >= kb) L[(size_t)(k0 + r) * n + k0 + cc] = panel[r * PLD + cc];
-    }
-    __syncthreads();
-  }
-  // solve L L^T x = gc - rm, blocked: 32x32 diagonal solves by warp 0, rectangular updates by all threads
-  double* x = sm;
-  double* Ld = sm + n;                                  // [NB][NB+1]
-  for (int i = tid; i < n; i += blockDim.x) x[i] = d.gc[i] - d.rm[i];
-  __syncthreads();
-  for (int k0 = 0; k0 < n; k0 += NB) {                  // forward: L y = b
-    const int kb = min(NB, n - k0);
-    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
-      const int r = idx / kb, cc = idx - r * kb;
-      Ld[r * PLD + cc] = (cc <= r) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
-    }
-    __syncthreads();
-    if (wid == 0) {
-      double xi = lane < kb ? x[k0 + lane] : 0.0;
-      for (int j = 0; j < kb; j++) {
-        if (lane == j) xi /= Ld[j * PLD + j];
-        const double yj = __shfl_sync(0xffffffffu, xi, j);
-        if (lane > j && lane < kb) xi -= Ld[lane * PLD + j] * yj;
-      }
-      if (lane < kb) x[k0 + lane] = xi;
-    }
-    __syncthreads();
-    for (int i = k0 + kb + tid; i < n; i += blockDim.x) {
-      const double* Li = L + (size_t)i * n + k0;
-      double s2 = 0;
-      for (int j = 0; j < kb; j++) s2 += Li[j] * x[k0 + j];
-      x[i] -= s2;
-    }
-    __syncthreads();
-  }
-  for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {   // backward: L^T x = y
-    const int kb = min(NB, n - k0);
-    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
-      const int r = idx / kb, cc = idx - r * kb;
-      Ld[r * PLD + cc] = (cc <= r) ? L[(size_t)(k0 + r) * n + k0 + cc] : 0.0;
-    }
-    __syncthreads();
-    if (wid == 0) {
-      double xi = lane < kb ? x[k0 + lane] : 0.0;
-      for (int j = kb - 1; j >= 0; j--) {
-        if (lane == j) xi /= Ld[j * PLD + j];
-        const double xj = __shfl_sync(0xffffffffu, xi, j);
-        if (lane < j) xi -= Ld[j * PLD + lane] * xj;
-      }
-      if (lane < kb) x[k0 + lane] = xi;
-    }
-    __syncthreads();
-    for (int i = tid; i < k0; i += blockDim.x) {
-      double s2 = 0;
-      for (int j = 0; j < kb; j++) s2 += L[(size_t)(k0 + j) * n + i] * x[k0 + j];
-      x[i] -= s2;
-    }
-    __syncthreads();
-  }
-  const int ok = s_ok;
-  double sc = 0, sq = 0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const double xi = ok ? x[i] : 0.0;
-    d.dc[i] = xi;
-    sc += xi * (lambda * xi + d.gc[i]);
-    sq += xi * xi;
-  }
-  const double scs = block_sum(sc, red);
-  const double sqs = block_sum(sq, red);
-  if (tid == 0) { ctrl->scale = scs; ctrl->sumsq = sqs; ctrl->solve_ok = ok; }
-  __syncthreads();
-  // pose update into the trial buffer (VertexPoseSE3::oplusImpl)
-  const int cur = ctrl->cur;
-  for (int i = tid; i < d.n_pose; i += blockDim.x) {
-    Se3 T;
-    const double* src = d.pose[cur] + 12 * (size_t)i;
-#pragma unroll
-    for (int k = 0; k < 9; k++) T.R[k] = src[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) T.t[k] = src[9 + k];
-    const int v = d.pose_var[i];
-    if (v >= 0) {
-      double mu[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) mu[k] = d.dc[6 * v + k];
-      Se3 E, O;
-      se3_exp(mu, E);
-      se3_mul(E, T, O);
-      T = O;
-    }
-    se3_store(d.pose[cur ^ 1] + 12 * (size_t)i, T);
   }
 }
 
@@ -1005,17 +845,17 @@ int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, c
   k_backsub_eval<<<g, 256, 0, s>>>(d, apply, which, err_out);
   return g;
 }
-void launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s) { k_select_sigma<<<1, 1024, 0, s>>>(d, which, mode); }
+int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
+{
+  int grid = (d.n_meas + 2047) / 2048;
+  if (grid < 1) grid = 1;
+  if (grid > 148) grid = 148;
+  for (int pass = 0; pass < SEL_PASSES; pass++) k_sel_pass<<<grid, 256, 0, s>>>(d, which, pass, mode);
+  return SEL_PASSES;
+}
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
 void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }
 void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
-size_t solve_smem_bytes(int nc)
-{
-  const size_t panel = (size_t)nc * (NB + 1) + (size_t)NB * (NB + 1);
-  const size_t vec = (size_t)nc + (size_t)NB * (NB + 1);
-  return sizeof(double) * (panel > vec ? panel : vec);
-}
-void launch_solve(const BaDev& d, cudaStream_t s) { k_solve<<<1, 1024, solve_smem_bytes(d.nc), s>>>(d); }
 void launch_lm_control(const BaDev& d, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
 {
   k_lm_control<<<1, 256, 0, s>>>(d, n_lin, n_bs, red_in, first_trial);
@@ -1041,8 +881,6 @@ int configure_kernels(int max_slots, int* warps_out, size_t* smem_out)
   e = cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
   if (e != cudaSuccess) return -2;
   e = cudaFuncSetAttribute(k_schur_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-  if (e != cudaSuccess) return -2;
-  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
   if (e != cudaSuccess) return -2;
   *warps_out = warps;
   *smem_out = smem;

@@ -1,0 +1,359 @@
+// ba_solve.cu — dense solve of the damped Schur-reduced camera system  (H0 + lambda I - Sm) dc = gc - rm.
+//
+// Replaces CHOLMOD inside g2o (reference src/ChainBundle.cc:1156) for the pose block.  The matrix is small
+// (6N = 294 at 200 KF, 744 at 1000 KF), so the factorisation is latency bound: it is organised as a tile
+// dataflow (32x32 fp64 tiles, left-looking): every tile of L is one task owned by one persistent CTA which
+// accumulates  A_ij - sum_k L_ik L_jk^T  as the tiles of earlier block columns become ready (acquire/release
+// flags in global memory, L2-resident), then either factors it (diagonal: register Cholesky by one warp +
+// explicit inverse) or multiplies with the inverse diagonal factor (off-diagonal).  The right-hand side rides
+// along as an extra block row, so the forward substitution is part of the same dataflow; the CTA that retires
+// the last task does the backward substitution, the SE3 pose update (VertexPoseSE3::oplusImpl,
+// src/ChainBundle.cc:82-86) and g2o's computeScale() partial sums.
+#include "ba_types.cuh"
+
+namespace mcp {
+
+constexpr int TB = 32;            // tile edge
+constexpr int TLD = TB + 1;       // padded smem stride
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ size_t tile_index(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
+
+// acc(2x2 per thread) -= As * Bs^T over the 32-wide k range
+__device__ __forceinline__ void tile_mm_sub(const double* As, const double* Bs, int ty, int tx, double acc[2][2])
+{
+#pragma unroll 8
+  for (int k = 0; k < TB; k++) {
+    const double a0 = As[ty * TLD + k], a1 = As[(ty + 16) * TLD + k];
+    const double b0 = Bs[tx * TLD + k], b1 = Bs[(tx + 16) * TLD + k];
+    acc[0][0] -= a0 * b0; acc[0][1] -= a0 * b1;
+    acc[1][0] -= a1 * b0; acc[1][1] -= a1 * b1;
+  }
+}
+
+
+// Cholesky of a 32x32 SPD tile held in shared memory (stride TLD), lower triangle in/out, upper zeroed.
+// One warp, lane = row, the row lives in registers; column j is broadcast with shuffles.
+// rinv[j] = 1 / L[j][j].  Returns true if a non-positive pivot was met (pivot replaced by 1).
+__device__ __noinline__ bool potrf32_warp(double* S, double* rinv, int lane)
+{
+  double a[TB];
+#pragma unroll
+  for (int c = 0; c < TB; c++) a[c] = (c <= lane) ? S[lane * TLD + c] : 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int jj = 0; jj < TB; jj++) {
+    double dj = __shfl_sync(0xffffffffu, a[jj], jj);
+    if (!(dj > 0.0) || !(dj < 1.0e300)) { bad = true; dj = 1.0; }
+    const double ri = rsqrt(dj);
+    if (lane == jj) { rinv[jj] = ri; a[jj] = dj * ri; }
+    else if (lane > jj) a[jj] *= ri;
+#pragma unroll
+    for (int c = jj + 1; c < TB; c++) {
+      const double v = __shfl_sync(0xffffffffu, a[jj], c);
+      if (lane >= c) a[c] -= a[jj] * v;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < TB; c++) S[lane * TLD + c] = a[c];
+  return bad;
+}
+
+// Inverse of the lower-triangular 32x32 factor L (shared, stride TLD) into X (shared, stride TLD), by
+// recursive 2x2 blocking: [A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1] with 8x8 leaves.  256 threads.
+// rinv: reciprocals of the diagonal of L; tmp: >= 256 doubles of scratch.
+__device__ __forceinline__ void inverse32_block(const double* L, double* X, const double* rinv, double* tmp, int tid)
+{
+  for (int e = tid; e < TB * TLD; e += 256) X[e] = 0.0;
+  __syncthreads();
+  if (tid < 32) {
+    // leaf: column c of the inverse of diagonal 8x8 block b
+    const int b = tid >> 3, c = tid & 7, o = 8 * b;
+    double x[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; k++) s -= L[(o + r) * TLD + o + k] * ((k >= c) ? x[k] : 0.0);
+      x[r] = (r >= c) ? s * rinv[o + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) X[(o + r) * TLD + o + c] = x[r];
+  }
+  __syncthreads();
+  // level 1: 8x8 off-diagonal blocks of the two 16x16 diagonal blocks:  X10 = -D1inv * (L10 * D0inv)
+  if (tid < 128) {
+    const int h = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7, o = 16 * h;
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m += L[(o + 8 + r) * TLD + o + k] * X[(o + k) * TLD + o + c];
+    tmp[tid] = m;
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int h = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7, o = 16 * h;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v += X[(o + 8 + r) * TLD + o + 8 + k] * tmp[h * 64 + k * 8 + c];
+    X[(o + 8 + r) * TLD + o + c] = -v;
+  }
+  __syncthreads();
+  // level 2: 16x16 off-diagonal block:  X[16:32,0:16] = -Cinv * (B * Ainv)
+  {
+    const int r = tid >> 4, c = tid & 15;
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) m += L[(16 + r) * TLD + k] * X[k * TLD + c];
+    tmp[tid] = m;
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 4, c = tid & 15;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) v += X[(16 + r) * TLD + 16 + k] * tmp[k * 16 + c];
+    __syncthreads();
+    X[(16 + r) * TLD + c] = -v;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base0, int base1)
+{
+  __shared__ double As[TB * TLD];
+  __shared__ double Bs[TB * TLD];
+  __shared__ double xs[32 * TB + 64];     // backsolve vector (up to 32 block rows) + scratch
+  __shared__ double red[32];
+  __shared__ int s_task;
+  const int n = d.nc;
+  const int T = (n + TB - 1) / TB;
+  const int n_tasks = T * (T + 1) / 2 + T;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  BaCtrl* ctrl = d.ctrl;
+  const double lambda = ctrl->lambda;
+  double* Lt = d.L;
+  double* Linv = d.Linv;
+  int* ready = d.flags;
+  int* inv_ready = d.flags + n_tasks;
+  int* ctr = d.flags + n_tasks + T;      // [0] task counter, [1] done counter, [2] fail
+
+  for (;;) {
+    if (tid == 0) s_task = atomicAdd(&ctr[0], 1) - base0;
+    __syncthreads();
+    const int task = s_task;
+    if (task >= n_tasks) break;
+    // task -> (i, j): column-major over block columns; rows j..T (row T = right-hand side)
+    int j = 0, rem = task;
+    while (rem >= T + 1 - j) { rem -= T + 1 - j; j++; }
+    const int i = j + rem;
+    const bool is_rhs = (i == T);
+    unsigned long long t0 = 0, t1 = 0, t2 = 0;
+    if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // ---- initial value ------------------------------------------------------------------------------
+    double acc[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int r = ty + 16 * a, c = tx + 16 * b;
+        const int gc_ = TB * j + c;
+        double v = 0.0;
+        if (is_rhs) {
+          if (r == 0 && gc_ < n) v = d.gc[gc_] - d.rm[gc_];
+        } else {
+          const int gr = TB * i + r;
+          if (gr < n && gc_ < n) {
+            if (gc_ <= gr) {
+              v = d.H0[(size_t)gc_ * n + gr] - d.Sm[(size_t)gc_ * n + gr];
+              if (gr == gc_) v += lambda;
+            }
+          } else if (gr == gc_) v = 1.0;       // identity padding
+        }
+        acc[a][b] = v;
+      }
+    // ---- left-looking updates -----------------------------------------------------------------------
+    for (int k = 0; k < j; k++) {
+      const size_t ta = tile_index(i, k), tb = tile_index(j, k);
+      if (tid == 0) {
+        while (ld_acquire(&ready[ta]) != epoch) { }
+        while (ld_acquire(&ready[tb]) != epoch) { }
+      }
+      __syncthreads();
+      const double* ga = Lt + ta * (TB * TB);
+      const double* gb = Lt + tb * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        As[r * TLD + c] = __ldcg(ga + e);
+        Bs[r * TLD + c] = __ldcg(gb + e);
+      }
+      __syncthreads();
+      tile_mm_sub(As, Bs, ty, tx, acc);
+      __syncthreads();
+    }
+    if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (i == j) {
+      // ---- diagonal tile: Cholesky in registers (warp 0, lane = row), then explicit inverse ------------
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = acc[a][b];
+      __syncthreads();
+      if (wid == 0) {
+        if (potrf32_warp(As, xs + 32 * TB, lane) && lane == 0) atomicExch(&ctr[2], epoch);
+      }
+      __syncthreads();
+      inverse32_block(As, Bs, xs + 32 * TB, xs, tid);
+      __syncthreads();
+      double* gl = Lt + tile_index(j, j) * (TB * TB);
+      double* gi = Linv + (size_t)j * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        gl[e] = As[r * TLD + c];
+        gi[e] = Bs[r * TLD + c];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(&inv_ready[j], epoch);
+        st_release(&ready[tile_index(j, j)], epoch);
+      }
+    } else {
+      // ---- off-diagonal / rhs tile: X = acc * Linv_j^T ------------------------------------------------
+      if (tid == 0) { while (ld_acquire(&inv_ready[j]) != epoch) { } }
+      __syncthreads();
+      const double* gi = Linv + (size_t)j * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) Bs[(e >> 5) * TLD + (e & 31)] = __ldcg(gi + e);
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = acc[a][b];
+      __syncthreads();
+      double out[2][2] = { { 0, 0 }, { 0, 0 } };
+#pragma unroll 8
+      for (int k = 0; k < TB; k++) {
+        const double a0 = As[ty * TLD + k], a1 = As[(ty + 16) * TLD + k];
+        const double b0 = Bs[tx * TLD + k], b1 = Bs[(tx + 16) * TLD + k];
+        out[0][0] += a0 * b0; out[0][1] += a0 * b1;
+        out[1][0] += a1 * b0; out[1][1] += a1 * b1;
+      }
+      double* gx = Lt + tile_index(i, j) * (TB * TB);
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) gx[(ty + 16 * a) * TB + tx + 16 * b] = out[a][b];
+      __syncthreads();
+      if (tid == 0) { __threadfence(); st_release(&ready[tile_index(i, j)], epoch); }
+    }
+    // ---- retire --------------------------------------------------------------------------------------
+    if (d.dbg && tid == 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
+      double* o = d.dbg + 8 * (size_t)task;
+      o[0] = i; o[1] = j; o[2] = (double)(t0 % 1000000000ull); o[3] = (double)(t1 % 1000000000ull); o[4] = (double)(t2 % 1000000000ull); o[5] = blockIdx.x;
+    }
+    __syncthreads();
+    if (tid == 0) s_task = atomicAdd(&ctr[1], 1) - base1;
+    __syncthreads();
+    if (s_task != n_tasks - 1) continue;
+    // ======== last task retired: backward substitution, pose update, scalars (this CTA only) ============
+    __threadfence();
+    for (int k = T - 1; k >= 0; k--) {
+      // s[c] = sum_{i>k} sum_r L_ik[r][c] * x_i[r]
+      double part = 0.0;
+      const int c = lane;
+      for (int ii = k + 1; ii < T; ii++) {
+        const double* g = Lt + tile_index(ii, k) * (TB * TB);
+#pragma unroll
+        for (int r = wid; r < TB; r += 8) part += __ldcg(g + r * TB + c) * xs[ii * TB + r];
+      }
+      double* scratch = xs + 32 * TB;            // 64 doubles
+      __syncthreads();
+      As[wid * TLD + c] = part;
+      __syncthreads();
+      if (wid == 0) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += As[w * TLD + c];
+        const double yk = __ldcg(Lt + tile_index(T, k) * (TB * TB) + c);   // row 0 of the rhs tile
+        scratch[c] = yk - s;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        const double* gi = Linv + (size_t)k * (TB * TB);
+        double s = 0;
+#pragma unroll 8
+        for (int r = 0; r < TB; r++) s += __ldcg(gi + r * TB + c) * scratch[r];   // (Linv^T t)[c]
+        xs[k * TB + c] = s;
+      }
+      __syncthreads();
+    }
+    if (d.dbg && tid == 0) { unsigned long long t3; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3)); d.dbg[8 * (size_t)n_tasks] = (double)(t3 % 1000000000ull); }
+    const int ok = (ld_acquire(&ctr[2]) != epoch) && ctrl->solve_ok;
+    double sc = 0, sq = 0;
+    for (int e = tid; e < n; e += 256) {
+      const double xi = ok ? xs[e] : 0.0;
+      d.dc[e] = xi;
+      sc += xi * (lambda * xi + d.gc[e]);
+      sq += xi * xi;
+    }
+    sc = warp_sum(sc); sq = warp_sum(sq);
+    __syncthreads();
+    if (lane == 0) { red[wid] = sc; red[8 + wid] = sq; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0, b = 0;
+      for (int w = 0; w < 8; w++) { a += red[w]; b += red[8 + w]; }
+      ctrl->scale = a; ctrl->sumsq = b; ctrl->solve_ok = ok;
+    }
+    __syncthreads();
+    const int cur = ctrl->cur;
+    for (int p = tid; p < d.n_pose; p += 256) {
+      Se3 Tm;
+      const double* src = d.pose[cur] + 12 * (size_t)p;
+#pragma unroll
+      for (int q = 0; q < 9; q++) Tm.R[q] = src[q];
+#pragma unroll
+      for (int q = 0; q < 3; q++) Tm.t[q] = src[9 + q];
+      const int v = d.pose_var[p];
+      if (v >= 0) {
+        double mu[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) mu[q] = ok ? xs[6 * v + q] : 0.0;
+        Se3 E, O;
+        se3_exp(mu, E);
+        se3_mul(E, Tm, O);
+        Tm = O;
+      }
+      se3_store(d.pose[cur ^ 1] + 12 * (size_t)p, Tm);
+    }
+    // fall through to the next (failing) grab so that every CTA consumes exactly one id >= n_tasks
+  }
+}
+
+size_t chol_tiles_doubles(int nc) { const int T = (nc + TB - 1) / TB; return (size_t)(T * (T + 1) / 2 + T) * TB * TB; }
+size_t chol_inv_doubles(int nc) { const int T = (nc + TB - 1) / TB; return (size_t)T * TB * TB; }
+size_t chol_flag_ints(int nc) { const int T = (nc + TB - 1) / TB; return (size_t)(T * (T + 1) / 2 + T) + T + 8; }
+int chol_max_n() { return 32 * TB; }
+
+// The task and done counters are never reset: launch number `epoch` (1-based) consumes exactly
+// n_tasks + grid increments of the task counter and n_tasks of the done counter.
+void launch_chol_solve(const BaDev& d, int epoch, int n_sms, cudaStream_t s)
+{
+  const int T = (d.nc + TB - 1) / TB;
+  const int n_tasks = T * (T + 1) / 2 + T;
+  int grid = n_tasks < n_sms ? n_tasks : n_sms;      // all CTAs must be co-resident (spin-wait dataflow)
+  if (grid < 1) grid = 1;
+  k_chol_solve<<<grid, 256, 0, s>>>(d, epoch, (epoch - 1) * (n_tasks + grid), (epoch - 1) * n_tasks);
+}
+
+}  // namespace mcp

@@ -68,9 +68,13 @@ struct BaDev {
   double* gc;                    // [nc]
   double* rm;                    // [nc]   sum_p W (V+lambda I)^-1 g_p
   double* dc;                    // [nc]   pose update
-  double* L;                     // [nc*nc] Cholesky factor workspace (lower, row-major)
+  double* L;                     // Cholesky factor, 32x32 tiles (lower block triangle + rhs block row)
+  double* Linv;                  // inverse diagonal tiles
+  int* flags;                    // dataflow ready flags + counters (ba_solve.cu)
   double* part;                  // [8][MAX_PARTIALS] per-block partial sums
-  unsigned* hist;                // [SEL_PASSES][SEL_BINS]
+  unsigned* sel_hist;            // [SEL_PASSES][SEL_BINS] radix-select histograms (self re-arming)
+  unsigned* sel_done;            // [SEL_PASSES] ticket counters
+  unsigned long long* sel_state; // [SEL_PASSES][2] prefix, rank
   BaCtrl* ctrl;
   int* outlier_flags;            // [n_meas] (sorted order)
   double* dbg;                   // optional debug output
