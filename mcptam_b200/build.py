@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libmcptam_b200.so")
-SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
+SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_schur.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -43,6 +44,9 @@ void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cu
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s);
 int configure_kernels(int max_slots, int* warps_out, size_t* smem_out);
+void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
+void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
+void launch_schur_gather(const BaDev& d, cudaStream_t s);
 
 struct DevBuf {
   void* p = nullptr;
@@ -81,7 +85,8 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[2], b_pt[2], b_chi2[2], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt;
+  bool schur_scatter = false;
   int chol_epoch = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
   BaCtrl* ctrl_host = nullptr;   // pinned
@@ -152,7 +157,7 @@ int mcp_ba_destroy(McpBa* h)
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_pose[0],
                     &h->b_pose[1], &h->b_pt[0], &h->b_pt[1], &h->b_chi2[0], &h->b_chi2[1], &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt };
   for (DevBuf* b : all) b->release();
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
   if (h->flags_host) cudaFreeHost(h->flags_host);
@@ -259,7 +264,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   std::vector<int4> pt_info(n_pt), meas_a(n_meas), meas_b(n_meas);
   std::vector<double2> mxy(n_meas);
   std::vector<double> minfo(n_meas);
-  std::vector<int> pt_slot_off(n_pt + 1, 0), slot_var;
+  std::vector<int> pt_slot_off(n_pt + 1, 0), slot_var, slot_pt;
   slot_var.reserve((size_t)n_meas + n_pt);
   int max_slots = 1;
   std::vector<int> tmp;
@@ -287,7 +292,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
       if (any_src) tmp.push_back(src_var);
       std::sort(tmp.begin(), tmp.end());
       tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      for (int v : tmp) slot_var.push_back(v);
+      for (int v : tmp) { slot_var.push_back(v); slot_pt.push_back(p); }
       const int K = (int)tmp.size();
       max_slots = std::max(max_slots, K);
       for (int q = pt_meas_off[p]; q < pt_meas_off[p + 1]; q++)
@@ -313,7 +318,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   int rc;
 #define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
   UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_meas_off, pt_meas_off);
-  UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
+  UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_slot_pt, slot_pt); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
   UP(h->b_meas_a, meas_a); UP(h->b_meas_b, meas_b);
 #undef UP
   const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)std::max(n_pt, 1);
@@ -328,6 +333,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if ((rc = h->b_V.ensure(sizeof(double) * 6 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_gp.ensure(sizeof(double) * 3 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_W.ensure(sizeof(double) * 18 * (size_t)std::max(n_slots, 1)))) return rc;
+  if ((rc = h->b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
   // accumulators: [H0 | gc | red(8) | Sm | rm]
   const size_t ncp = (size_t)std::max(nc, 1);
   h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 8; h->off_rm = h->off_Sm + ncp * ncp;
@@ -369,7 +375,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.meas_xy = h->b_meas_xy.as<double2>(); d.meas_info = h->b_meas_info.as<double>();
   d.meas_a = h->b_meas_a.as<int4>(); d.meas_b = h->b_meas_b.as<int4>();
   for (int k = 0; k < 2; k++) { d.pose[k] = h->b_pose[k].as<double>(); d.pt[k] = h->b_pt[k].as<double>(); d.chi2[k] = h->b_chi2[k].as<double>(); }
-  d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>();
+  d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>(); d.Y = h->b_Y.as<double>();
+  d.slot_pt = h->b_slot_pt.as<int>(); d.slot_lo = pt_slot_off[d.p_lo]; d.slot_hi = pt_slot_off[d.p_hi];
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
   d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
@@ -390,6 +397,32 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   c.solve_ok = 1;
   c.sel_n = n_meas; c.sel_rank = n_meas / 2;
   MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+  {
+    // co-visibility lists for the gather-based Schur reduction (ba_schur.cu), built on the device
+    const char* env = getenv("MCP_BA_SCHUR_SCATTER");
+    h->schur_scatter = env && env[0] == '1';
+    const int n_pairs = npv * (npv + 1) / 2;
+    if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 1), h->stream));
+    launch_pair_count(d, h->b_paircnt.as<int>(), h->stream);
+    std::vector<int> cnt(n_pairs + 1, 0);
+    MCP_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), h->b_paircnt.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    std::vector<int> off(n_pairs + 1, 0);
+    for (int i = 0; i < n_pairs; i++) off[i + 1] = off[i] + cnt[i];
+    const int n_inc = off[n_pairs];
+    std::vector<int4> items;
+    const int CH = 128;
+    int pid = 0;
+    for (int a2 = 0; a2 < npv; a2++)
+      for (int b2 = a2; b2 < npv; b2++, pid++)
+        for (int q = off[pid]; q < off[pid + 1]; q += CH) items.push_back(make_int4(a2, b2, q, std::min(q + CH, off[pid + 1])));
+    if ((rc = h->b_inc.ensure(sizeof(int2) * (size_t)std::max(n_inc, 1)))) return rc;
+    if ((rc = upload(h, h->b_paircnt, off.data(), sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
+    if ((rc = upload(h, h->b_items, items.data(), sizeof(int4) * items.size()))) return rc;
+    launch_pair_fill(d, h->b_paircnt.as<int>(), h->b_inc.as<int2>(), h->stream);
+    d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items = (int)items.size();
+  }
   MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->outliers.clear();
   h->loaded = true;
@@ -511,11 +544,12 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       { Prof p(h, C_OTHER); launch_lambda_init(d, s); }
       if (multi) NCCL_CHECK(ncclAllReduce(d.part + PART_MAXDIAG * MAX_PARTIALS, d.part + PART_MAXDIAG * MAX_PARTIALS, 1, ncclDouble, ncclMax, h->comm, s));
       { Prof p(h, C_OTHER); launch_lambda_apply(d, s); }
-      { Prof p(h, C_SCHUR); launch_schur_only(d, h->lin_warps, h->lin_smem, s); }
+      { Prof p(h, C_SCHUR); if (h->schur_scatter) launch_schur_only(d, h->lin_warps, h->lin_smem, s); else { launch_schur_gather(d, s); h->launches++; } }
       if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, h->acc_doubles - h->off_Sm, ncclDouble, ncclSum, h->comm, s));
       c.need_lambda_init = 0;
     } else {
-      { Prof p(h, C_LIN); n_lin = launch_linearize(d, true, h->lin_warps, h->lin_smem, s); }
+      { Prof p(h, C_LIN); n_lin = launch_linearize(d, h->schur_scatter, h->lin_warps, h->lin_smem, s); }
+      if (!h->schur_scatter) { Prof p(h, C_SCHUR); launch_schur_gather(d, s); h->launches++; }
       if (multi) {
         launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
         NCCL_CHECK(ncclAllReduce(acc, acc, h->acc_doubles, ncclDouble, ncclSum, h->comm, s));
@@ -541,7 +575,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         break;
       }
       MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * (h->acc_doubles - h->off_Sm), s));
-      { Prof p(h, C_SCHUR); launch_schur_only(d, h->lin_warps, h->lin_smem, s); }
+      { Prof p(h, C_SCHUR); if (h->schur_scatter) launch_schur_only(d, h->lin_warps, h->lin_smem, s); else { launch_schur_gather(d, s); h->launches++; } }
       if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, h->acc_doubles - h->off_Sm, ncclDouble, ncclSum, h->comm, s));
     }
     if (single_step) return MCP_OK;

@@ -1,0 +1,159 @@
+// ba_schur.cu — per-point Schur complement as a gather:  Sm = sum_p W_p (V_p + lambda I)^-1 W_p^T.
+//
+// The scatter formulation (one warp per point, ~1300 fp64 atomics per point into the dense 6N x 6N matrix) is
+// bound by L2 atomic throughput.  Here the reduction is turned around: at load time every (point, pose-slot
+// pair) incidence is bucketed by the 6x6 block (a,b) of the reduced camera system it contributes to
+// ("co-visibility lists", built on the device).  Per LM trial
+//   k_schur_y      Y_s = W_s (V_p + lambda I)^-1 for every (point, slot) s      (coalesced, no reduction)
+//   k_schur_pairs  one warp per block-pair chunk: lanes stride the incidence list, each lane accumulates a
+//                  private 6x6 block  Y_A W_B^T  in registers, one warp reduction, 36 adds per chunk.
+// Reads are 144-byte contiguous records served from L2; there is no per-incidence atomic.
+#include "ba_types.cuh"
+
+namespace mcp {
+
+__device__ __forceinline__ int pair_id(int a, int b, int npv) { return a * npv - (a * (a - 1)) / 2 + (b - a); }
+
+__device__ __forceinline__ bool inv3_sym_s(const double* V6, double lambda, double* Vi)
+{
+  const double a = V6[0] + lambda, b = V6[1], c = V6[2], dd = V6[3] + lambda, e = V6[4], f = V6[5] + lambda;
+  const double c00 = dd * f - e * e, c01 = c * e - b * f, c02 = b * e - c * dd;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double id = 1.0 / det;
+  Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id;
+  Vi[3] = Vi[1]; Vi[4] = (a * f - c * c) * id; Vi[5] = (b * c - a * e) * id;
+  Vi[6] = Vi[2]; Vi[7] = Vi[5]; Vi[8] = (a * dd - b * b) * id;
+  return (a > 0) && (a * dd - b * b > 0) && (det > 0) && isfinite(id);
+}
+
+// ---- load-time construction of the co-visibility lists ------------------------------------------------
+__global__ void k_pair_count(BaDev d, int* __restrict__ cnt)
+{
+  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
+    if (d.pt_var[p] < 0) continue;
+    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+    for (int x = 0; x < K; x++)
+      for (int y = x; y < K; y++) atomicAdd(&cnt[pair_id(d.slot_var[s0 + x], d.slot_var[s0 + y], d.n_pose_var)], 1);
+  }
+}
+__global__ void k_pair_fill(BaDev d, int* __restrict__ cursor, int2* __restrict__ inc)
+{
+  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
+    if (d.pt_var[p] < 0) continue;
+    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+    for (int x = 0; x < K; x++)
+      for (int y = x; y < K; y++) {
+        const int pos = atomicAdd(&cursor[pair_id(d.slot_var[s0 + x], d.slot_var[s0 + y], d.n_pose_var)], 1);
+        inc[pos] = make_int2(s0 + x, s0 + y);
+      }
+  }
+}
+
+// ---- per trial --------------------------------------------------------------------------------------
+// one thread per (point, slot): Y = W Vinv (18 doubles), z = Y g_p (6 doubles)
+__global__ void __launch_bounds__(256) k_schur_y(BaDev d)
+{
+  const double lambda = d.ctrl->lambda;
+  const int s_lo = d.slot_lo, s_hi = d.slot_hi;
+  int fail = 0;
+  for (int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x; s < s_hi; s += gridDim.x * blockDim.x) {
+    const int p = d.slot_pt[s];
+    double V6[6], gp[3], Vi[9];
+#pragma unroll
+    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
+    if (!inv3_sym_s(V6, lambda, Vi)) fail = 1;
+    const double2* w2 = reinterpret_cast<const double2*>(d.W + 18 * (size_t)s);
+    double w[18];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double2 t = w2[i]; w[2 * i] = t.x; w[2 * i + 1] = t.y; }
+    double y[24];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) y[r * 3 + c] = w[r * 3] * Vi[c] + w[r * 3 + 1] * Vi[3 + c] + w[r * 3 + 2] * Vi[6 + c];
+      y[18 + r] = y[r * 3] * gp[0] + y[r * 3 + 1] * gp[1] + y[r * 3 + 2] * gp[2];
+    }
+    double2* y2 = reinterpret_cast<double2*>(d.Y + 24 * (size_t)s);
+#pragma unroll
+    for (int i = 0; i < 12; i++) y2[i] = make_double2(y[2 * i], y[2 * i + 1]);
+  }
+  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+}
+
+// One warp per work item {block row a, block col b, begin, end}.  Incidences are processed in groups of G:
+// the warp gathers the Y_A (192 B: Y + z) and W_B (144 B) records of the group with coalesced 16-byte pieces
+// into shared memory, then every lane accumulates the output entries it owns:
+//   lane l < 32 : S[r][c], (r,c) = (l / 6, l % 6);  lanes 0..3 additionally own entries 32..35;
+//   lanes 4..9  : rm[a][lane-4] on diagonal items (sum of z).
+constexpr int SG = 32;                       // incidences per group
+constexpr int SREC = 42;                     // doubles per staged incidence: Y(18) z(6) W(18)
+__global__ void __launch_bounds__(128) k_schur_pairs(BaDev d)
+{
+  __shared__ __align__(16) double stage[4][SG * SREC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  double* st = stage[wid];
+  const int r0 = lane / 6, c0 = lane - 6 * r0;           // entry `lane`
+  const int e1 = 32 + (lane & 3), r1 = e1 / 6, c1 = e1 - 6 * r1;
+  for (int it = gw; it < d.n_items; it += nw) {
+    const int4 item = d.items[it];
+    const bool diag = item.x == item.y;
+    double acc0 = 0.0, acc1 = 0.0, accz = 0.0;
+    for (int g0 = item.z; g0 < item.w; g0 += SG) {
+      const int ng = min(SG, item.w - g0);
+      int2 ab = make_int2(0, 0);
+      if (lane < ng) ab = d.inc[g0 + lane];
+      // 21 pieces of 16 B per incidence: 12 of the Y record, 9 of the W record
+      const int npiece = ng * 21;
+      // all 21 gathers of the group are issued back to back (static unroll), then staged to shared memory
+      double2 piece[21];
+#pragma unroll
+      for (int k = 0; k < 21; k++) {
+        const int e = k * 32 + lane;
+        const int q = min(e / 21, ng - 1), part = e - (e / 21) * 21;
+        const int sa = __shfl_sync(0xffffffffu, ab.x, q), sb = __shfl_sync(0xffffffffu, ab.y, q);
+        const double2* src = part < 12 ? reinterpret_cast<const double2*>(d.Y + 24 * (size_t)sa) + part
+                                       : reinterpret_cast<const double2*>(d.W + 18 * (size_t)sb) + (part - 12);
+        piece[k] = (e < npiece) ? __ldcg(src) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < 21; k++) {
+        const int e = k * 32 + lane;
+        if (e < npiece) reinterpret_cast<double2*>(st + (e / 21) * SREC)[e - (e / 21) * 21] = piece[k];
+      }
+      __syncwarp();
+      for (int q = 0; q < ng; q++) {
+        const double* y = st + q * SREC;
+        const double* w = y + 24;
+        acc0 += y[r0 * 3] * w[c0 * 3] + y[r0 * 3 + 1] * w[c0 * 3 + 1] + y[r0 * 3 + 2] * w[c0 * 3 + 2];
+        if (lane < 4) acc1 += y[r1 * 3] * w[c1 * 3] + y[r1 * 3 + 1] * w[c1 * 3 + 1] + y[r1 * 3 + 2] * w[c1 * 3 + 2];
+        else if (diag && lane < 10) accz += y[18 + lane - 4];
+      }
+      __syncwarp();
+    }
+    double* base = d.Sm + (size_t)(6 * item.x) * nc + 6 * item.y;
+    atomicAdd(base + (size_t)r0 * nc + c0, acc0);
+    if (lane < 4) atomicAdd(base + (size_t)r1 * nc + c1, acc1);
+    else if (diag && lane < 10) atomicAdd(d.rm + 6 * item.x + lane - 4, accz);
+  }
+}
+
+void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148, 128, 0, s>>>(d, cnt); }
+void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148, 128, 0, s>>>(d, cursor, inc); }
+void launch_schur_gather(const BaDev& d, cudaStream_t s)
+{
+  const int nslots = d.slot_hi - d.slot_lo;
+  int g1 = (nslots + 255) / 256;
+  if (g1 < 1) g1 = 1;
+  if (g1 > 148 * 8) g1 = 148 * 8;
+  k_schur_y<<<g1, 256, 0, s>>>(d);
+  int g2 = (d.n_items + 3) / 4;
+  if (g2 < 1) g2 = 1;
+  if (g2 > 148 * 5) g2 = 148 * 5;
+  k_schur_pairs<<<g2, 128, 0, s>>>(d);
+}
+
+}  // namespace mcp

@@ -51,18 +51,29 @@ __device__ __noinline__ bool potrf32_warp(double* S, double* rinv, int lane)
 #pragma unroll
   for (int c = 0; c < TB; c++) a[c] = (c <= lane) ? S[lane * TLD + c] : 0.0;
   bool bad = false;
+  // software pipelined: the pivot of column jj+1 (and its rsqrt) is produced right after the first
+  // rank-1 update of column jj, before the remaining 30-jj column updates are issued.
+  double dj = __shfl_sync(0xffffffffu, a[0], 0);
+  if (!(dj > 0.0) || !(dj < 1.0e300)) { bad = true; dj = 1.0; }
+  double ri = rsqrt(dj);
 #pragma unroll
   for (int jj = 0; jj < TB; jj++) {
-    double dj = __shfl_sync(0xffffffffu, a[jj], jj);
-    if (!(dj > 0.0) || !(dj < 1.0e300)) { bad = true; dj = 1.0; }
-    const double ri = rsqrt(dj);
     if (lane == jj) { rinv[jj] = ri; a[jj] = dj * ri; }
     else if (lane > jj) a[jj] *= ri;
+    double dn = 1.0, rn = 1.0;
+    if (jj + 1 < TB) {
+      const double v1 = __shfl_sync(0xffffffffu, a[jj], jj + 1);
+      if (lane >= jj + 1) a[jj + 1] -= a[jj] * v1;
+      dn = __shfl_sync(0xffffffffu, a[jj + 1], jj + 1);
+      if (!(dn > 0.0) || !(dn < 1.0e300)) { bad = true; dn = 1.0; }
+      rn = rsqrt(dn);
+    }
 #pragma unroll
-    for (int c = jj + 1; c < TB; c++) {
+    for (int c = jj + 2; c < TB; c++) {
       const double v = __shfl_sync(0xffffffffu, a[jj], c);
       if (lane >= c) a[c] -= a[jj] * v;
     }
+    dj = dn; ri = rn;
   }
 #pragma unroll
   for (int c = 0; c < TB; c++) S[lane * TLD + c] = a[c];
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
     while (rem >= T + 1 - j) { rem -= T + 1 - j; j++; }
     const int i = j + rem;
     const bool is_rhs = (i == T);
-    unsigned long long t0 = 0, t1 = 0, t2 = 0;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3p = 0, t4p = 0;
     if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     // ---- initial value ------------------------------------------------------------------------------
     double acc[2][2];
@@ -213,7 +224,9 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
         if (potrf32_warp(As, xs + 32 * TB, lane) && lane == 0) atomicExch(&ctr[2], epoch);
       }
       __syncthreads();
+      if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3p));
       inverse32_block(As, Bs, xs + 32 * TB, xs, tid);
+      if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t4p));
       __syncthreads();
       double* gl = Lt + tile_index(j, j) * (TB * TB);
       double* gi = Linv + (size_t)j * (TB * TB);
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
     if (d.dbg && tid == 0) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
       double* o = d.dbg + 8 * (size_t)task;
-      o[0] = i; o[1] = j; o[2] = (double)(t0 % 1000000000ull); o[3] = (double)(t1 % 1000000000ull); o[4] = (double)(t2 % 1000000000ull); o[5] = blockIdx.x;
+      o[0] = i; o[1] = j; o[2] = (double)(t0 % 1000000000ull); o[3] = (double)(t1 % 1000000000ull); o[4] = (double)(t2 % 1000000000ull); o[5] = blockIdx.x; o[6] = (double)(t3p % 1000000000ull); o[7] = (double)(t4p % 1000000000ull);
     }
     __syncthreads();
     if (tid == 0) s_task = atomicAdd(&ctr[1], 1) - base1;

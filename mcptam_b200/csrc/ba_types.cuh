@@ -63,6 +63,12 @@ struct BaDev {
   double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
   double* gp;                    // [n_pt*3]
   double* W;                     // [n_slots*18] 6x3 row-major
+  double* Y;                     // [n_slots*24] W (V + lambda I)^-1 (18) followed by Y g_p (6)
+  const int* slot_pt;            // [n_slots] owning point of each slot
+  int slot_lo, slot_hi;          // local slot range (multi-GPU shard)
+  const int2* inc;               // co-visibility incidences {slot A, slot B}, bucketed by block pair
+  const int4* items;             // work items {block row, block col, begin, end} into inc
+  int n_items, pad_items;
   double* H0;                    // [nc*nc] upper block triangle, pose-pose normal matrix (no damping)
   double* Sm;                    // [nc*nc] upper block triangle, sum_p W (V+lambda I)^-1 W^T
   double* gc;                    // [nc]
