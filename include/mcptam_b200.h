@@ -137,6 +137,8 @@ int mcp_ba_reset_state(McpBa* h);
  * nccl_unique_id is the 128-byte ncclUniqueId created on rank 0. */
 int mcp_ba_comm_init(McpBa* h, const void* nccl_unique_id, int32_t rank, int32_t world);
 int mcp_nccl_unique_id(void* out128);
+/* The point partition used for `world` ranks: part_pt[world+1] boundaries (pure host code, no GPU needed). */
+int mcp_ba_partition(int32_t n_pt, const int32_t* meas_pt, int32_t n_meas, int32_t world, int32_t* part_pt);
 
 /* Test / diagnostic hooks (not part of the reference surface). */
 int mcp_ba_eval(McpBa* h, double* err_xy, double* chi2);                 /* original measurement order */
@@ -229,6 +231,8 @@ int mcp_fe_shitomasi(McpFe* h, int32_t kf, int32_t level, int32_t n, const int32
 int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t level, int32_t n,
                           const int32_t* src_xy, const int32_t* start_xy, int32_t range, int32_t* pos_out,
                           int32_t* found);
+/* Debug: FAST score map of one level (0 = no corner at b=5, else fast_corner_score_10). */
+int mcp_fe_debug_scores(McpFe* h, int32_t slot, int32_t level, uint8_t* out);
 typedef struct McpFeTiming { double ms_pyramid, ms_fast, ms_compact, ms_search, ms_other; int32_t n_launches, pad_; } McpFeTiming;
 int mcp_fe_get_timing(McpFe* h, McpFeTiming* out);
 

@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libmcptam_b200.so")
 SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_schur.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"] + (["-DMCP_FE_DEBUG"] if os.environ.get("MCP_FE_DEBUG") else [])
 
 
 def _stale() -> bool:

@@ -80,6 +80,7 @@ def lib():
         L.mcp_ba_reset_state.argtypes = [C.c_void_p]
         L.mcp_ba_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.mcp_nccl_unique_id.argtypes = [C.c_void_p]
+        L.mcp_ba_partition.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mcp_ba_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcp_ba_debug_jacobians.argtypes = [C.c_void_p, C.c_void_p]
         L.mcp_ba_lm_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -225,7 +226,176 @@ class BaHandle:
         return t.as_dict()
 
 
+def ba_partition(n_pt, meas_pt, world):
+    meas_pt = np.ascontiguousarray(meas_pt, np.int32)
+    out = np.zeros(world + 1, np.int32)
+    check(lib().mcp_ba_partition(n_pt, _p(meas_pt), len(meas_pt), world, _p(out)))
+    return out
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     check(lib().mcp_nccl_unique_id(buf))
     return buf.raw
+
+
+# ---------------------------------------------------------------------------------------------
+# front end
+# ---------------------------------------------------------------------------------------------
+class FeConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("adaptive_thresh", C.c_int32),
+                ("max_corners_per_level", C.c_int32), ("max_keyframes", C.c_int32), ("max_patches", C.c_int32),
+                ("device", C.c_int32), ("halfsample_round", C.c_int32), ("transform_round", C.c_int32), ("pad_", C.c_int32)]
+
+
+class LevelOut(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_corners", C.c_int32), ("fast_thresh", C.c_int32),
+                ("fast_freq", C.c_int32 * 31), ("pad_", C.c_int32), ("image", C.c_void_p), ("corners_xy", C.c_void_p),
+                ("corners_cap", C.c_int32), ("pad2_", C.c_int32), ("row_lut", C.c_void_p)]
+
+
+class PatchReq(C.Structure):
+    _fields_ = [("src_kf", C.c_int32), ("src_level", C.c_int32), ("src_cx", C.c_int32), ("src_cy", C.c_int32),
+                ("warp_inv", C.c_double * 4), ("search_level", C.c_int32), ("pred_x", C.c_int32), ("pred_y", C.c_int32),
+                ("range", C.c_int32), ("subpix_its", C.c_int32), ("exhaustive", C.c_int32)]
+
+
+class PatchRes(C.Structure):
+    _fields_ = [("template_bad", C.c_int32), ("found", C.c_int32), ("did_subpix", C.c_int32), ("score", C.c_int32),
+                ("coarse_x", C.c_int32), ("coarse_y", C.c_int32), ("found_x", C.c_double), ("found_y", C.c_double),
+                ("n_candidates", C.c_int32), ("pad_", C.c_int32)]
+
+
+class FeTiming(C.Structure):
+    _fields_ = [("ms_pyramid", C.c_double), ("ms_fast", C.c_double), ("ms_compact", C.c_double), ("ms_search", C.c_double),
+                ("ms_other", C.c_double), ("n_launches", C.c_int32), ("pad_", C.c_int32)]
+
+
+PATCH_REQ_DTYPE = np.dtype([("src_kf", "i4"), ("src_level", "i4"), ("src_cx", "i4"), ("src_cy", "i4"), ("warp_inv", "f8", 4),
+                            ("search_level", "i4"), ("pred_x", "i4"), ("pred_y", "i4"), ("range", "i4"), ("subpix_its", "i4"),
+                            ("exhaustive", "i4")], align=True)
+PATCH_RES_DTYPE = np.dtype([("template_bad", "i4"), ("found", "i4"), ("did_subpix", "i4"), ("score", "i4"), ("coarse_x", "i4"),
+                            ("coarse_y", "i4"), ("found_x", "f8"), ("found_y", "f8"), ("n_candidates", "i4"), ("pad_", "i4")], align=True)
+assert PATCH_REQ_DTYPE.itemsize == C.sizeof(PatchReq) and PATCH_RES_DTYPE.itemsize == C.sizeof(PatchRes)
+
+_fe_bound = False
+
+
+def _bind_fe(L):
+    global _fe_bound
+    if _fe_bound:
+        return
+    L.mcp_fe_default_config.argtypes = [C.POINTER(FeConfig)]
+    L.mcp_fe_create.argtypes = [C.POINTER(FeConfig), C.POINTER(C.c_void_p)]
+    L.mcp_fe_destroy.argtypes = [C.c_void_p]
+    L.mcp_fe_set_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.mcp_fe_make_keyframe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    L.mcp_fe_search_patches.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.mcp_fe_get_templates.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.mcp_fe_shitomasi.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.mcp_fe_minipatch_find.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p]
+    L.mcp_fe_get_timing.argtypes = [C.c_void_p, C.POINTER(FeTiming)]
+    L.mcp_fe_debug_scores.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    _fe_bound = True
+
+
+class FeHandle:
+    """One mcp_fe handle = one camera: resident keyframe pyramids + corner lists on the device."""
+
+    def __init__(self, width=640, height=480, device=-1, **cfg_kw):
+        self.L = lib()
+        _bind_fe(self.L)
+        cfg = FeConfig()
+        self.L.mcp_fe_default_config(C.byref(cfg))
+        cfg.width, cfg.height, cfg.device = width, height, device
+        for k, v in cfg_kw.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        check(self.L.mcp_fe_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.mcp_fe_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mask(self, mask):
+        if mask is None:
+            check(self.L.mcp_fe_set_mask(self.h, None, 0))
+        else:
+            m = np.ascontiguousarray(mask, np.uint8)
+            check(self.L.mcp_fe_set_mask(self.h, _p(m), m.shape[1]))
+
+    def make_keyframe(self, slot, img, want_images=False, outputs=True):
+        """MakeKeyFrame_Lite of one image into resident slot `slot`.  Returns a list of 4 per-level dicts."""
+        img = np.ascontiguousarray(img, np.uint8)
+        if not outputs:
+            check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], None))
+            return None
+        outs = (LevelOut * 4)()
+        cap = self.cfg.max_corners_per_level
+        keep = []
+        w, h = self.cfg.width, self.cfg.height
+        for l in range(4):
+            cor = np.zeros((cap, 2), np.int32)
+            lut = np.zeros(h, np.int32)
+            im = np.zeros((h, w), np.uint8) if want_images else None
+            keep.append((cor, lut, im))
+            outs[l].corners_xy = cor.ctypes.data
+            outs[l].corners_cap = cap
+            outs[l].row_lut = lut.ctypes.data
+            outs[l].image = im.ctypes.data if im is not None else None
+            w //= 2
+            h //= 2
+        check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], C.cast(outs, C.c_void_p)))
+        res = []
+        for l in range(4):
+            cor, lut, im = keep[l]
+            n = outs[l].n_corners
+            res.append({"width": outs[l].width, "height": outs[l].height, "n_corners": n, "corners": cor[:n].copy(),
+                        "row_lut": lut, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
+                        "image": im})
+        return res
+
+    def search_patches(self, target_kf, req: np.ndarray) -> np.ndarray:
+        req = np.ascontiguousarray(req, PATCH_REQ_DTYPE)
+        res = np.zeros(len(req), PATCH_RES_DTYPE)
+        check(self.L.mcp_fe_search_patches(self.h, target_kf, len(req), _p(req), _p(res)))
+        return res
+
+    def templates(self, n):
+        t = np.zeros((n, 64), np.uint8)
+        check(self.L.mcp_fe_get_templates(self.h, n, _p(t)))
+        return t
+
+    def shitomasi(self, kf, level, xy):
+        xy = np.ascontiguousarray(xy, np.int32)
+        out = np.zeros(len(xy))
+        check(self.L.mcp_fe_shitomasi(self.h, kf, level, len(xy), _p(xy), _p(out)))
+        return out
+
+    def minipatch_find(self, kf_src, kf_dst, level, src_xy, start_xy, rng):
+        src_xy = np.ascontiguousarray(src_xy, np.int32)
+        start_xy = np.ascontiguousarray(start_xy, np.int32)
+        pos = np.zeros_like(src_xy)
+        found = np.zeros(len(src_xy), np.int32)
+        check(self.L.mcp_fe_minipatch_find(self.h, kf_src, kf_dst, level, len(src_xy), _p(src_xy), _p(start_xy), rng, _p(pos), _p(found)))
+        return pos, found
+
+    def debug_scores(self, slot, level):
+        w, h = self.cfg.width >> level, self.cfg.height >> level
+        o = np.zeros((h, w), np.uint8)
+        check(self.L.mcp_fe_debug_scores(self.h, slot, level, _p(o)))
+        return o
+
+    def timing(self):
+        t = FeTiming()
+        check(self.L.mcp_fe_get_timing(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in t._fields_ if k != "pad_"}

@@ -204,19 +204,24 @@ static int upload(McpBa* h, DevBuf& b, const void* src, size_t bytes)
   return MCP_OK;
 }
 
-static void compute_partition(McpBa* h, const std::vector<int>& pt_meas_off, int n_pt)
+// contiguous, measurement-count-balanced partition of points; pure host code
+static void partition_points(const int* pt_meas_off, int n_pt, int world, int* part_pt)
 {
-  // contiguous, measurement-count-balanced partition of points
-  h->part_pt.assign(h->world + 1, 0);
-  h->part_meas.assign(h->world + 1, 0);
   const long long total = pt_meas_off[n_pt] + (long long)n_pt * 4;   // weight: measurements + per-point overhead
   int p = 0;
-  for (int r = 1; r < h->world; r++) {
-    const long long target = total * r / h->world;
+  part_pt[0] = 0;
+  for (int r = 1; r < world; r++) {
+    const long long target = total * r / world;
     while (p < n_pt && (long long)pt_meas_off[p] + (long long)p * 4 < target) p++;
-    h->part_pt[r] = p;
+    part_pt[r] = p;
   }
-  h->part_pt[h->world] = n_pt;
+  part_pt[world] = n_pt;
+}
+static void compute_partition(McpBa* h, const std::vector<int>& pt_meas_off, int n_pt)
+{
+  h->part_pt.assign(h->world + 1, 0);
+  h->part_meas.assign(h->world + 1, 0);
+  partition_points(pt_meas_off.data(), n_pt, h->world, h->part_pt.data());
   for (int r = 0; r <= h->world; r++) h->part_meas[r] = pt_meas_off[h->part_pt[r]];
 }
 
@@ -799,6 +804,19 @@ int mcp_nccl_unique_id(void* out128)
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   NCCL_CHECK(ncclGetUniqueId(&id));
   memcpy(out128, &id, sizeof(id));
+  return MCP_OK;
+}
+
+int mcp_ba_partition(int32_t n_pt, const int32_t* meas_pt, int32_t n_meas, int32_t world, int32_t* part_pt)
+{
+  if (n_pt < 0 || n_meas < 0 || world < 1 || !part_pt || (n_meas && !meas_pt)) { set_last_error("mcp_ba_partition: bad arguments"); return MCP_ERR_INVALID; }
+  std::vector<int> off(n_pt + 1, 0);
+  for (int m = 0; m < n_meas; m++) {
+    if (meas_pt[m] < 0 || meas_pt[m] >= n_pt) { set_last_error("mcp_ba_partition: point index out of range"); return MCP_ERR_INVALID; }
+    off[meas_pt[m] + 1]++;
+  }
+  for (int p = 0; p < n_pt; p++) off[p + 1] += off[p];
+  partition_points(off.data(), n_pt, world, part_pt);
   return MCP_OK;
 }
 

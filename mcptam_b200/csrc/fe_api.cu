@@ -1,0 +1,350 @@
+// fe_api.cu — C ABI of the front end (include/mcptam_b200.h): resident keyframe pyramids on the device,
+// KeyFrame::MakeKeyFrame_Lite (src/KeyFrame.cc:145-361) and the batched Tracker::SearchForPoints body
+// (src/Tracker.cc:1299-1377) as kernels; host<->device copies through pinned staging buffers.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fe_types.cuh"
+
+namespace mcp {
+void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s);
+int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s);
+void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s);
+void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s);
+void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
+                         int2* pos, int* found, cudaStream_t s);
+}  // namespace mcp
+
+using namespace mcp;
+
+struct McpFe {
+  McpFeConfig cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  std::vector<FeKf> kf_host;       // per slot (device pointers inside)
+  std::vector<bool> kf_valid;
+  FeKf* kf_dev = nullptr;
+  uint8_t* pool = nullptr;         // one device allocation for everything
+  size_t pool_bytes = 0;
+  size_t out_block_bytes = 0;      // per slot: meta + luts + corners (contiguous, copied to the host in one go)
+  std::vector<uint8_t*> out_block_dev;
+  uint8_t* mask_dev[MCP_LEVELS] = { nullptr, nullptr, nullptr, nullptr };
+  bool has_mask = false;
+  uint8_t* stage_img = nullptr;    // pinned
+  uint8_t* stage_out = nullptr;    // pinned
+  McpPatchReq* req_host = nullptr; // pinned
+  McpPatchRes* res_host = nullptr; // pinned
+  McpPatchReq* req_dev = nullptr;
+  McpPatchRes* res_dev = nullptr;
+  uint8_t* templ_dev = nullptr;
+  int2* xy_dev = nullptr; int2* xy2_dev = nullptr; int2* pos_dev = nullptr; int* found_dev = nullptr; double* sc_dev = nullptr;
+  void* aux_host = nullptr;        // pinned scratch for shitomasi / minipatch
+  int last_n = 0;
+  McpFeTiming timing;
+  int lw[MCP_LEVELS], lh[MCP_LEVELS], lp[MCP_LEVELS];
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+void mcp_fe_default_config(McpFeConfig* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->width = 640; c->height = 480;
+  c->adaptive_thresh = 1;             // KeyFrame::sbAdaptiveThresh, src/KeyFrame.cc:70
+  c->max_corners_per_level = 8192;
+  c->max_keyframes = 8;
+  c->max_patches = 4096;
+  c->device = -1;
+}
+
+int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
+{
+  if (!out) { set_last_error("mcp_fe_create: out is NULL"); return MCP_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("mcp_fe_create: no CUDA device available (this library has no CPU fallback)");
+    return MCP_ERR_NO_DEVICE;
+  }
+  McpFe* h = new McpFe();
+  if (cfg) h->cfg = *cfg; else mcp_fe_default_config(&h->cfg);
+  const McpFeConfig& c = h->cfg;
+  if (c.width < 64 || c.height < 64 || c.max_keyframes < 1 || c.max_corners_per_level < 16 || c.max_patches < 1) {
+    set_last_error("mcp_fe_create: bad configuration");
+    delete h;
+    return MCP_ERR_INVALID;
+  }
+  if (c.device >= 0) MCP_CUDA_CHECK(cudaSetDevice(c.device));
+  MCP_CUDA_CHECK(cudaGetDevice(&h->device));
+  MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) MCP_CUDA_CHECK(cudaEventCreate(&e));
+  int w = c.width, hh = c.height;
+  for (int l = 0; l < MCP_LEVELS; l++) { h->lw[l] = w; h->lh[l] = hh; h->lp[l] = (int)align_up((size_t)w + 8, 128); w /= 2; hh /= 2; }
+  // ---- carve one pool ---------------------------------------------------------------------------------
+  const int S = c.max_keyframes, cap = c.max_corners_per_level;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+  std::vector<size_t> o_img(S * MCP_LEVELS), o_score(S * MCP_LEVELS), o_rowcount(S * MCP_LEVELS), o_hist(S), o_out(S);
+  size_t lut_total = 0;
+  for (int l = 0; l < MCP_LEVELS; l++) lut_total += align_up(sizeof(int) * h->lh[l], 256);
+  h->out_block_bytes = align_up(sizeof(FeMeta), 256) + lut_total + (size_t)MCP_LEVELS * align_up(sizeof(int2) * cap, 256);
+  for (int s = 0; s < S; s++) {
+    for (int l = 0; l < MCP_LEVELS; l++) {
+      o_img[s * MCP_LEVELS + l] = take((size_t)h->lp[l] * (h->lh[l] + 2) + 64);
+      o_score[s * MCP_LEVELS + l] = take((size_t)h->lp[l] * h->lh[l]);
+      o_rowcount[s * MCP_LEVELS + l] = take(sizeof(int) * h->lh[l]);
+    }
+    o_hist[s] = take(sizeof(unsigned) * 32 * MCP_LEVELS);
+    o_out[s] = take(h->out_block_bytes);
+  }
+  size_t o_mask[MCP_LEVELS];
+  for (int l = 0; l < MCP_LEVELS; l++) o_mask[l] = take((size_t)h->lp[l] * h->lh[l]);
+  const size_t o_kf = take(sizeof(FeKf) * S);
+  const size_t o_req = take(sizeof(McpPatchReq) * c.max_patches);
+  const size_t o_res = take(sizeof(McpPatchRes) * c.max_patches);
+  const size_t o_templ = take((size_t)64 * c.max_patches);
+  const size_t o_xy = take(sizeof(int2) * c.max_patches), o_xy2 = take(sizeof(int2) * c.max_patches);
+  const size_t o_pos = take(sizeof(int2) * c.max_patches), o_found = take(sizeof(int) * c.max_patches), o_sc = take(sizeof(double) * c.max_patches);
+  h->pool_bytes = off;
+  MCP_CUDA_CHECK(cudaMalloc(&h->pool, h->pool_bytes));
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->stream));
+  h->kf_host.resize(S);
+  h->kf_valid.assign(S, false);
+  h->out_block_dev.resize(S);
+  for (int l = 0; l < MCP_LEVELS; l++) h->mask_dev[l] = h->pool + o_mask[l];
+  for (int s = 0; s < S; s++) {
+    FeKf& k = h->kf_host[s];
+    memset(&k, 0, sizeof(k));
+    uint8_t* ob = h->pool + o_out[s];
+    h->out_block_dev[s] = ob;
+    k.meta = reinterpret_cast<FeMeta*>(ob);
+    size_t oo = align_up(sizeof(FeMeta), 256);
+    int tiles = 0, rows = 0;
+    for (int l = 0; l < MCP_LEVELS; l++) {
+      FeLevel& L = k.lv[l];
+      L.w = h->lw[l]; L.h = h->lh[l]; L.pitch = h->lp[l];
+      L.img = h->pool + o_img[s * MCP_LEVELS + l];
+      L.score = h->pool + o_score[s * MCP_LEVELS + l];
+      L.rowcount = reinterpret_cast<int*>(h->pool + o_rowcount[s * MCP_LEVELS + l]);
+      L.hist = reinterpret_cast<unsigned*>(h->pool + o_hist[s]) + 32 * l;
+      L.mask = nullptr;
+      L.row_lut = reinterpret_cast<int*>(ob + oo);
+      oo += align_up(sizeof(int) * L.h, 256);
+      k.tile_off[l] = tiles; k.row_off[l] = rows;
+      tiles += ((L.w + 31) / 32) * ((L.h + 7) / 8);
+      rows += L.h;
+    }
+    for (int l = 0; l < MCP_LEVELS; l++) { k.lv[l].corners = reinterpret_cast<int2*>(ob + oo); oo += align_up(sizeof(int2) * cap, 256); }
+    k.tile_off[MCP_LEVELS] = tiles; k.row_off[MCP_LEVELS] = rows;
+    // old-style fixed thresholds (src/KeyFrame.cc:322-341)
+    k.fixed_thresh[0] = 10; k.fixed_thresh[1] = 15; k.fixed_thresh[2] = 15; k.fixed_thresh[3] = 10;
+    k.corner_cap = cap;
+  }
+  h->kf_dev = reinterpret_cast<FeKf*>(h->pool + o_kf);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->kf_dev, h->kf_host.data(), sizeof(FeKf) * S, cudaMemcpyHostToDevice, h->stream));
+  h->req_dev = reinterpret_cast<McpPatchReq*>(h->pool + o_req);
+  h->res_dev = reinterpret_cast<McpPatchRes*>(h->pool + o_res);
+  h->templ_dev = h->pool + o_templ;
+  h->xy_dev = reinterpret_cast<int2*>(h->pool + o_xy); h->xy2_dev = reinterpret_cast<int2*>(h->pool + o_xy2);
+  h->pos_dev = reinterpret_cast<int2*>(h->pool + o_pos); h->found_dev = reinterpret_cast<int*>(h->pool + o_found);
+  h->sc_dev = reinterpret_cast<double*>(h->pool + o_sc);
+  MCP_CUDA_CHECK(cudaMallocHost(&h->stage_img, (size_t)c.width * c.height));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->stage_out, h->out_block_bytes));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->req_host, sizeof(McpPatchReq) * c.max_patches));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->res_host, sizeof(McpPatchRes) * c.max_patches));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->aux_host, (size_t)64 * c.max_patches));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  memset(&h->timing, 0, sizeof(h->timing));
+  *out = h;
+  return MCP_OK;
+}
+
+int mcp_fe_destroy(McpFe* h)
+{
+  if (!h) return MCP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->pool) cudaFree(h->pool);
+  if (h->stage_img) cudaFreeHost(h->stage_img);
+  if (h->stage_out) cudaFreeHost(h->stage_out);
+  if (h->req_host) cudaFreeHost(h->req_host);
+  if (h->res_host) cudaFreeHost(h->res_host);
+  if (h->aux_host) cudaFreeHost(h->aux_host);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MCP_OK;
+}
+
+// KeyFrame::SetMask (src/KeyFrame.cc:116-126): level-0 mask, half-sampled down the pyramid
+int mcp_fe_set_mask(McpFe* h, const uint8_t* mask, int32_t stride)
+{
+  if (!h) { set_last_error("mcp_fe_set_mask: NULL handle"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  h->has_mask = mask != nullptr;
+  if (mask) {
+    for (int y = 0; y < h->lh[0]; y++) memcpy(h->stage_img + (size_t)y * h->lw[0], mask + (size_t)y * stride, h->lw[0]);
+    MCP_CUDA_CHECK(cudaMemcpy2DAsync(h->mask_dev[0], h->lp[0], h->stage_img, h->lw[0], h->lw[0], h->lh[0], cudaMemcpyHostToDevice, h->stream));
+    FeKf tmp = h->kf_host[0];
+    for (int l = 0; l < MCP_LEVELS; l++) tmp.lv[l].img = h->mask_dev[l];
+    fe_launch_pyramid(tmp, h->cfg.halfsample_round, h->stream);
+  }
+  for (auto& k : h->kf_host)
+    for (int l = 0; l < MCP_LEVELS; l++) k.lv[l].mask = mask ? h->mask_dev[l] : nullptr;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->kf_dev, h->kf_host.data(), sizeof(FeKf) * h->kf_host.size(), cudaMemcpyHostToDevice, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t stride, McpLevelOut out[MCP_LEVELS])
+{
+  if (!h || !img || slot < 0 || slot >= (int)h->kf_host.size() || stride < h->lw[0]) {
+    set_last_error("mcp_fe_make_keyframe: bad arguments");
+    return MCP_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  const FeKf& kf = h->kf_host[slot];
+  const int w = h->lw[0], hh = h->lh[0];
+  if (stride == w) memcpy(h->stage_img, img, (size_t)w * hh);
+  else for (int y = 0; y < hh; y++) memcpy(h->stage_img + (size_t)y * w, img + (size_t)y * stride, w);
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[0], s));
+  MCP_CUDA_CHECK(cudaMemcpy2DAsync(kf.lv[0].img, kf.lv[0].pitch, h->stage_img, w, w, hh, cudaMemcpyHostToDevice, s));
+  MCP_CUDA_CHECK(cudaMemsetAsync(kf.lv[0].hist, 0, sizeof(unsigned) * 32 * MCP_LEVELS, s));
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
+  fe_launch_pyramid(kf, h->cfg.halfsample_round, s);
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
+  const int nl = fe_launch_fast(kf, h->cfg.adaptive_thresh, s);
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[3], s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->stage_out, h->out_block_dev[slot], h->out_block_bytes, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[4], s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  h->kf_valid[slot] = true;
+  float t;
+  cudaEventElapsedTime(&t, h->ev[1], h->ev[2]); h->timing.ms_pyramid = t;
+  cudaEventElapsedTime(&t, h->ev[2], h->ev[3]); h->timing.ms_fast = t;
+  cudaEventElapsedTime(&t, h->ev[0], h->ev[1]); h->timing.ms_other = t;
+  cudaEventElapsedTime(&t, h->ev[3], h->ev[4]); h->timing.ms_compact = t;    // device->host copy of the results
+  h->timing.n_launches = 1 + nl;
+  if (out) {
+    const FeMeta* meta = reinterpret_cast<const FeMeta*>(h->stage_out);
+    size_t oo = align_up(sizeof(FeMeta), 256);
+    const int cap = h->cfg.max_corners_per_level;
+    size_t lut_off[MCP_LEVELS], cor_off[MCP_LEVELS];
+    for (int l = 0; l < MCP_LEVELS; l++) { lut_off[l] = oo; oo += align_up(sizeof(int) * h->lh[l], 256); }
+    for (int l = 0; l < MCP_LEVELS; l++) { cor_off[l] = oo; oo += align_up(sizeof(int2) * cap, 256); }
+    for (int l = 0; l < MCP_LEVELS; l++) {
+      McpLevelOut& o = out[l];
+      o.width = h->lw[l]; o.height = h->lh[l];
+      o.n_corners = std::min(meta->lv[l].n_corners, cap);
+      o.fast_thresh = meta->lv[l].fast_thresh;
+      memcpy(o.fast_freq, meta->lv[l].fast_freq, sizeof(o.fast_freq));
+      if (o.corners_xy) memcpy(o.corners_xy, h->stage_out + cor_off[l], sizeof(int32_t) * 2 * (size_t)std::min(o.n_corners, o.corners_cap));
+      if (o.row_lut) memcpy(o.row_lut, h->stage_out + lut_off[l], sizeof(int32_t) * h->lh[l]);
+      if (o.image) {
+        if (l == 0) memcpy(o.image, h->stage_img, (size_t)w * hh);
+        else MCP_CUDA_CHECK(cudaMemcpy2D(o.image, h->lw[l], kf.lv[l].img, kf.lv[l].pitch, h->lw[l], h->lh[l], cudaMemcpyDeviceToHost));
+      }
+    }
+  }
+  return MCP_OK;
+}
+
+int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatchReq* req, McpPatchRes* res)
+{
+  if (!h || n < 0 || (n && (!req || !res)) || target_kf < 0 || target_kf >= (int)h->kf_host.size()) {
+    set_last_error("mcp_fe_search_patches: bad arguments");
+    return MCP_ERR_INVALID;
+  }
+  if (n > h->cfg.max_patches) { set_last_error("mcp_fe_search_patches: n=%d exceeds max_patches=%d", n, h->cfg.max_patches); return MCP_ERR_INVALID; }
+  if (!h->kf_valid[target_kf]) { set_last_error("mcp_fe_search_patches: target keyframe slot %d is empty", target_kf); return MCP_ERR_STATE; }
+  if (n == 0) return MCP_OK;
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  memcpy(h->req_host, req, sizeof(McpPatchReq) * (size_t)n);
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[0], s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->req_dev, h->req_host, sizeof(McpPatchReq) * (size_t)n, cudaMemcpyHostToDevice, s));
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
+  FeDev fe;
+  fe.kf = h->kf_dev; fe.n_slots = (int)h->kf_host.size(); fe.transform_round = h->cfg.transform_round;
+  fe_launch_patch_search(fe, target_kf, n, h->req_dev, h->res_dev, h->templ_dev, s);
+  MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(McpPatchRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  memcpy(res, h->res_host, sizeof(McpPatchRes) * (size_t)n);
+  float t;
+  cudaEventElapsedTime(&t, h->ev[1], h->ev[2]); h->timing.ms_search = t;
+  h->timing.n_launches = 1;
+  h->last_n = n;
+  return MCP_OK;
+}
+
+int mcp_fe_get_templates(McpFe* h, int32_t n, uint8_t* templ)
+{
+  if (!h || !templ || n < 0 || n > h->last_n) { set_last_error("mcp_fe_get_templates: bad arguments"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(templ, h->templ_dev, (size_t)64 * n, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return MCP_OK;
+}
+
+int mcp_fe_shitomasi(McpFe* h, int32_t kf, int32_t level, int32_t n, const int32_t* xy, double* scores)
+{
+  if (!h || kf < 0 || kf >= (int)h->kf_host.size() || level < 0 || level >= MCP_LEVELS || n < 0 || n > h->cfg.max_patches || (n && (!xy || !scores))) {
+    set_last_error("mcp_fe_shitomasi: bad arguments");
+    return MCP_ERR_INVALID;
+  }
+  if (n == 0) return MCP_OK;
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  memcpy(h->aux_host, xy, sizeof(int32_t) * 2 * (size_t)n);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->xy_dev, h->aux_host, sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, s));
+  fe_launch_shitomasi(h->kf_host[kf].lv[level], n, h->xy_dev, h->sc_dev, s);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(scores, h->sc_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MCP_OK;
+}
+
+int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t level, int32_t n, const int32_t* src_xy,
+                          const int32_t* start_xy, int32_t range, int32_t* pos_out, int32_t* found)
+{
+  const int S = h ? (int)h->kf_host.size() : 0;
+  if (!h || kf_src < 0 || kf_src >= S || kf_dst < 0 || kf_dst >= S || level < 0 || level >= MCP_LEVELS || n < 0 || n > h->cfg.max_patches ||
+      (n && (!src_xy || !start_xy || !pos_out || !found))) {
+    set_last_error("mcp_fe_minipatch_find: bad arguments");
+    return MCP_ERR_INVALID;
+  }
+  if (n == 0) return MCP_OK;
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->xy_dev, src_xy, sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(h->xy2_dev, start_xy, sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, s));
+  // n_corners of the destination level is read from the device-side meta through the staged copy of the last keyframe
+  FeMeta meta;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&meta, h->kf_host[kf_dst].meta, sizeof(FeMeta), cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int nc = std::min(meta.lv[level].n_corners, h->cfg.max_corners_per_level);
+  fe_launch_minipatch(h->kf_host[kf_src].lv[level], h->kf_host[kf_dst].lv[level], nc, n, h->xy_dev, h->xy2_dev, range, h->pos_dev, h->found_dev, s);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(pos_out, h->pos_dev, sizeof(int2) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(found, h->found_dev, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MCP_OK;
+}
+
+/* Debug: FAST score map of one level (0 = not a corner at b=5, else fast_corner_score_10), width*height bytes. */
+int mcp_fe_debug_scores(McpFe* h, int32_t slot, int32_t level, uint8_t* out)
+{
+  if (!h || !out || slot < 0 || slot >= (int)h->kf_host.size() || level < 0 || level >= MCP_LEVELS) return MCP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const FeLevel& L = h->kf_host[slot].lv[level];
+  MCP_CUDA_CHECK(cudaMemcpy2D(out, L.w, L.score, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return MCP_OK;
+}
+
+int mcp_fe_get_timing(McpFe* h, McpFeTiming* out) { if (!h || !out) return MCP_ERR_INVALID; *out = h->timing; return MCP_OK; }
+
+}  // extern "C"

@@ -1,0 +1,640 @@
+// fe_kernels.cu — sm_100a kernels of the per-frame front end (integer / byte work, bit-exact by construction).
+//
+//   k_halfsample_fused / k_halfsample   CVD::halfSample x3                      (src/KeyFrame.cc:189-190)
+//   k_fast_score     fast_corner_detect_10(b=5) + fast_corner_score_10 + score histogram   (:259-275)
+//   k_fast_count     adaptive threshold from the histogram (:279-300), per-row corner counts
+//   k_fast_scan      exclusive scan of the row counts = Level::vCornerRowLUT (:348-355)
+//   k_fast_compact   raster-ordered corner list (mask + threshold filter, :302-312)
+//   k_patch_search   one warp per patch: CVD::transform template (src/PatchFinder.cc:135-182), template sums,
+//                    FindPatchCoarse over the row LUT / exhaustive disc (:229-355) with ZMSSDAtPoint (:511-658),
+//                    MakeSubPixTemplate + IterateSubPixToConvergence (:362-470)
+//   k_shitomasi      FindShiTomasiScoreAtPoint (src/ShiTomasi.cc:34-63)
+//   k_minipatch      MiniPatch::SampleFromImage / FindPatch / SSDAtPoint (src/MiniPatch.cc:34-122)
+#include "fe_types.cuh"
+
+namespace mcp {
+
+// ---------------------------------------------------------------------------------------------
+// pyramid
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned avg4(unsigned a, unsigned b, unsigned c, unsigned d, int rnd) { return (a + b + c + d + (rnd ? 2u : 0u)) >> 2; }
+
+// One thread per 8x8 level-0 block -> 4x4 L1, 2x2 L2, 1 L3 pixel (requires w,h multiples of 8).
+__global__ void __launch_bounds__(128) k_halfsample_fused(FeKf kf, int rnd)
+{
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+  const int w3 = kf.lv[3].w;
+  if (bx >= w3) return;
+  const uint8_t* src = kf.lv[0].img + (size_t)(8 * by) * kf.lv[0].pitch + 8 * bx;
+  unsigned l1[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint2 a = *reinterpret_cast<const uint2*>(src + (size_t)(2 * r) * kf.lv[0].pitch);
+    const uint2 b = *reinterpret_cast<const uint2*>(src + (size_t)(2 * r + 1) * kf.lv[0].pitch);
+    const unsigned aw[2] = { a.x, a.y }, bw[2] = { b.x, b.y };
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const unsigned wa = aw[c >> 1] >> (16 * (c & 1)), wb = bw[c >> 1] >> (16 * (c & 1));
+      l1[r][c] = avg4(wa & 0xff, (wa >> 8) & 0xff, wb & 0xff, (wb >> 8) & 0xff, rnd);
+    }
+  }
+  uint8_t* d1 = kf.lv[1].img + (size_t)(4 * by) * kf.lv[1].pitch + 4 * bx;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    *reinterpret_cast<unsigned*>(d1 + (size_t)r * kf.lv[1].pitch) = l1[r][0] | (l1[r][1] << 8) | (l1[r][2] << 16) | (l1[r][3] << 24);
+  unsigned l2[2][2];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) l2[r][c] = avg4(l1[2 * r][2 * c], l1[2 * r][2 * c + 1], l1[2 * r + 1][2 * c], l1[2 * r + 1][2 * c + 1], rnd);
+  uint8_t* d2 = kf.lv[2].img + (size_t)(2 * by) * kf.lv[2].pitch + 2 * bx;
+  *reinterpret_cast<unsigned short*>(d2) = (unsigned short)(l2[0][0] | (l2[0][1] << 8));
+  *reinterpret_cast<unsigned short*>(d2 + kf.lv[2].pitch) = (unsigned short)(l2[1][0] | (l2[1][1] << 8));
+  kf.lv[3].img[(size_t)by * kf.lv[3].pitch + bx] = (uint8_t)avg4(l2[0][0], l2[0][1], l2[1][0], l2[1][1], rnd);
+}
+// generic single level (any size): out = in.size()/2
+__global__ void k_halfsample(const uint8_t* in, int in_pitch, uint8_t* out, int out_pitch, int ow, int oh, int rnd)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  const uint8_t* r0 = in + (size_t)(2 * y) * in_pitch + 2 * x;
+  const uint8_t* r1 = r0 + in_pitch;
+  out[(size_t)y * out_pitch + x] = (uint8_t)avg4(r0[0], r0[1], r1[0], r1[1], rnd);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST-10
+// ---------------------------------------------------------------------------------------------
+__constant__ int c_ring_dx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
+__constant__ int c_ring_dy[16] = { -3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3 };
+
+constexpr int FT_W = 32, FT_H = 8;       // output tile
+constexpr int FT_SW = FT_W + 6, FT_SH = FT_H + 6;
+
+__device__ __forceinline__ bool has_run10(unsigned m)
+{
+  unsigned dd = m | (m << 16);
+  unsigned r = dd & (dd >> 1);      // runs of 2
+  r = r & (r >> 2);                 // 4
+  r = r & (r >> 4);                 // 8
+  r = r & (dd >> 8) & (dd >> 9);    // 10
+  return (r & 0xffffu) != 0;
+}
+
+// blocks are assigned to levels by prefix (kf.tile_off[l])
+__global__ void __launch_bounds__(FT_W* FT_H) k_fast_score(FeKf kf)
+{
+  __shared__ uint8_t tile[FT_SH][FT_SW + 2];
+  __shared__ unsigned hist[32];
+  int l = 0;
+  while (l < MCP_LEVELS - 1 && (int)blockIdx.x >= kf.tile_off[l + 1]) l++;
+  const FeLevel L = kf.lv[l];
+  const int t = blockIdx.x - kf.tile_off[l];
+  const int tiles_x = (L.w + FT_W - 1) / FT_W;
+  const int x0 = (t % tiles_x) * FT_W, y0 = (t / tiles_x) * FT_H;
+  const int tid = threadIdx.y * FT_W + threadIdx.x;
+  if (tid < 32) hist[tid] = 0;
+  for (int i = tid; i < FT_SH * FT_SW; i += FT_W * FT_H) {
+    const int sy = i / FT_SW, sx = i - sy * FT_SW;
+    const int gx = x0 + sx - 3, gy = y0 + sy - 3;
+    tile[sy][sx] = (gx >= 0 && gy >= 0 && gx < L.w && gy < L.h) ? L.img[(size_t)gy * L.pitch + gx] : 0;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  int score = 0;
+  if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
+    const int sx = threadIdx.x + 3, sy = threadIdx.y + 3;
+    const int c = tile[sy][sx];
+    const int b = MCP_MIN_FAST_THRESH;
+    const int cb = c + b, c_b = c - b;
+    int dv[16];
+    unsigned br = 0, dk = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int v = tile[sy + c_ring_dy[i]][sx + c_ring_dx[i]];
+      dv[i] = v - c;
+      br |= (unsigned)(v > cb) << i;
+      dk |= (unsigned)(v < c_b) << i;
+    }
+    if (has_run10(br) || has_run10(dk)) {
+      // fast_corner_score_10: largest t for which the pixel is still a corner = max over arcs of (min |diff|) - 1
+      // fast_corner_score_10 exactly as libCVD does it: bisection on the threshold (bmin = b, bmax = 255),
+      // each probe re-evaluating the FAST-10 criterion with compare masks only.
+      int bmin = b, bmax = 255, tt = (bmax + bmin) / 2;
+      for (;;) {
+        unsigned mb = 0, md = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { mb |= (unsigned)(dv[i] > tt) << i; md |= (unsigned)(dv[i] < -tt) << i; }
+        if (has_run10(mb) || has_run10(md)) bmin = tt; else bmax = tt;
+        if (bmin == bmax - 1 || bmin == bmax) break;
+        tt = (bmin + bmax) / 2;
+      }
+      const int best = bmin;
+      score = best;                                             // 5..254
+#ifdef MCP_FE_DEBUG
+      if (l == 0 && x == 488 && y == 3) { printf("dbg c=%d br=%x dk=%x best=%d dv:", c, br, dk, best); for (int i = 0; i < 16; i++) printf(" %d", dv[i]); printf("\n"); }
+#endif
+      atomicAdd(&hist[min(score, MCP_MAX_FAST_THRESH)], 1u);
+    }
+  }
+  if (x < L.w && y < L.h) L.score[(size_t)y * L.pitch + x] = (uint8_t)score;
+  __syncthreads();
+  if (tid < 32 && hist[tid]) atomicAdd(&L.hist[tid], hist[tid]);
+}
+
+// adaptive threshold from the capped-score histogram (src/KeyFrame.cc:264-300)
+__device__ __forceinline__ int fast_threshold(const unsigned* hist, int w, int h, int* freq_out /*31 or null*/)
+{
+  int freq[32];
+  int acc = 0;
+  for (int t = 31; t >= 0; t--) { acc += (t <= MCP_MAX_FAST_THRESH && t >= MCP_MIN_FAST_THRESH) ? (int)hist[t] : 0; freq[t] = (t >= MCP_MIN_FAST_THRESH && t <= MCP_MAX_FAST_THRESH) ? acc : 0; }
+  if (freq_out) for (int t = 0; t <= 30; t++) freq_out[t] = freq[t];
+  const double target = -1 * (w * h) / 500.0;
+  int thr = MCP_MIN_FAST_THRESH;
+  for (int t = MCP_MIN_FAST_THRESH; t <= MCP_MAX_FAST_THRESH; ++t) {
+    double deriv;
+    if (t == MCP_MIN_FAST_THRESH) deriv = freq[t + 1] - freq[t];
+    else if (t == MCP_MAX_FAST_THRESH) deriv = freq[t] - freq[t - 1];
+    else deriv = (freq[t + 1] - freq[t - 1]) / 2.0;
+    thr = t;
+    if (deriv > target) break;
+  }
+  return thr;
+}
+
+// one warp per image row (all levels): threshold + mask filter count
+__global__ void __launch_bounds__(256) k_fast_count(FeKf kf, int adaptive)
+{
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int l = 0;
+  while (l < MCP_LEVELS - 1 && row >= kf.row_off[l + 1]) l++;
+  if (row >= kf.row_off[MCP_LEVELS]) return;
+  const FeLevel L = kf.lv[l];
+  const int y = row - kf.row_off[l];
+  int thr;
+  if (adaptive) {
+    thr = 0;
+    if (lane == 0) thr = fast_threshold(L.hist, L.w, L.h, y == 0 ? kf.meta->lv[l].fast_freq : nullptr);
+    thr = __shfl_sync(0xffffffffu, thr, 0);
+  } else {
+    thr = kf.fixed_thresh[l];
+    if (y == 0 && lane == 0) for (int t = 0; t <= 30; t++) kf.meta->lv[l].fast_freq[t] = 0;
+  }
+  if (y == 0 && lane == 0) kf.meta->lv[l].fast_thresh = thr;
+  int cnt = 0;
+  const uint8_t* sc = L.score + (size_t)y * L.pitch;
+  const uint8_t* mk = (adaptive && L.mask) ? L.mask + (size_t)y * L.pitch : nullptr;
+  for (int x = lane; x < L.w; x += 32) {
+    const int s = sc[x];
+    cnt += (s >= thr && s > 0 && (!mk || mk[x] == 255)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) L.rowcount[y] = cnt;
+}
+
+// one block per level: exclusive scan of the row counts -> row LUT, total
+__global__ void __launch_bounds__(512) k_fast_scan(FeKf kf)
+{
+  __shared__ int wsum[16];
+  __shared__ int carry;
+  const FeLevel L = kf.lv[blockIdx.x];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < L.h; base += blockDim.x) {
+    const int y = base + threadIdx.x;
+    const int v = y < L.h ? L.rowcount[y] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += wsum[w];
+    if (y < L.h) L.row_lut[y] = off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { kf.meta->lv[blockIdx.x].n_corners = carry; kf.meta->lv[blockIdx.x].width = L.w; kf.meta->lv[blockIdx.x].height = L.h; }
+}
+
+// one warp per row: ordered compaction
+__global__ void __launch_bounds__(256) k_fast_compact(FeKf kf, int adaptive)
+{
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int l = 0;
+  while (l < MCP_LEVELS - 1 && row >= kf.row_off[l + 1]) l++;
+  if (row >= kf.row_off[MCP_LEVELS]) return;
+  const FeLevel L = kf.lv[l];
+  const int y = row - kf.row_off[l];
+  const int thr = kf.meta->lv[l].fast_thresh;
+  int pos = L.row_lut[y];
+  const uint8_t* sc = L.score + (size_t)y * L.pitch;
+  const uint8_t* mk = (adaptive && L.mask) ? L.mask + (size_t)y * L.pitch : nullptr;
+  for (int x0 = 0; x0 < L.w; x0 += 32) {
+    const int x = x0 + lane;
+    bool keep = false;
+    if (x < L.w) { const int s = sc[x]; keep = (s >= thr && s > 0 && (!mk || mk[x] == 255)); }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int idx = pos + __popc(m & ((1u << lane) - 1));
+      if (idx < kf.corner_cap) L.corners[idx] = make_int2(x, y);
+    }
+    pos += __popc(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch search
+// ---------------------------------------------------------------------------------------------
+// 8 bytes at an arbitrary address via two aligned 8-byte loads
+__device__ __forceinline__ unsigned long long load_u8x8(const uint8_t* p)
+{
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(a & 7) * 8;
+  const unsigned long long lo = __ldg(q);
+  if (sh == 0) return lo;
+  const unsigned long long hi = __ldg(q + 1);
+  return (lo >> sh) | (hi << (64 - sh));
+}
+
+// ZMSSDAtPoint (src/PatchFinder.cc:511-658): integer arithmetic, truncating division
+__device__ __forceinline__ int zmssd_at(const FeLevel& L, const unsigned long long* trow /*8 rows packed*/, int tsum, int tsumsq,
+                                        int x, int y, int max_ssd)
+{
+  if (!(x >= 4 && y >= 4 && x < L.w - 4 && y < L.h - 4)) return max_ssd + 1;
+  int isum = 0, isq = 0, cross = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const unsigned long long iv = load_u8x8(L.img + (size_t)(y - 4 + r) * L.pitch + (x - 4));
+    const unsigned long long tv = trow[r];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int n = (int)((iv >> (8 * c)) & 0xff), t = (int)((tv >> (8 * c)) & 0xff);
+      isum += n; isq += n * n; cross += n * t;
+    }
+  }
+  const int SA = tsum, SB = isum;
+  return ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsumsq - 2 * cross);
+}
+
+// CVD::sample<byte,byte>: double bilinear, no fused multiply-add, truncating (or rounding) conversion
+__device__ __forceinline__ uint8_t sample_u8(const FeLevel& L, double x, double y, int rnd)
+{
+  const int lx = (int)x, ly = (int)y;
+  x = __dsub_rn(x, (double)lx); y = __dsub_rn(y, (double)ly);
+  const uint8_t* p = L.img + (size_t)ly * L.pitch + lx;
+  const double a = p[0], b = p[1], c = p[L.pitch], dd = p[L.pitch + 1];
+  const double omx = __dsub_rn(1.0, x), omy = __dsub_rn(1.0, y);
+  const double top = __dadd_rn(__dmul_rn(omx, a), __dmul_rn(x, b));
+  const double bot = __dadd_rn(__dmul_rn(omx, c), __dmul_rn(x, dd));
+  double v = __dadd_rn(__dmul_rn(omy, top), __dmul_rn(y, bot));
+  if (rnd) v = __dadd_rn(v, 0.5);
+  return (uint8_t)v;
+}
+
+// TooN::Cholesky<3> (LDL^T) + get_inverse(), no contraction
+__device__ __forceinline__ void toon_chol3_inverse(const double* A, double* inv)
+{
+  double c[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) c[i] = A[i];
+  bool stop = false;
+  for (int col = 0; col < 3 && !stop; col++) {
+    double inv_diag = 1;
+    for (int row = col; row < 3; row++) {
+      double val = c[row * 3 + col];
+      for (int col2 = 0; col2 < col; col2++) val = __dsub_rn(val, __dmul_rn(c[col2 * 3 + col], c[row * 3 + col2]));
+      if (row == col) { c[row * 3 + col] = val; if (val == 0) { stop = true; break; } inv_diag = __ddiv_rn(1.0, val); }
+      else { c[col * 3 + row] = val; c[row * 3 + col] = __dmul_rn(val, inv_diag); }
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    double v[3] = { 0, 0, 0 }, y[3], r[3];
+    v[k] = 1;
+    for (int i = 0; i < 3; i++) { double val = v[i]; for (int j = 0; j < i; j++) val = __dsub_rn(val, __dmul_rn(c[i * 3 + j], y[j])); y[i] = val; }
+    for (int i = 0; i < 3; i++) y[i] = __ddiv_rn(y[i], c[i * 3 + i]);
+    for (int i = 2; i >= 0; i--) { double val = y[i]; for (int j = i + 1; j < 3; j++) val = __dsub_rn(val, __dmul_rn(c[j * 3 + i], r[j])); r[i] = val; }
+    inv[0 * 3 + k] = r[0]; inv[1 * 3 + k] = r[1]; inv[2 * 3 + k] = r[2];
+  }
+}
+
+__global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot, int n, const McpPatchReq* __restrict__ req,
+                                                     McpPatchRes* __restrict__ res, uint8_t* __restrict__ templ_out)
+{
+  __shared__ uint8_t s_t[4][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (i >= n) return;
+  const McpPatchReq rq = req[i];
+  McpPatchRes out;
+  out.template_bad = 1; out.found = 0; out.did_subpix = 0; out.score = 0; out.coarse_x = 0; out.coarse_y = 0;
+  out.found_x = 0; out.found_y = 0; out.n_candidates = 0; out.pad_ = 0;
+  const int max_ssd = 8 * 8 * 250;                                  // src/PatchFinder.cc:44,61
+  const bool args_ok = rq.src_kf >= 0 && rq.src_kf < fe.n_slots && rq.src_level >= 0 && rq.src_level < MCP_LEVELS &&
+                       rq.search_level >= 0 && rq.search_level < MCP_LEVELS;
+  if (!args_ok) { if (lane == 0) res[i] = out; return; }
+  // ---- template: MakeTemplateCoarseCont -------------------------------------------------------------
+  const FeLevel S = fe.kf[rq.src_kf].lv[rq.src_level];
+  // m2 = M2Inverse(mm2WarpInverse) * LevelScale(mnSearchLevel)       (include/mcptam/SmallMatrixOpts.h)
+  const double wi0 = rq.warp_inv[0], wi1 = rq.warp_inv[1], wi2 = rq.warp_inv[2], wi3 = rq.warp_inv[3];
+  const double det = __dsub_rn(__dmul_rn(wi0, wi3), __dmul_rn(wi1, wi2));
+  const double idet = __ddiv_rn(1.0, det);
+  const double ls = (double)(1 << rq.search_level);
+  const double M0 = __dmul_rn(__dmul_rn(wi3, idet), ls), M1 = __dmul_rn(__dmul_rn(-wi1, idet), ls);
+  const double M2 = __dmul_rn(__dmul_rn(-wi2, idet), ls), M3 = __dmul_rn(__dmul_rn(wi0, idet), ls);
+  const double ax = M0, ay = M2, dx = M1, dy = M3;                   // across = M.T()[0], down = M.T()[1]
+  const double p0x = __dsub_rn((double)rq.src_cx, __dadd_rn(__dmul_rn(M0, 4.0), __dmul_rn(M1, 4.0)));
+  const double p0y = __dsub_rn((double)rq.src_cy, __dadd_rn(__dmul_rn(M2, 4.0), __dmul_rn(M3, 4.0)));
+  double min_x = p0x, min_y = p0y, max_x = p0x, max_y = p0y;
+  if (ax < 0) min_x = __dadd_rn(min_x, __dmul_rn(8.0, ax)); else max_x = __dadd_rn(max_x, __dmul_rn(8.0, ax));
+  if (dx < 0) min_x = __dadd_rn(min_x, __dmul_rn(8.0, dx)); else max_x = __dadd_rn(max_x, __dmul_rn(8.0, dx));
+  if (ay < 0) min_y = __dadd_rn(min_y, __dmul_rn(8.0, ay)); else max_y = __dadd_rn(max_y, __dmul_rn(8.0, ay));
+  if (dy < 0) min_y = __dadd_rn(min_y, __dmul_rn(8.0, dy)); else max_y = __dadd_rn(max_y, __dmul_rn(8.0, dy));
+  const bool all_in = (min_x >= 0 && min_y >= 0 && max_x < S.w - 1 && max_y < S.h - 1);
+  const double crx = __dsub_rn(dx, __dmul_rn(8.0, ax)), cry = __dsub_rn(dy, __dmul_rn(8.0, ay));
+  const double xb = S.w - 1, yb = S.h - 1;
+  // the reference accumulates p incrementally (p += across / carriage_return); replay the same sequence
+  double px = p0x, py = p0y;
+  int n_out = 0;
+  uint8_t mine[2] = { 0, 0 };
+  for (int ii = 0; ii < 8; ++ii) {
+    for (int jj = 0; jj < 8; ++jj) {
+      const int k = ii * 8 + jj;
+      if ((k & 31) == lane) {
+        uint8_t v = 0;
+        if (all_in || (0 <= px && 0 <= py && px < xb && py < yb)) v = sample_u8(S, px, py, fe.transform_round);
+        else n_out++;
+        mine[k >> 5] = v;
+      }
+      px = __dadd_rn(px, ax); py = __dadd_rn(py, ay);
+    }
+    px = __dadd_rn(px, crx); py = __dadd_rn(py, cry);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
+  s_t[wid][lane] = mine[0]; s_t[wid][lane + 32] = mine[1];
+  __syncwarp();
+  if (templ_out) { templ_out[(size_t)i * 64 + lane] = mine[0]; templ_out[(size_t)i * 64 + 32 + lane] = mine[1]; }
+  const bool det_ok = isfinite(idet);
+  out.template_bad = (n_out > 0 || !det_ok) ? 1 : 0;
+  if (out.template_bad) { if (lane == 0) res[i] = out; return; }
+  // template sums and packed rows
+  int tsum = mine[0] + mine[1], tsq = mine[0] * mine[0] + mine[1] * mine[1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { tsum += __shfl_xor_sync(0xffffffffu, tsum, o); tsq += __shfl_xor_sync(0xffffffffu, tsq, o); }
+  unsigned long long trow[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) trow[r] = *reinterpret_cast<const unsigned long long*>(&s_t[wid][r * 8]);
+
+  // ---- FindPatchCoarse --------------------------------------------------------------------------------
+  const FeLevel T = fe.kf[target_slot].lv[rq.search_level];
+  const int n_corners = min(fe.kf[target_slot].meta->lv[rq.search_level].n_corners, fe.kf[target_slot].corner_cap);
+  const int lsc = 1 << rq.search_level;
+  const int ipx = rq.pred_x / lsc, ipy = rq.pred_y / lsc;
+  const unsigned nRange = ((unsigned)rq.range + lsc - 1) / lsc;
+  int nTop = ipy - (int)nRange, nBottomPlusOne = ipy + (int)nRange + 1, nLeft = ipx - (int)nRange;
+  const int nRight = ipx + (int)nRange;
+  bool early = false;
+  if (nTop < 0) nTop = 0;
+  if (nTop >= T.h) early = true;
+  if (nBottomPlusOne <= 0) early = true;
+  if (nLeft < 0) nLeft = 0;
+  if (nLeft >= T.w) early = true;
+  int best_ssd = max_ssd + 1, best_idx = 0x7fffffff, best_x = 0, best_y = 0, n_valid = 0;
+  if (!early) {
+    if (rq.exhaustive) {
+      const int y_end = min(nBottomPlusOne, T.h), x_end = min(nRight + 1, T.w);
+      const int bw = x_end - nLeft, bh = y_end - nTop;
+      const int total = (bw > 0 && bh > 0) ? bw * bh : 0;
+      for (int k = lane; k < total; k += 32) {
+        const int y = nTop + k / bw, x = nLeft + k % bw;
+        if ((unsigned)((ipx - x) * (ipx - x) + (ipy - y) * (ipy - y)) > nRange * nRange) continue;
+        n_valid++;
+        const int s = zmssd_at(T, trow, tsum, tsq, x, y, max_ssd);
+        if (s < best_ssd || (s == best_ssd && k < best_idx)) { best_ssd = s; best_idx = k; best_x = x; best_y = y; }
+      }
+    } else {
+      const int i0 = T.row_lut[nTop];
+      const int i1 = nBottomPlusOne >= T.h ? n_corners : min(T.row_lut[nBottomPlusOne], n_corners);
+      for (int k = i0 + lane; k < i1; k += 32) {
+        const int2 c = T.corners[k];
+        if (c.x < nLeft || c.x > nRight) continue;
+        if ((unsigned)((ipx - c.x) * (ipx - c.x) + (ipy - c.y) * (ipy - c.y)) > nRange * nRange) continue;
+        n_valid++;
+        const int s = zmssd_at(T, trow, tsum, tsq, c.x, c.y, max_ssd);
+        if (s < best_ssd || (s == best_ssd && k < best_idx)) { best_ssd = s; best_idx = k; best_x = c.x; best_y = c.y; }
+      }
+    }
+    // first-best in list order: lexicographic (ssd, index) minimum; ssd == max_ssd+1 with no index never wins
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int os = __shfl_xor_sync(0xffffffffu, best_ssd, o), oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+      const int ox = __shfl_xor_sync(0xffffffffu, best_x, o), oy = __shfl_xor_sync(0xffffffffu, best_y, o);
+      if (os < best_ssd || (os == best_ssd && oi < best_idx)) { best_ssd = os; best_idx = oi; best_x = ox; best_y = oy; }
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    }
+  }
+  out.score = best_ssd;
+  out.n_candidates = n_valid;
+  const bool found = !early && best_ssd < max_ssd;
+  if (!found) { if (early) out.score = max_ssd + 1; if (lane == 0) res[i] = out; return; }
+  out.found = 1;
+  out.coarse_x = best_x; out.coarse_y = best_y;
+  // mv2CoarsePos = LevelZeroPos(irBest, level)   (include/mcptam/LevelHelpers.h:61-64)
+  double posx = __dsub_rn(__dmul_rn(__dadd_rn((double)best_x, 0.5), (double)lsc), 0.5);
+  double posy = __dsub_rn(__dmul_rn(__dadd_rn((double)best_y, 0.5), (double)lsc), 0.5);
+  out.found_x = posx; out.found_y = posy;
+  if (rq.subpix_its <= 0) { if (lane == 0) res[i] = out; return; }
+  // ---- MakeSubPixTemplate + IterateSubPixToConvergence (mixed fp32/fp64, no contraction) ----------------
+  out.did_subpix = 1;
+  // lanes 0..31 and +32: inner pixel k = y*6+x (y,x in 1..6) -> jacobians
+  float jxv[2] = { 0.f, 0.f }, jyv[2] = { 0.f, 0.f };
+  int tv[2] = { 0, 0 };
+  double H[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+  for (int h2 = 0; h2 < 2; h2++) {
+    const int k = lane + 32 * h2;
+    if (k < 36) {
+      const int yy = 1 + k / 6, xx = 1 + k % 6;
+      const uint8_t* t = s_t[wid];
+      const double gx = __dmul_rn(0.5, (double)((int)t[yy * 8 + xx + 1] - (int)t[yy * 8 + xx - 1]));
+      const double gy = __dmul_rn(0.5, (double)((int)t[(yy + 1) * 8 + xx] - (int)t[(yy - 1) * 8 + xx]));
+      jxv[h2] = (float)gx; jyv[h2] = (float)gy; tv[h2] = t[yy * 8 + xx];
+      const double g[3] = { gx, gy, 1.0 };
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) H[r * 3 + c] += g[r] * g[c];   // exact (multiples of 1/4)
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; q++) { for (int o = 16; o > 0; o >>= 1) H[q] += __shfl_xor_sync(0xffffffffu, H[q], o); }
+  double Hinv[9];
+  toon_chol3_inverse(H, Hinv);
+  double mean_diff = 0.0;
+  int converged = 0;
+  for (int it = 0; it < rq.subpix_its; it++) {
+    const double cxl = __dsub_rn(__ddiv_rn(__dadd_rn(posx, 0.5), (double)lsc), 0.5);    // LevelNPos
+    const double cyl = __dsub_rn(__ddiv_rn(__dadd_rn(posy, 0.5), (double)lsc), 0.5);
+    const int rx = (int)(cxl > 0.0 ? __dadd_rn(cxl, 0.5) : __dsub_rn(cxl, 0.5));
+    const int ry = (int)(cyl > 0.0 ? __dadd_rn(cyl, 0.5) : __dsub_rn(cyl, 0.5));
+    if (!(rx >= 5 && ry >= 5 && rx < T.w - 5 && ry < T.h - 5)) { converged = 0; break; }
+    const double bx = __dsub_rn(cxl, 4.0), by = __dsub_rn(cyl, 4.0);
+    const double dX = __dsub_rn(bx, floor(bx)), dY = __dsub_rn(by, floor(by));
+    const float fMixTL = (float)__dmul_rn(__dsub_rn(1.0, dX), __dsub_rn(1.0, dY));
+    const float fMixTR = (float)__dmul_rn(dX, __dsub_rn(1.0, dY));
+    const float fMixBL = (float)__dmul_rn(__dsub_rn(1.0, dX), dY);
+    const float fMixBR = (float)__dmul_rn(dX, dY);
+    const int ibx = (int)bx, iby = (int)by;
+    double dd[2] = { 0, 0 };
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+      const int k = lane + 32 * h2;
+      if (k < 36) {
+        const int yy = 1 + k / 6, xx = 1 + k % 6;
+        const uint8_t* tl = T.img + (size_t)(iby + yy) * T.pitch + ibx + xx;
+        const float fPixel = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fMixTL, (float)tl[0]), __fmul_rn(fMixTR, (float)tl[1])),
+                                                   __fmul_rn(fMixBL, (float)tl[T.pitch])), __fmul_rn(fMixBR, (float)tl[T.pitch + 1]));
+        dd[h2] = __dadd_rn((double)__fsub_rn(fPixel, (float)tv[h2]), mean_diff);
+      }
+    }
+    // sequential accumulation in the reference's pixel order (y outer, x inner)
+    double acc0 = 0, acc1 = 0, acc2 = 0;
+    for (int k = 0; k < 36; k++) {
+      const double dk = __shfl_sync(0xffffffffu, dd[k >> 5], k & 31);
+      const float jxk = __shfl_sync(0xffffffffu, jxv[k >> 5], k & 31), jyk = __shfl_sync(0xffffffffu, jyv[k >> 5], k & 31);
+      acc0 = __dadd_rn(acc0, __dmul_rn(dk, (double)jxk));
+      acc1 = __dadd_rn(acc1, __dmul_rn(dk, (double)jyk));
+      acc2 = __dadd_rn(acc2, dk);
+    }
+    double upd[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      upd[r] = __dadd_rn(__dadd_rn(__dmul_rn(Hinv[r * 3], acc0), __dmul_rn(Hinv[r * 3 + 1], acc1)), __dmul_rn(Hinv[r * 3 + 2], acc2));
+    posx = __dsub_rn(posx, __dmul_rn(upd[0], (double)lsc));
+    posy = __dsub_rn(posy, __dmul_rn(upd[1], (double)lsc));
+    mean_diff = __dsub_rn(mean_diff, upd[2]);
+    const double u2 = __dadd_rn(__dmul_rn(upd[0], upd[0]), __dmul_rn(upd[1], upd[1]));
+    if (u2 < 0.03 * 0.03) { converged = 1; break; }
+  }
+  if (!converged) out.found = 0;                                   // src/Tracker.cc:1355-1362
+  else { out.found_x = posx; out.found_y = posy; }
+  if (lane == 0) res[i] = out;
+}
+
+// FindShiTomasiScoreAtPoint (half box 3), one thread per corner
+__global__ void k_shitomasi(FeLevel L, int n, const int2* __restrict__ xy, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cx = xy[i].x, cy = xy[i].y, hb = 3;
+  if (!(cx >= hb + 1 && cy >= hb + 1 && cx < L.w - hb - 1 && cy < L.h - hb - 1)) { out[i] = 0.0; return; }
+  double dXX = 0, dYY = 0, dXY = 0;
+  for (int y = cy - hb; y <= cy + hb; y++)
+    for (int x = cx - hb; x <= cx + hb; x++) {
+      const double dx = (int)L.img[(size_t)y * L.pitch + x + 1] - (int)L.img[(size_t)y * L.pitch + x - 1];
+      const double dy = (int)L.img[(size_t)(y + 1) * L.pitch + x] - (int)L.img[(size_t)(y - 1) * L.pitch + x];
+      dXX += dx * dx; dYY += dy * dy; dXY += dx * dy;             // exact integers
+    }
+  const int nPixels = (2 * hb + 1) * (2 * hb + 1);
+  dXX = __ddiv_rn(dXX, __dmul_rn(2.0, (double)nPixels));
+  dYY = __ddiv_rn(dYY, __dmul_rn(2.0, (double)nPixels));
+  dXY = __ddiv_rn(dXY, __dmul_rn(2.0, (double)nPixels));
+  const double tr = __dadd_rn(dXX, dYY);
+  const double disc = __dsub_rn(__dmul_rn(tr, tr), __dmul_rn(4.0, __dsub_rn(__dmul_rn(dXX, dYY), __dmul_rn(dXY, dXY))));
+  out[i] = __dmul_rn(0.5, __dsub_rn(tr, sqrt(disc)));
+}
+
+// MiniPatch: one warp per query.  9x9 SSD, first-best over corners in the +-range box (src/MiniPatch.cc:61-113)
+__global__ void __launch_bounds__(128) k_minipatch(FeLevel S, FeLevel T, int n_corners, int n, const int2* __restrict__ src_xy,
+                                                  const int2* __restrict__ start_xy, int range, int2* __restrict__ pos_out,
+                                                  int* __restrict__ found)
+{
+  __shared__ uint8_t s_p[4][81 + 3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (i >= n) return;
+  const int2 sp = src_xy[i], st = start_xy[i];
+  const bool ok = sp.x >= 4 && sp.y >= 4 && sp.x < S.w - 4 && sp.y < S.h - 4;      // assert in SampleFromImage
+  for (int k = lane; k < 81; k += 32) s_p[wid][k] = ok ? S.img[(size_t)(sp.y - 4 + k / 9) * S.pitch + sp.x - 4 + k % 9] : 0;
+  __syncwarp();
+  const int max_ssd = 9999;
+  int best = max_ssd + 1, best_idx = 0x7fffffff, bx = 0, by = 0;
+  const int tlx = st.x - range, tly = st.y - range, brx = st.x + range, bry = st.y + range;
+  int top = tly;
+  if (top < 0) top = 0;
+  if (top >= T.h) top = T.h - 1;
+  const int i0 = T.row_lut[top];
+  const int bot = bry + 1;
+  const int i1 = bot >= T.h ? n_corners : (bot < 0 ? 0 : min(T.row_lut[bot], n_corners));
+  if (ok)
+    for (int k = i0 + lane; k < i1; k += 32) {
+      const int2 c = T.corners[k];
+      if (c.x < tlx || c.x > brx) continue;
+      int s = max_ssd + 1;
+      if (c.x >= 4 && c.y >= 4 && c.x < T.w - 4 && c.y < T.h - 4) {
+        s = 0;
+        for (int r = 0; r < 9; r++) {
+          const uint8_t* ip = T.img + (size_t)(c.y - 4 + r) * T.pitch + c.x - 4;
+          for (int cc = 0; cc < 9; cc++) { const int dfr = (int)ip[cc] - (int)s_p[wid][r * 9 + cc]; s += dfr * dfr; }
+        }
+      }
+      if (s < best || (s == best && k < best_idx)) { best = s; best_idx = k; bx = c.x; by = c.y; }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int os = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    const int ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o);
+    if (os < best || (os == best && oi < best_idx)) { best = os; best_idx = oi; bx = ox; by = oy; }
+  }
+  if (lane == 0) {
+    const int f = (ok && best < max_ssd) ? 1 : 0;
+    found[i] = f;
+    pos_out[i] = f ? make_int2(bx, by) : st;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s)
+{
+  const bool fused = (kf.lv[0].w % 8 == 0) && (kf.lv[0].h % 8 == 0) && kf.lv[1].w == kf.lv[0].w / 2 && kf.lv[3].w == kf.lv[0].w / 8;
+  if (fused) {
+    dim3 grid((kf.lv[3].w + 127) / 128, kf.lv[3].h);
+    k_halfsample_fused<<<grid, 128, 0, s>>>(kf, rnd);
+  } else {
+    for (int l = 1; l < MCP_LEVELS; l++) {
+      dim3 blk(32, 8), grid((kf.lv[l].w + 31) / 32, (kf.lv[l].h + 7) / 8);
+      k_halfsample<<<grid, blk, 0, s>>>(kf.lv[l - 1].img, kf.lv[l - 1].pitch, kf.lv[l].img, kf.lv[l].pitch, kf.lv[l].w, kf.lv[l].h, rnd);
+    }
+  }
+}
+int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s)
+{
+  dim3 blk(FT_W, FT_H);
+  k_fast_score<<<kf.tile_off[MCP_LEVELS], blk, 0, s>>>(kf);
+  const int rows = kf.row_off[MCP_LEVELS];
+  k_fast_count<<<(rows + 7) / 8, 256, 0, s>>>(kf, adaptive);
+  k_fast_scan<<<MCP_LEVELS, 512, 0, s>>>(kf);
+  k_fast_compact<<<(rows + 7) / 8, 256, 0, s>>>(kf, adaptive);
+  return 4;
+}
+void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s)
+{
+  if (n <= 0) return;
+  k_patch_search<<<(n + 3) / 4, 128, 0, s>>>(fe, target, n, req, res, templ);
+}
+void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s)
+{
+  if (n > 0) k_shitomasi<<<(n + 127) / 128, 128, 0, s>>>(L, n, xy, out);
+}
+void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
+                         int2* pos, int* found, cudaStream_t s)
+{
+  if (n > 0) k_minipatch<<<(n + 3) / 4, 128, 0, s>>>(S, T, n_corners, n, src, start, range, pos, found);
+}
+
+}  // namespace mcp

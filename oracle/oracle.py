@@ -80,7 +80,7 @@ def lib():
         L.ora_patch_template.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.ora_zmssd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 5
         L.ora_find_patch_coarse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                            C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+                                            C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
         L.ora_subpix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ora_minipatch_ssd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.ora_minipatch_find.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -178,3 +178,143 @@ class OracleBA:
         s = C.c_double(); r = C.c_double()
         rc = self.L.ora_ba_lm_step(self.h, float(lam), float(sigma_sq), solve_mode, _p(d), C.byref(s), C.byref(r))
         return rc, d, s.value, r.value
+
+
+# ---------------------------------------------------------------------------------------------
+# front-end wrappers (numpy in / numpy out)
+# ---------------------------------------------------------------------------------------------
+def halfsample(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h // 2, w // 2), np.uint8)
+    lib().ora_halfsample(_p(img), w, h, w, _p(out), w // 2)
+    return out
+
+
+def pyramid(img, levels=4):
+    out = [np.ascontiguousarray(img, np.uint8)]
+    for _ in range(levels - 1):
+        out.append(halfsample(out[-1]))
+    return out
+
+
+def fast10_detect(img, b, brute=False, n_arc=10):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    L = lib()
+    if brute:
+        n = L.ora_fastN_detect_bruteforce(_p(img), w, h, w, b, n_arc, None, 0)
+        xy = np.zeros((max(n, 1), 2), np.int32)
+        L.ora_fastN_detect_bruteforce(_p(img), w, h, w, b, n_arc, _p(xy), n)
+    else:
+        n = L.ora_fast10_detect(_p(img), w, h, w, b, None, 0)
+        xy = np.zeros((max(n, 1), 2), np.int32)
+        L.ora_fast10_detect(_p(img), w, h, w, b, _p(xy), n)
+    return xy[:n]
+
+
+def fast10_score(img, xy, b, bisect=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int32)
+    sc = np.zeros(max(len(xy), 1), np.int32)
+    f = lib().ora_fast10_score_bisect if bisect else lib().ora_fast10_score
+    f(_p(img), img.shape[1], _p(xy), len(xy), b, _p(sc))
+    return sc[:len(xy)]
+
+
+def level_corners(img, mask=None, adaptive=True, fixed_thresh=10, cap=1 << 20):
+    """One pyramid level of MakeKeyFrame_Lite."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    xy = np.zeros((cap, 2), np.int32)
+    freq = np.zeros(31, np.int32)
+    thr = C.c_int32()
+    lut = np.zeros(h, np.int32)
+    m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+    n = lib().ora_level_corners(_p(img), w, h, w, _p(m), w if m is not None else 0, int(adaptive), fixed_thresh, _p(xy), cap,
+                                _p(freq), C.byref(thr), _p(lut))
+    return {"corners": xy[:n].copy(), "n_corners": n, "fast_freq": freq, "fast_thresh": thr.value, "row_lut": lut}
+
+
+def shitomasi(img, x, y, half_box=3):
+    img = np.ascontiguousarray(img, np.uint8)
+    return lib().ora_shitomasi(_p(img), img.shape[1], half_box, int(x), int(y))
+
+
+def warp_matrix(warp_inv, level):
+    """opts::M2Inverse(mm2WarpInverse) * LevelScale(level)  (src/PatchFinder.cc:138)."""
+    m = np.asarray(warp_inv, np.float64).reshape(2, 2)
+    det = m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]
+    idet = 1.0 / det
+    r = np.array([[m[1, 1] * idet, -m[0, 1] * idet], [-m[1, 0] * idet, m[0, 0] * idet]])
+    return r * float(1 << level)
+
+
+def patch_template(src_img, m2, cx, cy):
+    src_img = np.ascontiguousarray(src_img, np.uint8)
+    m2 = np.ascontiguousarray(m2, np.float64)
+    t = np.zeros(64, np.uint8)
+    nout = lib().ora_patch_template(_p(src_img), src_img.shape[1], src_img.shape[0], src_img.shape[1], _p(m2), float(cx), float(cy), _p(t))
+    return t, nout
+
+
+def find_patch_coarse(img, corners, lut, templ, level, pred, rng, exhaustive=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    corners = np.ascontiguousarray(corners, np.int32)
+    lut = np.ascontiguousarray(lut, np.int32)
+    best = np.zeros(2, np.int32)
+    score = C.c_int32()
+    f = lib().ora_find_patch_coarse(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(corners), len(corners), _p(lut),
+                                    _p(np.ascontiguousarray(templ, np.uint8)), level, int(pred[0]), int(pred[1]), rng,
+                                    int(exhaustive), _p(best), C.byref(score))
+    return bool(f), best, score.value
+
+
+def subpix(img, templ, level, pos, max_its):
+    img = np.ascontiguousarray(img, np.uint8)
+    p = np.array(pos, np.float64)
+    ok = lib().ora_subpix(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(np.ascontiguousarray(templ, np.uint8)), level, _p(p), max_its)
+    return bool(ok), p
+
+
+def search_patch(pyr_src, pyr_tgt, tgt_levels, req):
+    """Oracle of one Tracker::SearchForPoints iteration (src/Tracker.cc:1299-1377) for one request dict/record."""
+    res = dict(template_bad=1, found=0, did_subpix=0, score=0, coarse_x=0, coarse_y=0, found_x=0.0, found_y=0.0)
+    lvl = int(req["search_level"])
+    m2 = warp_matrix(req["warp_inv"], lvl)
+    t, nout = patch_template(pyr_src[int(req["src_level"])], m2, req["src_cx"], req["src_cy"])
+    res["template"] = t
+    if nout:
+        return res
+    res["template_bad"] = 0
+    L = tgt_levels[lvl]
+    found, best, score = find_patch_coarse(pyr_tgt[lvl], L["corners"], L["row_lut"], t, lvl, (req["pred_x"], req["pred_y"]),
+                                           int(req["range"]), bool(req["exhaustive"]))
+    res["score"] = score
+    if not found:
+        return res
+    res.update(found=1, coarse_x=int(best[0]), coarse_y=int(best[1]))
+    ls = 1 << lvl
+    pos = ((best[0] + 0.5) * ls - 0.5, (best[1] + 0.5) * ls - 0.5)
+    res.update(found_x=pos[0], found_y=pos[1])
+    if int(req["subpix_its"]) > 0:
+        res["did_subpix"] = 1
+        ok, p = subpix(pyr_tgt[lvl], t, lvl, pos, int(req["subpix_its"]))
+        if not ok:
+            res["found"] = 0
+        else:
+            res.update(found_x=float(p[0]), found_y=float(p[1]))
+    return res
+
+
+def minipatch_find(img_src, img_dst, corners, lut, src_xy, start_xy, rng):
+    img_src = np.ascontiguousarray(img_src, np.uint8)
+    img_dst = np.ascontiguousarray(img_dst, np.uint8)
+    corners = np.ascontiguousarray(corners, np.int32)
+    lut = np.ascontiguousarray(lut, np.int32)
+    x, y = int(src_xy[0]), int(src_xy[1])
+    patch = np.ascontiguousarray(img_src[y - 4:y + 5, x - 4:x + 5]).reshape(-1)
+    pos = np.array(start_xy, np.int32)
+    f = lib().ora_minipatch_find(_p(img_dst), img_dst.shape[1], img_dst.shape[0], img_dst.shape[1], _p(patch), _p(corners), len(corners),
+                                 _p(lut), len(lut), rng, _p(pos))
+    return bool(f), pos

@@ -1,0 +1,206 @@
+"""GPU parity tests of the front end: CUDA path (through the C ABI) vs the CPU oracle (oracle/fe_oracle.c).
+
+Integer / byte / index work is compared bit-exactly; the mixed fp32/fp64 sub-pixel refinement is compared
+bit-exactly too (the kernel forbids FMA contraction on that path, the oracle is built with -ffp-contract=off).
+The comparator is a RESTATEMENT of the reference (parity unpinned, see oracle/oracle.h).
+"""
+import numpy as np
+import pytest
+
+from mcptam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mcptam_b200 import capi
+    capi.lib()
+    return capi
+
+
+@pytest.fixture(scope="module")
+def ora():
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+def _check_levels(ora, img, lv, mask=None, adaptive=True):
+    pyr = ora.pyramid(img)
+    mpyr = ora.pyramid(mask) if mask is not None else [None] * 4
+    fixed = [10, 15, 15, 10]
+    for l in range(4):
+        ref = ora.level_corners(pyr[l], mask=mpyr[l] if adaptive else None, adaptive=adaptive, fixed_thresh=fixed[l])
+        assert lv[l]["n_corners"] == ref["n_corners"], (l, lv[l]["n_corners"], ref["n_corners"])
+        assert lv[l]["fast_thresh"] == ref["fast_thresh"]
+        assert np.array_equal(lv[l]["fast_freq"], ref["fast_freq"])
+        assert np.array_equal(lv[l]["corners"], ref["corners"])                 # raster order, index-exact
+        assert np.array_equal(lv[l]["row_lut"][: pyr[l].shape[0]], ref["row_lut"])
+    return pyr
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_pyramid_and_corners(capi, ora, seed):
+    img = synth.make_frame(seed=seed)
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    lv = f.make_keyframe(0, img, want_images=True)
+    pyr = _check_levels(ora, img, lv)
+    for l in range(4):
+        h, w = pyr[l].shape
+        assert np.array_equal(lv[l]["image"].reshape(-1)[: h * w].reshape(h, w), pyr[l])
+
+
+def test_corners_with_mask_and_fixed_threshold(capi, ora):
+    img = synth.make_frame(seed=4)
+    mask = np.full((480, 640), 255, np.uint8)
+    mask[100:300, 200:420] = 0
+    mask[::7, ::5] = 128
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    f.set_mask(mask)
+    _check_levels(ora, img, f.make_keyframe(0, img), mask=mask)
+    f.set_mask(None)
+    _check_levels(ora, img, f.make_keyframe(1, img))
+    g = capi.FeHandle(640, 480, adaptive_thresh=0, max_corners_per_level=16384)
+    _check_levels(ora, img, g.make_keyframe(0, img), adaptive=False)
+
+
+def test_odd_size_and_edge_images(capi, ora):
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (250, 330), dtype=np.uint8)       # not a multiple of 8: generic pyramid path
+    f = capi.FeHandle(330, 250, max_corners_per_level=1 << 16)
+    lv = f.make_keyframe(0, img)
+    _check_levels(ora, img, lv)
+    flat = np.full((250, 330), 77, np.uint8)                     # no corners at all
+    lv = f.make_keyframe(1, flat)
+    assert all(l["n_corners"] == 0 for l in lv)
+    sat = np.zeros((250, 330), np.uint8); sat[::2, ::2] = 255    # extreme contrast, maximum scores
+    _check_levels(ora, sat, f.make_keyframe(2, sat))
+
+
+def _make_requests(capi, rng, lv_src, n, shift, src_slot=0, subpix=True, exhaustive_frac=0.05):
+    req = np.zeros(n, capi.PATCH_REQ_DTYPE)
+    k = 0
+    while k < n:
+        sl = int(rng.integers(0, 4))
+        cor = lv_src[sl]["corners"]
+        if len(cor) == 0:
+            continue
+        cx, cy = cor[rng.integers(len(cor))]
+        w, h = lv_src[sl]["width"], lv_src[sl]["height"]
+        if not (10 <= cx < w - 10 and 10 <= cy < h - 10):
+            if rng.random() < 0.9:
+                continue
+        ang = rng.normal(0, 0.08)
+        sc = np.exp(rng.normal(0, 0.08)) * (1 << sl)     # warp_inv maps source-level pixels to level-0 target pixels
+        A = sc * np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+        det = np.linalg.det(A)
+        lvl = 0
+        while det > 3 and lvl < 3:
+            lvl += 1
+            det *= 0.25
+        l0 = ((cx + 0.5) * (1 << sl) - 0.5 - shift[0], (cy + 0.5) * (1 << sl) - 0.5 - shift[1])
+        r = req[k]
+        r["src_kf"] = src_slot; r["src_level"] = sl; r["src_cx"] = cx; r["src_cy"] = cy
+        r["warp_inv"] = A.reshape(-1)
+        r["search_level"] = lvl
+        r["pred_x"] = int(l0[0] + rng.uniform(-3, 3)); r["pred_y"] = int(l0[1] + rng.uniform(-3, 3))
+        r["range"] = int(rng.choice([5, 10, 30]))
+        r["subpix_its"] = int(rng.choice([0, 8, 10])) if subpix else 0
+        r["exhaustive"] = int(rng.random() < exhaustive_frac)
+        if r["exhaustive"]:
+            r["range"] = 10
+            r["subpix_its"] = 10
+        k += 1
+    return req
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_patch_search_parity(capi, ora, seed):
+    rng = np.random.default_rng(seed)
+    shift = (3.0, -2.0)
+    a = synth.make_frame(seed=seed)
+    b = synth.make_frame(seed=seed, shift=shift)
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    lva = f.make_keyframe(0, a)
+    lvb = f.make_keyframe(1, b)
+    req = _make_requests(capi, rng, lva, 600, shift)
+    # some requests off the image / degenerate
+    req[0]["pred_x"] = -50; req[1]["pred_y"] = 5000; req[2]["src_cx"] = 1; req[2]["src_cy"] = 1
+    res = f.search_patches(1, req)
+    templ = f.templates(len(req))
+    pa, pb = ora.pyramid(a), ora.pyramid(b)
+    tl = [ora.level_corners(im) for im in pb]
+    n_found = n_sub = 0
+    for i in range(len(req)):
+        ref = ora.search_patch(pa, pb, tl, req[i])
+        assert res[i]["template_bad"] == ref["template_bad"], i
+        if not ref["template_bad"]:
+            assert np.array_equal(templ[i], ref["template"]), i           # CVD::transform bytes
+        assert res[i]["found"] == ref["found"], (i, res[i], ref)
+        if not ref["template_bad"]:
+            assert res[i]["score"] == ref["score"], (i, res[i]["score"], ref["score"])
+        if ref["found"]:
+            n_found += 1
+            assert (res[i]["coarse_x"], res[i]["coarse_y"]) == (ref["coarse_x"], ref["coarse_y"])
+            assert res[i]["did_subpix"] == ref["did_subpix"]
+            n_sub += ref["did_subpix"]
+            assert res[i]["found_x"] == ref["found_x"] and res[i]["found_y"] == ref["found_y"], (i, res[i], ref)
+    assert n_found > 200 and n_sub > 100                                   # the test exercises the interesting paths
+
+
+def test_patch_search_identity_recovers_shift(capi):
+    """Size-independent property: with an identity warp the search finds each corner at the shifted position."""
+    rng = np.random.default_rng(5)
+    shift = (4.0, 1.0)
+    a = synth.make_frame(seed=21)
+    b = synth.make_frame(seed=21, shift=shift)
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    lva = f.make_keyframe(0, a)
+    f.make_keyframe(1, b, outputs=False)
+    cor = lva[0]["corners"]
+    cor = cor[(cor[:, 0] > 20) & (cor[:, 0] < 620) & (cor[:, 1] > 20) & (cor[:, 1] < 460)]
+    cor = cor[rng.choice(len(cor), 1000, replace=False)]
+    req = np.zeros(len(cor), capi.PATCH_REQ_DTYPE)
+    req["src_kf"] = 0; req["src_level"] = 0; req["src_cx"] = cor[:, 0]; req["src_cy"] = cor[:, 1]
+    req["warp_inv"] = np.array([1.0, 0, 0, 1.0]); req["search_level"] = 0
+    req["pred_x"] = cor[:, 0] - 4; req["pred_y"] = cor[:, 1] - 1
+    req["range"] = 10; req["subpix_its"] = 8
+    res = f.search_patches(1, req)
+    ok = res["found"] == 1
+    assert ok.mean() > 0.9
+    err = np.hypot(res["found_x"][ok] - (cor[ok, 0] - shift[0]), res["found_y"][ok] - (cor[ok, 1] - shift[1]))
+    assert np.median(err) < 0.2
+
+
+def test_shitomasi_and_minipatch(capi, ora):
+    rng = np.random.default_rng(9)
+    a = synth.make_frame(seed=31)
+    b = synth.make_frame(seed=31, shift=(2.0, 1.0))
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    lva = f.make_keyframe(0, a)
+    lvb = f.make_keyframe(1, b)
+    pa, pb = ora.pyramid(a), ora.pyramid(b)
+    for l in (0, 2):
+        cor = lva[l]["corners"]
+        h, w = pa[l].shape
+        cor = cor[(cor[:, 0] >= 10) & (cor[:, 0] < w - 10) & (cor[:, 1] >= 10) & (cor[:, 1] < h - 10)][:300]
+        st = f.shitomasi(0, l, cor)
+        ref = np.array([ora.shitomasi(pa[l], x, y) for x, y in cor])
+        assert np.array_equal(st, ref)
+        start = cor + rng.integers(-3, 4, cor.shape)
+        pos, found = f.minipatch_find(0, 1, l, cor, start, 10)
+        for i in range(len(cor)):
+            fr, pr = ora.minipatch_find(pa[l], pb[l], lvb[l]["corners"], lvb[l]["row_lut"][: pb[l].shape[0]], cor[i], start[i], 10)
+            assert bool(found[i]) == fr, i
+            if fr:
+                assert tuple(pos[i]) == tuple(pr), i
+
+
+def test_fe_errors(capi):
+    f = capi.FeHandle(640, 480)
+    req = np.zeros(1, capi.PATCH_REQ_DTYPE)
+    with pytest.raises(capi.McpError):
+        f.search_patches(0, req)                                  # empty keyframe slot
+    with pytest.raises(capi.McpError):
+        f.make_keyframe(99, np.zeros((480, 640), np.uint8))

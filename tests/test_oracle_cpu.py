@@ -1,0 +1,191 @@
+"""CPU tests (no GPU): the oracle against its own invariants, an independent library (OpenCV FAST 9-16) and
+the committed golden fixtures.  The reference has no tests or golden vectors (parity unpinned)."""
+import os
+
+import numpy as np
+import pytest
+
+from mcptam_b200 import synth
+from oracle import oracle as ora
+from oracle.oracle import OracleBA
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return synth.make_ba_config("tiny", seed=0)
+
+
+def test_camera_project_unproject_roundtrip():
+    cam = synth.make_rig(1, np.random.default_rng(0))[0][0]
+    rng = np.random.default_rng(1)
+    px = rng.uniform([40, 40], [600, 440], (200, 2))
+    ray = synth.cam_unproject_np(cam, px)
+    back, invalid = synth.cam_project_np(cam, ray * 3.7)
+    assert not invalid.any()
+    assert np.abs(back - px).max() < 2e-4          # inverse polynomial fitted to 1e-4 px (src/TaylorCamera.cc:157)
+    # C oracle projection agrees with the numpy restatement
+    L = ora.lib()
+    out = np.zeros(2); D = np.zeros(4)
+    import ctypes as C
+    for r, p in zip(ray[:20], back[:20]):
+        v = np.ascontiguousarray(r * 3.7)
+        L.ora_cam_project(C.byref(cam), ora._p(v), ora._p(out), ora._p(D))
+        assert np.allclose(out, p, atol=1e-9)
+
+
+def test_analytic_vs_numeric_jacobians(tiny):
+    """The reference's own (commented-out) validation: central differences, src/ChainBundle.cc:688-740."""
+    prob = tiny
+    o = OracleBA(prob)
+    rng = np.random.default_rng(2)
+    d = 1e-6
+    for m in rng.choice(prob.n_meas, 25, replace=False):
+        jo, js, jp = o.jacobians(m)
+        P0, X0 = o.poses(), o.points()
+        err = lambda: o.eval()[0][m].copy()
+        obs0, src0 = prob.meas_chain[m][0], prob.pt_chain[prob.meas_pt[m]][0]
+        for pid in {obs0, src0}:
+            if prob.pose_fixed[pid]:
+                continue
+            num = np.zeros((2, 6))
+            for k in range(6):
+                dd = np.zeros(6); dd[k] = d
+                o.set_state(P0, X0); o.oplus_pose(pid, dd); ep = err()
+                o.set_state(P0, X0); o.oplus_pose(pid, -dd); em = err()
+                num[:, k] = (ep - em) / (2 * d)
+            o.set_state(P0, X0)
+            tot = (jo[0] if obs0 == pid else 0) + (js[0] if src0 == pid else 0)
+            assert np.abs(num - tot).max() <= 2e-5 * max(1.0, np.abs(num).max())
+        p = prob.meas_pt[m]
+        num = np.zeros((2, 3))
+        for k in range(3):
+            dd = np.zeros(3); dd[k] = d * (0.01 if k == 2 else 1)
+            o.set_state(P0, X0); o.oplus_point(p, dd); ep = err()
+            o.set_state(P0, X0); o.oplus_point(p, -dd); em = err()
+            num[:, k] = (ep - em) / (2 * dd[k])
+        o.set_state(P0, X0)
+        assert np.abs(num - jp).max() <= 2e-5 * max(1.0, np.abs(num).max())
+
+
+def test_schur_equals_full_system(tiny):
+    """The per-point Schur complement + dense pose solve is the reference's full (poses+points) CHOLMOD solve."""
+    o = OracleBA(tiny)
+    for lam in (1e-3, 1.0, 100.0):
+        rc0, d0, s0, _ = o.lm_step(lam, -1, 0)
+        rc1, d1, s1, _ = o.lm_step(lam, -1, 1)
+        assert rc0 == 0 and rc1 == 0 and s0 == s1
+        assert np.linalg.norm(d0 - d1) <= 1e-9 * np.linalg.norm(d1)
+
+
+def test_huber_tukey_sigma():
+    v = np.random.default_rng(3).uniform(0, 10, 101)
+    srt = np.sort(v)
+    med = srt[len(v) // 2]
+    s = 1.4826 * (1 + 5.0 / (len(v) * 2 - 6)) * np.sqrt(med)
+    assert ora.lib().ora_huber_sigma_sq(ora._p(v), len(v)) == pytest.approx((1.345 * s) ** 2, rel=1e-15)
+    assert ora.lib().ora_tukey_sigma_sq(ora._p(v), len(v)) == pytest.approx((4.6851 * s) ** 2, rel=1e-15)
+
+
+def test_lm_converges_noise_free():
+    prob = synth.make_ba_problem(n_cam=2, n_mkf=5, n_pt=150, seed=7, outlier_frac=0.0, pix_sigma=0.0)
+    o = OracleBA(prob)
+    rc, st = o.compute(60)
+    assert rc > 0
+    assert np.abs(o.poses() - prob.truth_pose_Rt).max() < 1e-5
+    assert np.abs(o.points() - prob.truth_pt_xyz).max() < 1e-4
+
+
+def test_ba_golden(tiny):
+    g = np.load(os.path.join(GOLD, "ba_tiny_seed0.npz"))
+    o = OracleBA(tiny)
+    e, c = o.eval()
+    assert np.allclose(e, g["err"], rtol=1e-12, atol=1e-12) and np.allclose(c, g["chi2"], rtol=1e-12, atol=1e-12)
+    rc, delta, sig, chi = o.lm_step(10.0, -1.0, 0)
+    assert np.allclose(delta, g["lm_delta"], rtol=1e-9, atol=1e-12) and sig == pytest.approx(float(g["lm_sigma_sq"]), rel=1e-12)
+    rc, st = o.compute(8)
+    assert st.iterations == int(g["iterations"]) and st.total_trials == int(g["total_trials"])
+    assert np.allclose(o.points(), g["points"], rtol=1e-9) and np.allclose(o.poses(), g["poses"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(o.outliers(), g["outliers"])
+
+
+# ---- front end ---------------------------------------------------------------------------------------
+def test_halfsample_definition():
+    img = np.random.default_rng(0).integers(0, 256, (37, 51), dtype=np.uint8)
+    out = ora.halfsample(img)
+    a = img[:36:2, :50:2].astype(int) + img[:36:2, 1:51:2] + img[1:37:2, :50:2] + img[1:37:2, 1:51:2]
+    assert out.shape == (18, 25) and np.array_equal(out, (a // 4).astype(np.uint8))
+
+
+def test_fast_detector_pins():
+    img = synth.make_frame(w=320, h=240, seed=2, n_shapes=100)
+    for b in (5, 20, 60):
+        assert np.array_equal(ora.fast10_detect(img, b), ora.fast10_detect(img, b, brute=True))
+    xy = ora.fast10_detect(img, 5)
+    assert np.array_equal(ora.fast10_score(img, xy, 5), ora.fast10_score(img, xy, 5, bisect=True))
+    assert (np.diff(xy[:, 1] * 10000 + xy[:, 0]) > 0).all()           # raster order
+    assert xy[:, 0].min() >= 3 and xy[:, 1].min() >= 3 and xy[:, 0].max() < 317 and xy[:, 1].max() < 237
+
+
+def test_fast_ring_against_opencv():
+    """Independent pin of the ring layout / strict comparisons / border: 9-of-16 mode == cv2 FAST TYPE_9_16."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_frame(w=320, h=240, seed=3, n_shapes=100)
+    for thr in (10, 25):
+        f = cv2.FastFeatureDetector_create(threshold=thr, nonmaxSuppression=False, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        cvxy = sorted((int(k.pt[1]), int(k.pt[0])) for k in f.detect(img, None))
+        mine = sorted((int(y), int(x)) for x, y in ora.fast10_detect(img, thr, brute=True, n_arc=9))
+        assert cvxy == mine
+
+
+def test_level_corners_golden_and_lut():
+    g = np.load(os.path.join(GOLD, "fe_320x240_seed5.npz"))
+    for l, im in enumerate(ora.pyramid(g["img"])):
+        r = ora.level_corners(im)
+        assert np.array_equal(r["corners"], g["corners%d" % l]) and np.array_equal(r["row_lut"], g["lut%d" % l])
+        assert r["fast_thresh"] == int(g["thresh%d" % l]) and np.array_equal(r["fast_freq"], g["freq%d" % l])
+        ys = r["corners"][:, 1]
+        for y in range(im.shape[0]):                                  # LUT[y] = first corner with row >= y
+            assert r["row_lut"][y] == np.searchsorted(ys, y, side="left")
+        # mask filter: masked-out pixels never survive; the threshold is chosen before masking
+        mask = np.full(im.shape, 255, np.uint8); mask[:, : im.shape[1] // 2] = 0
+        rm = ora.level_corners(im, mask=mask)
+        assert rm["fast_thresh"] == r["fast_thresh"] and (rm["corners"][:, 0] >= im.shape[1] // 2).all()
+
+
+def test_zmssd_identity_and_template_copy():
+    img = synth.make_frame(w=320, h=240, seed=4, n_shapes=60)
+    t, nout = ora.patch_template(img, np.eye(2), 100, 80)
+    assert nout == 0 and np.array_equal(t.reshape(8, 8), img[76:84, 96:104])     # identity warp = plain copy
+    L = ora.lib()
+    tsum, tsq = int(t.astype(int).sum()), int((t.astype(int) ** 2).sum())
+    assert L.ora_zmssd(ora._p(img), 320, 240, 320, ora._p(t), tsum, tsq, 100, 80, 16000) == 0
+    a = img[50:58, 60:68].astype(int); b = t.reshape(8, 8).astype(int)
+    SA, SB = b.sum(), a.sum()
+    num = 2 * SA * SB - SA * SA - SB * SB
+    ref = int(np.trunc(num / 64)) + (a * a).sum() + (b * b).sum() - 2 * (a * b).sum()   # truncating division
+    assert L.ora_zmssd(ora._p(img), 320, 240, 320, ora._p(t), tsum, tsq, 64, 54, 16000) == ref
+    assert L.ora_zmssd(ora._p(img), 320, 240, 320, ora._p(t), tsum, tsq, 3, 54, 16000) == 16001  # border
+    _, nout = ora.patch_template(img, np.eye(2) * 3.0, 2, 2)
+    assert nout > 0                                                     # leaves the image -> template bad
+
+
+def test_subpix_recovers_translation():
+    from scipy import ndimage
+    a = synth.make_frame(w=320, h=240, seed=6, n_shapes=80)
+    a = np.clip(np.rint(ndimage.gaussian_filter(a.astype(float), 1.0)), 0, 255).astype(np.uint8)
+    # B(x, y) = A(x + 0.4, y - 0.3) by bilinear resampling: a feature at (cx, cy) in A sits at (cx - 0.4, cy + 0.3) in B
+    b = np.clip(np.rint(ndimage.shift(a.astype(float), (0.3, -0.4), order=1, mode="nearest")), 0, 255).astype(np.uint8)
+    la = ora.level_corners(a)
+    n_ok = 0
+    errs = []
+    for cx, cy in la["corners"][::15]:
+        if not (12 <= cx < 308 and 12 <= cy < 228):
+            continue
+        t, nout = ora.patch_template(a, np.eye(2), cx, cy)
+        ok, p = ora.subpix(b, t, 0, (float(cx), float(cy)), 10)
+        if ok:
+            n_ok += 1
+            errs.append(np.hypot(p[0] - (cx - 0.4), p[1] - (cy + 0.3)))
+    assert n_ok > 20 and np.median(errs) < 0.15
