@@ -102,6 +102,53 @@ def cpu_reference_run(prob, steps, warmup, lm_iters_cpu):
     return total_it / total_t, float(np.mean(per_step)) * 1e3, total_it
 
 
+def bench_frontend(capi, synth, device, steps=20, warmup=3, n_cams=4, n_patches=1000):
+    """BASELINE.json configs[2]: 4-cam 640x480 pyramids, FAST-10 + 1k PatchFinder searches per frame per camera.
+    One handle (= one CUDA stream) per camera; host buffers in, host results out (H2D/D2H inside the timing)."""
+    import time as _t
+    rng = np.random.default_rng(0)
+    cams, frames, reqs = [], [], []
+    for c in range(n_cams):
+        f = capi.FeHandle(640, 480, device=device, max_corners_per_level=16384)
+        a = synth.make_frame(seed=100 + c)
+        b = synth.make_frame(seed=100 + c, shift=(3.0, -2.0))
+        lva = f.make_keyframe(0, a)                         # source keyframe (map)
+        cor = lva[0]["corners"]
+        cor = cor[(cor[:, 0] > 16) & (cor[:, 0] < 624) & (cor[:, 1] > 16) & (cor[:, 1] < 464)]
+        cor = cor[rng.choice(len(cor), n_patches, replace=len(cor) < n_patches)]
+        rq = np.zeros(n_patches, capi.PATCH_REQ_DTYPE)
+        rq["src_kf"] = 0; rq["src_level"] = 0; rq["src_cx"] = cor[:, 0]; rq["src_cy"] = cor[:, 1]
+        rq["warp_inv"] = np.array([1.0, 0.02, -0.02, 1.0]); rq["search_level"] = 0
+        rq["pred_x"] = cor[:, 0] - 3 + rng.integers(-2, 3, n_patches); rq["pred_y"] = cor[:, 1] + 2 + rng.integers(-2, 3, n_patches)
+        rq["range"] = 10; rq["subpix_its"] = 8
+        cams.append(f); frames.append(b); reqs.append(rq)
+    t_kf = t_ps = 0.0
+    dev_kf = dev_ps = 0.0
+    found = 0
+    for s in range(warmup + steps):
+        for c in range(n_cams):
+            t0 = _t.perf_counter()
+            cams[c].make_keyframe(1, frames[c])
+            t1 = _t.perf_counter()
+            res = cams[c].search_patches(1, reqs[c])
+            t2 = _t.perf_counter()
+            if s >= warmup:
+                t_kf += t1 - t0; t_ps += t2 - t1
+                tm = cams[c].timing()
+                dev_ps += tm["ms_search"]
+                found += int(res["found"].sum())
+        if s >= warmup:
+            pass
+    n_frames = steps * n_cams
+    tm = cams[0].timing()
+    return {"workload": "cfg3: %d-cam 640x480, 4-level pyramid + FAST-10 + %d PatchFinder searches (8 sub-pixel its) per frame" % (n_cams, n_patches),
+            "camera_frames_per_sec_e2e": n_frames / (t_kf + t_ps), "keyframe_ms_e2e": 1e3 * t_kf / n_frames,
+            "patches_per_sec_e2e": n_frames * n_patches / t_ps, "patches_per_sec_device": n_frames * n_patches / (dev_ps * 1e-3),
+            "patch_search_ms_device": dev_ps / n_frames, "found_fraction": found / (n_frames * n_patches),
+            "pyramid_ms_device": tm["ms_pyramid"], "fast_ms_device": tm["ms_fast"],
+            "algorithmic_bytes_per_camera_frame": 307200 + 100800 + 100800, "patch_bytes_each": 800}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -112,6 +159,7 @@ def main():
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frontend", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +301,9 @@ def main():
 
     if rank != 0:
         return 0
+    frontend = None
+    if world == 1 and not args.no_frontend:
+        frontend = bench_frontend(capi, synth, local_rank)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         val, ms, n_it = cpu_reference_run(prob, 2, 0, 3)
@@ -267,7 +318,7 @@ def main():
                        "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "roofline": roofline, "cpu_baseline": cpu, "wall_s": wall,
+            "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "wall_s": wall,
             "lm": {"iterations_per_step": iters / args.steps, "trials_last_step": st.total_trials}}
     print(json.dumps(line))
     if dist is not None:
