@@ -1,0 +1,58 @@
+// BundleAdjusterCuda.h — drop-in for BundleAdjusterMulti (include/mcptam/BundleAdjusterMulti.h:62-113):
+// subclasses the BundleAdjusterBase call surface (include/mcptam/BundleAdjusterBase.h:110-128) and marshals the
+// map exactly like src/BundleAdjusterMulti.cc:55-337, but the ChainBundle it drives runs on the B200.
+#pragma once
+
+#include <set>
+#include <utility>
+#include <vector>
+
+#include "ChainBundle.h"
+#include "shim/MapTypes.h"
+
+namespace mcp_host {
+
+class BundleAdjusterBase {       // the members MapMaker relies on (include/mcptam/BundleAdjusterBase.h)
+ public:
+  virtual ~BundleAdjusterBase() {}
+  void RequestAbort() { mbBundleAbortRequested = true; }
+  bool Running() const { return mbBundleRunning; }
+  bool ConvergedFull() const { return mbBundleConverged_Full; }
+  bool ConvergedRecent() const { return mbBundleConverged_Recent; }
+  void UseTukey(bool b) { mbUseTukey = b; }
+  void UseTwoStep(bool b) { mbUseTwoStep = b; }
+  void UseRobust(bool b) { mbUseRobust = b; }
+  double GetSigmaSquared() const { return mdSigmaSquared; }
+  double GetMeanChiSquared() const { return mdMeanChiSquared; }
+  double GetMaxCov() const { return mdMaxCov; }
+  int TotalIterations() const { return mnTotalIterations; }
+  static int snMinMapPoints;       // src/BundleAdjusterBase.cc:49
+  virtual int BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::set<MultiKeyFrame*> spFixedSet, std::set<MapPoint*> spMapPoints,
+                           std::vector<std::pair<KeyFrame*, MapPoint*> >& vOutliers, bool bRecent) = 0;
+
+ protected:
+  bool mbBundleRunning = false, mbBundleRunningIsRecent = false, mbBundleConverged_Full = false, mbBundleConverged_Recent = false;
+  bool mbBundleAbortRequested = false, mbUseTukey = true, mbUseTwoStep = true, mbUseRobust = true, mbApplyUpdates = true, mbVerbose = false;
+  double mdSigmaSquared = 0, mdMeanChiSquared = 0, mdMaxCov = 0;
+  int mnTotalIterations = 0;
+};
+
+class BundleAdjusterCuda : public BundleAdjusterBase {
+ public:
+  explicit BundleAdjusterCuda(TaylorCameraMap& cameras) : mmCameraModels(cameras) {}
+  int BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::set<MultiKeyFrame*> spFixedSet, std::set<MapPoint*> spMapPoints,
+                   std::vector<std::pair<KeyFrame*, MapPoint*> >& vOutliers, bool bRecent) override;
+  double LastGpuMs() const { return mdGpuMs; }
+
+ protected:
+  int AdjustAndUpdate(ChainBundle& multiBundle, std::set<MultiKeyFrame*> spAdjustSet, std::set<MapPoint*> spMapPoints, int nIterations = -1);
+  TaylorCameraMap& mmCameraModels;
+  std::map<MapPoint*, int> mmPoint_BundleID;
+  std::map<int, MapPoint*> mmBundleID_Point;
+  std::map<MultiKeyFrame*, int> mmBase_BundleID;
+  std::map<int, MultiKeyFrame*> mmBundleID_Base;
+  std::map<std::string, int> mmCamName_BundleID;
+  double mdGpuMs = 0;
+};
+
+}  // namespace mcp_host

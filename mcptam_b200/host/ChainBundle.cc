@@ -1,0 +1,132 @@
+#include "ChainBundle.h"
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+
+namespace mcp_host {
+
+int ChainBundle::snMaxIterations = 100;
+int ChainBundle::snMaxTrialsAfterFailure = 100;
+double ChainBundle::sdUpdatePercentConvergenceLimit = 1e-10;
+double ChainBundle::sdUpdateRMSConvergenceLimit = 1e-10;
+double ChainBundle::sdMinMEstimatorSigma = 0.5;
+
+// one cached device handle per host thread (the MapMaker thread): buffers survive across BundleAdjust calls
+static thread_local McpBa* tl_pooled = nullptr;
+
+ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey, bool bVerbose)
+    : mmCameraModels(cams), mbUseRobust(bUseRobust), mbUseTukey(bUseTukey), mbVerbose(bVerbose)
+{
+  mvIdKind.push_back(-1); mvIdIndex.push_back(-1);     // id 0 unused
+}
+ChainBundle::~ChainBundle()
+{
+  if (mpHandle) {
+    if (!tl_pooled) tl_pooled = mpHandle; else mcp_ba_destroy(mpHandle);
+  }
+}
+
+int ChainBundle::AddPose(SE3 pose, bool bFixed)
+{
+  double rt[12];
+  pose.pack(rt);
+  mvPoseRt.insert(mvPoseRt.end(), rt, rt + 12);
+  mvPoseFixed.push_back(bFixed ? 1 : 0);
+  mvIdKind.push_back(0); mvIdIndex.push_back((int)mvPoseFixed.size() - 1);
+  return mnCurrId++;
+}
+int ChainBundle::AddPoint(Vector<3> p, std::vector<int> vCams, bool bFixed)
+{
+  if (vCams.empty() || vCams.size() > 2) throw std::invalid_argument("ChainBundle::AddPoint: chains of 1 or 2 poses are supported");
+  for (int k = 0; k < 3; k++) mvPtXyz.push_back(p[k]);
+  for (int k = 0; k < 2; k++) mvPtChain.push_back(k < (int)vCams.size() ? mvIdIndex.at(vCams[k]) : -1);
+  mvPtFixed.push_back(bFixed ? 1 : 0);
+  mvIdKind.push_back(1); mvIdIndex.push_back((int)mvPtFixed.size() - 1);
+  return mnCurrId++;
+}
+void ChainBundle::AddMeas(std::vector<int> vCams, int nPointIdx, Vector<2> v2Pos, double dNoiseSigmaSquared, std::string cameraName)
+{
+  if (vCams.empty() || vCams.size() > 2) throw std::invalid_argument("ChainBundle::AddMeas: chains of 1 or 2 poses are supported");
+  mvMeasXy.push_back(v2Pos[0]); mvMeasXy.push_back(v2Pos[1]);
+  for (int k = 0; k < 2; k++) mvMeasChain.push_back(k < (int)vCams.size() ? mvIdIndex.at(vCams[k]) : -1);
+  mvMeasPt.push_back(mvIdIndex.at(nPointIdx));
+  mvMeasNoise.push_back(dNoiseSigmaSquared);
+  mvMeasFirstId.push_back(vCams[0]);
+  int ci = -1;
+  for (size_t i = 0; i < mvCamNames.size(); i++) if (mvCamNames[i] == cameraName) ci = (int)i;
+  if (ci < 0) { if (!mmCameraModels.count(cameraName)) throw std::invalid_argument("ChainBundle::AddMeas: unknown camera " + cameraName); mvCamNames.push_back(cameraName); ci = (int)mvCamNames.size() - 1; }
+  mvMeasCam.push_back(ci);
+}
+
+int ChainBundle::Upload()
+{
+  if (!mpHandle) {
+    if (tl_pooled) { mpHandle = tl_pooled; tl_pooled = nullptr; mcp_ba_destroy(mpHandle); mpHandle = nullptr; }   // config may differ: recreate
+    McpBaConfig cfg;
+    mcp_ba_default_config(&cfg);
+    cfg.use_robust = mbUseRobust; cfg.use_tukey = mbUseTukey; cfg.verbose = mbVerbose;
+    cfg.max_trials_after_failure = snMaxTrialsAfterFailure;
+    cfg.update_pct_limit = sdUpdatePercentConvergenceLimit; cfg.update_rms_limit = sdUpdateRMSConvergenceLimit;
+    cfg.min_sigma = sdMinMEstimatorSigma;
+    int rc = mcp_ba_create(&cfg, &mpHandle);
+    if (rc) return rc;
+  }
+  std::vector<McpTaylorCam> cams;
+  for (auto& n : mvCamNames) cams.push_back(mmCameraModels[n].ToAbi());
+  if (cams.empty()) return MCP_ERR_STATE;
+  int rc = mcp_ba_set_cameras(mpHandle, (int)cams.size(), cams.data());
+  if (rc) return rc;
+  rc = mcp_ba_load(mpHandle, (int)mvPoseFixed.size(), mvPoseRt.data(), mvPoseFixed.data(), (int)mvPtFixed.size(), mvPtXyz.data(),
+                   mvPtChain.data(), mvPtFixed.data(), (int)mvMeasPt.size(), mvMeasXy.data(), mvMeasChain.data(), mvMeasPt.data(),
+                   mvMeasNoise.data(), mvMeasCam.data());
+  if (rc) return rc;
+  mbUploaded = true;
+  return MCP_OK;
+}
+
+void ChainBundle::Fetch()
+{
+  mcp_ba_get_poses(mpHandle, mvPoseRt.data());
+  mcp_ba_get_points(mpHandle, mvPtXyz.data());
+}
+
+int ChainBundle::Compute(bool* pAbortSignal, int nNumIter, double dUserLambda)
+{
+  mvOutlierMeasurementIdx.clear();
+  if (!mbUploaded) {
+    const int rc = Upload();
+    if (rc) { std::fprintf(stderr, "ChainBundle: %s\n", mcp_last_error()); return -1; }
+  }
+  McpBaStats st;
+  static_assert(sizeof(bool) == 1, "abort flag is polled as a byte");
+  const int n = mcp_ba_compute(mpHandle, reinterpret_cast<volatile const uint8_t*>(pAbortSignal), nNumIter, dUserLambda, &st);
+  if (n < -1) { std::fprintf(stderr, "ChainBundle: %s\n", mcp_last_error()); return -1; }
+  mbConverged = st.converged != 0;
+  // the reference's convergence actions raise the shared abort flag (src/ChainBundle.cc:1028,1106)
+  if (mbConverged && pAbortSignal) *pAbortSignal = true;
+  mnTotalIterations = st.total_trials;
+  mdSigmaSquared = st.sigma_sq; mdMeanChiSquared = st.mean_chi2; mdLambda = st.lambda; mdLastMaxCov = st.max_cov; mdGpuMs = st.gpu_ms;
+  Fetch();
+  if (n > 0 && mbUseTukey) {
+    std::vector<int32_t> idx(st.n_outliers > 0 ? st.n_outliers : 1);
+    const int no = mcp_ba_get_outliers(mpHandle, idx.data(), (int)idx.size());
+    for (int i = 0; i < no && i < (int)idx.size(); i++) {
+      const int m = idx[i];
+      int pid = -1;                                           // bundle id of the point
+      for (size_t id = 1; id < mvIdKind.size(); id++) if (mvIdKind[id] == 1 && mvIdIndex[id] == mvMeasPt[m]) { pid = (int)id; break; }
+      mvOutlierMeasurementIdx.push_back(std::make_tuple(pid, mvMeasFirstId[m], mvCamNames[mvMeasCam[m]]));
+    }
+  }
+  return n;
+}
+
+Vector<3> ChainBundle::GetPoint(int n)
+{
+  const int i = mvIdIndex.at(n);
+  return makeVector(mvPtXyz[3 * i], mvPtXyz[3 * i + 1], mvPtXyz[3 * i + 2]);
+}
+SE3 ChainBundle::GetPose(int n) { return SE3::unpack(&mvPoseRt[12 * (size_t)mvIdIndex.at(n)]); }
+std::vector<std::tuple<int, int, std::string> > ChainBundle::GetOutlierMeasurements() { return mvOutlierMeasurementIdx; }
+
+}  // namespace mcp_host
