@@ -299,6 +299,12 @@ def main():
                 "per_kernel_ms_per_step": {k: v for k, v in tm.items() if k.startswith("ms_")},
                 "per_kernel_launches_per_step": {k: v for k, v in tm.items() if k.startswith("n_")}}
 
+    if world > 1:
+        h.close(); h2.close()
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        dist = None
     if rank != 0:
         return 0
     frontend = None
@@ -321,8 +327,6 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "wall_s": wall,
             "lm": {"iterations_per_step": iters / args.steps, "trials_last_step": st.total_trials}}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
     return 0
 
 

@@ -8,6 +8,8 @@
 //   k_schur_pairs  one warp per block-pair chunk: lanes stride the incidence list, each lane accumulates a
 //                  private 6x6 block  Y_A W_B^T  in registers, one warp reduction, 36 adds per chunk.
 // Reads are 144-byte contiguous records served from L2; there is no per-incidence atomic.
+#include <cstdlib>
+
 #include "ba_types.cuh"
 
 namespace mcp {
@@ -141,6 +143,123 @@ __global__ void __launch_bounds__(128) k_schur_pairs(BaDev d)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_schur_pairs_tma: same work items, B200-native data path.
+//   * every lane issues two cp.async.bulk (TMA 1-D bulk) copies for "its" incidence of the group — the 192-byte
+//     Y record and the 144-byte W record — straight from L2 into the warp's staging buffer; completion is counted
+//     in bytes on an mbarrier (no per-piece address arithmetic, no register staging), double buffered;
+//   * the 6x6 block  sum_q Y_q W_q^T  is a true contraction over k = (incidence, 3):  D(8x8) += A(8x4) B(4x8) with
+//     fp64 tensor cores (mma.sync m8n8k4, rows/cols 6,7 are zero padding), 24 DMMAs per 32 incidences.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int TG = 32;                       // incidences per group (K = 96)
+constexpr int TW = 4;                        // warps per block
+__global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* stage = reinterpret_cast<double*>(smem_raw) + (size_t)wid * 2 * TG * SREC;          // [2][TG][SREC]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)TW * 2 * TG * SREC * sizeof(double)) + wid * 2;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  const int g = lane >> 2, kk = lane & 3;              // fragment coordinates
+  // per-phase offsets inside a 4-incidence (12 k) block: k = 4p + kk -> (incidence, component)
+  int offA[3], offB[3];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int k = 4 * p + kk, q = k / 3, t = k - 3 * q;
+    offA[p] = q * SREC + g * 3 + t;                    // Y_q[g][t]
+    offB[p] = q * SREC + 24 + g * 3 + t;               // W_q[g][t]
+  }
+  const bool gvalid = g < 6;
+  unsigned phase[2] = { 0u, 0u };
+  for (int it = gw; it < d.n_items; it += nw) {
+    const int4 item = d.items[it];
+    const bool diag = item.x == item.y;
+    const int n_groups = (item.w - item.z + TG - 1) / TG;
+    double c0 = 0.0, c1 = 0.0, accz = 0.0;
+    // prologue: issue group 0 into buffer 0
+    auto issue = [&](int grp, int buf) {
+      const int g0 = item.z + grp * TG, ng = min(TG, item.w - g0);
+      double* st = stage + (size_t)buf * TG * SREC;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&bars[buf], (unsigned)ng * (192u + 144u));
+      __syncwarp();
+      if (lane < ng) {
+        const int2 ab = d.inc[g0 + lane];
+        bulk_g2s(st + lane * SREC, d.Y + 24 * (size_t)ab.x, 192u, &bars[buf]);
+        bulk_g2s(st + lane * SREC + 24, d.W + 18 * (size_t)ab.y, 144u, &bars[buf]);
+      } else {
+        for (int i = 0; i < SREC; i++) st[lane * SREC + i] = 0.0;          // zero padding of a partial group
+      }
+    };
+    issue(0, 0);
+    for (int grp = 0; grp < n_groups; grp++) {
+      const int buf = grp & 1;
+      if (grp + 1 < n_groups) issue(grp + 1, buf ^ 1);
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      __syncwarp();
+      const double* st = stage + (size_t)buf * TG * SREC;
+#pragma unroll
+      for (int m = 0; m < TG / 4; m++) {
+        const double* blk = st + m * 4 * SREC;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          const double a = gvalid ? blk[offA[p]] : 0.0;
+          const double b = gvalid ? blk[offB[p]] : 0.0;
+          dmma_m8n8k4(c0, c1, a, b);
+        }
+      }
+      if (diag && lane < 6) {
+#pragma unroll 8
+        for (int q = 0; q < TG; q++) accz += st[q * SREC + 18 + lane];
+      }
+      __syncwarp();
+    }
+    // D fragment: row g, cols 2*kk, 2*kk+1
+    if (g < 6) {
+      double* base = d.Sm + (size_t)(6 * item.x + g) * nc + 6 * item.y;
+      if (2 * kk < 6) atomicAdd(base + 2 * kk, c0);
+      if (2 * kk + 1 < 6) atomicAdd(base + 2 * kk + 1, c1);
+    }
+    if (diag && lane < 6) atomicAdd(d.rm + 6 * item.x + lane, accz);
+  }
+}
+
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148, 128, 0, s>>>(d, cnt); }
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148, 128, 0, s>>>(d, cursor, inc); }
 void launch_schur_gather(const BaDev& d, cudaStream_t s)
@@ -150,10 +269,20 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s)
   if (g1 < 1) g1 = 1;
   if (g1 > 148 * 8) g1 = 148 * 8;
   k_schur_y<<<g1, 256, 0, s>>>(d);
+  static int use_v1 = -1;
+  if (use_v1 < 0) { const char* e = getenv("MCP_BA_SCHUR_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
   int g2 = (d.n_items + 3) / 4;
   if (g2 < 1) g2 = 1;
-  if (g2 > 148 * 5) g2 = 148 * 5;
-  k_schur_pairs<<<g2, 128, 0, s>>>(d);
+  if (use_v1) {
+    if (g2 > 148 * 5) g2 = 148 * 5;
+    k_schur_pairs<<<g2, 128, 0, s>>>(d);
+  } else {
+    const size_t smem = (size_t)TW * 2 * TG * SREC * sizeof(double) + TW * 2 * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_schur_pairs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (g2 > 148 * 2) g2 = 148 * 2;
+    k_schur_pairs_tma<<<g2, TW * 32, smem, s>>>(d);
+  }
 }
 
 }  // namespace mcp

@@ -80,6 +80,99 @@ __device__ __noinline__ bool potrf32_warp(double* S, double* rinv, int lane)
   return bad;
 }
 
+
+// Blocked Cholesky of the 32x32 tile in shared memory S (stride TLD) by the whole CTA (256 threads):
+// four 8-column panels; the 8x8 diagonal block is factored (and inverted) in registers by 8 lanes of warp 0,
+// the panel below and the trailing update are small matrix products spread over all threads.  The dependent
+// chain is 32 pivots (rsqrt) long instead of 32 pivots + 496 serial rank-1 column updates in one warp.
+// rinv[32]: reciprocal diagonal; linv8: 64 doubles scratch; tmp: >= 256 doubles scratch.  Returns via *bad.
+__device__ __forceinline__ void potrf32_blocked(double* S, double* rinv, double* linv8, double* tmp, int tid, int* bad)
+{
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int b = 0; b < 4; b++) {
+    const int o = 8 * b;
+    if (wid == 0) {
+      const int r = lane & 7;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] = (c <= r) ? S[(o + r) * TLD + o + c] : 0.0;
+      bool isbad = false;
+      double dj = __shfl_sync(0xffffffffu, a[0], 0);
+      if (!(dj > 0.0) || !(dj < 1.0e300)) { isbad = true; dj = 1.0; }
+      double ri = rsqrt(dj);
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+        if (r == jj) { a[jj] = dj * ri; if (lane < 8) rinv[o + jj] = ri; }
+        else if (r > jj) a[jj] *= ri;
+        double dn = 1.0, rn = 1.0;
+        if (jj + 1 < 8) {
+          const double v1 = __shfl_sync(0xffffffffu, a[jj], jj + 1);
+          if (r >= jj + 1) a[jj + 1] -= a[jj] * v1;
+          dn = __shfl_sync(0xffffffffu, a[jj + 1], jj + 1);
+          if (!(dn > 0.0) || !(dn < 1.0e300)) { isbad = true; dn = 1.0; }
+          rn = rsqrt(dn);
+        }
+#pragma unroll
+        for (int c = jj + 2; c < 8; c++) {
+          const double v = __shfl_sync(0xffffffffu, a[jj], c);
+          if (r >= c) a[c] -= a[jj] * v;
+        }
+        dj = dn; ri = rn;
+      }
+      if (isbad && lane == 0) *bad = 1;
+      if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) S[(o + r) * TLD + o + c] = a[c];
+      }
+      __syncwarp();
+      if (lane < 8) {            // inverse of the 8x8 factor: lane = column
+        const int c = lane;
+        double x[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+          double sacc = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < rr; k++) sacc -= S[(o + rr) * TLD + o + k] * ((k >= c) ? x[k] : 0.0);
+          x[rr] = (rr >= c) ? sacc * rinv[o + rr] : 0.0;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) linv8[rr * 8 + c] = x[rr];
+      }
+    }
+    __syncthreads();
+    const int nrow = 24 - o;                       // rows below the diagonal block
+    if (nrow > 0) {
+      // panel: X[i][c] = sum_{k<=c} A[i][o+k] * Linv[c][k]
+      double xv = 0.0;
+      const int pi = tid >> 3, pc = tid & 7;
+      if (pi < nrow) {
+        const double* arow = S + (o + 8 + pi) * TLD + o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) xv += arow[k] * linv8[pc * 8 + k];
+      }
+      __syncthreads();
+      if (pi < nrow) S[(o + 8 + pi) * TLD + o + pc] = xv;
+      __syncthreads();
+      // trailing update of the lower triangle: A[i][j] -= sum_k X[i][k] X[j][k]
+      for (int e = tid; e < nrow * nrow; e += 256) {
+        const int i = e / nrow, j = e - i * nrow;
+        if (j > i) continue;
+        const double* xi = S + (o + 8 + i) * TLD + o;
+        const double* xj = S + (o + 8 + j) * TLD + o;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += xi[k] * xj[k];
+        S[(o + 8 + i) * TLD + o + 8 + j] -= acc;
+      }
+      __syncthreads();
+    }
+  }
+  // zero the strict upper triangle (the tile is consumed as a full 32x32 lower-triangular factor)
+  for (int e = tid; e < TB * TB; e += 256) { const int r = e >> 5, c = e & 31; if (c > r) S[r * TLD + c] = 0.0; }
+  (void)tmp;
+  __syncthreads();
+}
+
 // Inverse of the lower-triangular 32x32 factor L (shared, stride TLD) into X (shared, stride TLD), by
 // recursive 2x2 blocking: [A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1] with 8x8 leaves.  256 threads.
 // rinv: reciprocals of the diagonal of L; tmp: >= 256 doubles of scratch.
@@ -220,10 +313,13 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
 #pragma unroll
         for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = acc[a][b];
       __syncthreads();
-      if (wid == 0) {
-        if (potrf32_warp(As, xs + 32 * TB, lane) && lane == 0) atomicExch(&ctr[2], epoch);
+      {
+        __shared__ int s_bad;
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        potrf32_blocked(As, xs + 32 * TB, xs + 32 * TB - 64, xs, tid, &s_bad);
+        if (tid == 0 && s_bad) atomicExch(&ctr[2], epoch);
       }
-      __syncthreads();
       if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3p));
       inverse32_block(As, Bs, xs + 32 * TB, xs, tid);
       if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t4p));

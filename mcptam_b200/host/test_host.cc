@@ -1,6 +1,7 @@
 // test_host.cc — exercises the C++ host mirror end to end on a small synthetic map (needs a GPU):
 //   TaylorCamera fit, BundleAdjusterCuda::BundleAdjust over MultiKeyFrame/KeyFrame/MapPoint shim types,
 //   MakeKeyFrame_Lite + SearchForPoints over the front-end device.  Prints "HOST_TEST OK" on success.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,10 +54,10 @@ int main()
   std::vector<SE3> truth;
   for (int m = 0; m < M; m++) {
     mkfs.emplace_back(new MultiKeyFrame);
-    SE3 worldFromBase = RotZ(0.05 * m, makeVector(0.4 * m, 0.1 * m, 0.02 * m));
+    SE3 worldFromBase = RotZ(0.05 * m, makeVector(0.1 * m, 0.5 * m, 0.05 * m));   // sideways motion: parallax for both cameras
     truth.push_back(worldFromBase.inverse());
     mkfs[m]->mse3BaseFromWorld = truth[m];
-    mkfs[m]->mbFixed = (m == 0);
+    mkfs[m]->mbFixed = (m == 0 || m == M - 1);      // two fixed MKFs pin the scale gauge (0.2 m rig baseline alone is weak)
     for (int c = 0; c < 2; c++) {
       kfs.emplace_back(new KeyFrame);
       KeyFrame* kf = kfs.back().get();
@@ -92,7 +93,7 @@ int main()
     pts.push_back(std::move(mp));
   }
   // perturb the estimate
-  for (int m = 1; m < M; m++) {
+  for (int m = 1; m < M - 1; m++) {
     Vector<6> d;
     for (int k = 0; k < 3; k++) { d[k] = 0.02 * N(rng); d[3 + k] = 0.008 * N(rng); }
     mkfs[m]->mse3BaseFromWorld = SE3::exp(d) * mkfs[m]->mse3BaseFromWorld;
@@ -109,10 +110,13 @@ int main()
   const int n = ba.BundleAdjust(adj, fixed, sp, outliers, false);
   double pose_err = 0, pt_err = 0;
   for (int m = 0; m < M; m++) for (int k = 0; k < 3; k++) pose_err = std::max(pose_err, std::fabs(mkfs[m]->mse3BaseFromWorld.trans[k] - truth[m].trans[k]));
-  for (size_t i = 0; i < pts.size(); i++) { Vector<3> d = pts[i]->mv3WorldPos - ptTruth[i]; pt_err = std::max(pt_err, std::sqrt(d * d)); }
-  std::printf("BundleAdjusterCuda: %zu points, %zu meas, accepted %d, total trials %d, converged %d, sigma^2 %.3f, outliers %zu, pose err %.4f m, point err %.3f m, gpu %.2f ms\n",
+  std::vector<double> errs;
+  for (size_t i = 0; i < pts.size(); i++) { Vector<3> d = pts[i]->mv3WorldPos - ptTruth[i]; errs.push_back(std::sqrt(d * d)); }
+  std::sort(errs.begin(), errs.end());
+  pt_err = errs[errs.size() / 2];                      // median: single low-parallax points may legitimately drift
+  std::printf("BundleAdjusterCuda: %zu points, %zu meas, accepted %d, total trials %d, converged %d, sigma^2 %.3f, outliers %zu, pose err %.4f m, median point err %.3f m, gpu %.2f ms\n",
               pts.size(), meas.size(), n, ba.TotalIterations(), (int)ba.ConvergedFull(), ba.GetSigmaSquared(), outliers.size(), pose_err, pt_err, ba.LastGpuMs());
-  if (n <= 0 || pose_err > 0.02 || pt_err > 0.5) return 1;
+  if (n <= 0 || pose_err > 0.02 || pt_err > 0.05) return 1;
 
   // ---- front end --------------------------------------------------------------------------------------
   FrontEndDevice dev(640, 480);
