@@ -141,7 +141,22 @@ def bench_frontend(capi, synth, device, steps=20, warmup=3, n_cams=4, n_patches=
             pass
     n_frames = steps * n_cams
     tm = cams[0].timing()
-    return {"workload": "cfg3: %d-cam 640x480, 4-level pyramid + FAST-10 + %d PatchFinder searches (8 sub-pixel its) per frame" % (n_cams, n_patches),
+    # CPU restatement of the same per-frame work on one host core (the reference tracker is single threaded)
+    from oracle import oracle as ora
+    t0 = _t.perf_counter()
+    pyr_b = ora.pyramid(frames[0])
+    lv_b = [ora.level_corners(im) for im in pyr_b]
+    t1 = _t.perf_counter()
+    pyr_a = ora.pyramid(synth.make_frame(seed=100))
+    n_cpu = len(reqs[0])
+    ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0][:8])      # warm the marshalling path
+    t1b = _t.perf_counter()
+    flags_cpu, _ = ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0])
+    t2 = _t.perf_counter()
+    t1 = t1 + 0.0; t2 = t1 + (t2 - t1b)
+    cpu = {"keyframe_ms": 1e3 * (t1 - t0), "patches_per_sec": n_cpu / (t2 - t1), "cores": 1, "kind": "port",
+           "sample": "1 camera frame (pyramid + FAST-10 + threshold + LUT) and %d patch searches in one C call, oracle/fe_oracle.c" % n_cpu}
+    return {"cpu_baseline": cpu,"workload": "cfg3: %d-cam 640x480, 4-level pyramid + FAST-10 + %d PatchFinder searches (8 sub-pixel its) per frame" % (n_cams, n_patches),
             "camera_frames_per_sec_e2e": n_frames / (t_kf + t_ps), "keyframe_ms_e2e": 1e3 * t_kf / n_frames,
             "patches_per_sec_e2e": n_frames * n_patches / t_ps, "patches_per_sec_device": n_frames * n_patches / (dev_ps * 1e-3),
             "patch_search_ms_device": dev_ps / n_frames, "found_fraction": found / (n_frames * n_patches),
@@ -160,6 +175,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frontend", action="store_true")
+    ap.add_argument("--scale-config", default="cfg4", help="map used for the extra multi-GPU strong-scaling section (none to skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -309,6 +325,52 @@ def main():
                 "per_kernel_ms_per_step": {k: v for k, v in tm.items() if k.startswith("ms_")},
                 "per_kernel_launches_per_step": {k: v for k, v in tm.items() if k.startswith("n_")}}
 
+    scale = None
+    if world > 1 and args.scale_config != "none":
+        # BASELINE.json configs[3]: the 1000 KF / 100k-point map, points sharded over the ranks, next to the same map
+        # on one GPU (rank 0 alone) measured in the same run
+        big = synth.make_ba_config(args.scale_config, seed=args.seed)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        hb = capi.BaHandle(device=local_rank)
+        hb.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        hb.load(big)
+        sb = torch.cuda.ExternalStream(hb.stream(), device=torch.device("cuda", local_rank))
+        tms, its = [], 0
+        for s in range(2 + 3):
+            barrier()
+            hb.reset_state()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(sb)
+            rc, stb = hb.compute(args.lm_iters)
+            e1.record(sb)
+            e1.synchronize()
+            if s >= 2:
+                tms.append(e0.elapsed_time(e1)); its += rc
+        tot = torch.tensor([float(np.sum(tms))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        hb.close()
+        val1 = None
+        if rank == 0:
+            h1 = capi.BaHandle(device=local_rank)
+            h1.load(big)
+            s1 = torch.cuda.ExternalStream(h1.stream(), device=torch.device("cuda", local_rank))
+            t1, i1 = [], 0
+            for s in range(2 + 3):
+                h1.reset_state()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s1)
+                rc, st1 = h1.compute(args.lm_iters)
+                e1.record(s1)
+                e1.synchronize()
+                if s >= 2:
+                    t1.append(e0.elapsed_time(e1)); i1 += rc
+            val1 = i1 / (float(np.sum(t1)) * 1e-3)
+            h1.close()
+        scale = {"workload": "%s: %d poses / %d points / %d measurements, points sharded x%d" % (args.scale_config, big.n_pose, big.n_pt, big.n_meas, world),
+                 "value_n_gpus": its / (float(tot.item()) * 1e-3), "value_1_gpu_same_run": val1, "unit": UNIT, "n_gpus": world}
     if world > 1:
         h.close(); h2.close()
         dist.barrier()
@@ -334,7 +396,7 @@ def main():
                        "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "wall_s": wall,
+            "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "scale_big_map": scale, "wall_s": wall,
             "lm": {"iterations_per_step": iters / args.steps, "trials_last_step": st.total_trials}}
     print(json.dumps(line))
     return 0

@@ -233,6 +233,20 @@ int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t leve
                           int32_t* found);
 /* Debug: FAST score map of one level (0 = no corner at b=5, else fast_corner_score_10). */
 int mcp_fe_debug_scores(McpFe* h, int32_t slot, int32_t level, uint8_t* out);
+/* FindPVS building block: TrackerData::Project + GetDerivsUnsafe (include/mcptam/TrackerData.h:102-129) and
+ * PatchFinder::CalcSearchLevelAndWarpMatrix (src/PatchFinder.cc:69-122) for n map points against one camera pose. */
+typedef struct McpProjRes {
+  double px[2];          /* td.mv2Image */
+  double cam_derivs[4];  /* td.mm2CamDerivs, row-major */
+  double warp_inv[4];    /* PatchFinder::mm2WarpInverse, row-major */
+  double v3cam[3];       /* td.mv3Cam */
+  int32_t in_image;      /* td.mbInImage (camera valid and inside the image, '>' size as in the reference) */
+  int32_t search_level;  /* GetLevel(), -1 = template bad */
+} McpProjRes;
+int mcp_fe_set_camera(McpFe* h, const McpTaylorCam* cam);
+/* cam_from_world: 12 doubles (row-major R, t); world_xyz / pixel_right_w / pixel_down_w: n x 3 doubles (host) */
+int mcp_fe_project_points(McpFe* h, const double* cam_from_world, int32_t n, const double* world_xyz,
+                          const double* pixel_right_w, const double* pixel_down_w, McpProjRes* out);
 typedef struct McpFeTiming { double ms_pyramid, ms_fast, ms_compact, ms_search, ms_other; int32_t n_launches, pad_; } McpFeTiming;
 int mcp_fe_get_timing(McpFe* h, McpFeTiming* out);
 

@@ -274,6 +274,7 @@ class FeTiming(C.Structure):
 PATCH_REQ_DTYPE = np.dtype([("src_kf", "i4"), ("src_level", "i4"), ("src_cx", "i4"), ("src_cy", "i4"), ("warp_inv", "f8", 4),
                             ("search_level", "i4"), ("pred_x", "i4"), ("pred_y", "i4"), ("range", "i4"), ("subpix_its", "i4"),
                             ("exhaustive", "i4")], align=True)
+PROJ_RES_DTYPE = np.dtype([("px", "f8", 2), ("cam_derivs", "f8", 4), ("warp_inv", "f8", 4), ("v3cam", "f8", 3), ("in_image", "i4"), ("search_level", "i4")], align=True)
 PATCH_RES_DTYPE = np.dtype([("template_bad", "i4"), ("found", "i4"), ("did_subpix", "i4"), ("score", "i4"), ("coarse_x", "i4"),
                             ("coarse_y", "i4"), ("found_x", "f8"), ("found_y", "f8"), ("n_candidates", "i4"), ("pad_", "i4")], align=True)
 assert PATCH_REQ_DTYPE.itemsize == C.sizeof(PatchReq) and PATCH_RES_DTYPE.itemsize == C.sizeof(PatchRes)
@@ -296,6 +297,8 @@ def _bind_fe(L):
     L.mcp_fe_minipatch_find.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p, C.c_void_p]
     L.mcp_fe_get_timing.argtypes = [C.c_void_p, C.POINTER(FeTiming)]
+    L.mcp_fe_set_camera.argtypes = [C.c_void_p, C.c_void_p]
+    L.mcp_fe_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcp_fe_debug_scores.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     _fe_bound = True
 
@@ -388,6 +391,17 @@ class FeHandle:
         found = np.zeros(len(src_xy), np.int32)
         check(self.L.mcp_fe_minipatch_find(self.h, kf_src, kf_dst, level, len(src_xy), _p(src_xy), _p(start_xy), rng, _p(pos), _p(found)))
         return pos, found
+
+    def set_camera(self, cam):
+        self._cam = cam
+        check(self.L.mcp_fe_set_camera(self.h, C.byref(cam)))
+
+    def project_points(self, cam_from_world, world_xyz, right_w, down_w):
+        T = np.ascontiguousarray(cam_from_world, np.float64)
+        pw = np.ascontiguousarray(world_xyz, np.float64); rw = np.ascontiguousarray(right_w, np.float64); dw = np.ascontiguousarray(down_w, np.float64)
+        out = np.zeros(len(pw), PROJ_RES_DTYPE)
+        check(self.L.mcp_fe_project_points(self.h, _p(T), len(pw), _p(pw), _p(rw), _p(dw), _p(out)))
+        return out
 
     def debug_scores(self, slot, level):
         w, h = self.cfg.width >> level, self.cfg.height >> level

@@ -96,28 +96,36 @@ __device__ __forceinline__ void potrf32_blocked(double* S, double* rinv, double*
       double a[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) a[c] = (c <= r) ? S[(o + r) * TLD + o + c] : 0.0;
+      // branch-free pivot chain: l_jj = d_j * rsqrt(d_j) is the same multiply as the column scaling, bad pivots are
+      // handled with selects (no divergence / reconvergence inside the dependent chain)
       bool isbad = false;
       double dj = __shfl_sync(0xffffffffu, a[0], 0);
-      if (!(dj > 0.0) || !(dj < 1.0e300)) { isbad = true; dj = 1.0; }
+      {
+        const bool ok = (dj > 0.0) && (dj < 1.0e300);
+        isbad |= !ok;
+        dj = ok ? dj : 1.0;
+      }
       double ri = rsqrt(dj);
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) {
-        if (r == jj) { a[jj] = dj * ri; if (lane < 8) rinv[o + jj] = ri; }
-        else if (r > jj) a[jj] *= ri;
-        double dn = 1.0, rn = 1.0;
+        a[jj] = (r >= jj) ? a[jj] * ri : a[jj];
+        if (lane == jj) rinv[o + jj] = ri;
+        double rn = 1.0;
         if (jj + 1 < 8) {
           const double v1 = __shfl_sync(0xffffffffu, a[jj], jj + 1);
-          if (r >= jj + 1) a[jj + 1] -= a[jj] * v1;
-          dn = __shfl_sync(0xffffffffu, a[jj + 1], jj + 1);
-          if (!(dn > 0.0) || !(dn < 1.0e300)) { isbad = true; dn = 1.0; }
+          a[jj + 1] = (r >= jj + 1) ? a[jj + 1] - a[jj] * v1 : a[jj + 1];
+          double dn = __shfl_sync(0xffffffffu, a[jj + 1], jj + 1);
+          const bool ok = (dn > 0.0) && (dn < 1.0e300);
+          isbad |= !ok;
+          dn = ok ? dn : 1.0;
           rn = rsqrt(dn);
         }
 #pragma unroll
         for (int c = jj + 2; c < 8; c++) {
           const double v = __shfl_sync(0xffffffffu, a[jj], c);
-          if (r >= c) a[c] -= a[jj] * v;
+          a[c] = (r >= c) ? a[c] - a[jj] * v : a[c];
         }
-        dj = dn; ri = rn;
+        ri = rn;
       }
       if (isbad && lane == 0) *bad = 1;
       if (lane < 8) {

@@ -12,6 +12,7 @@ void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s);
 int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s);
 void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s);
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s);
+void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s);
 void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
                          int2* pos, int* found, cudaStream_t s);
 }  // namespace mcp
@@ -42,6 +43,8 @@ struct McpFe {
   int2* xy_dev = nullptr; int2* xy2_dev = nullptr; int2* pos_dev = nullptr; int* found_dev = nullptr; double* sc_dev = nullptr;
   void* aux_host = nullptr;        // pinned scratch for shitomasi / minipatch
   int last_n = 0;
+  DevCam cam; bool has_cam = false;
+  double* proj_in = nullptr; McpProjRes* proj_out = nullptr; size_t proj_cap = 0;
   McpFeTiming timing;
   int lw[MCP_LEVELS], lh[MCP_LEVELS], lp[MCP_LEVELS];
 };
@@ -174,6 +177,8 @@ int mcp_fe_destroy(McpFe* h)
   if (h->req_host) cudaFreeHost(h->req_host);
   if (h->res_host) cudaFreeHost(h->res_host);
   if (h->aux_host) cudaFreeHost(h->aux_host);
+  if (h->proj_in) cudaFree(h->proj_in);
+  if (h->proj_out) cudaFree(h->proj_out);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -342,6 +347,47 @@ int mcp_fe_debug_scores(McpFe* h, int32_t slot, int32_t level, uint8_t* out)
   cudaSetDevice(h->device);
   const FeLevel& L = h->kf_host[slot].lv[level];
   MCP_CUDA_CHECK(cudaMemcpy2D(out, L.w, L.score, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return MCP_OK;
+}
+
+int mcp_fe_set_camera(McpFe* h, const McpTaylorCam* s)
+{
+  if (!h || !s || s->n_inv < 2 || s->n_inv > 32) { set_last_error("mcp_fe_set_camera: bad arguments"); return MCP_ERR_INVALID; }
+  DevCam& c = h->cam;
+  memset(&c, 0, sizeof(c));
+  memcpy(c.poly, s->poly, sizeof(c.poly));
+  c.dmod[0] = -s->poly[0]; c.dmod[1] = s->poly[1]; c.dmod[2] = s->poly[2]; c.dmod[3] = 2 * s->poly[3]; c.dmod[4] = 3 * s->poly[4];
+  memcpy(c.center, s->center, sizeof(c.center)); memcpy(c.affine, s->affine, sizeof(c.affine)); memcpy(c.image_size, s->image_size, sizeof(c.image_size));
+  c.min_theta = s->min_theta; c.theta_mean = s->theta_mean; c.theta_std = s->theta_std; c.n_inv = s->n_inv;
+  memcpy(c.inv, s->inv_poly, sizeof(double) * 32);
+  h->has_cam = true;
+  return MCP_OK;
+}
+
+int mcp_fe_project_points(McpFe* h, const double* cam_from_world, int32_t n, const double* world_xyz, const double* pixel_right_w,
+                          const double* pixel_down_w, McpProjRes* out)
+{
+  if (!h || !cam_from_world || n < 0 || (n && (!world_xyz || !pixel_right_w || !pixel_down_w || !out))) { set_last_error("mcp_fe_project_points: bad arguments"); return MCP_ERR_INVALID; }
+  if (!h->has_cam) { set_last_error("mcp_fe_project_points: call mcp_fe_set_camera first"); return MCP_ERR_STATE; }
+  if (n == 0) return MCP_OK;
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  if ((size_t)n > h->proj_cap) {
+    if (h->proj_in) cudaFree(h->proj_in);
+    if (h->proj_out) cudaFree(h->proj_out);
+    h->proj_cap = (size_t)n + n / 4 + 64;
+    MCP_CUDA_CHECK(cudaMalloc(&h->proj_in, sizeof(double) * 9 * h->proj_cap));
+    MCP_CUDA_CHECK(cudaMalloc(&h->proj_out, sizeof(McpProjRes) * h->proj_cap));
+  }
+  double* pw = h->proj_in; double* rw = pw + 3 * h->proj_cap; double* dw = rw + 3 * h->proj_cap;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(pw, world_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(rw, pixel_right_w, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(dw, pixel_down_w, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  Se3 T;
+  memcpy(T.R, cam_from_world, sizeof(double) * 9); memcpy(T.t, cam_from_world + 9, sizeof(double) * 3);
+  fe_launch_project(h->cam, T, n, pw, rw, dw, h->proj_out, s);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, h->proj_out, sizeof(McpProjRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
   return MCP_OK;
 }
 

@@ -596,6 +596,63 @@ __global__ void __launch_bounds__(128) k_minipatch(FeLevel S, FeLevel T, int n_c
   }
 }
 
+// FindPVS building block (src/Tracker.cc:663-723): TrackerData::Project + GetDerivsUnsafe
+// (include/mcptam/TrackerData.h:102-129) and PatchFinder::CalcSearchLevelAndWarpMatrix (src/PatchFinder.cc:69-122)
+// for every map point against one camera pose.  One thread per point.
+__global__ void k_project_points(DevCam cam, Se3 T, int n, const double* __restrict__ pw, const double* __restrict__ rw,
+                                 const double* __restrict__ dw, McpProjRes* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = { pw[3 * i], pw[3 * i + 1], pw[3 * i + 2] };
+  const double r[3] = { rw[3 * i], rw[3 * i + 1], rw[3 * i + 2] }, dn[3] = { dw[3 * i], dw[3 * i + 1], dw[3 * i + 2] };
+  double vc[3], mr[3], md[3];
+  se3_apply(T, p, vc);
+  m3_vec(T.R, r, mr);
+  m3_vec(T.R, dn, md);
+  // projection, pixel derivatives w.r.t. (theta, phi) and the sphere derivatives, kept separate like the reference
+  const double n2 = vc[0] * vc[0] + vc[1] * vc[1], norm = sqrt(n2);
+  double theta, rho, cphi, sphi;
+  if (norm == 0) { theta = 1.5707963267948966; rho = 0; cphi = 0; sphi = 0; }
+  else {
+    theta = atan(vc[2] / norm);
+    const double xs = (theta - cam.theta_mean) / cam.theta_std;
+    double val = 0;
+    for (int q = cam.n_inv - 1; q > 0; q--) { val += cam.inv[q]; val *= xs; }
+    rho = val + cam.inv[0];
+    cphi = vc[0] / norm; sphi = vc[1] / norm;
+  }
+  bool invalid = theta < cam.min_theta;
+  const double u = cphi * rho, w = sphi * rho;
+  McpProjRes o;
+  o.px[0] = cam.affine[0] * u + cam.affine[1] * w + cam.center[0];
+  o.px[1] = cam.affine[2] * u + cam.affine[3] * w + cam.center[1];
+  if (!(o.px[0] >= 0 && o.px[0] < cam.image_size[0] && o.px[1] >= 0 && o.px[1] < cam.image_size[1])) invalid = true;
+  o.in_image = (!invalid && !(o.px[0] < 0 || o.px[1] < 0 || o.px[0] > cam.image_size[0] || o.px[1] > cam.image_size[1])) ? 1 : 0;
+  const double wv = polyval5(cam.poly, rho);
+  const double drho = (rho * rho + wv * wv) / polyval5(cam.dmod, rho);
+  const double dth0 = cphi * drho, dth1 = sphi * drho, dph0 = -sphi * rho, dph1 = cphi * rho;
+  o.cam_derivs[0] = cam.affine[0] * dth0 + cam.affine[1] * dth1; o.cam_derivs[2] = cam.affine[2] * dth0 + cam.affine[3] * dth1;
+  o.cam_derivs[1] = cam.affine[0] * dph0 + cam.affine[1] * dph1; o.cam_derivs[3] = cam.affine[2] * dph0 + cam.affine[3] * dph1;
+  double dth[3], dph[3];
+  const double x = vc[0], y = vc[1], z = vc[2], z2 = z * z, nn2 = norm * norm, n3 = nn2 * norm;
+  if (norm == 0) { dth[0] = dth[1] = dth[2] = 0; dph[0] = dph[1] = dph[2] = 0; }
+  else {
+    dth[0] = -z * x / (n3 + norm * z2); dth[1] = -z * y / (n3 + norm * z2); dth[2] = norm / (nn2 + z2);
+    dph[0] = -y / (x * x + y * y); dph[1] = x / (x * x + y * y); dph[2] = 0;
+  }
+  const double r0 = dth[0] * mr[0] + dth[1] * mr[1] + dth[2] * mr[2], r1 = dph[0] * mr[0] + dph[1] * mr[1] + dph[2] * mr[2];
+  const double d0 = dth[0] * md[0] + dth[1] * md[1] + dth[2] * md[2], d1 = dph[0] * md[0] + dph[1] * md[1] + dph[2] * md[2];
+  o.warp_inv[0] = o.cam_derivs[0] * r0 + o.cam_derivs[1] * r1; o.warp_inv[2] = o.cam_derivs[2] * r0 + o.cam_derivs[3] * r1;
+  o.warp_inv[1] = o.cam_derivs[0] * d0 + o.cam_derivs[1] * d1; o.warp_inv[3] = o.cam_derivs[2] * d0 + o.cam_derivs[3] * d1;
+  double dDet = o.warp_inv[0] * o.warp_inv[3] - o.warp_inv[1] * o.warp_inv[2];
+  int level = 0;
+  while (dDet > 3 && level < MCP_LEVELS - 1) { level++; dDet *= 0.25; }
+  o.search_level = (dDet > 3 || dDet < 0.5 || !isfinite(dDet)) ? -1 : level;
+  o.v3cam[0] = vc[0]; o.v3cam[1] = vc[1]; o.v3cam[2] = vc[2];
+  out[i] = o;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -626,6 +683,10 @@ void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchRe
 {
   if (n <= 0) return;
   k_patch_search<<<(n + 3) / 4, 128, 0, s>>>(fe, target, n, req, res, templ);
+}
+void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s)
+{
+  if (n > 0) k_project_points<<<(n + 127) / 128, 128, 0, s>>>(cam, T, n, pw, rw, dw, out);
 }
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s)
 {

@@ -255,59 +255,69 @@ def make_ba_problem(n_cam=1, n_mkf=20, n_pt=1000, seed=0, mean_track=8.0, outlie
     pts = np.array(pts)
     del centre
 
-    # visibility table: for each (mkf, cam): pixel + valid
-    cam_from_world = [[rt_mul(extr[c], base_from_world[m]) for c in range(n_cam)] for m in range(n_mkf)]
-    px_all = np.zeros((n_mkf, n_cam, n_pt, 2))
-    ok_all = np.zeros((n_mkf, n_cam, n_pt), bool)
-    for m in range(n_mkf):
+    # visibility: every point has a "home" MKF; only MKFs within +-win of it are considered (co-visibility is local
+    # in real maps, and this keeps the table at O(P * win * C) instead of O(P * M * C))
+    win = min(n_mkf - 1, 12)
+    home = rng.integers(0, n_mkf, n_pt)
+    Rs = np.array([[rt_mul(extr[c], base_from_world[m])[0] for c in range(n_cam)] for m in range(n_mkf)])   # (M,C,3,3)
+    ts = np.array([[rt_mul(extr[c], base_from_world[m])[1] for c in range(n_cam)] for m in range(n_mkf)])   # (M,C,3)
+    offs = np.arange(-win, win + 1)
+    mk_idx = np.clip(home[:, None] + offs[None, :], 0, n_mkf - 1)          # (P, 2win+1)
+    nW = len(offs)
+    px_all = np.zeros((n_pt, nW, n_cam, 2), np.float32)
+    ok_all = np.zeros((n_pt, nW, n_cam), bool)
+    for j in range(nW):
+        m = mk_idx[:, j]
+        first = np.ones(n_pt, bool) if j == 0 else (m != mk_idx[:, j - 1])   # clipped duplicates count once
         for c in range(n_cam):
-            R, t = cam_from_world[m][c]
-            pc = pts @ R.T + t
+            pc = np.einsum("pij,pj->pi", Rs[m, c], pts) + ts[m, c]
             px, invalid = cam_project_np(cams[c], pc)
-            # keep away from the exact optical axis (asin/normalize singularity) and image border
             margin = (px[:, 0] > 8) & (px[:, 0] < cams[c].image_size[0] - 8) & (px[:, 1] > 8) & (px[:, 1] < cams[c].image_size[1] - 8)
             off_axis = np.hypot(pc[:, 0], pc[:, 1]) > 1e-3 * np.abs(pc[:, 2])
-            px_all[m, c] = px
-            ok_all[m, c] = (~invalid) & margin & off_axis
+            px_all[:, j, c] = px
+            ok_all[:, j, c] = (~invalid) & margin & off_axis & first
 
     meas_xy, meas_chain, meas_pt, meas_noise, meas_cam = [], [], [], [], []
     pt_chain = np.zeros((n_pt, 2), np.int32)
     pt_rel_true = np.zeros((n_pt, 3))
     keep_pt = np.zeros(n_pt, bool)
     level_p = np.array([0.5, 0.25, 0.15, 0.1])
+    Ls = np.maximum(2, np.rint(rng.gamma(4.0, mean_track / 4.0, n_pt)).astype(int))
+    u_all = rng.random((n_pt, 4))
     for p in range(n_pt):
-        vis = np.argwhere(ok_all[:, :, p])
+        okp = ok_all[p]
+        vis = np.argwhere(okp)
         if len(vis) < 2:
             continue
-        ms, cs = vis[rng.integers(len(vis))]
-        # observers: window of consecutive MKFs around the source (co-visibility is local in real maps)
-        L = max(2, int(round(rng.gamma(4.0, mean_track / 4.0))))
-        mk_vis = np.unique(vis[:, 0])
-        order = mk_vis[np.argsort(np.abs(mk_vis - ms), kind="stable")]
-        chosen = order[:L]
+        js, cs = vis[int(u_all[p, 0] * len(vis))]
+        ms = int(mk_idx[p, js])
+        # observers: the MKFs of the window closest to the source
+        jv = np.unique(vis[:, 0])
+        order = jv[np.argsort(np.abs(mk_idx[p, jv] - ms), kind="stable")]
+        chosen = order[: Ls[p]]
         obs = []
-        for m in chosen:
-            cc = np.flatnonzero(ok_all[m, :, p])
-            if m == ms:
+        for j in chosen:
+            cc = np.flatnonzero(okp[j])
+            if j == js:
                 sel = [cs]
                 if len(cc) > 1 and rng.random() < 0.15:
                     sel.append(int(rng.choice(cc[cc != cs])))
             else:
-                sel = [int(rng.choice(cc))]
+                sel = [int(cc[int(rng.random() * len(cc))])]
                 if len(cc) > 1 and rng.random() < 0.15:
                     sel.append(int(rng.choice(cc[cc != sel[0]])))
-            obs += [(int(m), int(c)) for c in sel]
-        if len({m for m, _ in obs}) < 2 and len(obs) < 2:
+            obs += [(int(j), int(c)) for c in sel]
+        if len(obs) < 2:
             continue
         keep_pt[p] = True
         pt_chain[p] = (ms, n_mkf + cs)
-        R, t = cam_from_world[ms][cs]
-        pt_rel_true[p] = R @ pts[p] + t
-        for m, c in obs:
+        pt_rel_true[p] = Rs[ms, cs] @ pts[p] + ts[ms, cs]
+        for j, c in obs:
+            m = int(mk_idx[p, j])
             lvl = int(rng.choice(4, p=level_p))
-            z = px_all[m, c, p] + rng.standard_normal(2) * pix_sigma * (1 << lvl)
+            z = px_all[p, j, c].astype(np.float64) + rng.standard_normal(2) * pix_sigma * (1 << lvl)
             if rng.random() < outlier_frac and not (m == ms and c == cs):
-                z = px_all[m, c, p] + rng.uniform(-30, 30, 2)
+                z = px_all[p, j, c].astype(np.float64) + rng.uniform(-30, 30, 2)
             meas_xy.append(z)
             meas_chain.append((m, n_mkf + c))
             meas_pt.append(p)

@@ -430,3 +430,61 @@ int ora_minipatch_find(const uint8_t* im, int w, int h, int stride, const uint8_
   if (nBest < 9999) { pos[0] = bx; pos[1] = by; return 1; }
   return 0;
 }
+
+/* include/mcptam/TrackerData.h:102-129 (Project, GetDerivsUnsafe) + src/PatchFinder.cc:69-122
+   (CalcSearchLevelAndWarpMatrix).  pose_Rt: camera-from-world, 12 doubles.  Returns the search level or -1. */
+int ora_project_point(const OraTaylorCam* cam, const double* pose_Rt, const double* pw, const double* right_w, const double* down_w,
+                      double* px2, double* derivs4, double* warp_inv4, double* v3cam, int* in_image)
+{
+  const double* R = pose_Rt; const double* t = pose_Rt + 9;
+  double vc[3], mr[3], md[3];
+  for (int i = 0; i < 3; i++) {
+    vc[i] = R[i * 3] * pw[0] + R[i * 3 + 1] * pw[1] + R[i * 3 + 2] * pw[2] + t[i];
+    mr[i] = R[i * 3] * right_w[0] + R[i * 3 + 1] * right_w[1] + R[i * 3 + 2] * right_w[2];
+    md[i] = R[i * 3] * down_w[0] + R[i * 3 + 1] * down_w[1] + R[i * 3 + 2] * down_w[2];
+  }
+  const int invalid = ora_cam_project(cam, vc, px2, derivs4);
+  for (int i = 0; i < 3; i++) v3cam[i] = vc[i];
+  *in_image = 0;
+  if (!invalid && !(px2[0] < 0 || px2[1] < 0 || px2[0] > cam->image_size[0] || px2[1] > cam->image_size[1])) *in_image = 1;   /* note '>' (TrackerData.h:113) */
+  double dth[3], dph[3];
+  ora_cam_sphere_deriv(vc, dth, dph);
+  const double r0 = dth[0] * mr[0] + dth[1] * mr[1] + dth[2] * mr[2], r1 = dph[0] * mr[0] + dph[1] * mr[1] + dph[2] * mr[2];
+  const double d0 = dth[0] * md[0] + dth[1] * md[1] + dth[2] * md[2], d1 = dph[0] * md[0] + dph[1] * md[1] + dph[2] * md[2];
+  /* mm2WarpInverse.T()[0] = D * right ; .T()[1] = D * down   (row-major out) */
+  warp_inv4[0] = derivs4[0] * r0 + derivs4[1] * r1; warp_inv4[2] = derivs4[2] * r0 + derivs4[3] * r1;
+  warp_inv4[1] = derivs4[0] * d0 + derivs4[1] * d1; warp_inv4[3] = derivs4[2] * d0 + derivs4[3] * d1;
+  double dDet = warp_inv4[0] * warp_inv4[3] - warp_inv4[1] * warp_inv4[2];
+  int level = 0;
+  while (dDet > 3 && level < 3) { level++; dDet *= 0.25; }
+  if (dDet > 3 || dDet < 0.5) return -1;
+  return level;
+}
+
+/* Batch driver of the per-patch oracle functions (src/Tracker.cc:1299-1377 loop body) for CPU timing without
+   per-call Python overhead.  req: n x {src_level, src_cx, src_cy, search_level, pred_x, pred_y, range, subpix_its,
+   exhaustive} ints + warp (2x2 m2 already inverted/scaled) doubles.  Returns the number found. */
+int ora_search_patches_batch(const uint8_t* const* src_pyr, const uint8_t* const* tgt_pyr, const int* widths, const int* heights,
+                             const int32_t* const* corners, const int* n_corners, const int32_t* const* luts, int n,
+                             const int32_t* req_i /*9 per req*/, const double* m2 /*4 per req*/, double* found_xy /*2 per req*/,
+                             int32_t* found_flag)
+{
+  int nf = 0;
+  for (int i = 0; i < n; i++) {
+    const int32_t* r = req_i + 9 * i;
+    const int sl = r[0], lvl = r[3];
+    uint8_t t[64];
+    found_flag[i] = 0;
+    if (ora_patch_template(src_pyr[sl], widths[sl], heights[sl], widths[sl], m2 + 4 * i, r[1], r[2], t)) continue;
+    int32_t best[2], score;
+    if (!ora_find_patch_coarse(tgt_pyr[lvl], widths[lvl], heights[lvl], widths[lvl], corners[lvl], n_corners[lvl], luts[lvl], t, lvl,
+                               r[4], r[5], r[6], r[8], best, &score)) continue;
+    const int ls = 1 << lvl;
+    double pos[2] = { (best[0] + 0.5) * ls - 0.5, (best[1] + 0.5) * ls - 0.5 };
+    if (r[7] > 0 && !ora_subpix(tgt_pyr[lvl], widths[lvl], heights[lvl], widths[lvl], t, lvl, pos, r[7])) continue;
+    found_xy[2 * i] = pos[0]; found_xy[2 * i + 1] = pos[1];
+    found_flag[i] = 1;
+    nf++;
+  }
+  return nf;
+}

@@ -139,6 +139,12 @@ int ora_minipatch_find(const uint8_t* im, int w, int h, int stride, const uint8_
                        const int32_t* corners_xy, int n_corners, const int32_t* row_lut_or_null,
                        int n_lut, int range, int32_t* pos_io);
 
+int ora_search_patches_batch(const uint8_t* const* src_pyr, const uint8_t* const* tgt_pyr, const int* widths, const int* heights,
+                             const int32_t* const* corners, const int* n_corners, const int32_t* const* luts, int n,
+                             const int32_t* req_i, const double* m2, double* found_xy, int32_t* found_flag);
+int ora_project_point(const OraTaylorCam* cam, const double* pose_Rt, const double* pw, const double* right_w, const double* down_w,
+                      double* px2, double* derivs4, double* warp_inv4, double* v3cam, int* in_image);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,7 @@ def lib():
         L.ora_minipatch_ssd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.ora_minipatch_find.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ora_project_point.argtypes = [C.c_void_p] * 10
     return _lib
 
 
@@ -318,3 +319,33 @@ def minipatch_find(img_src, img_dst, corners, lut, src_xy, start_xy, rng):
     f = lib().ora_minipatch_find(_p(img_dst), img_dst.shape[1], img_dst.shape[0], img_dst.shape[1], _p(patch), _p(corners), len(corners),
                                  _p(lut), len(lut), rng, _p(pos))
     return bool(f), pos
+
+
+def project_point(cam, pose_Rt, pw, right_w, down_w):
+    pose_Rt = np.ascontiguousarray(pose_Rt, np.float64); pw = np.ascontiguousarray(pw, np.float64)
+    right_w = np.ascontiguousarray(right_w, np.float64); down_w = np.ascontiguousarray(down_w, np.float64)
+    px = np.zeros(2); D = np.zeros(4); W = np.zeros(4); vc = np.zeros(3); inim = C.c_int()
+    lvl = lib().ora_project_point(C.byref(cam), _p(pose_Rt), _p(pw), _p(right_w), _p(down_w), _p(px), _p(D), _p(W), _p(vc), C.byref(inim))
+    return {"px": px, "derivs": D, "warp_inv": W, "v3cam": vc, "in_image": inim.value, "level": lvl}
+
+
+def search_patches_batch(pyr_src, pyr_tgt, tgt_levels, req):
+    """All requests in one C call (CPU timing baseline).  Returns (found flags, positions)."""
+    L = lib()
+    L.ora_search_patches_batch.argtypes = [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 4
+    n = len(req)
+    src = [np.ascontiguousarray(x, np.uint8) for x in pyr_src]
+    tgt = [np.ascontiguousarray(x, np.uint8) for x in pyr_tgt]
+    cor = [np.ascontiguousarray(l["corners"], np.int32) for l in tgt_levels]
+    lut = [np.ascontiguousarray(l["row_lut"], np.int32) for l in tgt_levels]
+    ptr = lambda arrs: (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    widths = np.array([x.shape[1] for x in src], np.int32); heights = np.array([x.shape[0] for x in src], np.int32)
+    ncor = np.array([len(c) for c in cor], np.int32)
+    ri = np.zeros((n, 9), np.int32); m2 = np.zeros((n, 4))
+    for i in range(n):
+        r = req[i]
+        ri[i] = (r["src_level"], r["src_cx"], r["src_cy"], r["search_level"], r["pred_x"], r["pred_y"], r["range"], r["subpix_its"], r["exhaustive"])
+        m2[i] = warp_matrix(r["warp_inv"], int(r["search_level"])).reshape(-1)
+    xy = np.zeros((n, 2)); flag = np.zeros(n, np.int32)
+    L.ora_search_patches_batch(ptr(src), ptr(tgt), _p(widths), _p(heights), ptr(cor), _p(ncor), ptr(lut), n, _p(ri), _p(m2), _p(xy), _p(flag))
+    return flag, xy

@@ -197,6 +197,33 @@ def test_shitomasi_and_minipatch(capi, ora):
                 assert tuple(pos[i]) == tuple(pr), i
 
 
+def test_project_points_parity(capi, ora):
+    """FindPVS building block: Project + GetDerivsUnsafe + CalcSearchLevelAndWarpMatrix vs the oracle (1e-12 relative)."""
+    rng = np.random.default_rng(3)
+    cams, extr = synth.make_rig(2, rng)
+    cam = cams[0]
+    f = capi.FeHandle(640, 480)
+    f.set_camera(cam)
+    R = synth.so3_exp(rng.normal(0, 0.3, 3)); t = rng.normal(0, 0.5, 3)
+    T = synth.rt_pack((R, t))
+    n = 4000
+    pc = rng.normal(0, 1, (n, 3)) * [4, 4, 2] + [0, 0, 6]              # mostly in front of the camera
+    pw = (pc - t) @ R                                                   # world = R^T (pc - t)
+    rw = rng.normal(0, 1, (n, 3)) * 0.01 * np.linalg.norm(pc, axis=1)[:, None]
+    dw = rng.normal(0, 1, (n, 3)) * 0.01 * np.linalg.norm(pc, axis=1)[:, None]
+    res = f.project_points(T, pw, rw, dw)
+    n_lvl = 0
+    for i in range(n):
+        ref = ora.project_point(cam, T, pw[i], rw[i], dw[i])
+        assert res[i]["in_image"] == ref["in_image"], i
+        assert res[i]["search_level"] == ref["level"], (i, res[i]["search_level"], ref["level"], res[i]["warp_inv"], ref["warp_inv"])
+        n_lvl += ref["level"] >= 0
+        for key in ("px", "cam_derivs", "warp_inv", "v3cam"):
+            a, b = res[i][key], ref[key if key != "cam_derivs" else "derivs"]
+            assert np.allclose(a, b, rtol=1e-11, atol=1e-9), (i, key, a, b)
+    assert n_lvl > 50 and res["in_image"].sum() > 500
+
+
 def test_fe_errors(capi):
     f = capi.FeHandle(640, 480)
     req = np.zeros(1, capi.PATCH_REQ_DTYPE)
