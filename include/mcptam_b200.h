@@ -247,6 +247,34 @@ int mcp_fe_set_camera(McpFe* h, const McpTaylorCam* cam);
 /* cam_from_world: 12 doubles (row-major R, t); world_xyz / pixel_right_w / pixel_down_w: n x 3 doubles (host) */
 int mcp_fe_project_points(McpFe* h, const double* cam_from_world, int32_t n, const double* world_xyz,
                           const double* pixel_right_w, const double* pixel_down_w, McpProjRes* out);
+/* Tracker pose update ("next" row): TrackerData::ProjectAndDerivs + CalcJacobian (include/mcptam/TrackerData.h:102-178)
+ * and Tracker::CalcPoseUpdate (src/Tracker.cc:1386-1511, TooN WLS<6> with prior 100). */
+typedef struct McpJacRes {
+  double px[2];          /* td.mv2Image */
+  double jac[12];        /* td.mm26Jacobian, row-major 2x6, w.r.t. the MKF base pose */
+  int32_t in_image, pad_;
+} McpJacRes;
+typedef struct McpPoseMeas {
+  double found[2];       /* td.mv2Found */
+  double image[2];       /* td.mv2Image */
+  double sqrt_inv_noise; /* td.mdSqrtInvNoise */
+  double jac[12];        /* td.mm26Jacobian */
+  int32_t found_flag;    /* td.mbFound */
+  int32_t pad_;
+} McpPoseMeas;
+typedef struct McpPoseUpdate {
+  double mu[6];          /* wls.get_mu(): the 6-vector pose update */
+  double sigma_sq;       /* M-estimator sigma^2 used */
+  double c_inv[36];      /* wls.get_C_inv() (for the pose covariance) */
+  int32_t n_inliers;     /* measurements with non-zero weight */
+  int32_t n_valid;       /* found measurements */
+} McpPoseUpdate;
+int mcp_fe_calc_jacobians(McpFe* h, const double* base_from_world, const double* cam_from_base, int32_t n,
+                          const double* world_xyz, McpJacRes* out);
+/* estimator: 0 Tukey, 1 Cauchy, 2 Huber (Tracker::sMEstimatorName); override_sigma <= 0: estimate from the data.
+ * outlier[i] = 1 where the weight is exactly zero (may be NULL). */
+int mcp_fe_pose_update(McpFe* h, int32_t n, const McpPoseMeas* meas, int32_t estimator, double override_sigma,
+                       McpPoseUpdate* out, int32_t* outlier);
 typedef struct McpFeTiming { double ms_pyramid, ms_fast, ms_compact, ms_search, ms_other; int32_t n_launches, pad_; } McpFeTiming;
 int mcp_fe_get_timing(McpFe* h, McpFeTiming* out);
 

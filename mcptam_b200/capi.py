@@ -274,6 +274,9 @@ class FeTiming(C.Structure):
 PATCH_REQ_DTYPE = np.dtype([("src_kf", "i4"), ("src_level", "i4"), ("src_cx", "i4"), ("src_cy", "i4"), ("warp_inv", "f8", 4),
                             ("search_level", "i4"), ("pred_x", "i4"), ("pred_y", "i4"), ("range", "i4"), ("subpix_its", "i4"),
                             ("exhaustive", "i4")], align=True)
+JAC_RES_DTYPE = np.dtype([("px", "f8", 2), ("jac", "f8", 12), ("in_image", "i4"), ("pad_", "i4")], align=True)
+POSE_MEAS_DTYPE = np.dtype([("found", "f8", 2), ("image", "f8", 2), ("sqrt_inv_noise", "f8"), ("jac", "f8", 12), ("found_flag", "i4"), ("pad_", "i4")], align=True)
+POSE_UPDATE_DTYPE = np.dtype([("mu", "f8", 6), ("sigma_sq", "f8"), ("c_inv", "f8", 36), ("n_inliers", "i4"), ("n_valid", "i4")], align=True)
 PROJ_RES_DTYPE = np.dtype([("px", "f8", 2), ("cam_derivs", "f8", 4), ("warp_inv", "f8", 4), ("v3cam", "f8", 3), ("in_image", "i4"), ("search_level", "i4")], align=True)
 PATCH_RES_DTYPE = np.dtype([("template_bad", "i4"), ("found", "i4"), ("did_subpix", "i4"), ("score", "i4"), ("coarse_x", "i4"),
                             ("coarse_y", "i4"), ("found_x", "f8"), ("found_y", "f8"), ("n_candidates", "i4"), ("pad_", "i4")], align=True)
@@ -298,6 +301,8 @@ def _bind_fe(L):
                                         C.c_int32, C.c_void_p, C.c_void_p]
     L.mcp_fe_get_timing.argtypes = [C.c_void_p, C.POINTER(FeTiming)]
     L.mcp_fe_set_camera.argtypes = [C.c_void_p, C.c_void_p]
+    L.mcp_fe_calc_jacobians.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.mcp_fe_pose_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     L.mcp_fe_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcp_fe_debug_scores.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     _fe_bound = True
@@ -402,6 +407,20 @@ class FeHandle:
         out = np.zeros(len(pw), PROJ_RES_DTYPE)
         check(self.L.mcp_fe_project_points(self.h, _p(T), len(pw), _p(pw), _p(rw), _p(dw), _p(out)))
         return out
+
+    def calc_jacobians(self, base_from_world, cam_from_base, world_xyz):
+        b = np.ascontiguousarray(base_from_world, np.float64); cb = np.ascontiguousarray(cam_from_base, np.float64)
+        pw = np.ascontiguousarray(world_xyz, np.float64)
+        out = np.zeros(len(pw), JAC_RES_DTYPE)
+        check(self.L.mcp_fe_calc_jacobians(self.h, _p(b), _p(cb), len(pw), _p(pw), _p(out)))
+        return out
+
+    def pose_update(self, meas, estimator=0, override_sigma=0.0):
+        meas = np.ascontiguousarray(meas, POSE_MEAS_DTYPE)
+        out = np.zeros(1, POSE_UPDATE_DTYPE)
+        outlier = np.zeros(max(len(meas), 1), np.int32)
+        check(self.L.mcp_fe_pose_update(self.h, len(meas), _p(meas), estimator, float(override_sigma), _p(out), _p(outlier)))
+        return out[0], outlier[:len(meas)]
 
     def debug_scores(self, slot, level):
         w, h = self.cfg.width >> level, self.cfg.height >> level

@@ -12,6 +12,8 @@ void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s);
 int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s);
 void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s);
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s);
+void fe_launch_calc_jacobians(const DevCam& cam, const Se3& B, const Se3& Cb, int n, const double* pw, McpJacRes* out, cudaStream_t s);
+void fe_launch_pose_update(int n, const McpPoseMeas* meas, int estimator, double override_sigma, double* e2buf, McpPoseUpdate* res, int* outlier, cudaStream_t s);
 void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s);
 void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
                          int2* pos, int* found, cudaStream_t s);
@@ -45,6 +47,7 @@ struct McpFe {
   int last_n = 0;
   DevCam cam; bool has_cam = false;
   double* proj_in = nullptr; McpProjRes* proj_out = nullptr; size_t proj_cap = 0;
+  void* pu_buf = nullptr; size_t pu_cap = 0;
   McpFeTiming timing;
   int lw[MCP_LEVELS], lh[MCP_LEVELS], lp[MCP_LEVELS];
 };
@@ -179,6 +182,7 @@ int mcp_fe_destroy(McpFe* h)
   if (h->aux_host) cudaFreeHost(h->aux_host);
   if (h->proj_in) cudaFree(h->proj_in);
   if (h->proj_out) cudaFree(h->proj_out);
+  if (h->pu_buf) cudaFree(h->pu_buf);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -375,6 +379,7 @@ int mcp_fe_project_points(McpFe* h, const double* cam_from_world, int32_t n, con
   if ((size_t)n > h->proj_cap) {
     if (h->proj_in) cudaFree(h->proj_in);
     if (h->proj_out) cudaFree(h->proj_out);
+  if (h->pu_buf) cudaFree(h->pu_buf);
     h->proj_cap = (size_t)n + n / 4 + 64;
     MCP_CUDA_CHECK(cudaMalloc(&h->proj_in, sizeof(double) * 9 * h->proj_cap));
     MCP_CUDA_CHECK(cudaMalloc(&h->proj_out, sizeof(McpProjRes) * h->proj_cap));
@@ -387,6 +392,58 @@ int mcp_fe_project_points(McpFe* h, const double* cam_from_world, int32_t n, con
   memcpy(T.R, cam_from_world, sizeof(double) * 9); memcpy(T.t, cam_from_world + 9, sizeof(double) * 3);
   fe_launch_project(h->cam, T, n, pw, rw, dw, h->proj_out, s);
   MCP_CUDA_CHECK(cudaMemcpyAsync(out, h->proj_out, sizeof(McpProjRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MCP_OK;
+}
+
+static int ensure_pu(McpFe* h, size_t n)
+{
+  if (n <= h->pu_cap) return MCP_OK;
+  if (h->pu_buf) cudaFree(h->pu_buf);
+  h->pu_cap = n + n / 4 + 64;
+  const size_t per = sizeof(McpPoseMeas) + sizeof(McpJacRes) + sizeof(double) * 4 + sizeof(int);
+  MCP_CUDA_CHECK(cudaMalloc(&h->pu_buf, per * h->pu_cap + sizeof(McpPoseUpdate) + 256));
+  return MCP_OK;
+}
+
+int mcp_fe_calc_jacobians(McpFe* h, const double* base_from_world, const double* cam_from_base, int32_t n, const double* world_xyz, McpJacRes* out)
+{
+  if (!h || !base_from_world || !cam_from_base || n < 0 || (n && (!world_xyz || !out))) { set_last_error("mcp_fe_calc_jacobians: bad arguments"); return MCP_ERR_INVALID; }
+  if (!h->has_cam) { set_last_error("mcp_fe_calc_jacobians: call mcp_fe_set_camera first"); return MCP_ERR_STATE; }
+  if (n == 0) return MCP_OK;
+  cudaSetDevice(h->device);
+  int rc = ensure_pu(h, (size_t)n);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  double* pw = reinterpret_cast<double*>(h->pu_buf);
+  McpJacRes* jr = reinterpret_cast<McpJacRes*>(pw + 4 * h->pu_cap);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(pw, world_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  Se3 B, Cb;
+  memcpy(B.R, base_from_world, 72); memcpy(B.t, base_from_world + 9, 24);
+  memcpy(Cb.R, cam_from_base, 72); memcpy(Cb.t, cam_from_base + 9, 24);
+  fe_launch_calc_jacobians(h->cam, B, Cb, n, pw, jr, s);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, jr, sizeof(McpJacRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MCP_OK;
+}
+
+int mcp_fe_pose_update(McpFe* h, int32_t n, const McpPoseMeas* meas, int32_t estimator, double override_sigma, McpPoseUpdate* out, int32_t* outlier)
+{
+  if (!h || n < 0 || (n && !meas) || !out || estimator < 0 || estimator > 2) { set_last_error("mcp_fe_pose_update: bad arguments"); return MCP_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  int rc = ensure_pu(h, (size_t)std::max(n, 1));
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  // layout: [pw 4*cap doubles | McpJacRes cap | McpPoseMeas cap | int cap | McpPoseUpdate]; e2 scratch aliases the pw region
+  double* e2 = reinterpret_cast<double*>(h->pu_buf);
+  McpJacRes* jr = reinterpret_cast<McpJacRes*>(e2 + 4 * h->pu_cap);
+  McpPoseMeas* dm = reinterpret_cast<McpPoseMeas*>(jr + h->pu_cap);
+  int* dout = reinterpret_cast<int*>(dm + h->pu_cap);
+  McpPoseUpdate* dres = reinterpret_cast<McpPoseUpdate*>(reinterpret_cast<char*>(dout + h->pu_cap) + 128 - (reinterpret_cast<uintptr_t>(dout + h->pu_cap) % 128));
+  if (n) MCP_CUDA_CHECK(cudaMemcpyAsync(dm, meas, sizeof(McpPoseMeas) * (size_t)n, cudaMemcpyHostToDevice, s));
+  fe_launch_pose_update(n, dm, estimator, override_sigma, e2, dres, dout, s);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(out, dres, sizeof(McpPoseUpdate), cudaMemcpyDeviceToHost, s));
+  if (outlier && n) MCP_CUDA_CHECK(cudaMemcpyAsync(outlier, dout, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));
   return MCP_OK;
 }

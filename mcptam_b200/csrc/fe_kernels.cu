@@ -654,6 +654,178 @@ __global__ void k_project_points(DevCam cam, Se3 T, int n, const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tracker pose update ("next" row f-1): TrackerData::ProjectAndDerivs + CalcJacobian per point
+// (include/mcptam/TrackerData.h:102-178) and Tracker::CalcPoseUpdate (src/Tracker.cc:1386-1511).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_calc_jacobians(DevCam cam, Se3 B, Se3 Cb, int n, const double* __restrict__ pw, McpJacRes* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = { pw[3 * i], pw[3 * i + 1], pw[3 * i + 2] };
+  double vb[3], vc[3], G[6];
+  se3_apply(B, p, vb);
+  se3_apply(Cb, vb, vc);
+  McpJacRes o;
+  const bool invalid = cam_project(cam, vc, o.px, G);       // G = D * [dTheta; dPhi]  (2x3)
+  o.in_image = (!invalid && !(o.px[0] < 0 || o.px[1] < 0 || o.px[0] > cam.image_size[0] || o.px[1] > cam.image_size[1])) ? 1 : 0;
+  o.pad_ = 0;
+  double A[6];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) A[r * 3 + c] = G[r * 3] * Cb.R[c] + G[r * 3 + 1] * Cb.R[3 + c] + G[r * 3 + 2] * Cb.R[6 + c];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const double a0 = A[r * 3], a1 = A[r * 3 + 1], a2 = A[r * 3 + 2];
+    o.jac[r * 6 + 0] = a0; o.jac[r * 6 + 1] = a1; o.jac[r * 6 + 2] = a2;
+    o.jac[r * 6 + 3] = -a1 * vb[2] + a2 * vb[1];
+    o.jac[r * 6 + 4] = a0 * vb[2] - a2 * vb[0];
+    o.jac[r * 6 + 5] = -a0 * vb[1] + a1 * vb[0];
+  }
+  out[i] = o;
+}
+
+// one block: errors, exact upper median (radix select in shared/global), M-estimator weights, 6x6 WLS with prior
+__global__ void __launch_bounds__(1024) k_pose_update(int n, const McpPoseMeas* __restrict__ meas, int estimator, double override_sigma,
+                                                     double* __restrict__ e2buf, McpPoseUpdate* __restrict__ res, int* __restrict__ outlier)
+{
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank, s_count;
+  __shared__ double acc[27][33];
+  __shared__ double s_sig2;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    double e2 = -1.0;
+    if (meas[i].found_flag) {
+      const double ex = meas[i].sqrt_inv_noise * (meas[i].found[0] - meas[i].image[0]);
+      const double ey = meas[i].sqrt_inv_noise * (meas[i].found[1] - meas[i].image[1]);
+      e2 = ex * ex + ey * ey;
+      atomicAdd(&s_count, 1u);
+    }
+    e2buf[i] = e2;
+    outlier[i] = 0;
+  }
+  __syncthreads();
+  const unsigned nv = s_count;
+  if (nv == 0) {
+    if (tid == 0) { for (int k = 0; k < 6; k++) res->mu[k] = 0; res->sigma_sq = 0; res->n_inliers = 0; res->n_valid = 0; }
+    return;
+  }
+  if (override_sigma > 0) { if (tid == 0) s_sig2 = override_sigma; }
+  else {
+    if (tid == 0) { s_prefix = 0ull; s_rank = nv / 2; }
+    for (int pass = 0; pass < 6; pass++) {
+      const int shift = 63 - 11 * (pass + 1);
+      for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const double v = e2buf[i];
+        if (v < 0) continue;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+        unsigned long long hi; unsigned dig;
+        if (shift >= 0) { hi = key >> (shift + 11); dig = (unsigned)(key >> shift) & 2047u; }
+        else { hi = key >> (11 + shift); dig = (unsigned)(key << (-shift)) & 2047u; }
+        if (pass == 0 || hi == prefix) atomicAdd(&hist[dig], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned r = s_rank, a = 0; int b = 0;
+        for (b = 0; b < 2048; b++) { if (a + hist[b] > r) break; a += hist[b]; }
+        if (b >= 2048) b = 2047;
+        s_rank = r - a;
+        s_prefix = (shift >= 0) ? ((prefix << 11) | (unsigned)b) : ((prefix << (11 + shift)) | ((unsigned)b >> (-shift)));
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const double med = __longlong_as_double((long long)s_prefix);
+      double s = 1.4826 * (1 + 5.0 / (double)((size_t)nv * 2 - 6)) * sqrt(med);
+      s = (estimator == 2 ? 1.345 : 4.6851) * s;
+      s_sig2 = s * s;
+    }
+  }
+  __syncthreads();
+  const double sig2 = s_sig2;
+  // 21 upper-triangle entries of C_inv + 6 of the vector, per-thread partials
+  double part[27];
+#pragma unroll
+  for (int k = 0; k < 27; k++) part[k] = 0.0;
+  int n_in = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double esq = e2buf[i];
+    if (esq < 0) continue;
+    double w;
+    if (estimator == 0) { const double sq = esq > sig2 ? 0.0 : 1.0 - (esq / sig2); w = sq * sq; }
+    else if (estimator == 1) w = 1.0 / (1.0 + esq / sig2);
+    else w = esq < sig2 ? 1.0 : sqrt(sig2 / esq);
+    if (w == 0.0) { outlier[i] = 1; continue; }
+    n_in++;
+    const double sn = meas[i].sqrt_inv_noise;
+    const double ex = sn * (meas[i].found[0] - meas[i].image[0]), ey = sn * (meas[i].found[1] - meas[i].image[1]);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      double J[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) J[k] = sn * meas[i].jac[6 * r + k];
+      const double er = r == 0 ? ex : ey;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int b = a; b < 6; b++) part[q++] += (J[a] * w) * J[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; a++) part[21 + a] += er * (J[a] * w);
+    }
+  }
+  // block reduction (warp shuffles, then 32 warp partials in shared memory)
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    double v = part[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) acc[k][wid] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  __shared__ int s_nin[32];
+  if (lane == 0) s_nin[wid] = n_in;
+  __syncthreads();
+  if (tid == 0) {
+    const int nwarps = blockDim.x >> 5;
+    double Cinv[36], vec[6];
+    int q = 0, total_in = 0;
+    for (int w2 = 0; w2 < nwarps; w2++) total_in += s_nin[w2];
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++, q++) { double s = 0; for (int w2 = 0; w2 < nwarps; w2++) s += acc[q][w2]; Cinv[a * 6 + b] = s; Cinv[b * 6 + a] = s; }
+    for (int a = 0; a < 6; a++) { double s = 0; for (int w2 = 0; w2 < nwarps; w2++) s += acc[21 + a][w2]; vec[a] = s; Cinv[a * 6 + a] += 100.0; }   // add_prior(100)
+    // TooN::Cholesky<6> (LDL^T) backsub
+    double c[36];
+    for (int i = 0; i < 36; i++) { c[i] = Cinv[i]; res->c_inv[i] = Cinv[i]; }
+    for (int col = 0; col < 6; col++) {
+      double inv_diag = 1;
+      for (int row = col; row < 6; row++) {
+        double val = c[row * 6 + col];
+        for (int col2 = 0; col2 < col; col2++) val -= c[col2 * 6 + col] * c[row * 6 + col2];
+        if (row == col) { c[row * 6 + col] = val; inv_diag = 1 / val; }
+        else { c[col * 6 + row] = val; c[row * 6 + col] = val * inv_diag; }
+      }
+    }
+    double y[6], mu[6];
+    for (int i = 0; i < 6; i++) { double val = vec[i]; for (int j = 0; j < i; j++) val -= c[i * 6 + j] * y[j]; y[i] = val; }
+    for (int i = 0; i < 6; i++) y[i] /= c[i * 6 + i];
+    for (int i = 5; i >= 0; i--) { double val = y[i]; for (int j = i + 1; j < 6; j++) val -= c[j * 6 + i] * mu[j]; mu[i] = val; }
+    for (int k = 0; k < 6; k++) res->mu[k] = mu[k];
+    res->sigma_sq = sig2; res->n_inliers = total_in; res->n_valid = (int)nv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s)
@@ -687,6 +859,14 @@ void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchRe
 void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s)
 {
   if (n > 0) k_project_points<<<(n + 127) / 128, 128, 0, s>>>(cam, T, n, pw, rw, dw, out);
+}
+void fe_launch_calc_jacobians(const DevCam& cam, const Se3& B, const Se3& Cb, int n, const double* pw, McpJacRes* out, cudaStream_t s)
+{
+  if (n > 0) k_calc_jacobians<<<(n + 127) / 128, 128, 0, s>>>(cam, B, Cb, n, pw, out);
+}
+void fe_launch_pose_update(int n, const McpPoseMeas* meas, int estimator, double override_sigma, double* e2buf, McpPoseUpdate* res, int* outlier, cudaStream_t s)
+{
+  k_pose_update<<<1, 1024, 0, s>>>(n, meas, estimator, override_sigma, e2buf, res, outlier);
 }
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s)
 {

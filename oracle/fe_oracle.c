@@ -488,3 +488,95 @@ int ora_search_patches_batch(const uint8_t* const* src_pyr, const uint8_t* const
   }
   return nf;
 }
+
+/* TrackerData::ProjectAndDerivs + CalcJacobian (include/mcptam/TrackerData.h:102-178): 2x6 Jacobian of the pixel
+   w.r.t. the MKF base pose.  base_Rt: base-from-world, cfb_Rt: cam-from-base.  J12 row-major 2x6. */
+int ora_calc_jacobian(const OraTaylorCam* cam, const double* base_Rt, const double* cfb_Rt, const double* pw, double* px2,
+                      double* derivs4, double* J12)
+{
+  double vb[3], vc[3];
+  for (int i = 0; i < 3; i++) vb[i] = base_Rt[i * 3] * pw[0] + base_Rt[i * 3 + 1] * pw[1] + base_Rt[i * 3 + 2] * pw[2] + base_Rt[9 + i];
+  for (int i = 0; i < 3; i++) vc[i] = cfb_Rt[i * 3] * vb[0] + cfb_Rt[i * 3 + 1] * vb[1] + cfb_Rt[i * 3 + 2] * vb[2] + cfb_Rt[9 + i];
+  const int invalid = ora_cam_project(cam, vc, px2, derivs4);
+  double dth[3], dph[3];
+  ora_cam_sphere_deriv(vc, dth, dph);
+  for (int m = 0; m < 6; m++) {
+    double mb[3] = { 0, 0, 0 };
+    if (m < 3) mb[m] = 1.0;
+    else { const int k = m - 3; mb[(k + 1) % 3] = -vb[(k + 2) % 3]; mb[(k + 2) % 3] = vb[(k + 1) % 3]; }
+    double mc[3];
+    for (int i = 0; i < 3; i++) mc[i] = cfb_Rt[i * 3] * mb[0] + cfb_Rt[i * 3 + 1] * mb[1] + cfb_Rt[i * 3 + 2] * mb[2];
+    const double s0 = dth[0] * mc[0] + dth[1] * mc[1] + dth[2] * mc[2], s1 = dph[0] * mc[0] + dph[1] * mc[1] + dph[2] * mc[2];
+    J12[m] = derivs4[0] * s0 + derivs4[1] * s1;
+    J12[6 + m] = derivs4[2] * s0 + derivs4[3] * s1;
+  }
+  return invalid;
+}
+
+static int cmp_d(const void* a, const void* b) { const double x = *(const double*)a, y = *(const double*)b; return (x > y) - (x < y); }
+/* Tracker::CalcPoseUpdate (src/Tracker.cc:1386-1511) with [3P] TooN WLS<6> (prior 100, Cholesky LDL^T).
+   estimator: 0 Tukey, 1 Cauchy, 2 Huber (include/mcptam/MEstimator.h).  outlier[i] = 1 where the weight is exactly 0. */
+int ora_pose_update(int n, const double* found_xy, const double* image_xy, const double* sqrt_inv_noise, const double* jac12,
+                    const int32_t* found, int estimator, double override_sigma, double* mu6, double* sigma_sq_out, int32_t* outlier)
+{
+  double* e2 = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  double* ex = (double*)malloc(sizeof(double) * 2 * (size_t)(n > 0 ? n : 1));
+  int nv = 0;
+  for (int i = 0; i < n; i++) {
+    outlier[i] = 0;
+    if (!found[i]) continue;
+    ex[2 * i] = sqrt_inv_noise[i] * (found_xy[2 * i] - image_xy[2 * i]);
+    ex[2 * i + 1] = sqrt_inv_noise[i] * (found_xy[2 * i + 1] - image_xy[2 * i + 1]);
+    e2[nv++] = ex[2 * i] * ex[2 * i] + ex[2 * i + 1] * ex[2 * i + 1];
+  }
+  for (int k = 0; k < 6; k++) mu6[k] = 0;
+  *sigma_sq_out = 0;
+  if (nv == 0) { free(e2); free(ex); return 0; }
+  double sig2;
+  if (override_sigma > 0) sig2 = override_sigma;
+  else {
+    qsort(e2, (size_t)nv, sizeof(double), cmp_d);
+    const double med = e2[nv / 2];
+    double s = 1.4826 * (1 + 5.0 / (double)((size_t)nv * 2 - 6)) * sqrt(med);
+    s = (estimator == 2 ? 1.345 : 4.6851) * s;
+    sig2 = s * s;
+  }
+  *sigma_sq_out = sig2;
+  double Cinv[36], vec[6];
+  for (int i = 0; i < 36; i++) Cinv[i] = 0;
+  for (int i = 0; i < 6; i++) { Cinv[i * 6 + i] = 100.0; vec[i] = 0; }
+  int n_in = 0;
+  for (int i = 0; i < n; i++) {
+    if (!found[i]) continue;
+    const double esq = ex[2 * i] * ex[2 * i] + ex[2 * i + 1] * ex[2 * i + 1];
+    double w;
+    if (estimator == 0) { const double sq = esq > sig2 ? 0.0 : 1.0 - (esq / sig2); w = sq * sq; }
+    else if (estimator == 1) w = 1.0 / (1.0 + esq / sig2);
+    else w = esq < sig2 ? 1.0 : sqrt(sig2 / esq);
+    if (w == 0.0) { outlier[i] = 1; continue; }
+    n_in++;
+    for (int r = 0; r < 2; r++) {
+      double J[6], Jw[6];
+      for (int k = 0; k < 6; k++) { J[k] = sqrt_inv_noise[i] * jac12[12 * i + 6 * r + k]; Jw[k] = J[k] * w; }
+      for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) Cinv[a * 6 + b] += Jw[a] * J[b]; vec[a] += ex[2 * i + r] * Jw[a]; }
+    }
+  }
+  /* TooN::Cholesky<6> (LDL^T) backsub */
+  double c[36];
+  for (int i = 0; i < 36; i++) c[i] = Cinv[i];
+  for (int col = 0; col < 6; col++) {
+    double inv_diag = 1;
+    for (int row = col; row < 6; row++) {
+      double val = c[row * 6 + col];
+      for (int col2 = 0; col2 < col; col2++) val -= c[col2 * 6 + col] * c[row * 6 + col2];
+      if (row == col) { c[row * 6 + col] = val; inv_diag = 1 / val; }
+      else { c[col * 6 + row] = val; c[row * 6 + col] = val * inv_diag; }
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) { double val = vec[i]; for (int j = 0; j < i; j++) val -= c[i * 6 + j] * y[j]; y[i] = val; }
+  for (int i = 0; i < 6; i++) y[i] /= c[i * 6 + i];
+  for (int i = 5; i >= 0; i--) { double val = y[i]; for (int j = i + 1; j < 6; j++) val -= c[j * 6 + i] * mu6[j]; mu6[i] = val; }
+  free(e2); free(ex);
+  return n_in;
+}

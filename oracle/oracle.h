@@ -142,6 +142,9 @@ int ora_minipatch_find(const uint8_t* im, int w, int h, int stride, const uint8_
 int ora_search_patches_batch(const uint8_t* const* src_pyr, const uint8_t* const* tgt_pyr, const int* widths, const int* heights,
                              const int32_t* const* corners, const int* n_corners, const int32_t* const* luts, int n,
                              const int32_t* req_i, const double* m2, double* found_xy, int32_t* found_flag);
+int ora_calc_jacobian(const OraTaylorCam* cam, const double* base_Rt, const double* cfb_Rt, const double* pw, double* px2, double* derivs4, double* J12);
+int ora_pose_update(int n, const double* found_xy, const double* image_xy, const double* sqrt_inv_noise, const double* jac12,
+                    const int32_t* found, int estimator, double override_sigma, double* mu6, double* sigma_sq_out, int32_t* outlier);
 int ora_project_point(const OraTaylorCam* cam, const double* pose_Rt, const double* pw, const double* right_w, const double* down_w,
                       double* px2, double* derivs4, double* warp_inv4, double* v3cam, int* in_image);
 

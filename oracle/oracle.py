@@ -349,3 +349,24 @@ def search_patches_batch(pyr_src, pyr_tgt, tgt_levels, req):
     xy = np.zeros((n, 2)); flag = np.zeros(n, np.int32)
     L.ora_search_patches_batch(ptr(src), ptr(tgt), _p(widths), _p(heights), ptr(cor), _p(ncor), ptr(lut), n, _p(ri), _p(m2), _p(xy), _p(flag))
     return flag, xy
+
+
+def calc_jacobian(cam, base_Rt, cfb_Rt, pw):
+    L = lib()
+    L.ora_calc_jacobian.argtypes = [C.c_void_p] * 7
+    b = np.ascontiguousarray(base_Rt, np.float64); c = np.ascontiguousarray(cfb_Rt, np.float64); w = np.ascontiguousarray(pw, np.float64)
+    px = np.zeros(2); D = np.zeros(4); J = np.zeros(12)
+    inv = L.ora_calc_jacobian(C.byref(cam), _p(b), _p(c), _p(w), _p(px), _p(D), _p(J))
+    return px, D, J.reshape(2, 6), inv
+
+
+def pose_update(found_xy, image_xy, sqrt_inv_noise, jac, found, estimator=0, override_sigma=0.0):
+    L = lib()
+    L.ora_pose_update.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_double] + [C.c_void_p] * 3
+    n = len(found)
+    f = np.ascontiguousarray(found_xy, np.float64); im = np.ascontiguousarray(image_xy, np.float64)
+    s = np.ascontiguousarray(sqrt_inv_noise, np.float64); j = np.ascontiguousarray(jac, np.float64).reshape(n, 12)
+    fl = np.ascontiguousarray(found, np.int32)
+    mu = np.zeros(6); sig = C.c_double(); out = np.zeros(n, np.int32)
+    nin = L.ora_pose_update(n, _p(f), _p(im), _p(s), _p(j), _p(fl), estimator, float(override_sigma), _p(mu), C.byref(sig), _p(out))
+    return mu, sig.value, out, nin

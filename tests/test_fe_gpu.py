@@ -224,6 +224,48 @@ def test_project_points_parity(capi, ora):
     assert n_lvl > 50 and res["in_image"].sum() > 500
 
 
+@pytest.mark.parametrize("estimator", [0, 1, 2])
+def test_pose_update_parity(capi, ora, estimator):
+    """Tracker pose update: CalcJacobian per point (1e-11) and CalcPoseUpdate (robust WLS<6>, 1e-9) vs the oracle."""
+    rng = np.random.default_rng(17 + estimator)
+    cams, extr = synth.make_rig(2, rng)
+    cam = cams[1]
+    f = capi.FeHandle(640, 480)
+    f.set_camera(cam)
+    B = synth.rt_pack((synth.so3_exp(rng.normal(0, 0.2, 3)), rng.normal(0, 0.5, 3)))
+    Cb = synth.rt_pack(extr[1])
+    n = 1500
+    Rb, tb = B[:9].reshape(3, 3), B[9:]
+    Rc, tc = Cb[:9].reshape(3, 3), Cb[9:]
+    pc = rng.normal(0, 1, (n, 3)) * [3, 3, 1.5] + [0, 0, 6]
+    pw = ((pc - tc) @ Rc - tb) @ Rb                      # world = Rb^T (Rc^T (pc - tc) - tb)
+    jr = f.calc_jacobians(B, Cb, pw)
+    meas = np.zeros(n, capi.POSE_MEAS_DTYPE)
+    for i in range(n):
+        px, D, J, inv = ora.calc_jacobian(cam, B, Cb, pw[i])
+        assert np.allclose(jr[i]["px"], px, rtol=1e-12, atol=1e-9)
+        assert np.allclose(jr[i]["jac"].reshape(2, 6), J, rtol=1e-10, atol=1e-8), i
+    meas["image"] = jr["px"]; meas["jac"] = jr["jac"]
+    lvl = rng.integers(0, 4, n)
+    meas["sqrt_inv_noise"] = 1.0 / (1 << lvl)
+    true_mu = np.array([0.02, -0.01, 0.015, 0.004, -0.003, 0.002])
+    pred = np.einsum("nij,j->ni", jr["jac"].reshape(n, 2, 6), true_mu)
+    meas["found"] = jr["px"] + pred + rng.normal(0, 0.3, (n, 2)) * (1 << lvl)[:, None]
+    bad = rng.random(n) < 0.1
+    meas["found"][bad] += rng.uniform(-40, 40, (bad.sum(), 2))
+    meas["found_flag"] = (rng.random(n) < 0.8) & (jr["in_image"] == 1)
+    for override in (0.0, 25.0):
+        res, outl = f.pose_update(meas, estimator, override)
+        mu, sig, out_ref, nin = ora.pose_update(meas["found"], meas["image"], meas["sqrt_inv_noise"], meas["jac"], meas["found_flag"], estimator, override)
+        assert abs(res["sigma_sq"] - sig) <= 1e-12 * sig         # same median element (errors differ by FMA rounding only)
+        assert np.array_equal(outl, out_ref) and res["n_inliers"] == nin
+        assert np.linalg.norm(res["mu"] - mu) <= 1e-9 * np.linalg.norm(mu)
+    assert np.linalg.norm(res["mu"] - true_mu) < 0.01       # and it recovers the motion
+    empty = np.zeros(5, capi.POSE_MEAS_DTYPE)
+    res, _ = f.pose_update(empty, estimator)
+    assert not res["mu"].any() and res["n_valid"] == 0      # no valid measurements -> null update (src/Tracker.cc:1423-1424)
+
+
 def test_fe_errors(capi):
     f = capi.FeHandle(640, 480)
     req = np.zeros(1, capi.PATCH_REQ_DTYPE)
