@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_linearize(BaDev d)
   const int cur = ctrl->cur;
   const double* __restrict__ pose = d.pose[cur];
   const double* __restrict__ ptv = d.pt[cur];
-  const double lambda = ctrl->lambda;
+  const double lambda = trial_lambda(d);
   const int nc = d.nc;
   double chi_acc = 0.0;
   int fail = 0;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) k_linearize(BaDev d)
   }
   const double tot = block_sum(chi_acc, red);
   if (threadIdx.x == 0) d.part[PART_CUR_CHI * MAX_PARTIALS + blockIdx.x] = tot;
-  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
 }
 
 __global__ void __launch_bounds__(256) k_schur_only(BaDev d)
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_schur_only(BaDev d)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double* Wsm = smem + (size_t)wid * d.max_slots * 36;
   double* Ysm = Wsm + (size_t)d.max_slots * 18;
-  const double lambda = d.ctrl->lambda;
+  const double lambda = trial_lambda(d);
   int fail = 0;
   for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
     if (d.pt_var[p] < 0) continue;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) k_schur_only(BaDev d)
     if (!schur_point(d, lane, K, d.slot_var + s0, V6, gp, lambda, Wsm, Ysm)) fail = 1;
     __syncwarp();
   }
-  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,9 +475,9 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
-  const int dst = apply ? (cur ^ 1) : (which_in < 0 ? cur : which_in);
+  const int dst = apply ? trial_buffer(d, cur) : (which_in < 0 ? cur : which_in);
   const double* __restrict__ pose = d.pose[dst];
-  const double lambda = ctrl->lambda;
+  const double lambda = trial_lambda(d);
   double chi_acc = 0, scale_acc = 0, sumsq_acc = 0;
   for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
     const int4 pi = d.pt_info[p];
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
         const double rr[3] = { gp[0] - t[0], gp[1] - t[1], gp[2] - t[2] };
         double dp[3];
         m3_vec(Vi, rr, dp);
-        if (!ctrl->solve_ok) { dp[0] = dp[1] = dp[2] = 0.0; }
+        if (!ctrl->solve_ok[d.cand]) { dp[0] = dp[1] = dp[2] = 0.0; }
         point_oplus(po, dp, pnew);
         if (lane == 0) {
 #pragma unroll
@@ -679,58 +679,77 @@ __global__ void k_lambda_apply(BaDev d)
 
 // ---------------------------------------------------------------------------------------------
 // k_lm_control: [3P] OptimizationAlgorithmLevenberg::solve trial bookkeeping + post-iteration actions.
-// red_in != nullptr: sums already reduced (multi-GPU); else reduce the per-block partials here.
+// n_cand speculative candidates were evaluated concurrently (candidate c used lambda after c rejections); they are
+// consumed strictly in g2o's order, so the accepted step and the lambda/ni sequence are those of the sequential
+// algorithm.  red_in != nullptr: sums already reduced (multi-GPU, single candidate); else reduce partials here.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lm_control(BaDev d, int n_part_lin, int n_part_bs, const double* red_in, int first_trial)
+__global__ void __launch_bounds__(256) k_lm_control(BaDev d, const double* part1, int n_cand, int n_part_lin, int n_part_bs,
+                                                   const double* red_in, int first_trial)
 {
   __shared__ double red[32];
-  double cur_chi = 0, tmp_chi = 0, sc = 0, sq = 0;
+  __shared__ double s_sum[2][4];
   if (red_in) {
-    cur_chi = red_in[0]; tmp_chi = red_in[1]; sc = red_in[2]; sq = red_in[3];
+    if (threadIdx.x == 0) { s_sum[0][0] = red_in[0]; s_sum[0][1] = red_in[1]; s_sum[0][2] = red_in[2]; s_sum[0][3] = red_in[3]; }
   } else {
-    double a = 0, b = 0, c = 0, e = 0;
+    double a = 0;
     for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
-    for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
-      b += d.part[PART_TMP_CHI * MAX_PARTIALS + i];
-      c += d.part[PART_SCALE * MAX_PARTIALS + i];
-      e += d.part[PART_SUMSQ * MAX_PARTIALS + i];
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) s_sum[0][0] = a;
+    for (int cnd = 0; cnd < n_cand; cnd++) {
+      const double* part = cnd == 0 ? d.part : part1;
+      double b = 0, c = 0, e = 0;
+      for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
+        b += part[PART_TMP_CHI * MAX_PARTIALS + i];
+        c += part[PART_SCALE * MAX_PARTIALS + i];
+        e += part[PART_SUMSQ * MAX_PARTIALS + i];
+      }
+      b = block_sum(b, red); c = block_sum(c, red); e = block_sum(e, red);
+      if (threadIdx.x == 0) { s_sum[cnd][1] = b; s_sum[cnd][2] = c; s_sum[cnd][3] = e; }
     }
-    cur_chi = block_sum(a, red); tmp_chi = block_sum(b, red); sc = block_sum(c, red); sq = block_sum(e, red);
   }
+  __syncthreads();
   if (threadIdx.x != 0) return;
   BaCtrl* c = d.ctrl;
-  if (first_trial) { c->current_chi = cur_chi; c->lin_chi = cur_chi; }
-  const double temp_raw = tmp_chi;
-  double temp_chi = temp_raw;
-  if (!c->solve_ok) temp_chi = 1.7976931348623157e308;
-  c->temp_chi = temp_raw;
-  double rho = c->current_chi - temp_chi;
-  double scale = c->scale + sc;
-  scale += 1e-3;
-  rho /= scale;
-  const double sumsq = c->sumsq + sq;
-  if (rho > 0 && isfinite(temp_chi)) {
-    const double t = 2 * rho - 1;
-    double alpha = 1. - t * t * t;
-    alpha = fmin(alpha, 2. / 3.);
-    const double sf = fmax(1. / 3., alpha);
-    c->lambda *= sf;
-    c->ni = 2;
-    c->current_chi = temp_chi;
-    c->cur ^= 1;
-    c->accepted = 1;
-  } else {
-    c->lambda *= c->ni;
-    c->ni *= 2;
-    c->accepted = 0;
+  if (first_trial) { c->current_chi = s_sum[0][0]; c->lin_chi = s_sum[0][0]; }
+  const int cur0 = c->cur;
+  bool again = true;
+  double temp_raw = 0, sumsq = 0;
+  int used = 0;
+  for (int cnd = 0; cnd < n_cand && again; cnd++) {
+    used++;
+    temp_raw = s_sum[cnd][1];
+    double temp_chi = temp_raw;
+    if (!c->solve_ok[cnd]) temp_chi = 1.7976931348623157e308;
+    c->temp_chi = temp_raw;
+    double rho = c->current_chi - temp_chi;
+    double scale = c->scale[cnd] + s_sum[cnd][2];
+    scale += 1e-3;
+    rho /= scale;
+    sumsq = c->sumsq[cnd] + s_sum[cnd][3];
+    if (rho > 0 && isfinite(temp_chi)) {
+      const double t = 2 * rho - 1;
+      double alpha = 1. - t * t * t;
+      alpha = fmin(alpha, 2. / 3.);
+      const double sf = fmax(1. / 3., alpha);
+      c->lambda *= sf;          // for candidate 1 c->lambda was already advanced by the rejection of candidate 0
+      c->ni = 2;
+      c->current_chi = temp_chi;
+      c->cur = (cur0 + 1 + cnd) % 3;
+      c->accepted = 1;
+    } else {
+      c->lambda *= c->ni;
+      c->ni *= 2;
+      c->accepted = 0;
+    }
+    c->rho = rho;
+    c->qmax++;
+    again = (rho < 0) && (c->qmax < c->max_trials);
+    if (!again && (c->qmax == c->max_trials || rho == 0)) c->terminate = 1;
   }
-  c->rho = rho;
-  c->qmax++;
-  c->solve_ok = 1;
-  const bool again = (rho < 0) && (c->qmax < c->max_trials);
+  c->cand_used = used;
+  c->solve_ok[0] = 1; c->solve_ok[1] = 1;
   c->stop_trials = again ? 0 : 1;
   if (!again) {
-    if (c->qmax == c->max_trials || rho == 0) c->terminate = 1;
     c->iter++;
     // CheckConvergedUpdateMagAction (src/ChainBundle.cc:1009-1047)
     const double rms = sqrt(sumsq / c->dim);
@@ -792,7 +811,7 @@ __global__ void k_debug_jacobians(BaDev d, double* out)
 // gathers the full update vector (movable poses then movable points) for mcp_ba_lm_step
 __global__ void k_gather_delta(BaDev d, double* out)
 {
-  const double lambda = d.ctrl->lambda;
+  const double lambda = trial_lambda(d);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int i = tid; i < d.nc; i += nt) out[i] = d.dc[i];
   for (int p = tid; p < d.n_pt; p += nt) {
@@ -856,9 +875,9 @@ int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
 void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }
 void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
-void launch_lm_control(const BaDev& d, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
+void launch_lm_control(const BaDev& d, const double* part1, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
 {
-  k_lm_control<<<1, 256, 0, s>>>(d, n_lin, n_bs, red_in, first_trial);
+  k_lm_control<<<1, 256, 0, s>>>(d, part1, n_cand, n_lin, n_bs, red_in, first_trial);
 }
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s)
 {

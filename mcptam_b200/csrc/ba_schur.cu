@@ -55,7 +55,7 @@ __global__ void k_pair_fill(BaDev d, int* __restrict__ cursor, int2* __restrict_
 // one thread per (point, slot): Y = W Vinv (18 doubles), z = Y g_p (6 doubles)
 __global__ void __launch_bounds__(256) k_schur_y(BaDev d)
 {
-  const double lambda = d.ctrl->lambda;
+  const double lambda = trial_lambda(d);
   const int s_lo = d.slot_lo, s_hi = d.slot_hi;
   int fail = 0;
   for (int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x; s < s_hi; s += gridDim.x * blockDim.x) {
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_schur_y(BaDev d)
 #pragma unroll
     for (int i = 0; i < 12; i++) y2[i] = make_double2(y[2 * i], y[2 * i + 1]);
   }
-  if (fail) atomicExch(&d.ctrl->solve_ok, 0);
+  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
 }
 
 // One warp per work item {block row a, block col b, begin, end}.  Incidences are processed in groups of G:

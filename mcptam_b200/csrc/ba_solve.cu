@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;
   BaCtrl* ctrl = d.ctrl;
-  const double lambda = ctrl->lambda;
+  const double lambda = trial_lambda(d);
   double* Lt = d.L;
   double* Linv = d.Linv;
   int* ready = d.flags;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
       __syncthreads();
     }
     if (d.dbg && tid == 0) { unsigned long long t3; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3)); d.dbg[8 * (size_t)n_tasks] = (double)(t3 % 1000000000ull); }
-    const int ok = (ld_acquire(&ctr[2]) != epoch) && ctrl->solve_ok;
+    const int ok = (ld_acquire(&ctr[2]) != epoch) && ctrl->solve_ok[d.cand];
     double sc = 0, sq = 0;
     for (int e = tid; e < n; e += 256) {
       const double xi = ok ? xs[e] : 0.0;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
     if (tid == 0) {
       double a = 0, b = 0;
       for (int w = 0; w < 8; w++) { a += red[w]; b += red[8 + w]; }
-      ctrl->scale = a; ctrl->sumsq = b; ctrl->solve_ok = ok;
+      ctrl->scale[d.cand] = a; ctrl->sumsq[d.cand] = b; ctrl->solve_ok[d.cand] = ok;
     }
     __syncthreads();
     const int cur = ctrl->cur;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
         se3_mul(E, Tm, O);
         Tm = O;
       }
-      se3_store(d.pose[cur ^ 1] + 12 * (size_t)p, Tm);
+      se3_store(d.pose[trial_buffer(d, cur)] + 12 * (size_t)p, Tm);
     }
     // fall through to the next (failing) grab so that every CTA consumes exactly one id >= n_tasks
   }

@@ -17,7 +17,7 @@ struct BaCtrl {
   double lambda, ni;
   double sigma_sq_raw, sigma_sq_lim, sigma_lim;   // RobustKernelData (src/ChainBundle.cc:810-833)
   double current_chi, temp_chi;
-  double scale, sumsq;                            // computeScale(), sum x^2 of the last solve
+  double scale[2], sumsq[2];                      // computeScale(), sum x^2 of the last solve, per speculative candidate
   double max_diag;
   double last_chi2;                               // CheckConvergedResidualAction::_dLastChi2
   double rho;
@@ -29,7 +29,7 @@ struct BaCtrl {
   int stop_trials;    // trial loop of this outer iteration is over
   int terminate;      // solver returned Terminate (qmax hit / rho == 0)
   int qmax;           // trials in this outer iteration
-  int solve_ok;
+  int solve_ok[2];    // per candidate
   int iter;           // outer iterations completed in this Compute
   int conv_mag, conv_res;
   int total_trials;
@@ -39,7 +39,7 @@ struct BaCtrl {
   int n_outliers;
   int sel_n;          // number of values in the selection (global measurement count)
   int sel_rank;       // n/2
-  int pad_;
+  int cand_used;      // candidates consumed by the last k_lm_control
 };
 
 struct BaDev {
@@ -57,9 +57,10 @@ struct BaDev {
   const double* meas_info;       // [n_meas] 1/sqrt(dNoiseSigmaSquared)
   const int4* meas_a;            // [n_meas] {obs link0 pose id, obs link1 pose id | -1, camera, original index}
   const int4* meas_b;            // [n_meas] {obs var | -1 (no obs Jacobian), obs slot | -1, has_src_jac, point id}
-  double* pose[2];               // [n_pose*12]
-  double* pt[2];                 // [n_pt*3]
-  double* chi2[2];               // [n_meas] signed as EdgeChainMeas::chi2
+  double* pose[3];               // [n_pose*12]  accepted state + one trial buffer per speculative candidate
+  double* pt[3];                 // [n_pt*3]
+  double* chi2[3];               // [n_meas] signed as EdgeChainMeas::chi2
+  int cand, pad_cand;            // speculative candidate index of this launch (0: lambda, 1: lambda * ni)
   double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
   double* gp;                    // [n_pt*3]
   double* W;                     // [n_slots*18] 6x3 row-major
@@ -85,6 +86,10 @@ struct BaDev {
   int* outlier_flags;            // [n_meas] (sorted order)
   double* dbg;                   // optional debug output
 };
+
+// lambda of the LM trial this launch belongs to: candidate 1 is the trial g2o would run after rejecting candidate 0
+__device__ __forceinline__ double trial_lambda(const BaDev& d) { return d.cand ? d.ctrl->lambda * d.ctrl->ni : d.ctrl->lambda; }
+__device__ __forceinline__ int trial_buffer(const BaDev& d, int cur) { return (cur + 1 + d.cand) % 3; }
 
 enum PartialRow { PART_CUR_CHI = 0, PART_MAXDIAG = 1, PART_TMP_CHI = 2, PART_SCALE = 3, PART_SUMSQ = 4 };
 
