@@ -27,8 +27,7 @@ void set_last_error(const char* fmt, ...)
 }
 
 // launchers defined in ba_kernels.cu
-int launch_linearize(const BaDev& d, bool schur, int warps, size_t smem, cudaStream_t s);
-int launch_schur_only(const BaDev& d, int warps, size_t smem, cudaStream_t s);
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s);
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
@@ -39,7 +38,7 @@ size_t chol_tiles_doubles(int nc);
 size_t chol_inv_doubles(int nc);
 size_t chol_flag_ints(int nc);
 int chol_max_n();
-void launch_lm_control(const BaDev& d, const double* part1, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
+void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s);
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s);
@@ -83,17 +82,19 @@ struct McpBa {
   int lin_warps = 8;
   size_t lin_smem = 0;
   // device buffers (pooled)
-  DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
-      b_meas_a, b_meas_b, b_pose[3], b_pt[3], b_chi2[3], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
+  DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
+      b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
       b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt;
-  bool schur_scatter = false;
-  // speculative second LM candidate (lambda * ni) evaluated on a second stream
-  DevBuf b_acc1, b_dc1, b_L1, b_Linv1, b_cflags1, b_part1, b_Y1;
-  BaDev d1;
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_done1 = nullptr;
-  int chol_epoch1 = 0;
-  bool spec_enabled = true, spec_hint = true;
+  // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
+  struct Cand {
+    DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
+    BaDev d;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_done = nullptr;
+    int chol_epoch = 0;
+  } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
+  cudaEvent_t ev_ready = nullptr;
+  int n_spec = 3;                 // candidates per round (1 = no speculation)
   int spec_rounds = 0, spec_used = 0;
   int chol_epoch = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
@@ -147,10 +148,13 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   MCP_CUDA_CHECK(cudaGetDevice(&h->device));
   { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->n_sms = sms; }
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
-  MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done1, cudaEventDisableTiming));
-  { const char* e = getenv("MCP_BA_SPECULATE"); h->spec_enabled = !(e && e[0] == '0'); }
+  for (int q = 1; q < MAX_CAND; q++) {
+    MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cand[q].stream, cudaStreamNonBlocking));
+    MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->cand[q].ev_done, cudaEventDisableTiming));
+  }
+  // MCP_BA_SPECULATE = number of LM candidates evaluated per round (1 or 0: sequential trials)
+  { const char* e = getenv("MCP_BA_SPECULATE"); if (e && e[0]) { int v = atoi(e); h->n_spec = v < 1 ? 1 : (v > MAX_CAND ? MAX_CAND : v); } }
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev0));
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
   MCP_CUDA_CHECK(cudaMallocHost(&h->ctrl_host, sizeof(BaCtrl)));
@@ -166,19 +170,25 @@ int mcp_ba_destroy(McpBa* h)
   if (!h) return MCP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_meas_off, &h->b_pt_slot_off,
-                    &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_pose[0],
-                    &h->b_pose[1], &h->b_pose[2], &h->b_pt[0], &h->b_pt[1], &h->b_pt[2], &h->b_chi2[0], &h->b_chi2[1], &h->b_chi2[2], &h->b_acc1, &h->b_dc1, &h->b_L1, &h->b_Linv1, &h->b_cflags1, &h->b_part1, &h->b_Y1, &h->b_V, &h->b_gp, &h->b_W,
+  DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
+                    &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
                     &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt };
   for (DevBuf* b : all) b->release();
+  for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
+  for (int q = 1; q < MAX_CAND; q++) {
+    McpBa::Cand& cq = h->cand[q];
+    if (cq.stream) cudaStreamSynchronize(cq.stream);
+    DevBuf* cb[] = { &cq.b_acc, &cq.b_dc, &cq.b_L, &cq.b_Linv, &cq.b_cflags, &cq.b_part, &cq.b_Y };
+    for (DevBuf* b : cb) b->release();
+    if (cq.stream) cudaStreamDestroy(cq.stream);
+    if (cq.ev_done) cudaEventDestroy(cq.ev_done);
+  }
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
   if (h->flags_host) cudaFreeHost(h->flags_host);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-  if (h->ev_done1) cudaEventDestroy(h->ev_done1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MCP_OK;
@@ -334,15 +344,22 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     return MCP_ERR_UNSUPPORTED;
   }
   compute_partition(h, pt_meas_off, n_pt);
+  // visiting order of the per-point kernels: inside every rank's range, heaviest points first (stable)
+  std::vector<int> pt_order((size_t)std::max(n_pt, 1), 0);
+  for (int q = 0; q < n_pt; q++) pt_order[q] = q;
+  for (int r = 0; r < h->world; r++)
+    std::stable_sort(pt_order.begin() + h->part_pt[r], pt_order.begin() + h->part_pt[r + 1], [&](int a, int b) {
+      return pt_meas_off[a + 1] - pt_meas_off[a] > pt_meas_off[b + 1] - pt_meas_off[b];
+    });
 
   int rc;
 #define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
-  UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_meas_off, pt_meas_off);
+  UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_order, pt_order); UP(h->b_pt_meas_off, pt_meas_off);
   UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_slot_pt, slot_pt); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
   UP(h->b_meas_a, meas_a); UP(h->b_meas_b, meas_b);
 #undef UP
   const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)std::max(n_pt, 1);
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < N_STATE; k++) {
     if ((rc = upload(h, h->b_pose[k], pose_Rt, pose_bytes))) return rc;
     if ((rc = upload(h, h->b_pt[k], pt_xyz, sizeof(double) * 3 * (size_t)n_pt))) return rc;
     if ((rc = h->b_chi2[k].ensure(sizeof(double) * (size_t)std::max(n_meas, 1)))) return rc;
@@ -390,11 +407,11 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.n_slots = n_slots; d.max_slots = max_slots;
   d.p_lo = h->part_pt[h->rank]; d.p_hi = h->part_pt[h->rank + 1];
   d.m_lo = h->part_meas[h->rank]; d.m_hi = h->part_meas[h->rank + 1];
-  d.pose_var = h->b_pose_var.as<int>(); d.pt_info = h->b_pt_info.as<int4>(); d.pt_var = h->b_pt_var.as<int>();
+  d.pose_var = h->b_pose_var.as<int>(); d.pt_info = h->b_pt_info.as<int4>(); d.pt_var = h->b_pt_var.as<int>(); d.pt_order = h->b_pt_order.as<int>();
   d.pt_meas_off = h->b_pt_meas_off.as<int>(); d.pt_slot_off = h->b_pt_slot_off.as<int>(); d.slot_var = h->b_slot_var.as<int>();
   d.meas_xy = h->b_meas_xy.as<double2>(); d.meas_info = h->b_meas_info.as<double>();
   d.meas_a = h->b_meas_a.as<int4>(); d.meas_b = h->b_meas_b.as<int4>();
-  for (int k = 0; k < 3; k++) { d.pose[k] = h->b_pose[k].as<double>(); d.pt[k] = h->b_pt[k].as<double>(); d.chi2[k] = h->b_chi2[k].as<double>(); }
+  for (int k = 0; k < N_STATE; k++) { d.pose[k] = h->b_pose[k].as<double>(); d.pt[k] = h->b_pt[k].as<double>(); d.chi2[k] = h->b_chi2[k].as<double>(); }
   d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>(); d.Y = h->b_Y.as<double>();
   d.slot_pt = h->b_slot_pt.as<int>(); d.slot_lo = pt_slot_off[d.p_lo]; d.slot_hi = pt_slot_off[d.p_hi];
   double* acc = h->b_acc.as<double>();
@@ -405,25 +422,26 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();
   d.ctrl = h->b_ctrl.as<BaCtrl>(); d.outlier_flags = h->b_flags.as<int>();
 
-  {
+  for (int q = 1; q < MAX_CAND; q++) {
+    McpBa::Cand& cq = h->cand[q];
+    cq.d = d;
+    cq.d.cand = q;
+    cq.chol_epoch = 0;
+    if (q >= h->n_spec) continue;
     const size_t sm_doubles = h->acc_doubles - h->off_Sm;
-    if ((rc = h->b_acc1.ensure(sizeof(double) * sm_doubles))) return rc;
-    if ((rc = h->b_dc1.ensure(sizeof(double) * ncp))) return rc;
-    if ((rc = h->b_L1.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
-    if ((rc = h->b_Linv1.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
-    if ((rc = h->b_cflags1.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
-    if ((rc = h->b_part1.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
-    if ((rc = h->b_Y1.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_cflags1.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_dc1.p, 0, sizeof(double) * ncp, h->stream));
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_part1.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
-    h->chol_epoch1 = 0;
-    h->d1 = d;
-    h->d1.cand = 1;
-    h->d1.Sm = h->b_acc1.as<double>(); h->d1.rm = h->d1.Sm + (h->off_rm - h->off_Sm);
-    h->d1.dc = h->b_dc1.as<double>(); h->d1.L = h->b_L1.as<double>(); h->d1.Linv = h->b_Linv1.as<double>();
-    h->d1.flags = h->b_cflags1.as<int>(); h->d1.part = h->b_part1.as<double>(); h->d1.Y = h->b_Y1.as<double>();
-    h->spec_hint = true;
+    if ((rc = cq.b_acc.ensure(sizeof(double) * sm_doubles))) return rc;
+    if ((rc = cq.b_dc.ensure(sizeof(double) * ncp))) return rc;
+    if ((rc = cq.b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
+    if ((rc = cq.b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
+    if ((rc = cq.b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
+    if ((rc = cq.b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
+    if ((rc = cq.b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
+    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_dc.p, 0, sizeof(double) * ncp, h->stream));
+    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
+    cq.d.Sm = cq.b_acc.as<double>(); cq.d.rm = cq.d.Sm + (h->off_rm - h->off_Sm);
+    cq.d.dc = cq.b_dc.as<double>(); cq.d.L = cq.b_L.as<double>(); cq.d.Linv = cq.b_Linv.as<double>();
+    cq.d.flags = cq.b_cflags.as<int>(); cq.d.part = cq.b_part.as<double>(); cq.d.Y = cq.b_Y.as<double>();
   }
   BaCtrl& c = *h->ctrl_host;
   memset(&c, 0, sizeof(c));
@@ -434,13 +452,11 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   c.pct_limit = h->cfg.update_pct_limit; c.rms_limit = h->cfg.update_rms_limit;
   c.max_trials = h->cfg.max_trials_after_failure; c.use_robust = h->cfg.use_robust;
   c.dim = 6 * npv + 3 * nptv;
-  c.solve_ok[0] = 1; c.solve_ok[1] = 1;
+  for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1;
   c.sel_n = n_meas; c.sel_rank = n_meas / 2;
   MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
   {
     // co-visibility lists for the gather-based Schur reduction (ba_schur.cu), built on the device
-    const char* env = getenv("MCP_BA_SCHUR_SCATTER");
-    h->schur_scatter = env && env[0] == '1';
     const int n_pairs = npv * (npv + 1) / 2;
     if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
     MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 1), h->stream));
@@ -462,7 +478,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     if ((rc = upload(h, h->b_items, items.data(), sizeof(int4) * items.size()))) return rc;
     launch_pair_fill(d, h->b_paircnt.as<int>(), h->b_inc.as<int2>(), h->stream);
     d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items = (int)items.size();
-    h->d1.inc = d.inc; h->d1.items = d.items; h->d1.n_items = d.n_items;
+    for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.inc = d.inc; h->cand[q].d.items = d.items; h->cand[q].d.n_items = d.n_items; }
   }
   MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->outliers.clear();
@@ -538,7 +554,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
 
   if ((rc = sync_ctrl(h))) return rc;
   c.need_lambda_init = 1; c.user_lambda = user_lambda; c.iter = 0; c.conv_mag = 0; c.conv_res = 0; c.total_trials = 0;
-  c.terminate = 0; c.qmax = 0; c.solve_ok[0] = 1; c.solve_ok[1] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0;
+  c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0;
   if ((rc = push_ctrl(h))) return rc;
   h->outliers.clear();
 
@@ -576,7 +592,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
     }
     MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
-    { Prof p(h, C_LIN); n_lin = launch_linearize(d, false, h->lin_warps, h->lin_smem, s); }
+    { Prof p(h, C_LIN); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); }
     if (multi) {
       launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
       NCCL_CHECK(ncclAllReduce(acc, acc, h->off_Sm, ncclDouble, ncclSum, h->comm, s));
@@ -590,35 +606,37 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     bool first = true;
     const size_t sm_doubles = h->acc_doubles - h->off_Sm;
     for (;;) {
-      // speculate on the trial g2o would run after a rejection of this one (lambda * ni) when rejections are likely
-      const bool two = h->spec_enabled && !multi && !single_step && !h->profiling && h->spec_hint;
+      // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
+      // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
+      const int n_cand = (!multi && !single_step && !h->profiling) ? h->n_spec : 1;
       if (!first) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
-      if (two) {
-        cudaStream_t s2 = h->stream2;
-        MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
-        MCP_CUDA_CHECK(cudaStreamWaitEvent(s2, h->ev_ready, 0));
-        MCP_CUDA_CHECK(cudaMemsetAsync(h->d1.Sm, 0, sizeof(double) * sm_doubles, s2));
-        launch_schur_gather(h->d1, s2);
-        launch_chol_solve(h->d1, ++h->chol_epoch1, h->n_sms, s2);
-        launch_backsub_eval(h->d1, 1, -1, nullptr, s2);
-        MCP_CUDA_CHECK(cudaEventRecord(h->ev_done1, s2));
-        h->launches += 4; h->spec_rounds++;
-      }
+      CandParts parts;
+      for (int q = 0; q < MAX_CAND; q++) parts.p[q] = d.part;
+      if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
       { Prof p(h, C_SCHUR); launch_schur_gather(d, s); h->launches++; }
       if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
       { Prof p(h, C_SOLVE); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
       { Prof p(h, C_BACKSUB); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
+      for (int q = 1; q < n_cand; q++) {
+        McpBa::Cand& cq = h->cand[q];
+        parts.p[q] = cq.d.part;
+        MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
+        MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
+        launch_schur_gather(cq.d, cq.stream);
+        launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms, cq.stream);
+        launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream);
+        MCP_CUDA_CHECK(cudaEventRecord(cq.ev_done, cq.stream));
+        h->launches += 4; h->spec_rounds++;
+      }
       if (multi) {
         launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
         NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3, ncclDouble, ncclSum, h->comm, s));
       }
-      if (two) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_done1, 0));
-      { Prof p(h, C_CONTROL); launch_lm_control(d, h->d1.part, two ? 2 : 1, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
+      for (int q = 1; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->cand[q].ev_done, 0));
+      { Prof p(h, C_CONTROL); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
       if ((rc = sync_ctrl(h))) return rc;
-      if (two && c.cand_used > 1) h->spec_used++;
-      // next round: speculate if this round's leading candidate was rejected
-      h->spec_hint = !(c.accepted && c.cand_used == 1);
+      if (c.cand_used > 1) h->spec_used++;
       if (single_step) break;
       if (c.stop_trials) break;
       if (aborted()) {
@@ -762,7 +780,7 @@ int mcp_ba_set_state(McpBa* h, const double* pose_Rt, const double* pt_xyz)
   if (!h || !h->loaded) { set_last_error("mcp_ba_set_state: no problem loaded"); return MCP_ERR_STATE; }
   cudaSetDevice(h->device);
   const int cur = h->ctrl_host->cur;
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < N_STATE; k++) {
     if (pose_Rt) MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pose[k], pose_Rt, sizeof(double) * 12 * (size_t)h->d.n_pose, cudaMemcpyHostToDevice, h->stream));
     if (pt_xyz && (k == cur)) MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pt[k], pt_xyz, sizeof(double) * 3 * (size_t)h->d.n_pt, cudaMemcpyHostToDevice, h->stream));
   }
@@ -773,7 +791,7 @@ int mcp_ba_reset_state(McpBa* h)
 {
   if (!h || !h->loaded) { set_last_error("mcp_ba_reset_state: no problem loaded"); return MCP_ERR_STATE; }
   cudaSetDevice(h->device);
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < N_STATE; k++) {
     MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pose[k], h->b_pose0.p, sizeof(double) * 12 * (size_t)h->d.n_pose, cudaMemcpyDeviceToDevice, h->stream));
     MCP_CUDA_CHECK(cudaMemcpyAsync(h->d.pt[k], h->b_pt0.p, sizeof(double) * 3 * (size_t)h->d.n_pt, cudaMemcpyDeviceToDevice, h->stream));
   }

@@ -1,18 +1,19 @@
 // ba_kernels.cu — sm_100a kernels of the ChainBundle LM bundle adjuster.
 //
-//   k_linearize<SCHUR>  one warp per map point: per-measurement TaylorCamera reprojection, 2x6 / 2x3
+//   k_linearize         eight lanes per map point: per-measurement TaylorCamera reprojection, 2x6 / 2x3
 //                       Jacobians (reference src/ChainBundle.cc:376-397, 449-685), robust weights
-//                       (:871-897), per-point 3x3 / 6x3 blocks in shared memory, pose-pose blocks and the
-//                       per-point Schur complement accumulated into the dense reduced camera system.
-//   k_schur_only        re-does only the Schur reduction for a new lambda (LM re-trial).
-//   k_select_sigma      exact upper median of |chi2| (radix select) -> Huber / Tukey sigma^2
-//                       (include/mcptam/MEstimator.h:109-126,194-204; src/ChainBundle.cc:810-833).
+//                       (:871-897), per-point 3x3 / 6x3 blocks in shared memory, pose-pose blocks by fp64
+//                       atomics.  (The Schur reduction for each lambda lives in ba_schur.cu.)
+//   k_select_cluster /  exact upper median of |chi2| (radix select) -> Huber / Tukey sigma^2
+//   k_sel_pass          (include/mcptam/MEstimator.h:109-126,194-204; src/ChainBundle.cc:810-833).
 //   k_lambda_init       g2o computeLambdaInit: 1e-5 * max diagonal.
 //   k_solve             dense Cholesky of the damped reduced camera system + pose update (:82-86).
 //   k_backsub_eval      per point back-substitution, VertexRelPoint::oplusImpl (:237-281) and the trial
 //                       error evaluation.
 //   k_lm_control        accept / reject, lambda schedule, convergence actions (:1009-1118).
 #include "ba_types.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace mcp {
 
@@ -208,62 +209,45 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 32 double
 }
 
 // ---------------------------------------------------------------------------------------------
-// Schur reduction of one point (warp-cooperative).  Wsm/Ysm: K x 18 doubles in shared memory.
+// Work distribution of the per-point kernels: a map point has ~8 measurements on average, so a full warp per
+// point leaves three quarters of the lanes idle in the per-measurement geometry.  Each point gets a group of
+// LG = 8 lanes (four points per warp); points are visited through d.pt_order (sorted by measurement count,
+// heaviest first) so that the four groups of a warp run the same number of iterations and the block scheduler
+// sees the long units first.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool schur_point(const BaDev& d, int lane, int K, const int* __restrict__ svar,
-                                            const double* V6, const double* gp, double lambda, double* Wsm, double* Ysm)
+constexpr int LG = 8;            // lanes per map point
+constexpr int PPW = 32 / LG;     // points per warp
+
+__device__ __forceinline__ double group_sum(double v, unsigned gmask)
 {
-  double Vi[9];
-  const bool ok = inv3_sym(V6, lambda, Vi);
-  for (int i = lane; i < K * 18; i += 32) {
-    const int a6 = i / 3, c = i - a6 * 3;
-    const double* w = Wsm + a6 * 3;
-    Ysm[i] = w[0] * Vi[c] + w[1] * Vi[3 + c] + w[2] * Vi[6 + c];
-  }
-  __syncwarp();
-  const int nc = d.nc;
-  for (int i = lane; i < K * 6; i += 32) {
-    const int a = i / 6, r = i - a * 6;
-    const double* y = Ysm + i * 3;
-    atomicAdd(d.rm + 6 * svar[a] + r, y[0] * gp[0] + y[1] * gp[1] + y[2] * gp[2]);
-  }
-  for (int a = 0; a < K; a++) {
-    const int va = svar[a];
-    const double* Ya = Ysm + a * 18;
-    const int n = (K - a) * 36;
-    for (int i = lane; i < n; i += 32) {
-      const int bo = i / 36, rc = i - bo * 36;
-      const int r = rc / 6, c = rc - r * 6;
-      if (bo == 0 && c < r) continue;               // diagonal block: upper triangle only
-      const double* y = Ya + r * 3;
-      const double* w = Wsm + (a + bo) * 18 + c * 3;
-      atomicAdd(d.Sm + (size_t)(6 * va + r) * nc + 6 * svar[a + bo] + c, y[0] * w[0] + y[1] * w[1] + y[2] * w[2]);
-    }
-  }
-  return ok;
+#pragma unroll
+  for (int o = LG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_linearize
 // ---------------------------------------------------------------------------------------------
-template <bool DO_SCHUR>
 __global__ void __launch_bounds__(256) k_linearize(BaDev d)
 {
   extern __shared__ double smem[];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* Wsm = smem + (size_t)wid * d.max_slots * 36;
-  double* Ysm = Wsm + (size_t)d.max_slots * 18;
+  const int gl = lane & (LG - 1), grp = lane / LG;
+  const unsigned gmask = ((1u << LG) - 1u) << (grp * LG);
+  double* Wsm = smem + (size_t)(wid * PPW + grp) * d.max_slots * 18;
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
   const double* __restrict__ pose = d.pose[cur];
   const double* __restrict__ ptv = d.pt[cur];
-  const double lambda = trial_lambda(d);
   const int nc = d.nc;
+  const int n_local = d.p_hi - d.p_lo;
   double chi_acc = 0.0;
-  int fail = 0;
 
-  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
+  for (int u = blockIdx.x * nw + wid; u * PPW < n_local; u += gridDim.x * nw) {
+    const int idx = u * PPW + grp;
+    if (idx >= n_local) continue;
+    const int p = d.pt_order[d.p_lo + idx];
     const int4 pi = d.pt_info[p];
     const int pvar = d.pt_var[p];
     const double prel[3] = { ptv[3 * (size_t)p], ptv[3 * (size_t)p + 1], ptv[3 * (size_t)p + 2] };
@@ -272,111 +256,107 @@ __global__ void __launch_bounds__(256) k_linearize(BaDev d)
     double M[9];
     point_tangent(prel, M);
     const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
-    const int* __restrict__ svar = d.slot_var + s0;
-    for (int i = lane; i < K * 18; i += 32) Wsm[i] = 0.0;
-    __syncwarp();
+    for (int i = gl; i < K * 18; i += LG) Wsm[i] = 0.0;
+    __syncwarp(gmask);
 
     // sums over the measurements of this point
     double P3[6] = { 0, 0, 0, 0, 0, 0 }, t3[3] = { 0, 0, 0 };
     double Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 }, P2[6] = { 0, 0, 0, 0, 0, 0 }, t2[3] = { 0, 0, 0 };
     const int m0 = d.pt_meas_off[p], m1 = d.pt_meas_off[p + 1];
-    for (int mb = m0; mb < m1; mb += 32) {
-      const int m = mb + lane;
-      if (m < m1) {
-        const int4 ma = d.meas_a[m];
-        const int4 mbi = d.meas_b[m];
-        const double2 z = d.meas_xy[m];
-        const double info = d.meas_info[m];
-        MeasGeom g;
-        meas_geometry<true>(d, pose, c, ma, z, g);
-        double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
-        if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;             // src/ChainBundle.cc:413-414
-        double rho0, rho1;
-        robustify(ctrl, chi2, rho0, rho1);
-        chi_acc += rho0;
-        const double w = rho1 * info;
-        const double we0 = w * g.e[0], we1 = w * g.e[1];
-        if (pvar >= 0) {
-          // P3 += w A3^T A3 ; t3 += w A3^T e
-          P3[0] += w * (g.A3[0] * g.A3[0] + g.A3[3] * g.A3[3]);
-          P3[1] += w * (g.A3[0] * g.A3[1] + g.A3[3] * g.A3[4]);
-          P3[2] += w * (g.A3[0] * g.A3[2] + g.A3[3] * g.A3[5]);
-          P3[3] += w * (g.A3[1] * g.A3[1] + g.A3[4] * g.A3[4]);
-          P3[4] += w * (g.A3[1] * g.A3[2] + g.A3[4] * g.A3[5]);
-          P3[5] += w * (g.A3[2] * g.A3[2] + g.A3[5] * g.A3[5]);
+    for (int m = m0 + gl; m < m1; m += LG) {
+      const int4 ma = d.meas_a[m];
+      const int4 mbi = d.meas_b[m];
+      const double2 z = d.meas_xy[m];
+      const double info = d.meas_info[m];
+      MeasGeom g;
+      meas_geometry<true>(d, pose, c, ma, z, g);
+      double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
+      if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;             // src/ChainBundle.cc:413-414
+      double rho0, rho1;
+      robustify(ctrl, chi2, rho0, rho1);
+      chi_acc += rho0;
+      const double w = rho1 * info;
+      const double we0 = w * g.e[0], we1 = w * g.e[1];
+      if (pvar >= 0) {
+        // P3 += w A3^T A3 ; t3 += w A3^T e
+        P3[0] += w * (g.A3[0] * g.A3[0] + g.A3[3] * g.A3[3]);
+        P3[1] += w * (g.A3[0] * g.A3[1] + g.A3[3] * g.A3[4]);
+        P3[2] += w * (g.A3[0] * g.A3[2] + g.A3[3] * g.A3[5]);
+        P3[3] += w * (g.A3[1] * g.A3[1] + g.A3[4] * g.A3[4]);
+        P3[4] += w * (g.A3[1] * g.A3[2] + g.A3[4] * g.A3[5]);
+        P3[5] += w * (g.A3[2] * g.A3[2] + g.A3[5] * g.A3[5]);
 #pragma unroll
-          for (int k = 0; k < 3; k++) t3[k] += g.A3[k] * we0 + g.A3[3 + k] * we1;
-        }
-        const bool has_src = mbi.z != 0;
-        if (has_src) {
+        for (int k = 0; k < 3; k++) t3[k] += g.A3[k] * we0 + g.A3[3 + k] * we1;
+      }
+      const bool has_src = mbi.z != 0;
+      if (has_src) {
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            t2[r] += g.A2[r] * we0 + g.A2[3 + r] * we1;
-            if (pvar >= 0) {
-#pragma unroll
-              for (int k = 0; k < 3; k++) Q[r * 3 + k] += w * (g.A2[r] * g.A3[k] + g.A2[3 + r] * g.A3[3 + k]);
-            }
-          }
-          P2[0] += w * (g.A2[0] * g.A2[0] + g.A2[3] * g.A2[3]);
-          P2[1] += w * (g.A2[0] * g.A2[1] + g.A2[3] * g.A2[4]);
-          P2[2] += w * (g.A2[0] * g.A2[2] + g.A2[3] * g.A2[5]);
-          P2[3] += w * (g.A2[1] * g.A2[1] + g.A2[4] * g.A2[4]);
-          P2[4] += w * (g.A2[1] * g.A2[2] + g.A2[4] * g.A2[5]);
-          P2[5] += w * (g.A2[2] * g.A2[2] + g.A2[5] * g.A2[5]);
-        }
-        const int vo = mbi.x;
-        if (vo >= 0) {
-          double Jo[12];
-          pose_jac(g.A, g.q, -1.0, Jo);
-          // H0[vo,vo] upper triangle, gc[vo]
-#pragma unroll
-          for (int r = 0; r < 6; r++) {
-            atomicAdd(d.gc + 6 * vo + r, -(Jo[r] * we0 + Jo[6 + r] * we1));
-#pragma unroll
-            for (int cc = r; cc < 6; cc++)
-              atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vo + cc, w * (Jo[r] * Jo[cc] + Jo[6 + r] * Jo[6 + cc]));
-          }
+        for (int r = 0; r < 3; r++) {
+          t2[r] += g.A2[r] * we0 + g.A2[3 + r] * we1;
           if (pvar >= 0) {
-            // J_pt = -A3 * M ; W_obs = w Jo^T J_pt
-            double Jp[6];
 #pragma unroll
-            for (int r = 0; r < 2; r++)
+            for (int k = 0; k < 3; k++) Q[r * 3 + k] += w * (g.A2[r] * g.A3[k] + g.A2[3 + r] * g.A3[3 + k]);
+          }
+        }
+        P2[0] += w * (g.A2[0] * g.A2[0] + g.A2[3] * g.A2[3]);
+        P2[1] += w * (g.A2[0] * g.A2[1] + g.A2[3] * g.A2[4]);
+        P2[2] += w * (g.A2[0] * g.A2[2] + g.A2[3] * g.A2[5]);
+        P2[3] += w * (g.A2[1] * g.A2[1] + g.A2[4] * g.A2[4]);
+        P2[4] += w * (g.A2[1] * g.A2[2] + g.A2[4] * g.A2[5]);
+        P2[5] += w * (g.A2[2] * g.A2[2] + g.A2[5] * g.A2[5]);
+      }
+      const int vo = mbi.x;
+      if (vo >= 0) {
+        double Jo[12];
+        pose_jac(g.A, g.q, -1.0, Jo);
+        // H0[vo,vo] upper triangle, gc[vo]
 #pragma unroll
-              for (int k = 0; k < 3; k++) Jp[r * 3 + k] = -(g.A3[r * 3] * M[k] + g.A3[r * 3 + 1] * M[3 + k] + g.A3[r * 3 + 2] * M[6 + k]);
-            double* Wo = Wsm + mbi.y * 18;
+        for (int r = 0; r < 6; r++) {
+          atomicAdd(d.gc + 6 * vo + r, -(Jo[r] * we0 + Jo[6 + r] * we1));
+#pragma unroll
+          for (int cc = r; cc < 6; cc++)
+            atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vo + cc, w * (Jo[r] * Jo[cc] + Jo[6 + r] * Jo[6 + cc]));
+        }
+        if (pvar >= 0) {
+          // J_pt = -A3 * M ; W_obs = w Jo^T J_pt
+          double Jp[6];
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) Jp[r * 3 + k] = -(g.A3[r * 3] * M[k] + g.A3[r * 3 + 1] * M[3 + k] + g.A3[r * 3 + 2] * M[6 + k]);
+          double* Wo = Wsm + mbi.y * 18;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) atomicAdd(Wo + r * 3 + k, w * (Jo[r] * Jp[k] + Jo[6 + r] * Jp[3 + k]));
+        }
+        if (has_src) {
+          double Js[12];
+          pose_jac(g.A2, c.qs, 1.0, Js);
+          const int vs = pi.z;
+          if (vo < vs) {
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
-              for (int k = 0; k < 3; k++) atomicAdd(Wo + r * 3 + k, w * (Jo[r] * Jp[k] + Jo[6 + r] * Jp[3 + k]));
-          }
-          if (has_src) {
-            double Js[12];
-            pose_jac(g.A2, c.qs, 1.0, Js);
-            const int vs = pi.z;
-            if (vo < vs) {
+              for (int cc = 0; cc < 6; cc++)
+                atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vs + cc, w * (Jo[r] * Js[cc] + Jo[6 + r] * Js[6 + cc]));
+          } else {
 #pragma unroll
-              for (int r = 0; r < 6; r++)
+            for (int r = 0; r < 6; r++)
 #pragma unroll
-                for (int cc = 0; cc < 6; cc++)
-                  atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vs + cc, w * (Jo[r] * Js[cc] + Jo[6 + r] * Js[6 + cc]));
-            } else {
-#pragma unroll
-              for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int cc = 0; cc < 6; cc++)
-                  atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vo + cc, w * (Js[r] * Jo[cc] + Js[6 + r] * Jo[6 + cc]));
-            }
+              for (int cc = 0; cc < 6; cc++)
+                atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vo + cc, w * (Js[r] * Jo[cc] + Js[6 + r] * Jo[6 + cc]));
           }
         }
       }
     }
-    // warp-reduce the point sums (every lane ends up with the totals)
+    // group-reduce the point sums (every lane of the group ends up with the totals)
 #pragma unroll
-    for (int i = 0; i < 6; i++) { P3[i] = warp_sum(P3[i]); P2[i] = warp_sum(P2[i]); }
+    for (int i = 0; i < 6; i++) { P3[i] = group_sum(P3[i], gmask); P2[i] = group_sum(P2[i], gmask); }
 #pragma unroll
-    for (int i = 0; i < 3; i++) { t3[i] = warp_sum(t3[i]); t2[i] = warp_sum(t2[i]); }
+    for (int i = 0; i < 3; i++) { t3[i] = group_sum(t3[i], gmask); t2[i] = group_sum(t2[i], gmask); }
 #pragma unroll
-    for (int i = 0; i < 9; i++) Q[i] = warp_sum(Q[i]);
+    for (int i = 0; i < 9; i++) Q[i] = group_sum(Q[i], gmask);
 
     // point block: V = M^T P3 M, gp = M^T t3   (J_pt = -A3 M, b_p = -sum w J_pt^T e)
     double V6[6] = { 0, 0, 0, 0, 0, 0 }, gp[3] = { 0, 0, 0 };
@@ -400,69 +380,44 @@ __global__ void __launch_bounds__(256) k_linearize(BaDev d)
       const double q0 = c.qs[0], q1 = c.qs[1], q2 = c.qs[2];
       const double Gs[18] = { 1, 0, 0, 0, q2, -q1, 0, 1, 0, -q2, 0, q0, 0, 0, 1, q1, -q0, 0 };
       const double P[9] = { P2[0], P2[1], P2[2], P2[1], P2[3], P2[4], P2[2], P2[4], P2[5] };
-      if (lane < 21) {
-        // upper-triangle entry (r,cc) of the 6x6
-        int r = 0, k = lane;
-        while (k >= 6 - r) { k -= 6 - r; r++; }
-        const int cc = r + k;
-        double acc = 0;
+      for (int e = gl; e < 27; e += LG) {
+        if (e < 21) {
+          // upper-triangle entry (r,cc) of the 6x6
+          int r = 0, k = e;
+          while (k >= 6 - r) { k -= 6 - r; r++; }
+          const int cc = r + k;
+          double acc = 0;
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+          for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) acc += Gs[i * 6 + r] * P[i * 3 + j] * Gs[j * 6 + cc];
-        atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vs + cc, acc);
-      } else if (lane < 27) {
-        const int r = lane - 21;
-        atomicAdd(d.gc + 6 * vs + r, -(Gs[r] * t2[0] + Gs[6 + r] * t2[1] + Gs[12 + r] * t2[2]));
+            for (int j = 0; j < 3; j++) acc += Gs[i * 6 + r] * P[i * 3 + j] * Gs[j * 6 + cc];
+          atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vs + cc, acc);
+        } else {
+          const int r = e - 21;
+          atomicAdd(d.gc + 6 * vs + r, -(Gs[r] * t2[0] + Gs[6 + r] * t2[1] + Gs[12 + r] * t2[2]));
+        }
       }
-      __syncwarp();
-      if (pvar >= 0 && pi.w >= 0 && lane < 18) {
+      __syncwarp(gmask);
+      if (pvar >= 0 && pi.w >= 0) {
         double X[9];
         m3_mul(Q, M, X);
-        const int r = lane / 3, k = lane - r * 3;
-        Wsm[pi.w * 18 + lane] += -(Gs[r] * X[k] + Gs[6 + r] * X[3 + k] + Gs[12 + r] * X[6 + k]);
+        for (int e = gl; e < 18; e += LG) {
+          const int r = e / 3, k = e - r * 3;
+          Wsm[pi.w * 18 + e] += -(Gs[r] * X[k] + Gs[6 + r] * X[3 + k] + Gs[12 + r] * X[6 + k]);
+        }
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (pvar >= 0) {
       double* Wg = d.W + (size_t)s0 * 18;
-      for (int i = lane; i < K * 18; i += 32) Wg[i] = Wsm[i];
-      if (lane < 6) d.V[6 * (size_t)p + lane] = V6[lane];
-      if (lane < 3) d.gp[3 * (size_t)p + lane] = gp[lane];
-      if (DO_SCHUR) {
-        if (!schur_point(d, lane, K, svar, V6, gp, lambda, Wsm, Ysm)) fail = 1;
-      }
+      for (int i = gl; i < K * 18; i += LG) Wg[i] = Wsm[i];
+      if (gl < 6) d.V[6 * (size_t)p + gl] = V6[gl];
+      if (gl < 3) d.gp[3 * (size_t)p + gl] = gp[gl];
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
   const double tot = block_sum(chi_acc, red);
   if (threadIdx.x == 0) d.part[PART_CUR_CHI * MAX_PARTIALS + blockIdx.x] = tot;
-  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
-}
-
-__global__ void __launch_bounds__(256) k_schur_only(BaDev d)
-{
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* Wsm = smem + (size_t)wid * d.max_slots * 36;
-  double* Ysm = Wsm + (size_t)d.max_slots * 18;
-  const double lambda = trial_lambda(d);
-  int fail = 0;
-  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
-    if (d.pt_var[p] < 0) continue;
-    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
-    const double* Wg = d.W + (size_t)s0 * 18;
-    for (int i = lane; i < K * 18; i += 32) Wsm[i] = Wg[i];
-    double V6[6], gp[3];
-#pragma unroll
-    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
-#pragma unroll
-    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
-    __syncwarp();
-    if (!schur_point(d, lane, K, d.slot_var + s0, V6, gp, lambda, Wsm, Ysm)) fail = 1;
-    __syncwarp();
-  }
-  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -473,13 +428,19 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
 {
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int gl = lane & (LG - 1), grp = lane / LG;
+  const unsigned gmask = ((1u << LG) - 1u) << (grp * LG);
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
   const int dst = apply ? trial_buffer(d, cur) : (which_in < 0 ? cur : which_in);
   const double* __restrict__ pose = d.pose[dst];
   const double lambda = trial_lambda(d);
+  const int n_local = d.p_hi - d.p_lo;
   double chi_acc = 0, scale_acc = 0, sumsq_acc = 0;
-  for (int p = d.p_lo + blockIdx.x * nw + wid; p < d.p_hi; p += gridDim.x * nw) {
+  for (int u = blockIdx.x * nw + wid; u * PPW < n_local; u += gridDim.x * nw) {
+    const int idx = u * PPW + grp;
+    if (idx >= n_local) continue;
+    const int p = d.pt_order[d.p_lo + idx];
     const int4 pi = d.pt_info[p];
     const int pvar = d.pt_var[p];
     double pnew[3];
@@ -491,12 +452,12 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
         const double* Wg = d.W + (size_t)s0 * 18;
         const int* svar = d.slot_var + s0;
         double t[3] = { 0, 0, 0 };
-        for (int i = lane; i < K * 18; i += 32) {
+        for (int i = gl; i < K * 18; i += LG) {
           const int a = i / 18, rem = i - a * 18, r = rem / 3, k = rem - r * 3;
           const double v = Wg[i] * d.dc[6 * svar[a] + r];
           t[0] += (k == 0) ? v : 0.0; t[1] += (k == 1) ? v : 0.0; t[2] += (k == 2) ? v : 0.0;
         }
-        t[0] = warp_sum(t[0]); t[1] = warp_sum(t[1]); t[2] = warp_sum(t[2]);
+        t[0] = group_sum(t[0], gmask); t[1] = group_sum(t[1], gmask); t[2] = group_sum(t[2], gmask);
         double V6[6], gp[3], Vi[9];
 #pragma unroll
         for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
@@ -508,7 +469,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
         m3_vec(Vi, rr, dp);
         if (!ctrl->solve_ok[d.cand]) { dp[0] = dp[1] = dp[2] = 0.0; }
         point_oplus(po, dp, pnew);
-        if (lane == 0) {
+        if (gl == 0) {
 #pragma unroll
           for (int i = 0; i < 3; i++) {
             scale_acc += dp[i] * (lambda * dp[i] + gp[i]);
@@ -516,7 +477,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
           }
         }
       } else { pnew[0] = po[0]; pnew[1] = po[1]; pnew[2] = po[2]; }
-      if (lane < 3) d.pt[dst][3 * (size_t)p + lane] = pnew[lane];
+      if (gl < 3) d.pt[dst][3 * (size_t)p + gl] = pnew[gl];
     } else {
       const double* pp = d.pt[dst] + 3 * (size_t)p;
       pnew[0] = pp[0]; pnew[1] = pp[1]; pnew[2] = pp[2];
@@ -524,7 +485,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
     PtCtx c;
     load_pt_ctx(d, pose, pi, pnew, c);
     const int m0 = d.pt_meas_off[p], m1 = d.pt_meas_off[p + 1];
-    for (int m = m0 + lane; m < m1; m += 32) {
+    for (int m = m0 + gl; m < m1; m += LG) {
       const int4 ma = d.meas_a[m];
       MeasGeom g;
       meas_geometry<false>(d, pose, c, ma, d.meas_xy[m], g);
@@ -634,6 +595,125 @@ __global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pas
   if (threadIdx.x == 0) d.sel_done[pass] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_select_cluster: the same exact radix select in ONE launch for n <= SELC_CAP values.  One thread-block cluster
+// of 8 CTAs; every thread keeps its <= 16 keys in registers for all six digits, each CTA histograms into its own
+// shared memory, and after a cluster barrier every CTA sums the eight histograms through distributed shared
+// memory and narrows (prefix, rank) redundantly -- no global-memory round trips between the passes.
+// ---------------------------------------------------------------------------------------------
+constexpr int SELC_CTAS = 8, SELC_THREADS = 1024, SELC_K = 16;
+constexpr int SELC_CAP = SELC_CTAS * SELC_THREADS * SELC_K;      // 131072
+
+__global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode)
+{
+  namespace cg = cooperative_groups;
+  __shared__ unsigned hist[2][SEL_BINS];
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank();
+  BaCtrl* ctrl = d.ctrl;
+  const int which = which_in < 0 ? ctrl->cur : which_in;
+  const double* __restrict__ v = d.chi2[which];
+  const int n = d.n_meas;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gtid = (int)crank * SELC_THREADS + tid;
+  unsigned long long key[SELC_K];
+#pragma unroll
+  for (int k = 0; k < SELC_K; k++) {
+    const int i = gtid + k * (SELC_CTAS * SELC_THREADS);
+    key[k] = (i < n) ? (unsigned long long)__double_as_longlong(fabs(v[i])) : ~0ull;   // ~0: never matches (sign bit)
+  }
+  unsigned long long prefix = 0;
+  unsigned rank = (unsigned)(n / 2);
+  for (int pass = 0; pass < SEL_PASSES; pass++) {
+    unsigned* h = hist[pass & 1];
+    const int shift = 63 - SEL_BITS * (pass + 1);       // 52, 41, 30, 19, 8, -3
+    for (int i = tid; i < SEL_BINS; i += SELC_THREADS) h[i] = 0;
+    __syncthreads();
+    // Digits cluster heavily (pass 0 is the exponent): combine a thread's keys that share its first digit, then
+    // aggregate equal digits across the warp, so that one shared-memory atomic serves many keys.
+    auto digit = [&](unsigned long long kk) -> unsigned {
+      return (shift >= 0) ? ((unsigned)(kk >> shift) & (SEL_BINS - 1)) : ((unsigned)(kk << (-shift)) & (SEL_BINS - 1));
+    };
+    unsigned mbits = 0;
+#pragma unroll
+    for (int k = 0; k < SELC_K; k++) {
+      const unsigned long long hi = (shift >= 0) ? (key[k] >> (shift + SEL_BITS)) : (key[k] >> (SEL_BITS + shift));
+      const bool match = (key[k] != ~0ull) && (pass == 0 || hi == prefix);
+      mbits |= match ? (1u << k) : 0u;
+    }
+    unsigned d0 = 0, n0 = 0;
+#pragma unroll
+    for (int k = SELC_K - 1; k >= 0; k--) if (mbits & (1u << k)) d0 = digit(key[k]);     // digit of the first matching key
+#pragma unroll
+    for (int k = 0; k < SELC_K; k++) if ((mbits & (1u << k)) && digit(key[k]) == d0) { n0++; mbits &= ~(1u << k); }
+    {
+      const unsigned act = __ballot_sync(0xffffffffu, n0 > 0);
+      if (n0 > 0) {
+        const unsigned peers = __match_any_sync(act, d0);
+        const unsigned tot = __reduce_add_sync(peers, n0);
+        if (lane == __ffs(peers) - 1) atomicAdd(&h[d0], tot);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SELC_K; k++) {
+      const bool indiv = (mbits >> k) & 1u;
+      const unsigned act = __ballot_sync(0xffffffffu, indiv);
+      if (act == 0) continue;
+      if (indiv) {
+        const unsigned dk = digit(key[k]);
+        const unsigned peers = __match_any_sync(act, dk);
+        if (lane == __ffs(peers) - 1) atomicAdd(&h[dk], (unsigned)__popc(peers));
+      }
+    }
+    cluster.sync();
+    // global counts of bins 2*tid, 2*tid+1
+    unsigned c0 = 0, c1 = 0;
+#pragma unroll
+    for (int r = 0; r < SELC_CTAS; r++) {
+      const unsigned* rh = cluster.map_shared_rank(h, r);
+      const uint2 t = *reinterpret_cast<const uint2*>(rh + 2 * tid);
+      c0 += t.x; c1 += t.y;
+    }
+    const unsigned tsum = c0 + c1;
+    unsigned incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int w = 0; w < wid; w++) woff += wsum[w];
+    const unsigned excl = woff + incl - tsum;
+    if (rank >= excl && rank < excl + tsum) {
+      const unsigned bin = (rank < excl + c0) ? 2 * tid : 2 * tid + 1;
+      const unsigned acc = (rank < excl + c0) ? excl : excl + c0;
+      s_prefix = (shift >= 0) ? ((prefix << SEL_BITS) | bin) : ((prefix << (SEL_BITS + shift)) | (bin >> (-shift)));
+      s_rank = rank - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix; rank = s_rank;
+  }
+  cluster.sync();                                       // nobody leaves while its histogram may still be read
+  if (crank == 0 && tid == 0) {
+    const double med = __longlong_as_double((long long)prefix);
+    const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
+    double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
+    if (mode == 0) {
+      s = 1.345 * s;
+      ctrl->sigma_sq_raw = s * s;
+      ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
+      ctrl->sigma_lim = sqrt(ctrl->sigma_sq_lim);
+    } else {
+      s = 4.6851 * s;
+      double t = s * s;
+      if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq;
+      ctrl->tukey_sigma_sq = t;
+    }
+  }
+}
+
 // Tukey outlier flags (src/ChainBundle.cc:1385-1398)
 __global__ void k_tukey_flags(BaDev d)
 {
@@ -683,11 +763,11 @@ __global__ void k_lambda_apply(BaDev d)
 // consumed strictly in g2o's order, so the accepted step and the lambda/ni sequence are those of the sequential
 // algorithm.  red_in != nullptr: sums already reduced (multi-GPU, single candidate); else reduce partials here.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lm_control(BaDev d, const double* part1, int n_cand, int n_part_lin, int n_part_bs,
+__global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, int n_cand, int n_part_lin, int n_part_bs,
                                                    const double* red_in, int first_trial)
 {
   __shared__ double red[32];
-  __shared__ double s_sum[2][4];
+  __shared__ double s_sum[MAX_CAND][4];
   if (red_in) {
     if (threadIdx.x == 0) { s_sum[0][0] = red_in[0]; s_sum[0][1] = red_in[1]; s_sum[0][2] = red_in[2]; s_sum[0][3] = red_in[3]; }
   } else {
@@ -696,7 +776,7 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, const double* part1
     a = block_sum(a, red);
     if (threadIdx.x == 0) s_sum[0][0] = a;
     for (int cnd = 0; cnd < n_cand; cnd++) {
-      const double* part = cnd == 0 ? d.part : part1;
+      const double* part = parts.p[cnd];
       double b = 0, c = 0, e = 0;
       for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
         b += part[PART_TMP_CHI * MAX_PARTIALS + i];
@@ -731,10 +811,10 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, const double* part1
       double alpha = 1. - t * t * t;
       alpha = fmin(alpha, 2. / 3.);
       const double sf = fmax(1. / 3., alpha);
-      c->lambda *= sf;          // for candidate 1 c->lambda was already advanced by the rejection of candidate 0
+      c->lambda *= sf;          // c->lambda was already advanced by the rejections of the earlier candidates
       c->ni = 2;
       c->current_chi = temp_chi;
-      c->cur = (cur0 + 1 + cnd) % 3;
+      c->cur = (cur0 + 1 + cnd) % N_STATE;
       c->accepted = 1;
     } else {
       c->lambda *= c->ni;
@@ -747,7 +827,7 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, const double* part1
     if (!again && (c->qmax == c->max_trials || rho == 0)) c->terminate = 1;
   }
   c->cand_used = used;
-  c->solve_ok[0] = 1; c->solve_ok[1] = 1;
+  for (int q = 0; q < MAX_CAND; q++) c->solve_ok[q] = 1;
   c->stop_trials = again ? 0 : 1;
   if (!again) {
     c->iter++;
@@ -838,24 +918,17 @@ __global__ void k_gather_delta(BaDev d, double* out)
 // ---------------------------------------------------------------------------------------------
 static int per_point_grid(const BaDev& d, int warps)
 {
-  const int npts = d.p_hi - d.p_lo;
-  int g = (npts + warps - 1) / warps;
+  const int units = (d.p_hi - d.p_lo + PPW - 1) / PPW;     // one warp per PPW points
+  int g = (units + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > MAX_PARTIALS) g = MAX_PARTIALS;
   return g;
 }
 
-int launch_linearize(const BaDev& d, bool schur, int warps, size_t smem, cudaStream_t s)
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s)
 {
   const int g = per_point_grid(d, warps);
-  if (schur) k_linearize<true><<<g, warps * 32, smem, s>>>(d);
-  else k_linearize<false><<<g, warps * 32, smem, s>>>(d);
-  return g;
-}
-int launch_schur_only(const BaDev& d, int warps, size_t smem, cudaStream_t s)
-{
-  const int g = per_point_grid(d, warps);
-  k_schur_only<<<g, warps * 32, smem, s>>>(d);
+  k_linearize<<<g, warps * 32, smem, s>>>(d);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)
@@ -866,6 +939,8 @@ int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, c
 }
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
 {
+  static const bool multi_launch = [] { const char* e = getenv("MCP_BA_SELECT_MULTI"); return e && e[0] == '1'; }();
+  if (d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, 0, s>>>(d, which, mode); return 1; }
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
   if (grid > 148) grid = 148;
@@ -875,9 +950,9 @@ int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
 void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }
 void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
-void launch_lm_control(const BaDev& d, const double* part1, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
+void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
 {
-  k_lm_control<<<1, 256, 0, s>>>(d, part1, n_cand, n_lin, n_bs, red_in, first_trial);
+  k_lm_control<<<1, 256, 0, s>>>(d, parts, n_cand, n_lin, n_bs, red_in, first_trial);
 }
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s)
 {
@@ -888,19 +963,13 @@ void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s) { k_gather
 
 int configure_kernels(int max_slots, int* warps_out, size_t* smem_out)
 {
-  // shared memory per warp: W and Y blocks, max_slots x 18 doubles each
-  const size_t per_warp = (size_t)max_slots * 36 * sizeof(double);
+  // shared memory per warp: the W blocks of its PPW points, max_slots x 18 doubles each
+  const size_t per_warp = (size_t)max_slots * 18 * sizeof(double) * PPW;
   int warps = 8;
-  while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   const size_t smem = per_warp * warps;
   if (smem > 200 * 1024) return -1;
-  cudaError_t e;
-  e = cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-  if (e != cudaSuccess) return -2;
-  e = cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-  if (e != cudaSuccess) return -2;
-  e = cudaFuncSetAttribute(k_schur_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-  if (e != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) return -2;
   *warps_out = warps;
   *smem_out = smem;
   return 0;

@@ -295,6 +295,57 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
         acc[a][b] = v;
       }
     // ---- left-looking updates -----------------------------------------------------------------------
+    if (i == j && j > 0) {
+      // Diagonal tile: the critical path of the factorisation runs  potrf(j-1) -> L_{j,j-1} -> potrf(j).
+      // Instead of waiting for the separate (j, j-1) task to publish L_{j,j-1}, this CTA accumulates that
+      // tile as well and applies Linv_{j-1} itself, so the chain waits on inv_ready[j-1] only.
+      double acc2[2][2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int gr = TB * j + ty + 16 * a, gc_ = TB * (j - 1) + tx + 16 * b;
+          acc2[a][b] = (gr < n) ? d.H0[(size_t)gc_ * n + gr] - d.Sm[(size_t)gc_ * n + gr] : 0.0;
+        }
+      for (int k = 0; k < j - 1; k++) {
+        const size_t ta = tile_index(j, k), tb = tile_index(j - 1, k);
+        if (tid == 0) {
+          while (ld_acquire(&ready[ta]) != epoch) { }
+          while (ld_acquire(&ready[tb]) != epoch) { }
+        }
+        __syncthreads();
+        const double* ga = Lt + ta * (TB * TB);
+        const double* gb = Lt + tb * (TB * TB);
+        for (int e = tid; e < TB * TB; e += 256) {
+          const int r = e >> 5, c = e & 31;
+          As[r * TLD + c] = __ldcg(ga + e);
+          Bs[r * TLD + c] = __ldcg(gb + e);
+        }
+        __syncthreads();
+        tile_mm_sub(As, Bs, ty, tx, acc2);
+        tile_mm_sub(As, As, ty, tx, acc);
+        __syncthreads();
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = acc2[a][b];
+      if (tid == 0) { while (ld_acquire(&inv_ready[j - 1]) != epoch) { } }
+      __syncthreads();
+      const double* gi = Linv + (size_t)(j - 1) * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) Bs[(e >> 5) * TLD + (e & 31)] = __ldcg(gi + e);
+      __syncthreads();
+      double x[2][2] = { { 0, 0 }, { 0, 0 } };
+      tile_mm_sub(As, Bs, ty, tx, x);          // x = -(acc2 * Linv^T)
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = x[a][b];
+      __syncthreads();
+      tile_mm_sub(As, As, ty, tx, acc);        // sign cancels: (-X)(-X)^T
+      __syncthreads();
+    } else
     for (int k = 0; k < j; k++) {
       const size_t ta = tile_index(i, k), tb = tile_index(j, k);
       if (tid == 0) {
@@ -334,17 +385,12 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
       __syncthreads();
       double* gl = Lt + tile_index(j, j) * (TB * TB);
       double* gi = Linv + (size_t)j * (TB * TB);
-      for (int e = tid; e < TB * TB; e += 256) {
-        const int r = e >> 5, c = e & 31;
-        gl[e] = As[r * TLD + c];
-        gi[e] = Bs[r * TLD + c];
-      }
+      for (int e = tid; e < TB * TB; e += 256) gi[e] = Bs[(e >> 5) * TLD + (e & 31)];
       __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(&inv_ready[j], epoch);
-        st_release(&ready[tile_index(j, j)], epoch);
-      }
+      if (tid == 0) { __threadfence(); st_release(&inv_ready[j], epoch); }     // the critical consumer needs Linv only
+      for (int e = tid; e < TB * TB; e += 256) gl[e] = As[(e >> 5) * TLD + (e & 31)];
+      __syncthreads();
+      if (tid == 0) { __threadfence(); st_release(&ready[tile_index(j, j)], epoch); }
     } else {
       // ---- off-diagonal / rhs tile: X = acc * Linv_j^T ------------------------------------------------
       if (tid == 0) { while (ld_acquire(&inv_ready[j]) != epoch) { } }

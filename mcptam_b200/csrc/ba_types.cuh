@@ -9,6 +9,8 @@ constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;   // 2048
 constexpr int SEL_PASSES = 6;             // 6 x 11 bits >= 63 significant bits of |chi2|
 constexpr int MAX_PARTIALS = 4096;        // per-block partial sums (grid size cap for the per-point kernels)
+constexpr int MAX_CAND = 4;               // speculative LM candidates evaluated concurrently
+constexpr int N_STATE = MAX_CAND + 1;     // accepted state + one trial buffer per candidate
 
 // LM control block: lives in device memory, mirrored into pinned host memory after every trial.
 // Restates the state of g2o::OptimizationAlgorithmLevenberg + the ChainBundle actions
@@ -17,7 +19,7 @@ struct BaCtrl {
   double lambda, ni;
   double sigma_sq_raw, sigma_sq_lim, sigma_lim;   // RobustKernelData (src/ChainBundle.cc:810-833)
   double current_chi, temp_chi;
-  double scale[2], sumsq[2];                      // computeScale(), sum x^2 of the last solve, per speculative candidate
+  double scale[MAX_CAND], sumsq[MAX_CAND];                     // computeScale(), sum x^2 of the last solve, per speculative candidate
   double max_diag;
   double last_chi2;                               // CheckConvergedResidualAction::_dLastChi2
   double rho;
@@ -29,7 +31,7 @@ struct BaCtrl {
   int stop_trials;    // trial loop of this outer iteration is over
   int terminate;      // solver returned Terminate (qmax hit / rho == 0)
   int qmax;           // trials in this outer iteration
-  int solve_ok[2];    // per candidate
+  int solve_ok[MAX_CAND];    // per candidate
   int iter;           // outer iterations completed in this Compute
   int conv_mag, conv_res;
   int total_trials;
@@ -50,6 +52,7 @@ struct BaDev {
   const int* pose_var;           // [n_pose] variable index or -1
   const int4* pt_info;           // [n_pt] {src link0 pose id, src link1 pose id | -1, src var | -1, src slot | -1}
   const int* pt_var;             // [n_pt] point variable index or -1 (fixed)
+  const int* pt_order;           // [n_pt] visiting order: each rank's point range sorted by measurement count, heaviest first
   const int* pt_meas_off;        // [n_pt+1]
   const int* pt_slot_off;        // [n_pt+1]
   const int* slot_var;           // [n_slots] pose variable of each (point, slot), ascending within a point
@@ -57,10 +60,10 @@ struct BaDev {
   const double* meas_info;       // [n_meas] 1/sqrt(dNoiseSigmaSquared)
   const int4* meas_a;            // [n_meas] {obs link0 pose id, obs link1 pose id | -1, camera, original index}
   const int4* meas_b;            // [n_meas] {obs var | -1 (no obs Jacobian), obs slot | -1, has_src_jac, point id}
-  double* pose[3];               // [n_pose*12]  accepted state + one trial buffer per speculative candidate
-  double* pt[3];                 // [n_pt*3]
-  double* chi2[3];               // [n_meas] signed as EdgeChainMeas::chi2
-  int cand, pad_cand;            // speculative candidate index of this launch (0: lambda, 1: lambda * ni)
+  double* pose[N_STATE];              // [n_pose*12]  accepted state + one trial buffer per speculative candidate
+  double* pt[N_STATE];               // [n_pt*3]
+  double* chi2[N_STATE];              // [n_meas] signed as EdgeChainMeas::chi2
+  int cand, pad_cand;            // speculative candidate index of this launch (c: lambda after c rejections)
   double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
   double* gp;                    // [n_pt*3]
   double* W;                     // [n_slots*18] 6x3 row-major
@@ -87,9 +90,17 @@ struct BaDev {
   double* dbg;                   // optional debug output
 };
 
-// lambda of the LM trial this launch belongs to: candidate 1 is the trial g2o would run after rejecting candidate 0
-__device__ __forceinline__ double trial_lambda(const BaDev& d) { return d.cand ? d.ctrl->lambda * d.ctrl->ni : d.ctrl->lambda; }
-__device__ __forceinline__ int trial_buffer(const BaDev& d, int cur) { return (cur + 1 + d.cand) % 3; }
+// lambda of the LM trial this launch belongs to: candidate c is the trial g2o would run after rejecting candidates
+// 0..c-1 (each rejection: lambda *= ni, ni *= 2)
+__device__ __forceinline__ double trial_lambda(const BaDev& d)
+{
+  double l = d.ctrl->lambda, ni = d.ctrl->ni;
+  for (int c = 0; c < d.cand; c++) { l *= ni; ni *= 2; }
+  return l;
+}
+__device__ __forceinline__ int trial_buffer(const BaDev& d, int cur) { return (cur + 1 + d.cand) % N_STATE; }
+
+struct CandParts { const double* p[MAX_CAND]; };   // per-candidate partial-sum arrays handed to k_lm_control
 
 enum PartialRow { PART_CUR_CHI = 0, PART_MAXDIAG = 1, PART_TMP_CHI = 2, PART_SCALE = 3, PART_SUMSQ = 4 };
 
