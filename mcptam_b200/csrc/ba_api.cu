@@ -42,7 +42,8 @@ void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s);
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s);
-int configure_kernels(int max_slots, int* warps_out, size_t* smem_out);
+int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* smem_out);
+int stage_doubles_for(int n_pose, int n_cam);
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
@@ -339,7 +340,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     return MCP_ERR_UNSUPPORTED;
   }
   cudaSetDevice(h->device);
-  if (configure_kernels(max_slots, &h->lin_warps, &h->lin_smem) != 0) {
+  const int stage_doubles = stage_doubles_for(n_pose, n_cam);
+  if (configure_kernels(max_slots, stage_doubles, &h->lin_warps, &h->lin_smem) != 0) {
     set_last_error("mcp_ba_load: a point is observed from %d movable keyframes, more than the kernel supports", max_slots);
     return MCP_ERR_UNSUPPORTED;
   }
@@ -404,7 +406,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   memset(&d, 0, sizeof(d));
   d.cams = h->b_cams.as<DevCam>();
   d.n_pose = n_pose; d.n_pt = n_pt; d.n_meas = n_meas; d.n_pose_var = npv; d.n_pt_var = nptv; d.nc = nc;
-  d.n_slots = n_slots; d.max_slots = max_slots;
+  d.n_slots = n_slots; d.max_slots = max_slots; d.n_cam = n_cam; d.stage_doubles = stage_doubles;
   d.p_lo = h->part_pt[h->rank]; d.p_hi = h->part_pt[h->rank + 1];
   d.m_lo = h->part_meas[h->rank]; d.m_hi = h->part_meas[h->rank + 1];
   d.pose_var = h->b_pose_var.as<int>(); d.pt_info = h->b_pt_info.as<int4>(); d.pt_var = h->b_pt_var.as<int>(); d.pt_order = h->b_pt_order.as<int>();

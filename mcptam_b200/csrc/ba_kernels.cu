@@ -35,7 +35,7 @@ struct PtCtx {
   double prel[3];  // point in the source camera frame (the estimate)
 };
 
-__device__ __forceinline__ void load_pt_ctx(const BaDev& d, const double* __restrict__ pose, const int4 pi,
+__device__ __forceinline__ void load_pt_ctx(const BaDev& d, const double* pose, const int4 pi,
                                             const double* prel, PtCtx& c)
 {
   se3_load(pose + 12 * (size_t)pi.x, c.Bs);
@@ -118,7 +118,7 @@ struct MeasGeom {
 };
 
 template <bool WITH_JAC>
-__device__ __forceinline__ void meas_geometry(const BaDev& d, const double* __restrict__ pose, const PtCtx& c,
+__device__ __forceinline__ void meas_geometry(const DevCam* cams, const double* pose, const PtCtx& c,
                                               const int4 ma, const double2 z, MeasGeom& g)
 {
   Se3 Bm;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void meas_geometry(const BaDev& d, const double* __re
     for (int i = 0; i < 9; i++) RC[i] = (i % 4 == 0) ? 1.0 : 0.0;
   }
   double px[2], G[6];
-  cam_project(d.cams[ma.z], v, px, WITH_JAC ? G : nullptr);
+  cam_project(cams[ma.z], v, px, WITH_JAC ? G : nullptr);
   g.e[0] = z.x - px[0];
   g.e[1] = z.y - px[1];
   if (WITH_JAC) {
@@ -215,6 +215,22 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 32 double
 // heaviest first) so that the four groups of a warp run the same number of iterations and the block scheduler
 // sees the long units first.
 // ---------------------------------------------------------------------------------------------
+// The pose array and the camera models are read with data-dependent indices by every measurement; staged in shared
+// memory the dependent load costs ~30 cycles instead of an L2 round trip (the per-point kernels are latency bound).
+__device__ __forceinline__ void stage_pose_cams(const BaDev& d, const double* pose_g, double* sm, const double*& pose, const DevCam*& cams)
+{
+  if (d.stage_doubles == 0) { pose = pose_g; cams = d.cams; return; }
+  const int np = d.n_pose * 12, ncd = d.n_cam * (int)(sizeof(DevCam) / 8);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(sm);
+  const unsigned long long* pg = reinterpret_cast<const unsigned long long*>(pose_g);
+  const unsigned long long* cg = reinterpret_cast<const unsigned long long*>(d.cams);
+  for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = pg[i];
+  for (int i = threadIdx.x; i < ncd; i += blockDim.x) dst[np + i] = cg[i];
+  __syncthreads();
+  pose = sm;
+  cams = reinterpret_cast<const DevCam*>(sm + np);
+}
+
 constexpr int LG = 8;            // lanes per map point
 constexpr int PPW = 32 / LG;     // points per warp
 
@@ -228,17 +244,20 @@ __device__ __forceinline__ double group_sum(double v, unsigned gmask)
 // ---------------------------------------------------------------------------------------------
 // k_linearize
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_linearize(BaDev d)
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int gl = lane & (LG - 1), grp = lane / LG;
   const unsigned gmask = ((1u << LG) - 1u) << (grp * LG);
-  double* Wsm = smem + (size_t)(wid * PPW + grp) * d.max_slots * 18;
+  double* Wsm = smem + d.stage_doubles + (size_t)(wid * PPW + grp) * d.max_slots * 18;
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
-  const double* __restrict__ pose = d.pose[cur];
+  const double* pose;
+  const DevCam* cams;
+  stage_pose_cams(d, d.pose[cur], smem, pose, cams);
   const double* __restrict__ ptv = d.pt[cur];
   const int nc = d.nc;
   const int n_local = d.p_hi - d.p_lo;
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(256) k_linearize(BaDev d)
       const double2 z = d.meas_xy[m];
       const double info = d.meas_info[m];
       MeasGeom g;
-      meas_geometry<true>(d, pose, c, ma, z, g);
+      meas_geometry<true>(cams, pose, c, ma, z, g);
       double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
       if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;             // src/ChainBundle.cc:413-414
       double rho0, rho1;
@@ -433,7 +452,10 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
   const int dst = apply ? trial_buffer(d, cur) : (which_in < 0 ? cur : which_in);
-  const double* __restrict__ pose = d.pose[dst];
+  extern __shared__ __align__(16) double smem[];
+  const double* pose;
+  const DevCam* cams;
+  stage_pose_cams(d, d.pose[dst], smem, pose, cams);
   const double lambda = trial_lambda(d);
   const int n_local = d.p_hi - d.p_lo;
   double chi_acc = 0, scale_acc = 0, sumsq_acc = 0;
@@ -488,7 +510,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
     for (int m = m0 + gl; m < m1; m += LG) {
       const int4 ma = d.meas_a[m];
       MeasGeom g;
-      meas_geometry<false>(d, pose, c, ma, d.meas_xy[m], g);
+      meas_geometry<false>(cams, pose, c, ma, d.meas_xy[m], g);
       double chi2 = d.meas_info[m] * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
       if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;
       d.chi2[dst][m] = chi2;
@@ -604,13 +626,22 @@ __global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pas
 constexpr int SELC_CTAS = 8, SELC_THREADS = 1024, SELC_K = 16;
 constexpr int SELC_CAP = SELC_CTAS * SELC_THREADS * SELC_K;      // 131072
 
+constexpr int SELC_COPIES = 8;                                   // histogram replicas per CTA (lane & 7)
+constexpr size_t SELC_SMEM = sizeof(unsigned) * (size_t)(SELC_COPIES + 2) * SEL_BINS;
+
 __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode)
 {
   namespace cg = cooperative_groups;
-  __shared__ unsigned hist[2][SEL_BINS];
+  // The first digit is the exponent: a handful of hot bins.  Same-address shared-memory atomics serialise, so every
+  // CTA keeps SELC_COPIES replicas of the histogram (replica = lane & 7, interleaved so that replicas of one bin sit in
+  // different banks) and folds them into `red` before the cluster-wide sum.
+  extern __shared__ __align__(16) unsigned sel_smem[];
+  unsigned* copies = sel_smem;                                   // [SEL_BINS][SELC_COPIES]
+  unsigned* redh = sel_smem + SELC_COPIES * SEL_BINS;            // [2][SEL_BINS]
   __shared__ unsigned wsum[32];
   __shared__ unsigned long long s_prefix;
-  __shared__ unsigned s_rank;
+  __shared__ unsigned s_rank, s_count;
+  __shared__ int s_prefix_shift;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   BaCtrl* ctrl = d.ctrl;
@@ -619,6 +650,7 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   const int n = d.n_meas;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gtid = (int)crank * SELC_THREADS + tid;
+  const unsigned rep = lane & (SELC_COPIES - 1);
   unsigned long long key[SELC_K];
 #pragma unroll
   for (int k = 0; k < SELC_K; k++) {
@@ -627,45 +659,35 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   }
   unsigned long long prefix = 0;
   unsigned rank = (unsigned)(n / 2);
-  for (int pass = 0; pass < SEL_PASSES; pass++) {
-    unsigned* h = hist[pass & 1];
+  bool done = false;
+  for (int pass = 0; pass < SEL_PASSES && !done; pass++) {
+    unsigned* h = redh + (pass & 1) * SEL_BINS;
     const int shift = 63 - SEL_BITS * (pass + 1);       // 52, 41, 30, 19, 8, -3
-    for (int i = tid; i < SEL_BINS; i += SELC_THREADS) h[i] = 0;
-    __syncthreads();
-    // Digits cluster heavily (pass 0 is the exponent): combine a thread's keys that share its first digit, then
-    // aggregate equal digits across the warp, so that one shared-memory atomic serves many keys.
-    auto digit = [&](unsigned long long kk) -> unsigned {
-      return (shift >= 0) ? ((unsigned)(kk >> shift) & (SEL_BINS - 1)) : ((unsigned)(kk << (-shift)) & (SEL_BINS - 1));
-    };
-    unsigned mbits = 0;
+    if (pass == 0) {
+      // every key takes part and the digit is the exponent (hot bins): replicated histogram, folded afterwards
+      for (int i = tid; i < SELC_COPIES * SEL_BINS; i += SELC_THREADS) copies[i] = 0;
+      __syncthreads();
 #pragma unroll
-    for (int k = 0; k < SELC_K; k++) {
-      const unsigned long long hi = (shift >= 0) ? (key[k] >> (shift + SEL_BITS)) : (key[k] >> (SEL_BITS + shift));
-      const bool match = (key[k] != ~0ull) && (pass == 0 || hi == prefix);
-      mbits |= match ? (1u << k) : 0u;
-    }
-    unsigned d0 = 0, n0 = 0;
+      for (int k = 0; k < SELC_K; k++)
+        if (key[k] != ~0ull) atomicAdd(&copies[(unsigned)(key[k] >> 52) * SELC_COPIES + rep], 1u);
+      __syncthreads();
+      const uint4* cp = reinterpret_cast<const uint4*>(copies + (size_t)2 * tid * SELC_COPIES);
+      const uint4 a0 = cp[0], a1 = cp[1], b0 = cp[2], b1 = cp[3];
+      uint2 f;
+      f.x = a0.x + a0.y + a0.z + a0.w + a1.x + a1.y + a1.z + a1.w;
+      f.y = b0.x + b0.y + b0.z + b0.w + b1.x + b1.y + b1.z + b1.w;
+      *reinterpret_cast<uint2*>(h + 2 * tid) = f;
+    } else {
+      // later digits are mantissa bits (well spread) and only the keys under the current prefix take part
+      *reinterpret_cast<uint2*>(h + 2 * tid) = make_uint2(0u, 0u);
+      __syncthreads();
 #pragma unroll
-    for (int k = SELC_K - 1; k >= 0; k--) if (mbits & (1u << k)) d0 = digit(key[k]);     // digit of the first matching key
-#pragma unroll
-    for (int k = 0; k < SELC_K; k++) if ((mbits & (1u << k)) && digit(key[k]) == d0) { n0++; mbits &= ~(1u << k); }
-    {
-      const unsigned act = __ballot_sync(0xffffffffu, n0 > 0);
-      if (n0 > 0) {
-        const unsigned peers = __match_any_sync(act, d0);
-        const unsigned tot = __reduce_add_sync(peers, n0);
-        if (lane == __ffs(peers) - 1) atomicAdd(&h[d0], tot);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < SELC_K; k++) {
-      const bool indiv = (mbits >> k) & 1u;
-      const unsigned act = __ballot_sync(0xffffffffu, indiv);
-      if (act == 0) continue;
-      if (indiv) {
-        const unsigned dk = digit(key[k]);
-        const unsigned peers = __match_any_sync(act, dk);
-        if (lane == __ffs(peers) - 1) atomicAdd(&h[dk], (unsigned)__popc(peers));
+      for (int k = 0; k < SELC_K; k++) {
+        const unsigned long long hi = (shift >= 0) ? (key[k] >> (shift + SEL_BITS)) : (key[k] >> (SEL_BITS + shift));
+        if (hi == prefix) {
+          const unsigned dig = (shift >= 0) ? ((unsigned)(key[k] >> shift) & (SEL_BINS - 1)) : ((unsigned)(key[k] << (-shift)) & (SEL_BINS - 1));
+          atomicAdd(&h[dig], 1u);
+        }
       }
     }
     cluster.sync();
@@ -683,21 +705,40 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
     for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
-    unsigned woff = 0;
-    for (int w = 0; w < wid; w++) woff += wsum[w];
+    // exclusive offset of this warp: scan of the 32 warp totals by every warp
+    unsigned wv = wsum[lane], winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    const unsigned woff = __shfl_sync(0xffffffffu, winc - wv, wid);
     const unsigned excl = woff + incl - tsum;
     if (rank >= excl && rank < excl + tsum) {
-      const unsigned bin = (rank < excl + c0) ? 2 * tid : 2 * tid + 1;
-      const unsigned acc = (rank < excl + c0) ? excl : excl + c0;
+      const bool first = rank < excl + c0;
+      const unsigned bin = first ? 2 * tid : 2 * tid + 1;
+      const unsigned acc = first ? excl : excl + c0;
       s_prefix = (shift >= 0) ? ((prefix << SEL_BITS) | bin) : ((prefix << (SEL_BITS + shift)) | (bin >> (-shift)));
       s_rank = rank - acc;
+      s_count = first ? c0 : c1;
+      s_prefix_shift = shift;                              // key >> shift == prefix for the keys under it (shift >= 0 here when used)
     }
     __syncthreads();
     prefix = s_prefix; rank = s_rank;
+    done = (s_count == 1u) && (pass + 1 < SEL_PASSES);      // a single key is left under the prefix: it is the answer
+  }
+  // `prefix` holds the leading bits of the wanted key.  If the passes ran to the end it is the whole key; otherwise
+  // exactly one key in the cluster starts with it, and the thread that owns it finishes the job.
+  unsigned long long med_bits = prefix;
+  bool owner = (crank == 0 && tid == 0);
+  if (done) {
+    owner = false;
+#pragma unroll
+    for (int k = 0; k < SELC_K; k++) {
+      // number of prefix bits after p passes: 11p + 1 leading (sign) bit => compare key >> (63 - 11p) ... done by length
+      if (key[k] != ~0ull && (key[k] >> s_prefix_shift) == prefix) { owner = true; med_bits = key[k]; }
+    }
   }
   cluster.sync();                                       // nobody leaves while its histogram may still be read
-  if (crank == 0 && tid == 0) {
-    const double med = __longlong_as_double((long long)prefix);
+  if (owner) {
+    const double med = __longlong_as_double((long long)med_bits);
     const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
     double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
     if (mode == 0) {
@@ -874,7 +915,7 @@ __global__ void k_debug_jacobians(BaDev d, double* out)
     PtCtx c;
     load_pt_ctx(d, pose, pi, prel, c);
     MeasGeom g;
-    meas_geometry<true>(d, pose, c, ma, d.meas_xy[m], g);
+    meas_geometry<true>(d.cams, pose, c, ma, d.meas_xy[m], g);
     double* o = out + 30 * (size_t)ma.w;
     for (int i = 0; i < 30; i++) o[i] = 0;
     if (mbi.x >= 0) pose_jac(g.A, g.q, -1.0, o);
@@ -925,22 +966,37 @@ static int per_point_grid(const BaDev& d, int warps)
   return g;
 }
 
+// Register-allocation variants of k_linearize (the kernel is latency bound; fewer registers = more resident warps
+// but spills).  MCP_BA_LIN_VARIANT: 0 = 256 threads, 1 block/SM (no cap), 1 = 128 threads x 3 blocks/SM (<= 168 regs),
+// 2 = 256 threads x 2 blocks/SM (<= 128 regs).
+static int lin_variant()
+{
+  static const int v = [] { const char* e = getenv("MCP_BA_LIN_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
+  return v;
+}
 int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s)
 {
+  const size_t stage = sizeof(double) * d.stage_doubles;
+  if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
+    const int g = per_point_grid(d, 4);
+    k_linearize<128, 3><<<g, 128, smem / warps * 4 + stage, s>>>(d);
+    return g;
+  }
   const int g = per_point_grid(d, warps);
-  k_linearize<<<g, warps * 32, smem, s>>>(d);
+  if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) k_linearize<256, 2><<<g, 256, smem + stage, s>>>(d);
+  else k_linearize<256, 1><<<g, warps * 32, smem + stage, s>>>(d);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)
 {
   const int g = per_point_grid(d, 8);
-  k_backsub_eval<<<g, 256, 0, s>>>(d, apply, which, err_out);
+  k_backsub_eval<<<g, 256, sizeof(double) * d.stage_doubles, s>>>(d, apply, which, err_out);
   return g;
 }
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
 {
   static const bool multi_launch = [] { const char* e = getenv("MCP_BA_SELECT_MULTI"); return e && e[0] == '1'; }();
-  if (d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, 0, s>>>(d, which, mode); return 1; }
+  if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, SELC_SMEM, s>>>(d, which, mode); return 1; }
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
   if (grid > 148) grid = 148;
@@ -961,15 +1017,25 @@ void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cu
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s) { k_debug_jacobians<<<148, 128, 0, s>>>(d, out); }
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s) { k_gather_delta<<<148, 128, 0, s>>>(d, out); }
 
-int configure_kernels(int max_slots, int* warps_out, size_t* smem_out)
+int stage_doubles_for(int n_pose, int n_cam)
+{
+  const size_t n = (size_t)n_pose * 12 + (size_t)n_cam * (sizeof(DevCam) / 8);
+  return n * sizeof(double) <= 40 * 1024 ? (int)n : 0;
+}
+
+int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* smem_out)
 {
   // shared memory per warp: the W blocks of its PPW points, max_slots x 18 doubles each
   const size_t per_warp = (size_t)max_slots * 18 * sizeof(double) * PPW;
   int warps = 8;
-  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  const size_t stage = sizeof(double) * (size_t)stage_doubles;
+  while (warps > 1 && per_warp * warps + stage > 200 * 1024) warps >>= 1;
   const size_t smem = per_warp * warps;
-  if (smem > 200 * 1024) return -1;
-  if (cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) return -2;
+  if (smem + stage > 200 * 1024) return -1;
+  if (cudaFuncSetAttribute(k_select_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELC_SMEM) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_linearize<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_linearize<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_linearize<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(72 * 1024)) != cudaSuccess) return -2;
   *warps_out = warps;
   *smem_out = smem;
   return 0;

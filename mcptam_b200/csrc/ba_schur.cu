@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
     const int4 item = d.items[it];
     const bool diag = item.x == item.y;
     const int n_groups = (item.w - item.z + TG - 1) / TG;
-    double c0 = 0.0, c1 = 0.0, accz = 0.0;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, accz = 0.0;      // two accumulator pairs: halves the dependent DMMA chain
     // prologue: issue group 0 into buffer 0
     auto issue = [&](int grp, int buf) {
       const int g0 = item.z + grp * TG, ng = min(TG, item.w - g0);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
         for (int p = 0; p < 3; p++) {
           const double a = gvalid ? blk[offA[p]] : 0.0;
           const double b = gvalid ? blk[offB[p]] : 0.0;
-          dmma_m8n8k4(c0, c1, a, b);
+          if (m & 1) dmma_m8n8k4(e0, e1, a, b); else dmma_m8n8k4(c0, c1, a, b);
         }
       }
       if (diag && lane < 6) {
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
       }
       __syncwarp();
     }
+    c0 += e0; c1 += e1;
     // D fragment: row g, cols 2*kk, 2*kk+1
     if (g < 6) {
       double* base = d.Sm + (size_t)(6 * item.x + g) * nc + 6 * item.y;

@@ -431,32 +431,60 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
     // ======== last task retired: backward substitution, pose update, scalars (this CTA only) ============
     __threadfence();
     for (int k = T - 1; k >= 0; k--) {
-      // s[c] = sum_{i>k} sum_r L_ik[r][c] * x_i[r]
-      double part = 0.0;
       const int c = lane;
-      for (int ii = k + 1; ii < T; ii++) {
-        const double* g = Lt + tile_index(ii, k) * (TB * TB);
-#pragma unroll
-        for (int r = wid; r < TB; r += 8) part += __ldcg(g + r * TB + c) * xs[ii * TB + r];
-      }
       double* scratch = xs + 32 * TB;            // 64 doubles
+      // prefetch what does not depend on the x blocks still being formed: four rows of Linv_k and y_k
+      const double* gi = Linv + (size_t)k * (TB * TB);
+      double li[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) li[q] = __ldcg(gi + (wid * 4 + q) * TB + c);
+      const double yk = (wid == 0) ? __ldcg(Lt + tile_index(T, k) * (TB * TB) + c) : 0.0;   // row 0 of the rhs tile
+      // s[c] = sum_{i>k} sum_r L_ik[r][c] * x_i[r]   (rows split over the warps, loads batched four tiles deep)
+      double part = 0.0;
+      int ii = k + 1;
+      for (; ii + 3 < T; ii += 4) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const double* g = Lt + tile_index(ii + u, k) * (TB * TB);
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[u * 4 + q] = __ldcg(g + (wid + 8 * q) * TB + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) part += v[u * 4 + q] * xs[(ii + u) * TB + wid + 8 * q];
+      }
+      for (; ii < T; ii++) {
+        const double* g = Lt + tile_index(ii, k) * (TB * TB);
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = __ldcg(g + (wid + 8 * q) * TB + c);
+#pragma unroll
+        for (int q = 0; q < 4; q++) part += v[q] * xs[ii * TB + wid + 8 * q];
+      }
       __syncthreads();
       As[wid * TLD + c] = part;
       __syncthreads();
       if (wid == 0) {
-        double s = 0;
+        double sacc = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) s += As[w * TLD + c];
-        const double yk = __ldcg(Lt + tile_index(T, k) * (TB * TB) + c);   // row 0 of the rhs tile
-        scratch[c] = yk - s;
+        for (int w = 0; w < 8; w++) sacc += As[w * TLD + c];
+        scratch[c] = yk - sacc;
+      }
+      __syncthreads();
+      {
+        double p2 = 0;                             // (Linv^T t)[c], rows 4*wid .. 4*wid+3
+#pragma unroll
+        for (int q = 0; q < 4; q++) p2 += li[q] * scratch[wid * 4 + q];
+        Bs[wid * TLD + c] = p2;
       }
       __syncthreads();
       if (wid == 0) {
-        const double* gi = Linv + (size_t)k * (TB * TB);
-        double s = 0;
-#pragma unroll 8
-        for (int r = 0; r < TB; r++) s += __ldcg(gi + r * TB + c) * scratch[r];   // (Linv^T t)[c]
-        xs[k * TB + c] = s;
+        double sacc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) sacc += Bs[w * TLD + c];
+        xs[k * TB + c] = sacc;
       }
       __syncthreads();
     }

@@ -47,6 +47,7 @@ struct BaCtrl {
 struct BaDev {
   const DevCam* cams;
   int n_pose, n_pt, n_meas, n_pose_var, n_pt_var, nc, n_slots, max_slots;
+  int n_cam, stage_doubles;      // cameras; doubles of shared memory used to stage poses + cameras (0: read from global)
   int p_lo, p_hi;                // local point range (multi-GPU shard)
   int m_lo, m_hi;                // local measurement range (sorted order)
   const int* pose_var;           // [n_pose] variable index or -1

@@ -95,13 +95,13 @@ __device__ __forceinline__ void se3_mul(const Se3& a, const Se3& b, Se3& o)
   r.t[0] += a.t[0]; r.t[1] += a.t[1]; r.t[2] += a.t[2];
   o = r;
 }
-__device__ __forceinline__ void se3_load(const double* __restrict__ p, Se3& T)
+__device__ __forceinline__ void se3_load(const double* p, Se3& T)
 {
   // 12 doubles = 96 B, 16 B aligned: three double2 x2 loads
   const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    const double2 v = __ldg(q + i);
+    const double2 v = q[i];          // generic load: the pose array may be staged in shared memory
     if (2 * i < 9) T.R[2 * i] = v.x; else T.t[2 * i - 9] = v.x;
     if (2 * i + 1 < 9) T.R[2 * i + 1] = v.y; else T.t[2 * i + 1 - 9] = v.y;
   }
