@@ -44,13 +44,14 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, csv line)
+        self.windows = []        # [t0, t1] perf_counter intervals of the timed regions
 
     def start(self):
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -59,7 +60,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
@@ -70,7 +74,13 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        # keep the samples taken inside the timed regions (a sample describes the 25 ms before it arrived)
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.05 for a, b in self.windows)]
+        scope = "timed regions"
+        if len(inside) < 3:
+            inside, scope = [ln for _, ln in self.lines], "whole run (timed regions shorter than the sampling period)"
+        self.scope = scope
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -82,7 +92,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "scope": scope}
 
 
 def cpu_reference_run(prob, steps, warmup, lm_iters_cpu):
@@ -167,7 +177,7 @@ def bench_frontend(capi, synth, device, steps=20, warmup=3, n_cams=4, n_patches=
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lm-iters", type=int, default=10)
@@ -234,12 +244,12 @@ def main():
 
     # ---- resident-data arm: K timed steps, CUDA events on the handle's stream ------------------
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                            # nvidia-smi needs ~1 s to start: launched before the warm-up
     times, iters, launches = [], 0, 0
     for s in range(warmup + args.steps):
         if s == warmup:
             barrier()
-            if rank == 0:
-                sampler.start()
             t_wall0 = time.perf_counter()
         flush.fill_(s & 0xFF)                      # L2 flush between steps (outside the timed events)
         torch.cuda.synchronize()
@@ -255,7 +265,7 @@ def main():
             times.append(e0.elapsed_time(e1)); iters += rc; launches += st.kernel_launches
     barrier()
     wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.window(t_wall0, t_wall0 + wall)
     tot_ms = float(np.sum(times))
     if dist is not None:
         t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
@@ -277,6 +287,8 @@ def main():
     e2e_t, e2e_it = 0.0, 0
     for s in range(warmup + args.steps):
         barrier()
+        if s == warmup:
+            t_e2e0 = time.perf_counter()
         t = time.perf_counter()
         h2.load(prob)
         rc, st = h2.compute(args.lm_iters)
@@ -291,6 +303,8 @@ def main():
         if s >= warmup:
             e2e_t += dt; e2e_it += rc
     e2e_val = e2e_it / e2e_t
+    sampler.window(t_e2e0, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing of one profiled step (CUDA events around every launch) ----------------
     h.set_profiling(True)
