@@ -343,7 +343,10 @@ def main():
     if world > 1 and args.scale_config != "none":
         # BASELINE.json configs[3]: the 1000 KF / 100k-point map, points sharded over the ranks, next to the same map
         # on one GPU (rank 0 alone) measured in the same run
-        big = synth.make_ba_config(args.scale_config, seed=args.seed)
+        big = synth.make_ba_config(args.scale_config, seed=args.seed) if rank == 0 else None   # ~25 s of Python once per box,
+        dist.barrier()                                                                         # then served from the disk cache
+        if big is None:
+            big = synth.make_ba_config(args.scale_config, seed=args.seed)
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))

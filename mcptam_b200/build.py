@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+    link = [nvcc, "-arch=sm_100a", "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
     subprocess.check_call(link)
     return LIB
 

@@ -91,10 +91,11 @@ struct McpBa {
     DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
     BaDev d;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_done = nullptr;
+    cudaEvent_t ev_done = nullptr, ev_schur = nullptr;
     int chol_epoch = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
-  cudaEvent_t ev_ready = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_red = nullptr;
+  int n_spec_multi = 2;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
   int n_spec = 3;                 // candidates per round (1 = no speculation)
   int spec_rounds = 0, spec_used = 0;
   int chol_epoch = 0, n_sms = 148;
@@ -150,12 +151,15 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->n_sms = sms; }
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
   for (int q = 1; q < MAX_CAND; q++) {
     MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cand[q].stream, cudaStreamNonBlocking));
     MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->cand[q].ev_done, cudaEventDisableTiming));
+    MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->cand[q].ev_schur, cudaEventDisableTiming));
   }
   // MCP_BA_SPECULATE = number of LM candidates evaluated per round (1 or 0: sequential trials)
   { const char* e = getenv("MCP_BA_SPECULATE"); if (e && e[0]) { int v = atoi(e); h->n_spec = v < 1 ? 1 : (v > MAX_CAND ? MAX_CAND : v); } }
+  { const char* e = getenv("MCP_BA_SPECULATE_MULTI"); if (e && e[0]) { int v = atoi(e); h->n_spec_multi = v < 1 ? 1 : (v > MAX_CAND ? MAX_CAND : v); } }
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev0));
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
   MCP_CUDA_CHECK(cudaMallocHost(&h->ctrl_host, sizeof(BaCtrl)));
@@ -183,6 +187,7 @@ int mcp_ba_destroy(McpBa* h)
     for (DevBuf* b : cb) b->release();
     if (cq.stream) cudaStreamDestroy(cq.stream);
     if (cq.ev_done) cudaEventDestroy(cq.ev_done);
+    if (cq.ev_schur) cudaEventDestroy(cq.ev_schur);
   }
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
   if (h->flags_host) cudaFreeHost(h->flags_host);
@@ -190,6 +195,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_red) cudaEventDestroy(h->ev_red);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MCP_OK;
@@ -375,7 +381,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if ((rc = h->b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
   // accumulators: [H0 | gc | red(8) | Sm | rm]
   const size_t ncp = (size_t)std::max(nc, 1);
-  h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 8; h->off_rm = h->off_Sm + ncp * ncp;
+  h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 16; h->off_rm = h->off_Sm + ncp * ncp;
   h->acc_doubles = h->off_rm + ncp;
   if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
   if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
@@ -610,31 +616,52 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     for (;;) {
       // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
       // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
-      const int n_cand = (!multi && !single_step && !h->profiling) ? h->n_spec : 1;
+      const int n_cand = (single_step || h->profiling) ? 1 : (multi ? std::min(h->n_spec, h->n_spec_multi) : h->n_spec);
       if (!first) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
       CandParts parts;
       for (int q = 0; q < MAX_CAND; q++) parts.p[q] = d.part;
       if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
       { Prof p(h, C_SCHUR); launch_schur_gather(d, s); h->launches++; }
-      if (multi) NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
+      if (multi) {
+        // every candidate's reduced camera system goes through ONE grouped all-reduce (one NCCL launch) per round
+        for (int q = 1; q < n_cand; q++) {
+          McpBa::Cand& cq = h->cand[q];
+          MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
+          MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
+          launch_schur_gather(cq.d, cq.stream);
+          MCP_CUDA_CHECK(cudaEventRecord(cq.ev_schur, cq.stream));
+          MCP_CUDA_CHECK(cudaStreamWaitEvent(s, cq.ev_schur, 0));
+          h->launches += 2;
+        }
+        NCCL_CHECK(ncclGroupStart());
+        NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
+        for (int q = 1; q < n_cand; q++) NCCL_CHECK(ncclAllReduce(h->cand[q].d.Sm, h->cand[q].d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
+        NCCL_CHECK(ncclGroupEnd());
+        if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_red, s));
+      }
       { Prof p(h, C_SOLVE); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
       { Prof p(h, C_BACKSUB); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
       for (int q = 1; q < n_cand; q++) {
         McpBa::Cand& cq = h->cand[q];
         parts.p[q] = cq.d.part;
-        MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
-        MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
-        launch_schur_gather(cq.d, cq.stream);
+        if (multi) {
+          MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_red, 0));
+        } else {
+          MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
+          MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
+          launch_schur_gather(cq.d, cq.stream);
+          h->launches += 2;
+        }
         launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms, cq.stream);
         launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream);
+        h->launches += 2;
+        if (multi) { launch_reduce_partials(cq.d, 0, n_bs, red + 3 * q, cq.stream); h->launches++; }
         MCP_CUDA_CHECK(cudaEventRecord(cq.ev_done, cq.stream));
-        h->launches += 4; h->spec_rounds++;
+        h->spec_rounds++;
       }
-      if (multi) {
-        launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
-        NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3, ncclDouble, ncclSum, h->comm, s));
-      }
+      if (multi) { launch_reduce_partials(d, 0, n_bs, red, s); h->launches++; }
       for (int q = 1; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->cand[q].ev_done, 0));
+      if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand, ncclDouble, ncclSum, h->comm, s));
       { Prof p(h, C_CONTROL); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
       if ((rc = sync_ctrl(h))) return rc;

@@ -802,7 +802,7 @@ __global__ void k_lambda_apply(BaDev d)
 // k_lm_control: [3P] OptimizationAlgorithmLevenberg::solve trial bookkeeping + post-iteration actions.
 // n_cand speculative candidates were evaluated concurrently (candidate c used lambda after c rejections); they are
 // consumed strictly in g2o's order, so the accepted step and the lambda/ni sequence are those of the sequential
-// algorithm.  red_in != nullptr: sums already reduced (multi-GPU, single candidate); else reduce partials here.
+// algorithm.  red_in != nullptr: sums already reduced over the ranks (multi-GPU); else reduce partials here.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, int n_cand, int n_part_lin, int n_part_bs,
                                                    const double* red_in, int first_trial)
@@ -810,7 +810,11 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
   __shared__ double red[32];
   __shared__ double s_sum[MAX_CAND][4];
   if (red_in) {
-    if (threadIdx.x == 0) { s_sum[0][0] = red_in[0]; s_sum[0][1] = red_in[1]; s_sum[0][2] = red_in[2]; s_sum[0][3] = red_in[3]; }
+    // red_in = { cur_chi, (tmp_chi, scale, sumsq) per candidate }
+    if (threadIdx.x == 0) {
+      s_sum[0][0] = red_in[0];
+      for (int cnd = 0; cnd < n_cand; cnd++) { s_sum[cnd][1] = red_in[1 + 3 * cnd]; s_sum[cnd][2] = red_in[2 + 3 * cnd]; s_sum[cnd][3] = red_in[3 + 3 * cnd]; }
+    }
   } else {
     double a = 0;
     for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];

@@ -9,6 +9,10 @@ crosses the C ABI (include/mcptam_b200.h: McpTaylorCam).
 from __future__ import annotations
 
 import ctypes
+import bisect
+import hashlib
+import os
+import tempfile
 import dataclasses
 import math
 
@@ -282,6 +286,9 @@ def make_ba_problem(n_cam=1, n_mkf=20, n_pt=1000, seed=0, mean_track=8.0, outlie
     pt_rel_true = np.zeros((n_pt, 3))
     keep_pt = np.zeros(n_pt, bool)
     level_p = np.array([0.5, 0.25, 0.15, 0.1])
+    level_cdf = level_p.cumsum()
+    level_cdf /= level_cdf[-1]
+    level_cdf = level_cdf.tolist()
     Ls = np.maximum(2, np.rint(rng.gamma(4.0, mean_track / 4.0, n_pt)).astype(int))
     u_all = rng.random((n_pt, 4))
     for p in range(n_pt):
@@ -314,7 +321,7 @@ def make_ba_problem(n_cam=1, n_mkf=20, n_pt=1000, seed=0, mean_track=8.0, outlie
         pt_rel_true[p] = Rs[ms, cs] @ pts[p] + ts[ms, cs]
         for j, c in obs:
             m = int(mk_idx[p, j])
-            lvl = int(rng.choice(4, p=level_p))
+            lvl = bisect.bisect_right(level_cdf, rng.random())   # == rng.choice(4, p=level_p): same draw, same stream
             z = px_all[p, j, c].astype(np.float64) + rng.standard_normal(2) * pix_sigma * (1 << lvl)
             if rng.random() < outlier_frac and not (m == ms and c == cs):
                 z = px_all[p, j, c].astype(np.float64) + rng.uniform(-30, 30, 2)
@@ -361,10 +368,45 @@ BA_CONFIGS = {
 }
 
 
+_ARRAY_FIELDS = ("pose_Rt", "pose_fixed", "pt_xyz", "pt_chain", "pt_fixed", "meas_xy", "meas_chain", "meas_pt", "meas_noise",
+                 "meas_cam", "truth_pose_Rt", "truth_pt_xyz")
+
+
+def _cache_path(name, seed):
+    """The big maps take tens of seconds of per-point Python to generate; the arrays are cached on local disk
+    (keyed by this file's contents, so a generator change never serves stale data).  MCP_SYNTH_CACHE=0 disables."""
+    root = os.environ.get("MCP_SYNTH_CACHE", os.path.join(tempfile.gettempdir(), "mcptam_b200_synth"))
+    if root in ("", "0"):
+        return None
+    with open(__file__, "rb") as f:
+        tag = hashlib.sha1(f.read()).hexdigest()[:12]
+    return os.path.join(root, "%s_seed%d_%s.npz" % (name, seed, tag))
+
+
 def make_ba_config(name, seed=0, **kw) -> BaProblem:
     args = dict(BA_CONFIGS[name])
     args.update(kw)
-    return make_ba_problem(seed=seed, **args)
+    path = _cache_path(name, seed) if not kw and args["n_pt"] >= 5000 else None
+    if path and os.path.exists(path):
+        try:
+            z = np.load(path)
+            cams = []
+            for raw in z["cams_raw"]:
+                cams.append(TaylorCamStruct.from_buffer_copy(raw.tobytes()))
+            return BaProblem(cams=cams, n_mkf=int(z["n_mkf"]), **{k: np.ascontiguousarray(z[k]) for k in _ARRAY_FIELDS})
+        except Exception:
+            pass                                   # unreadable / partial file: regenerate
+    prob = make_ba_problem(seed=seed, **args)
+    if path:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            tmp = "%s.%d.tmp.npz" % (path, os.getpid())
+            raw = np.stack([np.frombuffer(bytes(c), np.uint8) for c in prob.cams])
+            np.savez(tmp, cams_raw=raw, n_mkf=prob.n_mkf, **{k: getattr(prob, k) for k in _ARRAY_FIELDS})
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return prob
 
 
 # ---------------------------------------------------------------------------------------------

@@ -18,7 +18,10 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    prob = synth.make_ba_config(cfg, seed=0)
+    prob = synth.make_ba_config(cfg, seed=0) if rank == 0 else None
+    dist.barrier()
+    if prob is None:
+        prob = synth.make_ba_config(cfg, seed=0)          # disk cache written by rank 0
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
