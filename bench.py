@@ -216,6 +216,7 @@ def main():
         print(json.dumps(line))
         return 0
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / debug lines must not share stdout with the JSON line
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")

@@ -231,6 +231,34 @@ int mcp_fe_shitomasi(McpFe* h, int32_t kf, int32_t level, int32_t n, const int32
 int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t level, int32_t n,
                           const int32_t* src_xy, const int32_t* start_xy, int32_t range, int32_t* pos_out,
                           int32_t* found);
+/* KeyFrame::MakeKeyFrame_Rest candidate generation (src/KeyFrame.cc:363-531) for the pyramid resident in `slot`:
+ * CVD::fast_nonmax at Level::nFastThresh, in_image_with_border(10), FAST or Shi-Tomasi scoring, "percent" (top
+ * fraction of the descending sort) or "thresh" selection, then the MiniPatch stable-point test against the oldest
+ * stored previous frame (Level::imagePrev[0] / vCornersPrev[0], here another resident slot).  Fills Level::vCandidates. */
+typedef struct McpCandidate {
+  int32_t x, y;                 /* Candidate::irLevelPos */
+  double score;                 /* Candidate::dSTScore */
+} McpCandidate;
+typedef struct McpRestConfig {
+  int32_t use_shi;              /* KeyFrame::ssCandidateType == "shi" (default "fast": 0) */
+  int32_t use_thresh;           /* KeyFrame::ssCandidateCriterion == "thresh" (default "percent": 0) */
+  double top_fraction;          /* KeyFrame::sdCandidateTopFraction (0.8) */
+  double thresh;                /* KeyFrame::sdCandidateThresh (70) */
+  int32_t nonmax_strict;        /* 0: libCVD nonmax_suppression (dropped only by a strictly higher neighbour, default);
+                                   1: nonmax_suppression_strict (dropped by a higher-or-equal neighbour) */
+  int32_t prev_slot;            /* resident slot holding imagePrev[0] / vCornersPrev[0]; -1: no history (no pruning) */
+  int32_t n_prev;               /* imagePrev.size(): the MiniPatch search range is 10 * n_prev */
+  int32_t pad_;
+} McpRestConfig;
+typedef struct McpRestLevelOut {
+  int32_t n_max;                /* vScoresAndMaxCorners.size() */
+  int32_t n_selected;           /* candidates before the stable-point test */
+  int32_t n_candidates;         /* vCandidates.size() */
+  int32_t cap;                  /* capacity of cand[] (entries beyond it are dropped) */
+  McpCandidate* cand;           /* host out, may be NULL */
+} McpRestLevelOut;
+void mcp_fe_default_rest_config(McpRestConfig* cfg);
+int mcp_fe_make_keyframe_rest(McpFe* h, int32_t slot, const McpRestConfig* cfg, McpRestLevelOut out[MCP_LEVELS]);
 /* Debug: FAST score map of one level (0 = no corner at b=5, else fast_corner_score_10). */
 int mcp_fe_debug_scores(McpFe* h, int32_t slot, int32_t level, uint8_t* out);
 /* FindPVS building block: TrackerData::Project + GetDerivsUnsafe (include/mcptam/TrackerData.h:102-129) and

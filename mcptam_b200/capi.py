@@ -271,6 +271,16 @@ class FeTiming(C.Structure):
                 ("ms_other", C.c_double), ("n_launches", C.c_int32), ("pad_", C.c_int32)]
 
 
+class RestConfig(C.Structure):
+    _fields_ = [("use_shi", C.c_int32), ("use_thresh", C.c_int32), ("top_fraction", C.c_double), ("thresh", C.c_double),
+                ("nonmax_strict", C.c_int32), ("prev_slot", C.c_int32), ("n_prev", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RestLevelOut(C.Structure):
+    _fields_ = [("n_max", C.c_int32), ("n_selected", C.c_int32), ("n_candidates", C.c_int32), ("cap", C.c_int32), ("cand", C.c_void_p)]
+
+
+CANDIDATE_DTYPE = np.dtype([("x", "i4"), ("y", "i4"), ("score", "f8")], align=True)
 PATCH_REQ_DTYPE = np.dtype([("src_kf", "i4"), ("src_level", "i4"), ("src_cx", "i4"), ("src_cy", "i4"), ("warp_inv", "f8", 4),
                             ("search_level", "i4"), ("pred_x", "i4"), ("pred_y", "i4"), ("range", "i4"), ("subpix_its", "i4"),
                             ("exhaustive", "i4")], align=True)
@@ -305,6 +315,9 @@ def _bind_fe(L):
     L.mcp_fe_pose_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     L.mcp_fe_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcp_fe_debug_scores.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.mcp_fe_default_rest_config.argtypes = [C.POINTER(RestConfig)]
+    L.mcp_fe_default_rest_config.restype = None
+    L.mcp_fe_make_keyframe_rest.argtypes = [C.c_void_p, C.c_int32, C.POINTER(RestConfig), C.c_void_p]
     _fe_bound = True
 
 
@@ -396,6 +409,25 @@ class FeHandle:
         found = np.zeros(len(src_xy), np.int32)
         check(self.L.mcp_fe_minipatch_find(self.h, kf_src, kf_dst, level, len(src_xy), _p(src_xy), _p(start_xy), rng, _p(pos), _p(found)))
         return pos, found
+
+    def make_keyframe_rest(self, slot, prev_slot=-1, n_prev=0, **cfg_kw):
+        """KeyFrame::MakeKeyFrame_Rest candidate generation for the pyramid in `slot`; returns 4 per-level dicts."""
+        cfg = RestConfig()
+        self.L.mcp_fe_default_rest_config(C.byref(cfg))
+        cfg.prev_slot, cfg.n_prev = prev_slot, n_prev
+        for k, v in cfg_kw.items():
+            setattr(cfg, k, v)
+        outs = (RestLevelOut * 4)()
+        cap = self.cfg.max_corners_per_level
+        keep = []
+        for l in range(4):
+            c = np.zeros(cap, CANDIDATE_DTYPE)
+            keep.append(c)
+            outs[l].cand = c.ctypes.data
+            outs[l].cap = cap
+        check(self.L.mcp_fe_make_keyframe_rest(self.h, slot, C.byref(cfg), C.cast(outs, C.c_void_p)))
+        return [{"n_max": outs[l].n_max, "n_selected": outs[l].n_selected, "n_candidates": outs[l].n_candidates,
+                 "cand": keep[l][:outs[l].n_candidates].copy()} for l in range(4)]
 
     def set_camera(self, cam):
         self._cam = cam

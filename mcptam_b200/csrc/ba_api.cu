@@ -95,7 +95,7 @@ struct McpBa {
     int chol_epoch = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
   cudaEvent_t ev_ready = nullptr, ev_red = nullptr;
-  int n_spec_multi = 2;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
+  int n_spec_multi = 3;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
   int n_spec = 3;                 // candidates per round (1 = no speculation)
   int spec_rounds = 0, spec_used = 0;
   int chol_epoch = 0, n_sms = 148;

@@ -181,6 +181,126 @@ __device__ __forceinline__ void potrf32_blocked(double* S, double* rinv, double*
   __syncthreads();
 }
 
+// 1/sqrt(d) for a validated pivot: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-20) + one cubic Newton step
+// y (1 + e/2 + 3e^2/8), e = 1 - d y^2  ->  relative error ~2^-58, branch free (rsqrt() carries special-case
+// branches that keep the compiler from interleaving the pivot chain with the column updates).
+__device__ __forceinline__ double fast_rsqrt(double d)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double dy = d * y;
+  const double e = fma(-dy, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+
+// Cholesky of the 32x32 tile in shared memory S (stride TLD) by the whole CTA (256 threads), four 8-column panels.
+// Warp 0 (lane = row) runs the pivot chain of a panel over ALL rows below the diagonal, so the panel of L leaves
+// the chain finished (no separate 8x8 inverse / triangular solve); the trailing update of the remaining columns is
+// a rank-8 update spread over all threads.  Two barriers per panel.  rinv[32]: reciprocal diagonal.
+template <bool FAST, int PW = 8>
+__device__ __forceinline__ void potrf32_panel(double* S, double* rinv, int tid, int* bad)
+{
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll 1
+  for (int b = 0; b < TB / PW; b++) {
+    const int o = PW * b;
+    if (wid == 0) {
+      double a[PW];
+#pragma unroll
+      for (int c = 0; c < PW; c++) a[c] = S[lane * TLD + o + c];
+      bool isbad = false;
+      double dj = __shfl_sync(0xffffffffu, a[0], o);
+      {
+        const bool ok = (dj > 1.0e-290) && (dj < 1.0e290);
+        isbad |= !ok;
+        dj = ok ? dj : 1.0;
+      }
+      double ri = FAST ? fast_rsqrt(dj) : rsqrt(dj);
+#pragma unroll
+      for (int jj = 0; jj < PW; jj++) {
+        a[jj] = (lane >= o + jj) ? a[jj] * ri : 0.0;          // rows above the diagonal: strict upper triangle := 0
+        if (lane == o + jj) rinv[o + jj] = ri;
+        double rn = 1.0;
+        if (jj + 1 < PW) {
+          const double v1 = __shfl_sync(0xffffffffu, a[jj], o + jj + 1);
+          a[jj + 1] = fma(-a[jj], v1, a[jj + 1]);
+          double dn = __shfl_sync(0xffffffffu, a[jj + 1], o + jj + 1);
+          const bool ok = (dn > 1.0e-290) && (dn < 1.0e290);
+          isbad |= !ok;
+          dn = ok ? dn : 1.0;
+          rn = FAST ? fast_rsqrt(dn) : rsqrt(dn);
+        }
+#pragma unroll
+        for (int c = jj + 2; c < PW; c++) {
+          const double v = __shfl_sync(0xffffffffu, a[jj], o + c);
+          a[c] = fma(-a[jj], v, a[c]);
+        }
+        ri = rn;
+      }
+      if (isbad && lane == 0) *bad = 1;
+#pragma unroll
+      for (int c = 0; c < PW; c++) S[lane * TLD + o + c] = a[c];
+    }
+    __syncthreads();
+    const int nrow = TB - PW - o;                       // rows / columns right of the panel
+    if (nrow > 0) {
+      // trailing update of the lower triangle: A[i][j] -= sum_k L[i][o+k] L[j][o+k]
+      for (int e = tid; e < nrow * nrow; e += 256) {
+        const int i = e / nrow, j = e - i * nrow;
+        if (j > i) continue;
+        const double* xi = S + (o + PW + i) * TLD + o;
+        const double* xj = S + (o + PW + j) * TLD + o;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < PW; k++) acc = fma(xi[k], xj[k], acc);
+        S[(o + PW + i) * TLD + o + PW + j] -= acc;
+      }
+      __syncthreads();
+    }
+  }
+  // rows < o of later panels were zeroed by the chain's own select; nothing else to clear
+}
+
+// Cholesky of the 32x32 tile by 8 warps: warp w owns columns 4w..4w+3, lane = row, the tile lives in registers.
+// Per pivot: the owning warp scales its column and posts it to shared memory, ONE barrier, every warp applies the
+// rank-1 update to its own (at most four) columns.  colbuf: 64 doubles (double buffered column).
+template <bool FAST>
+__device__ __forceinline__ void potrf32_cols(double* S, double* rinv, double* colbuf, int tid, int* bad)
+{
+  const int lane = tid & 31, wid = tid >> 5;
+  double a[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) a[q] = S[lane * TLD + 4 * wid + q];
+  bool isbad = false;
+#pragma unroll
+  for (int j = 0; j < TB; j++) {
+    const int ow = j >> 2, oq = j & 3;
+    double* cb = colbuf + 32 * (j & 1);
+    if (wid == ow) {
+      double dj = __shfl_sync(0xffffffffu, a[oq], j);
+      const bool ok = (dj > 1.0e-290) && (dj < 1.0e290);
+      isbad |= !ok;
+      dj = ok ? dj : 1.0;
+      const double ri = FAST ? fast_rsqrt(dj) : rsqrt(dj);
+      a[oq] = (lane >= j) ? a[oq] * ri : 0.0;
+      cb[lane] = a[oq];
+      if (lane == j) rinv[j] = ri;
+    }
+    __syncthreads();
+    if (wid >= ow) {
+      const double lr = cb[lane];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (4 * wid + q > j) a[q] = fma(-lr, cb[4 * wid + q], a[q]);
+    }
+  }
+  if (isbad && lane == 0) *bad = 1;
+#pragma unroll
+  for (int q = 0; q < 4; q++) S[lane * TLD + 4 * wid + q] = a[q];
+  __syncthreads();
+}
+
 // Inverse of the lower-triangular 32x32 factor L (shared, stride TLD) into X (shared, stride TLD), by
 // recursive 2x2 blocking: [A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1, C^-1] with 8x8 leaves.  256 threads.
 // rinv: reciprocals of the diagonal of L; tmp: >= 256 doubles of scratch.

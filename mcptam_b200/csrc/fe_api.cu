@@ -17,6 +17,9 @@ void fe_launch_pose_update(int n, const McpPoseMeas* meas, int estimator, double
 void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s);
 void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
                          int2* pos, int* found, cudaStream_t s);
+void fe_launch_rest_level(const FeKf& kf, const FeKf* prev, int level, int n_hint, int n_prev_corners, int adaptive, int strict, int use_shi,
+                          int use_thresh, double top_fraction, double thresh, int n_prev, int* flag, double* score, McpCandidate* cand,
+                          McpCandidate* cand_out, int2* cand_xy, int2* pos1, int2* pos2, int* f1, int* f2, int* ctr, cudaStream_t s);
 }  // namespace mcp
 
 using namespace mcp;
@@ -48,6 +51,7 @@ struct McpFe {
   DevCam cam; bool has_cam = false;
   double* proj_in = nullptr; McpProjRes* proj_out = nullptr; size_t proj_cap = 0;
   void* pu_buf = nullptr; size_t pu_cap = 0;
+  uint8_t* rest_buf = nullptr; void* rest_host = nullptr;   // MakeKeyFrame_Rest scratch (lazy)
   McpFeTiming timing;
   int lw[MCP_LEVELS], lh[MCP_LEVELS], lp[MCP_LEVELS];
 };
@@ -183,6 +187,8 @@ int mcp_fe_destroy(McpFe* h)
   if (h->proj_in) cudaFree(h->proj_in);
   if (h->proj_out) cudaFree(h->proj_out);
   if (h->pu_buf) cudaFree(h->pu_buf);
+  if (h->rest_buf) cudaFree(h->rest_buf);
+  if (h->rest_host) cudaFreeHost(h->rest_host);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -341,6 +347,69 @@ int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t leve
   MCP_CUDA_CHECK(cudaMemcpyAsync(pos_out, h->pos_dev, sizeof(int2) * (size_t)n, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaMemcpyAsync(found, h->found_dev, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MCP_OK;
+}
+
+void mcp_fe_default_rest_config(McpRestConfig* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->use_shi = 0; c->use_thresh = 0;            // src/KeyFrame.cc:68-69 ("fast", "percent")
+  c->top_fraction = 0.8; c->thresh = 70;        // :67, :64
+  c->nonmax_strict = 0;
+  c->prev_slot = -1; c->n_prev = 0;
+}
+
+int mcp_fe_make_keyframe_rest(McpFe* h, int32_t slot, const McpRestConfig* cfg, McpRestLevelOut out[MCP_LEVELS])
+{
+  const int S = h ? (int)h->kf_host.size() : 0;
+  if (!h || !cfg || !out || slot < 0 || slot >= S || !h->kf_valid[slot] || cfg->prev_slot >= S ||
+      (cfg->prev_slot >= 0 && (!h->kf_valid[cfg->prev_slot] || cfg->prev_slot == slot || cfg->n_prev < 1))) {
+    set_last_error("mcp_fe_make_keyframe_rest: bad arguments (slot / prev_slot must hold keyframes)");
+    return MCP_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  const size_t cap = (size_t)h->cfg.max_corners_per_level;
+  // scratch per level: flag, f1, f2 (int) | score (double) | cand, cand_out (16 B) | cand_xy, pos1, pos2 (int2) | 8 counters
+  const size_t per_level = align_up(cap * (3 * sizeof(int) + sizeof(double) + 2 * sizeof(McpCandidate) + 3 * sizeof(int2)) + 8 * 256, 256);
+  if (!h->rest_buf) {
+    MCP_CUDA_CHECK(cudaMalloc(&h->rest_buf, per_level * MCP_LEVELS));
+    MCP_CUDA_CHECK(cudaMallocHost(&h->rest_host, (sizeof(McpCandidate) * cap + 256) * MCP_LEVELS));
+  }
+  FeMeta meta, meta_prev;
+  memset(&meta_prev, 0, sizeof(meta_prev));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&meta, h->kf_host[slot].meta, sizeof(FeMeta), cudaMemcpyDeviceToHost, s));
+  if (cfg->prev_slot >= 0) MCP_CUDA_CHECK(cudaMemcpyAsync(&meta_prev, h->kf_host[cfg->prev_slot].meta, sizeof(FeMeta), cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  McpCandidate* host_c = reinterpret_cast<McpCandidate*>(h->rest_host);
+  int* host_ctr = reinterpret_cast<int*>(host_c + cap * MCP_LEVELS);
+  const bool prune = cfg->prev_slot >= 0 && cfg->n_prev > 0;
+  for (int l = 0; l < MCP_LEVELS; l++) {
+    uint8_t* b = h->rest_buf + per_level * l;
+    int* ctr = reinterpret_cast<int*>(b);
+    double* score = reinterpret_cast<double*>(b + 256);
+    McpCandidate* cand = reinterpret_cast<McpCandidate*>(score + cap);
+    McpCandidate* cand_out = cand + cap;
+    int2* cand_xy = reinterpret_cast<int2*>(cand_out + cap);
+    int2* pos1 = cand_xy + cap; int2* pos2 = pos1 + cap;
+    int* flag = reinterpret_cast<int*>(pos2 + cap);
+    int* f1 = flag + cap; int* f2 = f1 + cap;
+    MCP_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 256, s));
+    const int n = std::min(meta.lv[l].n_corners, (int)cap);
+    const int np = std::min(meta_prev.lv[l].n_corners, (int)cap);
+    fe_launch_rest_level(h->kf_host[slot], prune ? &h->kf_host[cfg->prev_slot] : nullptr, l, n, np, h->cfg.adaptive_thresh, cfg->nonmax_strict,
+                         cfg->use_shi, cfg->use_thresh, cfg->top_fraction, cfg->thresh, cfg->n_prev, flag, score, cand, cand_out, cand_xy,
+                         pos1, pos2, f1, f2, ctr, s);
+    MCP_CUDA_CHECK(cudaMemcpyAsync(host_ctr + 4 * l, ctr, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    MCP_CUDA_CHECK(cudaMemcpyAsync(host_c + cap * l, prune ? cand_out : cand, sizeof(McpCandidate) * (size_t)std::max(n, 1), cudaMemcpyDeviceToHost, s));
+  }
+  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int l = 0; l < MCP_LEVELS; l++) {
+    const int* c = host_ctr + 4 * l;
+    out[l].n_max = c[0]; out[l].n_selected = c[1]; out[l].n_candidates = prune ? c[2] : c[1];
+    if (out[l].cand && out[l].cap > 0)
+      memcpy(out[l].cand, host_c + cap * l, sizeof(McpCandidate) * (size_t)std::min(out[l].n_candidates, out[l].cap));
+  }
   return MCP_OK;
 }
 

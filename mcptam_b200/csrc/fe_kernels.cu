@@ -524,13 +524,11 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
   if (lane == 0) res[i] = out;
 }
 
-// FindShiTomasiScoreAtPoint (half box 3), one thread per corner
-__global__ void k_shitomasi(FeLevel L, int n, const int2* __restrict__ xy, double* __restrict__ out)
+// FindShiTomasiScoreAtPoint (src/ShiTomasi.cc:34-63, half box 3)
+__device__ __forceinline__ double shitomasi_at(const FeLevel& L, int cx, int cy)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int cx = xy[i].x, cy = xy[i].y, hb = 3;
-  if (!(cx >= hb + 1 && cy >= hb + 1 && cx < L.w - hb - 1 && cy < L.h - hb - 1)) { out[i] = 0.0; return; }
+  const int hb = 3;
+  if (!(cx >= hb + 1 && cy >= hb + 1 && cx < L.w - hb - 1 && cy < L.h - hb - 1)) return 0.0;
   double dXX = 0, dYY = 0, dXY = 0;
   for (int y = cy - hb; y <= cy + hb; y++)
     for (int x = cx - hb; x <= cx + hb; x++) {
@@ -544,17 +542,26 @@ __global__ void k_shitomasi(FeLevel L, int n, const int2* __restrict__ xy, doubl
   dXY = __ddiv_rn(dXY, __dmul_rn(2.0, (double)nPixels));
   const double tr = __dadd_rn(dXX, dYY);
   const double disc = __dsub_rn(__dmul_rn(tr, tr), __dmul_rn(4.0, __dsub_rn(__dmul_rn(dXX, dYY), __dmul_rn(dXY, dXY))));
-  out[i] = __dmul_rn(0.5, __dsub_rn(tr, sqrt(disc)));
+  return __dmul_rn(0.5, __dsub_rn(tr, sqrt(disc)));
+}
+
+// one thread per corner
+__global__ void k_shitomasi(FeLevel L, int n, const int2* __restrict__ xy, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = shitomasi_at(L, xy[i].x, xy[i].y);
 }
 
 // MiniPatch: one warp per query.  9x9 SSD, first-best over corners in the +-range box (src/MiniPatch.cc:61-113)
 __global__ void __launch_bounds__(128) k_minipatch(FeLevel S, FeLevel T, int n_corners, int n, const int2* __restrict__ src_xy,
                                                   const int2* __restrict__ start_xy, int range, int2* __restrict__ pos_out,
-                                                  int* __restrict__ found)
+                                                  int* __restrict__ found, const int* __restrict__ n_dev)
 {
   __shared__ uint8_t s_p[4][81 + 3];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (n_dev) n = min(n, *n_dev);          // the query count lives on the device (MakeKeyFrame_Rest)
   if (i >= n) return;
   const int2 sp = src_xy[i], st = start_xy[i];
   const bool ok = sp.x >= 4 && sp.y >= 4 && sp.x < S.w - 4 && sp.y < S.h - 4;      // assert in SampleFromImage
@@ -868,6 +875,164 @@ void fe_launch_pose_update(int n, const McpPoseMeas* meas, int estimator, double
 {
   k_pose_update<<<1, 1024, 0, s>>>(n, meas, estimator, override_sigma, e2buf, res, outlier);
 }
+
+// ---------------------------------------------------------------------------------------------
+// KeyFrame::MakeKeyFrame_Rest candidate generation (src/KeyFrame.cc:363-531), one pyramid level per launch
+// ---------------------------------------------------------------------------------------------
+// [3P] libCVD old_style_corner_score: the score fast_nonmax suppresses on
+__device__ __forceinline__ int fast_old_score(const FeLevel& L, int x, int y, int b)
+{
+  const uint8_t* p = L.img + (size_t)y * L.pitch + x;
+  const int cb = (int)*p + b, c_b = (int)*p - b;
+  int sp = 0, sn = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int v = p[c_ring_dy[i] * L.pitch + c_ring_dx[i]];
+    sp += (v > cb) ? v - cb : 0;
+    sn += (v < c_b) ? c_b - v : 0;
+  }
+  return sp > sn ? sp : sn;
+}
+
+// is (x, y) in Level::vCorners?  (same predicate as k_fast_compact)
+__device__ __forceinline__ bool listed_corner(const FeLevel& L, int x, int y, int thr, bool use_mask)
+{
+  const int sc = L.score[(size_t)y * L.pitch + x];
+  return sc >= thr && sc > 0 && (!use_mask || L.mask[(size_t)y * L.pitch + x] == 255);
+}
+
+// fast_nonmax (3x3, old-style score) + in_image_with_border(10) + candidate score.  One thread per listed corner.
+// ctr[0] += number of maximal corners kept (= vScoresAndMaxCorners.size()).
+__global__ void __launch_bounds__(128) k_rest_flags(FeKf kf, int level, int adaptive, int strict, int use_shi, int* __restrict__ flag,
+                                                   double* __restrict__ score, int* __restrict__ ctr)
+{
+  const FeLevel L = kf.lv[level];
+  const int n = min(kf.meta->lv[level].n_corners, kf.corner_cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int thr = kf.meta->lv[level].fast_thresh;
+  const bool use_mask = adaptive && L.mask;
+  const int2 c = L.corners[i];
+  const int s0 = fast_old_score(L, c.x, c.y, thr);
+  bool is_max = true;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      if (dx == 0 && dy == 0) continue;
+      const int x = c.x + dx, y = c.y + dy;           // corners lie >= 3 px inside the image: always addressable
+      if (!listed_corner(L, x, y, thr, use_mask)) continue;
+      const int o = fast_old_score(L, x, y, thr);
+      if (strict ? (o >= s0) : (o > s0)) is_max = false;
+    }
+  const bool keep = is_max && c.x >= 10 && c.y >= 10 && c.x < L.w - 10 && c.y < L.h - 10;
+  flag[i] = keep ? 1 : 0;
+  double sc = 0.0;
+  if (keep) sc = use_shi ? shitomasi_at(L, c.x, c.y) : (double)L.score[(size_t)c.y * L.pitch + c.x];   // fast_corner_score_10(.., nFastThresh)
+  score[i] = sc;
+  const unsigned m = __ballot_sync(__activemask(), keep);
+  if (keep && (threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(&ctr[0], __popc(m));
+}
+
+// Candidate selection by rank: "percent": descending (score, y, x) order, first (int)(n_max * top_fraction) kept
+// (std::sort on reverse iterators of pair<double, ImageRef>); "thresh": raster order, score > thresh.
+// One thread per corner, all corners streamed through shared memory.  ctr[1] = number of candidates.
+__global__ void __launch_bounds__(256) k_rest_select(FeKf kf, int level, int use_thresh, double top_fraction, double thresh,
+                                                    const int* __restrict__ flag, const double* __restrict__ score,
+                                                    McpCandidate* __restrict__ cand, int2* __restrict__ cand_xy, int* __restrict__ ctr)
+{
+  __shared__ double s_sc[256];
+  __shared__ int2 s_xy[256];
+  __shared__ int s_fl[256];
+  const FeLevel L = kf.lv[level];
+  const int n = min(kf.meta->lv[level].n_corners, kf.corner_cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_max = ctr[0];
+  const int n_use = use_thresh ? n_max : min((int)(n_max * top_fraction), n_max);
+  bool mine = false;
+  double sc = 0;
+  int2 c = make_int2(0, 0);
+  if (i < n) { c = L.corners[i]; sc = score[i]; mine = flag[i] != 0 && (!use_thresh || sc > thresh); }
+  int rank = 0;
+  for (int base = 0; base < n; base += 256) {
+    const int j = base + threadIdx.x;
+    if (j < n) { s_sc[threadIdx.x] = score[j]; s_xy[threadIdx.x] = L.corners[j]; s_fl[threadIdx.x] = flag[j]; }
+    else s_fl[threadIdx.x] = 0;
+    __syncthreads();
+    if (mine) {
+      const int lim = min(256, n - base);
+      for (int k = 0; k < lim; k++) {
+        if (!s_fl[k]) continue;
+        const double os = s_sc[k];
+        const int2 oc = s_xy[k];
+        bool before;
+        if (use_thresh) before = (os > thresh) && (base + k < i);
+        else before = (os > sc) || (os == sc && (oc.y > c.y || (oc.y == c.y && oc.x > c.x)));
+        rank += before ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+  if (mine && rank < n_use) {
+    McpCandidate o;
+    o.x = c.x; o.y = c.y; o.score = sc;
+    cand[rank] = o;
+    cand_xy[rank] = c;
+    if (use_thresh) atomicAdd(&ctr[1], 1);
+  }
+  if (!use_thresh && i == 0) ctr[1] = n_use;
+}
+
+// stable-point pruning (src/KeyFrame.cc:455-527): keep candidate i if both MiniPatch searches succeeded and the
+// round trip ends within sqrt(2) px; ordered compaction by one block.  ctr[2] = number kept.
+__global__ void __launch_bounds__(1024) k_rest_prune(const McpCandidate* __restrict__ cand, const int2* __restrict__ back_pos,
+                                                    const int* __restrict__ f1, const int* __restrict__ f2, McpCandidate* __restrict__ out,
+                                                    int* __restrict__ ctr)
+{
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int n = ctr[1];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool keep = false;
+    McpCandidate c;
+    if (i < n) {
+      c = cand[i];
+      const int dx = back_pos[i].x - c.x, dy = back_pos[i].y - c.y;
+      keep = f1[i] && f2[i] && (dx * dx + dy * dy <= 2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wsum[wid] = __popc(m);
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < wid; w++) off += wsum[w];
+    if (keep) out[off + __popc(m & ((1u << lane) - 1))] = c;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = off + __popc(m);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ctr[2] = carry;
+}
+
+// cfg mirrors McpRestConfig; scratch arrays hold >= corner_cap entries each.  n_hint: upper bound of the corner count.
+void fe_launch_rest_level(const FeKf& kf, const FeKf* prev, int level, int n_hint, int n_prev_corners, int adaptive, int strict, int use_shi,
+                          int use_thresh, double top_fraction, double thresh, int n_prev, int* flag, double* score, McpCandidate* cand,
+                          McpCandidate* cand_out, int2* cand_xy, int2* pos1, int2* pos2, int* f1, int* f2, int* ctr, cudaStream_t s)
+{
+  if (n_hint <= 0) return;
+  k_rest_flags<<<(n_hint + 127) / 128, 128, 0, s>>>(kf, level, adaptive, strict, use_shi, flag, score, ctr);
+  k_rest_select<<<(n_hint + 255) / 256, 256, 0, s>>>(kf, level, use_thresh, top_fraction, thresh, flag, score, cand, cand_xy, ctr);
+  if (prev && n_prev > 0) {
+    // back to the oldest stored frame, then forward to the current one (range 10 per stored frame)
+    k_minipatch<<<(n_hint + 3) / 4, 128, 0, s>>>(kf.lv[level], prev->lv[level], n_prev_corners, n_hint, cand_xy, cand_xy, 10 * n_prev, pos1, f1, ctr + 1);
+    k_minipatch<<<(n_hint + 3) / 4, 128, 0, s>>>(prev->lv[level], kf.lv[level], n_hint, n_hint, pos1, pos1, 10 * n_prev, pos2, f2, ctr + 1);
+    k_rest_prune<<<1, 1024, 0, s>>>(cand, pos2, f1, f2, cand_out, ctr);
+  }
+}
+
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s)
 {
   if (n > 0) k_shitomasi<<<(n + 127) / 128, 128, 0, s>>>(L, n, xy, out);
@@ -875,7 +1040,7 @@ void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, c
 void fe_launch_minipatch(const FeLevel& S, const FeLevel& T, int n_corners, int n, const int2* src, const int2* start, int range,
                          int2* pos, int* found, cudaStream_t s)
 {
-  if (n > 0) k_minipatch<<<(n + 3) / 4, 128, 0, s>>>(S, T, n_corners, n, src, start, range, pos, found);
+  if (n > 0) k_minipatch<<<(n + 3) / 4, 128, 0, s>>>(S, T, n_corners, n, src, start, range, pos, found, nullptr);
 }
 
 }  // namespace mcp

@@ -580,3 +580,114 @@ int ora_pose_update(int n, const double* found_xy, const double* image_xy, const
   free(e2); free(ex);
   return n_in;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * KeyFrame::MakeKeyFrame_Rest candidate generation (src/KeyFrame.cc:363-531)
+ * ------------------------------------------------------------------------------------------ */
+/* [3P] libCVD fast_corner.cpp old_style_corner_score (the score fast_nonmax suppresses on):
+   sp = sum over the ring of (p - (c + b)) where p > c + b,  sn = sum of ((c - b) - p) where p < c - b; max(sp, sn). */
+int ora_fast_old_score(const uint8_t* im, int stride, int x, int y, int barrier)
+{
+  const uint8_t* p = im + (size_t)y * stride + x;
+  const int cb = *p + barrier, c_b = *p - barrier;
+  int sp = 0, sn = 0;
+  for (int i = 0; i < 16; i++) {
+    const int v = p[RING_DY[i] * stride + RING_DX[i]];
+    if (v > cb) sp += v - cb;
+    else if (v < c_b) sn += c_b - v;
+  }
+  return sp > sn ? sp : sn;
+}
+
+/* [3P] libCVD fast_nonmax (src/KeyFrame.cc:393,411): 3x3 suppression among the listed corners on the old-style score.
+   strict = 0 (libCVD nonmax_suppression): a corner is dropped when a neighbouring corner scores strictly higher;
+   strict = 1 (nonmax_suppression_strict): dropped when a neighbour scores higher or equal.
+   Writes 1/0 per input corner into keep[]; returns the number kept. */
+int ora_fast_nonmax(const uint8_t* im, int w, int h, int stride, const int32_t* cxy, int nc, int barrier, int strict, uint8_t* keep)
+{
+  int32_t* map = (int32_t*)malloc(sizeof(int32_t) * (size_t)w * h);
+  for (size_t i = 0; i < (size_t)w * h; i++) map[i] = -1;
+  for (int i = 0; i < nc; i++) map[(size_t)cxy[2 * i + 1] * w + cxy[2 * i]] = ora_fast_old_score(im, stride, cxy[2 * i], cxy[2 * i + 1], barrier);
+  int n = 0;
+  for (int i = 0; i < nc; i++) {
+    const int x = cxy[2 * i], y = cxy[2 * i + 1], s = map[(size_t)y * w + x];
+    int ok = 1;
+    for (int dy = -1; dy <= 1 && ok; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        if (!dx && !dy) continue;
+        const int xx = x + dx, yy = y + dy;
+        if (xx < 0 || yy < 0 || xx >= w || yy >= h) continue;
+        const int o = map[(size_t)yy * w + xx];
+        if (o < 0) continue;
+        if (strict ? (o >= s) : (o > s)) { ok = 0; break; }
+      }
+    keep[i] = (uint8_t)ok;
+    n += ok;
+  }
+  free(map);
+  return n;
+}
+
+typedef struct { double score; int32_t x, y; } ora_cand_t;
+/* std::sort(rbegin, rend) on std::pair<double, CVD::ImageRef>: descending score, ties by descending ImageRef
+   (CVD::ImageRef::operator< is raster order: y, then x). */
+static int cmp_cand_desc(const void* a, const void* b)
+{
+  const ora_cand_t* p = (const ora_cand_t*)a; const ora_cand_t* q = (const ora_cand_t*)b;
+  if (p->score != q->score) return p->score > q->score ? -1 : 1;
+  if (p->y != q->y) return p->y > q->y ? -1 : 1;
+  if (p->x != q->x) return p->x > q->x ? -1 : 1;
+  return 0;
+}
+
+/* One level of MakeKeyFrame_Rest.  cxy/nc/lut: Level::vCorners + vCornerRowLUT of the current image; fast_thresh: nFastThresh.
+   prev_*: imagePrev[0] / vCornersPrev[0] (NULL when the history is empty), n_prev = imagePrev.size().
+   Returns the number of candidates, written to out_xy / out_score; *n_max = vScoresAndMaxCorners.size(). */
+int ora_keyframe_rest_level(const uint8_t* im, int w, int h, int stride, const int32_t* cxy, int nc, const int32_t* lut, int fast_thresh,
+                            int use_shi, int use_thresh, double top_fraction, double thresh, int nonmax_strict,
+                            const uint8_t* prev_im, const int32_t* prev_cxy, int prev_nc, const int32_t* prev_lut, int n_prev,
+                            int32_t* out_xy, double* out_score, int cap, int32_t* n_max)
+{
+  uint8_t* keep = (uint8_t*)malloc((size_t)nc + 1);
+  ora_fast_nonmax(im, w, h, stride, cxy, nc, fast_thresh, nonmax_strict, keep);
+  ora_cand_t* v = (ora_cand_t*)malloc(sizeof(ora_cand_t) * ((size_t)nc + 1));
+  int nv = 0;
+  for (int i = 0; i < nc; i++) {
+    if (!keep[i]) continue;
+    const int x = cxy[2 * i], y = cxy[2 * i + 1];
+    if (!(x >= 10 && y >= 10 && x < w - 10 && y < h - 10)) continue;          /* in_image_with_border(.., 10), :400,415 */
+    double sc;
+    if (use_shi) sc = ora_shitomasi(im, stride, 3, x, y);
+    else { int32_t s; const int32_t one[2] = { x, y }; ora_fast10_score_bisect(im, stride, one, 1, fast_thresh, &s); sc = s; }
+    v[nv].score = sc; v[nv].x = x; v[nv].y = y; nv++;
+  }
+  if (n_max) *n_max = nv;
+  ora_cand_t* cand = (ora_cand_t*)malloc(sizeof(ora_cand_t) * ((size_t)nv + 1));
+  int ncand = 0;
+  if (!use_thresh) {
+    qsort(v, (size_t)nv, sizeof(ora_cand_t), cmp_cand_desc);
+    const int n_use = (int)(nv * top_fraction);
+    for (int i = 0; i < n_use && i < nv; i++) cand[ncand++] = v[i];
+  } else {
+    for (int i = 0; i < nv; i++) if (v[i].score > thresh) cand[ncand++] = v[i];
+  }
+  int nout = 0;
+  for (int i = 0; i < ncand; i++) {
+    if (prev_im && n_prev > 0) {                                               /* :455-527 stable-point pruning */
+      uint8_t patch[81];
+      const int cx = cand[i].x, cy = cand[i].y;
+      for (int r = 0; r < 9; r++) for (int c = 0; c < 9; c++) patch[r * 9 + c] = im[(size_t)(cy - 4 + r) * stride + cx - 4 + c];
+      int32_t pp[2] = { cx, cy };
+      if (!ora_minipatch_find(prev_im, w, h, stride, patch, prev_cxy, prev_nc, prev_lut, h, n_prev * 10, pp)) continue;
+      for (int r = 0; r < 9; r++) for (int c = 0; c < 9; c++) patch[r * 9 + c] = prev_im[(size_t)(pp[1] - 4 + r) * stride + pp[0] - 4 + c];
+      int32_t pn[2] = { pp[0], pp[1] };
+      if (!ora_minipatch_find(im, w, h, stride, patch, cxy, nc, lut, h, n_prev * 10, pn)) continue;
+      const int dx = pn[0] - cx, dy = pn[1] - cy;
+      if (dx * dx + dy * dy > 2) continue;
+    }
+    if (nout < cap) { out_xy[2 * nout] = cand[i].x; out_xy[2 * nout + 1] = cand[i].y; out_score[nout] = cand[i].score; }
+    nout++;
+  }
+  free(keep); free(v); free(cand);
+  return nout;
+}

@@ -139,6 +139,14 @@ int ora_minipatch_find(const uint8_t* im, int w, int h, int stride, const uint8_
                        const int32_t* corners_xy, int n_corners, const int32_t* row_lut_or_null,
                        int n_lut, int range, int32_t* pos_io);
 
+/* KeyFrame::MakeKeyFrame_Rest candidate generation (src/KeyFrame.cc:363-531); fast_nonmax restated from libCVD [3P] */
+int ora_fast_old_score(const uint8_t* im, int stride, int x, int y, int barrier);
+int ora_fast_nonmax(const uint8_t* im, int w, int h, int stride, const int32_t* cxy, int nc, int barrier, int strict, uint8_t* keep);
+int ora_keyframe_rest_level(const uint8_t* im, int w, int h, int stride, const int32_t* cxy, int nc, const int32_t* lut, int fast_thresh,
+                            int use_shi, int use_thresh, double top_fraction, double thresh, int nonmax_strict,
+                            const uint8_t* prev_im, const int32_t* prev_cxy, int prev_nc, const int32_t* prev_lut, int n_prev,
+                            int32_t* out_xy, double* out_score, int cap, int32_t* n_max);
+
 int ora_search_patches_batch(const uint8_t* const* src_pyr, const uint8_t* const* tgt_pyr, const int* widths, const int* heights,
                              const int32_t* const* corners, const int* n_corners, const int32_t* const* luts, int n,
                              const int32_t* req_i, const double* m2, double* found_xy, int32_t* found_flag);

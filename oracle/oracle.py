@@ -237,6 +237,45 @@ def level_corners(img, mask=None, adaptive=True, fixed_thresh=10, cap=1 << 20):
     return {"corners": xy[:n].copy(), "n_corners": n, "fast_freq": freq, "fast_thresh": thr.value, "row_lut": lut}
 
 
+def fast_nonmax(img, corners, barrier, strict=False):
+    """[3P] CVD::fast_nonmax restatement: boolean keep mask over `corners`."""
+    img = np.ascontiguousarray(img, np.uint8)
+    corners = np.ascontiguousarray(corners, np.int32)
+    keep = np.zeros(len(corners) + 1, np.uint8)
+    h, w = img.shape
+    f = lib().ora_fast_nonmax
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    f(_p(img), w, h, w, _p(corners), len(corners), int(barrier), int(strict), _p(keep))
+    return keep[:len(corners)].astype(bool)
+
+
+def keyframe_rest_level(img, lev, prev_img=None, prev_lev=None, n_prev=0, use_shi=False, use_thresh=False, top_fraction=0.8,
+                        thresh=70.0, nonmax_strict=False):
+    """One level of KeyFrame::MakeKeyFrame_Rest (src/KeyFrame.cc:363-531).  lev / prev_lev: dicts from level_corners()."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cor = np.ascontiguousarray(lev["corners"], np.int32)
+    lut = np.ascontiguousarray(lev["row_lut"], np.int32)
+    cap = len(cor) + 1
+    out_xy = np.zeros((cap, 2), np.int32)
+    out_sc = np.zeros(cap)
+    n_max = C.c_int32()
+    f = lib().ora_keyframe_rest_level
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                  C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    if prev_img is not None and n_prev > 0:
+        pim = np.ascontiguousarray(prev_img, np.uint8)
+        pcor = np.ascontiguousarray(prev_lev["corners"], np.int32)
+        plut = np.ascontiguousarray(prev_lev["row_lut"], np.int32)
+        pa = (_p(pim), _p(pcor), len(pcor), _p(plut), int(n_prev))
+    else:
+        pim = pcor = plut = None
+        pa = (None, None, 0, None, 0)
+    n = f(_p(img), w, h, w, _p(cor), len(cor), _p(lut), int(lev["fast_thresh"]), int(use_shi), int(use_thresh), float(top_fraction),
+          float(thresh), int(nonmax_strict), *pa, _p(out_xy), _p(out_sc), cap, C.byref(n_max))
+    return {"n_max": n_max.value, "n_candidates": n, "xy": out_xy[:n].copy(), "score": out_sc[:n].copy()}
+
+
 def shitomasi(img, x, y, half_box=3):
     img = np.ascontiguousarray(img, np.uint8)
     return lib().ora_shitomasi(_p(img), img.shape[1], half_box, int(x), int(y))

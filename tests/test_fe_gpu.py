@@ -273,3 +273,32 @@ def test_fe_errors(capi):
         f.search_patches(0, req)                                  # empty keyframe slot
     with pytest.raises(capi.McpError):
         f.make_keyframe(99, np.zeros((480, 640), np.uint8))
+
+
+@pytest.mark.parametrize("mode", ["fast_percent", "shi_percent", "fast_thresh", "strict", "pruned", "pruned_shi_thresh"])
+def test_keyframe_rest_candidates(capi, ora, mode):
+    """MakeKeyFrame_Rest candidate generation (src/KeyFrame.cc:363-531): fast_nonmax, scoring, selection order and
+    the MiniPatch stable-point test — candidates index-exact and scores bit-exact against the oracle, all 4 levels."""
+    cur = synth.make_frame(seed=11)
+    prev = synth.make_frame(seed=11, shift=(1.0, -1.0))
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    f.make_keyframe(0, prev)
+    f.make_keyframe(1, cur)
+    kw = dict(use_shi=mode in ("shi_percent", "pruned_shi_thresh"), use_thresh=mode in ("fast_thresh", "pruned_shi_thresh"),
+              nonmax_strict=mode == "strict", thresh=40.0 if mode == "fast_thresh" else 500.0)
+    pruned = mode.startswith("pruned")
+    got = f.make_keyframe_rest(1, prev_slot=0 if pruned else -1, n_prev=2 if pruned else 0,
+                               **{k: int(v) if isinstance(v, bool) else v for k, v in kw.items()})
+    pc, pp = ora.pyramid(cur), ora.pyramid(prev)
+    total = 0
+    for l in range(4):
+        lc, lp = ora.level_corners(pc[l]), ora.level_corners(pp[l])
+        ref = ora.keyframe_rest_level(pc[l], lc, prev_img=pp[l] if pruned else None, prev_lev=lp if pruned else None,
+                                      n_prev=2 if pruned else 0, **kw)
+        g = got[l]
+        assert g["n_max"] == ref["n_max"], (l, g["n_max"], ref["n_max"])
+        assert g["n_candidates"] == ref["n_candidates"], (l, g["n_candidates"], ref["n_candidates"])
+        assert np.array_equal(np.stack([g["cand"]["x"], g["cand"]["y"]], 1), ref["xy"])
+        assert np.array_equal(g["cand"]["score"], ref["score"])
+        total += ref["n_candidates"]
+    assert total > 50

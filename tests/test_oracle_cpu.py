@@ -189,3 +189,67 @@ def test_subpix_recovers_translation():
             n_ok += 1
             errs.append(np.hypot(p[0] - (cx - 0.4), p[1] - (cy + 0.3)))
     assert n_ok > 20 and np.median(errs) < 0.15
+
+
+def _nonmax_numpy(img, corners, barrier, strict):
+    """Independent, definition-level restatement of CVD::fast_nonmax (old-style score, 3x3 window)."""
+    ring = [(0, -3), (1, -3), (2, -2), (3, -1), (3, 0), (3, 1), (2, 2), (1, 3), (0, 3), (-1, 3), (-2, 2), (-3, 1), (-3, 0), (-3, -1), (-2, -2), (-1, -3)]
+    im = img.astype(np.int64)
+    sc = {}
+    for x, y in corners:
+        c = im[y, x]
+        v = np.array([im[y + dy, x + dx] for dx, dy in ring])
+        sp = np.sum(np.where(v > c + barrier, v - (c + barrier), 0))
+        sn = np.sum(np.where(v < c - barrier, (c - barrier) - v, 0))
+        sc[(int(x), int(y))] = int(max(sp, sn))
+    keep = []
+    for x, y in corners:
+        s = sc[(int(x), int(y))]
+        ok = True
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                o = sc.get((int(x) + dx, int(y) + dy))
+                if (dx or dy) and o is not None and (o >= s if strict else o > s):
+                    ok = False
+        keep.append(ok)
+    return np.array(keep)
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_fast_nonmax_matches_definition(strict):
+    img = synth.make_frame(320, 240, seed=5)
+    lev = ora.level_corners(img)
+    keep = ora.fast_nonmax(img, lev["corners"], lev["fast_thresh"], strict=strict)
+    ref = _nonmax_numpy(img, lev["corners"], lev["fast_thresh"], strict)
+    assert np.array_equal(keep, ref)
+    assert 0 < keep.sum() < len(keep)
+    if not strict:          # the non-strict test can only keep more corners than the strict one
+        assert keep.sum() >= ora.fast_nonmax(img, lev["corners"], lev["fast_thresh"], strict=True).sum()
+
+
+def test_keyframe_rest_candidates():
+    """MakeKeyFrame_Rest (src/KeyFrame.cc:363-531): ordering, top-fraction count, border, stable-point pruning."""
+    a = synth.make_frame(320, 240, seed=7)
+    b = synth.make_frame(320, 240, seed=7, shift=(1.0, 0.0))          # previous frame: 1 px camera shift
+    la, lb = ora.level_corners(a), ora.level_corners(b)
+    r = ora.keyframe_rest_level(a, la)
+    assert r["n_candidates"] == int(r["n_max"] * 0.8)
+    s, xy = r["score"], r["xy"]
+    key = list(zip(s.tolist(), xy[:, 1].tolist(), xy[:, 0].tolist()))
+    assert key == sorted(key, reverse=True)                             # descending (score, y, x)
+    assert (xy[:, 0] >= 10).all() and (xy[:, 0] < 310).all() and (xy[:, 1] >= 10).all() and (xy[:, 1] < 230).all()
+    # FAST candidate score == fast_corner_score_10 at the level threshold
+    assert np.array_equal(s.astype(int), ora.fast10_score(a, xy, la["fast_thresh"], bisect=True))
+    # "thresh" criterion keeps raster order
+    t = ora.keyframe_rest_level(a, la, use_thresh=True, thresh=float(np.median(s)))
+    ty = t["xy"]
+    assert (np.diff(ty[:, 1] * 1000 + ty[:, 0]) > 0).all() and (t["score"] > np.median(s)).all()
+    # Shi-Tomasi scoring
+    sh = ora.keyframe_rest_level(a, la, use_shi=True)
+    assert sh["n_candidates"] == r["n_candidates"] and np.isclose(sh["score"][0], ora.shitomasi(a, *sh["xy"][0]))
+    # pruning against itself keeps every candidate; against a shifted frame it keeps a proper, non-empty subset
+    same = ora.keyframe_rest_level(a, la, prev_img=a, prev_lev=la, n_prev=1)
+    assert same["n_candidates"] == r["n_candidates"] and np.array_equal(same["xy"], r["xy"])
+    pr = ora.keyframe_rest_level(a, la, prev_img=b, prev_lev=lb, n_prev=2)
+    assert 0 < pr["n_candidates"] <= r["n_candidates"]
+    assert set(map(tuple, pr["xy"])) <= set(map(tuple, r["xy"]))
