@@ -450,20 +450,30 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
       for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = acc2[a][b];
-      if (tid == 0) { while (ld_acquire(&inv_ready[j - 1]) != epoch) { } }
+      // X = acc2 * L_{j-1,j-1}^-T by forward substitution against the factor itself (published with the reciprocal
+      // pivots on its diagonal) -- the chain does not wait for the explicit inverse.  8 threads per row of X,
+      // thread (row, g) keeps columns g, g+8, g+16, g+24; the solved column is broadcast with one shuffle.
+      if (tid == 0) { while (ld_acquire(&ready[tile_index(j - 1, j - 1)]) != epoch) { } }
       __syncthreads();
-      const double* gi = Linv + (size_t)(j - 1) * (TB * TB);
-      for (int e = tid; e < TB * TB; e += 256) Bs[(e >> 5) * TLD + (e & 31)] = __ldcg(gi + e);
-      __syncthreads();
-      double x[2][2] = { { 0, 0 }, { 0, 0 } };
-      tile_mm_sub(As, Bs, ty, tx, x);          // x = -(acc2 * Linv^T)
+      const double* gd = Lt + tile_index(j - 1, j - 1) * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) Bs[(e >> 5) * TLD + (e & 31)] = __ldcg(gd + e);
+      const int xr = 4 * wid + (lane >> 3), xg = lane & 7;
+      double a4[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) a4[q] = As[xr * TLD + xg + 8 * q];
       __syncthreads();
 #pragma unroll
-      for (int a = 0; a < 2; a++)
+      for (int c = 0; c < TB; c++) {
+        const double xv = __shfl_sync(0xffffffffu, a4[c >> 3] * Bs[c * TLD + c], (lane & 24) | (c & 7));
+        if (xg == (c & 7)) As[xr * TLD + c] = xv;
 #pragma unroll
-        for (int b = 0; b < 2; b++) As[(ty + 16 * a) * TLD + tx + 16 * b] = x[a][b];
+        for (int q = 0; q < 4; q++) {
+          const int k = xg + 8 * q;
+          if (8 * q + 7 > c) a4[q] = (k > c) ? fma(-Bs[k * TLD + c], xv, a4[q]) : a4[q];
+        }
+      }
       __syncthreads();
-      tile_mm_sub(As, As, ty, tx, acc);        // sign cancels: (-X)(-X)^T
+      tile_mm_sub(As, As, ty, tx, acc);        // acc -= X X^T
       __syncthreads();
     } else
     for (int k = 0; k < j; k++) {
@@ -496,21 +506,26 @@ __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base
         __shared__ int s_bad;
         if (tid == 0) s_bad = 0;
         __syncthreads();
-        potrf32_blocked(As, xs + 32 * TB, xs + 32 * TB - 64, xs, tid, &s_bad);
+        potrf32_panel<true, 16>(As, xs + 32 * TB, tid, &s_bad);
         if (tid == 0 && s_bad) atomicExch(&ctr[2], epoch);
       }
       if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3p));
+      // publish the factor first (reciprocal pivots on the diagonal): the next diagonal task solves against it directly
+      double* gl = Lt + tile_index(j, j) * (TB * TB);
+      for (int e = tid; e < TB * TB; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        gl[e] = (r == c) ? xs[32 * TB + r] : As[r * TLD + c];
+      }
+      __syncthreads();
+      if (tid == 0) { __threadfence(); st_release(&ready[tile_index(j, j)], epoch); }
+      // explicit inverse for the off-diagonal tiles of this block column and the back substitution
       inverse32_block(As, Bs, xs + 32 * TB, xs, tid);
       if (d.dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t4p));
       __syncthreads();
-      double* gl = Lt + tile_index(j, j) * (TB * TB);
       double* gi = Linv + (size_t)j * (TB * TB);
       for (int e = tid; e < TB * TB; e += 256) gi[e] = Bs[(e >> 5) * TLD + (e & 31)];
       __syncthreads();
-      if (tid == 0) { __threadfence(); st_release(&inv_ready[j], epoch); }     // the critical consumer needs Linv only
-      for (int e = tid; e < TB * TB; e += 256) gl[e] = As[(e >> 5) * TLD + (e & 31)];
-      __syncthreads();
-      if (tid == 0) { __threadfence(); st_release(&ready[tile_index(j, j)], epoch); }
+      if (tid == 0) { __threadfence(); st_release(&inv_ready[j], epoch); }
     } else {
       // ---- off-diagonal / rhs tile: X = acc * Linv_j^T ------------------------------------------------
       if (tid == 0) { while (ld_acquire(&inv_ready[j]) != epoch) { } }
