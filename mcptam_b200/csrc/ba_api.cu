@@ -47,6 +47,7 @@ int stage_doubles_for(int n_pose, int n_cam);
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
+void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 
 struct DevBuf {
   void* p = nullptr;
@@ -716,7 +717,26 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     for (int q = 0; q < d.n_meas; q++) if (h->flags_host[q]) h->outliers.push_back(h->meas_orig[q]);
     std::sort(h->outliers.begin(), h->outliers.end());
   }
-  if (st) { st->n_outliers = (int)h->outliers.size(); st->max_cov = 0; st->kernel_launches = h->launches; }
+  // median point-depth covariance (src/ChainBundle.cc:1401-1448): attempted only with < 3 movable poses
+  double max_cov = 0;                               // the reference's "computeMarginals() failed" value
+  if (d.n_pose_var < 3 && !multi) {
+    if (d.n_pt_var == 0) max_cov = 1.7976931348623157e308;
+    else {
+      if ((rc = h->b_tmp.ensure(sizeof(double) * ((size_t)d.n_pt_var + 2)))) return rc;
+      BaDev dm = d;
+      dm.cand = -1;                                 // lambda = 0: the stored Hessian of the last linearisation
+      MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * (h->acc_doubles - h->off_Sm), s));
+      launch_schur_gather(dm, s);
+      launch_marginals(dm, h->b_tmp.as<double>(), s);
+      BaDev ds = d;
+      ds.n_meas = d.n_pt_var;
+      for (int k = 0; k < N_STATE; k++) ds.chi2[k] = h->b_tmp.as<double>();
+      h->launches += 3 + launch_select_sigma(ds, 0, 2, s);
+      if ((rc = sync_ctrl(h))) return rc;
+      max_cov = c.marg_fail ? 0.0 : c.median_out;
+    }
+  }
+  if (st) { st->n_outliers = (int)h->outliers.size(); st->max_cov = max_cov; st->kernel_launches = h->launches; }
   return counter;
 }
 

@@ -601,7 +601,8 @@ __global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pas
       const double med = __longlong_as_double((long long)np);
       const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
       double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
-      if (mode == 0) {
+      if (mode == 2) ctrl->median_out = med;
+      else if (mode == 0) {
         s = 1.345 * s;
         ctrl->sigma_sq_raw = s * s;
         ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
@@ -741,7 +742,8 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
     const double med = __longlong_as_double((long long)med_bits);
     const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
     double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
-    if (mode == 0) {
+    if (mode == 2) ctrl->median_out = med;                      // plain upper median (src/ChainBundle.cc:1434)
+    else if (mode == 0) {
       s = 1.345 * s;
       ctrl->sigma_sq_raw = s * s;
       ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;

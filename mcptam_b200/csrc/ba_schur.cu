@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_schur_y(BaDev d)
 #pragma unroll
     for (int i = 0; i < 12; i++) y2[i] = make_double2(y[2 * i], y[2 * i + 1]);
   }
-  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand], 0);
+  if (fail) atomicExch(&d.ctrl->solve_ok[d.cand < 0 ? 0 : d.cand], 0);
 }
 
 // One warp per work item {block row a, block col b, begin, end}.  Incidences are processed in groups of G:
@@ -260,6 +260,91 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
     if (diag && lane < 6) atomicAdd(d.rm + 6 * item.x + lane, accz);
   }
 }
+
+// ChainBundle's point-depth covariance (src/ChainBundle.cc:1401-1448; [3P] SparseOptimizer::computeMarginals on the
+// undamped Hessian of the last buildSystem): (H^-1)_pp = V^-1 + Y^T S^-1 Y with Y = W V^-1 (lambda = 0) and
+// S = H_cc - sum W V^-1 W^T.  Only the (2,2) entry (radial direction) of every non-fixed point is needed.
+// The reference only attempts this with < 3 movable poses, so S is at most 12 x 12: one block, S^-1 by thread 0.
+constexpr int MARG_MAXN = 32;
+__global__ void __launch_bounds__(256) k_marginals(BaDev d, double* __restrict__ cov)
+{
+  __shared__ double S[MARG_MAXN * MARG_MAXN], Si[MARG_MAXN * MARG_MAXN];
+  __shared__ int s_fail;
+  const int n = d.nc;
+  if (threadIdx.x == 0) s_fail = (n > MARG_MAXN) ? 1 : 0;
+  for (int e = threadIdx.x; e < n * n && n <= MARG_MAXN; e += blockDim.x) {
+    const int r = e / n, c = e - r * n;
+    const int lo = r < c ? r : c, hi = r < c ? c : r;                 // the upper triangle is the valid one
+    S[e] = d.H0[(size_t)lo * n + hi] - d.Sm[(size_t)lo * n + hi];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && !s_fail && n > 0) {
+    // Cholesky S = L L^T in place (lower), then S^-1 = L^-T L^-1 column by column
+    for (int j = 0; j < n && !s_fail; j++) {
+      double dj = S[j * n + j];
+      for (int k = 0; k < j; k++) dj -= S[j * n + k] * S[j * n + k];
+      if (!(dj > 0.0) || !isfinite(dj)) { s_fail = 1; break; }
+      const double l = sqrt(dj);
+      S[j * n + j] = l;
+      for (int i = j + 1; i < n; i++) {
+        double v = S[i * n + j];
+        for (int k = 0; k < j; k++) v -= S[i * n + k] * S[j * n + k];
+        S[i * n + j] = v / l;
+      }
+    }
+    for (int c = 0; c < n && !s_fail; c++) {
+      double y[MARG_MAXN];
+      for (int i = 0; i < n; i++) {
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; k++) v -= S[i * n + k] * y[k];
+        y[i] = v / S[i * n + i];
+      }
+      for (int i = n - 1; i >= 0; i--) {
+        double v = y[i];
+        for (int k = i + 1; k < n; k++) v -= S[k * n + i] * y[k];
+        y[i] = v / S[i * n + i];
+      }
+      for (int i = 0; i < n; i++) Si[i * n + c] = y[i];
+    }
+  }
+  __syncthreads();
+  int fail = 0;
+  if (!s_fail)
+    for (int p = threadIdx.x; p < d.n_pt; p += blockDim.x) {
+      const int pv = d.pt_var[p];
+      if (pv < 0) continue;
+      double V6[6], Vi[9];
+#pragma unroll
+      for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+      if (!inv3_sym_s(V6, 0.0, Vi)) fail = 1;
+      double c22 = Vi[8];
+      const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
+      for (int a = 0; a < K; a++) {
+        const int va = d.slot_var[s0 + a];
+        double ya[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) ya[r] = d.Y[24 * (size_t)(s0 + a) + 3 * r + 2];
+        for (int b = 0; b < K; b++) {
+          const int vb = d.slot_var[s0 + b];
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) t += Si[(6 * va + r) * n + 6 * vb + c] * d.Y[24 * (size_t)(s0 + b) + 3 * c + 2];
+            c22 += ya[r] * t;
+          }
+        }
+      }
+      cov[pv] = c22;
+    }
+  if (fail) atomicExch(&s_fail, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    d.ctrl->marg_fail = (s_fail || !d.ctrl->solve_ok[0]) ? 1 : 0;
+    d.ctrl->solve_ok[0] = 1;
+  }
+}
+void launch_marginals(const BaDev& d, double* cov, cudaStream_t s) { k_marginals<<<1, 256, 0, s>>>(d, cov); }
 
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148, 128, 0, s>>>(d, cnt); }
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148, 128, 0, s>>>(d, cursor, inc); }

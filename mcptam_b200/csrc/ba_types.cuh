@@ -42,6 +42,8 @@ struct BaCtrl {
   int sel_n;          // number of values in the selection (global measurement count)
   int sel_rank;       // n/2
   int cand_used;      // candidates consumed by the last k_lm_control
+  int marg_fail;      // computeMarginals() failed (singular block)
+  double median_out;  // plain upper median of the last mode-2 selection (point-depth covariances)
 };
 
 struct BaDev {
@@ -95,6 +97,7 @@ struct BaDev {
 // 0..c-1 (each rejection: lambda *= ni, ni *= 2)
 __device__ __forceinline__ double trial_lambda(const BaDev& d)
 {
+  if (d.cand < 0) return 0.0;                      // marginals pass: the undamped Hessian
   double l = d.ctrl->lambda, ni = d.ctrl->ni;
   for (int c = 0; c < d.cand; c++) { l *= ni; ni *= 2; }
   return l;

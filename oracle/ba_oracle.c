@@ -718,7 +718,7 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
   memset(h->b, 0, sizeof(double) * (size_t)dim);
   ptblk_t* blk = (ptblk_t*)malloc(sizeof(ptblk_t));
   double* Hfull = NULL;
-  if (solve_mode == 1) Hfull = (double*)calloc((size_t)dim * (size_t)dim + 1, sizeof(double));
+  if (solve_mode >= 1) Hfull = (double*)calloc((size_t)dim * (size_t)dim + 1, sizeof(double));
   /* per-point storage for Schur back-substitution */
   double* Vinv_all = (double*)calloc((size_t)nptv * 9 + 1, sizeof(double));
   int* slot_off = (int*)calloc((size_t)h->n_pt + 1, sizeof(int));
@@ -791,7 +791,7 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
       slot_var[slot_off[p] + s] = blk->var[s];
       memcpy(slot_W + (size_t)(slot_off[p] + s) * 18, blk->W[s], sizeof(blk->W[s]));
     }
-    if (solve_mode == 1) {
+    if (solve_mode >= 1) {
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Hfull[(size_t)(nc + 3 * pv + r) * dim + nc + 3 * pv + c] = blk->V[r * 3 + c];
       for (int s = 0; s < blk->nslot; s++)
@@ -825,7 +825,31 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
 
   int rc = 0;
   if (fail) rc = -1;
-  if (!rc && solve_mode == 1) {
+  if (!rc && solve_mode == 2) {
+    /* [3P] SparseOptimizer::computeMarginals on the stored (undamped) Hessian: (H^-1)_pp(2,2) per point, dense.
+       (H^-1)_ii = || L^-1 e_i ||^2 with H = L L^T.  Median (element [n/2]) as src/ChainBundle.cc:1420-1436. */
+    for (int r = 0; r < nc; r++)
+      for (int c = 0; c < nc; c++) Hfull[(size_t)r * dim + c] = Hcc[(size_t)r * nc + c];
+    if (chol_dense(Hfull, dim)) rc = -1;
+    else {
+      double* cov = (double*)malloc(sizeof(double) * (size_t)(nptv + 1));
+      double* y = (double*)malloc(sizeof(double) * (size_t)(dim + 1));
+      for (int pv = 0; pv < nptv; pv++) {
+        const int i0 = nc + 3 * pv + 2;
+        double acc = 0;
+        for (int i = i0; i < dim; i++) {
+          double v = (i == i0) ? 1.0 : 0.0;
+          for (int k = i0; k < i; k++) v -= Hfull[(size_t)i * dim + k] * y[k];
+          y[i] = v / Hfull[(size_t)i * dim + i];
+          acc += y[i] * y[i];
+        }
+        cov[pv] = acc;
+      }
+      qsort(cov, (size_t)nptv, sizeof(double), cmp_double);
+      h->max_cov = nptv > 0 ? cov[nptv / 2] : DBL_MAX;
+      free(cov); free(y);
+    }
+  } else if (!rc && solve_mode == 1) {
     for (int r = 0; r < nc; r++)
       for (int c = 0; c < nc; c++) Hfull[(size_t)r * dim + c] = Hcc[(size_t)r * nc + c];
     for (int i = 0; i < dim; i++) Hfull[(size_t)i * dim + i] += lambda;
@@ -1021,6 +1045,23 @@ int ora_ba_compute(OraBa* h, volatile const uint8_t* abort_ext, int n_iter, doub
     }
     h->total_trials += qmax;                                  /* UpdateTotalIterationsAction */
   }
+  /* marginals (:1401-1448): only with <3 movable poses, on the Hessian of the LAST buildSystem, i.e. the state the
+     final iteration was linearised at (pose_bak / pt_bak), with that iteration's robust weights */
+  h->max_cov = 0;
+  if (counter > 0 && npv < 3) {
+    if (nptv == 0) h->max_cov = DBL_MAX;
+    else if (dim <= 2500) {
+      se3_t* pose_fin = (se3_t*)malloc(sizeof(se3_t) * (size_t)h->n_pose);
+      double* pt_fin = (double*)malloc(sizeof(double) * 3 * (size_t)h->n_pt);
+      memcpy(pose_fin, h->pose, sizeof(se3_t) * (size_t)h->n_pose); memcpy(pt_fin, h->pt, sizeof(double) * 3 * (size_t)h->n_pt);
+      memcpy(h->pose, pose_bak, sizeof(se3_t) * (size_t)h->n_pose); memcpy(h->pt, pt_bak, sizeof(double) * 3 * (size_t)h->n_pt);
+      h->recompute_sigma = 0;
+      compute_errors(h);
+      if (build_and_solve(h, 0.0, 2)) h->max_cov = 0;         /* computeMarginals() failed */
+      memcpy(h->pose, pose_fin, sizeof(se3_t) * (size_t)h->n_pose); memcpy(h->pt, pt_fin, sizeof(double) * 3 * (size_t)h->n_pt);
+      free(pose_fin); free(pt_fin);
+    }
+  }
   free(pose_bak); free(pt_bak);
 
   h->hit_max = (counter == n_iter);
@@ -1054,9 +1095,7 @@ int ora_ba_compute(OraBa* h, volatile const uint8_t* abort_ext, int n_iter, doub
     }
     free(a);
   }
-  /* marginals (:1401-1448): only attempted with <3 movable poses; not restated -> "failed" branch value */
-  h->max_cov = 0;
-  st->max_cov = h->max_cov;
+  st->max_cov = h->max_cov;                                   /* computed above, before the AFTER block */
   st->n_outliers = h->n_outliers;
   return counter;
 }

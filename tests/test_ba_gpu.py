@@ -133,3 +133,23 @@ def test_convergence_noise_free(capi):
     assert rc > 0
     assert np.abs(g.poses() - prob.truth_pose_Rt).max() < 1e-5
     assert np.abs(g.points() - prob.truth_pt_xyz).max() < 1e-4
+
+
+@pytest.mark.parametrize("robust", [True, False])
+def test_point_depth_covariance(capi, robust):
+    """GetMaxCov(): median (2,2) point covariance with < 3 movable poses (src/ChainBundle.cc:1401-1448).  The CUDA
+    path uses the Schur form V^-1 + Y^T S^-1 Y, the oracle a dense factorisation of the full Hessian."""
+    from oracle.oracle import OracleBA
+    prob = synth.make_ba_problem(n_cam=2, n_mkf=3, n_pt=150, seed=3)
+    g = capi.BaHandle(use_robust=robust, use_tukey=robust)
+    g.load(prob)
+    o = OracleBA(prob, use_robust=robust, use_tukey=robust)
+    rc_g, st_g = g.compute(6)
+    rc_o, st_o = o.compute(6)
+    assert rc_g == rc_o and st_g.total_trials == st_o.total_trials
+    assert st_o.max_cov > 0 and abs(st_g.max_cov - st_o.max_cov) <= 1e-6 * st_o.max_cov
+    # >= 3 movable poses: not attempted, the reference's "failed" value
+    g2 = capi.BaHandle()
+    g2.load(synth.make_ba_config("tiny", seed=0))
+    rc, st = g2.compute(2)
+    assert st.max_cov == 0

@@ -253,3 +253,34 @@ def test_keyframe_rest_candidates():
     pr = ora.keyframe_rest_level(a, la, prev_img=b, prev_lev=lb, n_prev=2)
     assert 0 < pr["n_candidates"] <= r["n_candidates"]
     assert set(map(tuple, pr["xy"])) <= set(map(tuple, r["xy"]))
+
+
+def test_marginals_match_dense_numpy_inverse():
+    """ChainBundle's median point-depth covariance (src/ChainBundle.cc:1401-1448): the oracle's value equals the
+    (2,2) entries of the point blocks of a numpy inverse of the Hessian assembled from the oracle's Jacobians."""
+    prob = synth.make_ba_problem(n_cam=2, n_mkf=3, n_pt=60, seed=3, outlier_frac=0.0)
+    o = OracleBA(prob, use_robust=False, use_tukey=False)
+    pose_var = np.cumsum(prob.pose_fixed == 0) - 1
+    pose_var[prob.pose_fixed != 0] = -1
+    npv, nptv = o.n_pose_var, o.n_pt_var
+    assert npv == 2
+    dim = 6 * npv + 3 * nptv
+    H = np.zeros((dim, dim))
+    for m in range(prob.n_meas):                                     # Hessian at the initial state = the state the
+        jo, js, jp = o.jacobians(m)                                  # single iteration below is linearised at
+        J = np.zeros((2, dim))
+        p = prob.meas_pt[m]
+        for chain, jac in ((prob.meas_chain[m], jo), (prob.pt_chain[p], js)):
+            for i, pid in enumerate(chain):
+                if pid >= 0 and pose_var[pid] >= 0:
+                    J[:, 6 * pose_var[pid]:6 * pose_var[pid] + 6] += jac[i]
+        J[:, 6 * npv + 3 * p:6 * npv + 3 * p + 3] = jp
+        H += J.T @ J / np.sqrt(prob.meas_noise[m])
+    cov = np.linalg.inv(H)
+    c22 = np.sort([cov[6 * npv + 3 * p + 2, 6 * npv + 3 * p + 2] for p in range(nptv)])
+    rc, st = o.compute(1)
+    assert rc == 1
+    assert np.isclose(st.max_cov, c22[nptv // 2], rtol=1e-8)
+    # >= 3 movable poses: the reference does not attempt it and reports 0 ("failed")
+    rc, st = OracleBA(synth.make_ba_config("tiny", seed=0)).compute(2)
+    assert st.max_cov == 0
