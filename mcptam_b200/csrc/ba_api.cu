@@ -86,7 +86,7 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items;
   // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
   struct Cand {
     DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
@@ -178,7 +178,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items };
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
   for (int q = 1; q < MAX_CAND; q++) {
@@ -361,8 +361,40 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
       return pt_meas_off[a + 1] - pt_meas_off[a] > pt_meas_off[b + 1] - pt_meas_off[b];
     });
 
+  // work lists of k_pose_blocks: this rank's measurements bucketed by the pose block they contribute to
+  // ((v,v): observed from movable pose v; (lo,hi): observer / source pair), cut into items of <= 128 measurements
+  std::vector<int> pb_idx;
+  std::vector<int4> pb_items;
+  {
+    const int m_lo = h->part_meas[h->rank], m_hi = h->part_meas[h->rank + 1];
+    std::vector<std::pair<long long, int> > keyed;
+    keyed.reserve((size_t)(m_hi - m_lo) * 2);
+    for (int q = m_lo; q < m_hi; q++) {
+      const int vo = meas_b[q].x;
+      if (vo < 0) continue;
+      keyed.emplace_back((long long)vo * npv + vo, q);
+      if (meas_b[q].z) {
+        const int vs = pt_info[meas_b[q].w].z;
+        keyed.emplace_back((long long)std::min(vo, vs) * npv + std::max(vo, vs), q);
+      }
+    }
+    std::sort(keyed.begin(), keyed.end());
+    pb_idx.resize(keyed.size());
+    const int CH = 128;
+    for (size_t i = 0; i < keyed.size();) {
+      size_t j = i;
+      while (j < keyed.size() && keyed[j].first == keyed[i].first) j++;
+      const int lo = (int)(keyed[i].first / npv), hi = (int)(keyed[i].first % npv);
+      for (size_t b = i; b < j; b += CH) pb_items.push_back(make_int4(lo, hi, (int)b, (int)std::min(b + CH, j)));
+      for (size_t k = i; k < j; k++) pb_idx[k] = keyed[k].second;
+      i = j;
+    }
+  }
+
   int rc;
 #define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
+  UP(h->b_pb_idx, pb_idx); UP(h->b_pb_items, pb_items);
+  if ((rc = h->b_mrec.ensure(sizeof(double) * MREC * (size_t)std::max(n_meas, 1)))) return rc;
   UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_order, pt_order); UP(h->b_pt_meas_off, pt_meas_off);
   UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_slot_pt, slot_pt); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
   UP(h->b_meas_a, meas_a); UP(h->b_meas_b, meas_b);
@@ -426,6 +458,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
   d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
+  d.mrec = h->b_mrec.as<double>(); d.pb_idx = h->b_pb_idx.as<int>(); d.pb_items = h->b_pb_items.as<int4>(); d.n_pb_items = (int)pb_items.size();
   d.sel_state = h->b_sel.as<unsigned long long>();
   d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
   d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();

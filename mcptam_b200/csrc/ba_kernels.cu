@@ -326,17 +326,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
       }
       const int vo = mbi.x;
       if (vo >= 0) {
-        double Jo[12];
-        pose_jac(g.A, g.q, -1.0, Jo);
-        // H0[vo,vo] upper triangle, gc[vo]
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-          atomicAdd(d.gc + 6 * vo + r, -(Jo[r] * we0 + Jo[6 + r] * we1));
-#pragma unroll
-          for (int cc = r; cc < 6; cc++)
-            atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vo + cc, w * (Jo[r] * Jo[cc] + Jo[6 + r] * Jo[6 + cc]));
+        // The pose-pose blocks (U_oo, g_o and the observer/source cross block) are NOT accumulated here: 63 fp64
+        // global atomics per measurement made this kernel atomic-throughput bound.  The measurement leaves a
+        // record instead and k_pose_blocks reduces the records pose block by pose block.
+        double2* rec = reinterpret_cast<double2*>(d.mrec + (size_t)MREC * m);
+        rec[0] = make_double2(g.A[0], g.A[1]); rec[1] = make_double2(g.A[2], g.A[3]); rec[2] = make_double2(g.A[4], g.A[5]);
+        rec[3] = make_double2(g.q[0], g.q[1]); rec[4] = make_double2(g.q[2], w); rec[5] = make_double2(we0, we1);
+        if (has_src) {
+          rec[6] = make_double2(g.A2[0], g.A2[1]); rec[7] = make_double2(g.A2[2], g.A2[3]); rec[8] = make_double2(g.A2[4], g.A2[5]);
+          rec[9] = make_double2(c.qs[0], c.qs[1]); rec[10] = make_double2(c.qs[2], (double)vo);
         }
         if (pvar >= 0) {
+          double Jo[12];
+          pose_jac(g.A, g.q, -1.0, Jo);
           // J_pt = -A3 * M ; W_obs = w Jo^T J_pt
           double Jp[6];
 #pragma unroll
@@ -348,24 +350,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
           for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int k = 0; k < 3; k++) atomicAdd(Wo + r * 3 + k, w * (Jo[r] * Jp[k] + Jo[6 + r] * Jp[3 + k]));
-        }
-        if (has_src) {
-          double Js[12];
-          pose_jac(g.A2, c.qs, 1.0, Js);
-          const int vs = pi.z;
-          if (vo < vs) {
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int cc = 0; cc < 6; cc++)
-                atomicAdd(d.H0 + (size_t)(6 * vo + r) * nc + 6 * vs + cc, w * (Jo[r] * Js[cc] + Jo[6 + r] * Js[6 + cc]));
-          } else {
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int cc = 0; cc < 6; cc++)
-                atomicAdd(d.H0 + (size_t)(6 * vs + r) * nc + 6 * vo + cc, w * (Js[r] * Jo[cc] + Js[6 + r] * Jo[6 + cc]));
-          }
         }
       }
     }
@@ -437,6 +421,82 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
   }
   const double tot = block_sum(chi_acc, red);
   if (threadIdx.x == 0) d.part[PART_CUR_CHI * MAX_PARTIALS + blockIdx.x] = tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pose_blocks: pose-pose part of the normal equations (g2o constructQuadraticForm [3P]) from the
+// per-measurement records of k_linearize.  One warp per work item {block row, block col, begin, end}: a diagonal
+// item sums U_vv (upper triangle) and g_v over measurements observed from pose v, an off-diagonal item sums the
+// observer/source cross block of one pose pair.  Lane = measurement; the 27 / 36 sums are warp-reduced and added
+// with one atomic per entry per item (items of one block are <= 128 measurements each).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pose_blocks(BaDev d)
+{
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  for (int it = gw; it < d.n_pb_items; it += nw) {
+    const int4 item = d.pb_items[it];
+    const int lo = item.x, hi = item.y;
+    const bool diag = lo == hi;
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = 0.0;
+    for (int e = item.z + lane; e < item.w; e += 32) {
+      const int m = d.pb_idx[e];
+      const double2* rec = reinterpret_cast<const double2*>(d.mrec + (size_t)MREC * m);
+      const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5];
+      const double A[6] = { r0.x, r0.y, r1.x, r1.y, r2.x, r2.y };
+      const double q[3] = { r3.x, r3.y, r4.x };
+      const double w = r4.y, we0 = r5.x, we1 = r5.y;
+      double Jo[12];
+      pose_jac(A, q, -1.0, Jo);
+      if (diag) {
+        int t = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int cc = r; cc < 6; cc++) acc[t++] += w * (Jo[r] * Jo[cc] + Jo[6 + r] * Jo[6 + cc]);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) acc[21 + r] -= Jo[r] * we0 + Jo[6 + r] * we1;
+      } else {
+        const double2 r6 = rec[6], r7 = rec[7], r8 = rec[8], r9 = rec[9], r10 = rec[10];
+        const double A2[6] = { r6.x, r6.y, r7.x, r7.y, r8.x, r8.y };
+        const double qs[3] = { r9.x, r9.y, r10.x };
+        double Js[12];
+        pose_jac(A2, qs, 1.0, Js);
+        const bool obs_first = ((int)r10.y == lo);          // block row = the smaller pose variable
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) {
+            const double v = obs_first ? (Jo[r] * Js[cc] + Jo[6 + r] * Js[6 + cc]) : (Js[r] * Jo[cc] + Js[6 + r] * Jo[6 + cc]);
+            acc[r * 6 + cc] += w * v;
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 36; i++) {
+      if (diag && i >= 27) break;
+      acc[i] = warp_sum(acc[i]);
+    }
+    // lane l adds entries l and l + 32
+#pragma unroll
+    for (int i = 0; i < 36; i++) {
+      if ((i & 31) != lane) continue;
+      if (diag) {
+        if (i < 21) {
+          int r = 0, k = i;
+          while (k >= 6 - r) { k -= 6 - r; r++; }
+          atomicAdd(d.H0 + (size_t)(6 * lo + r) * nc + 6 * lo + r + k, acc[i]);
+        } else if (i < 27) atomicAdd(d.gc + 6 * lo + (i - 21), acc[i]);
+      } else {
+        const int r = i / 6, cc = i - 6 * r;
+        atomicAdd(d.H0 + (size_t)(6 * lo + r) * nc + 6 * hi + cc, acc[i]);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -980,17 +1040,26 @@ static int lin_variant()
   static const int v = [] { const char* e = getenv("MCP_BA_LIN_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
   return v;
 }
+static void launch_pose_blocks(const BaDev& d, cudaStream_t s)
+{
+  if (d.n_pb_items <= 0) return;
+  int g = (d.n_pb_items + 3) / 4;
+  if (g > 148 * 16) g = 148 * 16;
+  k_pose_blocks<<<g, 128, 0, s>>>(d);
+}
 int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s)
 {
   const size_t stage = sizeof(double) * d.stage_doubles;
   if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
     const int g = per_point_grid(d, 4);
     k_linearize<128, 3><<<g, 128, smem / warps * 4 + stage, s>>>(d);
+    launch_pose_blocks(d, s);
     return g;
   }
   const int g = per_point_grid(d, warps);
   if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) k_linearize<256, 2><<<g, 256, smem + stage, s>>>(d);
   else k_linearize<256, 1><<<g, warps * 32, smem + stage, s>>>(d);
+  launch_pose_blocks(d, s);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)

@@ -9,6 +9,7 @@ constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;   // 2048
 constexpr int SEL_PASSES = 6;             // 6 x 11 bits >= 63 significant bits of |chi2|
 constexpr int MAX_PARTIALS = 4096;        // per-block partial sums (grid size cap for the per-point kernels)
+constexpr int MREC = 22;                  // doubles per measurement record: A(6) q(3) w we0 we1 A2(6) qs(3) obs-var
 constexpr int MAX_CAND = 4;               // speculative LM candidates evaluated concurrently
 constexpr int N_STATE = MAX_CAND + 1;     // accepted state + one trial buffer per candidate
 
@@ -76,6 +77,10 @@ struct BaDev {
   const int2* inc;               // co-visibility incidences {slot A, slot B}, bucketed by block pair
   const int4* items;             // work items {block row, block col, begin, end} into inc
   int n_items, pad_items;
+  double* mrec;                  // [n_meas][MREC] per-measurement record written by k_linearize for k_pose_blocks
+  const int* pb_idx;             // measurement indices bucketed by pose block: (v,v) diagonal blocks, then (lo,hi) observer/source pairs
+  const int4* pb_items;          // work items {block row, block col, begin, end} into pb_idx
+  int n_pb_items, pad_pb;
   double* H0;                    // [nc*nc] upper block triangle, pose-pose normal matrix (no damping)
   double* Sm;                    // [nc*nc] upper block triangle, sum_p W (V+lambda I)^-1 W^T
   double* gc;                    // [nc]
