@@ -48,6 +48,7 @@ void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
+void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
 
 struct DevBuf {
   void* p = nullptr;
@@ -95,7 +96,8 @@ struct McpBa {
     cudaEvent_t ev_done = nullptr, ev_schur = nullptr;
     int chol_epoch = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
-  cudaEvent_t ev_ready = nullptr, ev_red = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_red = nullptr, ev_ctrl = nullptr;
+  cudaStream_t copy_stream = nullptr;   // control-block read-back that does not queue behind look-ahead kernels
   int n_spec_multi = 3;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
   int n_spec = 3;                 // candidates per round (1 = no speculation)
   int spec_rounds = 0, spec_used = 0;
@@ -153,6 +155,8 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
+  MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ctrl, cudaEventDisableTiming));
+  MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int q = 1; q < MAX_CAND; q++) {
     MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cand[q].stream, cudaStreamNonBlocking));
     MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->cand[q].ev_done, cudaEventDisableTiming));
@@ -197,6 +201,8 @@ int mcp_ba_destroy(McpBa* h)
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_red) cudaEventDestroy(h->ev_red);
+  if (h->ev_ctrl) cudaEventDestroy(h->ev_ctrl);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MCP_OK;
@@ -628,13 +634,24 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   MCP_CUDA_CHECK(cudaEventRecord(h->ev0, s));
   int counter = 0;
   bool ok = true, local_abort = false;
+  // Look-ahead: most trial rounds end their outer iteration, so the next iteration's sigma selection and linearisation
+  // are enqueued right behind k_lm_control -- predicated on the device on that kernel's verdict -- and run while the
+  // host is still reading the control block back.  (Single GPU only: the multi-GPU path has collectives in between.)
+  static const bool ahead_env = [] { const char* e = getenv("MCP_BA_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+  const bool can_look_ahead = ahead_env && !multi && !single_step && !h->profiling;
+  bool next_iteration_started = false;
+  BaDev d_ahead = d;
+  d_ahead.ahead = 1;
   for (int it = 0; it < n_iter && !local_abort && !aborted() && ok; it++) {
-    if (it > 0) {
-      if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
-      if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
+    if (!next_iteration_started) {
+      if (it > 0) {
+        if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
+        if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
+      }
+      MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
+      { Prof p(h, C_LIN); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); h->launches++; }
     }
-    MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
-    { Prof p(h, C_LIN); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); }
+    next_iteration_started = false;
     if (multi) {
       launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
       NCCL_CHECK(ncclAllReduce(acc, acc, h->off_Sm, ncclDouble, ncclSum, h->comm, s));
@@ -698,10 +715,21 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand, ncclDouble, ncclSum, h->comm, s));
       { Prof p(h, C_CONTROL); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
-      if ((rc = sync_ctrl(h))) return rc;
+      const bool ahead = can_look_ahead && it + 1 < n_iter;
+      if (ahead) {
+        // the control block is read back on a side stream so that the copy does not queue behind the look-ahead kernels
+        MCP_CUDA_CHECK(cudaEventRecord(h->ev_ctrl, s));
+        MCP_CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_ctrl, 0));
+        MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (h->cfg.use_robust) h->launches += launch_select_sigma(d_ahead, -1, 0, s);
+        launch_zero_acc(d_ahead, acc, h->acc_doubles, s);
+        n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s);
+        h->launches += 3;
+        MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
+      } else if ((rc = sync_ctrl(h))) return rc;
       if (c.cand_used > 1) h->spec_used++;
       if (single_step) break;
-      if (c.stop_trials) break;
+      if (c.stop_trials) { next_iteration_started = ahead && !c.terminate && !c.conv_mag && !c.conv_res; break; }
       if (aborted()) {
         // the trial loop ends on terminate(); close the outer iteration bookkeeping like g2o does
         c.iter++; c.total_trials += c.qmax; c.qmax = 0;

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int gl = lane & (LG - 1), grp = lane / LG;
   const unsigned gmask = ((1u << LG) - 1u) << (grp * LG);
+  if (lookahead_skip(d)) return;
   double* Wsm = smem + d.stage_doubles + (size_t)(wid * PPW + grp) * d.max_slots * 18;
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pose_blocks(BaDev d)
 {
+  if (lookahead_skip(d)) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int nc = d.nc;
@@ -599,6 +601,7 @@ __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int wh
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pass, int mode)
 {
+  if (lookahead_skip(d)) return;
   __shared__ unsigned hist[SEL_BINS];
   __shared__ unsigned wsum[8];
   __shared__ int s_last;
@@ -692,6 +695,7 @@ constexpr size_t SELC_SMEM = sizeof(unsigned) * (size_t)(SELC_COPIES + 2) * SEL_
 
 __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode)
 {
+  if (lookahead_skip(d)) return;                                  // uniform over the whole cluster
   namespace cg = cooperative_groups;
   // The first digit is the exponent: a handful of hot bins.  Same-address shared-memory atomics serialise, so every
   // CTA keeps SELC_COPIES replicas of the histogram (replica = lane & 7, interleaved so that replicas of one bin sit in
@@ -1040,6 +1044,13 @@ static int lin_variant()
   static const int v = [] { const char* e = getenv("MCP_BA_LIN_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
   return v;
 }
+// zeroes the linearisation accumulators [H0 | gc | red] (a memset that honours the look-ahead predicate)
+__global__ void k_zero_acc(BaDev d, double* acc, size_t n)
+{
+  if (lookahead_skip(d)) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = 0.0;
+}
+void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s) { k_zero_acc<<<148, 512, 0, s>>>(d, acc, n); }
 static void launch_pose_blocks(const BaDev& d, cudaStream_t s)
 {
   if (d.n_pb_items <= 0) return;

@@ -67,7 +67,8 @@ struct BaDev {
   double* pose[N_STATE];              // [n_pose*12]  accepted state + one trial buffer per speculative candidate
   double* pt[N_STATE];               // [n_pt*3]
   double* chi2[N_STATE];              // [n_meas] signed as EdgeChainMeas::chi2
-  int cand, pad_cand;            // speculative candidate index of this launch (c: lambda after c rejections)
+  int cand, ahead;               // speculative candidate index of this launch (c: lambda after c rejections); ahead = 1: this launch
+                                 // was enqueued before the host knew the trial loop ended (see next_iteration_started)
   double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
   double* gp;                    // [n_pt*3]
   double* W;                     // [n_slots*18] 6x3 row-major
@@ -106,6 +107,14 @@ __device__ __forceinline__ double trial_lambda(const BaDev& d)
   double l = d.ctrl->lambda, ni = d.ctrl->ni;
   for (int c = 0; c < d.cand; c++) { l *= ni; ni *= 2; }
   return l;
+}
+// Look-ahead launches (next outer iteration's sigma / linearisation enqueued right behind k_lm_control, before the host
+// has read the control block) run only if that k_lm_control closed the trial loop without ending the optimisation.
+__device__ __forceinline__ bool lookahead_skip(const BaDev& d)
+{
+  if (!d.ahead) return false;
+  const BaCtrl* c = d.ctrl;
+  return !(c->stop_trials && !c->terminate && !c->conv_mag && !c->conv_res);
 }
 __device__ __forceinline__ int trial_buffer(const BaDev& d, int cur) { return (cur + 1 + d.cand) % N_STATE; }
 
