@@ -87,7 +87,7 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items;
   // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
   struct Cand {
     DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
@@ -182,7 +182,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items };
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
   for (int q = 1; q < MAX_CAND; q++) {
@@ -397,9 +397,59 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     }
   }
 
+  // work lists of k_schur_rows: this rank's (point, slot) entries sorted by pose variable; entry = {slot, number of
+  // slots from it to the end of its point}; groups of entries that fit one staging buffer; items = runs of groups of
+  // one pose variable sized so that every resident warp gets about one item
+  std::vector<int2> rs_ent;
+  std::vector<int> rs_grp;
+  std::vector<int4> rs_items;
+  int rs_nblk = 1;
+  // MCP_BA_SCHUR: 1 (default) pair gathers with TMA, 2 staged pair gathers, 0 row-wise (k_schur_rows; measured slower
+  // than the pair kernel at cfg2 -- profiles/README.md -- kept selectable and parity-tested)
+  int schur_mode = 1;
+  { const char* e = getenv("MCP_BA_SCHUR"); if (e && e[0]) schur_mode = atoi(e); if (getenv("MCP_BA_SCHUR_V1") && getenv("MCP_BA_SCHUR_V1")[0] == '1') schur_mode = 2; }
+  if (schur_mode < 0 || schur_mode > 2) schur_mode = 1;
+  if (max_slots > 32 && schur_mode == 0) schur_mode = 1;       // an entry must fit one staging buffer
+  if (schur_mode == 0) {
+    const int s_lo = pt_slot_off[h->part_pt[h->rank]], s_hi = pt_slot_off[h->part_pt[h->rank + 1]];
+    std::vector<int> order;
+    order.reserve((size_t)std::max(s_hi - s_lo, 0));
+    for (int sidx = s_lo; sidx < s_hi; sidx++) order.push_back(sidx);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slot_var[x] < slot_var[y]; });
+    const int target = std::max(16, (int)((order.size() + 148 * 8 - 1) / (148 * 8)));     // entries per item
+    size_t i = 0;
+    while (i < order.size()) {
+      size_t j = i;
+      const int a = slot_var[order[i]];
+      while (j < order.size() && slot_var[order[j]] == a) j++;
+      for (size_t b = i; b < j; b += (size_t)target) {
+        const size_t e_end = std::min(b + (size_t)target, j);
+        const int g_begin = (int)rs_grp.size();
+        size_t k = b;
+        while (k < e_end) {
+          int bytes = 0, cnt = 0;
+          const int first = (int)rs_ent.size();
+          while (k < e_end && cnt < RS_MAXE) {
+            const int sidx = order[k];
+            const int nb = pt_slot_off[slot_pt[sidx] + 1] - sidx;
+            if (cnt > 0 && bytes + 192 + 144 * nb > RS_BYTES) break;
+            bytes += 192 + 144 * nb;
+            rs_ent.push_back(make_int2(sidx, nb));
+            rs_nblk = std::max(rs_nblk, slot_var[sidx + nb - 1] - a + 1);
+            cnt++; k++;
+          }
+          rs_grp.push_back((first << 4) | cnt);
+        }
+        rs_items.push_back(make_int4(a, g_begin, (int)rs_grp.size(), 0));
+      }
+      i = j;
+    }
+  }
+
   int rc;
 #define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
   UP(h->b_pb_idx, pb_idx); UP(h->b_pb_items, pb_items);
+  UP(h->b_rs_ent, rs_ent); UP(h->b_rs_grp, rs_grp); UP(h->b_rs_items, rs_items);
   if ((rc = h->b_mrec.ensure(sizeof(double) * MREC * (size_t)std::max(n_meas, 1)))) return rc;
   UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_order, pt_order); UP(h->b_pt_meas_off, pt_meas_off);
   UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_slot_pt, slot_pt); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
@@ -464,6 +514,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
   d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
+  d.rs_ent = h->b_rs_ent.as<int2>(); d.rs_grp = h->b_rs_grp.as<int>(); d.rs_items = h->b_rs_items.as<int4>(); d.n_rs_items = (int)rs_items.size();
+  d.schur_mode = schur_mode; d.rs_nblk = rs_nblk;
   d.mrec = h->b_mrec.as<double>(); d.pb_idx = h->b_pb_idx.as<int>(); d.pb_items = h->b_pb_items.as<int4>(); d.n_pb_items = (int)pb_items.size();
   d.sel_state = h->b_sel.as<unsigned long long>();
   d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
@@ -503,8 +555,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1;
   c.sel_n = n_meas; c.sel_rank = n_meas / 2;
   MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
-  {
-    // co-visibility lists for the gather-based Schur reduction (ba_schur.cu), built on the device
+  if (schur_mode != 0) {
+    // co-visibility lists for the pair-gather Schur kernels (ba_schur.cu), built on the device
     const int n_pairs = npv * (npv + 1) / 2;
     if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
     MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 1), h->stream));

@@ -261,6 +261,157 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_schur_rows: row-wise formulation.  The pair kernels above fetch two small records per (point, pose pair)
+// incidence -- 870 k bulk copies of 144-192 bytes per launch at 200 KF / 10 k points, and the kernel runs at the
+// TMA's issue rate, not at L2 bandwidth.  Here a work item is ONE pose variable a and a run of the (point, slot)
+// entries that observe it.  Per entry the warp fetches Y_a (192 B) and the W records of the point's slots from a to
+// the end of the point -- contiguous, because the slots of a point are stored in ascending pose order -- with two
+// bulk copies, and adds the blocks Y_a W_b^T for every b >= a of that point with one fp64 tensor-core MMA each
+// (m8n8k4: rows/cols 6,7 and k = 3 are padding).  The blocks of row a accumulate in a per-warp shared-memory strip
+// (every lane owns fixed fragment positions: no synchronisation), flushed with one atomic per touched entry.
+// One tenth of the copies, the same bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_schur_rows(BaDev d)
+{
+  const int nblk = d.rs_nblk;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const size_t acc_bytes = (size_t)(nblk + 8) * 48 * sizeof(double);
+  const size_t per_warp = acc_bytes + 2 * RS_BYTES + 2 * 64 * sizeof(int) + 2 * sizeof(unsigned long long);
+  unsigned char* base = smem_raw + per_warp * wid;
+  double* acc = reinterpret_cast<double*>(base);
+  unsigned char* stg = base + acc_bytes;
+  int* sv = reinterpret_cast<int*>(stg + 2 * RS_BYTES);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sv + 128);
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int i = lane; i < (nblk + 8) * 48; i += 32) acc[i] = 0.0;
+  __syncwarp();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  const int g = lane >> 2, kk = lane & 3;
+  const bool fvalid = g < 6 && kk < 3;
+  unsigned phase[2] = { 0u, 0u };
+
+  for (int it = gw; it < d.n_rs_items; it += nw) {
+    const int4 item = d.rs_items[it];
+    const int a = item.x, n_grp = item.z - item.y;
+    double accz = 0.0;
+    // lane k < count of a group holds entry k: {slot, number of slots to the end of the point}
+    auto load_ent = [&](int grp, int& cnt) -> int2 {
+      int2 e = make_int2(0, 0);
+      cnt = 0;
+      if (grp < n_grp) {
+        const int gd = __ldg(d.rs_grp + item.y + grp);
+        cnt = gd & 15;
+        if (lane < cnt) e = __ldg(d.rs_ent + (gd >> 4) + lane);
+      }
+      return e;
+    };
+    // byte offset of entry `lane` inside the staging buffer / index of its first block in the sv list
+    auto scan = [&](int2 e, int cnt, int& off, int& pre) {
+      const int sz = lane < cnt ? 192 + 144 * e.y : 0, nb = lane < cnt ? e.y : 0;
+      int io = sz, ip = nb;
+#pragma unroll
+      for (int o = 1; o < RS_MAXE; o <<= 1) {
+        const int to = __shfl_up_sync(0xffffffffu, io, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
+        if (lane >= o) { io += to; ip += tp; }
+      }
+      off = io - sz; pre = ip - nb;
+    };
+    // issue the copies of one group; returns the block indices (pose variable - a) this lane stages later
+    auto issue = [&](int2 e, int cnt, int buf, int& v0, int& v1) {
+      int off, pre;
+      scan(e, cnt, off, pre);
+      const int tot_bytes = __shfl_sync(0xffffffffu, off + (lane < cnt ? 192 + 144 * e.y : 0), cnt - 1);
+      const int tot_nb = __shfl_sync(0xffffffffu, pre + (lane < cnt ? e.y : 0), cnt - 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&bars[buf], (unsigned)tot_bytes);
+      __syncwarp();
+      if (lane < cnt) {
+        unsigned char* dst = stg + (size_t)buf * RS_BYTES + off;
+        bulk_g2s(dst, d.Y + 24 * (size_t)e.x, 192u, &bars[buf]);
+        bulk_g2s(dst + 192, d.W + 18 * (size_t)e.x, 144u * (unsigned)e.y, &bars[buf]);
+      }
+      // block index of (entry k, j): slot_var[slot_k + j] - a, flattened in entry order
+      v0 = 0; v1 = 0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int o = lane + 32 * h;
+        int sl = -1;
+#pragma unroll
+        for (int k = 0; k < RS_MAXE; k++) {
+          const int pk = __shfl_sync(0xffffffffu, pre, k), nk = __shfl_sync(0xffffffffu, e.y, k), sk = __shfl_sync(0xffffffffu, e.x, k);
+          if (k < cnt && o >= pk && o < pk + nk) sl = sk + (o - pk);
+        }
+        const int v = (sl >= 0 && o < tot_nb) ? __ldg(d.slot_var + sl) - a : 0;
+        if (h == 0) v0 = v; else v1 = v;
+      }
+    };
+
+    int cnt_cur, cnt_nxt;
+    int2 e_cur = load_ent(0, cnt_cur);
+    int2 e_nxt = load_ent(1, cnt_nxt);
+    int v0c, v1c, v0n = 0, v1n = 0;
+    issue(e_cur, cnt_cur, 0, v0c, v1c);
+    for (int grp = 0; grp < n_grp; grp++) {
+      const int buf = grp & 1;
+      if (grp + 1 < n_grp) issue(e_nxt, cnt_nxt, buf ^ 1, v0n, v1n);
+      int cnt_n2;
+      const int2 e_n2 = load_ent(grp + 2, cnt_n2);
+      int off, pre;
+      scan(e_cur, cnt_cur, off, pre);
+      sv[buf * 64 + lane] = v0c; sv[buf * 64 + 32 + lane] = v1c;
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      __syncwarp();
+      const unsigned char* sb = stg + (size_t)buf * RS_BYTES;
+      for (int k = 0; k < cnt_cur; k++) {
+        const int ok = __shfl_sync(0xffffffffu, off, k), pk = __shfl_sync(0xffffffffu, pre, k), nk = __shfl_sync(0xffffffffu, e_cur.y, k);
+        const double* Yb = reinterpret_cast<const double*>(sb + ok);
+        const double av = fvalid ? Yb[g * 3 + kk] : 0.0;
+        if (lane < 6) accz += Yb[18 + lane];
+        // the blocks of one entry are distinct (a point lists a pose once): eight read-modify-write updates of the
+        // accumulator strip are batched so that their shared-memory round trips overlap (unused lanes of a batch
+        // go to the spare blocks behind the strip)
+        for (int j0 = 0; j0 < nk; j0 += 8) {
+          double bv[8];
+          double2 c[8];
+          double2* cp[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const bool on = j0 + u < nk;
+            const double* Wj = Yb + 24 + 18 * (j0 + u);
+            bv[u] = (fvalid && on) ? Wj[g * 3 + kk] : 0.0;
+            const int blk = on ? sv[buf * 64 + pk + j0 + u] : nblk + u;
+            cp[u] = reinterpret_cast<double2*>(acc + (size_t)blk * 48 + g * 8 + 2 * kk);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) c[u] = fvalid ? *cp[u] : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < 8; u++) dmma_m8n8k4(c[u].x, c[u].y, av, bv[u]);
+#pragma unroll
+          for (int u = 0; u < 8; u++) if (fvalid) *cp[u] = c[u];
+        }
+      }
+      __syncwarp();
+      e_cur = e_nxt; cnt_cur = cnt_nxt; v0c = v0n; v1c = v1n;
+      e_nxt = e_n2; cnt_nxt = cnt_n2;
+    }
+    // flush row a: blocks (a, a + blk)
+    const int nb_row = min(nblk, d.n_pose_var - a);
+    for (int e = lane; e < nb_row * 36; e += 32) {
+      const int blk = e / 36, rc = e - 36 * blk, r = rc / 6, c = rc - 6 * r;
+      double* ap = acc + (size_t)blk * 48 + r * 8 + c;
+      const double v = *ap;
+      if (v != 0.0) { atomicAdd(d.Sm + (size_t)(6 * a + r) * nc + 6 * (a + blk) + c, v); *ap = 0.0; }
+    }
+    if (lane < 6) atomicAdd(d.rm + 6 * a + lane, accz);
+    __syncwarp();
+  }
+}
+
 // ChainBundle's point-depth covariance (src/ChainBundle.cc:1401-1448; [3P] SparseOptimizer::computeMarginals on the
 // undamped Hessian of the last buildSystem): (H^-1)_pp = V^-1 + Y^T S^-1 Y with Y = W V^-1 (lambda = 0) and
 // S = H_cc - sum W V^-1 W^T.  Only the (2,2) entry (radial direction) of every non-fixed point is needed.
@@ -355,8 +506,19 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s)
   if (g1 < 1) g1 = 1;
   if (g1 > 148 * 8) g1 = 148 * 8;
   k_schur_y<<<g1, 256, 0, s>>>(d);
-  static int use_v1 = -1;
-  if (use_v1 < 0) { const char* e = getenv("MCP_BA_SCHUR_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  if (d.schur_mode == 0) {
+    const size_t per_warp = (size_t)(d.rs_nblk + 8) * 48 * sizeof(double) + 2 * RS_BYTES + 2 * 64 * sizeof(int) + 2 * sizeof(unsigned long long);
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
+    static size_t attr = 0;
+    if (smem > attr) { cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+    int g = (d.n_rs_items + warps - 1) / warps;
+    if (g < 1) g = 1;
+    k_schur_rows<<<g, warps * 32, smem, s>>>(d);
+    return;
+  }
+  const int use_v1 = d.schur_mode == 2;
   int g2 = (d.n_items + 3) / 4;
   if (g2 < 1) g2 = 1;
   if (use_v1) {

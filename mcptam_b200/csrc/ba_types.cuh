@@ -9,6 +9,8 @@ constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;   // 2048
 constexpr int SEL_PASSES = 6;             // 6 x 11 bits >= 63 significant bits of |chi2|
 constexpr int MAX_PARTIALS = 4096;        // per-block partial sums (grid size cap for the per-point kernels)
+constexpr int RS_BYTES = 6144;            // staging bytes per buffer of k_schur_rows
+constexpr int RS_MAXE = 8;                // entries (point, pose slot) per group
 constexpr int MREC = 22;                  // doubles per measurement record: A(6) q(3) w we0 we1 A2(6) qs(3) obs-var
 constexpr int MAX_CAND = 4;               // speculative LM candidates evaluated concurrently
 constexpr int N_STATE = MAX_CAND + 1;     // accepted state + one trial buffer per candidate
@@ -78,6 +80,11 @@ struct BaDev {
   const int2* inc;               // co-visibility incidences {slot A, slot B}, bucketed by block pair
   const int4* items;             // work items {block row, block col, begin, end} into inc
   int n_items, pad_items;
+  const int2* rs_ent;            // row-wise Schur lists: {slot, slots from it to the end of its point}, sorted by pose variable
+  const int* rs_grp;             // groups of <= RS_MAXE entries that fit one staging buffer: (first entry << 4) | count
+  const int4* rs_items;          // work items {pose variable a, first group, end group, 0}
+  int n_rs_items, schur_mode;    // schur_mode 0: row-wise (k_schur_rows), 1: pair gathers with TMA, 2: staged pair gathers
+  int rs_nblk, pad_rs;           // blocks per accumulator strip: 1 + the largest (pose variable - a) inside one point
   double* mrec;                  // [n_meas][MREC] per-measurement record written by k_linearize for k_pose_blocks
   const int* pb_idx;             // measurement indices bucketed by pose block: (v,v) diagonal blocks, then (lo,hi) observer/source pairs
   const int4* pb_items;          // work items {block row, block col, begin, end} into pb_idx

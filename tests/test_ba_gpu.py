@@ -69,6 +69,29 @@ def test_lm_step_parity(capi, cfg, seed, lam):
         assert rc == 0 and _rel(d_g, d_f) < 1e-6
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("cfg,seed,lam", [("tiny", 0, 10.0), ("cfg1", 0, 50.0), ("cfg2", 0, 100.0)])
+def test_schur_variants_parity(capi, monkeypatch, cfg, seed, lam, mode):
+    """The non-default Schur reductions (MCP_BA_SCHUR=0 row-wise k_schur_rows, =2 staged pair gathers; the mode is
+    read by mcp_ba_load) give the same LM update as the oracle and as the default TMA pair kernel."""
+    from oracle.oracle import OracleBA
+    prob = _mk(cfg, seed)
+    o = OracleBA(prob)
+    rc, d_o, _, chi_o = o.lm_step(lam, -1.0, 0)
+    assert rc == 0
+    monkeypatch.delenv("MCP_BA_SCHUR", raising=False)
+    g1 = capi.BaHandle()
+    g1.load(prob)
+    d_1, _, _ = g1.lm_step(lam, -1.0)
+    monkeypatch.setenv("MCP_BA_SCHUR", mode)
+    g = capi.BaHandle()
+    g.load(prob)
+    d_g, _, chi_g = g.lm_step(lam, -1.0)
+    assert abs(chi_g - chi_o) <= 1e-9 * abs(chi_o)
+    assert _rel(d_g, d_o) < 1e-6
+    assert _rel(d_g, d_1) < 1e-9
+
+
 @pytest.mark.parametrize("cfg,seed,iters", [("tiny", 0, 12), ("tiny", 2, 12), ("cfg1", 0, 10), ("cfg1", 1, 10)])
 def test_compute_parity(capi, cfg, seed, iters):
     from oracle.oracle import OracleBA
