@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libmcptam_b200.so")
+PREP_LIB = os.path.join(OUT_DIR, "libmcptam_prep.so")      # CPU-only shim around ba_prep.hpp for the host-logic tests
 SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_schur.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"] + (["-DMCP_FE_DEBUG"] if os.environ.get("MCP_FE_DEBUG") else [])
@@ -49,6 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc, "-arch=sm_100a", "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
     subprocess.check_call(link)
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-Wall", "-fPIC", "-shared",
+                           os.path.join(CSRC, "ba_prep_cpu.cpp"), "-o", PREP_LIB])
     return LIB
 
 

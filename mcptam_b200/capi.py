@@ -233,6 +233,52 @@ def ba_partition(n_pt, meas_pt, world):
     return out
 
 
+class _PrepView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pose_var pt_var pt_info pt_order pt_meas_off pt_slot_off slot_var slot_pt meas_xy meas_info "
+                                          "meas_a meas_b pb_idx pb_items rs_ent rs_grp rs_items meas_orig part_pt part_meas").split()] + \
+               [(n, C.c_longlong) for n in "n_pb_idx n_pb_items n_rs_ent n_rs_grp n_rs_items n_inc".split()] + \
+               [(n, C.c_int) for n in "npv nptv n_slots max_slots rs_nblk pad".split()] + [("err", C.c_char_p)]
+
+
+def ba_prepare(prob, rank=0, world=1, want_rows=False, reps=1):
+    """Host marshalling of mcp_ba_load (csrc/ba_prep.hpp) run on the CPU through the test shim libmcptam_prep.so.
+    Returns (dict of numpy arrays / scalars, best time in ms).  Raises McpError with the message mcp_ba_load would set."""
+    from . import build
+    if not os.path.exists(build.PREP_LIB):
+        build.build(force=True)
+    L = C.CDLL(build.PREP_LIB)
+    k = [np.ascontiguousarray(prob.pose_fixed, np.uint8), np.ascontiguousarray(prob.pt_chain, np.int32),
+         np.ascontiguousarray(prob.pt_fixed, np.uint8), np.ascontiguousarray(prob.meas_xy, np.float64),
+         np.ascontiguousarray(prob.meas_chain, np.int32), np.ascontiguousarray(prob.meas_pt, np.int32),
+         np.ascontiguousarray(prob.meas_noise, np.float64), np.ascontiguousarray(prob.meas_cam, np.int32)]
+    v, ms = _PrepView(), C.c_double()
+    L.mcp_prep_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + \
+                              [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    rc = L.mcp_prep_run(len(prob.cams), prob.n_pose, _p(k[0]), prob.n_pt, _p(k[1]), _p(k[2]), prob.n_meas, _p(k[3]), _p(k[4]),
+                        _p(k[5]), _p(k[6]), _p(k[7]), rank, world, int(want_rows), reps, C.cast(C.byref(ms), C.c_void_p),
+                        C.cast(C.byref(v), C.c_void_p))
+    if rc != 0:
+        raise McpError(rc, (v.err or b"").decode())
+
+    def arr(ptr, n, dt=np.int32, cols=1):
+        if not ptr or n == 0:
+            return np.zeros((0, cols) if cols > 1 else 0, dt)
+        ct = C.c_double if dt == np.float64 else C.c_int
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), (int(n) * cols,)).copy()
+        return a.reshape(-1, cols) if cols > 1 else a
+
+    n_pt, n_meas = prob.n_pt, prob.n_meas
+    out = dict(pose_var=arr(v.pose_var, prob.n_pose), pt_var=arr(v.pt_var, n_pt), pt_info=arr(v.pt_info, n_pt, cols=4),
+               pt_order=arr(v.pt_order, n_pt), pt_meas_off=arr(v.pt_meas_off, n_pt + 1), pt_slot_off=arr(v.pt_slot_off, n_pt + 1),
+               slot_var=arr(v.slot_var, v.n_slots), slot_pt=arr(v.slot_pt, v.n_slots), meas_xy=arr(v.meas_xy, n_meas, np.float64, 2),
+               meas_info=arr(v.meas_info, n_meas, np.float64), meas_a=arr(v.meas_a, n_meas, cols=4), meas_b=arr(v.meas_b, n_meas, cols=4),
+               pb_idx=arr(v.pb_idx, v.n_pb_idx), pb_items=arr(v.pb_items, v.n_pb_items, cols=4), rs_ent=arr(v.rs_ent, v.n_rs_ent, cols=2),
+               rs_grp=arr(v.rs_grp, v.n_rs_grp), rs_items=arr(v.rs_items, v.n_rs_items, cols=4), meas_orig=arr(v.meas_orig, n_meas),
+               part_pt=arr(v.part_pt, world + 1), part_meas=arr(v.part_meas, world + 1), n_inc=int(v.n_inc), npv=v.npv, nptv=v.nptv,
+               n_slots=v.n_slots, max_slots=v.max_slots, rs_nblk=v.rs_nblk)
+    return out, ms.value
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     check(lib().mcp_nccl_unique_id(buf))

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <vector>
 
+#include "ba_prep.hpp"
 #include "ba_types.cuh"
 
 namespace mcp {
@@ -46,6 +47,7 @@ int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* 
 int stage_doubles_for(int n_pose, int n_cam);
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
+void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
@@ -67,6 +69,15 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// pinned host storage for the marshalling output (ba_prep.hpp): uploads from it are truly asynchronous
+static void* pinned_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+static void pinned_release(void* p) { cudaFreeHost(p); }
+static const PrepAlloc g_pinned_alloc = { pinned_alloc, pinned_release };
 
 enum Cat { C_SELECT = 0, C_LIN, C_SCHUR, C_SOLVE, C_BACKSUB, C_CONTROL, C_OTHER, C_N };
 
@@ -106,6 +117,7 @@ struct McpBa {
   BaCtrl* ctrl_host = nullptr;   // pinned
   int* flags_host = nullptr;     // pinned, n_meas
   size_t flags_cap = 0;
+  BaPrep prep;                   // host marshalling output in pinned memory, pooled across loads
   std::vector<int> meas_orig;    // sorted position -> original index
   std::vector<int32_t> outliers;
   // multi-GPU
@@ -196,6 +208,7 @@ int mcp_ba_destroy(McpBa* h)
   }
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
   if (h->flags_host) cudaFreeHost(h->flags_host);
+  h->prep.free_all(g_pinned_alloc);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -243,27 +256,6 @@ static int upload(McpBa* h, DevBuf& b, const void* src, size_t bytes)
   return MCP_OK;
 }
 
-// contiguous, measurement-count-balanced partition of points; pure host code
-static void partition_points(const int* pt_meas_off, int n_pt, int world, int* part_pt)
-{
-  const long long total = pt_meas_off[n_pt] + (long long)n_pt * 4;   // weight: measurements + per-point overhead
-  int p = 0;
-  part_pt[0] = 0;
-  for (int r = 1; r < world; r++) {
-    const long long target = total * r / world;
-    while (p < n_pt && (long long)pt_meas_off[p] + (long long)p * 4 < target) p++;
-    part_pt[r] = p;
-  }
-  part_pt[world] = n_pt;
-}
-static void compute_partition(McpBa* h, const std::vector<int>& pt_meas_off, int n_pt)
-{
-  h->part_pt.assign(h->world + 1, 0);
-  h->part_meas.assign(h->world + 1, 0);
-  partition_points(pt_meas_off.data(), n_pt, h->world, h->part_pt.data());
-  for (int r = 0; r <= h->world; r++) h->part_meas[r] = pt_meas_off[h->part_pt[r]];
-}
-
 int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* pose_fixed, int32_t n_pt,
                 const double* pt_xyz, const int32_t* pt_chain, const uint8_t* pt_fixed, int32_t n_meas,
                 const double* meas_xy, const int32_t* meas_chain, const int32_t* meas_pt, const double* meas_noise,
@@ -278,192 +270,59 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   }
   h->loaded = false;
   const int n_cam = (int)h->cams.size();
-  std::vector<int> pose_var(n_pose);
-  int npv = 0;
-  for (int i = 0; i < n_pose; i++) pose_var[i] = pose_fixed[i] ? -1 : npv++;
-  for (int p = 0; p < n_pt; p++) {
-    const int a = pt_chain[2 * p], b = pt_chain[2 * p + 1];
-    if (a < 0 || a >= n_pose || b >= n_pose) { set_last_error("point %d: chain index out of range", p); return MCP_ERR_INVALID; }
-    if (b >= 0 && !pose_fixed[b]) { set_last_error("point %d: movable second chain link is not supported", p); return MCP_ERR_UNSUPPORTED; }
-  }
-  for (int m = 0; m < n_meas; m++) {
-    const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
-    if (a < 0 || a >= n_pose || b >= n_pose) { set_last_error("measurement %d: chain index out of range", m); return MCP_ERR_INVALID; }
-    if (b >= 0 && !pose_fixed[b]) { set_last_error("measurement %d: movable second chain link is not supported", m); return MCP_ERR_UNSUPPORTED; }
-    if (meas_pt[m] < 0 || meas_pt[m] >= n_pt) { set_last_error("measurement %d: point index out of range", m); return MCP_ERR_INVALID; }
-    if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) { set_last_error("measurement %d: camera index out of range", m); return MCP_ERR_INVALID; }
-    if (!(meas_noise[m] > 0)) { set_last_error("measurement %d: noise must be > 0", m); return MCP_ERR_INVALID; }
-  }
-  // sort measurements by point (stable counting sort)
-  std::vector<int> pt_meas_off(n_pt + 1, 0);
-  for (int m = 0; m < n_meas; m++) pt_meas_off[meas_pt[m] + 1]++;
-  for (int p = 0; p < n_pt; p++) pt_meas_off[p + 1] += pt_meas_off[p];
-  std::vector<int> cursor(pt_meas_off.begin(), pt_meas_off.end() - 1);
-  h->meas_orig.assign(n_meas, 0);
-  for (int m = 0; m < n_meas; m++) h->meas_orig[cursor[meas_pt[m]]++] = m;
-
-  std::vector<int> pt_var(n_pt);
-  int nptv = 0;
-  for (int p = 0; p < n_pt; p++) pt_var[p] = pt_fixed[p] ? -1 : nptv++;
-  std::vector<int4> pt_info(n_pt), meas_a(n_meas), meas_b(n_meas);
-  std::vector<double2> mxy(n_meas);
-  std::vector<double> minfo(n_meas);
-  std::vector<int> pt_slot_off(n_pt + 1, 0), slot_var, slot_pt;
-  slot_var.reserve((size_t)n_meas + n_pt);
-  int max_slots = 1;
-  std::vector<int> tmp;
-  for (int p = 0; p < n_pt; p++) {
-    const int src0 = pt_chain[2 * p], src1 = pt_chain[2 * p + 1];
-    const int src_var = pose_var[src0];
-    bool any_src = false;
-    tmp.clear();
-    for (int q = pt_meas_off[p]; q < pt_meas_off[p + 1]; q++) {
-      const int m = h->meas_orig[q];
-      const int obs0 = meas_chain[2 * m];
-      const bool has_jac = (obs0 != src0);                 // PoseChainHelper::MoveTogether at depth 0
-      const int ov = has_jac ? pose_var[obs0] : -1;
-      const bool has_src = has_jac && src_var >= 0;
-      any_src |= has_src;
-      if (ov >= 0) tmp.push_back(ov);
-      meas_a[q] = make_int4(obs0, meas_chain[2 * m + 1], meas_cam[m], m);
-      meas_b[q] = make_int4(ov, -1, has_src ? 1 : 0, p);
-      mxy[q] = make_double2(meas_xy[2 * m], meas_xy[2 * m + 1]);
-      minfo[q] = 1.0 / std::sqrt(meas_noise[m]);          // src/ChainBundle.cc:1244-1245
-    }
-    int src_slot = -1;
-    pt_slot_off[p] = (int)slot_var.size();
-    if (pt_var[p] >= 0) {
-      if (any_src) tmp.push_back(src_var);
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      for (int v : tmp) { slot_var.push_back(v); slot_pt.push_back(p); }
-      const int K = (int)tmp.size();
-      max_slots = std::max(max_slots, K);
-      for (int q = pt_meas_off[p]; q < pt_meas_off[p + 1]; q++)
-        if (meas_b[q].x >= 0) meas_b[q].y = (int)(std::lower_bound(tmp.begin(), tmp.end(), meas_b[q].x) - tmp.begin());
-      if (any_src) src_slot = (int)(std::lower_bound(tmp.begin(), tmp.end(), src_var) - tmp.begin());
-    }
-    pt_info[p] = make_int4(src0, src1, src_var, src_slot);
-  }
-  pt_slot_off[n_pt] = (int)slot_var.size();
-  const int n_slots = (int)slot_var.size();
-  const int nc = 6 * npv;
-  if (nc > chol_max_n()) {
-    set_last_error("mcp_ba_load: %d movable poses exceed the dense solver capacity (%d rows)", npv, chol_max_n());
-    return MCP_ERR_UNSUPPORTED;
-  }
   cudaSetDevice(h->device);
-  const int stage_doubles = stage_doubles_for(n_pose, n_cam);
-  if (configure_kernels(max_slots, stage_doubles, &h->lin_warps, &h->lin_smem) != 0) {
-    set_last_error("mcp_ba_load: a point is observed from %d movable keyframes, more than the kernel supports", max_slots);
-    return MCP_ERR_UNSUPPORTED;
-  }
-  compute_partition(h, pt_meas_off, n_pt);
-  // visiting order of the per-point kernels: inside every rank's range, heaviest points first (stable)
-  std::vector<int> pt_order((size_t)std::max(n_pt, 1), 0);
-  for (int q = 0; q < n_pt; q++) pt_order[q] = q;
-  for (int r = 0; r < h->world; r++)
-    std::stable_sort(pt_order.begin() + h->part_pt[r], pt_order.begin() + h->part_pt[r + 1], [&](int a, int b) {
-      return pt_meas_off[a + 1] - pt_meas_off[a] > pt_meas_off[b + 1] - pt_meas_off[b];
-    });
-
-  // work lists of k_pose_blocks: this rank's measurements bucketed by the pose block they contribute to
-  // ((v,v): observed from movable pose v; (lo,hi): observer / source pair), cut into items of <= 128 measurements
-  std::vector<int> pb_idx;
-  std::vector<int4> pb_items;
-  {
-    const int m_lo = h->part_meas[h->rank], m_hi = h->part_meas[h->rank + 1];
-    std::vector<std::pair<long long, int> > keyed;
-    keyed.reserve((size_t)(m_hi - m_lo) * 2);
-    for (int q = m_lo; q < m_hi; q++) {
-      const int vo = meas_b[q].x;
-      if (vo < 0) continue;
-      keyed.emplace_back((long long)vo * npv + vo, q);
-      if (meas_b[q].z) {
-        const int vs = pt_info[meas_b[q].w].z;
-        keyed.emplace_back((long long)std::min(vo, vs) * npv + std::max(vo, vs), q);
-      }
-    }
-    std::sort(keyed.begin(), keyed.end());
-    pb_idx.resize(keyed.size());
-    const int CH = 128;
-    for (size_t i = 0; i < keyed.size();) {
-      size_t j = i;
-      while (j < keyed.size() && keyed[j].first == keyed[i].first) j++;
-      const int lo = (int)(keyed[i].first / npv), hi = (int)(keyed[i].first % npv);
-      for (size_t b = i; b < j; b += CH) pb_items.push_back(make_int4(lo, hi, (int)b, (int)std::min(b + CH, j)));
-      for (size_t k = i; k < j; k++) pb_idx[k] = keyed[k].second;
-      i = j;
-    }
-  }
-
-  // work lists of k_schur_rows: this rank's (point, slot) entries sorted by pose variable; entry = {slot, number of
-  // slots from it to the end of its point}; groups of entries that fit one staging buffer; items = runs of groups of
-  // one pose variable sized so that every resident warp gets about one item
-  std::vector<int2> rs_ent;
-  std::vector<int> rs_grp;
-  std::vector<int4> rs_items;
-  int rs_nblk = 1;
   // MCP_BA_SCHUR: 1 (default) pair gathers with TMA, 2 staged pair gathers, 0 row-wise (k_schur_rows; measured slower
   // than the pair kernel at cfg2 -- profiles/README.md -- kept selectable and parity-tested)
   int schur_mode = 1;
   { const char* e = getenv("MCP_BA_SCHUR"); if (e && e[0]) schur_mode = atoi(e); if (getenv("MCP_BA_SCHUR_V1") && getenv("MCP_BA_SCHUR_V1")[0] == '1') schur_mode = 2; }
   if (schur_mode < 0 || schur_mode > 2) schur_mode = 1;
-  if (max_slots > 32 && schur_mode == 0) schur_mode = 1;       // an entry must fit one staging buffer
-  if (schur_mode == 0) {
-    const int s_lo = pt_slot_off[h->part_pt[h->rank]], s_hi = pt_slot_off[h->part_pt[h->rank + 1]];
-    std::vector<int> order;
-    order.reserve((size_t)std::max(s_hi - s_lo, 0));
-    for (int sidx = s_lo; sidx < s_hi; sidx++) order.push_back(sidx);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slot_var[x] < slot_var[y]; });
-    const int target = std::max(16, (int)((order.size() + 148 * 8 - 1) / (148 * 8)));     // entries per item
-    size_t i = 0;
-    while (i < order.size()) {
-      size_t j = i;
-      const int a = slot_var[order[i]];
-      while (j < order.size() && slot_var[order[j]] == a) j++;
-      for (size_t b = i; b < j; b += (size_t)target) {
-        const size_t e_end = std::min(b + (size_t)target, j);
-        const int g_begin = (int)rs_grp.size();
-        size_t k = b;
-        while (k < e_end) {
-          int bytes = 0, cnt = 0;
-          const int first = (int)rs_ent.size();
-          while (k < e_end && cnt < RS_MAXE) {
-            const int sidx = order[k];
-            const int nb = pt_slot_off[slot_pt[sidx] + 1] - sidx;
-            if (cnt > 0 && bytes + 192 + 144 * nb > RS_BYTES) break;
-            bytes += 192 + 144 * nb;
-            rs_ent.push_back(make_int2(sidx, nb));
-            rs_nblk = std::max(rs_nblk, slot_var[sidx + nb - 1] - a + 1);
-            cnt++; k++;
-          }
-          rs_grp.push_back((first << 4) | cnt);
-        }
-        rs_items.push_back(make_int4(a, g_begin, (int)rs_grp.size(), 0));
-      }
-      i = j;
-    }
+
+  // host marshalling (ba_prep.hpp): linear passes into pinned staging that is pooled across calls
+  BaPrep& pr = h->prep;
+  int prc = ba_prepare(pr, g_pinned_alloc, n_cam, n_pose, pose_fixed, n_pt, pt_chain, pt_fixed, n_meas, meas_xy, meas_chain,
+                       meas_pt, meas_noise, meas_cam, h->rank, h->world, schur_mode == 0);
+  if (prc == PREP_OK && schur_mode == 0 && pr.max_slots > 32) {          // an entry must fit one staging buffer
+    schur_mode = 1;
+    pr.rs_ent.n = pr.rs_grp.n = pr.rs_items.n = 0;
   }
+  if (prc != PREP_OK) {
+    set_last_error("%s", pr.err);
+    return prc == PREP_INVALID ? MCP_ERR_INVALID : prc == PREP_UNSUPPORTED ? MCP_ERR_UNSUPPORTED : MCP_ERR_CUDA;
+  }
+  const int npv = pr.npv, nptv = pr.nptv, n_slots = pr.n_slots, max_slots = pr.max_slots, rs_nblk = pr.rs_nblk;
+  const int nc = 6 * npv;
+  if (nc > chol_max_n()) {
+    set_last_error("mcp_ba_load: %d movable poses exceed the dense solver capacity (%d rows)", npv, chol_max_n());
+    return MCP_ERR_UNSUPPORTED;
+  }
+  const int stage_doubles = stage_doubles_for(n_pose, n_cam);
+  if (configure_kernels(max_slots, stage_doubles, &h->lin_warps, &h->lin_smem) != 0) {
+    set_last_error("mcp_ba_load: a point is observed from %d movable keyframes, more than the kernel supports", max_slots);
+    return MCP_ERR_UNSUPPORTED;
+  }
+  h->part_pt = pr.part_pt; h->part_meas = pr.part_meas;
+  h->meas_orig.swap(pr.meas_orig);
 
   int rc;
-#define UP(buf, vec) if ((rc = upload(h, buf, (vec).data(), sizeof((vec)[0]) * (vec).size()))) return rc
-  UP(h->b_pb_idx, pb_idx); UP(h->b_pb_items, pb_items);
-  UP(h->b_rs_ent, rs_ent); UP(h->b_rs_grp, rs_grp); UP(h->b_rs_items, rs_items);
+#define UP(buf, arr) if ((rc = upload(h, buf, (arr).p, (arr).bytes()))) return rc
+  UP(h->b_pb_idx, pr.pb_idx); UP(h->b_pb_items, pr.pb_items);
+  UP(h->b_rs_ent, pr.rs_ent); UP(h->b_rs_grp, pr.rs_grp); UP(h->b_rs_items, pr.rs_items);
   if ((rc = h->b_mrec.ensure(sizeof(double) * MREC * (size_t)std::max(n_meas, 1)))) return rc;
-  UP(h->b_pose_var, pose_var); UP(h->b_pt_info, pt_info); UP(h->b_pt_var, pt_var); UP(h->b_pt_order, pt_order); UP(h->b_pt_meas_off, pt_meas_off);
-  UP(h->b_pt_slot_off, pt_slot_off); UP(h->b_slot_var, slot_var); UP(h->b_slot_pt, slot_pt); UP(h->b_meas_xy, mxy); UP(h->b_meas_info, minfo);
-  UP(h->b_meas_a, meas_a); UP(h->b_meas_b, meas_b);
+  UP(h->b_pose_var, pr.pose_var); UP(h->b_pt_info, pr.pt_info); UP(h->b_pt_var, pr.pt_var); UP(h->b_pt_order, pr.pt_order);
+  UP(h->b_pt_meas_off, pr.pt_meas_off); UP(h->b_pt_slot_off, pr.pt_slot_off); UP(h->b_slot_var, pr.slot_var); UP(h->b_slot_pt, pr.slot_pt);
+  UP(h->b_meas_xy, pr.meas_xy); UP(h->b_meas_info, pr.meas_info); UP(h->b_meas_a, pr.meas_a); UP(h->b_meas_b, pr.meas_b);
 #undef UP
-  const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)std::max(n_pt, 1);
-  for (int k = 0; k < N_STATE; k++) {
-    if ((rc = upload(h, h->b_pose[k], pose_Rt, pose_bytes))) return rc;
-    if ((rc = upload(h, h->b_pt[k], pt_xyz, sizeof(double) * 3 * (size_t)n_pt))) return rc;
-    if ((rc = h->b_chi2[k].ensure(sizeof(double) * (size_t)std::max(n_meas, 1)))) return rc;
-  }
+  // initial state: one copy from the caller's (pageable) arrays, replicated on the device
+  const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)n_pt;
   if ((rc = upload(h, h->b_pose0, pose_Rt, pose_bytes))) return rc;
-  if ((rc = upload(h, h->b_pt0, pt_xyz, sizeof(double) * 3 * (size_t)n_pt))) return rc;
-  (void)pt_bytes;
+  if ((rc = upload(h, h->b_pt0, pt_xyz, pt_bytes))) return rc;
+  for (int k = 0; k < N_STATE; k++) {
+    if ((rc = h->b_pose[k].ensure(pose_bytes))) return rc;
+    if ((rc = h->b_pt[k].ensure(pt_bytes ? pt_bytes : 16))) return rc;
+    if ((rc = h->b_chi2[k].ensure(sizeof(double) * (size_t)std::max(n_meas, 1)))) return rc;
+    MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_pose[k].p, h->b_pose0.p, pose_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (pt_bytes) MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_pt[k].p, h->b_pt0.p, pt_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
   if ((rc = h->b_V.ensure(sizeof(double) * 6 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_gp.ensure(sizeof(double) * 3 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_W.ensure(sizeof(double) * 18 * (size_t)std::max(n_slots, 1)))) return rc;
@@ -510,13 +369,13 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.meas_a = h->b_meas_a.as<int4>(); d.meas_b = h->b_meas_b.as<int4>();
   for (int k = 0; k < N_STATE; k++) { d.pose[k] = h->b_pose[k].as<double>(); d.pt[k] = h->b_pt[k].as<double>(); d.chi2[k] = h->b_chi2[k].as<double>(); }
   d.V = h->b_V.as<double>(); d.gp = h->b_gp.as<double>(); d.W = h->b_W.as<double>(); d.Y = h->b_Y.as<double>();
-  d.slot_pt = h->b_slot_pt.as<int>(); d.slot_lo = pt_slot_off[d.p_lo]; d.slot_hi = pt_slot_off[d.p_hi];
+  d.slot_pt = h->b_slot_pt.as<int>(); d.slot_lo = pr.pt_slot_off[d.p_lo]; d.slot_hi = pr.pt_slot_off[d.p_hi];
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
   d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
-  d.rs_ent = h->b_rs_ent.as<int2>(); d.rs_grp = h->b_rs_grp.as<int>(); d.rs_items = h->b_rs_items.as<int4>(); d.n_rs_items = (int)rs_items.size();
+  d.rs_ent = h->b_rs_ent.as<int2>(); d.rs_grp = h->b_rs_grp.as<int>(); d.rs_items = h->b_rs_items.as<int4>(); d.n_rs_items = (int)pr.rs_items.n;
   d.schur_mode = schur_mode; d.rs_nblk = rs_nblk;
-  d.mrec = h->b_mrec.as<double>(); d.pb_idx = h->b_pb_idx.as<int>(); d.pb_items = h->b_pb_items.as<int4>(); d.n_pb_items = (int)pb_items.size();
+  d.mrec = h->b_mrec.as<double>(); d.pb_idx = h->b_pb_idx.as<int>(); d.pb_items = h->b_pb_items.as<int4>(); d.n_pb_items = (int)pr.pb_items.n;
   d.sel_state = h->b_sel.as<unsigned long long>();
   d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
   d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();
@@ -556,29 +415,20 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   c.sel_n = n_meas; c.sel_rank = n_meas / 2;
   MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
   if (schur_mode != 0) {
-    // co-visibility lists for the pair-gather Schur kernels (ba_schur.cu), built on the device
+    // co-visibility lists for the pair-gather Schur kernels (ba_schur.cu), built entirely on the device: count per
+    // block pair, scan + work items (k_pair_items), fill.  Only their sizes (upper bounds) are known to the host.
     const int n_pairs = npv * (npv + 1) / 2;
-    if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 1), h->stream));
+    const size_t max_items = (size_t)(pr.n_inc / 128) + (size_t)n_pairs + 1;
+    if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 2)))) return rc;
+    if ((rc = h->b_inc.ensure(sizeof(int2) * (size_t)std::max<long long>(pr.n_inc, 1)))) return rc;
+    if ((rc = h->b_items.ensure(sizeof(int4) * max_items + 16))) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 2), h->stream));
+    int* n_items_dev = reinterpret_cast<int*>(h->b_items.as<int4>() + max_items);
     launch_pair_count(d, h->b_paircnt.as<int>(), h->stream);
-    std::vector<int> cnt(n_pairs + 1, 0);
-    MCP_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), h->b_paircnt.p, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
-    MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    std::vector<int> off(n_pairs + 1, 0);
-    for (int i = 0; i < n_pairs; i++) off[i + 1] = off[i] + cnt[i];
-    const int n_inc = off[n_pairs];
-    std::vector<int4> items;
-    const int CH = 128;
-    int pid = 0;
-    for (int a2 = 0; a2 < npv; a2++)
-      for (int b2 = a2; b2 < npv; b2++, pid++)
-        for (int q = off[pid]; q < off[pid + 1]; q += CH) items.push_back(make_int4(a2, b2, q, std::min(q + CH, off[pid + 1])));
-    if ((rc = h->b_inc.ensure(sizeof(int2) * (size_t)std::max(n_inc, 1)))) return rc;
-    if ((rc = upload(h, h->b_paircnt, off.data(), sizeof(int) * (size_t)(n_pairs + 1)))) return rc;
-    if ((rc = upload(h, h->b_items, items.data(), sizeof(int4) * items.size()))) return rc;
+    launch_pair_items(d, h->b_paircnt.as<int>(), h->b_items.as<int4>(), n_items_dev, h->stream);
     launch_pair_fill(d, h->b_paircnt.as<int>(), h->b_inc.as<int2>(), h->stream);
-    d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items = (int)items.size();
-    for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.inc = d.inc; h->cand[q].d.items = d.items; h->cand[q].d.n_items = d.n_items; }
+    d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items_dev = n_items_dev; d.max_items = (int)max_items;
+    for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.inc = d.inc; h->cand[q].d.items = d.items; h->cand[q].d.n_items_dev = d.n_items_dev; h->cand[q].d.max_items = d.max_items; }
   }
   MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->outliers.clear();

@@ -51,6 +51,39 @@ __global__ void k_pair_fill(BaDev d, int* __restrict__ cursor, int2* __restrict_
   }
 }
 
+// one block: exclusive scan of the per-pair incidence counts (in place: cnt becomes the fill cursor of k_pair_fill,
+// cnt[n_pairs] the total), the work items {block row, block col, begin, end} of <= 128 incidences in (row, col, begin)
+// order, and their number -- on the device, so that mcp_ba_load never waits for a read-back
+__global__ void __launch_bounds__(1024) k_pair_items(BaDev d, int* __restrict__ cnt, int4* __restrict__ items, int* __restrict__ n_items_out)
+{
+  __shared__ int sh_inc[1024], sh_it[1024];
+  const int npv = d.n_pose_var, n_pairs = npv * (npv + 1) / 2;
+  const int t = threadIdx.x, per = (n_pairs + 1023) / 1024;
+  const int lo = min(t * per, n_pairs), hi = min(lo + per, n_pairs);
+  int s_inc = 0, s_it = 0;
+  for (int i = lo; i < hi; i++) { const int c = cnt[i]; s_inc += c; s_it += (c + 127) >> 7; }
+  sh_inc[t] = s_inc; sh_it[t] = s_it;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int a = t >= o ? sh_inc[t - o] : 0, b = t >= o ? sh_it[t - o] : 0;
+    __syncthreads();
+    sh_inc[t] += a; sh_it[t] += b;
+    __syncthreads();
+  }
+  int off_inc = sh_inc[t] - s_inc, off_it = sh_it[t] - s_it;
+  int a = 0, rem = lo;
+  while (a < npv && rem >= npv - a) { rem -= npv - a; a++; }
+  int b = a + rem;
+  for (int i = lo; i < hi; i++) {
+    const int c = cnt[i];
+    cnt[i] = off_inc;
+    for (int q = 0; q < c; q += 128) items[off_it++] = make_int4(a, b, off_inc + q, off_inc + min(q + 128, c));
+    off_inc += c;
+    if (++b == npv) { a++; b = a; }
+  }
+  if (t == 1023) { cnt[n_pairs] = sh_inc[1023]; *n_items_out = sh_it[1023]; }
+}
+
 // ---- per trial --------------------------------------------------------------------------------------
 // one thread per (point, slot): Y = W Vinv (18 doubles), z = Y g_p (6 doubles)
 __global__ void __launch_bounds__(256) k_schur_y(BaDev d)
@@ -100,7 +133,8 @@ __global__ void __launch_bounds__(128) k_schur_pairs(BaDev d)
   double* st = stage[wid];
   const int r0 = lane / 6, c0 = lane - 6 * r0;           // entry `lane`
   const int e1 = 32 + (lane & 3), r1 = e1 / 6, c1 = e1 - 6 * r1;
-  for (int it = gw; it < d.n_items; it += nw) {
+  const int n_items = __ldg(d.n_items_dev);
+  for (int it = gw; it < n_items; it += nw) {
     const int4 item = d.items[it];
     const bool diag = item.x == item.y;
     double acc0 = 0.0, acc1 = 0.0, accz = 0.0;
@@ -206,7 +240,8 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
   }
   const bool gvalid = g < 6;
   unsigned phase[2] = { 0u, 0u };
-  for (int it = gw; it < d.n_items; it += nw) {
+  const int n_items = __ldg(d.n_items_dev);
+  for (int it = gw; it < n_items; it += nw) {
     const int4 item = d.items[it];
     const bool diag = item.x == item.y;
     const int n_groups = (item.w - item.z + TG - 1) / TG;
@@ -499,6 +534,7 @@ void launch_marginals(const BaDev& d, double* cov, cudaStream_t s) { k_marginals
 
 void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148, 128, 0, s>>>(d, cnt); }
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148, 128, 0, s>>>(d, cursor, inc); }
+void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s) { k_pair_items<<<1, 1024, 0, s>>>(d, cnt, items, n_items_out); }
 void launch_schur_gather(const BaDev& d, cudaStream_t s)
 {
   const int nslots = d.slot_hi - d.slot_lo;
@@ -519,7 +555,7 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s)
     return;
   }
   const int use_v1 = d.schur_mode == 2;
-  int g2 = (d.n_items + 3) / 4;
+  int g2 = (d.max_items + 3) / 4;                       // upper bound; the kernels read the count from the device
   if (g2 < 1) g2 = 1;
   if (use_v1) {
     if (g2 > 148 * 5) g2 = 148 * 5;

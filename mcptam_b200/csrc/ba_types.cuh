@@ -79,7 +79,8 @@ struct BaDev {
   int slot_lo, slot_hi;          // local slot range (multi-GPU shard)
   const int2* inc;               // co-visibility incidences {slot A, slot B}, bucketed by block pair
   const int4* items;             // work items {block row, block col, begin, end} into inc
-  int n_items, pad_items;
+  const int* n_items_dev;        // number of work items (written by k_pair_items at load time)
+  int max_items, pad_items;      // host-side upper bound of it (grid sizing)
   const int2* rs_ent;            // row-wise Schur lists: {slot, slots from it to the end of its point}, sorted by pose variable
   const int* rs_grp;             // groups of <= RS_MAXE entries that fit one staging buffer: (first entry << 4) | count
   const int4* rs_items;          // work items {pose variable a, first group, end group, 0}
