@@ -286,17 +286,22 @@ def main():
                                                 prob.meas_xy, prob.meas_chain, prob.meas_pt, prob.meas_noise, prob.meas_cam))
     d2h = prob.pose_Rt.nbytes + prob.pt_xyz.nbytes
     e2e_t, e2e_it = 0.0, 0
+    e2e_parts = np.zeros(3)                        # load (marshal + H2D), compute, read-back: host wall clock
     for s in range(warmup + args.steps):
         barrier()
         if s == warmup:
             t_e2e0 = time.perf_counter()
         t = time.perf_counter()
         h2.load(prob)
+        t1 = time.perf_counter()
         rc, st = h2.compute(args.lm_iters)
+        t2 = time.perf_counter()
         P, X = h2.poses(), h2.points()
         _ = h2.outliers()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
+        if s >= warmup:
+            e2e_parts += (t1 - t, t2 - t1, t + dt - t2)
         if dist is not None:
             tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -413,7 +418,9 @@ def main():
                        "lm_iters_per_step": args.lm_iters, "l2": "256 MiB flush between steps; within a step the map stays L2-resident",
                        "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": {"load": 1e3 * e2e_parts[0] / args.steps, "compute": 1e3 * e2e_parts[1] / args.steps,
+                                    "read_back": 1e3 * e2e_parts[2] / args.steps}},
             "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "scale_big_map": scale, "wall_s": wall,
             "lm": {"iterations_per_step": iters / args.steps, "trials_last_step": st.total_trials}}
     print(json.dumps(line))

@@ -240,7 +240,7 @@ class _PrepView(C.Structure):
                [(n, C.c_int) for n in "npv nptv n_slots max_slots rs_nblk pad".split()] + [("err", C.c_char_p)]
 
 
-def ba_prepare(prob, rank=0, world=1, want_rows=False, reps=1):
+def ba_prepare(prob, rank=0, world=1, want_rows=False, reps=1, threads=1, par_min_meas=-1):
     """Host marshalling of mcp_ba_load (csrc/ba_prep.hpp) run on the CPU through the test shim libmcptam_prep.so.
     Returns (dict of numpy arrays / scalars, best time in ms).  Raises McpError with the message mcp_ba_load would set."""
     from . import build
@@ -253,9 +253,9 @@ def ba_prepare(prob, rank=0, world=1, want_rows=False, reps=1):
          np.ascontiguousarray(prob.meas_noise, np.float64), np.ascontiguousarray(prob.meas_cam, np.int32)]
     v, ms = _PrepView(), C.c_double()
     L.mcp_prep_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + \
-                              [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+                              [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
     rc = L.mcp_prep_run(len(prob.cams), prob.n_pose, _p(k[0]), prob.n_pt, _p(k[1]), _p(k[2]), prob.n_meas, _p(k[3]), _p(k[4]),
-                        _p(k[5]), _p(k[6]), _p(k[7]), rank, world, int(want_rows), reps, C.cast(C.byref(ms), C.c_void_p),
+                        _p(k[5]), _p(k[6]), _p(k[7]), rank, world, int(want_rows), reps, threads, par_min_meas, C.cast(C.byref(ms), C.c_void_p),
                         C.cast(C.byref(v), C.c_void_p))
     if rc != 0:
         raise McpError(rc, (v.err or b"").decode())

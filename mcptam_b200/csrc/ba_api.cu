@@ -7,10 +7,14 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "ba_prep.hpp"
@@ -118,6 +122,7 @@ struct McpBa {
   int* flags_host = nullptr;     // pinned, n_meas
   size_t flags_cap = 0;
   BaPrep prep;                   // host marshalling output in pinned memory, pooled across loads
+  std::unique_ptr<HostPool> pool; // host threads of the marshalling passes
   std::vector<int> meas_orig;    // sorted position -> original index
   std::vector<int32_t> outliers;
   // multi-GPU
@@ -278,17 +283,37 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if (schur_mode < 0 || schur_mode > 2) schur_mode = 1;
 
   // host marshalling (ba_prep.hpp): linear passes into pinned staging that is pooled across calls
+  static const bool trace = getenv("MCP_BA_LOAD_TRACE") && getenv("MCP_BA_LOAD_TRACE")[0] == '1';
+  const auto t_begin = std::chrono::steady_clock::now();
   BaPrep& pr = h->prep;
+  {
+    // host threads for the marshalling passes: MCP_BA_HOST_THREADS, else half the cores shared between the ranks
+    int want = 0;
+    if (const char* e = getenv("MCP_BA_HOST_THREADS")) want = atoi(e);
+    if (want <= 0) want = std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / (2 * std::max(h->world, 1))));
+    if (!h->pool || h->pool->size() != want) h->pool.reset(new HostPool(want));
+  }
+  int rc = MCP_OK;
+#define UP(buf, arr) if (rc == MCP_OK) rc = upload(h, buf, (arr).p, (arr).bytes())
+  // called by ba_prepare as soon as the measurement / point / slot arrays are final: their upload overlaps the
+  // construction of the work lists
+  const std::function<void()> upload_points = [&]() {
+    UP(h->b_pose_var, pr.pose_var); UP(h->b_pt_info, pr.pt_info); UP(h->b_pt_var, pr.pt_var);
+    UP(h->b_pt_meas_off, pr.pt_meas_off); UP(h->b_pt_slot_off, pr.pt_slot_off); UP(h->b_slot_var, pr.slot_var); UP(h->b_slot_pt, pr.slot_pt);
+    UP(h->b_meas_xy, pr.meas_xy); UP(h->b_meas_info, pr.meas_info); UP(h->b_meas_a, pr.meas_a); UP(h->b_meas_b, pr.meas_b);
+  };
   int prc = ba_prepare(pr, g_pinned_alloc, n_cam, n_pose, pose_fixed, n_pt, pt_chain, pt_fixed, n_meas, meas_xy, meas_chain,
-                       meas_pt, meas_noise, meas_cam, h->rank, h->world, schur_mode == 0);
+                       meas_pt, meas_noise, meas_cam, h->rank, h->world, schur_mode == 0, h->pool.get(), &upload_points);
   if (prc == PREP_OK && schur_mode == 0 && pr.max_slots > 32) {          // an entry must fit one staging buffer
     schur_mode = 1;
     pr.rs_ent.n = pr.rs_grp.n = pr.rs_items.n = 0;
   }
   if (prc != PREP_OK) {
+    cudaStreamSynchronize(h->stream);                                    // uploads from the staging may be in flight
     set_last_error("%s", pr.err);
     return prc == PREP_INVALID ? MCP_ERR_INVALID : prc == PREP_UNSUPPORTED ? MCP_ERR_UNSUPPORTED : MCP_ERR_CUDA;
   }
+  if (rc != MCP_OK) return rc;
   const int npv = pr.npv, nptv = pr.nptv, n_slots = pr.n_slots, max_slots = pr.max_slots, rs_nblk = pr.rs_nblk;
   const int nc = 6 * npv;
   if (nc > chol_max_n()) {
@@ -302,16 +327,13 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   }
   h->part_pt = pr.part_pt; h->part_meas = pr.part_meas;
   h->meas_orig.swap(pr.meas_orig);
+  const auto t_prep = std::chrono::steady_clock::now();
 
-  int rc;
-#define UP(buf, arr) if ((rc = upload(h, buf, (arr).p, (arr).bytes()))) return rc
-  UP(h->b_pb_idx, pr.pb_idx); UP(h->b_pb_items, pr.pb_items);
+  UP(h->b_pt_order, pr.pt_order); UP(h->b_pb_idx, pr.pb_idx); UP(h->b_pb_items, pr.pb_items);
   UP(h->b_rs_ent, pr.rs_ent); UP(h->b_rs_grp, pr.rs_grp); UP(h->b_rs_items, pr.rs_items);
-  if ((rc = h->b_mrec.ensure(sizeof(double) * MREC * (size_t)std::max(n_meas, 1)))) return rc;
-  UP(h->b_pose_var, pr.pose_var); UP(h->b_pt_info, pr.pt_info); UP(h->b_pt_var, pr.pt_var); UP(h->b_pt_order, pr.pt_order);
-  UP(h->b_pt_meas_off, pr.pt_meas_off); UP(h->b_pt_slot_off, pr.pt_slot_off); UP(h->b_slot_var, pr.slot_var); UP(h->b_slot_pt, pr.slot_pt);
-  UP(h->b_meas_xy, pr.meas_xy); UP(h->b_meas_info, pr.meas_info); UP(h->b_meas_a, pr.meas_a); UP(h->b_meas_b, pr.meas_b);
 #undef UP
+  if (rc != MCP_OK) return rc;
+  if ((rc = h->b_mrec.ensure(sizeof(double) * MREC * (size_t)std::max(n_meas, 1)))) return rc;
   // initial state: one copy from the caller's (pageable) arrays, replicated on the device
   const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)n_pt;
   if ((rc = upload(h, h->b_pose0, pose_Rt, pose_bytes))) return rc;
@@ -430,7 +452,13 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items_dev = n_items_dev; d.max_items = (int)max_items;
     for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.inc = d.inc; h->cand[q].d.items = d.items; h->cand[q].d.n_items_dev = d.n_items_dev; h->cand[q].d.max_items = d.max_items; }
   }
+  const auto t_enq = std::chrono::steady_clock::now();
   MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (trace) {
+    const auto t_end = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "mcp_ba_load: marshal %.3f ms, enqueue %.3f ms, drain %.3f ms\n", ms(t_begin, t_prep), ms(t_prep, t_enq), ms(t_enq, t_end));
+  }
   h->outliers.clear();
   h->loaded = true;
   return MCP_OK;

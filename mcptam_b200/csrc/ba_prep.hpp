@@ -11,14 +11,86 @@
 // Header-only so that the CPU tests and tools/prep_bench.cpp can compile it without nvcc.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace mcp {
+
+// A few persistent host threads for the marshalling passes.  run(f) calls f(tid) for tid in [0, size()) -- tid 0 on the
+// caller -- and returns when all are done.  Workers spin briefly between the back-to-back passes of one load and sleep
+// on a condition variable otherwise.
+class HostPool {
+ public:
+  explicit HostPool(int n_threads) : n_(std::max(n_threads, 1))
+  {
+    for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~HostPool()
+  {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (std::thread& w : workers_) w.join();
+  }
+  HostPool(const HostPool&) = delete;
+  HostPool& operator=(const HostPool&) = delete;
+  int size() const { return n_; }
+  void run(const std::function<void(int)>& f)
+  {
+    if (n_ == 1) { f(0); return; }
+    job_ = &f;
+    remaining_.store(n_ - 1, std::memory_order_relaxed);
+    { std::lock_guard<std::mutex> lk(mu_); gen_.fetch_add(1, std::memory_order_release); }
+    cv_.notify_all();
+    f(0);
+    while (remaining_.load(std::memory_order_acquire) > 0) cpu_relax();
+  }
+
+ private:
+  static void cpu_relax()
+  {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
+  void loop(int tid)
+  {
+    unsigned long long last = 0;
+    for (;;) {
+      bool got = false;
+      for (int spin = 0; spin < 4000; spin++) {
+        if (gen_.load(std::memory_order_acquire) != last) { got = true; break; }
+        cpu_relax();
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != last; });
+        if (stop_) return;
+      }
+      last = gen_.load(std::memory_order_acquire);
+      (*job_)(tid);
+      remaining_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::atomic<unsigned long long> gen_{ 0 };
+  std::atomic<int> remaining_{ 0 };
+  const std::function<void(int)>* job_ = nullptr;
+  bool stop_ = false;
+};
 
 // layout-compatible with CUDA's int4 / int2 / double2
 struct alignas(16) PInt4 { int x, y, z, w; };
@@ -81,9 +153,9 @@ struct BaPrep {
   int npv = 0, nptv = 0, n_slots = 0, max_slots = 1, rs_nblk = 1;
   long long n_inc = 0;            // co-visibility incidences of this rank: sum over its points of K(K+1)/2
   char err[256] = "";
+  int par_min_meas = 16384;       // below this many measurements the passes run on the calling thread only
   // scratch, kept between calls
-  std::vector<int> cursor, stamp, pos, tmp, key_cnt, order;
-  std::vector<long long> keys;
+  std::vector<int> cursor, key_cnt, order, slot_tmp, thr_bad, thr_max, thr_lo;
 
   void free_all(const PrepAlloc& a)
   {
@@ -110,10 +182,15 @@ inline void partition_points(const int* pt_meas_off, int n_pt, int world, int* p
 
 #define MCP_PREP_FAIL(code, ...) do { snprintf(o.err, sizeof(o.err), __VA_ARGS__); return code; } while (0)
 
+// `after_points` (may be NULL) is called once the per-measurement, per-point and slot arrays are final -- the caller
+// starts their upload while the work lists are still being built.
+// `pool` (may be NULL) runs the three heavy passes -- validation + histogram, the per-point pass and the pose-block
+// bucketing -- on several host threads; the result is identical for any thread count.
 inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, const uint8_t* pose_fixed, int n_pt,
                       const int32_t* pt_chain, const uint8_t* pt_fixed, int n_meas, const double* meas_xy,
                       const int32_t* meas_chain, const int32_t* meas_pt, const double* meas_noise, const int32_t* meas_cam,
-                      int rank, int world, bool want_rows)
+                      int rank, int world, bool want_rows, HostPool* pool = nullptr,
+                      const std::function<void()>* after_points = nullptr)
 {
   o.err[0] = 0;
   const size_t np1 = (size_t)std::max(n_pt, 1), nm1 = (size_t)std::max(n_meas, 1);
@@ -122,6 +199,8 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       !o.slot_var.resize((size_t)n_meas + n_pt + 1, al) || !o.slot_pt.resize((size_t)n_meas + n_pt + 1, al) ||
       !o.meas_xy.resize(nm1, al) || !o.meas_info.resize(nm1, al) || !o.meas_a.resize(nm1, al) || !o.meas_b.resize(nm1, al))
     MCP_PREP_FAIL(PREP_NOMEM, "mcp_ba_load: host staging allocation failed");
+  const int T = (pool && n_meas >= o.par_min_meas) ? pool->size() : 1;
+  auto par = [&](const std::function<void(int)>& f) { if (T > 1) pool->run(f); else f(0); };
 
   int npv = 0;
   for (int i = 0; i < n_pose; i++) o.pose_var[i] = pose_fixed[i] ? -1 : npv++;
@@ -131,17 +210,36 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     if (a < 0 || a >= n_pose || b >= n_pose) MCP_PREP_FAIL(PREP_INVALID, "point %d: chain index out of range", p);
     if (b >= 0 && !pose_fixed[b]) MCP_PREP_FAIL(PREP_UNSUPPORTED, "point %d: movable second chain link is not supported", p);
   }
-  // validation + histogram of measurements per point in one pass
+  // validation + histogram of measurements per point in one pass; the first offending measurement (in index order) is
+  // reported, as a sequential scan would
   int* pmo = o.pt_meas_off.p;
   std::fill(pmo, pmo + n_pt + 1, 0);
-  for (int m = 0; m < n_meas; m++) {
-    const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
-    if (a < 0 || a >= n_pose || b >= n_pose) MCP_PREP_FAIL(PREP_INVALID, "measurement %d: chain index out of range", m);
-    if (b >= 0 && !pose_fixed[b]) MCP_PREP_FAIL(PREP_UNSUPPORTED, "measurement %d: movable second chain link is not supported", m);
-    if (meas_pt[m] < 0 || meas_pt[m] >= n_pt) MCP_PREP_FAIL(PREP_INVALID, "measurement %d: point index out of range", m);
-    if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) MCP_PREP_FAIL(PREP_INVALID, "measurement %d: camera index out of range", m);
-    if (!(meas_noise[m] > 0)) MCP_PREP_FAIL(PREP_INVALID, "measurement %d: noise must be > 0", m);
-    pmo[meas_pt[m] + 1]++;
+  o.thr_bad.assign((size_t)T * 2, -1);
+  par([&](int t) {
+    const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+    for (int m = lo; m < hi; m++) {
+      const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
+      int bad = 0;
+      if (a < 0 || a >= n_pose || b >= n_pose) bad = 1;
+      else if (b >= 0 && !pose_fixed[b]) bad = 2;
+      else if (meas_pt[m] < 0 || meas_pt[m] >= n_pt) bad = 3;
+      else if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) bad = 4;
+      else if (!(meas_noise[m] > 0)) bad = 5;
+      if (bad) { o.thr_bad[2 * t] = m; o.thr_bad[2 * t + 1] = bad; return; }
+      if (T > 1) __atomic_fetch_add(&pmo[meas_pt[m] + 1], 1, __ATOMIC_RELAXED);
+      else pmo[meas_pt[m] + 1]++;
+    }
+  });
+  for (int t = 0; t < T; t++) {
+    const int m = o.thr_bad[2 * t];
+    if (m < 0) continue;
+    switch (o.thr_bad[2 * t + 1]) {
+      case 1: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: chain index out of range", m);
+      case 2: MCP_PREP_FAIL(PREP_UNSUPPORTED, "measurement %d: movable second chain link is not supported", m);
+      case 3: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: point index out of range", m);
+      case 4: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: camera index out of range", m);
+      default: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: noise must be > 0", m);
+    }
   }
   // measurements sorted by point (stable counting sort)
   for (int p = 0; p < n_pt; p++) pmo[p + 1] += pmo[p];
@@ -153,58 +251,103 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
   for (int p = 0; p < n_pt; p++) o.pt_var[p] = pt_fixed[p] ? -1 : nptv++;
   o.nptv = nptv;
 
-  // per point: the ascending list of movable poses that carry a Jacobian block of the point (its slots)
-  o.stamp.assign((size_t)std::max(npv, 1), -1);
-  o.pos.assign((size_t)std::max(npv, 1), 0);
-  int n_slots = 0, max_slots = 1;
-  std::vector<int>& tmp = o.tmp;
-  for (int p = 0; p < n_pt; p++) {
-    const int src0 = pt_chain[2 * p], src1 = pt_chain[2 * p + 1];
-    const int src_var = o.pose_var[src0];
-    const bool movable = o.pt_var[p] >= 0;
-    bool any_src = false;
-    tmp.clear();
-    for (int q = pmo[p]; q < pmo[p + 1]; q++) {
-      const int m = o.meas_orig[q];
-      const int obs0 = meas_chain[2 * m];
-      const bool has_jac = (obs0 != src0);                 // PoseChainHelper::MoveTogether at depth 0
-      const int ov = has_jac ? o.pose_var[obs0] : -1;
-      const bool has_src = has_jac && src_var >= 0;
-      any_src |= has_src;
-      if (ov >= 0 && movable && o.stamp[ov] != p) { o.stamp[ov] = p; tmp.push_back(ov); }
-      o.meas_a[q] = PInt4{ obs0, meas_chain[2 * m + 1], meas_cam[m], m };
-      o.meas_b[q] = PInt4{ ov, -1, has_src ? 1 : 0, p };
-      o.meas_xy[q] = PDouble2{ meas_xy[2 * m], meas_xy[2 * m + 1] };
-      o.meas_info[q] = 1.0 / std::sqrt(meas_noise[m]);     // src/ChainBundle.cc:1244-1245
-    }
-    int src_slot = -1;
-    o.pt_slot_off[p] = n_slots;
-    if (movable) {
-      if (any_src && o.stamp[src_var] != p) { o.stamp[src_var] = p; tmp.push_back(src_var); }
-      const int K = (int)tmp.size();
-      if (K <= 16) {                                       // insertion sort: the lists are short and nearly sorted
-        for (int i = 1; i < K; i++) {
-          const int v = tmp[i];
-          int j = i - 1;
-          while (j >= 0 && tmp[j] > v) { tmp[j + 1] = tmp[j]; j--; }
-          tmp[j + 1] = v;
-        }
-      } else {
-        std::sort(tmp.begin(), tmp.end());
+  // per point: the ascending list of movable poses that carry a Jacobian block of the point (its slots).  Threads take
+  // measurement-balanced point ranges; the lists first go to a provisional place (point p at pmo[p] + p: a point has
+  // at most one slot per measurement plus its source pose), then an exclusive scan of the list lengths places them.
+  o.slot_tmp.resize((size_t)n_meas + n_pt + 1);
+  o.thr_max.assign((size_t)T, 1);
+  o.thr_lo.assign((size_t)T + 1, n_pt);
+  for (int t = 0; t < T; t++)
+    o.thr_lo[t] = (int)(std::lower_bound(pmo, pmo + n_pt, (int)((long long)n_meas * t / T)) - pmo);
+  o.thr_lo[0] = 0;
+  par([&](int t) {
+    // thread-private scratch and local copies of every pointer: the loop below must not reload them through the closure
+    std::vector<int> stamp((size_t)std::max(npv, 1), -1), pos((size_t)std::max(npv, 1), 0), tmp;
+    tmp.reserve(64);
+    const int* const pose_var_ = o.pose_var.p;
+    const int* const pt_var_ = o.pt_var.p;
+    const int* const orig_ = o.meas_orig.data();
+    const int* const off_ = pmo;
+    PInt4* const ma = o.meas_a.p;
+    PInt4* const mb = o.meas_b.p;
+    PDouble2* const mxy = o.meas_xy.p;
+    double* const minfo = o.meas_info.p;
+    PInt4* const pinfo = o.pt_info.p;
+    int* const slot_cnt = o.pt_slot_off.p;
+    int* const slot_tmp = o.slot_tmp.data();
+    const double* const in_xy = meas_xy;
+    const double* const in_noise = meas_noise;
+    const int32_t* const in_chain = meas_chain;
+    const int32_t* const in_cam = meas_cam;
+    const int32_t* const in_ptchain = pt_chain;
+    const int p_lo = o.thr_lo[t], p_hi = o.thr_lo[t + 1];
+    int max_slots = 1;
+    double last_noise = -1.0, last_info = 0.0;
+    for (int p = p_lo; p < p_hi; p++) {
+      const int src0 = in_ptchain[2 * p], src1 = in_ptchain[2 * p + 1];
+      const int src_var = pose_var_[src0];
+      const bool movable = pt_var_[p] >= 0;
+      const int q_lo = off_[p], q_hi = off_[p + 1];
+      bool any_src = false;
+      tmp.clear();
+      for (int q = q_lo; q < q_hi; q++) {
+        const int m = orig_[q];
+        const int obs0 = in_chain[2 * m];
+        const bool has_jac = (obs0 != src0);               // PoseChainHelper::MoveTogether at depth 0
+        const int ov = has_jac ? pose_var_[obs0] : -1;
+        const bool has_src = has_jac && src_var >= 0;
+        any_src |= has_src;
+        if (ov >= 0 && movable && stamp[ov] != p) { stamp[ov] = p; tmp.push_back(ov); }
+        ma[q] = PInt4{ obs0, in_chain[2 * m + 1], in_cam[m], m };
+        mb[q] = PInt4{ ov, -1, has_src ? 1 : 0, p };
+        mxy[q] = PDouble2{ in_xy[2 * m], in_xy[2 * m + 1] };
+        const double nz = in_noise[m];
+        if (nz != last_noise) { last_noise = nz; last_info = 1.0 / std::sqrt(nz); }
+        minfo[q] = last_info;                              // 1/sqrt(noise), src/ChainBundle.cc:1244-1245
       }
-      for (int i = 0; i < K; i++) { o.slot_var[n_slots + i] = tmp[i]; o.slot_pt[n_slots + i] = p; o.pos[tmp[i]] = i; }
-      n_slots += K;
-      max_slots = std::max(max_slots, K);
-      for (int q = pmo[p]; q < pmo[p + 1]; q++)
-        if (o.meas_b[q].x >= 0) o.meas_b[q].y = o.pos[o.meas_b[q].x];
-      if (any_src) src_slot = o.pos[src_var];
+      int src_slot = -1, K = 0;
+      if (movable) {
+        if (any_src && stamp[src_var] != p) { stamp[src_var] = p; tmp.push_back(src_var); }
+        K = (int)tmp.size();
+        int* const tv = tmp.data();
+        if (K <= 16) {                                     // insertion sort: the lists are short and nearly sorted
+          for (int i = 1; i < K; i++) {
+            const int v = tv[i];
+            int j = i - 1;
+            while (j >= 0 && tv[j] > v) { tv[j + 1] = tv[j]; j--; }
+            tv[j + 1] = v;
+          }
+        } else {
+          std::sort(tmp.begin(), tmp.end());
+        }
+        int* dst = slot_tmp + q_lo + p;
+        for (int i = 0; i < K; i++) { dst[i] = tv[i]; pos[tv[i]] = i; }
+        max_slots = std::max(max_slots, K);
+        for (int q = q_lo; q < q_hi; q++)
+          if (mb[q].x >= 0) mb[q].y = pos[mb[q].x];
+        if (any_src) src_slot = pos[src_var];
+      }
+      slot_cnt[p + 1] = K;
+      pinfo[p] = PInt4{ src0, src1, src_var, src_slot };
     }
-    o.pt_info[p] = PInt4{ src0, src1, src_var, src_slot };
-  }
-  o.pt_slot_off[n_pt] = n_slots;
+    o.thr_max[t] = max_slots;
+  });
+  o.pt_slot_off[0] = 0;
+  for (int p = 0; p < n_pt; p++) o.pt_slot_off[p + 1] += o.pt_slot_off[p];
+  const int n_slots = o.pt_slot_off[n_pt];
+  int max_slots = 1;
+  for (int t = 0; t < T; t++) max_slots = std::max(max_slots, o.thr_max[t]);
+  par([&](int t) {
+    for (int p = o.thr_lo[t]; p < o.thr_lo[t + 1]; p++) {
+      const int* src = o.slot_tmp.data() + pmo[p] + p;
+      const int s0 = o.pt_slot_off[p], K = o.pt_slot_off[p + 1] - s0;
+      for (int i = 0; i < K; i++) { o.slot_var[s0 + i] = src[i]; o.slot_pt[s0 + i] = p; }
+    }
+  });
   o.n_slots = n_slots; o.max_slots = max_slots;
   o.slot_var.n = o.slot_pt.n = (size_t)std::max(n_slots, 1);
   if (n_slots == 0) { o.slot_var[0] = 0; o.slot_pt[0] = 0; }
+  if (after_points) (*after_points)();
 
   o.part_pt.assign((size_t)world + 1, 0);
   o.part_meas.assign((size_t)world + 1, 0);
@@ -239,44 +382,47 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
 
   // work lists of k_pose_blocks: this rank's measurements bucketed by the pose block they contribute to
   // ((v,v): observed from movable pose v; (lo,hi): observer / source pair), cut into items of <= 128 measurements.
-  // Counting sort over the npv^2 block keys; inside a block the measurements keep ascending position.
+  // Counting sort over the npv^2 block keys; inside a block the measurements keep ascending position: every thread
+  // histograms a contiguous range of positions, the cursors are laid out key-major / thread-minor.
   {
     const int m_lo = o.part_meas[rank], m_hi = o.part_meas[rank + 1];
-    const size_t n_keys = (size_t)std::max(npv, 1) * (size_t)std::max(npv, 1);
+    const size_t nv = (size_t)std::max(npv, 1), n_keys = nv * nv;
+    const int TP = (T > 1 && m_hi - m_lo >= o.par_min_meas) ? T : 1;
     std::vector<int>& cnt = o.key_cnt;
-    cnt.assign(n_keys + 1, 0);
-    size_t n_ent = 0;
-    for (int q = m_lo; q < m_hi; q++) {
-      const int vo = o.meas_b[q].x;
-      if (vo < 0) continue;
-      cnt[(size_t)vo * npv + vo + 1]++;
-      n_ent++;
-      if (o.meas_b[q].z) {
-        const int vs = o.pt_info[o.meas_b[q].w].z;
-        cnt[(size_t)std::min(vo, vs) * npv + std::max(vo, vs) + 1]++;
-        n_ent++;
+    cnt.assign(n_keys * (size_t)TP, 0);
+    auto walk = [&](int t, auto&& emit) {
+      const int lo = m_lo + (int)((long long)(m_hi - m_lo) * t / TP), hi = m_lo + (int)((long long)(m_hi - m_lo) * (t + 1) / TP);
+      const PInt4* const mb = o.meas_b.p;
+      const PInt4* const pinfo = o.pt_info.p;
+      for (int q = lo; q < hi; q++) {
+        const int vo = mb[q].x;
+        if (vo < 0) continue;
+        emit((size_t)vo * nv + vo, q);
+        if (mb[q].z) {
+          const int vs = pinfo[mb[q].w].z;
+          emit((size_t)std::min(vo, vs) * nv + std::max(vo, vs), q);
+        }
       }
+    };
+    auto count_pass = [&](int t) { if (t < TP) { int* c = cnt.data() + n_keys * (size_t)t; walk(t, [&](size_t key, int) { c[key]++; }); } };
+    if (TP > 1) pool->run(count_pass); else count_pass(0);
+    size_t n_ent = 0, n_items = 0;
+    for (size_t k = 0; k < n_keys; k++) {
+      const size_t b = n_ent;
+      for (int t = 0; t < TP; t++) { int& c = cnt[n_keys * (size_t)t + k]; const int v = c; c = (int)n_ent; n_ent += (size_t)v; }
+      n_items += (n_ent - b + PREP_PB_CHUNK - 1) / PREP_PB_CHUNK;
     }
-    size_t n_items = 0;
-    for (size_t k = 0; k < n_keys; k++) { n_items += ((size_t)cnt[k + 1] + PREP_PB_CHUNK - 1) / PREP_PB_CHUNK; cnt[k + 1] += cnt[k]; }
     if (!o.pb_idx.resize(std::max(n_ent, (size_t)1), al) || !o.pb_items.resize(std::max(n_items, (size_t)1), al))
       MCP_PREP_FAIL(PREP_NOMEM, "mcp_ba_load: host staging allocation failed");
     size_t it = 0;
     for (size_t k = 0; k < n_keys; k++) {
-      const int b = cnt[k], e = cnt[k + 1];
-      const int lo = (int)(k / (size_t)std::max(npv, 1)), hi = (int)(k % (size_t)std::max(npv, 1));
-      for (int s = b; s < e; s += PREP_PB_CHUNK) o.pb_items[it++] = PInt4{ lo, hi, s, std::min(s + PREP_PB_CHUNK, e) };
+      const int b = cnt[k], e = (k + 1 < n_keys) ? cnt[k + 1] : (int)n_ent;      // thread 0's cursor = start of the key
+      const int lo = (int)(k / nv), hi = (int)(k % nv);
+      for (int s2 = b; s2 < e; s2 += PREP_PB_CHUNK) o.pb_items[it++] = PInt4{ lo, hi, s2, std::min(s2 + PREP_PB_CHUNK, e) };
     }
     o.pb_items.n = it;                                     // 0 items is legal (nothing movable is observed)
-    for (int q = m_lo; q < m_hi; q++) {
-      const int vo = o.meas_b[q].x;
-      if (vo < 0) continue;
-      o.pb_idx[cnt[(size_t)vo * npv + vo]++] = q;
-      if (o.meas_b[q].z) {
-        const int vs = o.pt_info[o.meas_b[q].w].z;
-        o.pb_idx[cnt[(size_t)std::min(vo, vs) * npv + std::max(vo, vs)]++] = q;
-      }
-    }
+    auto fill_pass = [&](int t) { if (t < TP) { int* c = cnt.data() + n_keys * (size_t)t; int* const out = o.pb_idx.p; walk(t, [&](size_t key, int q) { out[c[key]++] = q; }); } };
+    if (TP > 1) pool->run(fill_pass); else fill_pass(0);
     o.pb_idx.n = n_ent;
   }
 

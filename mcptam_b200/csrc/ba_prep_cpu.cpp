@@ -11,6 +11,7 @@ void* host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void host_release(void* p) { free(p); }
 mcp::BaPrep g_prep;
 const mcp::PrepAlloc g_alloc = { host_alloc, host_release };
+mcp::HostPool* g_pool = nullptr;
 }
 
 extern "C" {
@@ -26,14 +27,17 @@ struct McpPrepView {
 
 int mcp_prep_run(int n_cam, int n_pose, const uint8_t* pose_fixed, int n_pt, const int32_t* pt_chain, const uint8_t* pt_fixed,
                  int n_meas, const double* meas_xy, const int32_t* meas_chain, const int32_t* meas_pt, const double* meas_noise,
-                 const int32_t* meas_cam, int rank, int world, int want_rows, int reps, double* ms_out, McpPrepView* v)
+                 const int32_t* meas_cam, int rank, int world, int want_rows, int reps, int threads, int par_min_meas,
+                 double* ms_out, McpPrepView* v)
 {
+  if (!g_pool || g_pool->size() != (threads > 0 ? threads : 1)) { delete g_pool; g_pool = new mcp::HostPool(threads); }
+  if (par_min_meas >= 0) g_prep.par_min_meas = par_min_meas;
   int rc = 0;
   double best = 1e300;
   for (int r = 0; r < (reps > 0 ? reps : 1); r++) {
     const auto t0 = std::chrono::steady_clock::now();
     rc = mcp::ba_prepare(g_prep, g_alloc, n_cam, n_pose, pose_fixed, n_pt, pt_chain, pt_fixed, n_meas, meas_xy, meas_chain,
-                         meas_pt, meas_noise, meas_cam, rank, world, want_rows != 0);
+                         meas_pt, meas_noise, meas_cam, rank, world, want_rows != 0, g_pool);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     best = ms < best ? ms : best;
     if (rc) break;

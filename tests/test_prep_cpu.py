@@ -106,6 +106,31 @@ def test_layout_matches_restatement(cfg, seed, world):
         assert np.array_equal(got["part_pt"], capi_partition(prob, world))
 
 
+@pytest.mark.parametrize("threads", [2, 4, 7])
+def test_threaded_passes_give_identical_layout(threads):
+    """the marshalling passes run on several host threads for large maps; the output does not depend on the count"""
+    prob = synth.make_ba_config("cfg1", seed=1)
+    rng = np.random.default_rng(5)
+    prob = copy.copy(prob)
+    perm = rng.permutation(prob.n_meas)
+    for k in ("meas_xy", "meas_chain", "meas_pt", "meas_noise", "meas_cam"):
+        setattr(prob, k, np.ascontiguousarray(np.asarray(getattr(prob, k))[perm]))
+    for world, rank in [(1, 0), (2, 1)]:
+        one, _ = capi.ba_prepare(prob, rank=rank, world=world, want_rows=True, threads=1, par_min_meas=16384)
+        many, _ = capi.ba_prepare(prob, rank=rank, world=world, want_rows=True, threads=threads, par_min_meas=0)
+        for k, v in one.items():
+            assert np.array_equal(np.asarray(many[k]), np.asarray(v)), k
+    # the first offending measurement is reported whichever thread finds it
+    bad = copy.copy(prob)
+    a = np.array(prob.meas_cam, copy=True)
+    a[[prob.n_meas - 2, prob.n_meas // 2 + 1, 17]] = 99
+    bad.meas_cam = a
+    with pytest.raises(capi.McpError) as e:
+        capi.ba_prepare(bad, threads=threads, par_min_meas=0)
+    assert "measurement 17:" in str(e.value)
+    capi.ba_prepare(prob, threads=1, par_min_meas=16384)
+
+
 def capi_partition(prob, world):
     """the same partition through a pure numpy statement of SURVEY.md §8(e): contiguous, measurement-count balanced"""
     off = np.concatenate([[0], np.cumsum(np.bincount(np.asarray(prob.meas_pt), minlength=prob.n_pt))])
