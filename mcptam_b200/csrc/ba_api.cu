@@ -53,6 +53,7 @@ void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
 void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
+void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
 
@@ -102,7 +103,7 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items, b_R;
   // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
   struct Cand {
     DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
@@ -115,6 +116,7 @@ struct McpBa {
   cudaStream_t copy_stream = nullptr;   // control-block read-back that does not queue behind look-ahead kernels
   int n_spec_multi = 3;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
   int n_spec = 3;                 // candidates per round (1 = no speculation)
+  bool fuse_schur = true;         // one multi-candidate Schur pass per round (MCP_BA_FUSE_SCHUR=0: one pass per candidate)
   int spec_rounds = 0, spec_used = 0;
   int chol_epoch = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
@@ -129,6 +131,11 @@ struct McpBa {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   std::vector<int> part_pt, part_meas;   // world+1 boundaries
+  // MCP_BA_TIMELINE=1: start/stop events around the launches of every stream (does not serialise the streams);
+  // dumped to stderr at the end of mcp_ba_compute as 'TL name stream start_us stop_us'
+  struct Tl { const char* name; int sid; cudaEvent_t a, b; };
+  std::vector<Tl> tl;
+  bool timeline = false;
   // profiling
   bool profiling = false;
   McpBaTiming timing;
@@ -181,6 +188,7 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   }
   // MCP_BA_SPECULATE = number of LM candidates evaluated per round (1 or 0: sequential trials)
   { const char* e = getenv("MCP_BA_SPECULATE"); if (e && e[0]) { int v = atoi(e); h->n_spec = v < 1 ? 1 : (v > MAX_CAND ? MAX_CAND : v); } }
+  { const char* e = getenv("MCP_BA_FUSE_SCHUR"); h->fuse_schur = !(e && e[0] == '0'); }
   { const char* e = getenv("MCP_BA_SPECULATE_MULTI"); if (e && e[0]) { int v = atoi(e); h->n_spec_multi = v < 1 ? 1 : (v > MAX_CAND ? MAX_CAND : v); } }
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev0));
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
@@ -199,7 +207,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items, &h->b_R };
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
   for (int q = 1; q < MAX_CAND; q++) {
@@ -349,6 +357,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if ((rc = h->b_gp.ensure(sizeof(double) * 3 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_W.ensure(sizeof(double) * 18 * (size_t)std::max(n_slots, 1)))) return rc;
   if ((rc = h->b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
+  if ((rc = h->b_R.ensure(sizeof(double) * (36 * (size_t)std::max(n_pt, 1) + 2)))) return rc;      // + the work counter
   // accumulators: [H0 | gc | red(8) | Sm | rm]
   const size_t ncp = (size_t)std::max(nc, 1);
   h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 16; h->off_rm = h->off_Sm + ncp * ncp;
@@ -485,6 +494,19 @@ struct Prof {
   ~Prof() { if (h->profiling) { cudaEventRecord(b, h->stream); h->evs.push_back({ cat, a, b }); } }
 };
 
+struct TlScope {
+  McpBa* h; cudaStream_t s; cudaEvent_t b = nullptr;
+  TlScope(McpBa* h_, const char* name, int sid, cudaStream_t s_) : h(h_), s(s_)
+  {
+    if (!h->timeline) return;
+    cudaEvent_t a;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    h->tl.push_back({ name, sid, a, b });
+  }
+  ~TlScope() { if (b) cudaEventRecord(b, s); }
+};
+
 int sync_ctrl(McpBa* h)
 {
   MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->stream));
@@ -530,6 +552,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   int rc;
   auto aborted = [&]() { return abort_flag && *abort_flag; };
 
+  { const char* e = getenv("MCP_BA_TIMELINE"); h->timeline = e && e[0] == '1'; }
   if ((rc = sync_ctrl(h))) return rc;
   c.need_lambda_init = 1; c.user_lambda = user_lambda; c.iter = 0; c.conv_mag = 0; c.conv_res = 0; c.total_trials = 0;
   c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0;
@@ -579,7 +602,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
       }
       MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
-      { Prof p(h, C_LIN); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); h->launches++; }
+      { Prof p(h, C_LIN); TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); h->launches++; }
     }
     next_iteration_started = false;
     if (multi) {
@@ -598,14 +621,29 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
       // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
       const int n_cand = (single_step || h->profiling) ? 1 : (multi ? std::min(h->n_spec, h->n_spec_multi) : h->n_spec);
-      if (!first) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
       CandParts parts;
       for (int q = 0; q < MAX_CAND; q++) parts.p[q] = d.part;
-      if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
-      { Prof p(h, C_SCHUR); launch_schur_gather(d, s); h->launches++; }
+      // 2 or 3 candidates: ONE pass over the co-visibility lists reduces every candidate's camera system
+      // (k_schur_pairs_multi); otherwise one reduction per candidate on its own stream
+      const bool fused = h->fuse_schur && d.schur_mode == 1 && n_cand >= 2 && n_cand <= 3;
+      if (!first && !fused) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
+      if (n_cand > 1 && !fused) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
+      if (fused) {
+        SchurMulti mc;
+        memset(&mc, 0, sizeof(mc));
+        mc.n_cand = n_cand; mc.R = h->b_R.as<double>(); mc.sm_doubles = sm_doubles;
+        mc.next_item = reinterpret_cast<int*>(mc.R + 36 * (size_t)std::max(d.n_pt, 1));
+        mc.Sm[0] = d.Sm; mc.rm[0] = d.rm;
+        mc.zero_mask = first ? 0 : 1;                    // candidate 0 shares the accumulator zeroed before the linearisation
+        for (int q = 1; q < n_cand; q++) { mc.Sm[q] = h->cand[q].d.Sm; mc.rm[q] = h->cand[q].d.rm; mc.zero_mask |= 1 << q; }
+        { Prof p(h, C_SCHUR); TlScope t(h, "schur", 0, s); launch_schur_multi(d, mc, s); h->launches += 2; }
+        if (!multi) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
+      } else {
+        Prof p(h, C_SCHUR); TlScope t(h, "schur", 0, s); launch_schur_gather(d, s); h->launches++;
+      }
       if (multi) {
         // every candidate's reduced camera system goes through ONE grouped all-reduce (one NCCL launch) per round
-        for (int q = 1; q < n_cand; q++) {
+        for (int q = 1; q < n_cand && !fused; q++) {
           McpBa::Cand& cq = h->cand[q];
           MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
           MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
@@ -620,8 +658,8 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         NCCL_CHECK(ncclGroupEnd());
         if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_red, s));
       }
-      { Prof p(h, C_SOLVE); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
-      { Prof p(h, C_BACKSUB); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
+      { Prof p(h, C_SOLVE); TlScope t(h, "solve", 0, s); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
+      { Prof p(h, C_BACKSUB); TlScope t(h, "backsub", 0, s); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
       for (int q = 1; q < n_cand; q++) {
         McpBa::Cand& cq = h->cand[q];
         parts.p[q] = cq.d.part;
@@ -629,12 +667,14 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
           MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_red, 0));
         } else {
           MCP_CUDA_CHECK(cudaStreamWaitEvent(cq.stream, h->ev_ready, 0));
-          MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
-          launch_schur_gather(cq.d, cq.stream);
-          h->launches += 2;
+          if (!fused) {
+            MCP_CUDA_CHECK(cudaMemsetAsync(cq.d.Sm, 0, sizeof(double) * sm_doubles, cq.stream));
+            { TlScope t(h, "schur", q, cq.stream); launch_schur_gather(cq.d, cq.stream); }
+            h->launches += 2;
+          }
         }
-        launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms, cq.stream);
-        launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream);
+        { TlScope t(h, "solve", q, cq.stream); launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms, cq.stream); }
+        { TlScope t(h, "backsub", q, cq.stream); launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream); }
         h->launches += 2;
         if (multi) { launch_reduce_partials(cq.d, 0, n_bs, red + 3 * q, cq.stream); h->launches++; }
         MCP_CUDA_CHECK(cudaEventRecord(cq.ev_done, cq.stream));
@@ -643,7 +683,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       if (multi) { launch_reduce_partials(d, 0, n_bs, red, s); h->launches++; }
       for (int q = 1; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->cand[q].ev_done, 0));
       if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand, ncclDouble, ncclSum, h->comm, s));
-      { Prof p(h, C_CONTROL); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
+      { Prof p(h, C_CONTROL); TlScope t(h, "control", 0, s); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
       const bool ahead = can_look_ahead && it + 1 < n_iter;
       if (ahead) {
@@ -651,9 +691,9 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         MCP_CUDA_CHECK(cudaEventRecord(h->ev_ctrl, s));
         MCP_CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_ctrl, 0));
         MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (h->cfg.use_robust) h->launches += launch_select_sigma(d_ahead, -1, 0, s);
+        if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s); }
         launch_zero_acc(d_ahead, acc, h->acc_doubles, s);
-        n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s);
+        { TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s); }
         h->launches += 3;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
       } else if ((rc = sync_ctrl(h))) return rc;
@@ -673,6 +713,16 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     if (c.conv_mag || c.conv_res) local_abort = true;
   }
   MCP_CUDA_CHECK(cudaEventRecord(h->ev1, s));
+  if (h->timeline) {
+    cudaDeviceSynchronize();
+    for (const McpBa::Tl& e : h->tl) {
+      float ta = 0, tb = 0;
+      cudaEventElapsedTime(&ta, h->ev0, e.a); cudaEventElapsedTime(&tb, h->ev0, e.b);
+      fprintf(stderr, "TL %s %d %.1f %.1f\n", e.name, e.sid, 1e3 * ta, 1e3 * tb);
+      cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    h->tl.clear();
+  }
 
   // "AFTER" block (src/ChainBundle.cc:1338-1345): errors + sigma of the final state
   eval_state(h, -1, nullptr);

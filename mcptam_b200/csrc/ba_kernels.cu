@@ -873,7 +873,6 @@ __global__ void k_lambda_apply(BaDev d)
 __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, int n_cand, int n_part_lin, int n_part_bs,
                                                    const double* red_in, int first_trial)
 {
-  __shared__ double red[32];
   __shared__ double s_sum[MAX_CAND][4];
   if (red_in) {
     // red_in = { cur_chi, (tmp_chi, scale, sumsq) per candidate }
@@ -882,20 +881,36 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
       for (int cnd = 0; cnd < n_cand; cnd++) { s_sum[cnd][1] = red_in[1 + 3 * cnd]; s_sum[cnd][2] = red_in[2 + 3 * cnd]; s_sum[cnd][3] = red_in[3 + 3 * cnd]; }
     }
   } else {
-    double a = 0;
-    for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
-    a = block_sum(a, red);
-    if (threadIdx.x == 0) s_sum[0][0] = a;
-    for (int cnd = 0; cnd < n_cand; cnd++) {
-      const double* part = parts.p[cnd];
-      double b = 0, c = 0, e = 0;
-      for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
-        b += part[PART_TMP_CHI * MAX_PARTIALS + i];
-        c += part[PART_SCALE * MAX_PARTIALS + i];
-        e += part[PART_SUMSQ * MAX_PARTIALS + i];
+    // every partial sum is loaded before the first reduction (one round of independent loads instead of ten
+    // dependent ones), then the 1 + 3 n_cand values are reduced together
+    double v[1 + 3 * MAX_CAND];
+#pragma unroll
+    for (int k = 0; k < 1 + 3 * MAX_CAND; k++) v[k] = 0.0;
+    for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) v[0] += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
+#pragma unroll
+    for (int cnd = 0; cnd < MAX_CAND; cnd++) {
+      if (cnd < n_cand) {
+        const double* part = parts.p[cnd];
+        for (int i = threadIdx.x; i < n_part_bs; i += blockDim.x) {
+          v[1 + 3 * cnd] += part[PART_TMP_CHI * MAX_PARTIALS + i];
+          v[2 + 3 * cnd] += part[PART_SCALE * MAX_PARTIALS + i];
+          v[3 + 3 * cnd] += part[PART_SUMSQ * MAX_PARTIALS + i];
+        }
       }
-      b = block_sum(b, red); c = block_sum(c, red); e = block_sum(e, red);
-      if (threadIdx.x == 0) { s_sum[cnd][1] = b; s_sum[cnd][2] = c; s_sum[cnd][3] = e; }
+    }
+    __shared__ double s_red[1 + 3 * MAX_CAND][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 1 + 3 * MAX_CAND; k++) {
+      const double w = warp_sum(v[k]);
+      if (lane == 0) s_red[k][wid] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 1 + 3 * MAX_CAND) {
+      double t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_red[threadIdx.x][w];
+      if (threadIdx.x == 0) s_sum[0][0] = t;
+      else s_sum[(threadIdx.x - 1) / 3][1 + (threadIdx.x - 1) % 3] = t;
     }
   }
   __syncthreads();

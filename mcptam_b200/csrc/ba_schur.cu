@@ -8,6 +8,7 @@
 //   k_schur_pairs  one warp per block-pair chunk: lanes stride the incidence list, each lane accumulates a
 //                  private 6x6 block  Y_A W_B^T  in registers, one warp reduction, 36 adds per chunk.
 // Reads are 144-byte contiguous records served from L2; there is no per-incidence atomic.
+#include <algorithm>
 #include <cstdlib>
 
 #include "ba_types.cuh"
@@ -29,25 +30,22 @@ __device__ __forceinline__ bool inv3_sym_s(const double* V6, double lambda, doub
 }
 
 // ---- load-time construction of the co-visibility lists ------------------------------------------------
+// one thread per (point, slot) entry x: the incidences (x, y >= x) of its point
 __global__ void k_pair_count(BaDev d, int* __restrict__ cnt)
 {
-  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
-    if (d.pt_var[p] < 0) continue;
-    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
-    for (int x = 0; x < K; x++)
-      for (int y = x; y < K; y++) atomicAdd(&cnt[pair_id(d.slot_var[s0 + x], d.slot_var[s0 + y], d.n_pose_var)], 1);
+  for (int s = d.slot_lo + blockIdx.x * blockDim.x + threadIdx.x; s < d.slot_hi; s += gridDim.x * blockDim.x) {
+    const int s_end = d.pt_slot_off[d.slot_pt[s] + 1], a = d.slot_var[s];
+    for (int y = s; y < s_end; y++) atomicAdd(&cnt[pair_id(a, d.slot_var[y], d.n_pose_var)], 1);
   }
 }
 __global__ void k_pair_fill(BaDev d, int* __restrict__ cursor, int2* __restrict__ inc)
 {
-  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
-    if (d.pt_var[p] < 0) continue;
-    const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
-    for (int x = 0; x < K; x++)
-      for (int y = x; y < K; y++) {
-        const int pos = atomicAdd(&cursor[pair_id(d.slot_var[s0 + x], d.slot_var[s0 + y], d.n_pose_var)], 1);
-        inc[pos] = make_int2(s0 + x, s0 + y);
-      }
+  for (int s = d.slot_lo + blockIdx.x * blockDim.x + threadIdx.x; s < d.slot_hi; s += gridDim.x * blockDim.x) {
+    const int s_end = d.pt_slot_off[d.slot_pt[s] + 1], a = d.slot_var[s];
+    for (int y = s; y < s_end; y++) {
+      const int pos = atomicAdd(&cursor[pair_id(a, d.slot_var[y], d.n_pose_var)], 1);
+      inc[pos] = make_int2(s, y);
+    }
   }
 }
 
@@ -297,6 +295,291 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-candidate Schur reduction.  The speculative LM candidates of one trial round differ only in lambda, i.e. in
+// the 3x3 inverse (V_p + lambda_c I)^-1 of every point; W, the co-visibility lists and the work items are shared.
+// Three separate pair kernels (one per candidate stream) each saturate the copy engine and serialise (timeline:
+// 3 x ~52 us on the critical path of the round).  Here ONE pass over the incidence lists serves all candidates:
+//   k_schur_vinv_multi   per point: R_p = [Vinv_0 | Vinv_1 | Vinv_2 | u_0 | u_1 | u_2], u_c = Vinv_c g_p   (288 B)
+//   k_schur_pairs_multi  per incidence three bulk copies -- W_A, W_B (144 B each) and R_p -- instead of two per
+//                        candidate; Y_A^(c) = W_A Vinv_c is formed in registers on the way into the fp64 tensor-core
+//                        MMA (same expression as k_schur_y: identical rounding), z_A^(c) = W_A u_c on diagonal items.
+// ---------------------------------------------------------------------------------------------
+constexpr int MG_CA = 16;                    // incidences per group of the cp.async variant
+constexpr int MRECD = 72;                    // doubles per staged incidence: W_A(18) W_B(18) R(36)
+constexpr int RPD = 36;                      // doubles per point record
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_schur_vinv_multi(BaDev d, SchurMulti mc)
+{
+  double lam[NC];
+  {
+    double l = d.ctrl->lambda, ni = d.ctrl->ni;
+#pragma unroll
+    for (int c = 0; c < NC; c++) { lam[c] = l; l *= ni; ni *= 2; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *mc.next_item = mc.first_dynamic_item;
+  // the reduced systems accumulate by atomics: clear them here instead of one memset per candidate in the stream
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+    if (mc.zero_mask & (1 << c))
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mc.sm_doubles; i += (size_t)gridDim.x * blockDim.x) mc.Sm[c][i] = 0.0;
+  int fail = 0;
+  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
+    if (d.pt_var[p] < 0) continue;
+    double V6[6], gp[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
+    double* R = mc.R + RPD * (size_t)p;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      double Vi[9];
+      if (!inv3_sym_s(V6, lam[c], Vi)) fail |= 1 << c;
+#pragma unroll
+      for (int i = 0; i < 9; i++) R[9 * c + i] = Vi[i];
+#pragma unroll
+      for (int r = 0; r < 3; r++) R[27 + 3 * c + r] = Vi[3 * r] * gp[0] + Vi[3 * r + 1] * gp[1] + Vi[3 * r + 2] * gp[2];
+    }
+#pragma unroll
+    for (int c = NC; c < 3; c++) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) R[9 * c + i] = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; r++) R[27 + 3 * c + r] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+    if (fail & (1 << c)) atomicExch(&d.ctrl->solve_ok[c], 0);
+}
+
+template <int NC, int MG>
+__global__ void __launch_bounds__(TW * 32) k_schur_pairs_multi(BaDev d, SchurMulti mc)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* stage = reinterpret_cast<double*>(smem_raw) + (size_t)wid * 2 * MG * MRECD;          // [2][MG][MRECD]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)TW * 2 * MG * MRECD * sizeof(double)) + wid * 2;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  const int g = lane >> 2, kk = lane & 3;              // fragment coordinates
+  // per-phase offsets inside a 4-incidence (12 k) block: k = 4p + kk -> (incidence q, component t)
+  int offW[3], offV[3], offB[3];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int k = 4 * p + kk, q = k / 3, t = k - 3 * q;
+    offW[p] = q * MRECD + g * 3;                       // W_A,q[g][0..2]
+    offV[p] = q * MRECD + 36 + 3 * t;                  // Vinv_c,q[t][0..2] (+ 9 c; symmetric: row t = column t)
+    offB[p] = q * MRECD + 18 + g * 3 + t;              // W_B,q[g][t]
+  }
+  const bool gvalid = g < 6;
+  unsigned phase[2] = { 0u, 0u };
+  const int n_items = __ldg(d.n_items_dev);
+  for (int it = gw; it < n_items; it += nw) {
+    const int4 item = d.items[it];
+    const bool diag = item.x == item.y;
+    const int n_groups = (item.w - item.z + MG - 1) / MG;
+    double acc[NC][4], accz[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0; accz[c] = 0.0; }
+    auto issue = [&](int grp, int buf) {
+      const int g0 = item.z + grp * MG, ng = min(MG, item.w - g0);
+      double* st = stage + (size_t)buf * MG * MRECD;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&bars[buf], (unsigned)ng * (unsigned)(MRECD * sizeof(double)));
+      __syncwarp();
+      if (lane < ng) {
+        const int2 ab = d.inc[g0 + lane];
+        const int pt = __ldg(d.slot_pt + ab.x);
+        bulk_g2s(st + lane * MRECD, d.W + 18 * (size_t)ab.x, 144u, &bars[buf]);
+        bulk_g2s(st + lane * MRECD + 18, d.W + 18 * (size_t)ab.y, 144u, &bars[buf]);
+        bulk_g2s(st + lane * MRECD + 36, mc.R + RPD * (size_t)pt, (unsigned)(RPD * sizeof(double)), &bars[buf]);
+      } else if (lane < MG) {
+        for (int i = 0; i < MRECD; i++) st[lane * MRECD + i] = 0.0;        // zero padding of a partial group
+      }
+    };
+    issue(0, 0);
+    for (int grp = 0; grp < n_groups; grp++) {
+      const int buf = grp & 1;
+      if (grp + 1 < n_groups) issue(grp + 1, buf ^ 1);
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      __syncwarp();
+      const double* st = stage + (size_t)buf * MG * MRECD;
+#pragma unroll
+      for (int m = 0; m < MG / 4; m++) {
+        const double* blk = st + m * 4 * MRECD;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          const double w0 = blk[offW[p]], w1 = blk[offW[p] + 1], w2 = blk[offW[p] + 2];
+          const double b = gvalid ? blk[offB[p]] : 0.0;
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const double* v = blk + offV[p] + 9 * c;
+            double a = w0 * v[0] + w1 * v[1] + w2 * v[2];
+            a = gvalid ? a : 0.0;
+            dmma_m8n8k4(acc[c][2 * (m & 1)], acc[c][2 * (m & 1) + 1], a, b);
+          }
+        }
+      }
+      if (diag && lane < 6) {
+#pragma unroll 4
+        for (int q = 0; q < MG; q++) {
+          const double* rec = st + q * MRECD;
+          const double w0 = rec[lane * 3], w1 = rec[lane * 3 + 1], w2 = rec[lane * 3 + 2];
+#pragma unroll
+          for (int c = 0; c < NC; c++) accz[c] += w0 * rec[63 + 3 * c] + w1 * rec[64 + 3 * c] + w2 * rec[65 + 3 * c];
+        }
+      }
+      __syncwarp();
+    }
+    // D fragment: row g, cols 2*kk, 2*kk+1
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (g < 6) {
+        double* base = mc.Sm[c] + (size_t)(6 * item.x + g) * nc + 6 * item.y;
+        if (2 * kk < 6) atomicAdd(base + 2 * kk, acc[c][0] + acc[c][2]);
+        if (2 * kk + 1 < 6) atomicAdd(base + 2 * kk + 1, acc[c][1] + acc[c][3]);
+      }
+      if (diag && lane < 6) atomicAdd(mc.rm[c] + 6 * item.x + lane, accz[c]);
+    }
+  }
+}
+
+// The same reduction with the staging done by the warp itself: 16-byte cp.async (LDGSTS) pieces, 32 per
+// instruction, instead of three bulk copies per incidence.  The bulk-copy version runs at the copy engine's
+// per-operation rate (~1 small copy per 20 cycles per SM: 1.16 M copies -> ~90 us at 200 KF / 10 k points) although
+// the bytes are a fraction of what the L2 can deliver; 36 pieces per incidence through the LSU cost 18 warp
+// instructions per group of 16 incidences.
+template <int NC>
+__global__ void __launch_bounds__(TW * 32, 3) k_schur_pairs_multi_ca(BaDev d, SchurMulti mc)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* stage = reinterpret_cast<double*>(smem_raw) + (size_t)wid * 2 * MG_CA * MRECD;          // [2][MG_CA][MRECD]
+  // per staged incidence the three source pointers (W_A, W_B, R_p), section-major: [2][3][MG_CA]
+  unsigned long long* ptrs = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)TW * 2 * MG_CA * MRECD * sizeof(double)) + wid * 2 * 3 * MG_CA;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = d.nc;
+  const int g = lane >> 2, kk = lane & 3;              // fragment coordinates
+  int offW[3], offV[3], offB[3];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int k = 4 * p + kk, q = k / 3, t = k - 3 * q;
+    offW[p] = q * MRECD + g * 3;
+    offV[p] = q * MRECD + 36 + 3 * t;
+    offB[p] = q * MRECD + 18 + g * 3 + t;
+  }
+  const bool gvalid = g < 6;
+  const unsigned long long Wb = reinterpret_cast<unsigned long long>(d.W), Rb = reinterpret_cast<unsigned long long>(mc.R);
+  const int n_items = __ldg(d.n_items_dev);
+  // the first item of a warp is its index, further ones come from a device counter (cleared by k_schur_vinv_multi):
+  // items range from 1 to 128 incidences, a static round-robin leaves a tail
+  (void)nw;
+  for (int it = gw; it < n_items;) {
+    const int4 item = d.items[it];
+    {
+      int nx = 0;
+      if (lane == 0) nx = atomicAdd(mc.next_item, 1);
+      it = __shfl_sync(0xffffffffu, nx, 0);
+    }
+    const bool diag = item.x == item.y;
+    const int n_groups = (item.w - item.z + MG_CA - 1) / MG_CA;
+    double acc[NC][4], accz[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0; accz[c] = 0.0; }
+    // lane q < MG_CA: indices {slot A, slot B, point} of incidence q of a group, -1 beyond the end of the item.  They
+    // are fetched one group ahead of the copies that need them (two dependent L2 round trips, hidden by the compute).
+    auto load_idx = [&](int grp) -> int3 {
+      int3 o = make_int3(-1, 0, 0);
+      const int e = item.z + grp * MG_CA + lane;
+      if (lane < MG_CA && grp < n_groups && e < item.w) {
+        const int2 ab = d.inc[e];
+        o = make_int3(ab.x, ab.y, __ldg(d.slot_pt + ab.x));
+      }
+      return o;
+    };
+    auto issue = [&](const int3 o, int buf) {
+      unsigned long long* pt = ptrs + buf * 3 * MG_CA;
+      if (lane < MG_CA) {
+        const bool on = o.x >= 0;
+        pt[lane] = on ? Wb + 144ull * (unsigned)o.x : 0ull;
+        pt[MG_CA + lane] = on ? Wb + 144ull * (unsigned)o.y : 0ull;
+        pt[2 * MG_CA + lane] = on ? Rb + 288ull * (unsigned)o.z : 0ull;
+      }
+      __syncwarp();
+      const unsigned dst0 = smem_u32(stage + (size_t)buf * MG_CA * MRECD);
+      int q = lane / 36, pc = lane - 36 * q;             // piece j = 32 i + lane of the group: incidence q, 16-byte piece pc
+#pragma unroll 6
+      for (int i = 0; i < MG_CA * 36 / 32; i++) {
+        const int sec = (pc >= 9) + (pc >= 18);          // 0: W_A, 1: W_B, 2: R_p
+        const unsigned long long base = pt[sec * MG_CA + q];
+        const unsigned long long src = base + (unsigned)(16 * (pc - 9 * sec));
+        const unsigned nbytes = base ? 16u : 0u;         // 0: zero fill (padding of a partial group)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (unsigned)(q * MRECD * 8 + pc * 16)), "l"(base ? src : Wb), "r"(nbytes) : "memory");
+        pc += 32;
+        if (pc >= 36) { pc -= 36; q++; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int3 o_next = load_idx(0);
+    issue(o_next, 0);
+    o_next = load_idx(1);
+    for (int grp = 0; grp < n_groups; grp++) {
+      const int buf = grp & 1;
+      if (grp + 1 < n_groups) {
+        issue(o_next, buf ^ 1);
+        o_next = load_idx(grp + 2);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+      const double* st = stage + (size_t)buf * MG_CA * MRECD;
+#pragma unroll
+      for (int m = 0; m < MG_CA / 4; m++) {
+        const double* blk = st + m * 4 * MRECD;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          const double w0 = blk[offW[p]], w1 = blk[offW[p] + 1], w2 = blk[offW[p] + 2];
+          const double b = gvalid ? blk[offB[p]] : 0.0;
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const double* v = blk + offV[p] + 9 * c;
+            double a = w0 * v[0] + w1 * v[1] + w2 * v[2];
+            a = gvalid ? a : 0.0;
+            dmma_m8n8k4(acc[c][2 * (m & 1)], acc[c][2 * (m & 1) + 1], a, b);
+          }
+        }
+      }
+      if (diag && lane < 6) {
+#pragma unroll 4
+        for (int q = 0; q < MG_CA; q++) {
+          const double* rec = st + q * MRECD;
+          const double w0 = rec[lane * 3], w1 = rec[lane * 3 + 1], w2 = rec[lane * 3 + 2];
+#pragma unroll
+          for (int c = 0; c < NC; c++) accz[c] += w0 * rec[63 + 3 * c] + w1 * rec[64 + 3 * c] + w2 * rec[65 + 3 * c];
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (g < 6) {
+        double* base = mc.Sm[c] + (size_t)(6 * item.x + g) * nc + 6 * item.y;
+        if (2 * kk < 6) atomicAdd(base + 2 * kk, acc[c][0] + acc[c][2]);
+        if (2 * kk + 1 < 6) atomicAdd(base + 2 * kk + 1, acc[c][1] + acc[c][3]);
+      }
+      if (diag && lane < 6) atomicAdd(mc.rm[c] + 6 * item.x + lane, accz[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_schur_rows: row-wise formulation.  The pair kernels above fetch two small records per (point, pose pair)
 // incidence -- 870 k bulk copies of 144-192 bytes per launch at 200 KF / 10 k points, and the kernel runs at the
 // TMA's issue rate, not at L2 bandwidth.  Here a work item is ONE pose variable a and a run of the (point, slot)
@@ -532,9 +815,60 @@ __global__ void __launch_bounds__(256) k_marginals(BaDev d, double* __restrict__
 }
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s) { k_marginals<<<1, 256, 0, s>>>(d, cov); }
 
-void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148, 128, 0, s>>>(d, cnt); }
-void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148, 128, 0, s>>>(d, cursor, inc); }
+void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<<<148 * 4, 256, 0, s>>>(d, cnt); }
+void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148 * 4, 256, 0, s>>>(d, cursor, inc); }
 void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s) { k_pair_items<<<1, 1024, 0, s>>>(d, cnt, items, n_items_out); }
+// all candidates of a trial round in one pass (mc.n_cand = 2 or 3); the per-candidate Sm / rm must be zeroed before
+template <int NC, int MGT>
+static void launch_pairs_multi_tma(const BaDev& d, const SchurMulti& mc, cudaStream_t s)
+{
+  const size_t smem = (size_t)TW * 2 * MGT * MRECD * sizeof(double) + TW * 2 * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_schur_pairs_multi<NC, MGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const int per_sm = (int)std::min<size_t>(6, (220 * 1024) / smem);
+  int g2 = (d.max_items + TW - 1) / TW;
+  if (g2 < 1) g2 = 1;
+  if (g2 > 148 * per_sm) g2 = 148 * per_sm;
+  k_schur_pairs_multi<NC, MGT><<<g2, TW * 32, smem, s>>>(d, mc);
+}
+
+void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s)
+{
+  // MCP_BA_SCHUR_STAGE: "ca" (default) = 16-byte cp.async pieces through the LSU; "tma8" / "tma16" = three bulk
+  // copies per incidence, groups of 8 / 16 incidences (measured slower: profiles/README.md)
+  static const int stage_mode = [] {
+    const char* e = getenv("MCP_BA_SCHUR_STAGE");
+    if (!e || e[0] != 't') return 2;
+    return (e[1] && e[2] && e[3] == '1') ? 1 : 0;
+  }();
+  SchurMulti mc = mc_in;
+  int g2 = (d.max_items + TW - 1) / TW;
+  if (g2 < 1) g2 = 1;
+  if (g2 > 148 * 3) g2 = 148 * 3;
+  mc.first_dynamic_item = g2 * TW;
+  int g1 = (d.p_hi - d.p_lo + 255) / 256;
+  if (g1 < 148) g1 = 148;
+  if (mc.n_cand == 2) k_schur_vinv_multi<2><<<g1, 256, 0, s>>>(d, mc);
+  else k_schur_vinv_multi<3><<<g1, 256, 0, s>>>(d, mc);
+  if (stage_mode == 0) {
+    if (mc.n_cand == 2) launch_pairs_multi_tma<2, 8>(d, mc, s); else launch_pairs_multi_tma<3, 8>(d, mc, s);
+    return;
+  }
+  if (stage_mode == 1) {
+    if (mc.n_cand == 2) launch_pairs_multi_tma<2, 16>(d, mc, s); else launch_pairs_multi_tma<3, 16>(d, mc, s);
+    return;
+  }
+  const size_t smem_ca = (size_t)TW * 2 * MG_CA * MRECD * sizeof(double) + (size_t)TW * 2 * 3 * MG_CA * sizeof(unsigned long long);
+  static bool attr_ca = false;
+  if (!attr_ca) {
+    cudaFuncSetAttribute(k_schur_pairs_multi_ca<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ca);
+    cudaFuncSetAttribute(k_schur_pairs_multi_ca<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ca);
+    attr_ca = true;
+  }
+  if (mc.n_cand == 2) k_schur_pairs_multi_ca<2><<<g2, TW * 32, smem_ca, s>>>(d, mc);
+  else k_schur_pairs_multi_ca<3><<<g2, TW * 32, smem_ca, s>>>(d, mc);
+}
+
 void launch_schur_gather(const BaDev& d, cudaStream_t s)
 {
   const int nslots = d.slot_hi - d.slot_lo;

@@ -126,6 +126,15 @@ __device__ __forceinline__ bool lookahead_skip(const BaDev& d)
 }
 __device__ __forceinline__ int trial_buffer(const BaDev& d, int cur) { return (cur + 1 + d.cand) % N_STATE; }
 
+// per-candidate outputs of the multi-candidate Schur reduction and the shared per-point record array
+struct SchurMulti {
+  double* Sm[3]; double* rm[3]; double* R;
+  int n_cand, zero_mask;          // bit c of zero_mask: k_schur_vinv_multi clears candidate c's [Sm | rm] first
+  size_t sm_doubles;              // doubles in one [Sm | rm] buffer
+  int* next_item;                 // work counter of k_schur_pairs_multi_ca, set to first_dynamic_item by k_schur_vinv_multi
+  int first_dynamic_item, pad;    // = number of warps of the pair kernel (every warp starts on its own index)
+};
+
 struct CandParts { const double* p[MAX_CAND]; };   // per-candidate partial-sum arrays handed to k_lm_control
 
 enum PartialRow { PART_CUR_CHI = 0, PART_MAXDIAG = 1, PART_TMP_CHI = 2, PART_SCALE = 3, PART_SUMSQ = 4 };

@@ -113,6 +113,30 @@ def test_compute_parity(capi, cfg, seed, iters):
     assert sorted(g.outliers().tolist()) == sorted(o.outliers().tolist())
 
 
+@pytest.mark.parametrize("cfg,seed,iters", [("cfg1", 0, 8), ("cfg2", 0, 4)])
+def test_speculation_variants_give_the_same_iterates(capi, monkeypatch, cfg, seed, iters):
+    """Sequential trials (MCP_BA_SPECULATE=1), 2 and 3 concurrent candidates, and the fused multi-candidate Schur
+    pass on/off (MCP_BA_FUSE_SCHUR) walk through the same lambda sequence and end in the same state."""
+    prob = _mk(cfg, seed)
+    res = {}
+    for name, env in [("seq", {"MCP_BA_SPECULATE": "1"}), ("spec2", {"MCP_BA_SPECULATE": "2"}), ("spec3", {}),
+                      ("spec3_unfused", {"MCP_BA_FUSE_SCHUR": "0"}), ("spec4", {"MCP_BA_SPECULATE": "4"})]:
+        for k in ("MCP_BA_SPECULATE", "MCP_BA_FUSE_SCHUR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = capi.BaHandle()
+        g.load(prob)
+        rc, st = g.compute(iters)
+        res[name] = (rc, st.total_trials, st.lambda_, st.chi2_after, g.poses().copy(), g.points().copy())
+    ref = res["seq"]
+    for name, r in res.items():
+        assert r[0] == ref[0] and r[1] == ref[1], name
+        assert abs(r[2] - ref[2]) <= 1e-9 * ref[2], name
+        assert abs(r[3] - ref[3]) <= 1e-9 * ref[3], name
+        assert _rel(r[4], ref[4]) < 1e-9 and _rel(r[5], ref[5]) < 1e-9, name
+
+
 def test_two_step_and_reset(capi):
     """Compute twice on the same handle (BundleAdjusterMulti two-step, src/BundleAdjusterMulti.cc:210-223)."""
     from oracle.oracle import OracleBA
