@@ -34,7 +34,7 @@ void set_last_error(const char* fmt, ...)
 // launchers defined in ba_kernels.cu
 int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s);
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
-int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s);
+int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr = nullptr, size_t zero_n = 0);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
 void launch_lambda_init(const BaDev& d, cudaStream_t s);
 void launch_lambda_apply(const BaDev& d, cudaStream_t s);
@@ -691,10 +691,11 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         MCP_CUDA_CHECK(cudaEventRecord(h->ev_ctrl, s));
         MCP_CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_ctrl, 0));
         MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s); }
-        launch_zero_acc(d_ahead, acc, h->acc_doubles, s);
+        // the sigma selection also clears the accumulators of the next linearisation
+        if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s, acc, h->acc_doubles); }
+        else { launch_zero_acc(d_ahead, acc, h->acc_doubles, s); h->launches++; }
         { TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s); }
-        h->launches += 3;
+        h->launches += 2;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
       } else if ((rc = sync_ctrl(h))) return rc;
       if (c.cand_used > 1) h->spec_used++;

@@ -693,9 +693,12 @@ constexpr int SELC_CAP = SELC_CTAS * SELC_THREADS * SELC_K;      // 131072
 constexpr int SELC_COPIES = 8;                                   // histogram replicas per CTA (lane & 7)
 constexpr size_t SELC_SMEM = sizeof(unsigned) * (size_t)(SELC_COPIES + 2) * SEL_BINS;
 
-__global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode)
+__global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode, double* zero_ptr,
+                                                                                                   size_t zero_n)
 {
   if (lookahead_skip(d)) return;                                  // uniform over the whole cluster
+  // look-ahead launches: the accumulators of the next linearisation are cleared here instead of by a kernel of their own
+  for (size_t i = (size_t)blockIdx.x * SELC_THREADS + threadIdx.x; i < zero_n; i += (size_t)SELC_CTAS * SELC_THREADS) zero_ptr[i] = 0.0;
   namespace cg = cooperative_groups;
   // The first digit is the exponent: a handful of hot bins.  Same-address shared-memory atomics serialise, so every
   // CTA keeps SELC_COPIES replicas of the histogram (replica = lane & 7, interleaved so that replicas of one bin sit in
@@ -1094,10 +1097,11 @@ int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, c
   k_backsub_eval<<<g, 256, sizeof(double) * d.stage_doubles, s>>>(d, apply, which, err_out);
   return g;
 }
-int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s)
+int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr, size_t zero_n)
 {
   static const bool multi_launch = [] { const char* e = getenv("MCP_BA_SELECT_MULTI"); return e && e[0] == '1'; }();
-  if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, SELC_SMEM, s>>>(d, which, mode); return 1; }
+  if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, SELC_SMEM, s>>>(d, which, mode, zero_ptr, zero_n); return 1; }
+  if (zero_n) launch_zero_acc(d, zero_ptr, zero_n, s);
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
   if (grid > 148) grid = 148;
