@@ -2,6 +2,7 @@
 // (include/mcptam/{KeyFrame,MapPoint,Map}.h).  In a real MCPTAM tree include those headers instead.
 #pragma once
 
+#include <list>
 #include <map>
 #include <set>
 #include <string>
@@ -43,18 +44,27 @@ typedef std::map<std::string, KeyFrame*> KeyFramePtrMap;
 struct MultiKeyFrame {
   SE3 mse3BaseFromWorld;
   bool mbFixed = false, mbBad = false;
+  int mnID = -1;
   KeyFramePtrMap mmpKeyFrames;
   void RefreshSceneDepthRobust() {}
 };
 struct MapPoint {
   Vector<3> mv3WorldPos;
   bool mbFixed = false, mbBad = false, mbOptimized = false;
+  int mnID = -1;
   KeyFrame* mpPatchSourceKF = nullptr;
   int mnSourceLevel = 0;
   ImageRef mirCenter;
   Vector<3> mv3PixelRight_W, mv3PixelDown_W;
   struct { std::set<KeyFrame*> spMeasurementKFs; int GoodMeasCount() const { return (int)spMeasurementKFs.size(); } } mMMData;
   void RefreshPixelVectors() {}
+};
+
+typedef std::list<MultiKeyFrame*> MultiKeyFramePtrList;
+typedef std::list<MapPoint*> MapPointPtrList;
+struct Map {                      // include/mcptam/Map.h: the two lists the dump / load code walks
+  MultiKeyFramePtrList mlpMultiKeyFrames;
+  MapPointPtrList mlpPoints;
 };
 
 }  // namespace mcp_shim
