@@ -199,7 +199,9 @@ typedef struct McpPatchReq {
   int32_t pred_x, pred_y;       /* CVD::ir(td.mv2Image) */
   int32_t range;                /* nRange, level-0 pixels */
   int32_t subpix_its;           /* nSubPixIts (0 = none) */
-  int32_t exhaustive;           /* bExhaustive || point.mbFixed */
+  int32_t exhaustive;           /* bExhaustive || point.mbFixed; 2: no coarse search -- pred_x / pred_y are a coarse match
+                                   (irBest, search-level coordinates) and only the sub-pixel iteration runs from it
+                                   (SetSubPixPos + IterateSubPixToConvergence, src/MapMakerServerBase.cc:832-846) */
 } McpPatchReq;
 
 typedef struct McpPatchRes {

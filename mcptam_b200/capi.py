@@ -57,11 +57,28 @@ def lib_path() -> str:
     return _build.LIB
 
 
+def _preload_bundled_nccl():
+    """torch ships its own libnccl.so.2 under site-packages/nvidia/nccl -- the same SONAME as the system NCCL the library
+    is linked against, so whichever is loaded first serves both.  Loading the bundled one first keeps a later
+    `import torch` in the same process working (its libtorch_cuda.so needs symbols the older system NCCL lacks)."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass                                    # no bundled NCCL: the system one is used
+
+
 def lib():
     """Loads libmcptam_b200.so (building it with nvcc if the tree is newer)."""
     global _lib
     if _lib is None:
         path = _build.build()
+        _preload_bundled_nccl()
         if not os.path.exists(path):
             raise RuntimeError("libmcptam_b200.so is missing: the CUDA extension must be built (no CPU fallback)")
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)

@@ -406,7 +406,11 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
   if (nLeft < 0) nLeft = 0;
   if (nLeft >= T.w) early = true;
   int best_ssd = max_ssd + 1, best_idx = 0x7fffffff, best_x = 0, best_y = 0, n_valid = 0;
-  if (!early) {
+  if (rq.exhaustive == 2) {
+    // PatchFinder::SetSubPixPos on a coarse match found earlier (AddPointEpipolar's second pass,
+    // src/MapMakerServerBase.cc:822-846): pred_x / pred_y ARE the match in search-level coordinates, no search
+    early = false; best_ssd = 0; best_x = rq.pred_x; best_y = rq.pred_y;
+  } else if (!early) {
     if (rq.exhaustive) {
       const int y_end = min(nBottomPlusOne, T.h), x_end = min(nRight + 1, T.w);
       const int bw = x_end - nLeft, bh = y_end - nTop;

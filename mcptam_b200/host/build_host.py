@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "..", "_build")
-SRCS = ["TaylorCamera.cc", "ChainBundle.cc", "BundleAdjusterCuda.cc", "FrontEnd.cc", "MapIO.cc"]
+SRCS = ["TaylorCamera.cc", "ChainBundle.cc", "BundleAdjusterCuda.cc", "FrontEnd.cc", "MapIO.cc", "Epipolar.cc"]
 
 
 def build(force=False):

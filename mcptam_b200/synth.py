@@ -441,3 +441,45 @@ def make_frame(w=640, h=480, seed=0, n_shapes=400, shift=(0.0, 0.0)) -> np.ndarr
         img[m] = val
     img += rng.standard_normal((h, w)) * 1.5
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# Two-view scene for the epipolar point creation tests: a textured plane rendered through the Taylor camera
+# ---------------------------------------------------------------------------------------------
+def render_plane_view(cam: TaylorCamStruct, cam_from_world, texture, plane_z=4.0, texel=0.0125):
+    """Image of the world plane z = plane_z (texture centred on the world z axis, `texel` metres per texture pixel) seen
+    by `cam` at pose cam_from_world (12 doubles: row-major R, t).  Bilinear texture lookup, 0 outside the texture."""
+    w, h = int(cam.image_size[0]), int(cam.image_size[1])
+    rt = np.asarray(cam_from_world, np.float64).reshape(-1)
+    R, t = rt[:9].reshape(3, 3), rt[9:]
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    rays_c = cam_unproject_np(cam, np.stack([xx, yy], -1))
+    rays_w = rays_c @ R                                   # R^T applied to every ray
+    origin = -R.T @ t
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lam = (plane_z - origin[2]) / rays_w[..., 2]
+    pw = origin + lam[..., None] * rays_w
+    th, tw = texture.shape
+    u = pw[..., 0] / texel + tw / 2.0
+    v = pw[..., 1] / texel + th / 2.0
+    ok = (lam > 0) & (u >= 0) & (u < tw - 1) & (v >= 0) & (v < th - 1)
+    u = np.where(ok, u, 0.0); v = np.where(ok, v, 0.0)
+    iu, iv = np.floor(u).astype(int), np.floor(v).astype(int)
+    fu, fv = u - iu, v - iv
+    tex = texture.astype(np.float64)
+    val = (tex[iv, iu] * (1 - fu) * (1 - fv) + tex[iv, iu + 1] * fu * (1 - fv) + tex[iv + 1, iu] * (1 - fu) * fv + tex[iv + 1, iu + 1] * fu * fv)
+    return np.where(ok, np.clip(np.rint(val), 0, 255), 0).astype(np.uint8)
+
+
+def make_stereo_scene(seed=0, baseline=0.5, plane_z=4.0, yaw=-0.04):
+    """Two cameras looking at a textured plane: returns dict(cam_a, cam_b, cfw_a, cfw_b (12 doubles), img_a, img_b,
+    plane_z).  Camera A sits at the world origin looking along +z."""
+    rng = np.random.default_rng(seed)
+    cams, _ = make_rig(2, rng)
+    texture = make_frame(w=1280, h=960, seed=seed + 11, n_shapes=500)
+    cfw_a = np.concatenate([np.eye(3).reshape(-1), np.zeros(3)])
+    Rb = so3_exp(np.array([0.01, yaw, 0.015]))
+    centre_b = np.array([baseline, 0.03, -0.05])
+    cfw_b = np.concatenate([Rb.reshape(-1), -Rb @ centre_b])
+    return dict(cam_a=cams[0], cam_b=cams[1], cfw_a=cfw_a, cfw_b=cfw_b, plane_z=plane_z,
+                img_a=render_plane_view(cams[0], cfw_a, texture, plane_z), img_b=render_plane_view(cams[1], cfw_b, texture, plane_z))

@@ -1,0 +1,146 @@
+"""Epipolar point creation (MapMakerServerBase::AddPointEpipolar, src/MapMakerServerBase.cc:604-914): the C++ host
+mirror (mcptam_b200/host/Epipolar.*, batched over the C ABI) against the CPU restatement oracle/epipolar.py.
+
+CPU part: the pure host pieces (un-projection, one-pixel angle, epipolar-arc hypotheses, pixel vectors,
+triangulation).  GPU part: the whole search on a rendered two-view scene, candidate by candidate."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from mcptam_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class EpiRes(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in "ok reason n_steps n_matches best best_score subpix_from pad_".split()] + \
+               [("world", C.c_double * 3), ("root", C.c_double * 2), ("subpix", C.c_double * 2)]
+
+
+REASONS = {0: "", 1: "endpoints", 2: "no match", 3: "ambiguous count", 4: "ambiguous index", 5: "subpix"}
+
+
+@pytest.fixture(scope="module")
+def host():
+    from mcptam_b200 import capi
+    capi.lib()                                  # builds and loads libmcptam_b200.so (RTLD_GLOBAL)
+    spec = importlib.util.spec_from_file_location("build_host", os.path.join(ROOT, "mcptam_b200", "host", "build_host.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    L = C.CDLL(os.path.join(ROOT, "mcptam_b200", "_build", "libmcptam_host.so"))
+    L.mcp_host_one_pixel_angle.restype = C.c_double
+    L.mcp_host_epi_hypotheses.argtypes = [C.c_void_p] * 3 + [C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 3
+    L.mcp_host_add_points_epipolar.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _two_poses(seed):
+    rng = np.random.default_rng(seed)
+    Ra = synth.so3_exp(0.2 * rng.standard_normal(3))
+    Rb = synth.so3_exp(0.2 * rng.standard_normal(3))
+    ca, cb = rng.standard_normal(3), rng.standard_normal(3) + np.array([0.6, 0.1, 0.0])
+    return np.concatenate([Ra.reshape(-1), -Ra @ ca]), np.concatenate([Rb.reshape(-1), -Rb @ cb])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_host_pieces_match_the_restatement(host, seed):
+    from oracle import epipolar as E
+    rng = np.random.default_rng(seed)
+    cams, _ = synth.make_rig(2, rng)
+    cam = cams[0]
+    # UnProject, OnePixelAngle
+    for px in ([320.0, 240.0], [10.5, 470.25], [630.0, 3.0], [cam.center[0], cam.center[1]]):
+        out = np.zeros(3)
+        host.mcp_host_unproject(C.byref(cam), _p(np.array(px)), _p(out))
+        assert np.allclose(out, E._unproject(cam, px), rtol=0, atol=1e-15)
+    assert abs(host.mcp_host_one_pixel_angle(C.byref(cam)) - E.one_pixel_angle(cam)) < 1e-12     # acos near 1
+    # hypotheses along the epipolar arc
+    src, tgt = _two_poses(seed)
+    sR, st, tR, tt = src[:9].reshape(3, 3), src[9:], tgt[:9].reshape(3, 3), tgt[9:]
+    for level, px in [(0, [300.0, 200.0]), (1, [420.5, 260.5]), (2, [101.5, 333.5]), (3, [323.5, 243.5])]:
+        ray = E._unproject(cams[0], px)
+        ref = E.hypotheses(cams[1], sR, st, tR, tt, ray, level)
+        cap = 4096
+        world, tc, se = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros(2)
+        n = host.mcp_host_epi_hypotheses(_p(src), _p(tgt), _p(ray), E.one_pixel_angle(cams[1]), level, cap, _p(world), _p(tc), _p(se))
+        if ref is None:
+            assert n == -1
+            continue
+        assert n == ref["n_steps"] + 1
+        assert abs(se[0] - ref["start_depth"]) <= 1e-12 * ref["start_depth"] and abs(se[1] - ref["end_depth"]) <= 1e-12 * ref["end_depth"]
+        rw = np.array([p[0] for p in ref["points"]]); rt = np.array([p[1] for p in ref["points"]])
+        assert np.allclose(world[:n], rw, rtol=1e-9, atol=1e-9) and np.allclose(tc[:n], rt, rtol=1e-9, atol=1e-9)
+        # pixel vectors of a hypothesis
+        c, r, d = (E._unproject(cams[0], np.array(px) + o) for o in ([0, 0], [1 << level, 0], [0, 1 << level]))
+        right, down = np.zeros(3), np.zeros(3)
+        host.mcp_host_pixel_vectors(_p(src), _p(np.ascontiguousarray(rw[n // 2])), _p(c), _p(r), _p(d), _p(right), _p(down))
+        er, ed = E.pixel_vectors(sR, st, rw[n // 2], c, r, d)
+        assert np.allclose(right, er, rtol=1e-12, atol=1e-15) and np.allclose(down, ed, rtol=1e-12, atol=1e-15)
+    # triangulation: exact rays of a known point, and noisy rays against the SVD
+    for k in range(20):
+        p_b = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(2, 8)])
+        R = synth.so3_exp(0.3 * rng.standard_normal(3)); t = rng.standard_normal(3) * 0.5
+        p_a = R @ p_b + t
+        va, vb = p_a / np.linalg.norm(p_a), p_b / np.linalg.norm(p_b)
+        if k >= 10:
+            va = va + 1e-3 * rng.standard_normal(3); va /= np.linalg.norm(va)
+        out = np.zeros(3)
+        host.mcp_host_reproject_point(_p(np.concatenate([R.reshape(-1), t])), _p(va), _p(vb), _p(out))
+        assert np.allclose(out, E.reproject_point(R, t, va, vb), rtol=1e-8, atol=1e-9)
+        if k < 10:
+            assert np.allclose(out, p_b, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_add_points_epipolar_matches_the_restatement(host):
+    from mcptam_b200 import capi
+    from oracle import epipolar as E, oracle as O
+    sc = synth.make_stereo_scene(0)
+    pa, pb = O.pyramid(sc["img_a"]), O.pyramid(sc["img_b"])
+    la, lb = [O.level_corners(x) for x in pa], [O.level_corners(x) for x in pb]
+    fe = capi.FeHandle(640, 480, max_corners_per_level=32768)
+    fe.set_camera(sc["cam_b"])
+    fe.make_keyframe(0, sc["img_a"])
+    fe.make_keyframe(1, sc["img_b"])
+    rng = np.random.default_rng(1)
+    cand = []
+    for level in (0, 1, 2):
+        cor = la[level]["corners"]
+        h, w = pa[level].shape
+        cor = cor[(cor[:, 0] > 20) & (cor[:, 0] < w - 20) & (cor[:, 1] > 20) & (cor[:, 1] < h - 20)]
+        for i in rng.choice(len(cor), 40, replace=False):
+            cand.append((level, int(cor[i][0]), int(cor[i][1])))
+    mask = np.full((480, 640), 255, np.uint8)
+    mask[:, 600:] = 0                                           # a masked strip of the target keyframe
+    lx = np.ascontiguousarray(np.array(cand, np.int32))
+    out = (EpiRes * len(cand))()
+    n_found = host.mcp_host_add_points_epipolar(fe.h, 0, 1, C.addressof(sc["cam_a"]), C.addressof(sc["cam_b"]), _p(np.ascontiguousarray(sc["cfw_a"])),
+                                                _p(np.ascontiguousarray(sc["cfw_b"])), _p(mask), 640, len(cand), _p(lx), C.cast(out, C.c_void_p))
+    assert n_found >= 0
+    n_ok = 0
+    outcomes = set()
+    for k, (level, x, y) in enumerate(cand):
+        ref = E.add_point_epipolar(sc["cam_a"], sc["cam_b"], sc["cfw_a"], sc["cfw_b"], pa, pb, lb, level, (x, y), tgt_mask=mask)
+        got = out[k]
+        assert bool(got.ok) == ref["ok"], (k, cand[k], got.reason, ref["reason"])
+        assert REASONS[got.reason] == ref["reason"], (k, cand[k])
+        outcomes.add(ref["reason"])
+        if ref["reason"] != "endpoints":
+            assert got.n_steps == ref["n_steps"] and got.n_matches == ref["n_matches"]
+        if ref["ok"]:
+            n_ok += 1
+            assert got.best == ref["best"] and got.best_score == ref["best_score"] and got.subpix_from == ref["subpix_from"]
+            assert np.allclose(got.root[:], ref["root"], atol=0)
+            assert np.allclose(got.subpix[:], ref["subpix"], atol=1e-4)         # mixed fp32/fp64 sub-pixel iteration
+            assert np.allclose(got.world[:], ref["world"], rtol=1e-5, atol=1e-5)
+            assert abs(got.world[2] - sc["plane_z"]) < 0.15                     # and the point lies on the rendered plane
+    assert n_ok == n_found and n_ok >= 30
+    assert {"", "no match"} <= outcomes
