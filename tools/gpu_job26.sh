@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_epipolar.py -x -q -m gpu 2>&1 | tail -15
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
