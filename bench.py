@@ -326,17 +326,26 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
     iter_bytes = 80.0 * n_m + 232.0 * n_p + 16.0 * nc * nc          # SURVEY.md §8(d), whole LM iteration
+    # dram__bytes_read + dram__bytes_write of one launch of each of the two kernels, from the committed ncu --set full
+    # capture (cold cache: k_pose_blocks re-reads the 176-byte measurement records k_linearize has just written, which
+    # stay in L2 inside a real step)
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_full_linearize.txt")
-    if os.path.exists(prof) and args.config == "cfg2":        # dram__bytes_read+write of one launch, ncu --set full (cold cache)
-        vals = {}
+    prof = os.path.join(ROOT, "profiles", "r01_ncu_full_v21_ba.txt")
+    if os.path.exists(prof) and args.config == "cfg2":
+        unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per_kernel, cur = {}, None
         for ln in open(prof):
             f = ln.split()
-            if len(f) >= 3 and f[0].startswith("dram__bytes_"):
-                vals[f[0]] = float(f[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[2], 1)
-        if len(vals) == 2:
-            traffic = sum(vals.values())
-    roofline = {"bound": "hbm", "kernel": "k_linearize (reprojection + Jacobians + normal-equation blocks)", "achieved": achieved, "peak": peak,
+            if ln.startswith("Kernel Name"):
+                name = "k_linearize" if "k_linearize" in ln else "k_pose_blocks" if "k_pose_blocks" in ln else None
+                cur = name if name and name not in per_kernel else None
+                if cur:
+                    per_kernel[cur] = 0.0
+            elif cur and len(f) >= 3 and f[0].startswith("dram__bytes_"):
+                per_kernel[cur] += float(f[1]) * unit.get(f[2], 1)
+        if len(per_kernel) == 2:
+            traffic = sum(per_kernel.values())
+    roofline = {"bound": "hbm", "kernel": "k_linearize + k_pose_blocks (reprojection, Jacobians, normal-equation blocks)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": lin_bytes, "kernel_ms": lin_ms,
                 "whole_iteration": {"algorithmic_bytes": iter_bytes,
