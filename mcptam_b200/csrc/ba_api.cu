@@ -18,6 +18,9 @@
 #include <vector>
 
 #include "ba_prep.hpp"
+#ifndef MCP_BA_PDL_DEFAULT
+#define MCP_BA_PDL_DEFAULT false      // programmatic dependent launch of the per-round kernel chain (mcp_common.cuh)
+#endif
 #include "ba_types.cuh"
 
 namespace mcp {
@@ -29,6 +32,12 @@ void set_last_error(const char* fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled()
+{
+  static const bool on = [] { const char* e = getenv("MCP_BA_PDL"); return e ? e[0] != '0' : MCP_BA_PDL_DEFAULT; }();
+  return on;
 }
 
 // launchers defined in ba_kernels.cu

@@ -247,6 +247,7 @@ __device__ __forceinline__ double group_sum(double v, unsigned gmask)
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pose_blocks(BaDev d)
 {
+  pdl_prologue();
   if (lookahead_skip(d)) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(128) k_pose_blocks(BaDev d)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_backsub_eval(BaDev d, int apply, int which_in, double* err_out)
 {
+  pdl_prologue();
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int gl = lane & (LG - 1), grp = lane / LG;
@@ -696,6 +699,7 @@ constexpr size_t SELC_SMEM = sizeof(unsigned) * (size_t)(SELC_COPIES + 2) * SEL_
 __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS) k_select_cluster(BaDev d, int which_in, int mode, double* zero_ptr,
                                                                                                    size_t zero_n)
 {
+  pdl_prologue();
   if (lookahead_skip(d)) return;                                  // uniform over the whole cluster
   // look-ahead launches: the accumulators of the next linearisation are cleared here instead of by a kernel of their own
   for (size_t i = (size_t)blockIdx.x * SELC_THREADS + threadIdx.x; i < zero_n; i += (size_t)SELC_CTAS * SELC_THREADS) zero_ptr[i] = 0.0;
@@ -876,6 +880,7 @@ __global__ void k_lambda_apply(BaDev d)
 __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, int n_cand, int n_part_lin, int n_part_bs,
                                                    const double* red_in, int first_trial)
 {
+  pdl_prologue();
   __shared__ double s_sum[MAX_CAND][4];
   if (red_in) {
     // red_in = { cur_chi, (tmp_chi, scale, sumsq) per candidate }
@@ -1065,42 +1070,43 @@ static int lin_variant()
 // zeroes the linearisation accumulators [H0 | gc | red] (a memset that honours the look-ahead predicate)
 __global__ void k_zero_acc(BaDev d, double* acc, size_t n)
 {
+  pdl_prologue();
   if (lookahead_skip(d)) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = 0.0;
 }
-void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s) { k_zero_acc<<<148, 512, 0, s>>>(d, acc, n); }
+void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s) { launch_chain(k_zero_acc, dim3(148), dim3(512), 0, s, d, acc, n); }
 static void launch_pose_blocks(const BaDev& d, cudaStream_t s)
 {
   if (d.n_pb_items <= 0) return;
   int g = (d.n_pb_items + 3) / 4;
   if (g > 148 * 16) g = 148 * 16;
-  k_pose_blocks<<<g, 128, 0, s>>>(d);
+  launch_chain(k_pose_blocks, dim3(g), dim3(128), 0, s, d);
 }
 int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s)
 {
   const size_t stage = sizeof(double) * d.stage_doubles;
   if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
     const int g = per_point_grid(d, 4);
-    k_linearize<128, 3><<<g, 128, smem / warps * 4 + stage, s>>>(d);
+    launch_chain(k_linearize<128, 3>, dim3(g), dim3(128), smem / warps * 4 + stage, s, d);
     launch_pose_blocks(d, s);
     return g;
   }
   const int g = per_point_grid(d, warps);
-  if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) k_linearize<256, 2><<<g, 256, smem + stage, s>>>(d);
-  else k_linearize<256, 1><<<g, warps * 32, smem + stage, s>>>(d);
+  if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) launch_chain(k_linearize<256, 2>, dim3(g), dim3(256), smem + stage, s, d);
+  else launch_chain(k_linearize<256, 1>, dim3(g), dim3(warps * 32), smem + stage, s, d);
   launch_pose_blocks(d, s);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)
 {
   const int g = per_point_grid(d, 8);
-  k_backsub_eval<<<g, 256, sizeof(double) * d.stage_doubles, s>>>(d, apply, which, err_out);
+  launch_chain(k_backsub_eval, dim3(g), dim3(256), sizeof(double) * d.stage_doubles, s, d, apply, which, err_out);
   return g;
 }
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr, size_t zero_n)
 {
   static const bool multi_launch = [] { const char* e = getenv("MCP_BA_SELECT_MULTI"); return e && e[0] == '1'; }();
-  if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { k_select_cluster<<<SELC_CTAS, SELC_THREADS, SELC_SMEM, s>>>(d, which, mode, zero_ptr, zero_n); return 1; }
+  if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { launch_chain(k_select_cluster, dim3(SELC_CTAS), dim3(SELC_THREADS), SELC_SMEM, s, d, which, mode, zero_ptr, zero_n); return 1; }
   if (zero_n) launch_zero_acc(d, zero_ptr, zero_n, s);
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
@@ -1113,7 +1119,7 @@ void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 102
 void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
 void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)
 {
-  k_lm_control<<<1, 256, 0, s>>>(d, parts, n_cand, n_lin, n_bs, red_in, first_trial);
+  launch_chain(k_lm_control, dim3(1), dim3(256), 0, s, d, parts, n_cand, n_lin, n_bs, red_in, first_trial);
 }
 void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s)
 {

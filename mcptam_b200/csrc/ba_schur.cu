@@ -311,6 +311,7 @@ constexpr int RPD = 36;                      // doubles per point record
 template <int NC>
 __global__ void __launch_bounds__(256) k_schur_vinv_multi(BaDev d, SchurMulti mc)
 {
+  pdl_prologue();
   double lam[NC];
   {
     double l = d.ctrl->lambda, ni = d.ctrl->ni;
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_multi(BaDev d, SchurMul
 template <int NC>
 __global__ void __launch_bounds__(TW * 32, 3) k_schur_pairs_multi_ca(BaDev d, SchurMulti mc)
 {
+  pdl_prologue();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* stage = reinterpret_cast<double*>(smem_raw) + (size_t)wid * 2 * MG_CA * MRECD;          // [2][MG_CA][MRECD]
@@ -819,12 +821,23 @@ void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s) { k_pair_count<
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s) { k_pair_fill<<<148 * 4, 256, 0, s>>>(d, cursor, inc); }
 void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s) { k_pair_items<<<1, 1024, 0, s>>>(d, cnt, items, n_items_out); }
 // all candidates of a trial round in one pass (mc.n_cand = 2 or 3); the per-candidate Sm / rm must be zeroed before
+// the opt-in shared-memory size of a kernel is a per-device attribute: set it the first time a kernel is launched on
+// each device of the process (a handle may live on any device)
+static bool first_launch_on_device(bool (&seen)[64])
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 template <int NC, int MGT>
 static void launch_pairs_multi_tma(const BaDev& d, const SchurMulti& mc, cudaStream_t s)
 {
   const size_t smem = (size_t)TW * 2 * MGT * MRECD * sizeof(double) + TW * 2 * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_schur_pairs_multi<NC, MGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  static bool seen[64] = { false };
+  if (first_launch_on_device(seen)) cudaFuncSetAttribute(k_schur_pairs_multi<NC, MGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int per_sm = (int)std::min<size_t>(6, (220 * 1024) / smem);
   int g2 = (d.max_items + TW - 1) / TW;
   if (g2 < 1) g2 = 1;
@@ -848,8 +861,8 @@ void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s)
   mc.first_dynamic_item = g2 * TW;
   int g1 = (d.p_hi - d.p_lo + 255) / 256;
   if (g1 < 148) g1 = 148;
-  if (mc.n_cand == 2) k_schur_vinv_multi<2><<<g1, 256, 0, s>>>(d, mc);
-  else k_schur_vinv_multi<3><<<g1, 256, 0, s>>>(d, mc);
+  if (mc.n_cand == 2) launch_chain(k_schur_vinv_multi<2>, dim3(g1), dim3(256), 0, s, d, mc);
+  else launch_chain(k_schur_vinv_multi<3>, dim3(g1), dim3(256), 0, s, d, mc);
   if (stage_mode == 0) {
     if (mc.n_cand == 2) launch_pairs_multi_tma<2, 8>(d, mc, s); else launch_pairs_multi_tma<3, 8>(d, mc, s);
     return;
@@ -859,14 +872,13 @@ void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s)
     return;
   }
   const size_t smem_ca = (size_t)TW * 2 * MG_CA * MRECD * sizeof(double) + (size_t)TW * 2 * 3 * MG_CA * sizeof(unsigned long long);
-  static bool attr_ca = false;
-  if (!attr_ca) {
+  static bool seen_ca[64] = { false };
+  if (first_launch_on_device(seen_ca)) {
     cudaFuncSetAttribute(k_schur_pairs_multi_ca<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ca);
     cudaFuncSetAttribute(k_schur_pairs_multi_ca<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ca);
-    attr_ca = true;
   }
-  if (mc.n_cand == 2) k_schur_pairs_multi_ca<2><<<g2, TW * 32, smem_ca, s>>>(d, mc);
-  else k_schur_pairs_multi_ca<3><<<g2, TW * 32, smem_ca, s>>>(d, mc);
+  if (mc.n_cand == 2) launch_chain(k_schur_pairs_multi_ca<2>, dim3(g2), dim3(TW * 32), smem_ca, s, d, mc);
+  else launch_chain(k_schur_pairs_multi_ca<3>, dim3(g2), dim3(TW * 32), smem_ca, s, d, mc);
 }
 
 void launch_schur_gather(const BaDev& d, cudaStream_t s)
@@ -881,8 +893,7 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s)
     int warps = 4;
     while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
-    static size_t attr = 0;
-    if (smem > attr) { cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+    cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // size varies per problem; non-default path
     int g = (d.n_rs_items + warps - 1) / warps;
     if (g < 1) g = 1;
     k_schur_rows<<<g, warps * 32, smem, s>>>(d);
@@ -896,8 +907,8 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s)
     k_schur_pairs<<<g2, 128, 0, s>>>(d);
   } else {
     const size_t smem = (size_t)TW * 2 * TG * SREC * sizeof(double) + TW * 2 * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_schur_pairs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    static bool seen_tma[64] = { false };
+    if (first_launch_on_device(seen_tma)) cudaFuncSetAttribute(k_schur_pairs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (g2 > 148 * 2) g2 = 148 * 2;
     k_schur_pairs_tma<<<g2, TW * 32, smem, s>>>(d);
   }

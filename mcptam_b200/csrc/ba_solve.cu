@@ -362,6 +362,7 @@ __device__ __forceinline__ void inverse32_block(const double* L, double* X, cons
 
 __global__ void __launch_bounds__(256) k_chol_solve(BaDev d, int epoch, int base0, int base1)
 {
+  pdl_prologue(false);
   __shared__ double As[TB * TLD];
   __shared__ double Bs[TB * TLD];
   __shared__ double xs[32 * TB + 64];     // backsolve vector (up to 32 block rows) + scratch
@@ -679,7 +680,7 @@ void launch_chol_solve(const BaDev& d, int epoch, int n_sms, cudaStream_t s)
   const int n_tasks = T * (T + 1) / 2 + T;
   int grid = n_tasks < n_sms ? n_tasks : n_sms;      // all CTAs must be co-resident (spin-wait dataflow)
   if (grid < 1) grid = 1;
-  k_chol_solve<<<grid, 256, 0, s>>>(d, epoch, (epoch - 1) * (n_tasks + grid), (epoch - 1) * n_tasks);
+  launch_chain(k_chol_solve, dim3(grid), dim3(256), 0, s, d, epoch, (epoch - 1) * (n_tasks + grid), (epoch - 1) * n_tasks);
 }
 
 }  // namespace mcp

@@ -21,6 +21,36 @@ void set_last_error(const char* fmt, ...);
     }                                                                                           \
   } while (0)
 
+// Programmatic dependent launch (PDL): the kernels of the per-round chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the next kernel's launch and prologue overlap the tail of
+// the current one.  Every such kernel starts with pdl_prologue(): it lets ITS dependents launch early and then waits
+// until the kernel before it in the stream has completed and flushed its memory.  The wait is the first statement on
+// every path (also before early returns): a kernel that skipped it could finish before its predecessor and break the
+// transitive ordering of the chain.  Without the launch attribute both instructions are no-ops.
+// early_dependents = false for long-running narrow kernels (k_chol_solve): CTAs of the dependent kernel that become
+// resident early sit on registers and thread slots until this kernel ends, which would keep the other candidates'
+// solvers (other streams) off the SMs.
+__device__ __forceinline__ void pdl_prologue(bool early_dependents = true)
+{
+  if (early_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();           // MCP_BA_PDL (ba_api.cu)
+
+// kernel<<<grid, block, smem, s>>>(args...) with the PDL attribute when enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Device-side camera (McpTaylorCam plus the derivative-polynomial coefficients of
 // TaylorCamera::RefreshParams, src/TaylorCamera.cc:107-110).
 struct DevCam {
