@@ -44,7 +44,37 @@ def fe_fixture():
     np.savez_compressed(os.path.join(HERE, "fe_320x240_seed5.npz"), **out)
 
 
+def epipolar_candidates(sc, per_level=8):
+    """The candidates the epipolar fixture / tests use: FAST corners of the source view, seeded choice per level."""
+    pa = ora.pyramid(sc["img_a"])
+    rng = np.random.default_rng(4)
+    cand = []
+    for level in (0, 1, 2):
+        cor = ora.level_corners(pa[level])["corners"]
+        h, w = pa[level].shape
+        cor = cor[(cor[:, 0] > 20) & (cor[:, 0] < w - 20) & (cor[:, 1] > 20) & (cor[:, 1] < h - 20)]
+        for i in rng.choice(len(cor), per_level, replace=False):
+            cand.append((level, int(cor[i][0]), int(cor[i][1])))
+    return cand
+
+
+def epipolar_fixture():
+    from oracle import epipolar as epi
+    sc = synth.make_stereo_scene(0)
+    pa, pb = ora.pyramid(sc["img_a"]), ora.pyramid(sc["img_b"])
+    lb = [ora.level_corners(x) for x in pb]
+    cand = epipolar_candidates(sc)
+    rows = []
+    for level, x, y in cand:
+        r = epi.add_point_epipolar(sc["cam_a"], sc["cam_b"], sc["cfw_a"], sc["cfw_b"], pa, pb, lb, level, (x, y))
+        rows.append((int(r["ok"]), r.get("n_steps", -1), r.get("n_matches", -1), r.get("best", -1), r.get("best_score", -1)) +
+                    tuple(r["world"] if r["ok"] else (0.0, 0.0, 0.0)) + tuple(r["subpix"] if r["ok"] else (0.0, 0.0)))
+    np.savez_compressed(os.path.join(HERE, "epipolar_seed0.npz"), cand=np.array(cand, np.int32), rows=np.array(rows, np.float64),
+                        img_a_sum=int(sc["img_a"].astype(np.int64).sum()), img_b_sum=int(sc["img_b"].astype(np.int64).sum()))
+
+
 if __name__ == "__main__":
     ba_fixture()
     fe_fixture()
+    epipolar_fixture()
     print("golden fixtures written to", HERE)

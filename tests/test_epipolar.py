@@ -99,6 +99,26 @@ def test_host_pieces_match_the_restatement(host, seed):
             assert np.allclose(out, p_b, rtol=1e-9, atol=1e-9)
 
 
+def test_restatement_golden():
+    """Regression guard of oracle/epipolar.py on the rendered two-view scene (tests/golden/make_golden.py)."""
+    from oracle import epipolar as E, oracle as O
+    g = np.load(os.path.join(ROOT, "tests", "golden", "epipolar_seed0.npz"))
+    sc = synth.make_stereo_scene(0)
+    assert int(sc["img_a"].astype(np.int64).sum()) == int(g["img_a_sum"]) and int(sc["img_b"].astype(np.int64).sum()) == int(g["img_b_sum"])
+    pa, pb = O.pyramid(sc["img_a"]), O.pyramid(sc["img_b"])
+    lb = [O.level_corners(x) for x in pb]
+    n_ok = 0
+    for (level, x, y), row in zip(g["cand"], g["rows"]):
+        r = E.add_point_epipolar(sc["cam_a"], sc["cam_b"], sc["cfw_a"], sc["cfw_b"], pa, pb, lb, int(level), (int(x), int(y)))
+        assert int(r["ok"]) == int(row[0]) and r.get("n_steps", -1) == int(row[1]) and r.get("n_matches", -1) == int(row[2])
+        if r["ok"]:
+            n_ok += 1
+            assert r["best"] == int(row[3]) and r["best_score"] == int(row[4])
+            assert np.allclose(r["world"], row[5:8], rtol=1e-9, atol=1e-9) and np.allclose(r["subpix"], row[8:10], rtol=0, atol=1e-9)
+            assert abs(r["world"][2] - sc["plane_z"]) < 0.15
+    assert n_ok >= 6
+
+
 @pytest.mark.gpu
 def test_add_points_epipolar_matches_the_restatement(host):
     from mcptam_b200 import capi

@@ -97,6 +97,45 @@ def test_lm_converges_noise_free():
     assert np.abs(o.points() - prob.truth_pt_xyz).max() < 1e-4
 
 
+def test_lm_reaches_the_least_squares_optimum_of_scipy():
+    """Independent pin of the BA oracle as a whole (cost function, gauge, oplus, LM driver): without the robust kernel the
+    optimum of sum e^T Omega e is unique, so whatever path g2o's lambda schedule takes, the converged state must be the
+    one an unrelated solver (scipy.optimize.least_squares, finite-difference Jacobians) finds for the same residuals."""
+    opt = pytest.importorskip("scipy.optimize")
+    prob = synth.make_ba_problem(n_cam=2, n_mkf=4, n_pt=60, seed=3, outlier_frac=0.0, pix_sigma=0.5)
+    o = OracleBA(prob, use_robust=False, use_tukey=False)
+    start = (o.poses().copy(), o.points().copy())
+    rc, st = o.compute(100)
+    assert rc > 0 and st.converged
+    best = (o.poses().copy(), o.points().copy())
+    mov_pose = np.flatnonzero(np.asarray(prob.pose_fixed) == 0)
+    mov_pt = np.flatnonzero(np.asarray(prob.pt_fixed) == 0)
+    sqrt_info = (1.0 / np.sqrt(np.asarray(prob.meas_noise, np.float64))) ** 0.5      # chi2 = info |e|^2, info = 1/sqrt(noise)
+    w = OracleBA(prob, use_robust=False, use_tukey=False)
+
+    def resid(delta, base):
+        w.set_state(*base)
+        for k, i in enumerate(mov_pose):
+            w.oplus_pose(int(i), delta[6 * k:6 * k + 6])
+        off = 6 * len(mov_pose)
+        for k, i in enumerate(mov_pt):
+            w.oplus_point(int(i), delta[off + 3 * k:off + 3 * k + 3])
+        e, _ = w.eval()
+        return (e * sqrt_info[:, None]).ravel()
+
+    n = 6 * len(mov_pose) + 3 * len(mov_pt)
+    assert abs((resid(np.zeros(n), best) ** 2).sum() - st.chi2_after) <= 1e-9 * st.chi2_after
+    # (a) started at the oracle's answer, scipy has nowhere to go
+    r = opt.least_squares(resid, np.zeros(n), args=(best,), method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    assert abs(2 * r.cost - st.chi2_after) <= 1e-8 * st.chi2_after
+    assert np.abs(r.x).max() < 1e-5
+    # (b) started where the oracle started, scipy arrives at the same state
+    r = opt.least_squares(resid, np.zeros(n), args=(start,), method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=200 * n)
+    resid(r.x, start)
+    assert abs(2 * r.cost - st.chi2_after) <= 1e-7 * st.chi2_after
+    assert np.abs(w.poses() - best[0]).max() < 1e-5 and np.abs(w.points() - best[1]).max() < 1e-4
+
+
 def test_ba_golden(tiny):
     g = np.load(os.path.join(GOLD, "ba_tiny_seed0.npz"))
     o = OracleBA(tiny)
