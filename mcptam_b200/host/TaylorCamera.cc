@@ -242,3 +242,51 @@ McpTaylorCam TaylorCamera::ToAbi() const
 }
 
 }  // namespace mcp_host
+
+// ---- C entry points for the CPU tests (ctypes): the camera mirror against the Python / C restatements -------------
+extern "C" {
+
+using namespace mcp_host;
+
+// Builds a TaylorCamera from the 9 calibration parameters and returns its ABI record; 0 on success
+int mcp_host_camera_abi(const double* params9, int w, int h, McpTaylorCam* out)
+{
+  Vector<9> p;
+  for (int i = 0; i < 9; i++) p[i] = params9[i];
+  TaylorCamera cam(p, ImageRef(w, h), ImageRef(w, h), ImageRef(w, h));
+  if (!cam.Good()) return -1;
+  *out = cam.ToAbi();
+  return 0;
+}
+// Project + GetProjectionDerivs of n camera-frame points; invalid[i] = TaylorCamera::Invalid()
+int mcp_host_camera_project(const double* params9, int w, int h, int n, const double* p3, double* px2, double* derivs4, int* invalid,
+                            double* one_pixel_angle)
+{
+  Vector<9> p;
+  for (int i = 0; i < 9; i++) p[i] = params9[i];
+  TaylorCamera cam(p, ImageRef(w, h), ImageRef(w, h), ImageRef(w, h));
+  if (!cam.Good()) return -1;
+  for (int i = 0; i < n; i++) {
+    const Vector<2> v = cam.Project(makeVector(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]));
+    invalid[i] = cam.Invalid() ? 1 : 0;
+    const Matrix<2> d = cam.GetProjectionDerivs();
+    px2[2 * i] = v[0]; px2[2 * i + 1] = v[1];
+    derivs4[4 * i] = d[0][0]; derivs4[4 * i + 1] = d[0][1]; derivs4[4 * i + 2] = d[1][0]; derivs4[4 * i + 3] = d[1][1];
+  }
+  if (one_pixel_angle) *one_pixel_angle = cam.OnePixelAngle();
+  return 0;
+}
+int mcp_host_camera_unproject(const double* params9, int w, int h, int n, const double* px2, double* ray3)
+{
+  Vector<9> p;
+  for (int i = 0; i < 9; i++) p[i] = params9[i];
+  TaylorCamera cam(p, ImageRef(w, h), ImageRef(w, h), ImageRef(w, h));
+  if (!cam.Good()) return -1;
+  for (int i = 0; i < n; i++) {
+    const Vector<3> r = cam.UnProject(makeVector(px2[2 * i], px2[2 * i + 1]));
+    for (int k = 0; k < 3; k++) ray3[3 * i + k] = r[k];
+  }
+  return 0;
+}
+
+}  // extern "C"
