@@ -45,78 +45,81 @@ void QuaternionToRotation(const double q[4], Matrix<3>& R)
   R[2][0] = xz - wy; R[2][1] = yz + wx; R[2][2] = 1.0 - (xx + yy);
 }
 
-static void WritePose(std::ofstream& ofs, const SE3& pose)
+static inline int LevelScale(int l) { return 1 << l; }
+
+namespace {
+
+// one dump record tail: ", px, py, pz, qx, qy, qz, qw" of the INVERSE of a stored transform (the file keeps the
+// conventional "pose of the frame" while PTAM stores frame-from-parent)
+void PutInversePose(std::ostream& os, const SE3& stored)
 {
+  const SE3 pose = stored.inverse();
   double q[4];
   RotationToQuaternion(pose.get_rotation().get_matrix(), q);
-  const Vector<3>& t = pose.get_translation();
-  ofs << ", " << t[0] << ", " << t[1] << ", " << t[2];
-  ofs << ", " << q[0] << ", " << q[1] << ", " << q[2] << ", " << q[3] << std::endl;
+  for (int k = 0; k < 3; k++) os << ", " << pose.get_translation()[k];
+  for (int k = 0; k < 4; k++) os << ", " << q[k];
+  os << std::endl;
 }
 
-static inline int LevelScale(int l) { return 1 << l; }
+// the three '%' lines that open every section of the file
+void PutHeader(std::ostream& os, const char* what, const char* count, const char* record)
+{
+  os << "% " << what << std::endl << "% " << count << std::endl << "% " << record << std::endl;
+}
+
+}  // namespace
 
 bool DumpToFile(Map& map, const std::string& filename)
 {
-  std::ofstream ofs(filename.c_str());
-  if (!ofs.good() || map.mlpMultiKeyFrames.empty()) return false;
+  if (map.mlpMultiKeyFrames.empty()) return false;
+  std::ofstream os(filename.c_str());
+  if (!os.good()) return false;
 
-  ofs << "% Camera poses in MKF frame, format:" << std::endl;
-  ofs << "% Total number of cameras" << std::endl;
-  ofs << "% Camera Name, Position (3 vector), Orientation (quaternion, 4 vector)" << std::endl;
-  MultiKeyFrame* pFirstMKF = *(map.mlpMultiKeyFrames.begin());
-  ofs << pFirstMKF->mmpKeyFrames.size() << std::endl;
-  for (KeyFramePtrMap::iterator kf_it = pFirstMKF->mmpKeyFrames.begin(); kf_it != pFirstMKF->mmpKeyFrames.end(); ++kf_it) {
-    KeyFrame& kf = *(kf_it->second);
-    ofs << kf.mCamName;
-    WritePose(ofs, kf.mse3CamFromBase.inverse());          // the conventional pose, i.e. the inverse of PTAM's
+  // section 1: the rig, taken from the first MKF (every MKF carries the same cameras)
+  const MultiKeyFrame& first = *map.mlpMultiKeyFrames.front();
+  PutHeader(os, "Camera poses in MKF frame, format:", "Total number of cameras",
+            "Camera Name, Position (3 vector), Orientation (quaternion, 4 vector)");
+  os << first.mmpKeyFrames.size() << std::endl;
+  for (const auto& name_kf : first.mmpKeyFrames) {
+    os << name_kf.second->mCamName;
+    PutInversePose(os, name_kf.second->mse3CamFromBase);
   }
 
-  ofs << "% MKFs in world frame, format:" << std::endl;
-  ofs << "% Total number of MKFs" << std::endl;
-  ofs << "% MKF number, Position (3 vector), Orientation (quaternion, 4 vector)" << std::endl;
-  ofs << map.mlpMultiKeyFrames.size() << std::endl;
-  int i = 0;
-  for (MultiKeyFramePtrList::iterator mkf_it = map.mlpMultiKeyFrames.begin(); mkf_it != map.mlpMultiKeyFrames.end(); ++i, ++mkf_it) {
-    MultiKeyFrame& mkf = *(*mkf_it);
-    mkf.mnID = i;
-    ofs << i;
-    WritePose(ofs, mkf.mse3BaseFromWorld.inverse());
+  // section 2: MKFs, numbered in list order (the numbering is stored in mnID, the later sections refer to it)
+  PutHeader(os, "MKFs in world frame, format:", "Total number of MKFs", "MKF number, Position (3 vector), Orientation (quaternion, 4 vector)");
+  os << map.mlpMultiKeyFrames.size() << std::endl;
+  int id = 0;
+  for (MultiKeyFrame* mkf : map.mlpMultiKeyFrames) {
+    mkf->mnID = id++;
+    os << mkf->mnID;
+    PutInversePose(os, mkf->mse3BaseFromWorld);
   }
 
-  ofs << "% Points in world frame, format:" << std::endl;
-  ofs << "% Total number of points" << std::endl;
-  ofs << "% Point number, Position (3 vector), Parent MKF number, Parent camera name" << std::endl;
-  ofs << map.mlpPoints.size() << std::endl;
-  int nTotalMeas = 0;
-  i = 0;
-  for (MapPointPtrList::iterator point_it = map.mlpPoints.begin(); point_it != map.mlpPoints.end(); ++i, ++point_it) {
-    MapPoint& point = *(*point_it);
-    point.mnID = i;
-    ofs << i;
-    ofs << ", " << point.mv3WorldPos[0] << ", " << point.mv3WorldPos[1] << ", " << point.mv3WorldPos[2];
-    ofs << ", " << point.mpPatchSourceKF->mpParent->mnID << ", " << point.mpPatchSourceKF->mCamName << std::endl;
-    nTotalMeas += (int)point.mMMData.spMeasurementKFs.size();
+  // section 3: points, numbered in list order, with the keyframe their patch comes from
+  PutHeader(os, "Points in world frame, format:", "Total number of points", "Point number, Position (3 vector), Parent MKF number, Parent camera name");
+  os << map.mlpPoints.size() << std::endl;
+  size_t n_meas = 0;
+  id = 0;
+  for (MapPoint* pt : map.mlpPoints) {
+    pt->mnID = id++;
+    os << pt->mnID;
+    for (int k = 0; k < 3; k++) os << ", " << pt->mv3WorldPos[k];
+    os << ", " << pt->mpPatchSourceKF->mpParent->mnID << ", " << pt->mpPatchSourceKF->mCamName << std::endl;
+    n_meas += pt->mMMData.spMeasurementKFs.size();
   }
 
-  ofs << "% Measurements of points from KeyFrames, format: " << std::endl;
-  ofs << "% Total number of measurements" << std::endl;
-  ofs << "% MKF number, camera name, point number, image position (2 vector) at level 0, measurement noise" << std::endl;
-  ofs << nTotalMeas << std::endl;
-  for (MultiKeyFramePtrList::iterator mkf_it = map.mlpMultiKeyFrames.begin(); mkf_it != map.mlpMultiKeyFrames.end(); ++mkf_it) {
-    MultiKeyFrame& mkf = *(*mkf_it);
-    for (KeyFramePtrMap::iterator kf_it = mkf.mmpKeyFrames.begin(); kf_it != mkf.mmpKeyFrames.end(); ++kf_it) {
-      KeyFrame& kf = *(kf_it->second);
-      for (MeasPtrMap::iterator meas_it = kf.mmpMeasurements.begin(); meas_it != kf.mmpMeasurements.end(); ++meas_it) {
-        MapPoint& point = *(meas_it->first);
-        Measurement& meas = *(meas_it->second);
-        ofs << mkf.mnID << ", " << kf.mCamName << ", " << point.mnID << ", ";
-        ofs << meas.v2RootPos[0] << ", " << meas.v2RootPos[1] << ", " << LevelScale(meas.nLevel) * LevelScale(meas.nLevel) << std::endl;
+  // section 4: measurements, grouped by MKF and camera; the noise column is LevelScale(level)^2
+  PutHeader(os, "Measurements of points from KeyFrames, format: ", "Total number of measurements",
+            "MKF number, camera name, point number, image position (2 vector) at level 0, measurement noise");
+  os << n_meas << std::endl;
+  for (MultiKeyFrame* mkf : map.mlpMultiKeyFrames)
+    for (const auto& name_kf : mkf->mmpKeyFrames)
+      for (const auto& pt_meas : name_kf.second->mmpMeasurements) {
+        const Measurement& m = *pt_meas.second;
+        os << mkf->mnID << ", " << name_kf.second->mCamName << ", " << pt_meas.first->mnID << ", " << m.v2RootPos[0] << ", " << m.v2RootPos[1]
+           << ", " << LevelScale(m.nLevel) * LevelScale(m.nLevel) << std::endl;
       }
-    }
-  }
-  ofs << "% The end";
-  ofs.close();
+  os << "% The end";
   return true;
 }
 
