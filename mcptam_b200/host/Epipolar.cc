@@ -35,46 +35,49 @@ double OnePixelAngle(const McpTaylorCam& cam)
   return std::acos(a * b) / std::sqrt(2.0);
 }
 
-bool EpipolarHypotheses(const SE3& src, const SE3& tgt, const Vector<3>& v3Ray_SC, double dOnePixelAngle, int nLevel,
-                        std::vector<std::pair<Vector<3>, Vector<3> > >& vPositions, double* pdStartDepth, double* pdEndDepth)
+// The depth hypotheses of AddPointEpipolar (:620-724).  The triangle source centre / target centre / scene point fixes
+// the depth range on the source ray through the admissible epipolar angle [0.05 rad, 60 deg] (law of sines); the
+// hypotheses are spaced EVENLY IN ANGLE as seen from the target camera -- three target pixels at the candidate's level --
+// by walking the unit circle of the epipolar plane and intersecting each direction with the source ray.
+bool EpipolarHypotheses(const SE3& src, const SE3& tgt, const Vector<3>& ray_s, double one_pixel_angle, int level,
+                        std::vector<std::pair<Vector<3>, Vector<3> > >& hypotheses, double* depth_near, double* depth_far)
 {
-  vPositions.clear();
-  const Vector<3> v3LineDirn_TC = tgt.get_rotation() * (src.get_rotation().inverse() * v3Ray_SC);
-  const Vector<3> v3CamCenter_TC = tgt * src.inverse().get_translation();
-  const Vector<3> v3CamCenter_SC = src * tgt.inverse().get_translation();
-  const double dMaxEpiAngle = M_PI / 3, dMinEpiAngle = 0.05;
-  const double dSeparationDist = Norm(v3CamCenter_SC);
-  const double dSourceAngle = std::acos((v3CamCenter_SC * v3Ray_SC) / dSeparationDist);
-  const double dMinTargetAngle = M_PI - dSourceAngle - dMaxEpiAngle;
-  double dStartDepth = dSeparationDist * std::sin(dMinTargetAngle) / std::sin(dMaxEpiAngle);
-  const double dMaxTargetAngle = M_PI - dSourceAngle - dMinEpiAngle;
-  const double dEndDepth = dSeparationDist * std::sin(dMaxTargetAngle) / std::sin(dMinEpiAngle);
-  if (dStartDepth < 0.2) dStartDepth = 0.2;
-  if (pdStartDepth) *pdStartDepth = dStartDepth;
-  if (pdEndDepth) *pdEndDepth = dEndDepth;
-  const Vector<3> v3RayStart_TC = v3CamCenter_TC + v3LineDirn_TC * dStartDepth;
-  const Vector<3> v3RayEnd_TC = v3CamCenter_TC + v3LineDirn_TC * dEndDepth;
-  const Vector<3> v3A = Normalized(v3RayStart_TC), v3B = Normalized(v3RayEnd_TC);
-  const Vector<3> v3Between = v3A - v3B;
-  if (v3Between * v3Between < 0.00000001) return false;
-  const Vector<3> v3PlaneNormal = Normalized(v3A ^ v3B);
-  const Vector<3> v3PlaneI = v3A, v3PlaneJ = v3PlaneNormal ^ v3PlaneI;
-  auto toPlane = [&](const Vector<3>& v) { return makeVector(v3PlaneI * v, v3PlaneJ * v); };
-  const Vector<2> v2PlaneB = toPlane(v3B);
-  const double dMaxAngleAlongCircle = std::acos(v2PlaneB[0]);
-  double dAngleStep = dOnePixelAngle * LevelScale(nLevel) * 3;
-  const int nSteps = (int)std::ceil(dMaxAngleAlongCircle / dAngleStep);
-  dAngleStep = dMaxAngleAlongCircle / nSteps;
-  const Vector<2> v2RayStartInPlane = toPlane(v3RayStart_TC), v2RayEndInPlane = toPlane(v3RayEnd_TC);
-  Vector<2> v2RayDirInPlane = v2RayEndInPlane - v2RayStartInPlane;
-  v2RayDirInPlane = v2RayDirInPlane * (1.0 / std::sqrt(v2RayDirInPlane * v2RayDirInPlane));
-  const SE3 se3WorldFromTargetCam = tgt.inverse();
-  for (int i = 0; i < nSteps + 1; ++i) {
-    const double dAngle = i * dAngleStep;
-    const Vector<2> c = makeVector(std::cos(dAngle), std::sin(dAngle));
-    const double dAlpha = (v2RayStartInPlane[0] * c[1] - v2RayStartInPlane[1] * c[0]) / (v2RayDirInPlane[1] * c[0] - v2RayDirInPlane[0] * c[1]);
-    const Vector<3> v3PointPos_TC = v3RayStart_TC + v3LineDirn_TC * dAlpha;
-    vPositions.push_back(std::make_pair(se3WorldFromTargetCam * v3PointPos_TC, v3PointPos_TC));
+  hypotheses.clear();
+  const SE3 world_from_tgt = tgt.inverse(), world_from_src = src.inverse();
+  // the source ray in the target frame: origin (source camera centre) and direction
+  const Vector<3> origin_t = tgt * world_from_src.get_translation();
+  const Vector<3> dir_t = tgt.get_rotation() * (world_from_src.get_rotation() * ray_s);
+  // the target centre seen from the source: baseline length and the angle between baseline and ray at the source
+  const Vector<3> tgt_centre_s = src * world_from_tgt.get_translation();
+  const double baseline = Norm(tgt_centre_s);
+  const double angle_at_source = std::acos((tgt_centre_s * ray_s) / baseline);
+  const double widest = M_PI / 3, narrowest = 0.05;                          // admissible angles at the scene point
+  auto depth_for = [&](double angle_at_point) { return baseline * std::sin(M_PI - angle_at_source - angle_at_point) / std::sin(angle_at_point); };
+  double near = depth_for(widest);
+  const double far = depth_for(narrowest);
+  if (near < 0.2) near = 0.2;                                                // "don't bother looking too close"
+  if (depth_near) *depth_near = near;
+  if (depth_far) *depth_far = far;
+  const Vector<3> p_near = origin_t + dir_t * near, p_far = origin_t + dir_t * far;
+  const Vector<3> u_near = Normalized(p_near), u_far = Normalized(p_far);
+  const Vector<3> gap = u_near - u_far;
+  if (gap * gap < 0.00000001) return false;                                  // the arc is too short to search
+  // orthonormal frame of the epipolar plane: e1 towards the near end of the arc, e2 in the plane, towards the far end
+  const Vector<3> normal = Normalized(u_near ^ u_far);
+  const Vector<3> e1 = u_near, e2 = normal ^ e1;
+  auto in_plane = [&](const Vector<3>& v) { return makeVector(e1 * v, e2 * v); };
+  const double arc = std::acos(in_plane(u_far)[0]);
+  const int n_steps = (int)std::ceil(arc / (one_pixel_angle * LevelScale(level) * 3));
+  const double step = arc / n_steps;
+  const Vector<2> a2 = in_plane(p_near), b2 = in_plane(p_far);
+  Vector<2> along = b2 - a2;
+  along = along * (1.0 / std::sqrt(along * along));
+  for (int i = 0; i <= n_steps; ++i) {
+    // direction (c, s) on the circle; the ray point a2 + t * along is parallel to it when their 2-D cross product vanishes
+    const double c = std::cos(i * step), s = std::sin(i * step);
+    const double t = (a2[0] * s - a2[1] * c) / (along[1] * c - along[0] * s);
+    const Vector<3> p_t = p_near + dir_t * t;
+    hypotheses.push_back(std::make_pair(world_from_tgt * p_t, p_t));
   }
   return true;
 }
