@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -18,9 +19,6 @@
 #include <vector>
 
 #include "ba_prep.hpp"
-#ifndef MCP_BA_PDL_DEFAULT
-#define MCP_BA_PDL_DEFAULT false      // programmatic dependent launch of the per-round kernel chain (mcp_common.cuh)
-#endif
 #include "ba_types.cuh"
 
 namespace mcp {
@@ -34,10 +32,15 @@ void set_last_error(const char* fmt, ...)
   va_end(ap);
 }
 
+// Programmatic dependent launch of the per-round kernel chain (mcp_common.cuh).  MCP_BA_PDL=0/1 overrides; the default is
+// on for single-GPU processes (the whole GPU test suite runs with it) and off once a handle of the process joins a
+// communicator (the multi-GPU path has NCCL kernels inside the chain and was not measured with it).
+static std::atomic<bool> g_pdl_multi_gpu{ false };
 bool pdl_enabled()
 {
-  static const bool on = [] { const char* e = getenv("MCP_BA_PDL"); return e ? e[0] != '0' : MCP_BA_PDL_DEFAULT; }();
-  return on;
+  static const int env = [] { const char* e = getenv("MCP_BA_PDL"); return e && e[0] ? (e[0] != '0' ? 1 : 0) : -1; }();
+  if (env >= 0) return env == 1;
+  return !g_pdl_multi_gpu.load(std::memory_order_relaxed);
 }
 
 // launchers defined in ba_kernels.cu
@@ -992,6 +995,7 @@ int mcp_ba_comm_init(McpBa* h, const void* nccl_unique_id, int32_t rank, int32_t
   h->rank = rank; h->world = world;
   if (world == 1) return MCP_OK;
   if (!nccl_unique_id) { set_last_error("mcp_ba_comm_init: unique id required for world > 1"); return MCP_ERR_INVALID; }
+  g_pdl_multi_gpu.store(true, std::memory_order_relaxed);
   ncclUniqueId id;
   memcpy(&id, nccl_unique_id, sizeof(id));
   NCCL_CHECK(ncclCommInitRank(&h->comm, world, id, rank));
