@@ -24,6 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the oracle is only TIMED here (cpu_baseline, --impl reference), never used as a checker: take its -O3 -march=native
+# build, compiled on this host (oracle/oracle.py)
+os.environ.setdefault("MCP_ORACLE_FAST", "1")
 
 METRIC = "chainbundle_lm_iters_per_sec"
 UNIT = "LM iterations/s"
@@ -210,7 +213,7 @@ def main():
                            "lm_iters_per_step": lm_cpu},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": ncores, "kind": "port",
                                  "sample": "%d LM iterations per step of the same map, CPU restatement (oracle/ba_oracle.c, "
-                                           "Schur solve), 1 thread like the reference's MapMaker thread; reference binary "
+                                           "-O3 -march=native, Schur solve), 1 thread like the reference's MapMaker thread; reference binary "
                                            "unavailable (no ROS/TooN/g2o/SuiteSparse)" % lm_cpu},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -418,7 +421,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         val, ms, n_it = cpu_reference_run(prob, 2, 0, 3)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
-               "sample": "2 x 3 LM iterations of the same map on the host, CPU restatement (oracle/ba_oracle.c, Schur solve), "
+               "sample": "2 x 3 LM iterations of the same map on the host, CPU restatement (oracle/ba_oracle.c, -O3 -march=native, Schur solve), "
                          "1 thread; reference binary unavailable"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

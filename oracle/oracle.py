@@ -12,7 +12,22 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+# MCP_ORACLE_FAST=1 (set by bench.py for its CPU timing legs only): the -O3 -march=native build.  It is compiled on the
+# machine that runs it and tagged with that machine's CPU flags, because a prebuilt file may travel to another host.
+_FAST = os.environ.get("MCP_ORACLE_FAST", "0") == "1"
+
+
+def _cpu_tag() -> str:
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_LIB_PATH = os.path.join(_HERE, "_build", ("liboracle_fast_%s.so" % _cpu_tag()) if _FAST else "liboracle.so")
 
 
 def build(force: bool = False) -> str:
@@ -20,7 +35,10 @@ def build(force: bool = False) -> str:
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+        cmd = ["make", "-C", _HERE, "-B"]
+        if _FAST:
+            cmd += ["FAST=1", "OUT=" + os.path.relpath(_LIB_PATH, _HERE)]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
