@@ -131,6 +131,18 @@ def test_threaded_passes_give_identical_layout(threads):
     capi.ba_prepare(prob, threads=1, par_min_meas=16384)
 
 
+def test_thread_pool_survives_many_back_to_back_loads():
+    """mcp_ba_load runs once per BundleAdjust call for the lifetime of the process: thousands of pool dispatches, also
+    with more threads than cores and after the pool has been re-created, must neither hang nor change the result."""
+    prob = synth.make_ba_config("tiny", seed=0)
+    one, _ = capi.ba_prepare(prob, threads=1, par_min_meas=1 << 30)
+    for threads in (8, 3, 32, 2):
+        many, _ = capi.ba_prepare(prob, threads=threads, par_min_meas=0, reps=1500)
+        for k, v in one.items():
+            assert np.array_equal(np.asarray(many[k]), np.asarray(v)), (k, threads)
+    capi.ba_prepare(prob, threads=1, par_min_meas=16384)
+
+
 def capi_partition(prob, world):
     """the same partition through a pure numpy statement of SURVEY.md §8(e): contiguous, measurement-count balanced"""
     off = np.concatenate([[0], np.cumsum(np.bincount(np.asarray(prob.meas_pt), minlength=prob.n_pt))])
