@@ -11,6 +11,17 @@
  * g2o, SuiteSparse are absent).  Every function below cites the reference file:line it
  * restates; g2o / TooN / libCVD behaviour that is not in the reference tree is restated
  * from their published algorithms and marked [3P].
+ *
+ * What the oracle IS pinned against (tests/test_oracle_cpu.py, tests/test_host_cpu.py, tests/test_epipolar.py):
+ *   - the reference's own validation device: analytic vs central-difference Jacobians (src/ChainBundle.cc:688-740);
+ *   - itself, through different algorithms: Schur vs dense full-system solve, closed-form vs bisection FAST score,
+ *     brute-force vs fast detector, marginal covariances vs a numpy inverse, fast_nonmax vs its definition;
+ *   - independent code: OpenCV's FAST 9_16 detector (ring / strictness / border semantics), scipy's
+ *     least_squares (the state the LM driver converges to is the least-squares optimum of the same residuals),
+ *     and the separately written C++ TaylorCamera mirror (inverse-polynomial fit, projection, derivatives);
+ *   - committed golden vectors (tests/golden/), which guard against regressions of the oracle itself.
+ * The build that CHECKS is -O2 -ffp-contract=off (Makefile); bench.py TIMES a -O3 -march=native build of the same
+ * sources (MCP_ORACLE_FAST=1, oracle.py), which is never used as a checker.
  */
 #ifndef MCPTAM_ORACLE_H
 #define MCPTAM_ORACLE_H
