@@ -16,7 +16,8 @@
  *   - the reference's own validation device: analytic vs central-difference Jacobians (src/ChainBundle.cc:688-740);
  *   - itself, through different algorithms: Schur vs dense full-system solve, closed-form vs bisection FAST score,
  *     brute-force vs fast detector, marginal covariances vs a numpy inverse, fast_nonmax vs its definition;
- *   - independent code: OpenCV's FAST 9_16 detector (ring / strictness / border semantics), scipy's
+ *   - independent code: OpenCV's FAST 9_16 detector (ring / strictness / border semantics) and matchTemplate
+ *     (MiniPatch SSD exactly, PatchFinder ZMSSD up to its integer truncation), scipy's
  *     least_squares (the state the LM driver converges to is the least-squares optimum of the same residuals),
  *     and the separately written C++ TaylorCamera mirror (inverse-polynomial fit, projection, derivatives);
  *   - committed golden vectors (tests/golden/), which guard against regressions of the oracle itself.

@@ -210,6 +210,32 @@ def test_zmssd_identity_and_template_copy():
     assert nout > 0                                                     # leaves the image -> template bad
 
 
+def test_ssd_scores_against_opencv_match_template():
+    """Independent pins of the two integer patch scores: MiniPatch's 9x9 SSD is exactly cv2.matchTemplate(TM_SQDIFF);
+    PatchFinder's ZMSSD is the zero-mean SSD up to the truncation of its integer mean term (|difference| < 1... per the
+    formula (2 SA SB - SA^2 - SB^2) / 64 of src/PatchFinder.cc:511-658)."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_frame(w=160, h=120, seed=9, n_shapes=60)
+    rng = np.random.default_rng(9)
+    L = ora.lib()
+    for _ in range(40):
+        x, y = int(rng.integers(10, 150)), int(rng.integers(10, 110))
+        tx, ty = int(rng.integers(10, 150)), int(rng.integers(10, 110))
+        # MiniPatch: 9x9 window centred on (x, y) against the patch sampled at (tx, ty)
+        patch = np.ascontiguousarray(img[ty - 4:ty + 5, tx - 4:tx + 5])
+        got = L.ora_minipatch_ssd(ora._p(img), img.shape[1], img.shape[0], img.shape[1], ora._p(patch.reshape(-1)), x, y)
+        ref = cv2.matchTemplate(img[y - 4:y + 5, x - 4:x + 5].astype(np.float32), patch.astype(np.float32), cv2.TM_SQDIFF)[0, 0]
+        assert got == int(round(float(ref)))
+        # PatchFinder: 8x8 window with top-left (x-4, y-4) against an 8x8 template
+        t = np.ascontiguousarray(img[ty - 4:ty + 4, tx - 4:tx + 4])
+        tsum, tsq = int(t.astype(int).sum()), int((t.astype(int) ** 2).sum())
+        z = L.ora_zmssd(ora._p(img), img.shape[1], img.shape[0], img.shape[1], ora._p(t.reshape(-1)), tsum, tsq, x, y, 8 * 8 * 250)
+        w = img[y - 4:y + 4, x - 4:x + 4].astype(np.float64)
+        tf = t.astype(np.float64)
+        zm = cv2.matchTemplate((w - w.mean()).astype(np.float32), (tf - tf.mean()).astype(np.float32), cv2.TM_SQDIFF)[0, 0]
+        assert abs(z - float(zm)) < 1.0 + 1e-3 * abs(float(zm))
+
+
 def test_subpix_recovers_translation():
     from scipy import ndimage
     a = synth.make_frame(w=320, h=240, seed=6, n_shapes=80)
