@@ -35,6 +35,30 @@ def test_camera_project_unproject_roundtrip():
         assert np.allclose(out, p, atol=1e-9)
 
 
+def test_se3_exp_against_scipy_expm():
+    """Independent pin of the Lie-algebra convention (TooN SE3<>::exp: 6-vector = translation part first, then rotation):
+    the 3x4 result equals the matrix exponential of the 4x4 twist, including the small-angle branches."""
+    la = pytest.importorskip("scipy.linalg")
+    rng = np.random.default_rng(0)
+    L = ora.lib()
+    for scale in (1.0, 1e-2, 5e-4, 1e-4, 5e-5, 1e-7, 3.0):
+        for _ in range(10):
+            mu = np.concatenate([rng.standard_normal(3), rng.standard_normal(3) * scale])
+            out = np.zeros(12)
+            L.ora_se3_exp(ora._p(mu), ora._p(out))
+            w = mu[3:]
+            T = np.zeros((4, 4))
+            T[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+            T[:3, 3] = mu[:3]
+            E = la.expm(T)
+            assert np.allclose(out[:9].reshape(3, 3), E[:3, :3], rtol=0, atol=1e-12)
+            # TooN's first branch (theta^2 < 1e-8) drops the C w x (w x t) term of the translation: an error of up to
+            # theta^2 |t| / 6 (2e-9 just below the threshold) that the restatement must reproduce, not fix
+            th2 = float(w @ w)
+            tol = 1e-12 + (th2 * np.linalg.norm(mu[:3]) / 6 * 1.01 if th2 < 1e-8 else 0.0)
+            assert np.abs(out[9:] - E[:3, 3]).max() <= tol
+
+
 def test_analytic_vs_numeric_jacobians(tiny):
     """The reference's own (commented-out) validation: central differences, src/ChainBundle.cc:688-740."""
     prob = tiny
@@ -234,6 +258,24 @@ def test_ssd_scores_against_opencv_match_template():
         tf = t.astype(np.float64)
         zm = cv2.matchTemplate((w - w.mean()).astype(np.float32), (tf - tf.mean()).astype(np.float32), cv2.TM_SQDIFF)[0, 0]
         assert abs(z - float(zm)) < 1.0 + 1e-3 * abs(float(zm))
+
+
+def test_shitomasi_against_opencv_min_eigenval():
+    """Independent pin of FindShiTomasiScoreAtPoint (src/ShiTomasi.cc:34-63): 7x7 window, un-halved central
+    differences, lambda_min / (2 * 49)  ==  cv2.cornerMinEigenVal(blockSize 7, ksize 1) * 255^2 / 2 (OpenCV halves the
+    central difference, divides by 255 per derivative and averages over the 49 pixels; float32 inside)."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_frame(w=160, h=120, seed=9, n_shapes=60)
+    e = cv2.cornerMinEigenVal(img, 7, ksize=1, borderType=cv2.BORDER_REFLECT_101)
+    rng = np.random.default_rng(2)
+    n = 0
+    for _ in range(200):
+        x, y = int(rng.integers(6, 154)), int(rng.integers(6, 114))
+        s = ora.shitomasi(img, x, y)
+        ref = float(e[y, x]) * 255.0 * 255.0 / 2.0
+        assert abs(s - ref) <= 2e-4 * max(abs(ref), 1.0) + 1e-3, (x, y, s, ref)
+        n += s > 10
+    assert n > 50                                                       # the sample is not all flat regions
 
 
 def test_subpix_recovers_translation():
