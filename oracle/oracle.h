@@ -19,6 +19,8 @@
  *   - independent code: OpenCV's FAST 9_16 detector (ring / strictness / border semantics) and matchTemplate
  *     (MiniPatch SSD exactly, PatchFinder ZMSSD up to its integer truncation), scipy's
  *     least_squares (the state the LM driver converges to is the least-squares optimum of the same residuals),
+ *     numpy (one LM step = the solution of the Huber-weighted normal equations assembled outside the oracle; SE3 exp
+ *     = scipy's matrix exponential of the twist; Shi-Tomasi = cv2.cornerMinEigenVal up to the documented scale),
  *     and the separately written C++ TaylorCamera mirror (inverse-polynomial fit, projection, derivatives);
  *   - committed golden vectors (tests/golden/), which guard against regressions of the oracle itself.
  * The build that CHECKS is -O2 -ffp-contract=off (Makefile); bench.py TIMES a -O3 -march=native build of the same

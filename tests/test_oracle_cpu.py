@@ -362,6 +362,49 @@ def test_keyframe_rest_candidates():
     assert set(map(tuple, pr["xy"])) <= set(map(tuple, r["xy"]))
 
 
+def test_lm_step_matches_numpy_normal_equations():
+    """g2o's buildSystem + solve restated independently in numpy: Huber weights from the exact upper median, H = sum
+    J^T (rho' Omega) J + lambda I, b = -sum J^T rho' Omega e assembled from the oracle's (numerically verified) Jacobians
+    and solved with numpy.linalg.solve, against the oracle's own LM step (Schur or dense, its own Cholesky)."""
+    prob = synth.make_ba_problem(n_cam=2, n_mkf=4, n_pt=50, seed=5, outlier_frac=0.05)
+    o = OracleBA(prob)
+    pose_var = np.cumsum(prob.pose_fixed == 0) - 1
+    pose_var[prob.pose_fixed != 0] = -1
+    pt_var = np.cumsum(prob.pt_fixed == 0) - 1
+    pt_var[prob.pt_fixed != 0] = -1
+    npv, nptv = o.n_pose_var, o.n_pt_var
+    dim = 6 * npv + 3 * nptv
+    e, chi2 = o.eval()
+    # RobustKernelData::RecomputeNow + Huber::FindSigmaSquared (src/ChainBundle.cc:810-833, MEstimator.h:194-204)
+    a = np.sort(np.abs(chi2))
+    med = a[len(a) // 2]
+    sig = 1.345 * 1.4826 * (1 + 5.0 / (2 * len(a) - 6)) * np.sqrt(med)
+    sig_sq = max(sig * sig, 0.5 ** 2)                                   # ChainBundle::sdMinMEstimatorSigma = 0.5
+    lam = 7.5
+    H = lam * np.eye(dim)
+    b = np.zeros(dim)
+    for m in range(prob.n_meas):
+        jo, js, jp = o.jacobians(m)
+        J = np.zeros((2, dim))
+        p = prob.meas_pt[m]
+        for chain, jac in ((prob.meas_chain[m], jo), (prob.pt_chain[p], js)):
+            for i, pid in enumerate(chain):
+                if pid >= 0 and pose_var[pid] >= 0:
+                    J[:, 6 * pose_var[pid]:6 * pose_var[pid] + 6] += jac[i]
+        if pt_var[p] >= 0:
+            J[:, 6 * npv + 3 * pt_var[p]:6 * npv + 3 * pt_var[p] + 3] = jp
+        info = 1.0 / np.sqrt(prob.meas_noise[m])
+        c = abs(chi2[m])
+        w = 1.0 if c <= sig_sq else np.sqrt(sig_sq) / np.sqrt(c)        # RobustKernelAdaptive::robustify: rho'
+        H += w * info * (J.T @ J)
+        b -= w * info * (J.T @ e[m])
+    ref = np.linalg.solve(H, b)
+    for mode in (0, 1):
+        rc, d, sig_o, _ = o.lm_step(lam, -1.0, mode)
+        assert rc == 0 and abs(sig_o - sig * sig) <= 1e-12 * sig * sig
+        assert np.linalg.norm(d - ref) <= 1e-8 * np.linalg.norm(ref), mode
+
+
 def test_marginals_match_dense_numpy_inverse():
     """ChainBundle's median point-depth covariance (src/ChainBundle.cc:1401-1448): the oracle's value equals the
     (2,2) entries of the point blocks of a numpy inverse of the Hessian assembled from the oracle's Jacobians."""
