@@ -278,6 +278,27 @@ def test_shitomasi_against_opencv_min_eigenval():
     assert n > 50                                                       # the sample is not all flat regions
 
 
+def test_patch_template_against_opencv_warp_affine():
+    """Independent pin of the template geometry (CVD::transform as used by MakeTemplateCoarseCont, src/PatchFinder.cc:
+    160-164): template pixel (row i, column j) samples the source at centre + M ((j, i) - (4, 4)) -- the same map as
+    cv2.warpAffine(WARP_INVERSE_MAP) with that offset; grey values agree to one level (truncating double bilinear vs
+    OpenCV's rounded fixed-point bilinear)."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_frame(w=320, h=240, seed=2, n_shapes=0)             # smooth texture: no hard edges inside the patch
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        A = np.eye(2) + 0.3 * rng.standard_normal((2, 2))
+        cx, cy = int(rng.integers(40, 280)), int(rng.integers(40, 200))
+        t, nout = ora.patch_template(img, A, cx, cy)
+        assert nout == 0
+        M = np.hstack([A, (np.array([cx, cy]) - A @ np.array([4.0, 4.0])).reshape(2, 1)])
+        ref = cv2.warpAffine(img, M, (8, 8), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP, borderMode=cv2.BORDER_REPLICATE)
+        assert np.abs(t.reshape(8, 8).astype(int) - ref.astype(int)).max() <= 1
+    # a patch that leaves the image is reported through the outside count (TemplateBad)
+    t, nout = ora.patch_template(img, np.eye(2) * 3.0, 5, 5)
+    assert nout > 0
+
+
 def test_subpix_recovers_translation():
     from scipy import ndimage
     a = synth.make_frame(w=320, h=240, seed=6, n_shapes=80)
