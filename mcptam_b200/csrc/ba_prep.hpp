@@ -155,7 +155,7 @@ struct BaPrep {
   char err[256] = "";
   int par_min_meas = 16384;       // below this many measurements the passes run on the calling thread only
   // scratch, kept between calls
-  std::vector<int> cursor, key_cnt, order, slot_tmp, thr_bad, thr_max, thr_lo;
+  std::vector<int> key_cnt, order, slot_tmp, thr_bad, thr_max, thr_lo, thr_hist;
 
   void free_all(const PrepAlloc& a)
   {
@@ -211,11 +211,14 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     if (b >= 0 && !pose_fixed[b]) MCP_PREP_FAIL(PREP_UNSUPPORTED, "point %d: movable second chain link is not supported", p);
   }
   // validation + histogram of measurements per point in one pass; the first offending measurement (in index order) is
-  // reported, as a sequential scan would
+  // reported, as a sequential scan would.  Every thread histograms its own contiguous range of measurements into a
+  // private row (no atomics); the rows then turn into the cursors of a STABLE parallel counting sort: thread t's
+  // measurements of point p go behind those of threads < t.
   int* pmo = o.pt_meas_off.p;
-  std::fill(pmo, pmo + n_pt + 1, 0);
   o.thr_bad.assign((size_t)T * 2, -1);
+  o.thr_hist.assign((size_t)T * ((size_t)n_pt + 1), 0);
   par([&](int t) {
+    int* hist = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
     const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
     for (int m = lo; m < hi; m++) {
       const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
@@ -226,8 +229,7 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       else if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) bad = 4;
       else if (!(meas_noise[m] > 0)) bad = 5;
       if (bad) { o.thr_bad[2 * t] = m; o.thr_bad[2 * t + 1] = bad; return; }
-      if (T > 1) __atomic_fetch_add(&pmo[meas_pt[m] + 1], 1, __ATOMIC_RELAXED);
-      else pmo[meas_pt[m] + 1]++;
+      hist[meas_pt[m]]++;
     }
   });
   for (int t = 0; t < T; t++) {
@@ -241,11 +243,22 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       default: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: noise must be > 0", m);
     }
   }
-  // measurements sorted by point (stable counting sort)
-  for (int p = 0; p < n_pt; p++) pmo[p + 1] += pmo[p];
-  o.cursor.assign(pmo, pmo + n_pt);
+  // offsets per point, and per (point, thread) the first position of that thread's measurements
+  {
+    int run = 0;
+    for (int p = 0; p < n_pt; p++) {
+      pmo[p] = run;
+      for (int t = 0; t < T; t++) { int& c = o.thr_hist[(size_t)t * ((size_t)n_pt + 1) + p]; const int v = c; c = run; run += v; }
+    }
+    pmo[n_pt] = run;
+  }
   o.meas_orig.resize((size_t)n_meas);
-  for (int m = 0; m < n_meas; m++) o.meas_orig[o.cursor[meas_pt[m]]++] = m;
+  par([&](int t) {
+    int* cur = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
+    int* orig = o.meas_orig.data();
+    const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+    for (int m = lo; m < hi; m++) orig[cur[meas_pt[m]]++] = m;
+  });
 
   int nptv = 0;
   for (int p = 0; p < n_pt; p++) o.pt_var[p] = pt_fixed[p] ? -1 : nptv++;
