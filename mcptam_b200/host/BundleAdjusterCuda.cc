@@ -14,6 +14,46 @@ int BundleAdjusterCuda::BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::
   ChainBundle multiBundle(mmCameraModels, mbUseRobust, mbUseTukey, mbVerbose);
   mbBundleRunning = true;
   mbBundleRunningIsRecent = bRecent;
+  Marshal(multiBundle, spAdjustSet, spFixedSet, spMapPoints);
+  int nAccepted = 0;
+  mnTotalIterations = 0;
+  mdGpuMs = 0;
+  if (mbUseTwoStep) {
+    nAccepted = AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints, 10);
+    mnTotalIterations = multiBundle.TotalIterations();
+    if (nAccepted < 0) return nAccepted;
+    if (!multiBundle.Converged()) {
+      // the first pass raised the abort flag only on convergence; an external abort request stays set
+      nAccepted += AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints);
+      mnTotalIterations += multiBundle.TotalIterations();
+    }
+  } else {
+    nAccepted = AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints);
+    mnTotalIterations = multiBundle.TotalIterations();
+  }
+  if (nAccepted < 0) return nAccepted;
+  if (multiBundle.Converged()) {
+    mbBundleConverged_Recent = true;
+    if (!mbBundleRunningIsRecent) mbBundleConverged_Full = true;
+  }
+  for (auto& o : multiBundle.GetOutlierMeasurements()) {
+    MapPoint* pPoint = mmBundleID_Point[std::get<0>(o)];
+    MultiKeyFrame* pMKF = mmBundleID_Base[std::get<1>(o)];
+    vOutliers.push_back(std::make_pair(pMKF->mmpKeyFrames[std::get<2>(o)], pPoint));
+  }
+  mbBundleRunning = false;
+  mbBundleAbortRequested = false;
+  return nAccepted;
+}
+
+// src/BundleAdjusterMulti.cc:83-203
+void BundleAdjusterCuda::Marshal(ChainBundle& multiBundle, std::set<MultiKeyFrame*>& spAdjustSet, std::set<MultiKeyFrame*>& spFixedSet,
+                                 std::set<MapPoint*>& spMapPoints)
+{
+  size_t nMeasUpper = 0;
+  for (MapPoint* pp : spMapPoints) nMeasUpper += pp->mMMData.spMeasurementKFs.size();
+  multiBundle.Reserve(spAdjustSet.size() + spFixedSet.size() + 16, spMapPoints.size(), nMeasUpper);
+  mmPoint_BundleID.reserve(spMapPoints.size() * 2);
   for (int pass = 0; pass < 2; pass++) {
     std::set<MultiKeyFrame*>& s = pass == 0 ? spAdjustSet : spFixedSet;
     for (MultiKeyFrame* pm : s) {
@@ -46,44 +86,17 @@ int BundleAdjusterCuda::BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::
     MultiKeyFrame& mkf = *mb.first;
     for (auto& kv : mkf.mmpKeyFrames) {
       KeyFrame& kf = *kv.second;
-      std::vector<int> vCams(2);
-      vCams[0] = mb.second; vCams[1] = mmCamName_BundleID[kv.first];
+      const int nBaseID = mb.second, nCamID = mmCamName_BundleID[kv.first];
+      int nCamIndex = -1;                                  // resolved at the keyframe's first measurement
       for (auto& mm : kf.mmpMeasurements) {
-        if (!mmPoint_BundleID.count(mm.first)) continue;
-        Measurement& meas = *mm.second;
-        multiBundle.AddMeas(vCams, mmPoint_BundleID[mm.first], meas.v2RootPos, LevelScale(meas.nLevel) * LevelScale(meas.nLevel), kv.first);
+        const auto itPoint = mmPoint_BundleID.find(mm.first);
+        if (itPoint == mmPoint_BundleID.end()) continue;
+        if (nCamIndex < 0) nCamIndex = multiBundle.CameraIndex(kv.first);
+        const Measurement& meas = *mm.second;
+        multiBundle.AddMeas(nBaseID, nCamID, itPoint->second, meas.v2RootPos, LevelScale(meas.nLevel) * LevelScale(meas.nLevel), nCamIndex);
       }
     }
   }
-  int nAccepted = 0;
-  mnTotalIterations = 0;
-  mdGpuMs = 0;
-  if (mbUseTwoStep) {
-    nAccepted = AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints, 10);
-    mnTotalIterations = multiBundle.TotalIterations();
-    if (nAccepted < 0) return nAccepted;
-    if (!multiBundle.Converged()) {
-      // the first pass raised the abort flag only on convergence; an external abort request stays set
-      nAccepted += AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints);
-      mnTotalIterations += multiBundle.TotalIterations();
-    }
-  } else {
-    nAccepted = AdjustAndUpdate(multiBundle, spAdjustSet, spMapPoints);
-    mnTotalIterations = multiBundle.TotalIterations();
-  }
-  if (nAccepted < 0) return nAccepted;
-  if (multiBundle.Converged()) {
-    mbBundleConverged_Recent = true;
-    if (!mbBundleRunningIsRecent) mbBundleConverged_Full = true;
-  }
-  for (auto& o : multiBundle.GetOutlierMeasurements()) {
-    MapPoint* pPoint = mmBundleID_Point[std::get<0>(o)];
-    MultiKeyFrame* pMKF = mmBundleID_Base[std::get<1>(o)];
-    vOutliers.push_back(std::make_pair(pMKF->mmpKeyFrames[std::get<2>(o)], pPoint));
-  }
-  mbBundleRunning = false;
-  mbBundleAbortRequested = false;
-  return nAccepted;
 }
 
 // src/BundleAdjusterMulti.cc:267-337

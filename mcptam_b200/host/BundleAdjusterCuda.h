@@ -4,6 +4,7 @@
 #pragma once
 
 #include <set>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -45,9 +46,15 @@ class BundleAdjusterCuda : public BundleAdjusterBase {
   double LastGpuMs() const { return mdGpuMs; }
 
  protected:
+  // The marshalling half of BundleAdjust (src/BundleAdjusterMulti.cc:83-203): poses, points and measurements of the map
+  // into the bundle, filling the id maps.  Same order of AddPose / AddPoint / AddMeas calls as the reference; the
+  // per-measurement lookups go through a hash map and the allocation-free ChainBundle::AddMeas overload (at 80 k
+  // measurements the reference-style std::map lookups and by-value vector / string arguments cost several times the
+  // bundle adjustment itself on the device).
+  void Marshal(ChainBundle& multiBundle, std::set<MultiKeyFrame*>& spAdjustSet, std::set<MultiKeyFrame*>& spFixedSet, std::set<MapPoint*>& spMapPoints);
   int AdjustAndUpdate(ChainBundle& multiBundle, std::set<MultiKeyFrame*> spAdjustSet, std::set<MapPoint*> spMapPoints, int nIterations = -1);
   TaylorCameraMap& mmCameraModels;
-  std::map<MapPoint*, int> mmPoint_BundleID;
+  std::unordered_map<MapPoint*, int> mmPoint_BundleID;
   std::map<int, MapPoint*> mmBundleID_Point;
   std::map<MultiKeyFrame*, int> mmBase_BundleID;
   std::map<int, MultiKeyFrame*> mmBundleID_Base;

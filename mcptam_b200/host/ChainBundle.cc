@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 
 namespace mcp_host {
@@ -12,8 +13,11 @@ double ChainBundle::sdUpdatePercentConvergenceLimit = 1e-10;
 double ChainBundle::sdUpdateRMSConvergenceLimit = 1e-10;
 double ChainBundle::sdMinMEstimatorSigma = 0.5;
 
-// one cached device handle per host thread (the MapMaker thread): buffers survive across BundleAdjust calls
+// one cached device handle per host thread (the MapMaker thread): device buffers, pinned staging and the marshalling
+// threads survive across BundleAdjust calls -- the reference builds a new ChainBundle on the stack for every call
+// (src/BundleAdjusterMulti.cc:75).  The handle is reused when the next object asks for the same configuration.
 static thread_local McpBa* tl_pooled = nullptr;
+static thread_local McpBaConfig tl_pooled_cfg;
 
 ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey, bool bVerbose)
     : mmCameraModels(cams), mbUseRobust(bUseRobust), mbUseTukey(bUseTukey), mbVerbose(bVerbose)
@@ -23,7 +27,7 @@ ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey,
 ChainBundle::~ChainBundle()
 {
   if (mpHandle) {
-    if (!tl_pooled) tl_pooled = mpHandle; else mcp_ba_destroy(mpHandle);
+    if (!tl_pooled) { tl_pooled = mpHandle; tl_pooled_cfg = mConfig; } else mcp_ba_destroy(mpHandle);
   }
 }
 
@@ -43,6 +47,7 @@ int ChainBundle::AddPoint(Vector<3> p, std::vector<int> vCams, bool bFixed)
   for (int k = 0; k < 2; k++) mvPtChain.push_back(k < (int)vCams.size() ? mvIdIndex.at(vCams[k]) : -1);
   mvPtFixed.push_back(bFixed ? 1 : 0);
   mvIdKind.push_back(1); mvIdIndex.push_back((int)mvPtFixed.size() - 1);
+  mvPtId.push_back(mnCurrId);
   return mnCurrId++;
 }
 void ChainBundle::AddMeas(std::vector<int> vCams, int nPointIdx, Vector<2> v2Pos, double dNoiseSigmaSquared, std::string cameraName)
@@ -53,24 +58,56 @@ void ChainBundle::AddMeas(std::vector<int> vCams, int nPointIdx, Vector<2> v2Pos
   mvMeasPt.push_back(mvIdIndex.at(nPointIdx));
   mvMeasNoise.push_back(dNoiseSigmaSquared);
   mvMeasFirstId.push_back(vCams[0]);
-  int ci = -1;
-  for (size_t i = 0; i < mvCamNames.size(); i++) if (mvCamNames[i] == cameraName) ci = (int)i;
-  if (ci < 0) { if (!mmCameraModels.count(cameraName)) throw std::invalid_argument("ChainBundle::AddMeas: unknown camera " + cameraName); mvCamNames.push_back(cameraName); ci = (int)mvCamNames.size() - 1; }
-  mvMeasCam.push_back(ci);
+  mvMeasCam.push_back(CameraIndex(cameraName));
+}
+
+int ChainBundle::CameraIndex(const std::string& cameraName)
+{
+  for (size_t i = 0; i < mvCamNames.size(); i++) if (mvCamNames[i] == cameraName) return (int)i;
+  if (!mmCameraModels.count(cameraName)) throw std::invalid_argument("ChainBundle::AddMeas: unknown camera " + cameraName);
+  mvCamNames.push_back(cameraName);
+  return (int)mvCamNames.size() - 1;
+}
+
+void ChainBundle::AddMeas(int nBasePoseId, int nCamPoseId, int nPointIdx, const Vector<2>& v2Pos, double dNoiseSigmaSquared, int nCameraIndex)
+{
+  mvMeasXy.push_back(v2Pos[0]); mvMeasXy.push_back(v2Pos[1]);
+  mvMeasChain.push_back(mvIdIndex.at(nBasePoseId));
+  mvMeasChain.push_back(nCamPoseId >= 0 ? mvIdIndex.at(nCamPoseId) : -1);
+  mvMeasPt.push_back(mvIdIndex.at(nPointIdx));
+  mvMeasNoise.push_back(dNoiseSigmaSquared);
+  mvMeasFirstId.push_back(nBasePoseId);
+  mvMeasCam.push_back(nCameraIndex);
+}
+
+void ChainBundle::Reserve(size_t nPoses, size_t nPoints, size_t nMeas)
+{
+  mvPoseRt.reserve(12 * nPoses); mvPoseFixed.reserve(nPoses);
+  mvPtXyz.reserve(3 * nPoints); mvPtChain.reserve(2 * nPoints); mvPtFixed.reserve(nPoints); mvPtId.reserve(nPoints);
+  mvIdKind.reserve(nPoses + nPoints + 1); mvIdIndex.reserve(nPoses + nPoints + 1);
+  mvMeasXy.reserve(2 * nMeas); mvMeasChain.reserve(2 * nMeas); mvMeasPt.reserve(nMeas); mvMeasNoise.reserve(nMeas);
+  mvMeasFirstId.reserve(nMeas); mvMeasCam.reserve(nMeas);
 }
 
 int ChainBundle::Upload()
 {
   if (!mpHandle) {
-    if (tl_pooled) { mpHandle = tl_pooled; tl_pooled = nullptr; mcp_ba_destroy(mpHandle); mpHandle = nullptr; }   // config may differ: recreate
     McpBaConfig cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
     mcp_ba_default_config(&cfg);
     cfg.use_robust = mbUseRobust; cfg.use_tukey = mbUseTukey; cfg.verbose = mbVerbose;
     cfg.max_trials_after_failure = snMaxTrialsAfterFailure;
     cfg.update_pct_limit = sdUpdatePercentConvergenceLimit; cfg.update_rms_limit = sdUpdateRMSConvergenceLimit;
     cfg.min_sigma = sdMinMEstimatorSigma;
-    int rc = mcp_ba_create(&cfg, &mpHandle);
-    if (rc) return rc;
+    if (tl_pooled && std::memcmp(&tl_pooled_cfg, &cfg, sizeof(cfg)) == 0) {
+      mpHandle = tl_pooled;                      // same configuration: keep the pooled buffers
+      tl_pooled = nullptr;
+    } else {
+      if (tl_pooled) { mcp_ba_destroy(tl_pooled); tl_pooled = nullptr; }
+      int rc = mcp_ba_create(&cfg, &mpHandle);
+      if (rc) return rc;
+    }
+    mConfig = cfg;
   }
   std::vector<McpTaylorCam> cams;
   for (auto& n : mvCamNames) cams.push_back(mmCameraModels[n].ToAbi());
@@ -113,8 +150,7 @@ int ChainBundle::Compute(bool* pAbortSignal, int nNumIter, double dUserLambda)
     const int no = mcp_ba_get_outliers(mpHandle, idx.data(), (int)idx.size());
     for (int i = 0; i < no && i < (int)idx.size(); i++) {
       const int m = idx[i];
-      int pid = -1;                                           // bundle id of the point
-      for (size_t id = 1; id < mvIdKind.size(); id++) if (mvIdKind[id] == 1 && mvIdIndex[id] == mvMeasPt[m]) { pid = (int)id; break; }
+      const int pid = mvPtId[mvMeasPt[m]];                    // bundle id of the point
       mvOutlierMeasurementIdx.push_back(std::make_tuple(pid, mvMeasFirstId[m], mvCamNames[mvMeasCam[m]]));
     }
   }

@@ -21,6 +21,11 @@ class ChainBundle {
   int AddPose(SE3 se3PoseFromRef, bool bFixed);                                        // src/ChainBundle.cc:1198
   int AddPoint(Vector<3> v3PointInCam, std::vector<int> vCams, bool bFixed);           // :1211
   void AddMeas(std::vector<int> vCams, int nPointIdx, Vector<2> v2Pos, double dNoiseSigmaSquared, std::string cameraName);  // :1239
+  // The same measurement without the per-call vector / string copies of the reference signature: the two pose ids of the
+  // observing chain and the index CameraIndex(name) returned for the camera.  BundleAdjusterCuda marshals through these.
+  int CameraIndex(const std::string& cameraName);
+  void AddMeas(int nBasePoseId, int nCamPoseId, int nPointIdx, const Vector<2>& v2Pos, double dNoiseSigmaSquared, int nCameraIndex);
+  void Reserve(size_t nPoses, size_t nPoints, size_t nMeas);
   int Compute(bool* pAbortSignal, int nNumIter = snMaxIterations, double dUserLambda = -1);   // :1305
   bool Converged() { return mbConverged; }
   int TotalIterations() { return mnTotalIterations; }
@@ -44,6 +49,8 @@ class ChainBundle {
   bool mbUseRobust, mbUseTukey, mbVerbose;
   int mnCurrId = 1;                        // ids are one shared counter starting at 1 (:1145)
   std::vector<int> mvIdKind, mvIdIndex;    // id -> (0 pose / 1 point), index
+  std::vector<int> mvPtId;                 // point index -> id
+  McpBaConfig mConfig;                     // configuration the device handle was created with
   std::vector<double> mvPoseRt, mvPtXyz, mvMeasXy, mvMeasNoise;
   std::vector<uint8_t> mvPoseFixed, mvPtFixed;
   std::vector<int32_t> mvPtChain, mvMeasChain, mvMeasPt, mvMeasCam, mvMeasFirstId;
