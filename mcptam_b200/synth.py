@@ -483,3 +483,79 @@ def make_stereo_scene(seed=0, baseline=0.5, plane_z=4.0, yaw=-0.04):
     cfw_b = np.concatenate([Rb.reshape(-1), -Rb @ centre_b])
     return dict(cam_a=cams[0], cam_b=cams[1], cfw_a=cfw_a, cfw_b=cfw_b, plane_z=plane_z,
                 img_a=render_plane_view(cams[0], cfw_a, texture, plane_z), img_b=render_plane_view(cams[1], cfw_b, texture, plane_z))
+
+
+# ---------------------------------------------------------------------------------------------
+# Variants of a problem that exercise the other chain shapes the reference builds
+# ---------------------------------------------------------------------------------------------
+def _rt_unpack(row):
+    row = np.asarray(row, np.float64)
+    return row[:9].reshape(3, 3), row[9:]
+
+
+def with_fixed_points(prob: BaProblem, frac=0.1, seed=0) -> BaProblem:
+    """Turns a fraction of the points into FIXED world points the way BundleAdjusterMulti marshals `point.mbFixed`
+    (src/BundleAdjusterMulti.cc:143-149): one extra fixed identity "world" pose, a ONE-link chain [world] and the
+    world position as coordinates.  Their chi2 enters the robust statistics negated (src/ChainBundle.cc:413-414).
+    The positions come from the ground truth (a fixed point is one the map trusts)."""
+    rng = np.random.default_rng(seed + 7919)
+    n_pt = prob.n_pt
+    pick = np.flatnonzero(rng.random(n_pt) < frac)
+    world_id = prob.n_pose
+    pose_Rt = np.vstack([prob.pose_Rt, np.concatenate([np.eye(3).reshape(-1), np.zeros(3)])[None]])
+    truth_pose = np.vstack([prob.truth_pose_Rt, pose_Rt[-1:]]) if prob.truth_pose_Rt is not None else None
+    pose_fixed = np.concatenate([prob.pose_fixed, np.ones(1, np.uint8)])
+    pt_xyz, pt_chain, pt_fixed = prob.pt_xyz.copy(), prob.pt_chain.copy(), prob.pt_fixed.copy()
+    truth_pt = prob.truth_pt_xyz.copy() if prob.truth_pt_xyz is not None else None
+    src_pose = prob.truth_pose_Rt if prob.truth_pose_Rt is not None else prob.pose_Rt
+    src_rel = prob.truth_pt_xyz if prob.truth_pt_xyz is not None else prob.pt_xyz
+    for p in pick:
+        m, c = prob.pt_chain[p]
+        T = rt_mul(_rt_unpack(src_pose[c]), _rt_unpack(src_pose[m])) if c >= 0 else _rt_unpack(src_pose[m])
+        Ri, ti = rt_inv(T)
+        w = Ri @ src_rel[p] + ti
+        pt_xyz[p] = w
+        if truth_pt is not None:
+            truth_pt[p] = w
+        pt_chain[p] = (world_id, -1)
+        pt_fixed[p] = 1
+    return dataclasses.replace(prob, pose_Rt=np.ascontiguousarray(pose_Rt), pose_fixed=pose_fixed, pt_xyz=pt_xyz,
+                               pt_chain=pt_chain, pt_fixed=pt_fixed, truth_pose_Rt=truth_pose, truth_pt_xyz=truth_pt)
+
+
+def as_single_link(prob: BaProblem) -> BaProblem:
+    """The same map marshalled the way BundleAdjusterSingle does (src/BundleAdjusterSingle.cc:83-151): every keyframe
+    carries its own CamFromWorld pose, measurement and point chains have ONE link.  (Each camera of a multi-keyframe
+    becomes an independent pose, so the optimum differs from the rig-constrained problem; it is the chain shape that
+    matters here.)  Fixed world points (one-link chains onto the world pose) are kept as they are."""
+    n_mkf = prob.n_mkf
+    key = {}
+    poses, truth, fixed = [], [], []
+
+    def kf_id(m, c):
+        if c < 0:
+            k = (int(m), -1)
+        else:
+            k = (int(m), int(c))
+        if k not in key:
+            key[k] = len(poses)
+            if c < 0:
+                poses.append(prob.pose_Rt[m]); fixed.append(prob.pose_fixed[m])
+                truth.append(prob.truth_pose_Rt[m] if prob.truth_pose_Rt is not None else prob.pose_Rt[m])
+            else:
+                poses.append(rt_pack(rt_mul(_rt_unpack(prob.pose_Rt[c]), _rt_unpack(prob.pose_Rt[m]))))
+                fixed.append(prob.pose_fixed[m])
+                tp = prob.truth_pose_Rt if prob.truth_pose_Rt is not None else prob.pose_Rt
+                truth.append(rt_pack(rt_mul(_rt_unpack(tp[c]), _rt_unpack(tp[m]))))
+        return key[k]
+
+    # keyframes in (mkf, cam) order so that the fixed first MKF's keyframes come first
+    pairs = sorted({(int(a), int(b)) for a, b in prob.meas_chain} | {(int(a), int(b)) for a, b in prob.pt_chain})
+    for m, c in pairs:
+        kf_id(m, c)
+    meas_chain = np.array([(kf_id(a, b), -1) for a, b in prob.meas_chain], np.int32)
+    pt_chain = np.array([(kf_id(a, b), -1) for a, b in prob.pt_chain], np.int32)
+    del n_mkf
+    return dataclasses.replace(prob, pose_Rt=np.ascontiguousarray(np.array(poses)), pose_fixed=np.array(fixed, np.uint8),
+                               meas_chain=meas_chain, pt_chain=pt_chain, n_mkf=len(poses),
+                               truth_pose_Rt=np.ascontiguousarray(np.array(truth)))

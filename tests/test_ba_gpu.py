@@ -92,9 +92,24 @@ def test_schur_variants_parity(capi, monkeypatch, cfg, seed, lam, mode):
     assert _rel(d_g, d_1) < 1e-9
 
 
-@pytest.mark.parametrize("cfg,seed,iters", [("tiny", 0, 12), ("tiny", 2, 12), ("cfg1", 0, 10), ("cfg1", 1, 10)])
-def test_compute_parity(capi, cfg, seed, iters):
+def _variant(prob, variant):
+    """The other chain shapes the reference builds: fixed world points on a one-link [world] chain
+    (src/BundleAdjusterMulti.cc:143-149, chi2 negated src/ChainBundle.cc:413-414) and BundleAdjusterSingle's one-link
+    keyframe chains (src/BundleAdjusterSingle.cc:83-151)."""
+    if "fixed" in variant:
+        prob = synth.with_fixed_points(prob, 0.15)
+    if "single" in variant:
+        prob = synth.as_single_link(prob)
+    return prob
+
+
+@pytest.mark.parametrize("cfg,seed,iters", [("tiny", 0, 12), ("tiny", 2, 12), ("cfg1", 0, 10), ("cfg1", 1, 10), ("cfg2", 0, 10)])
+def test_compute_parity(capi, monkeypatch, cfg, seed, iters):
+    """Full Compute through the DEFAULT path (3 speculative candidates, fused multi-candidate Schur pass, look-ahead,
+    PDL) vs the oracle -- including the benchmarked configuration (cfg2, 10 iterations = one bench.py step)."""
     from oracle.oracle import OracleBA
+    for k in ("MCP_BA_SPECULATE", "MCP_BA_FUSE_SCHUR", "MCP_BA_LOOKAHEAD", "MCP_BA_PDL", "MCP_BA_SCHUR", "MCP_BA_GRAPH"):
+        monkeypatch.delenv(k, raising=False)
     prob = _mk(cfg, seed)
     g = capi.BaHandle()
     g.load(prob)
@@ -200,3 +215,68 @@ def test_point_depth_covariance(capi, robust):
     g2.load(synth.make_ba_config("tiny", seed=0))
     rc, st = g2.compute(2)
     assert st.max_cov == 0
+
+
+@pytest.mark.parametrize("variant", ["fixed", "single", "fixed+single"])
+@pytest.mark.parametrize("cfg,seed", [("tiny", 0), ("cfg1", 2)])
+def test_fixed_points_and_one_link_chains(capi, cfg, seed, variant):
+    """Residuals, chi2 sign, Jacobians, one LM step and a full Compute on maps with fixed world points and/or
+    one-link chains, vs the oracle."""
+    from oracle.oracle import OracleBA
+    prob = _variant(_mk(cfg, seed), variant)
+    g = capi.BaHandle()
+    g.load(prob)
+    o = OracleBA(prob)
+    eg, cg = g.eval()
+    eo, co = o.eval()
+    assert np.allclose(eg, eo, rtol=1e-10, atol=1e-9)
+    assert np.allclose(cg, co, rtol=1e-10, atol=1e-9)
+    if "fixed" in variant:
+        assert (co < 0).sum() > 0 and np.array_equal(cg < 0, co < 0)      # the sign flip really is exercised
+    J = g.jacobians()
+    rng = np.random.default_rng(seed)
+    for m in rng.choice(prob.n_meas, min(prob.n_meas, 300), replace=False):
+        jo, js, jp = o.jacobians(m)
+        ref = np.concatenate([jo[0].ravel(), js[0].ravel(), jp.ravel()])
+        assert np.abs(J[m] - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1.0), (m, J[m], ref)
+    rc, d_o, sig_o, chi_o = o.lm_step(20.0, -1.0, 0)
+    assert rc == 0
+    d_g, sig_g, chi_g = g.lm_step(20.0, -1.0)
+    assert abs(sig_g - sig_o) <= 1e-12 * sig_o
+    assert abs(chi_g - chi_o) <= 1e-9 * abs(chi_o)
+    assert _rel(d_g, d_o) < 1e-6
+    rc_o, st_o = o.compute(8)
+    rc_g, st_g = g.compute(8)
+    assert rc_g == rc_o and st_g.total_trials == st_o.total_trials and st_g.converged == st_o.converged
+    assert _rel(g.poses(), o.poses()) < 1e-6 and _rel(g.points(), o.points()) < 1e-6
+    assert abs(st_g.sigma_sq - st_o.sigma_sq) <= 1e-6 * st_o.sigma_sq
+    assert abs(st_g.chi2_after - st_o.chi2_after) <= 1e-6 * abs(st_o.chi2_after)
+    assert sorted(g.outliers().tolist()) == sorted(o.outliers().tolist())
+    if "fixed" in variant:                                               # fixed points do not move
+        fx = prob.pt_fixed.astype(bool)
+        assert np.array_equal(g.points()[fx], prob.pt_xyz[fx])
+
+
+def test_cfg4_parity(capi):
+    """The 8-camera 1000 KF / 100k-point map (BASELINE.json configs[3]) on one GPU: one LM step and a 2-iteration
+    Compute through the default path vs the oracle (~25 s of CPU)."""
+    from oracle.oracle import OracleBA
+    prob = _mk("cfg4", 0)
+    g = capi.BaHandle()
+    g.load(prob)
+    o = OracleBA(prob)
+    rc, d_o, sig_o, chi_o = o.lm_step(100.0, -1.0, 0)
+    assert rc == 0
+    d_g, sig_g, chi_g = g.lm_step(100.0, -1.0)
+    assert abs(sig_g - sig_o) <= 1e-12 * sig_o
+    assert abs(chi_g - chi_o) <= 1e-9 * abs(chi_o)
+    nc = 6 * o.n_pose_var
+    assert _rel(d_g[:nc], d_o[:nc]) < 1e-6 and _rel(d_g[nc:], d_o[nc:]) < 1e-6
+    rc_o, st_o = o.compute(2)
+    rc_g, st_g = g.compute(2)
+    assert rc_g == rc_o and st_g.total_trials == st_o.total_trials
+    assert _rel(g.poses(), o.poses()) < 1e-6 and _rel(g.points(), o.points()) < 1e-6
+    assert abs(st_g.sigma_sq - st_o.sigma_sq) <= 1e-6 * st_o.sigma_sq
+    assert abs(st_g.lambda_ - st_o.lambda_) <= 1e-5 * st_o.lambda_
+    assert abs(st_g.chi2_after - st_o.chi2_after) <= 1e-6 * st_o.chi2_after
+    assert sorted(g.outliers().tolist()) == sorted(o.outliers().tolist())
