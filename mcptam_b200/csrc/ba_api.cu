@@ -50,9 +50,10 @@ int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, dou
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
 void launch_lambda_init(const BaDev& d, cudaStream_t s);
 void launch_lambda_apply(const BaDev& d, cudaStream_t s);
-void launch_chol_solve(const BaDev& d, int epoch, int n_sms, cudaStream_t s);
+void launch_chol_solve(const BaDev& d, int epoch, int max_ctas, int* task_base, cudaStream_t s);
 size_t chol_tiles_doubles(int nc);
 size_t chol_inv_doubles(int nc);
+size_t chol_ll_bytes(int nc);
 size_t chol_flag_ints(int nc);
 int chol_max_n();
 void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
@@ -115,14 +116,14 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items, b_R;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_Lll, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items, b_R;
   // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
   struct Cand {
-    DevBuf b_acc, b_dc, b_L, b_Linv, b_cflags, b_part, b_Y;
+    DevBuf b_acc, b_dc, b_L, b_Linv, b_Lll, b_cflags, b_part, b_Y;
     BaDev d;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_schur = nullptr;
-    int chol_epoch = 0;
+    int chol_epoch = 0, chol_task_base = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
   cudaEvent_t ev_ready = nullptr, ev_red = nullptr, ev_ctrl = nullptr;
   cudaStream_t copy_stream = nullptr;   // control-block read-back that does not queue behind look-ahead kernels
@@ -130,7 +131,7 @@ struct McpBa {
   int n_spec = 3;                 // candidates per round (1 = no speculation)
   bool fuse_schur = true;         // one multi-candidate Schur pass per round (MCP_BA_FUSE_SCHUR=0: one pass per candidate)
   int spec_rounds = 0, spec_used = 0;
-  int chol_epoch = 0, n_sms = 148;
+  int chol_epoch = 0, chol_task_base = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
   BaCtrl* ctrl_host = nullptr;   // pinned
   int* flags_host = nullptr;     // pinned, n_meas
@@ -219,13 +220,13 @@ int mcp_ba_destroy(McpBa* h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items, &h->b_R };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_Lll, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items, &h->b_R };
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
   for (int q = 1; q < MAX_CAND; q++) {
     McpBa::Cand& cq = h->cand[q];
     if (cq.stream) cudaStreamSynchronize(cq.stream);
-    DevBuf* cb[] = { &cq.b_acc, &cq.b_dc, &cq.b_L, &cq.b_Linv, &cq.b_cflags, &cq.b_part, &cq.b_Y };
+    DevBuf* cb[] = { &cq.b_acc, &cq.b_dc, &cq.b_L, &cq.b_Linv, &cq.b_Lll, &cq.b_cflags, &cq.b_part, &cq.b_Y };
     for (DevBuf* b : cb) b->release();
     if (cq.stream) cudaStreamDestroy(cq.stream);
     if (cq.ev_done) cudaEventDestroy(cq.ev_done);
@@ -380,7 +381,10 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if ((rc = h->b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
   if ((rc = h->b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
   MCP_CUDA_CHECK(cudaMemsetAsync(h->b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
-  h->chol_epoch = 0;
+  // LL tiles are tagged with the launch number (chol_epoch restarts at 1): stale tags of an earlier problem must go
+  if ((rc = h->b_Lll.ensure(chol_ll_bytes(nc)))) return rc;
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
+  h->chol_epoch = 0; h->chol_task_base = 0;
   {
     const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1);
     if ((rc = h->b_sel.ensure(sel_bytes))) return rc;
@@ -415,7 +419,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.slot_pt = h->b_slot_pt.as<int>(); d.slot_lo = pr.pt_slot_off[d.p_lo]; d.slot_hi = pr.pt_slot_off[d.p_hi];
   double* acc = h->b_acc.as<double>();
   d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
-  d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.flags = h->b_cflags.as<int>();
+  d.dc = h->b_dc.as<double>(); d.L = h->b_L.as<double>(); d.Linv = h->b_Linv.as<double>(); d.Lll = h->b_Lll.as<uint4>(); d.flags = h->b_cflags.as<int>();
   d.rs_ent = h->b_rs_ent.as<int2>(); d.rs_grp = h->b_rs_grp.as<int>(); d.rs_items = h->b_rs_items.as<int4>(); d.n_rs_items = (int)pr.rs_items.n;
   d.schur_mode = schur_mode; d.rs_nblk = rs_nblk;
   d.mrec = h->b_mrec.as<double>(); d.pb_idx = h->b_pb_idx.as<int>(); d.pb_items = h->b_pb_items.as<int4>(); d.n_pb_items = (int)pr.pb_items.n;
@@ -428,7 +432,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     McpBa::Cand& cq = h->cand[q];
     cq.d = d;
     cq.d.cand = q;
-    cq.chol_epoch = 0;
+    cq.chol_epoch = 0; cq.chol_task_base = 0;
     if (q >= h->n_spec) continue;
     const size_t sm_doubles = h->acc_doubles - h->off_Sm;
     if ((rc = cq.b_acc.ensure(sizeof(double) * sm_doubles))) return rc;
@@ -436,13 +440,15 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     if ((rc = cq.b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
     if ((rc = cq.b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
     if ((rc = cq.b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
+    if ((rc = cq.b_Lll.ensure(chol_ll_bytes(nc)))) return rc;
+    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
     if ((rc = cq.b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
     if ((rc = cq.b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
     MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
     MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_dc.p, 0, sizeof(double) * ncp, h->stream));
     MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
     cq.d.Sm = cq.b_acc.as<double>(); cq.d.rm = cq.d.Sm + (h->off_rm - h->off_Sm);
-    cq.d.dc = cq.b_dc.as<double>(); cq.d.L = cq.b_L.as<double>(); cq.d.Linv = cq.b_Linv.as<double>();
+    cq.d.dc = cq.b_dc.as<double>(); cq.d.L = cq.b_L.as<double>(); cq.d.Linv = cq.b_Linv.as<double>(); cq.d.Lll = cq.b_Lll.as<uint4>();
     cq.d.flags = cq.b_cflags.as<int>(); cq.d.part = cq.b_part.as<double>(); cq.d.Y = cq.b_Y.as<double>();
   }
   BaCtrl& c = *h->ctrl_host;
@@ -670,7 +676,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         NCCL_CHECK(ncclGroupEnd());
         if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_red, s));
       }
-      { Prof p(h, C_SOLVE); TlScope t(h, "solve", 0, s); launch_chol_solve(d, ++h->chol_epoch, h->n_sms, s); }
+      { Prof p(h, C_SOLVE); TlScope t(h, "solve", 0, s); launch_chol_solve(d, ++h->chol_epoch, h->n_sms / n_cand, &h->chol_task_base, s); }
       { Prof p(h, C_BACKSUB); TlScope t(h, "backsub", 0, s); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
       for (int q = 1; q < n_cand; q++) {
         McpBa::Cand& cq = h->cand[q];
@@ -685,7 +691,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
             h->launches += 2;
           }
         }
-        { TlScope t(h, "solve", q, cq.stream); launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms, cq.stream); }
+        { TlScope t(h, "solve", q, cq.stream); launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms / n_cand, &cq.chol_task_base, cq.stream); }
         { TlScope t(h, "backsub", q, cq.stream); launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream); }
         h->launches += 2;
         if (multi) { launch_reduce_partials(cq.d, 0, n_bs, red + 3 * q, cq.stream); h->launches++; }

@@ -97,6 +97,7 @@ struct BaDev {
   double* dc;                    // [nc]   pose update
   double* L;                     // Cholesky factor, 32x32 tiles (lower block triangle + rhs block row)
   double* Linv;                  // inverse diagonal tiles
+  uint4* Lll;                    // the same tiles as self-validating 16-byte lines {lo, epoch, hi, epoch} (ba_solve.cu)
   int* flags;                    // dataflow ready flags + counters (ba_solve.cu)
   double* part;                  // [8][MAX_PARTIALS] per-block partial sums
   unsigned* sel_hist;            // [SEL_PASSES][SEL_BINS] radix-select histograms (self re-arming)

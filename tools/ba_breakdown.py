@@ -21,10 +21,9 @@ g.reset_state(); g.compute(3); g.reset_state()
 g.solve_trace(arm=True)
 d, s, r = g.lm_step(100.0)
 tr = g.solve_trace()
-T = (6 * g.n_pose_var + 31) // 32; nt = T * (T + 1) // 2 + T
-tt = tr[:nt]; t0 = tt[:, 2].min()
-print(cfg, "solve: T", T, "tasks", nt, "span us", (tt[:, 4].max() - t0) / 1e3, "backsolve end us", (tr[nt, 0] - t0) / 1e3)
-for k in range(nt):
-    i, j, a, b, c, cta = tt[k][:6]
-    if i == j and (j < 4 or j >= T - 2):
-        print(f"  diag {int(j):2d} start {(a-t0)/1e3:7.1f} deps {(b-t0)/1e3:7.1f} potrf {(tt[k][6]-t0)/1e3:7.1f} inv {(tt[k][7]-t0)/1e3:7.1f} end {(c-t0)/1e3:7.1f}")
+T = (6 * g.n_pose_var + 31) // 32; nt = sum(2 + max(0, T - j - 2) for j in range(T))
+tt = tr[:nt]; ch = tr[nt + 1: nt + 1 + T]; t0 = min(tt[:, 2].min(), ch[:, 2].min())
+print(cfg, "solve: T", T, "worker tasks", nt, "factorisation span us", (max(tt[:, 4].max(), ch[:, 4].max()) - t0) / 1e3, "backsolve end us", (tr[nt, 0] - t0) / 1e3)
+for j in range(T):
+    if j < 4 or j >= T - 2:
+        print(f"  chain step {j:2d}: inputs ready {(ch[j][2]-t0)/1e3:7.1f}  sub-diagonal solved {(ch[j][3]-t0)/1e3:7.1f}  factor published {(ch[j][4]-t0)/1e3:7.1f}")
