@@ -115,13 +115,14 @@ def cpu_reference_run(prob, steps, warmup, lm_iters_cpu):
     return total_it / total_t, float(np.mean(per_step)) * 1e3, total_it
 
 
-def bench_frontend(capi, synth, device, steps=20, warmup=3, n_cams=4, n_patches=1000):
-    """BASELINE.json configs[2]: 4-cam 640x480 pyramids, FAST-10 + 1k PatchFinder searches per frame per camera.
-    One handle (= one CUDA stream) per camera; host buffers in, host results out (H2D/D2H inside the timing)."""
+def bench_frontend(capi, synth, device, cam_ids=(0, 1, 2, 3), steps=20, warmup=3, n_patches=1000, with_cpu=True):
+    """BASELINE.json configs[2]: 640x480 pyramids, FAST-10 + 1k PatchFinder searches per frame per camera, for the cameras
+    in `cam_ids` (all four on one GPU; camera c -> GPU c mod N when sharded).  One handle (= one CUDA
+    stream) per camera; host buffers in, host results out (H2D/D2H inside the timing)."""
     import time as _t
-    rng = np.random.default_rng(0)
     cams, frames, reqs = [], [], []
-    for c in range(n_cams):
+    for c in cam_ids:
+        rng = np.random.default_rng(1000 + c)
         f = capi.FeHandle(640, 480, device=device, max_corners_per_level=16384)
         a = synth.make_frame(seed=100 + c)
         b = synth.make_frame(seed=100 + c, shift=(3.0, -2.0))
@@ -135,46 +136,197 @@ def bench_frontend(capi, synth, device, steps=20, warmup=3, n_cams=4, n_patches=
         rq["pred_x"] = cor[:, 0] - 3 + rng.integers(-2, 3, n_patches); rq["pred_y"] = cor[:, 1] + 2 + rng.integers(-2, 3, n_patches)
         rq["range"] = 10; rq["subpix_its"] = 8
         cams.append(f); frames.append(b); reqs.append(rq)
-    t_kf = t_ps = 0.0
-    dev_kf = dev_ps = 0.0
-    found = 0
+    n_local = len(cams)
+    t_kf = t_ps = dev_ps = 0.0
+    found, checksum = 0, 0
     for s in range(warmup + steps):
-        for c in range(n_cams):
+        for c in range(n_local):
             t0 = _t.perf_counter()
-            cams[c].make_keyframe(1, frames[c])
+            lv = cams[c].make_keyframe(1, frames[c])
             t1 = _t.perf_counter()
             res = cams[c].search_patches(1, reqs[c])
             t2 = _t.perf_counter()
             if s >= warmup:
                 t_kf += t1 - t0; t_ps += t2 - t1
-                tm = cams[c].timing()
-                dev_ps += tm["ms_search"]
+                dev_ps += cams[c].timing()["ms_search"]
                 found += int(res["found"].sum())
-        if s >= warmup:
-            pass
-    n_frames = steps * n_cams
-    tm = cams[0].timing()
-    # CPU restatement of the same per-frame work on one host core (the reference tracker is single threaded)
-    from oracle import oracle as ora
-    t0 = _t.perf_counter()
-    pyr_b = ora.pyramid(frames[0])
-    lv_b = [ora.level_corners(im) for im in pyr_b]
-    t1 = _t.perf_counter()
-    pyr_a = ora.pyramid(synth.make_frame(seed=100))
-    n_cpu = len(reqs[0])
-    ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0][:8])      # warm the marshalling path
-    t1b = _t.perf_counter()
-    flags_cpu, _ = ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0])
-    t2 = _t.perf_counter()
-    t1 = t1 + 0.0; t2 = t1 + (t2 - t1b)
-    cpu = {"keyframe_ms": 1e3 * (t1 - t0), "patches_per_sec": n_cpu / (t2 - t1), "cores": 1, "kind": "port",
-           "sample": "1 camera frame (pyramid + FAST-10 + threshold + LUT) and %d patch searches in one C call, oracle/fe_oracle.c" % n_cpu}
-    return {"cpu_baseline": cpu,"workload": "cfg3: %d-cam 640x480, 4-level pyramid + FAST-10 + %d PatchFinder searches (8 sub-pixel its) per frame" % (n_cams, n_patches),
-            "camera_frames_per_sec_e2e": n_frames / (t_kf + t_ps), "keyframe_ms_e2e": 1e3 * t_kf / n_frames,
-            "patches_per_sec_e2e": n_frames * n_patches / t_ps, "patches_per_sec_device": n_frames * n_patches / (dev_ps * 1e-3),
-            "patch_search_ms_device": dev_ps / n_frames, "found_fraction": found / (n_frames * n_patches),
-            "pyramid_ms_device": tm["ms_pyramid"], "fast_ms_device": tm["ms_fast"],
-            "algorithmic_bytes_per_camera_frame": 307200 + 100800 + 100800, "patch_bytes_each": 800}
+            if s == warmup:                                  # result fingerprint of every camera (compared across GPU counts)
+                checksum += int(lv[0]["n_corners"]) * 1000003 + int(res["found"].sum()) * 7919 + int(np.rint(res["found_x"][res["found"] > 0] * 64).sum() % 1000003)
+    n_frames = steps * n_local
+    tm = cams[0].timing() if cams else {"ms_pyramid": 0.0, "ms_fast": 0.0}
+    out = {"cams": list(cam_ids), "n_frames": n_frames, "t_kf": t_kf, "t_ps": t_ps, "dev_ps_ms": dev_ps, "found": found, "checksum": checksum,
+           "pyramid_ms_device": tm["ms_pyramid"], "fast_ms_device": tm["ms_fast"], "n_patches": n_patches}
+    if with_cpu and cams:
+        # CPU restatement of the same per-frame work on one host core (the reference tracker is single threaded)
+        from oracle import oracle as ora
+        ora.lib()                                            # (first use compiles the -O3 build: not part of the timing)
+        ora.pyramid(frames[0])
+        t0 = _t.perf_counter()
+        pyr_b = ora.pyramid(frames[0])
+        lv_b = [ora.level_corners(im) for im in pyr_b]
+        t1 = _t.perf_counter()
+        pyr_a = ora.pyramid(synth.make_frame(seed=100 + cam_ids[0]))
+        ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0][:8])      # warm the marshalling path
+        t1b = _t.perf_counter()
+        ora.search_patches_batch(pyr_a, pyr_b, lv_b, reqs[0])
+        t2 = _t.perf_counter()
+        out["cpu_baseline"] = {"keyframe_ms": 1e3 * (t1 - t0), "patches_per_sec": len(reqs[0]) / (t2 - t1b), "cores": 1, "kind": "port",
+                               "sample": "1 camera frame (pyramid + FAST-10 + threshold + LUT) and %d patch searches in one C call, oracle/fe_oracle.c" % len(reqs[0])}
+    for f in cams:
+        f.close()
+    return out
+
+
+def frontend_report(parts, n_gpus, peak):
+    """Merges the per-rank results of bench_frontend (every rank timed its own cameras concurrently: the frame rate of
+    the rig is the total number of camera frames over the slowest rank's time)."""
+    n_frames = sum(p["n_frames"] for p in parts)
+    n_patches = parts[0]["n_patches"]
+    t_max = max(p["t_kf"] + p["t_ps"] for p in parts)
+    t_kf = sum(p["t_kf"] for p in parts); t_ps = sum(p["t_ps"] for p in parts); dev_ps = sum(p["dev_ps_ms"] for p in parts)
+    frame_bytes, patch_bytes = 307200 + 100800 + 100800, 800       # SURVEY.md §8(d)
+    kf_dev_ms = parts[0]["pyramid_ms_device"] + parts[0]["fast_ms_device"]
+    ps_dev_ms = dev_ps / n_frames
+    rep = {"workload": "cfg3: %d-cam 640x480, 4-level pyramid + FAST-10 + %d PatchFinder searches (8 sub-pixel its) per frame, camera c on GPU c mod %d"
+                       % (sum(len(p["cams"]) for p in parts), n_patches, n_gpus),
+           "n_gpus": n_gpus, "cameras_per_rank": [p["cams"] for p in parts],
+           "camera_frames_per_sec_e2e": n_frames / t_max, "keyframe_ms_e2e": 1e3 * t_kf / n_frames,
+           "patches_per_sec_e2e": n_frames * n_patches / (t_ps / max(len(parts), 1)) if n_gpus > 1 else n_frames * n_patches / t_ps,
+           "patches_per_sec_device": n_frames * n_patches / (dev_ps * 1e-3) * (len(parts) if n_gpus > 1 else 1),
+           "patch_search_ms_device": ps_dev_ms, "found_fraction": sum(p["found"] for p in parts) / (n_frames * n_patches),
+           "pyramid_ms_device": parts[0]["pyramid_ms_device"], "fast_ms_device": parts[0]["fast_ms_device"],
+           "algorithmic_bytes_per_camera_frame": frame_bytes, "patch_bytes_each": patch_bytes,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                        "keyframe": {"kernel": "k_halfsample_fused + k_fast_*", "achieved": frame_bytes / (kf_dev_ms * 1e-3) / 1e9 if kf_dev_ms > 0 else None,
+                                     "frac": frame_bytes / (kf_dev_ms * 1e-3) / 1e9 / peak if kf_dev_ms > 0 else None},
+                        "patch_search": {"kernel": "k_patch_search", "achieved": patch_bytes * n_patches / (ps_dev_ms * 1e-3) / 1e9 if ps_dev_ms > 0 else None,
+                                         "frac": patch_bytes * n_patches / (ps_dev_ms * 1e-3) / 1e9 / peak if ps_dev_ms > 0 else None},
+                        "note": "one 640x480 frame is 0.5 MB: launch / dependency latency bound, not HBM bound"},
+           "result_checksum_per_camera_set": sum(p["checksum"] for p in parts)}
+    for p in parts:
+        if "cpu_baseline" in p:
+            rep["cpu_baseline"] = p["cpu_baseline"]
+            break
+    return rep
+
+
+def bench_stream(capi, synth, device, seconds=2.0):
+    """BASELINE.json configs[4]: the 4-camera tracker loop (pyramid + FAST, batched FindPVS projection, 1k patch searches,
+    ten pose-update iterations per camera frame, src/Tracker.cc:916-1154) on the main thread while the MapMaker thread keeps
+    running bundle adjustments (cfg2, 10 LM iterations each) on its own handle = its own CUDA stream."""
+    import threading
+    import time as _t
+    rng = np.random.default_rng(7)
+    prob = synth.make_ba_config("cfg2", seed=0)
+    ba = capi.BaHandle(device=device)
+    ba.load(prob)
+    cam = prob.cams[0]
+    cams, frames, reqs, pts = [], [], [], []
+    for c in range(4):
+        f = capi.FeHandle(640, 480, device=device, max_corners_per_level=16384)
+        f.set_camera(cam)
+        a = synth.make_frame(seed=300 + c)
+        lva = f.make_keyframe(0, a)
+        cor = lva[0]["corners"]
+        cor = cor[(cor[:, 0] > 16) & (cor[:, 0] < 624) & (cor[:, 1] > 16) & (cor[:, 1] < 464)]
+        cor = cor[rng.choice(len(cor), 1000, replace=len(cor) < 1000)]
+        rq = np.zeros(len(cor), capi.PATCH_REQ_DTYPE)
+        rq["src_kf"] = 0; rq["src_level"] = 0; rq["src_cx"] = cor[:, 0]; rq["src_cy"] = cor[:, 1]
+        rq["warp_inv"] = np.array([1.0, 0.0, 0.0, 1.0]); rq["search_level"] = 0
+        rq["pred_x"] = cor[:, 0] - 2; rq["pred_y"] = cor[:, 1] + 1
+        rq["range"] = 10; rq["subpix_its"] = 8
+        # map points in front of the camera for the FindPVS projection and the pose update
+        rays = synth.cam_unproject_np(cam, cor.astype(np.float64))
+        pts.append(rays * rng.uniform(3.0, 9.0, (len(rays), 1)))
+        cams.append(f); reqs.append(rq)
+        frames.append([synth.make_frame(seed=300 + c, shift=(2.0 + 0.5 * k, -1.0)) for k in range(3)])
+    ident = np.concatenate([np.eye(3).reshape(-1), np.zeros(3)])
+    stop = {"flag": False, "n": 0, "iters": 0}
+
+    def mapmaker():
+        while not stop["flag"]:
+            ba.reset_state()
+            rc, st = ba.compute(10)
+            stop["n"] += 1; stop["iters"] += max(rc, 0)
+
+    def track_one(k):
+        for c, f in enumerate(cams):
+            f.make_keyframe(1, frames[c][k % 3])
+            zeros = np.zeros_like(pts[c])
+            f.project_points(ident, pts[c], zeros + np.array([1e-3, 0, 0]), zeros + np.array([0, 1e-3, 0]))     # FindPVS block
+            res = f.search_patches(1, reqs[c])
+            jr = f.calc_jacobians(ident, ident, pts[c])                                                    # TrackerData::CalcJacobian
+            meas = np.zeros(len(pts[c]), capi.POSE_MEAS_DTYPE)
+            meas["image"] = jr["px"]; meas["jac"] = jr["jac"]; meas["sqrt_inv_noise"] = 1.0
+            meas["found"][:, 0] = jr["px"][:, 0] + (res["found_x"] - res["coarse_x"]) * 0.1
+            meas["found"][:, 1] = jr["px"][:, 1] + (res["found_y"] - res["coarse_y"]) * 0.1
+            meas["found_flag"] = (res["found"] > 0) & (jr["in_image"] == 1)
+            for _ in range(10):                                                                            # src/Tracker.cc:1089-1140
+                f.pose_update(meas)
+
+    for k in range(3):
+        track_one(k)
+    t0 = _t.perf_counter(); n_alone = 0
+    while _t.perf_counter() - t0 < 0.5 * seconds:
+        track_one(n_alone); n_alone += 1
+    fps_alone = n_alone / (_t.perf_counter() - t0)
+    th = threading.Thread(target=mapmaker)
+    th.start()
+    t0 = _t.perf_counter(); n = 0
+    while _t.perf_counter() - t0 < seconds:
+        track_one(n); n += 1
+    dt = _t.perf_counter() - t0
+    stop["flag"] = True
+    th.join()
+    for f in cams:
+        f.close()
+    ba.close()
+    return {"workload": "cfg5: 4-cam 640x480 tracker loop (pyramid + FAST-10, FindPVS projection of 1k points, 1k patch searches, 10 pose updates "
+                        "per camera frame) with cfg2 bundle adjustments (10 LM iterations each) running on the BA handle's stream",
+            "rig_frames_per_sec_with_ba": n / dt, "rig_frames_per_sec_alone": fps_alone, "target_fps": 30.0,
+            "ba_calls_meanwhile": stop["n"], "ba_lm_iters_per_sec_meanwhile": stop["iters"] / dt}
+
+
+def bench_config(workload, prob, lm_iters, world):
+    """`config` of the JSON line: identical for both arms except for `parallelism` when ranks > 1."""
+    return {"workload": workload, "n_pose": prob.n_pose, "n_points": prob.n_pt, "n_meas": prob.n_meas, "lm_iters_per_step": lm_iters,
+            "l2": "256 MiB flush between steps; within a step the map stays L2-resident",
+            "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"}
+
+
+def csrc_digest():
+    """Content hash of the kernel sources: a committed ncu capture is only quoted if it was taken from these sources."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "mcptam_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the named kernel from profiles/r02_ncu_full_ba.txt
+    (tools/ncu_extract.py output, first line '# csrc <digest>').  None (and why) if the capture is from other sources."""
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_full_ba.txt")
+    if not os.path.exists(prof):
+        return None, "no capture committed"
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    lines = open(prof).read().splitlines()
+    tag = lines[0].split()[-1] if lines and lines[0].startswith("# csrc") else None
+    if tag != csrc_digest():
+        return None, "capture is from other kernel sources (%s, now %s)" % (tag, csrc_digest())
+    tot, cur, seen = 0.0, False, False
+    for ln in lines:
+        f = ln.split()
+        if ln.startswith("Kernel Name"):
+            if seen and cur:
+                break
+            cur = kernel_substr in ln
+            seen = seen or cur
+        elif cur and len(f) >= 3 and f[0].startswith("dram__bytes_") and f[0].endswith(".sum"):
+            tot += float(f[1]) * unit.get(f[2], 1)
+    return (tot if seen else None), ("ok" if seen else "kernel not in the capture")
 
 
 def main():
@@ -195,6 +347,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    args.warmup = warmup
 
     from mcptam_b200 import synth
     prob = synth.make_ba_config(args.config, seed=args.seed)
@@ -204,17 +357,18 @@ def main():
         if rank != 0:
             return 0
         ncores = os.cpu_count()
-        lm_cpu = min(args.lm_iters, 3)          # bounded sample: ~1-2 s of CPU work per step
-        val, ms, n_it = cpu_reference_run(prob, args.steps, min(warmup, 1), lm_cpu)
-        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(warmup, 1),
+        # the same step as the GPU arm (--lm-iters outer iterations from the same initial estimate); one step is ~2 s of
+        # CPU work at cfg2, so the driver's K and W stay as they are
+        val, ms, n_it = cpu_reference_run(prob, args.steps, args.warmup, args.lm_iters)
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload, "n_pose": prob.n_pose, "n_points": prob.n_pt, "n_meas": prob.n_meas,
-                           "lm_iters_per_step": lm_cpu},
+                "config": bench_config(workload, prob, args.lm_iters, args.gpus),
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": ncores, "kind": "port",
-                                 "sample": "%d LM iterations per step of the same map, CPU restatement (oracle/ba_oracle.c, "
-                                           "-O3 -march=native, Schur solve), 1 thread like the reference's MapMaker thread; reference binary "
-                                           "unavailable (no ROS/TooN/g2o/SuiteSparse)" % lm_cpu},
+                                 "sample": "%d steps x %d LM iterations of the same map, CPU restatement (oracle/ba_oracle.c, "
+                                           "-O3 -march=native; points eliminated first = the order a fill-reducing sparse Cholesky of the "
+                                           "full system takes), 1 thread like the reference's MapMaker thread; reference binary "
+                                           "unavailable (no ROS/TooN/g2o/SuiteSparse)" % (args.steps, args.lm_iters)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -315,47 +469,82 @@ def main():
     sampler.window(t_e2e0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- per-kernel timing of one profiled step (CUDA events around every launch) ----------------
+    # ---- per-kernel timing of one profiled step (CUDA events around every launch, one LM candidate per round) ----
     h.set_profiling(True)
     h.reset_state()
     rc, st = h.compute(args.lm_iters)
     tm = h.timing()
     h.set_profiling(False)
     n_m, n_p, nc = prob.n_meas, prob.n_pt, 6 * h.n_pose_var
-    # algorithmic bytes of one linearise+Schur launch: measurement records (32 B), point records
-    # (32 B in, 72 B V/g_p out) and the reduced camera system written once
-    lin_bytes = 32.0 * n_m / world + (32.0 + 72.0) * n_p / world + 8.0 * (nc * nc + nc)
-    lin_ms = tm["ms_linearize"] / max(tm["n_linearize"], 1)
+    # (point, movable pose) slots: distinct movable keyframes (observers + source) a point's measurements touch
+    mov = ~prob.pose_fixed.astype(bool)
+    pairs = np.concatenate([np.stack([prob.meas_pt, prob.meas_chain[:, 0]], 1)[mov[prob.meas_chain[:, 0]]],
+                            np.stack([np.arange(n_p), prob.pt_chain[:, 0]], 1)[mov[prob.pt_chain[:, 0]]]])
+    n_slots = len(np.unique(pairs[:, 0].astype(np.int64) * prob.n_pose + pairs[:, 1]))
     peak, peak_src = measured_peaks()
-    achieved = lin_bytes / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else 0.0
+    # algorithmic bytes per launch (per-unit figures x the units one launch processes on this rank)
+    alg = {"linearize": ("k_linearize + k_pose_blocks", 32.0 * n_m / world + 104.0 * n_p / world + 8.0 * (nc * nc + nc)),
+           "schur": ("k_schur_vinv_multi + k_schur_pairs (one candidate)", (144.0 * n_slots + 96.0 * n_p) / world + 8.0 * (nc * nc + nc)),
+           "solve": ("k_chol_solve", 2 * 8.0 * (nc * nc + nc)),
+           "backsub": ("k_backsub_eval", (40.0 * n_m + 80.0 * n_p + 144.0 * n_slots) / world),
+           "select": ("k_select_cluster / k_select_grid", 8.0 * n_m)}
+    per_kernel = {}
+    for key, (name, nbytes) in alg.items():
+        n_l, ms = tm["n_" + key], tm["ms_" + key]
+        if n_l:
+            t = ms / n_l
+            per_kernel[key] = {"kernel": name, "launches_per_step": n_l, "ms_per_launch": t, "share_of_kernel_time": None,
+                               "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": nbytes / (t * 1e-3) / 1e9,
+                               "frac": nbytes / (t * 1e-3) / 1e9 / peak}
+    tot_k = sum(tm["ms_" + k] for k in ("select", "linearize", "schur", "solve", "backsub", "control", "other"))
+    for key in per_kernel:
+        per_kernel[key]["share_of_kernel_time"] = tm["ms_" + key] / tot_k
+    dom = max(per_kernel, key=lambda k: tm["ms_" + k])            # the dominant kernel by time
+    traffic, traffic_note = ncu_traffic(alg[dom][0].split()[0]) if args.config == "cfg2" else (None, "capture is of cfg2")
     iter_bytes = 80.0 * n_m + 232.0 * n_p + 16.0 * nc * nc          # SURVEY.md §8(d), whole LM iteration
-    # dram__bytes_read + dram__bytes_write of one launch of each of the two kernels, from the committed ncu --set full
-    # capture (cold cache: k_pose_blocks re-reads the 176-byte measurement records k_linearize has just written, which
-    # stay in L2 inside a real step)
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_full_v21_ba.txt")
-    if os.path.exists(prof) and args.config == "cfg2":
-        unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        per_kernel, cur = {}, None
-        for ln in open(prof):
-            f = ln.split()
-            if ln.startswith("Kernel Name"):
-                name = "k_linearize" if "k_linearize" in ln else "k_pose_blocks" if "k_pose_blocks" in ln else None
-                cur = name if name and name not in per_kernel else None
-                if cur:
-                    per_kernel[cur] = 0.0
-            elif cur and len(f) >= 3 and f[0].startswith("dram__bytes_"):
-                per_kernel[cur] += float(f[1]) * unit.get(f[2], 1)
-        if len(per_kernel) == 2:
-            traffic = sum(per_kernel.values())
-    roofline = {"bound": "hbm", "kernel": "k_linearize + k_pose_blocks (reprojection, Jacobians, normal-equation blocks)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": lin_bytes, "kernel_ms": lin_ms,
+    roofline = {"bound": "hbm", "kernel": per_kernel[dom]["kernel"] + " (dominant kernel by time: %.0f %% of the summed kernel time of a step)"
+                % (100 * per_kernel[dom]["share_of_kernel_time"]),
+                "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes_per_launch"], "kernel_ms": per_kernel[dom]["ms_per_launch"],
+                "note": "the working set (%.1f MB) is L2-resident and every kernel is bound by dependency latency / fp64 issue, not by HBM: "
+                        "fractions of the HBM roofline are small by construction (DESIGN.md §5)" % (iter_bytes / 1e6),
                 "whole_iteration": {"algorithmic_bytes": iter_bytes,
                                     "achieved_gbs": iter_bytes * iters / (tot_ms * 1e-3) / 1e9,
                                     "frac": iter_bytes * iters / (tot_ms * 1e-3) / 1e9 / peak},
+                "per_kernel": per_kernel,
                 "per_kernel_ms_per_step": {k: v for k, v in tm.items() if k.startswith("ms_")},
                 "per_kernel_launches_per_step": {k: v for k, v in tm.items() if k.startswith("n_")}}
+
+    def one_gpu_reference(problem, P, X, trials):
+        """rank 0: the same map on ONE GPU; the sharded result must agree with it (sum order differs: 1e-7 relative)."""
+        h1 = capi.BaHandle(device=local_rank)
+        h1.load(problem)
+        s1 = torch.cuda.ExternalStream(h1.stream(), device=torch.device("cuda", local_rank))
+        t1, i1 = [], 0
+        for k in range(2 + 3):
+            h1.reset_state()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s1)
+            rc1, st1 = h1.compute(args.lm_iters)
+            e1.record(s1)
+            e1.synchronize()
+            if k >= 2:
+                t1.append(e0.elapsed_time(e1)); i1 += rc1
+        P1, X1 = h1.poses(), h1.points()
+        h1.close()
+        relp = float(np.linalg.norm(P - P1) / np.linalg.norm(P1)); relx = float(np.linalg.norm(X - X1) / np.linalg.norm(X1))
+        ok = bool(relp < 1e-7 and relx < 1e-7 and trials == st1.total_trials)
+        return i1 / (float(np.sum(t1)) * 1e-3), {"rel_pose": relp, "rel_point": relx, "trials": [int(trials), int(st1.total_trials)], "ok": ok}
+
+    multi_parity = None
+    if world > 1:
+        h.reset_state()
+        rc, st = h.compute(args.lm_iters)
+        Pm, Xm = h.poses(), h.points()
+        if rank == 0:
+            _, multi_parity = one_gpu_reference(prob, Pm, Xm, st.total_trials)
+        dist.barrier()
 
     scale = None
     if world > 1 and args.scale_config != "none":
@@ -386,26 +575,30 @@ def main():
                 tms.append(e0.elapsed_time(e1)); its += rc
         tot = torch.tensor([float(np.sum(tms))], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        Pb, Xb = hb.poses(), hb.points()
         hb.close()
-        val1 = None
+        val1, big_parity = None, None
         if rank == 0:
-            h1 = capi.BaHandle(device=local_rank)
-            h1.load(big)
-            s1 = torch.cuda.ExternalStream(h1.stream(), device=torch.device("cuda", local_rank))
-            t1, i1 = [], 0
-            for s in range(2 + 3):
-                h1.reset_state()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(s1)
-                rc, st1 = h1.compute(args.lm_iters)
-                e1.record(s1)
-                e1.synchronize()
-                if s >= 2:
-                    t1.append(e0.elapsed_time(e1)); i1 += rc
-            val1 = i1 / (float(np.sum(t1)) * 1e-3)
-            h1.close()
+            val1, big_parity = one_gpu_reference(big, Pb, Xb, stb.total_trials)
         scale = {"workload": "%s: %d poses / %d points / %d measurements, points sharded x%d" % (args.scale_config, big.n_pose, big.n_pt, big.n_meas, world),
-                 "value_n_gpus": its / (float(tot.item()) * 1e-3), "value_1_gpu_same_run": val1, "unit": UNIT, "n_gpus": world}
+                 "value_n_gpus": its / (float(tot.item()) * 1e-3), "value_1_gpu_same_run": val1, "unit": UNIT, "n_gpus": world,
+                 "multi_gpu_parity": big_parity}
+    # ---- front end (configs[2]); sharded one camera per GPU when there are several ranks -------
+    frontend = None
+    if not args.no_frontend:
+        mine = [c for c in range(4) if c % world == rank]
+        part = bench_frontend(capi, synth, local_rank, cam_ids=mine, with_cpu=(rank == 0 and world == 1))
+        parts = [part]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+        if rank == 0:
+            frontend = frontend_report([p for p in parts if p["n_frames"]], world, peak)
+            if world > 1:
+                # the sharded rig must produce what one GPU produces for the same cameras
+                one = bench_frontend(capi, synth, local_rank, cam_ids=(0, 1, 2, 3), steps=2, warmup=1, with_cpu=False)
+                frontend["multi_gpu_parity"] = {"checksum_sharded": frontend["result_checksum_per_camera_set"], "checksum_one_gpu": one["checksum"],
+                                                "ok": bool(one["checksum"] == frontend["result_checksum_per_camera_set"])}
     if world > 1:
         h.close(); h2.close()
         dist.barrier()
@@ -414,28 +607,32 @@ def main():
         dist = None
     if rank != 0:
         return 0
-    frontend = None
+    stream_section = None
     if world == 1 and not args.no_frontend:
-        frontend = bench_frontend(capi, synth, local_rank)
+        stream_section = bench_stream(capi, synth, local_rank)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        val, ms, n_it = cpu_reference_run(prob, 2, 0, 3)
+        val, ms, n_it = cpu_reference_run(prob, 1, 0, args.lm_iters)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
-               "sample": "2 x 3 LM iterations of the same map on the host, CPU restatement (oracle/ba_oracle.c, -O3 -march=native, Schur solve), "
-                         "1 thread; reference binary unavailable"}
+               "sample": "1 step (%d LM iterations) of the same map on the host, CPU restatement (oracle/ba_oracle.c, -O3 -march=native; points "
+                         "eliminated first = the order a fill-reducing sparse Cholesky of the full system takes), 1 thread; reference binary unavailable"
+                         % args.lm_iters}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_pose": prob.n_pose, "n_points": prob.n_pt, "n_meas": prob.n_meas,
-                       "lm_iters_per_step": args.lm_iters, "l2": "256 MiB flush between steps; within a step the map stays L2-resident",
-                       "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"},
+            "config": bench_config(workload, prob, args.lm_iters, world),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": {"load": 1e3 * e2e_parts[0] / args.steps, "compute": 1e3 * e2e_parts[1] / args.steps,
                                     "read_back": 1e3 * e2e_parts[2] / args.steps}},
-            "roofline": roofline, "cpu_baseline": cpu, "frontend": frontend, "scale_big_map": scale, "wall_s": wall,
+            "roofline": roofline, "cpu_baseline": cpu, "multi_gpu_parity": multi_parity, "frontend": frontend, "tracker_mapmaker_stream": stream_section,
+            "scale_big_map": scale, "wall_s": wall,
             "lm": {"iterations_per_step": iters / args.steps, "trials_last_step": st.total_trials}}
     print(json.dumps(line))
+    bad = [p for p in (multi_parity, scale and scale.get("multi_gpu_parity"), frontend and frontend.get("multi_gpu_parity")) if p and not p["ok"]]
+    if bad:
+        sys.stderr.write("bench.py: a sharded result differs from the 1-GPU result: %r\n" % (bad,))
+        return 1
     return 0
 
 

@@ -69,6 +69,7 @@ void launch_schur_gather(const BaDev& d, cudaStream_t s);
 void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
+void launch_tri_pack(double* const* full, int count, double* packed, int n, int tail, bool unpack, cudaStream_t s);
 
 struct DevBuf {
   void* p = nullptr;
@@ -116,7 +117,7 @@ struct McpBa {
   // device buffers (pooled)
   DevBuf b_cams, b_pose_var, b_pt_info, b_pt_var, b_pt_order, b_pt_meas_off, b_pt_slot_off, b_slot_var, b_meas_xy, b_meas_info,
       b_meas_a, b_meas_b, b_pose[N_STATE], b_pt[N_STATE], b_chi2[N_STATE], b_V, b_gp, b_W, b_acc, b_dc, b_L, b_part, b_ctrl, b_flags,
-      b_pose0, b_pt0, b_tmp, b_Linv, b_Lll, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items, b_R;
+      b_pose0, b_pt0, b_tmp, b_Linv, b_Lll, b_cflags, b_dbg, b_sel, b_Y, b_slot_pt, b_inc, b_items, b_paircnt, b_mrec, b_pb_idx, b_pb_items, b_rs_ent, b_rs_grp, b_rs_items, b_R, b_pack;
   // speculative LM candidates 1..n_spec-1 (lambda after that many rejections), one extra stream each
   struct Cand {
     DevBuf b_acc, b_dc, b_L, b_Linv, b_Lll, b_cflags, b_part, b_Y;
@@ -134,6 +135,7 @@ struct McpBa {
   int chol_epoch = 0, chol_task_base = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
   BaCtrl* ctrl_host = nullptr;   // pinned
+  double* abort_word = nullptr;  // pinned [2]: this rank's abort flag for the next round, the all-reduced one of the last round
   int* flags_host = nullptr;     // pinned, n_meas
   size_t flags_cap = 0;
   BaPrep prep;                   // host marshalling output in pinned memory, pooled across loads
@@ -207,6 +209,8 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
   MCP_CUDA_CHECK(cudaMallocHost(&h->ctrl_host, sizeof(BaCtrl)));
   memset(h->ctrl_host, 0, sizeof(BaCtrl));
+  MCP_CUDA_CHECK(cudaMallocHost(&h->abort_word, 2 * sizeof(double)));
+  h->abort_word[0] = h->abort_word[1] = 0;
   memset(&h->d, 0, sizeof(h->d));
   memset(&h->timing, 0, sizeof(h->timing));
   *out = h;
@@ -220,7 +224,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = { &h->b_cams, &h->b_pose_var, &h->b_pt_info, &h->b_pt_var, &h->b_pt_order, &h->b_pt_meas_off, &h->b_pt_slot_off,
                     &h->b_slot_var, &h->b_meas_xy, &h->b_meas_info, &h->b_meas_a, &h->b_meas_b, &h->b_V, &h->b_gp, &h->b_W,
-                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_Lll, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items, &h->b_R };
+                    &h->b_acc, &h->b_dc, &h->b_L, &h->b_part, &h->b_ctrl, &h->b_flags, &h->b_pose0, &h->b_pt0, &h->b_tmp, &h->b_Linv, &h->b_Lll, &h->b_cflags, &h->b_dbg, &h->b_sel, &h->b_Y, &h->b_slot_pt, &h->b_inc, &h->b_items, &h->b_paircnt, &h->b_mrec, &h->b_pb_idx, &h->b_pb_items, &h->b_rs_ent, &h->b_rs_grp, &h->b_rs_items, &h->b_R, &h->b_pack };
   for (DevBuf* b : all) b->release();
   for (int k = 0; k < N_STATE; k++) { h->b_pose[k].release(); h->b_pt[k].release(); h->b_chi2[k].release(); }
   for (int q = 1; q < MAX_CAND; q++) {
@@ -233,6 +237,7 @@ int mcp_ba_destroy(McpBa* h)
     if (cq.ev_schur) cudaEventDestroy(cq.ev_schur);
   }
   if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+  if (h->abort_word) cudaFreeHost(h->abort_word);
   if (h->flags_host) cudaFreeHost(h->flags_host);
   h->prep.free_all(g_pinned_alloc);
   if (h->comm) ncclCommDestroy(h->comm);
@@ -376,6 +381,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 16; h->off_rm = h->off_Sm + ncp * ncp;
   h->acc_doubles = h->off_rm + ncp;
   if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
+  if (h->world > 1 && (rc = h->b_pack.ensure(sizeof(double) * MAX_CAND * (ncp * (ncp + 1) / 2 + ncp + 16)))) return rc;
   if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
   if ((rc = h->b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
   if ((rc = h->b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
@@ -568,7 +574,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   double* red = acc + h->off_red;
   const bool multi = h->world > 1;
   int rc;
-  auto aborted = [&]() { return abort_flag && *abort_flag; };
+  // Single GPU: the caller's flag is polled between trial rounds like the reference polls it between iterations.
+  // Several ranks: every rank must take the same branch (each round issues collectives), so the flag is only ever acted
+  // on through a value all ranks agreed on -- it rides on the per-round all-reduce of the trial sums (and on one
+  // all-reduce before the first round).
+  bool agreed_abort = false;
+  auto local_flag = [&]() { return abort_flag && *abort_flag; };
+  auto aborted = [&]() { return multi ? agreed_abort : local_flag(); };
 
   { const char* e = getenv("MCP_BA_TIMELINE"); h->timeline = e && e[0] == '1'; }
   if ((rc = sync_ctrl(h))) return rc;
@@ -602,6 +614,16 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));
   if (st) st->chi2_before = chi_before;
 
+  if (multi) {
+    // red[15] is free between rounds
+    const double mine = local_flag() ? 1.0 : 0.0;
+    double all = 0;
+    MCP_CUDA_CHECK(cudaMemcpyAsync(red + 15, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+    NCCL_CHECK(ncclAllReduce(red + 15, red + 15, 1, ncclDouble, ncclSum, h->comm, s));
+    MCP_CUDA_CHECK(cudaMemcpyAsync(&all, red + 15, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+    agreed_abort = all > 0;
+  }
   MCP_CUDA_CHECK(cudaEventRecord(h->ev0, s));
   int counter = 0;
   bool ok = true, local_abort = false;
@@ -616,8 +638,8 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   for (int it = 0; it < n_iter && !local_abort && !aborted() && ok; it++) {
     if (!next_iteration_started) {
       if (it > 0) {
-        if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
-        if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
+        { TlScope t(h, "ag_chi2", 0, s); if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc; }
+        if (h->cfg.use_robust) { Prof p(h, C_SELECT); TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
       }
       MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
       { Prof p(h, C_LIN); TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); h->launches++; }
@@ -625,7 +647,18 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     next_iteration_started = false;
     if (multi) {
       launch_reduce_partials(d, n_lin, 0, red, s); h->launches++;
-      NCCL_CHECK(ncclAllReduce(acc, acc, h->off_Sm, ncclDouble, ncclSum, h->comm, s));
+      {
+        // [H0 | gc | scalar sums] travel as the packed upper triangle + tail (k_tri_pack)
+        TlScope t(h, "ar_H0", 0, s);
+        const int tail = (int)(h->off_Sm - h->off_gc);
+        const size_t cnt = (size_t)d.nc * (d.nc + 1) / 2 + tail;
+        double* pk = h->b_pack.as<double>();
+        double* src[1] = { acc };
+        launch_tri_pack(src, 1, pk, d.nc, tail, false, s);
+        NCCL_CHECK(ncclAllReduce(pk, pk, cnt, ncclDouble, ncclSum, h->comm, s));
+        launch_tri_pack(src, 1, pk, d.nc, tail, true, s);
+        h->launches += 2;
+      }
     }
     if (c.need_lambda_init) {
       { Prof p(h, C_OTHER); launch_lambda_init(d, s); }
@@ -670,10 +703,18 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
           MCP_CUDA_CHECK(cudaStreamWaitEvent(s, cq.ev_schur, 0));
           h->launches += 2;
         }
-        NCCL_CHECK(ncclGroupStart());
-        NCCL_CHECK(ncclAllReduce(d.Sm, d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
-        for (int q = 1; q < n_cand; q++) NCCL_CHECK(ncclAllReduce(h->cand[q].d.Sm, h->cand[q].d.Sm, sm_doubles, ncclDouble, ncclSum, h->comm, s));
-        NCCL_CHECK(ncclGroupEnd());
+        {
+          // every candidate's [Sm | rm] as packed triangle + tail, ONE all-reduce for all of them
+          TlScope t(h, "ar_Sm", 0, s);
+          const size_t cnt = (size_t)d.nc * (d.nc + 1) / 2 + d.nc;
+          double* pk = h->b_pack.as<double>();
+          double* src[MAX_CAND];
+          for (int q = 0; q < n_cand; q++) src[q] = q ? h->cand[q].d.Sm : d.Sm;
+          launch_tri_pack(src, n_cand, pk, d.nc, d.nc, false, s);
+          NCCL_CHECK(ncclAllReduce(pk, pk, cnt * n_cand, ncclDouble, ncclSum, h->comm, s));
+          launch_tri_pack(src, n_cand, pk, d.nc, d.nc, true, s);
+          h->launches += 2;
+        }
         if (n_cand > 1) MCP_CUDA_CHECK(cudaEventRecord(h->ev_red, s));
       }
       { Prof p(h, C_SOLVE); TlScope t(h, "solve", 0, s); launch_chol_solve(d, ++h->chol_epoch, h->n_sms / n_cand, &h->chol_task_base, s); }
@@ -700,7 +741,14 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       }
       if (multi) { launch_reduce_partials(d, 0, n_bs, red, s); h->launches++; }
       for (int q = 1; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->cand[q].ev_done, 0));
-      if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand, ncclDouble, ncclSum, h->comm, s));
+      if (multi) {
+        // the trial sums of every candidate + this rank's view of the abort flag (slot 1 + 3 n_cand)
+        TlScope t(h, "ar_red", 0, s);
+        h->abort_word[0] = local_flag() ? 1.0 : 0.0;
+        MCP_CUDA_CHECK(cudaMemcpyAsync(red + 1 + 3 * n_cand, h->abort_word, sizeof(double), cudaMemcpyHostToDevice, s));
+        NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand + 1, ncclDouble, ncclSum, h->comm, s));
+        MCP_CUDA_CHECK(cudaMemcpyAsync(h->abort_word + 1, red + 1 + 3 * n_cand, sizeof(double), cudaMemcpyDeviceToHost, s));
+      }
       { Prof p(h, C_CONTROL); TlScope t(h, "control", 0, s); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
       const bool ahead = can_look_ahead && it + 1 < n_iter;
@@ -716,6 +764,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         h->launches += 2;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
       } else if ((rc = sync_ctrl(h))) return rc;
+      if (multi) agreed_abort = agreed_abort || h->abort_word[1] > 0;
       if (c.cand_used > 1) h->spec_used++;
       if (single_step) break;
       if (c.stop_trials) { next_iteration_started = ahead && !c.terminate && !c.conv_mag && !c.conv_res; break; }

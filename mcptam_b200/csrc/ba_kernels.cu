@@ -828,6 +828,113 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_select_grid: the same exact radix select for SELC_CAP < n <= SELG_CAP values in ONE cooperative launch: one CTA per
+// SM, every thread keeps its <= 16 keys in registers for all six digits; per digit the CTAs add their shared-memory
+// histogram into the global one, meet at a grid barrier, and every CTA narrows (prefix, rank) redundantly.  Replaces six
+// dependent launches of k_sel_pass (the 1000 KF map: 86 -> ~35 us).
+// ---------------------------------------------------------------------------------------------
+constexpr int SELG_THREADS = 1024, SELG_K = 16;
+__global__ void __launch_bounds__(SELG_THREADS, 1) k_select_grid(BaDev d, int which_in, int mode, double* zero_ptr, size_t zero_n)
+{
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  if (lookahead_skip(d)) return;                                  // uniform over the grid
+  for (size_t i = (size_t)blockIdx.x * SELG_THREADS + threadIdx.x; i < zero_n; i += (size_t)gridDim.x * SELG_THREADS) zero_ptr[i] = 0.0;
+  __shared__ unsigned hist[SEL_BINS];
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank, s_count;
+  __shared__ int s_prefix_shift;
+  BaCtrl* ctrl = d.ctrl;
+  const int which = which_in < 0 ? ctrl->cur : which_in;
+  const double* __restrict__ v = d.chi2[which];
+  const int n = d.n_meas;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gtid = blockIdx.x * SELG_THREADS + tid, gsz = gridDim.x * SELG_THREADS;
+  unsigned long long key[SELG_K];
+#pragma unroll
+  for (int k = 0; k < SELG_K; k++) {
+    const int i = gtid + k * gsz;
+    key[k] = (i < n) ? (unsigned long long)__double_as_longlong(fabs(v[i])) : ~0ull;
+  }
+  unsigned long long prefix = 0;
+  unsigned rank = (unsigned)(n / 2);
+  bool done = false;
+  for (int pass = 0; pass < SEL_PASSES && !done; pass++) {
+    unsigned* gh = d.sel_hist + pass * SEL_BINS;
+    const int shift = 63 - SEL_BITS * (pass + 1);
+    for (int i = tid; i < SEL_BINS; i += SELG_THREADS) hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SELG_K; k++) {
+      const unsigned long long hi = (shift >= 0) ? (key[k] >> (shift + SEL_BITS)) : (key[k] >> (SEL_BITS + shift));
+      const bool match = (key[k] != ~0ull) && (pass == 0 || hi == prefix);
+      const unsigned dig = (shift >= 0) ? ((unsigned)(key[k] >> shift) & (SEL_BINS - 1)) : ((unsigned)(key[k] << (-shift)) & (SEL_BINS - 1));
+      const unsigned act = __ballot_sync(0xffffffffu, match);
+      if (match) {
+        const unsigned peers = __match_any_sync(act, dig);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[dig], (unsigned)__popc(peers));
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < SEL_BINS; i += SELG_THREADS) if (hist[i]) atomicAdd(&gh[i], hist[i]);
+    grid.sync();
+    // global counts of bins 2*tid, 2*tid+1
+    const uint2 cc = __ldcg(reinterpret_cast<const uint2*>(gh) + tid);
+    const unsigned c0 = cc.x, c1 = cc.y, tsum = c0 + c1;
+    unsigned incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned wv = wsum[lane], winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    const unsigned woff = __shfl_sync(0xffffffffu, winc - wv, wid);
+    const unsigned excl = woff + incl - tsum;
+    if (rank >= excl && rank < excl + tsum) {
+      const bool first = rank < excl + c0;
+      const unsigned bin = first ? 2 * tid : 2 * tid + 1;
+      const unsigned acc = first ? excl : excl + c0;
+      s_prefix = (shift >= 0) ? ((prefix << SEL_BITS) | bin) : ((prefix << (SEL_BITS + shift)) | (bin >> (-shift)));
+      s_rank = rank - acc;
+      s_count = first ? c0 : c1;
+      s_prefix_shift = shift;
+    }
+    __syncthreads();
+    prefix = s_prefix; rank = s_rank;
+    done = (s_count == 1u) && (pass + 1 < SEL_PASSES);
+  }
+  unsigned long long med_bits = prefix;
+  bool owner = (blockIdx.x == 0 && tid == 0);
+  if (done) {
+    owner = false;
+#pragma unroll
+    for (int k = 0; k < SELG_K; k++)
+      if (key[k] != ~0ull && (key[k] >> s_prefix_shift) == prefix) { owner = true; med_bits = key[k]; }
+  }
+  grid.sync();                                          // every CTA has read the last histogram: re-arm them for the next call
+  for (int i = gtid; i < SEL_PASSES * SEL_BINS; i += gsz) d.sel_hist[i] = 0;
+  if (owner) {
+    const double med = __longlong_as_double((long long)med_bits);
+    const size_t denom = (size_t)n * 2 - 6;
+    double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
+    if (mode == 2) ctrl->median_out = med;
+    else if (mode == 0) {
+      s = 1.345 * s;
+      ctrl->sigma_sq_raw = s * s;
+      ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
+      ctrl->sigma_lim = sqrt(ctrl->sigma_sq_lim);
+    } else {
+      s = 4.6851 * s;
+      double t = s * s;
+      if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq;
+      ctrl->tukey_sigma_sq = t;
+    }
+  }
+}
+
 // Tukey outlier flags (src/ChainBundle.cc:1385-1398)
 __global__ void k_tukey_flags(BaDev d)
 {
@@ -979,6 +1086,39 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
   }
 }
 
+// Multi-GPU exchange buffers: the reduced camera system is symmetric and only its upper block triangle is ever written
+// (element (r, c), c <= r, lives at [c * n + r]), so the all-reduce carries the packed triangle plus the vector that
+// follows the matrix in memory (gc + the scalar sums, or rm) -- half the bytes of the square.
+//   packed[c * n - c (c - 1) / 2 + (r - c)] = full[c * n + r],   tail: packed[n (n + 1) / 2 + i] = full[n * n + i]
+struct TriPackArgs { double* full[MAX_CAND]; };
+__global__ void __launch_bounds__(256) k_tri_pack(TriPackArgs a, double* __restrict__ packed_all, int n, int tail, int unpack)
+{
+  const int c = blockIdx.y;
+  const size_t ntri = (size_t)n * (n + 1) / 2;
+  double* full = a.full[blockIdx.z];
+  double* packed = packed_all + (ntri + tail) * blockIdx.z;
+  if (c < n) {
+    const size_t po = (size_t)c * n - (size_t)c * (c - 1) / 2;
+    for (int r = c + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+      if (unpack) full[(size_t)c * n + r] = packed[po + (r - c)];
+      else packed[po + (r - c)] = full[(size_t)c * n + r];
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tail; i += gridDim.x * blockDim.x) {
+      if (unpack) full[(size_t)n * n + i] = packed[ntri + i];
+      else packed[ntri + i] = full[(size_t)n * n + i];
+    }
+  }
+}
+// `count` matrices [full | tail] <-> consecutive packed records of n (n + 1) / 2 + tail doubles, one launch
+void launch_tri_pack(double* const* full, int count, double* packed, int n, int tail, bool unpack, cudaStream_t s)
+{
+  if (n <= 0 || count <= 0) return;
+  TriPackArgs a;
+  for (int q = 0; q < MAX_CAND; q++) a.full[q] = full[q < count ? q : 0];
+  k_tri_pack<<<dim3((n + 255) / 256, n + 1, count), 256, 0, s>>>(a, packed, n, tail, unpack ? 1 : 0);
+}
+
 // sums the per-block partials into out[0..3] = {cur_chi, tmp_chi, scale, sumsq} (multi-GPU path)
 __global__ void __launch_bounds__(256) k_reduce_partials(BaDev d, int n_part_lin, int n_part_bs, double* out)
 {
@@ -1107,6 +1247,16 @@ int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, dou
 {
   static const bool multi_launch = [] { const char* e = getenv("MCP_BA_SELECT_MULTI"); return e && e[0] == '1'; }();
   if (d.n_meas > 0 && d.n_meas <= SELC_CAP && !multi_launch) { launch_chain(k_select_cluster, dim3(SELC_CTAS), dim3(SELC_THREADS), SELC_SMEM, s, d, which, mode, zero_ptr, zero_n); return 1; }
+  {
+    // one cooperative launch, one CTA per SM, keys in registers
+    static const int n_sms = [] { int dev = 0, v = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 1; }();
+    if (!multi_launch && (long long)d.n_meas <= (long long)n_sms * SELG_THREADS * SELG_K) {
+      BaDev dd = d;
+      void* args[] = { &dd, &which, &mode, &zero_ptr, &zero_n };
+      if (cudaLaunchCooperativeKernel((void*)k_select_grid, dim3(n_sms), dim3(SELG_THREADS), args, 0, s) == cudaSuccess) return 1;
+      (void)cudaGetLastError();                      // fall back to the multi-launch path
+    }
+  }
   if (zero_n) launch_zero_acc(d, zero_ptr, zero_n, s);
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
