@@ -201,7 +201,7 @@ Vector<3> TaylorCamera::UnProject(const Vector<2>& im)
   if (mdLastRho == 0) { mdLastCosPhi = 0; mdLastSinPhi = 0; }
   else { mdLastCosPhi = mv3LastCam[0] / mdLastRho; mdLastSinPhi = mv3LastCam[1] / mdLastRho; }
   const double n = std::sqrt(mv3LastCam * mv3LastCam);
-  mv3LastCam = mv3LastCam * (1.0 / n);
+  for (int k = 0; k < 3; k++) mv3LastCam[k] /= n;          // TooN::normalize: v /= sqrt(v * v), element-wise division
   return mv3LastCam;
 }
 

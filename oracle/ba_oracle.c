@@ -1,6 +1,6 @@
 /*
  * ba_oracle.c — CPU restatement of the ChainBundle Levenberg–Marquardt bundle adjuster.
- * TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: no reference golden vectors exist.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Pinned against src/ChainBundle.cc / TaylorCamera.cc / MEstimator.h compiled from the reference (tests/test_oracle_vs_ref.py); g2o / CHOLMOD restated [3P].
  *
  * Follows (file:line in /root/reference):
  *   src/ChainBundle.cc:82-86      VertexPoseSE3::oplusImpl          -> pose_oplus
@@ -232,10 +232,15 @@ int ora_cam_project(const OraTaylorCam* cam, const double* p3, double* px2, doub
 /* src/TaylorCamera.cc:319-346 */
 void ora_cam_unproject(const OraTaylorCam* cam, const double* px, double* ray)
 {
+  /* mm2AffineInv = opts::M2Inverse(mm2Affine) (SmallMatrixOpts.h:66-77: entries times 1/det), then
+     mv2LastDistCam = mm2AffineInv * (v2ImFrame - mv2Center)  (src/TaylorCamera.cc:322) -- same operation order, so that
+     the result is bit-identical to the reference's (tests/test_oracle_vs_ref.py) */
   const double det = cam->affine[0] * cam->affine[3] - cam->affine[1] * cam->affine[2];
+  const double idet = 1.0 / det;
+  const double i00 = cam->affine[3] * idet, i01 = -cam->affine[1] * idet, i10 = -cam->affine[2] * idet, i11 = cam->affine[0] * idet;
   const double dx = px[0] - cam->center[0], dy = px[1] - cam->center[1];
-  const double u = (cam->affine[3] * dx - cam->affine[1] * dy) / det;
-  const double v = (-cam->affine[2] * dx + cam->affine[0] * dy) / det;
+  const double u = i00 * dx + i01 * dy;
+  const double v = i10 * dx + i11 * dy;
   const double rho = sqrt(u * u + v * v);
   ray[0] = u; ray[1] = v; ray[2] = polyval(cam->poly, 5, rho);
   const double n = sqrt(ray[0] * ray[0] + ray[1] * ray[1] + ray[2] * ray[2]);

@@ -1,6 +1,6 @@
 /*
  * fe_oracle.c — CPU restatement of the per-frame front end.  TEST INFRASTRUCTURE ONLY (see oracle.h).
- * PARITY UNPINNED: the reference has no golden vectors; libCVD is not available here.
+ * Pinned against src/PatchFinder.cc / MiniPatch.cc / ShiTomasi.cc compiled from the reference (tests/test_oracle_vs_ref.py); libCVD (halfSample, FAST, transform) restated [3P] and pinned against OpenCV.
  *
  * Follows (file:line in /root/reference):
  *   src/KeyFrame.cc:189-190     CVD::halfSample                       [3P libCVD]  -> ora_halfsample

@@ -1,7 +1,7 @@
 """ctypes loader for the CPU oracle (oracle/_build/liboracle.so).
 
 TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs may import this module.  PARITY UNPINNED (see oracle.h).
+--impl reference legs may import this module.  Pinned against the reference's own code where it exists (oracle/_ref, tests/test_oracle_vs_ref.py); third-party behaviour restated (see oracle.h).
 """
 from __future__ import annotations
 

@@ -1,7 +1,7 @@
 """GPU parity tests of the bundle adjuster: CUDA path (through the C ABI) vs the CPU oracle.
 
 The comparator is a RESTATEMENT of the reference (oracle/ba_oracle.c), not the reference binary
-(parity unpinned, see oracle/oracle.h).  Tolerances: residuals/Jacobians 1e-10 relative (same fp64
+(itself pinned against the reference's own src/ChainBundle.cc in tests/test_oracle_vs_ref.py; g2o's LM loop [3P]).  Tolerances: residuals/Jacobians 1e-10 relative (same fp64
 formulae, different rounding order), LM step and iterates 1e-6 relative (BASELINE.json north_star).
 """
 import numpy as np

@@ -2,7 +2,7 @@
 
 Integer / byte / index work is compared bit-exactly; the mixed fp32/fp64 sub-pixel refinement is compared
 bit-exactly too (the kernel forbids FMA contraction on that path, the oracle is built with -ffp-contract=off).
-The comparator is a RESTATEMENT of the reference (parity unpinned, see oracle/oracle.h).
+The comparator is a RESTATEMENT of the reference (pinned against the reference's own PatchFinder / MiniPatch / ShiTomasi in tests/test_oracle_vs_ref.py; libCVD [3P]).
 """
 import numpy as np
 import pytest

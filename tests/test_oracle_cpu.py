@@ -1,5 +1,5 @@
 """CPU tests (no GPU): the oracle against its own invariants, an independent library (OpenCV FAST 9-16) and
-the committed golden fixtures.  The reference has no tests or golden vectors (parity unpinned)."""
+the committed golden fixtures.  The reference has no tests or golden vectors; its own code is the pin in tests/test_oracle_vs_ref.py."""
 import os
 
 import numpy as np
