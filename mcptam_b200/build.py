@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libmcptam_b200.so")
 PREP_LIB = os.path.join(OUT_DIR, "libmcptam_prep.so")      # CPU-only shim around ba_prep.hpp for the host-logic tests
-SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_schur.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
+SOURCES = ["ba_kernels.cu", "ba_solve.cu", "ba_schur.cu", "ba_p2p.cu", "ba_api.cu", "fe_kernels.cu", "fe_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"] + (["-DMCP_FE_DEBUG"] if os.environ.get("MCP_FE_DEBUG") else [])
 

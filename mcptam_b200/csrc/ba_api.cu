@@ -57,7 +57,7 @@ size_t chol_ll_bytes(int nc);
 size_t chol_flag_ints(int nc);
 int chol_max_n();
 void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s);
-void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s);
+void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s, const double* host_word = nullptr, int word_slot = 0);
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s);
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s);
 int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* smem_out);
@@ -70,6 +70,11 @@ void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
 void launch_tri_pack(double* const* full, int count, double* packed, int n, int tail, bool unpack, cudaStream_t s);
+struct P2pPeers { uint4* base[8]; };
+static inline size_t p2p_slice(size_t cnt, int world) { return (cnt + world - 1) / world; }   // as in ba_p2p.cu
+void launch_p2p_allreduce(double* buf, size_t cnt, const P2pPeers& peers, size_t box_off, int rank, int world, unsigned tag, cudaStream_t s);
+void launch_p2p_allgather(const BaDev& d, double* arr_or_null, int stride, const int* bounds, const P2pPeers& peers, size_t box_off, int rank, int world,
+                          unsigned tag, cudaStream_t s);
 
 struct DevBuf {
   void* p = nullptr;
@@ -146,6 +151,14 @@ struct McpBa {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   std::vector<int> part_pt, part_meas;   // world+1 boundaries
+  // peer-memory exchanges (ba_p2p.cu): this rank's exchange buffer, the peers' buffers as mapped through CUDA IPC, one region
+  // (two parities) per kind of exchange, call counters
+  enum { X_H0 = 0, X_SM, X_RED, X_CHI, X_N };
+  bool p2p = false;
+  uint4* xbuf = nullptr;
+  size_t xbuf_lines = 0, x_off[X_N] = { 0, 0, 0, 0 }, x_lines[X_N] = { 0, 0, 0, 0 };
+  unsigned x_calls[X_N] = { 0, 0, 0, 0 }, x_tag = 0;
+  P2pPeers peers;
   // MCP_BA_TIMELINE=1: start/stop events around the launches of every stream (does not serialise the streams);
   // dumped to stderr at the end of mcp_ba_compute as 'TL name stream start_us stop_us'
   struct Tl { const char* name; int sid; cudaEvent_t a, b; };
@@ -161,6 +174,9 @@ struct McpBa {
 };
 
 extern "C" {
+
+static int p2p_setup(McpBa* h, size_t n_meas, size_t ncp);
+static void p2p_release(McpBa* h);
 
 const char* mcp_last_error(void) { return g_err; }
 int mcp_abi_version(void) { return 1; }
@@ -240,6 +256,7 @@ int mcp_ba_destroy(McpBa* h)
   if (h->abort_word) cudaFreeHost(h->abort_word);
   if (h->flags_host) cudaFreeHost(h->flags_host);
   h->prep.free_all(g_pinned_alloc);
+  p2p_release(h);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -382,6 +399,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   h->acc_doubles = h->off_rm + ncp;
   if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
   if (h->world > 1 && (rc = h->b_pack.ensure(sizeof(double) * MAX_CAND * (ncp * (ncp + 1) / 2 + ncp + 16)))) return rc;
+  if (h->world > 1 && (rc = p2p_setup(h, (size_t)n_meas, ncp))) return rc;
   if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
   if ((rc = h->b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
   if ((rc = h->b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
@@ -506,6 +524,91 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     if (_r != ncclSuccess) { set_last_error("%s failed: %s", #expr, ncclGetErrorString(_r)); return MCP_ERR_NCCL; } \
   } while (0)
 
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange buffers (ba_p2p.cu)
+// ------------------------------------------------------------------------------------------
+static void p2p_release(McpBa* h)
+{
+  if (!h->xbuf) return;
+  cudaStreamSynchronize(h->stream);
+  for (int p = 0; p < h->world && p < 8; p++)
+    if (p != h->rank && h->peers.base[p]) cudaIpcCloseMemHandle(h->peers.base[p]);
+  cudaFree(h->xbuf);
+  h->xbuf = nullptr; h->xbuf_lines = 0; h->p2p = false;
+  memset(&h->peers, 0, sizeof(h->peers));
+}
+
+// (Re)allocates the exchange buffer when the problem outgrew it and maps every peer's buffer into this process.  Collective:
+// every rank takes the same decisions (same problem sizes), the IPC handles travel through one NCCL all-gather, and a rank
+// that cannot map a peer makes ALL ranks fall back to the NCCL path.  MCP_BA_P2P=0 disables.
+static int p2p_setup(McpBa* h, size_t n_meas, size_t ncp)
+{
+  static const bool off = [] { const char* e = getenv("MCP_BA_P2P"); return e && e[0] == '0'; }();
+  if (off || h->world > 8) { h->p2p = false; return MCP_OK; }
+  const int W = h->world;
+  const size_t ntri = ncp * (ncp + 1) / 2;
+  const size_t cnt[McpBa::X_N] = { ntri + ncp + 16, (size_t)MAX_CAND * (ntri + ncp), 16, n_meas };
+  size_t lines[McpBa::X_N], total = 0;
+  for (int k = 0; k < McpBa::X_N; k++) {
+    lines[k] = (k == McpBa::X_CHI) ? cnt[k] : 2 * (size_t)W * p2p_slice(cnt[k], W);
+    lines[k] = (lines[k] + 63) & ~(size_t)63;
+    total += 2 * lines[k];
+  }
+  bool same = h->xbuf && total <= h->xbuf_lines;
+  for (int k = 0; k < McpBa::X_N && same; k++) same = (lines[k] == h->x_lines[k]);
+  if (same) return MCP_OK;                                   // pooled across loads of the same shape
+  p2p_release(h);
+  MCP_CUDA_CHECK(cudaMalloc(&h->xbuf, total * sizeof(uint4)));
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->xbuf, 0, total * sizeof(uint4), h->stream));
+  h->xbuf_lines = total;
+  size_t o = 0;
+  for (int k = 0; k < McpBa::X_N; k++) { h->x_off[k] = o; h->x_lines[k] = lines[k]; o += 2 * lines[k]; h->x_calls[k] = 0; }
+  // exchange the IPC handles
+  cudaIpcMemHandle_t mine;
+  int fail = cudaIpcGetMemHandle(&mine, h->xbuf) == cudaSuccess ? 0 : 1;
+  if (fail) (void)cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  unsigned char* stage = nullptr;
+  MCP_CUDA_CHECK(cudaMalloc(&stage, 64 * (size_t)W + 16));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(stage + 64 * (size_t)h->rank, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+  NCCL_CHECK(ncclAllGather(stage + 64 * (size_t)h->rank, stage, 64, ncclChar, h->comm, h->stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(all.data(), stage, 64 * (size_t)W, cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  memset(&h->peers, 0, sizeof(h->peers));
+  for (int p = 0; p < W && !fail; p++) {
+    if (p == h->rank) { h->peers.base[p] = h->xbuf; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); fail = 1; break; }
+    h->peers.base[p] = reinterpret_cast<uint4*>(ptr);
+  }
+  // every rank must agree on the path
+  int* flag = reinterpret_cast<int*>(stage + 64 * (size_t)W);
+  MCP_CUDA_CHECK(cudaMemcpyAsync(flag, &fail, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  NCCL_CHECK(ncclAllReduce(flag, flag, 1, ncclInt, ncclMax, h->comm, h->stream));
+  int any = 0;
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&any, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  cudaFree(stage);
+  if (any) {
+    static bool told = false;
+    if (!told) { fprintf(stderr, "mcptam_b200: peer memory could not be mapped on every rank; the exchanges use NCCL\n"); told = true; }
+    p2p_release(h);
+    return MCP_OK;
+  }
+  h->p2p = true;
+  return MCP_OK;
+}
+
+// one exchange = one region, alternating parity, a tag that never repeats
+static inline size_t p2p_next(McpBa* h, int region, unsigned* tag)
+{
+  const unsigned par = h->x_calls[region]++ & 1u;
+  *tag = ++h->x_tag;
+  return h->x_off[region] + (size_t)par * h->x_lines[region];
+}
+
 namespace {
 
 struct Prof {
@@ -547,6 +650,13 @@ int push_ctrl(McpBa* h)
 int allgather_ranges(McpBa* h, double* base, const std::vector<int>& bounds, int stride)
 {
   if (h->world == 1) return MCP_OK;
+  if (h->p2p && stride == 1 && (size_t)bounds[h->world] <= h->x_lines[McpBa::X_CHI]) {
+    // chi2 shards: one peer-memory kernel per rank
+    unsigned tag;
+    const size_t off = p2p_next(h, McpBa::X_CHI, &tag);
+    launch_p2p_allgather(h->d, base, 1, bounds.data(), h->peers, off, h->rank, h->world, tag, h->stream);
+    return MCP_OK;
+  }
   NCCL_CHECK(ncclGroupStart());
   for (int r = 0; r < h->world; r++) {
     const size_t off = (size_t)bounds[r] * stride, cnt = (size_t)(bounds[r + 1] - bounds[r]) * stride;
@@ -585,7 +695,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   { const char* e = getenv("MCP_BA_TIMELINE"); h->timeline = e && e[0] == '1'; }
   if ((rc = sync_ctrl(h))) return rc;
   c.need_lambda_init = 1; c.user_lambda = user_lambda; c.iter = 0; c.conv_mag = 0; c.conv_res = 0; c.total_trials = 0;
-  c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0;
+  c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0; c.abort_agreed = 0;
   if ((rc = push_ctrl(h))) return rc;
   h->outliers.clear();
 
@@ -655,7 +765,8 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         double* pk = h->b_pack.as<double>();
         double* src[1] = { acc };
         launch_tri_pack(src, 1, pk, d.nc, tail, false, s);
-        NCCL_CHECK(ncclAllReduce(pk, pk, cnt, ncclDouble, ncclSum, h->comm, s));
+        if (h->p2p) { unsigned tag; const size_t off = p2p_next(h, McpBa::X_H0, &tag); launch_p2p_allreduce(pk, cnt, h->peers, off, h->rank, h->world, tag, s); }
+        else NCCL_CHECK(ncclAllReduce(pk, pk, cnt, ncclDouble, ncclSum, h->comm, s));
         launch_tri_pack(src, 1, pk, d.nc, tail, true, s);
         h->launches += 2;
       }
@@ -711,7 +822,8 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
           double* src[MAX_CAND];
           for (int q = 0; q < n_cand; q++) src[q] = q ? h->cand[q].d.Sm : d.Sm;
           launch_tri_pack(src, n_cand, pk, d.nc, d.nc, false, s);
-          NCCL_CHECK(ncclAllReduce(pk, pk, cnt * n_cand, ncclDouble, ncclSum, h->comm, s));
+          if (h->p2p) { unsigned tag; const size_t off = p2p_next(h, McpBa::X_SM, &tag); launch_p2p_allreduce(pk, cnt * n_cand, h->peers, off, h->rank, h->world, tag, s); }
+          else NCCL_CHECK(ncclAllReduce(pk, pk, cnt * n_cand, ncclDouble, ncclSum, h->comm, s));
           launch_tri_pack(src, n_cand, pk, d.nc, d.nc, true, s);
           h->launches += 2;
         }
@@ -739,15 +851,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         MCP_CUDA_CHECK(cudaEventRecord(cq.ev_done, cq.stream));
         h->spec_rounds++;
       }
-      if (multi) { launch_reduce_partials(d, 0, n_bs, red, s); h->launches++; }
+      if (multi) { h->abort_word[0] = local_flag() ? 1.0 : 0.0; launch_reduce_partials(d, 0, n_bs, red, s, h->abort_word, 1 + 3 * n_cand); h->launches++; }
       for (int q = 1; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->cand[q].ev_done, 0));
       if (multi) {
         // the trial sums of every candidate + this rank's view of the abort flag (slot 1 + 3 n_cand)
         TlScope t(h, "ar_red", 0, s);
-        h->abort_word[0] = local_flag() ? 1.0 : 0.0;
-        MCP_CUDA_CHECK(cudaMemcpyAsync(red + 1 + 3 * n_cand, h->abort_word, sizeof(double), cudaMemcpyHostToDevice, s));
-        NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand + 1, ncclDouble, ncclSum, h->comm, s));
-        MCP_CUDA_CHECK(cudaMemcpyAsync(h->abort_word + 1, red + 1 + 3 * n_cand, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (h->p2p) { unsigned tag; const size_t off = p2p_next(h, McpBa::X_RED, &tag); launch_p2p_allreduce(red + 1, (size_t)(3 * n_cand + 1), h->peers, off, h->rank, h->world, tag, s); }
+        else NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 3 * n_cand + 1, ncclDouble, ncclSum, h->comm, s));
       }
       { Prof p(h, C_CONTROL); TlScope t(h, "control", 0, s); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
@@ -764,7 +874,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         h->launches += 2;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
       } else if ((rc = sync_ctrl(h))) return rc;
-      if (multi) agreed_abort = agreed_abort || h->abort_word[1] > 0;
+      if (multi) agreed_abort = agreed_abort || c.abort_agreed > 0;
       if (c.cand_used > 1) h->spec_used++;
       if (single_step) break;
       if (c.stop_trials) { next_iteration_started = ahead && !c.terminate && !c.conv_mag && !c.conv_res; break; }

@@ -994,6 +994,7 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
     if (threadIdx.x == 0) {
       s_sum[0][0] = red_in[0];
       for (int cnd = 0; cnd < n_cand; cnd++) { s_sum[cnd][1] = red_in[1 + 3 * cnd]; s_sum[cnd][2] = red_in[2 + 3 * cnd]; s_sum[cnd][3] = red_in[3 + 3 * cnd]; }
+      d.ctrl->abort_agreed = red_in[1 + 3 * n_cand];
     }
   } else {
     // every partial sum is loaded before the first reduction (one round of independent loads instead of ten
@@ -1120,8 +1121,10 @@ void launch_tri_pack(double* const* full, int count, double* packed, int n, int 
 }
 
 // sums the per-block partials into out[0..3] = {cur_chi, tmp_chi, scale, sumsq} (multi-GPU path)
-__global__ void __launch_bounds__(256) k_reduce_partials(BaDev d, int n_part_lin, int n_part_bs, double* out)
+__global__ void __launch_bounds__(256) k_reduce_partials(BaDev d, int n_part_lin, int n_part_bs, double* out, const volatile double* host_word, int word_slot)
 {
+  // (multi-GPU) this rank's view of the caller's abort flag rides along: read from pinned host memory, summed with the trial sums
+  if (host_word && threadIdx.x == 0) out[word_slot] = *host_word;
   __shared__ double red[32];
   double a = 0, b = 0, c = 0, e = 0;
   for (int i = threadIdx.x; i < n_part_lin; i += blockDim.x) a += d.part[PART_CUR_CHI * MAX_PARTIALS + i];
@@ -1271,9 +1274,9 @@ void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n
 {
   launch_chain(k_lm_control, dim3(1), dim3(256), 0, s, d, parts, n_cand, n_lin, n_bs, red_in, first_trial);
 }
-void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s)
+void launch_reduce_partials(const BaDev& d, int n_lin, int n_bs, double* out, cudaStream_t s, const double* host_word, int word_slot)
 {
-  k_reduce_partials<<<1, 256, 0, s>>>(d, n_lin, n_bs, out);
+  k_reduce_partials<<<1, 256, 0, s>>>(d, n_lin, n_bs, out, host_word, word_slot);
 }
 void launch_debug_jacobians(const BaDev& d, double* out, cudaStream_t s) { k_debug_jacobians<<<148, 128, 0, s>>>(d, out); }
 void launch_gather_delta(const BaDev& d, double* out, cudaStream_t s) { k_gather_delta<<<148, 128, 0, s>>>(d, out); }

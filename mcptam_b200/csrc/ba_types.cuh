@@ -47,6 +47,7 @@ struct BaCtrl {
   int cand_used;      // candidates consumed by the last k_lm_control
   int marg_fail;      // computeMarginals() failed (singular block)
   double median_out;  // plain upper median of the last mode-2 selection (point-depth covariances)
+  double abort_agreed; // multi-GPU: sum over the ranks of their abort flags as of the last trial round (> 0: everybody stops)
 };
 
 struct BaDev {

@@ -19,3 +19,5 @@ def test_two_gpu_sharded_matches_single():
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("MULTI")]
     assert line and line[0].endswith("OK"), out.stdout[-2000:]
+    ab = [l for l in out.stdout.splitlines() if l.startswith("MULTI_ABORT")]
+    assert ab and ab[0].endswith("OK"), out.stdout[-2000:]

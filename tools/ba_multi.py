@@ -54,6 +54,14 @@ def main():
         ok = rc == rc1 and st.total_trials == st1.total_trials and relp < 1e-7 and relx < 1e-7
         print("MULTI", cfg, "world", world, "rc", rc, rc1, "trials", st.total_trials, st1.total_trials, "rel", relp, relx,
               "gpu_ms sharded", st.gpu_ms, "single", st1.gpu_ms, "wall", dt, dt1, "OK" if ok else "MISMATCH", flush=True)
+    # the abort flag of ONE rank must stop every rank in the same round (the decision is collective: no hang, same return code)
+    ab = np.array([1 if rank == world - 1 else 0], np.uint8)
+    h.reset_state()
+    rc_a, st_a = h.compute(iters, abort=ab)
+    rcs = [None] * world
+    dist.all_gather_object(rcs, (rc_a, st_a.iterations))
+    if rank == 0:
+        print("MULTI_ABORT", rcs, "OK" if all(r == rcs[0] for r in rcs) and rcs[0][0] == 0 else "MISMATCH", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
