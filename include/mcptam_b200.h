@@ -182,12 +182,13 @@ typedef struct McpLevelOut {
   int32_t n_corners;            /* after threshold + mask filtering; raster order */
   int32_t fast_thresh;          /* Level::nFastThresh */
   int32_t fast_freq[31];        /* Level::vFastFrequency[0..30] */
-  int32_t pad_;
+  int32_t n_corners_total;      /* corners the level really has; > n_corners means max_corners_per_level truncated the list (raise it) */
   uint8_t* image;               /* optional host out: width*height bytes, may be NULL */
   int32_t* corners_xy;          /* optional host out: 2*cap ints, may be NULL */
   int32_t corners_cap;
   int32_t pad2_;
   int32_t* row_lut;             /* optional host out: height ints (Level::vCornerRowLUT), may be NULL */
+  uint8_t* last_mask;           /* optional host out: width*height bytes, Level::lastMask (src/KeyFrame.cc:242), may be NULL */
 } McpLevelOut;
 
 typedef struct McpPatchReq {
@@ -220,6 +221,10 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out);
 int mcp_fe_destroy(McpFe* h);
 /* Optional fixed mask (KeyFrame::SetMask): level-0 mask, half-sampled internally; NULL clears it. */
 int mcp_fe_set_mask(McpFe* h, const uint8_t* mask, int32_t stride);
+/* bGlareMasking of KeyFrame::MakeKeyFrame_Lite (src/KeyFrame.cc:214-242; include/mcptam/KeyFrame.h:186): when enabled, the
+ * following mcp_fe_make_keyframe calls AND the internal mask with the glare mask -- 0 wherever a pixel brighter than 245 lies
+ * within five dilations by OpenCV's 5x5 MORPH_ELLIPSE element -- before the corners are filtered. */
+int mcp_fe_set_glare_masking(McpFe* h, int32_t enable);
 /* Builds the 4-level pyramid + corners of one image into resident keyframe slot `slot`
  * (H2D copy of the image, D2H copy of the corner lists/LUTs when out pointers are given). */
 int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t stride, McpLevelOut out[MCP_LEVELS]);

@@ -313,8 +313,8 @@ class FeConfig(C.Structure):
 
 class LevelOut(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_corners", C.c_int32), ("fast_thresh", C.c_int32),
-                ("fast_freq", C.c_int32 * 31), ("pad_", C.c_int32), ("image", C.c_void_p), ("corners_xy", C.c_void_p),
-                ("corners_cap", C.c_int32), ("pad2_", C.c_int32), ("row_lut", C.c_void_p)]
+                ("fast_freq", C.c_int32 * 31), ("n_corners_total", C.c_int32), ("image", C.c_void_p), ("corners_xy", C.c_void_p),
+                ("corners_cap", C.c_int32), ("pad2_", C.c_int32), ("row_lut", C.c_void_p), ("last_mask", C.c_void_p)]
 
 
 class PatchReq(C.Structure):
@@ -366,6 +366,7 @@ def _bind_fe(L):
     L.mcp_fe_create.argtypes = [C.POINTER(FeConfig), C.POINTER(C.c_void_p)]
     L.mcp_fe_destroy.argtypes = [C.c_void_p]
     L.mcp_fe_set_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.mcp_fe_set_glare_masking.argtypes = [C.c_void_p, C.c_int32]
     L.mcp_fe_make_keyframe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     L.mcp_fe_search_patches.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.mcp_fe_get_templates.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -417,7 +418,10 @@ class FeHandle:
             m = np.ascontiguousarray(mask, np.uint8)
             check(self.L.mcp_fe_set_mask(self.h, _p(m), m.shape[1]))
 
-    def make_keyframe(self, slot, img, want_images=False, outputs=True):
+    def set_glare_masking(self, on=True):
+        check(self.L.mcp_fe_set_glare_masking(self.h, int(bool(on))))
+
+    def make_keyframe(self, slot, img, want_images=False, outputs=True, want_masks=False):
         """MakeKeyFrame_Lite of one image into resident slot `slot`.  Returns a list of 4 per-level dicts."""
         img = np.ascontiguousarray(img, np.uint8)
         if not outputs:
@@ -431,7 +435,9 @@ class FeHandle:
             cor = np.zeros((cap, 2), np.int32)
             lut = np.zeros(h, np.int32)
             im = np.zeros((h, w), np.uint8) if want_images else None
-            keep.append((cor, lut, im))
+            mk = np.zeros((h, w), np.uint8) if want_masks else None
+            keep.append((cor, lut, im, mk))
+            outs[l].last_mask = mk.ctypes.data if mk is not None else None
             outs[l].corners_xy = cor.ctypes.data
             outs[l].corners_cap = cap
             outs[l].row_lut = lut.ctypes.data
@@ -441,11 +447,11 @@ class FeHandle:
         check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], C.cast(outs, C.c_void_p)))
         res = []
         for l in range(4):
-            cor, lut, im = keep[l]
+            cor, lut, im, mk = keep[l]
             n = outs[l].n_corners
             res.append({"width": outs[l].width, "height": outs[l].height, "n_corners": n, "corners": cor[:n].copy(),
-                        "row_lut": lut, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
-                        "image": im})
+                        "row_lut": lut, "n_corners_total": outs[l].n_corners_total, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
+                        "image": im, "last_mask": mk})
         return res
 
     def search_patches(self, target_kf, req: np.ndarray) -> np.ndarray:

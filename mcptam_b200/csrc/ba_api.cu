@@ -193,16 +193,8 @@ void mcp_ba_default_config(McpBaConfig* c)
   c->device = -1;
 }
 
-int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
+static int ba_create_impl(const McpBaConfig* cfg, McpBa* h)
 {
-  if (!out) { set_last_error("mcp_ba_create: out is NULL"); return MCP_ERR_INVALID; }
-  *out = nullptr;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_last_error("mcp_ba_create: no CUDA device available (this library has no CPU fallback)");
-    return MCP_ERR_NO_DEVICE;
-  }
-  McpBa* h = new McpBa();
   if (cfg) h->cfg = *cfg; else mcp_ba_default_config(&h->cfg);
   if (h->cfg.device >= 0) { MCP_CUDA_CHECK(cudaSetDevice(h->cfg.device)); }
   MCP_CUDA_CHECK(cudaGetDevice(&h->device));
@@ -229,6 +221,22 @@ int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
   h->abort_word[0] = h->abort_word[1] = 0;
   memset(&h->d, 0, sizeof(h->d));
   memset(&h->timing, 0, sizeof(h->timing));
+  return MCP_OK;
+}
+
+int mcp_ba_destroy(McpBa* h);
+int mcp_ba_create(const McpBaConfig* cfg, McpBa** out)
+{
+  if (!out) { set_last_error("mcp_ba_create: out is NULL"); return MCP_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_last_error("mcp_ba_create: no CUDA device available (this library has no CPU fallback)");
+    return MCP_ERR_NO_DEVICE;
+  }
+  McpBa* h = new McpBa();
+  const int rc = ba_create_impl(cfg, h);
+  if (rc != MCP_OK) { mcp_ba_destroy(h); return rc; }       // streams, events and pinned buffers created so far are released
   *out = h;
   return MCP_OK;
 }
@@ -291,6 +299,7 @@ int mcp_ba_set_cameras(McpBa* h, int32_t n_cam, const McpTaylorCam* cams)
   cudaSetDevice(h->device);
   int rc = h->b_cams.ensure(sizeof(DevCam) * n_cam);
   if (rc) return rc;
+  h->loaded = false;                                   // the camera table may have moved: a problem must be (re)loaded against it
   MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_cams.p, h->cams.data(), sizeof(DevCam) * n_cam, cudaMemcpyHostToDevice, h->stream));
   MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   return MCP_OK;

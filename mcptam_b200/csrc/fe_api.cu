@@ -10,6 +10,7 @@
 namespace mcp {
 void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s);
 int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s);
+void fe_launch_glare_mask(const FeKf& kf, const FeMasks& out, cudaStream_t s);
 void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s);
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s);
 void fe_launch_calc_jacobians(const DevCam& cam, const Se3& B, const Se3& Cb, int n, const double* pw, McpJacRes* out, cudaStream_t s);
@@ -37,7 +38,8 @@ struct McpFe {
   size_t out_block_bytes = 0;      // per slot: meta + luts + corners (contiguous, copied to the host in one go)
   std::vector<uint8_t*> out_block_dev;
   uint8_t* mask_dev[MCP_LEVELS] = { nullptr, nullptr, nullptr, nullptr };
-  bool has_mask = false;
+  uint8_t* gmask_dev[MCP_LEVELS] = { nullptr, nullptr, nullptr, nullptr };   // internal mask AND glare mask of the last frame (Level::lastMask)
+  bool has_mask = false, glare = false;
   uint8_t* stage_img = nullptr;    // pinned
   uint8_t* stage_out = nullptr;    // pinned
   McpPatchReq* req_host = nullptr; // pinned
@@ -113,6 +115,8 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
   }
   size_t o_mask[MCP_LEVELS];
   for (int l = 0; l < MCP_LEVELS; l++) o_mask[l] = take((size_t)h->lp[l] * h->lh[l]);
+  size_t o_gmask[MCP_LEVELS];
+  for (int l = 0; l < MCP_LEVELS; l++) o_gmask[l] = take((size_t)h->lp[l] * h->lh[l]);
   const size_t o_kf = take(sizeof(FeKf) * S);
   const size_t o_req = take(sizeof(McpPatchReq) * c.max_patches);
   const size_t o_res = take(sizeof(McpPatchRes) * c.max_patches);
@@ -125,7 +129,7 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
   h->kf_host.resize(S);
   h->kf_valid.assign(S, false);
   h->out_block_dev.resize(S);
-  for (int l = 0; l < MCP_LEVELS; l++) h->mask_dev[l] = h->pool + o_mask[l];
+  for (int l = 0; l < MCP_LEVELS; l++) { h->mask_dev[l] = h->pool + o_mask[l]; h->gmask_dev[l] = h->pool + o_gmask[l]; }
   for (int s = 0; s < S; s++) {
     FeKf& k = h->kf_host[s];
     memset(&k, 0, sizeof(k));
@@ -215,6 +219,14 @@ int mcp_fe_set_mask(McpFe* h, const uint8_t* mask, int32_t stride)
   return MCP_OK;
 }
 
+// bGlareMasking of KeyFrame::MakeKeyFrame_Lite (src/KeyFrame.cc:214-242): applies to the following mcp_fe_make_keyframe calls
+int mcp_fe_set_glare_masking(McpFe* h, int32_t enable)
+{
+  if (!h) { set_last_error("mcp_fe_set_glare_masking: NULL handle"); return MCP_ERR_INVALID; }
+  h->glare = enable != 0;
+  return MCP_OK;
+}
+
 int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t stride, McpLevelOut out[MCP_LEVELS])
 {
   if (!h || !img || slot < 0 || slot >= (int)h->kf_host.size() || stride < h->lw[0]) {
@@ -233,7 +245,15 @@ int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t str
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
   fe_launch_pyramid(kf, h->cfg.halfsample_round, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
-  const int nl = fe_launch_fast(kf, h->cfg.adaptive_thresh, s);
+  int nl = 0;
+  if (h->glare) {
+    // the frame's effective mask = internal mask AND (no pixel > 245 within the dilation footprint); FAST filters against it
+    FeMasks gm;
+    FeKf kg = kf;
+    for (int l = 0; l < MCP_LEVELS; l++) { gm.m[l] = h->gmask_dev[l]; kg.lv[l].mask = h->gmask_dev[l]; }
+    fe_launch_glare_mask(kf, gm, s);
+    nl = 1 + fe_launch_fast(kg, h->cfg.adaptive_thresh, s);
+  } else nl = fe_launch_fast(kf, h->cfg.adaptive_thresh, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[3], s));
   MCP_CUDA_CHECK(cudaMemcpyAsync(h->stage_out, h->out_block_dev[slot], h->out_block_bytes, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[4], s));
@@ -256,10 +276,18 @@ int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t str
       McpLevelOut& o = out[l];
       o.width = h->lw[l]; o.height = h->lh[l];
       o.n_corners = std::min(meta->lv[l].n_corners, cap);
+      o.n_corners_total = meta->lv[l].n_corners;            // > n_corners: the level overflowed max_corners_per_level (the tail is lost)
+      if (o.corners_cap < 0) o.corners_cap = 0;
       o.fast_thresh = meta->lv[l].fast_thresh;
       memcpy(o.fast_freq, meta->lv[l].fast_freq, sizeof(o.fast_freq));
       if (o.corners_xy) memcpy(o.corners_xy, h->stage_out + cor_off[l], sizeof(int32_t) * 2 * (size_t)std::min(o.n_corners, o.corners_cap));
       if (o.row_lut) memcpy(o.row_lut, h->stage_out + lut_off[l], sizeof(int32_t) * h->lh[l]);
+      if (o.last_mask) {
+        // Level::lastMask: the mask the corners were filtered with (all 255 when neither an internal mask nor glare masking is on)
+        const uint8_t* src = h->glare ? h->gmask_dev[l] : (h->has_mask ? h->mask_dev[l] : nullptr);
+        if (src) MCP_CUDA_CHECK(cudaMemcpy2D(o.last_mask, h->lw[l], src, h->lp[l], h->lw[l], h->lh[l], cudaMemcpyDeviceToHost));
+        else memset(o.last_mask, 255, (size_t)h->lw[l] * h->lh[l]);
+      }
       if (o.image) {
         if (l == 0) memcpy(o.image, h->stage_img, (size_t)w * hh);
         else MCP_CUDA_CHECK(cudaMemcpy2D(o.image, h->lw[l], kf.lv[l].img, kf.lv[l].pitch, h->lw[l], h->lh[l], cudaMemcpyDeviceToHost));
@@ -277,6 +305,10 @@ int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatch
   }
   if (n > h->cfg.max_patches) { set_last_error("mcp_fe_search_patches: n=%d exceeds max_patches=%d", n, h->cfg.max_patches); return MCP_ERR_INVALID; }
   if (!h->kf_valid[target_kf]) { set_last_error("mcp_fe_search_patches: target keyframe slot %d is empty", target_kf); return MCP_ERR_STATE; }
+  for (int i = 0; i < n; i++) {
+    const int sk = req[i].src_kf;
+    if (sk < 0 || sk >= (int)h->kf_host.size() || !h->kf_valid[sk]) { set_last_error("mcp_fe_search_patches: request %d: source keyframe slot %d is out of range or empty", i, sk); return MCP_ERR_STATE; }
+  }
   if (n == 0) return MCP_OK;
   cudaSetDevice(h->device);
   cudaStream_t s = h->stream;
@@ -313,6 +345,7 @@ int mcp_fe_shitomasi(McpFe* h, int32_t kf, int32_t level, int32_t n, const int32
     set_last_error("mcp_fe_shitomasi: bad arguments");
     return MCP_ERR_INVALID;
   }
+  if (!h->kf_valid[kf]) { set_last_error("mcp_fe_shitomasi: keyframe slot %d is empty", kf); return MCP_ERR_STATE; }
   if (n == 0) return MCP_OK;
   cudaSetDevice(h->device);
   cudaStream_t s = h->stream;
@@ -333,6 +366,7 @@ int mcp_fe_minipatch_find(McpFe* h, int32_t kf_src, int32_t kf_dst, int32_t leve
     set_last_error("mcp_fe_minipatch_find: bad arguments");
     return MCP_ERR_INVALID;
   }
+  if (!h->kf_valid[kf_src] || !h->kf_valid[kf_dst]) { set_last_error("mcp_fe_minipatch_find: keyframe slot %d is empty", h->kf_valid[kf_src] ? kf_dst : kf_src); return MCP_ERR_STATE; }
   if (n == 0) return MCP_OK;
   cudaSetDevice(h->device);
   cudaStream_t s = h->stream;

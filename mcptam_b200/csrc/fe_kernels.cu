@@ -839,6 +839,55 @@ __global__ void __launch_bounds__(1024) k_pose_update(int n, const McpPoseMeas* 
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Glare mask (KeyFrame::MakeKeyFrame_Lite with bGlareMasking, src/KeyFrame.cc:214-242):
+//   cv::dilate(img, 5x5 MORPH_ELLIPSE, 5 iterations) -> cv::threshold(245, 255, THRESH_BINARY_INV) -> bitwise_and with the
+//   internal mask.  Dilation commutes with the threshold, and five passes of the 5x5 ellipse (rows +-2: centre pixel only,
+//   rows -1..1: 5 wide) are ONE pass of their Minkowski sum: a 21-row shape of half-width 10 for |dy| <= 5 and
+//   10 - 2 (|dy| - 5) beyond.  One CTA per 32x32 tile: the tile plus a 10-pixel apron is thresholded into shared memory as
+//   the horizontal distance to the nearest bright pixel of its row, then every output pixel scans its 21 rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_glare_mask(FeKf kf, FeMasks out)
+{
+  const int l = blockIdx.z;
+  const FeLevel& L = kf.lv[l];
+  const int tiles_x = (L.w + 31) / 32;
+  if ((int)blockIdx.x >= tiles_x * ((L.h + 31) / 32)) return;
+  const int tx0 = (blockIdx.x % tiles_x) * 32, ty0 = (blockIdx.x / tiles_x) * 32;
+  __shared__ unsigned char bright[52][52 + 4];
+  __shared__ unsigned char dist[52][32];
+  for (int e = threadIdx.x; e < 52 * 52; e += 256) {
+    const int yy = e / 52, xx = e % 52, gx = tx0 + xx - 10, gy = ty0 + yy - 10;
+    bright[yy][xx] = (gx >= 0 && gy >= 0 && gx < L.w && gy < L.h && L.img[(size_t)gy * L.pitch + gx] > 245) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 52 * 32; e += 256) {
+    const int yy = e / 32, x = e % 32;
+    int dmin = 11;
+    for (int dx = 0; dx <= 10; dx++)
+      if (bright[yy][10 + x + dx] || bright[yy][10 + x - dx]) { dmin = dx; break; }
+    dist[yy][x] = (unsigned char)dmin;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+    const int y = e / 32, x = e % 32, gx = tx0 + x, gy = ty0 + y;
+    if (gx >= L.w || gy >= L.h) continue;
+    bool glare = false;
+#pragma unroll
+    for (int dy = -10; dy <= 10; dy++) {
+      const int ady = dy < 0 ? -dy : dy, hw = ady <= 5 ? 10 : 10 - 2 * (ady - 5);
+      glare = glare || (dist[10 + y + dy][x] <= hw);
+    }
+    const unsigned char internal = L.mask ? L.mask[(size_t)gy * L.pitch + gx] : 255;
+    out.m[l][(size_t)gy * L.pitch + gx] = glare ? 0 : internal;
+  }
+}
+void fe_launch_glare_mask(const FeKf& kf, const FeMasks& out, cudaStream_t s)
+{
+  const int tiles0 = ((kf.lv[0].w + 31) / 32) * ((kf.lv[0].h + 31) / 32);
+  k_glare_mask<<<dim3(tiles0, 1, MCP_LEVELS), 256, 0, s>>>(kf, out);
+}
+
 void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s)
 {
   const bool fused = (kf.lv[0].w % 8 == 0) && (kf.lv[0].h % 8 == 0) && kf.lv[1].w == kf.lv[0].w / 2 && kf.lv[3].w == kf.lv[0].w / 8;

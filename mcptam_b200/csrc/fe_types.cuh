@@ -32,6 +32,8 @@ struct FeKf {
   int corner_cap, pad_;
 };
 
+struct FeMasks { unsigned char* m[MCP_LEVELS]; };   // per-level effective masks (pitch = the level's image pitch)
+
 struct FeDev {
   const FeKf* kf;        // [n_slots] in device memory
   int n_slots;

@@ -124,8 +124,8 @@ int BundleAdjusterCuda::AdjustAndUpdate(ChainBundle& multiBundle, std::set<Multi
     mdSigmaSquared = multiBundle.GetSigmaSquared();
     mdMeanChiSquared = multiBundle.GetMeanChiSquared();
     mdMaxCov = multiBundle.GetMaxCov();
+    if (mUpdateCallback) mUpdateCallback(spAdjustSet, spMapPoints);
   }
-  (void)spAdjustSet; (void)spMapPoints;
   return nAccepted;
 }
 

@@ -3,6 +3,7 @@
 // map exactly like src/BundleAdjusterMulti.cc:55-337, but the ChainBundle it drives runs on the B200.
 #pragma once
 
+#include <functional>
 #include <set>
 #include <unordered_map>
 #include <utility>
@@ -44,6 +45,10 @@ class BundleAdjusterCuda : public BundleAdjusterBase {
   int BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::set<MultiKeyFrame*> spFixedSet, std::set<MapPoint*> spMapPoints,
                    std::vector<std::pair<KeyFrame*, MapPoint*> >& vOutliers, bool bRecent) override;
   double LastGpuMs() const { return mdGpuMs; }
+  // include/mcptam/BundleAdjusterMulti.h:69,86: called after every successful update of the map (src/BundleAdjusterMulti.cc:332-333),
+  // i.e. after each of the two Compute passes of the two-step adjuster -- the network MapMaker uses it to push updates
+  typedef std::function<void(std::set<MultiKeyFrame*>, std::set<MapPoint*>)> UpdateCallbackType;
+  void SetUpdateCallback(UpdateCallbackType up) { mUpdateCallback = up; }
 
  protected:
   // The marshalling half of BundleAdjust (src/BundleAdjusterMulti.cc:83-203): poses, points and measurements of the map
@@ -60,6 +65,7 @@ class BundleAdjusterCuda : public BundleAdjusterBase {
   std::map<int, MultiKeyFrame*> mmBundleID_Base;
   std::map<std::string, int> mmCamName_BundleID;
   double mdGpuMs = 0;
+  UpdateCallbackType mUpdateCallback;
 };
 
 }  // namespace mcp_host

@@ -16,8 +16,14 @@ double ChainBundle::sdMinMEstimatorSigma = 0.5;
 // one cached device handle per host thread (the MapMaker thread): device buffers, pinned staging and the marshalling
 // threads survive across BundleAdjust calls -- the reference builds a new ChainBundle on the stack for every call
 // (src/BundleAdjusterMulti.cc:75).  The handle is reused when the next object asks for the same configuration.
-static thread_local McpBa* tl_pooled = nullptr;
-static thread_local McpBaConfig tl_pooled_cfg;
+struct PooledHandle {
+  McpBa* h = nullptr;
+  McpBaConfig cfg;
+  ~PooledHandle() { if (h) mcp_ba_destroy(h); }            // released when the thread ends
+};
+static thread_local PooledHandle tl_pool;
+#define tl_pooled tl_pool.h
+#define tl_pooled_cfg tl_pool.cfg
 
 ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey, bool bVerbose)
     : mmCameraModels(cams), mbUseRobust(bUseRobust), mbUseTukey(bUseTukey), mbVerbose(bVerbose)
@@ -27,7 +33,8 @@ ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey,
 ChainBundle::~ChainBundle()
 {
   if (mpHandle) {
-    if (!tl_pooled) { tl_pooled = mpHandle; tl_pooled_cfg = mConfig; } else mcp_ba_destroy(mpHandle);
+    // a handle whose last call failed (CUDA error state) or that joined a communicator is not worth keeping
+    if (!tl_pooled && !mbHandleFailed) { tl_pooled = mpHandle; tl_pooled_cfg = mConfig; } else mcp_ba_destroy(mpHandle);
   }
 }
 
@@ -105,7 +112,7 @@ int ChainBundle::Upload()
     } else {
       if (tl_pooled) { mcp_ba_destroy(tl_pooled); tl_pooled = nullptr; }
       int rc = mcp_ba_create(&cfg, &mpHandle);
-      if (rc) return rc;
+      if (rc) { mbHandleFailed = true; return rc; }
     }
     mConfig = cfg;
   }
@@ -113,11 +120,11 @@ int ChainBundle::Upload()
   for (auto& n : mvCamNames) cams.push_back(mmCameraModels[n].ToAbi());
   if (cams.empty()) return MCP_ERR_STATE;
   int rc = mcp_ba_set_cameras(mpHandle, (int)cams.size(), cams.data());
-  if (rc) return rc;
+  if (rc) { mbHandleFailed = (rc == MCP_ERR_CUDA); return rc; }
   rc = mcp_ba_load(mpHandle, (int)mvPoseFixed.size(), mvPoseRt.data(), mvPoseFixed.data(), (int)mvPtFixed.size(), mvPtXyz.data(),
                    mvPtChain.data(), mvPtFixed.data(), (int)mvMeasPt.size(), mvMeasXy.data(), mvMeasChain.data(), mvMeasPt.data(),
                    mvMeasNoise.data(), mvMeasCam.data());
-  if (rc) return rc;
+  if (rc) { mbHandleFailed = (rc == MCP_ERR_CUDA || rc == MCP_ERR_NCCL); return rc; }
   mbUploaded = true;
   return MCP_OK;
 }
@@ -138,7 +145,7 @@ int ChainBundle::Compute(bool* pAbortSignal, int nNumIter, double dUserLambda)
   McpBaStats st;
   static_assert(sizeof(bool) == 1, "abort flag is polled as a byte");
   const int n = mcp_ba_compute(mpHandle, reinterpret_cast<volatile const uint8_t*>(pAbortSignal), nNumIter, dUserLambda, &st);
-  if (n < -1) { std::fprintf(stderr, "ChainBundle: %s\n", mcp_last_error()); return -1; }
+  if (n < -1) { mbHandleFailed = true; std::fprintf(stderr, "ChainBundle: %s\n", mcp_last_error()); return -1; }
   mbConverged = st.converged != 0;
   // the reference's convergence actions raise the shared abort flag (src/ChainBundle.cc:1028,1106)
   if (mbConverged && pAbortSignal) *pAbortSignal = true;

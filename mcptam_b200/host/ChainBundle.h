@@ -57,6 +57,7 @@ class ChainBundle {
   std::vector<std::string> mvCamNames;     // camera index -> name
   std::vector<int> mvMeasCamName;
   McpBa* mpHandle = nullptr;
+  bool mbHandleFailed = false;        // the last device call failed: the handle is destroyed instead of pooled
   bool mbUploaded = false, mbConverged = false;
   int mnTotalIterations = 0;
   double mdSigmaSquared = 0, mdMeanChiSquared = 0, mdLastMaxCov = 1.7976931348623157e308, mdLambda = 0, mdGpuMs = 0;

@@ -45,6 +45,78 @@ std::tuple<double, double, double> MakeKeyFrame_Lite(FrontEndDevice& dev, KeyFra
   return std::make_tuple(tm.ms_pyramid * 1e-3, 0.0, tm.ms_fast * 1e-3);
 }
 
+}  // namespace mcp_host
+
+// KeyFrame::MakeKeyFrame_Lite (src/KeyFrame.cc:145-361) with the reference's member signature.  The previous image and corner
+// list of every level go into the imagePrev / vCornersPrev rings before they are overwritten (:152-157,:184-198); the device
+// keeps the matching pyramids: the keyframe owns snNumPrev + 1 slots and the new frame takes the oldest one.
+namespace mcp_shim {
+std::tuple<double, double, double> KeyFrame::MakeKeyFrame_Lite(Image<byte>& im, bool bDeepCopy, bool bGlareMasking)
+{
+  using namespace mcp_host;
+  if (!mpDevice) throw std::runtime_error("KeyFrame::MakeKeyFrame_Lite: no FrontEndDevice attached (KeyFrame::AttachDevice)");
+  (void)bDeepCopy;                                       // the level images are always copies here (no reference-counted CVD::Image)
+  const bool bPushBack = maLevels[0].image.totalsize() > 0;
+  for (int l = 0; l < LEVELS; l++) {
+    Level& lev = maLevels[l];
+    if (bPushBack) {
+      lev.imagePrev.push_back(lev.image);
+      lev.vCornersPrev.push_back(std::vector<ImageRef>());
+      lev.vCornersPrev.back().swap(lev.vCorners);
+    }
+    lev.vCorners.clear();
+    for (int t = 0; t <= MAX_FAST_THRESH; t++) lev.vFastFrequency[t] = 0;
+    lev.nFastThresh = 0;
+  }
+  const int nSlots = Level::snNumPrev + 1;
+  const int slot = mnFirstSlot + (mnSlotTurn % nSlots);
+  mnSlotTurn++;
+  if (mcp_fe_set_glare_masking(mpDevice->handle(), bGlareMasking ? 1 : 0) != MCP_OK) throw std::runtime_error(mcp_last_error());
+  McpLevelOut out[MCP_LEVELS];
+  std::vector<std::vector<int32_t> > cor(MCP_LEVELS);
+  int w = mpDevice->width(), h = mpDevice->height();
+  const int cap = 16384;
+  for (int l = 0; l < MCP_LEVELS; l++) {
+    Level& lev = maLevels[l];
+    std::memset(&out[l], 0, sizeof(out[l]));
+    cor[l].resize(2 * (size_t)cap);
+    lev.vCornerRowLUT.assign(h, 0);
+    lev.image.resize(ImageRef(w, h));
+    lev.lastMask.resize(ImageRef(w, h));
+    out[l].image = lev.image.data(); out[l].last_mask = lev.lastMask.data();
+    out[l].corners_xy = cor[l].data(); out[l].corners_cap = cap; out[l].row_lut = lev.vCornerRowLUT.data();
+    w /= 2; h /= 2;
+  }
+  if (mcp_fe_make_keyframe(mpDevice->handle(), slot, im.data(), im.row_stride(), out) != MCP_OK)
+    throw std::runtime_error(std::string("KeyFrame::MakeKeyFrame_Lite: ") + mcp_last_error());
+  for (int l = 0; l < MCP_LEVELS; l++) {
+    Level& lev = maLevels[l];
+    lev.vCorners.resize(out[l].n_corners);
+    for (int i = 0; i < out[l].n_corners; i++) lev.vCorners[i] = ImageRef(cor[l][2 * i], cor[l][2 * i + 1]);
+    lev.nFastThresh = out[l].fast_thresh;
+    for (int t = 0; t <= MAX_FAST_THRESH; t++) lev.vFastFrequency[t] = out[l].fast_freq[t];
+  }
+  nDeviceSlot = slot;
+  McpFeTiming tm;
+  mcp_fe_get_timing(mpDevice->handle(), &tm);
+  return std::make_tuple(tm.ms_pyramid * 1e-3, 0.0, tm.ms_fast * 1e-3);      // (downsample, mask, feature) seconds; the mask is part of the feature pass
+}
+void KeyFrame::SetMask(Image<byte>& m)
+{
+  if (!mpDevice) throw std::runtime_error("KeyFrame::SetMask: no FrontEndDevice attached");
+  maLevels[0].mask = m;
+  if (mcp_fe_set_mask(mpDevice->handle(), m.totalsize() ? m.data() : nullptr, m.row_stride()) != MCP_OK) throw std::runtime_error(mcp_last_error());
+}
+int KeyFrame::PrevDeviceSlot(int nBack) const
+{
+  const int nSlots = Level::snNumPrev + 1;
+  if (nBack < 1 || nBack > Level::snNumPrev || nBack > (int)maLevels[0].imagePrev.size() || mnSlotTurn - 1 - nBack < 0) return -1;
+  return mnFirstSlot + ((mnSlotTurn - 1 - nBack) % nSlots);
+}
+}  // namespace mcp_shim
+
+namespace mcp_host {
+
 int CalcSearchLevelAndWarpMatrix(TrackerData& td, const SE3& se3CFromW)
 {
   MapPoint& point = *td.mpPoint;

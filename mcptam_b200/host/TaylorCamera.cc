@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 
 namespace mcp_host {
 
@@ -40,6 +41,12 @@ void TaylorCamera::RefreshParams()
   mdMinTheta = std::atan(PolyVal(mv5PolyCoeffs, 5, mdMaxRho) / mdMaxRho);
   mvxPolyInvCoeffs = FindInvPolyUsingRoots(-1, 0.0001);
   mbUsingInversePoly = !mvxPolyInvCoeffs.empty();
+  if (!mbUsingInversePoly)
+    // The reference falls back to a linear inverse + Newton iterations here (src/TaylorCamera.cc:159-175, 262-267: 'slow').  The
+    // device path evaluates the inverse polynomial only, so such a calibration is refused HERE, by name, instead of surfacing
+    // later as a bundle adjustment that returns -1 ('map corrupt').
+    std::fprintf(stderr, "TaylorCamera: no inverse polynomial of degree <= %d fits this calibration to 1e-4 px; the B200 path does not implement "
+                         "the reference's Newton fallback -- Good() is false, projections are invalid, and ChainBundle refuses the camera\n", MAX_INV_DEGREE);
   mm2Affine[0][0] = scale[0] * p[6]; mm2Affine[0][1] = scale[1] * p[7];
   mm2Affine[1][0] = scale[0] * p[8]; mm2Affine[1][1] = scale[1] * 1;
   const double det = mm2Affine[0][0] * mm2Affine[1][1] - mm2Affine[0][1] * mm2Affine[1][0], id = 1.0 / det;   // opts::M2Inverse

@@ -136,6 +136,12 @@ template <class T> struct Image : BasicImage<T> {
   std::vector<T> store;
   Image() {}
   explicit Image(ImageRef s) { resize(s); }
+  Image(const Image& o) : BasicImage<T>() { *this = o; }          // deep copy (CVD::Image shares; nothing here relies on sharing)
+  Image& operator=(const Image& o)
+  {
+    if (this != &o) { store = o.store; this->my_size = o.my_size; this->my_stride = o.my_stride; this->my_data = store.empty() ? nullptr : store.data(); }
+    return *this;
+  }
   void resize(ImageRef s) { store.assign((size_t)s.x * s.y, T()); this->my_data = store.data(); this->my_size = s; this->my_stride = s.x; }
 };
 

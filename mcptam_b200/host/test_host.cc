@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <random>
 
@@ -107,6 +108,9 @@ int main()
   for (auto& m : mkfs) adj.insert(m.get());
   for (auto& q : pts) sp.insert(q.get());
   std::vector<std::pair<KeyFrame*, MapPoint*> > outliers;
+  int nCallbacks = 0;
+  size_t nCallbackPoints = 0;
+  ba.SetUpdateCallback([&](std::set<MultiKeyFrame*> a, std::set<MapPoint*> p) { nCallbacks++; nCallbackPoints = p.size(); (void)a; });
   const int n = ba.BundleAdjust(adj, fixed, sp, outliers, false);
   double pose_err = 0, pt_err = 0;
   for (int m = 0; m < M; m++) for (int k = 0; k < 3; k++) pose_err = std::max(pose_err, std::fabs(mkfs[m]->mse3BaseFromWorld.trans[k] - truth[m].trans[k]));
@@ -117,6 +121,9 @@ int main()
   std::printf("BundleAdjusterCuda: %zu points, %zu meas, accepted %d, total trials %d, converged %d, sigma^2 %.3f, outliers %zu, pose err %.4f m, median point err %.3f m, gpu %.2f ms\n",
               pts.size(), meas.size(), n, ba.TotalIterations(), (int)ba.ConvergedFull(), ba.GetSigmaSquared(), outliers.size(), pose_err, pt_err, ba.LastGpuMs());
   if (n <= 0 || pose_err > 0.02 || pt_err > 0.05) return 1;
+  // the update callback fires after every successful update: once per pass of the two-step adjuster (src/BundleAdjusterMulti.cc:332-333)
+  std::printf("update callback: %d calls, %zu points\n", nCallbacks, nCallbackPoints);
+  if (nCallbacks < 1 || nCallbacks > 2 || nCallbackPoints != sp.size()) return 1;
 
   // ---- front end --------------------------------------------------------------------------------------
   FrontEndDevice dev(640, 480);
@@ -156,6 +163,36 @@ int main()
   for (auto* td : vTD) if (td->mbFound) { med += std::hypot(td->mv2Found[0] - (td->mpPoint->mirCenter.x - 2), td->mv2Found[1] - (td->mpPoint->mirCenter.y - 1)); cnt++; }
   std::printf("SearchForPoints: %d of %zu found (attempted L0 %d), mean position error %.3f px\n", nf, vTD.size(), att[0], cnt ? med / cnt : -1.0);
   if (nf < (int)vTD.size() / 2 || med / std::max(cnt, 1) > 0.5) return 1;
+  // ---- KeyFrame::MakeKeyFrame_Lite with the reference's member signature: rings, lastMask, glare masking -------------
+  {
+    KeyFrame kf;
+    kf.AttachDevice(&dev, 2);                           // slots 2..4 of the device (0, 1 are used above)
+    Image<byte> imC = imA;
+    for (int y = 200; y < 206; y++) for (int x = 300; x < 330; x++) imC[ImageRef(x, y)] = 255;     // a glare blob
+    kf.MakeKeyFrame_Lite(imA);
+    const std::vector<ImageRef> cornersA = kf.maLevels[0].vCorners;
+    if (kf.maLevels[0].imagePrev.size() != 0 || kf.nDeviceSlot != 2 || kf.PrevDeviceSlot(1) != -1) { std::printf("ring: first frame\n"); return 1; }
+    if (cornersA.size() != kfA.maLevels[0].vCorners.size()) { std::printf("member and free function disagree\n"); return 1; }
+    kf.MakeKeyFrame_Lite(imB);
+    const std::vector<ImageRef> cornersB = kf.maLevels[0].vCorners;
+    kf.MakeKeyFrame_Lite(imC, false, true);
+    bool ok = kf.maLevels[0].imagePrev.size() == 2 && kf.maLevels[3].imagePrev.size() == 2 && kf.maLevels[0].vCornersPrev.size() == 2;
+    ok = ok && kf.maLevels[0].vCornersPrev[0].size() == cornersA.size() && kf.maLevels[0].vCornersPrev[1].size() == cornersB.size();
+    ok = ok && std::memcmp(kf.maLevels[0].imagePrev[0].data(), imA.data(), 640 * 480) == 0 && std::memcmp(kf.maLevels[0].imagePrev[1].data(), imB.data(), 640 * 480) == 0;
+    ok = ok && kf.nDeviceSlot == 4 && kf.PrevDeviceSlot(1) == 3 && kf.PrevDeviceSlot(2) == 2;
+    int nMasked = 0;
+    for (int i = 0; i < 640 * 480; i++) nMasked += kf.maLevels[0].lastMask.data()[i] == 0;
+    bool cornerInMask = false;
+    for (const ImageRef& c : kf.maLevels[0].vCorners) cornerInMask = cornerInMask || kf.maLevels[0].lastMask[c] != 255;
+    std::printf("KeyFrame::MakeKeyFrame_Lite: rings %zu/%zu, glare-masked pixels %d, corners %zu (no corner inside the mask: %d)\n",
+                kf.maLevels[0].imagePrev.size(), kf.maLevels[0].vCornersPrev.size(), nMasked, kf.maLevels[0].vCorners.size(), (int)!cornerInMask);
+    ok = ok && nMasked > 30 * 6 && nMasked < 80 * 40 && !cornerInMask;
+    kf.MakeKeyFrame_Lite(imA);                            // a fourth frame: the rings stay at snNumPrev, the oldest slot is reused
+    ok = ok && kf.maLevels[0].imagePrev.size() == 2 && kf.nDeviceSlot == 2 && kf.PrevDeviceSlot(1) == 4 && kf.PrevDeviceSlot(2) == 3;
+    ok = ok && std::memcmp(kf.maLevels[0].imagePrev[0].data(), imB.data(), 640 * 480) == 0;
+    for (int i = 0; i < 640 * 480 && ok; i++) ok = kf.maLevels[0].lastMask.data()[i] == 255;
+    if (!ok) { std::printf("KeyFrame::MakeKeyFrame_Lite boundary state wrong\n"); return 1; }
+  }
   std::printf("HOST_TEST OK\n");
   return 0;
 }

@@ -294,6 +294,25 @@ def keyframe_rest_level(img, lev, prev_img=None, prev_lev=None, n_prev=0, use_sh
     return {"n_max": n_max.value, "n_candidates": n, "xy": out_xy[:n].copy(), "score": out_sc[:n].copy()}
 
 
+def glare_mask(img, internal=None):
+    """Level::lastMask with bGlareMasking (src/KeyFrame.cc:214-242): five dilations by OpenCV's 5x5 MORPH_ELLIPSE element
+    (rows +-2: the centre pixel, rows -1..1: five pixels; out-of-image pixels never count), threshold 245 inverted, AND with the
+    internal mask.  [3P] OpenCV semantics restated by definition (iterated max filter); pinned against cv2 in tests/test_oracle_cpu.py."""
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape
+    cur = img.copy()
+    offs = [(0, -2), (0, 2)] + [(dx, dy) for dy in (-1, 0, 1) for dx in (-2, -1, 0, 1, 2)]
+    for _ in range(5):
+        pad = np.zeros((h + 4, w + 4), np.uint8)
+        pad[2:-2, 2:-2] = cur
+        nxt = np.zeros_like(cur)
+        for dx, dy in offs:
+            nxt = np.maximum(nxt, pad[2 + dy:2 + dy + h, 2 + dx:2 + dx + w])
+        cur = nxt
+    glare = np.where(cur > 245, 0, 255).astype(np.uint8)
+    return glare if internal is None else (np.asarray(internal, np.uint8) & glare)
+
+
 def shitomasi(img, x, y, half_box=3):
     img = np.ascontiguousarray(img, np.uint8)
     return lib().ora_shitomasi(_p(img), img.shape[1], half_box, int(x), int(y))

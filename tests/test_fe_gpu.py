@@ -302,3 +302,32 @@ def test_keyframe_rest_candidates(capi, ora, mode):
         assert np.array_equal(g["cand"]["score"], ref["score"])
         total += ref["n_candidates"]
     assert total > 50
+
+
+def test_glare_masking(capi, ora):
+    """bGlareMasking (src/KeyFrame.cc:214-242): the per-level lastMask equals the oracle's (cv2-pinned) glare mask AND the
+    internal mask, and the corners are the oracle's corners filtered with that mask."""
+    img = synth.make_frame(seed=41).copy()
+    rng = np.random.default_rng(41)
+    for _ in range(25):
+        x, y = int(rng.integers(0, 640)), int(rng.integers(0, 480))
+        img[max(y - 3, 0):y + 4, max(x - 5, 0):x + 6] = 255
+    internal = np.full((480, 640), 255, np.uint8)
+    internal[:, :64] = 0
+    f = capi.FeHandle(640, 480, max_corners_per_level=16384)
+    for use_internal in (False, True):
+        f.set_mask(internal if use_internal else None)
+        f.set_glare_masking(True)
+        lv = f.make_keyframe(0, img, want_images=True, want_masks=True)
+        pyr = ora.pyramid(img)
+        mpyr = ora.pyramid(internal) if use_internal else [None] * 4
+        for l in range(4):
+            want_mask = ora.glare_mask(pyr[l], mpyr[l])
+            assert np.array_equal(lv[l]["last_mask"], want_mask), l
+            ref = ora.level_corners(pyr[l], mask=want_mask)
+            assert lv[l]["fast_thresh"] == ref["fast_thresh"] and np.array_equal(lv[l]["corners"], ref["corners"]), l
+            assert (want_mask == 0).sum() > 0
+        f.set_glare_masking(False)
+        lv0 = f.make_keyframe(0, img, want_masks=True)
+        assert np.array_equal(lv0[0]["last_mask"], internal if use_internal else np.full((480, 640), 255, np.uint8))
+        assert lv0[0]["n_corners"] >= lv[0]["n_corners"]

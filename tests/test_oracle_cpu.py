@@ -455,3 +455,24 @@ def test_marginals_match_dense_numpy_inverse():
     # >= 3 movable poses: the reference does not attempt it and reports 0 ("failed")
     rc, st = OracleBA(synth.make_ba_config("tiny", seed=0)).compute(2)
     assert st.max_cov == 0
+
+
+def test_glare_mask_matches_opencv():
+    """KeyFrame::MakeKeyFrame_Lite's glare mask (src/KeyFrame.cc:214-227) is three OpenCV calls; the oracle restates them by
+    definition and must reproduce cv2 exactly, including the image border and an internal mask."""
+    import cv2
+    from oracle import oracle as ora
+    from mcptam_b200 import synth
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5), (-1, -1))
+    for seed in (3, 4):
+        img = synth.make_frame(seed=seed).copy()
+        rng = np.random.default_rng(seed)
+        for _ in range(12):
+            x, y = int(rng.integers(0, 640)), int(rng.integers(0, 480))
+            img[max(y - 2, 0):y + 3, max(x - 4, 0):x + 5] = rng.choice([245, 246, 255])
+        img[0:3, 0:5] = 250; img[470:480, 630:640] = 255
+        d = cv2.dilate(img, k, iterations=5)
+        _, gm = cv2.threshold(d, 245, 255, cv2.THRESH_BINARY_INV)
+        assert np.array_equal(ora.glare_mask(img), gm) and (gm == 0).sum() > 1000
+        internal = np.full_like(img, 255); internal[:, :100] = 0
+        assert np.array_equal(ora.glare_mask(img, internal), cv2.bitwise_and(internal, gm))
