@@ -326,7 +326,7 @@ def test_glare_masking(capi, ora):
             assert np.array_equal(lv[l]["last_mask"], want_mask), l
             ref = ora.level_corners(pyr[l], mask=want_mask)
             assert lv[l]["fast_thresh"] == ref["fast_thresh"] and np.array_equal(lv[l]["corners"], ref["corners"]), l
-            assert (want_mask == 0).sum() > 0
+            assert l > 0 or (want_mask == 0).sum() > 0            # (the blobs average out below 245 on the coarse levels)
         f.set_glare_masking(False)
         lv0 = f.make_keyframe(0, img, want_masks=True)
         assert np.array_equal(lv0[0]["last_mask"], internal if use_internal else np.full((480, 640), 255, np.uint8))
