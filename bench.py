@@ -294,14 +294,15 @@ def bench_config(workload, prob, lm_iters, world):
             "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"}
 
 
-def csrc_digest():
-    """Content hash of the kernel sources: a committed ncu capture is only quoted if it was taken from these sources."""
+def csrc_digest(prefixes=("ba_", "mcp_common")):
+    """Content hash of the bundle-adjuster kernel sources: a committed ncu capture is only quoted if it was taken from them."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "mcptam_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        with open(os.path.join(d, f), "rb") as fh:
-            h.update(f.encode()); h.update(fh.read())
+        if f.startswith(prefixes):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]
 
 
@@ -313,7 +314,7 @@ def ncu_traffic(kernel_substr):
         return None, "no capture committed"
     unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     lines = open(prof).read().splitlines()
-    tag = lines[0].split()[-1] if lines and lines[0].startswith("# csrc") else None
+    tag = lines[0].split()[2] if lines and lines[0].startswith("# csrc") and len(lines[0].split()) > 2 else None
     if tag != csrc_digest():
         return None, "capture is from other kernel sources (%s, now %s)" % (tag, csrc_digest())
     tot, cur, seen = 0.0, False, False

@@ -989,12 +989,15 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
 {
   pdl_prologue();
   __shared__ double s_sum[MAX_CAND][4];
+  __shared__ double s_abort;
+  if (threadIdx.x == 0) s_abort = 0.0;
+  __syncthreads();
   if (red_in) {
     // red_in = { cur_chi, (tmp_chi, scale, sumsq) per candidate }
     if (threadIdx.x == 0) {
       s_sum[0][0] = red_in[0];
       for (int cnd = 0; cnd < n_cand; cnd++) { s_sum[cnd][1] = red_in[1 + 3 * cnd]; s_sum[cnd][2] = red_in[2 + 3 * cnd]; s_sum[cnd][3] = red_in[3 + 3 * cnd]; }
-      d.ctrl->abort_agreed = red_in[1 + 3 * n_cand];
+      s_abort = red_in[1 + 3 * n_cand];
     }
   } else {
     // every partial sum is loaded before the first reduction (one round of independent loads instead of ten
@@ -1029,9 +1032,18 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
       else s_sum[(threadIdx.x - 1) / 3][1 + (threadIdx.x - 1) % 3] = t;
     }
   }
+  // The bookkeeping below is a chain of dependent read-modify-writes of the control block: run it on a shared-memory copy
+  // (one coalesced load, one coalesced store) instead of ~40 serial round trips to global memory.
+  __shared__ BaCtrl s_ctrl;
+  {
+    const int* src = reinterpret_cast<const int*>(d.ctrl);
+    int* dst = reinterpret_cast<int*>(&s_ctrl);
+    for (int i = threadIdx.x; i < (int)(sizeof(BaCtrl) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  BaCtrl* c = d.ctrl;
+  if (threadIdx.x == 0) {
+  BaCtrl* c = &s_ctrl;
+  if (red_in) c->abort_agreed = s_abort;
   if (first_trial) { c->current_chi = s_sum[0][0]; c->lin_chi = s_sum[0][0]; }
   const int cur0 = c->cur;
   bool again = true;
@@ -1084,6 +1096,13 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
     c->last_chi2 = curchi;
     c->total_trials += c->qmax;
     c->qmax = 0;
+  }
+  }
+  __syncthreads();
+  {
+    int* dst = reinterpret_cast<int*>(d.ctrl);
+    const int* src = reinterpret_cast<const int*>(&s_ctrl);
+    for (int i = threadIdx.x; i < (int)(sizeof(BaCtrl) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
   }
 }
 

@@ -10,6 +10,8 @@
 //                    MakeSubPixTemplate + IterateSubPixToConvergence (:362-470)
 //   k_shitomasi      FindShiTomasiScoreAtPoint (src/ShiTomasi.cc:34-63)
 //   k_minipatch      MiniPatch::SampleFromImage / FindPatch / SSDAtPoint (src/MiniPatch.cc:34-122)
+#include <cuda.h>
+
 #include "fe_types.cuh"
 
 namespace mcp {
@@ -528,6 +530,274 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
   if (lane == 0) res[i] = out;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_patch_search_tma: the same search, B200 data path.
+//   * The part of the target level a patch can touch -- the search disc plus the 8x8 patch plus the sub-pixel drift -- is ONE
+//     64 x 48 byte box.  Lane 0 fetches it with a 2-D TMA tile copy (cp.async.bulk.tensor.2d, SASS UTMALDG; pixels outside the
+//     image arrive as zeros) into the warp's shared-memory window and the warp waits on an mbarrier.  Candidate scoring and all
+//     sub-pixel iterations then read shared memory: no per-candidate unaligned global loads, no global round trip per iteration.
+//   * Candidates are first compacted (ballot) and then scored FOUR AT A TIME, eight lanes per candidate, one template row per
+//     lane -- three or thirty candidates keep the warp equally busy.
+//   Arithmetic, candidate order and tie-breaks are those of k_patch_search (bit-identical results); a request whose footprint
+//   does not fit the box (search range > 17 level pixels) is handled by that kernel's global-memory path.
+// ---------------------------------------------------------------------------------------------
+constexpr int PSW_W = 64, PSW_H = 48;
+
+__device__ __forceinline__ unsigned ps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct PsWin { const uint8_t* win; int x0, y0; const uint8_t* img; int pitch; };
+__device__ __forceinline__ int ps_pix(const PsWin& W, int x, int y)
+{
+  const int wx = x - W.x0, wy = y - W.y0;
+  if ((unsigned)wx < (unsigned)PSW_W && (unsigned)wy < (unsigned)PSW_H) return W.win[wy * PSW_W + wx];
+  return W.img[(size_t)y * W.pitch + x];                     // (a sub-pixel walk that left the window: never in practice)
+}
+
+__global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const CUtensorMap* __restrict__ tmaps, int target_slot, int n,
+                                                         const McpPatchReq* __restrict__ req, McpPatchRes* __restrict__ res, uint8_t* __restrict__ templ_out)
+{
+  __shared__ __align__(128) uint8_t s_win[4][PSW_W * PSW_H];
+  __shared__ __align__(8) unsigned long long s_bar[4];
+  __shared__ __align__(8) uint8_t s_t[4][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (i >= n) return;
+  const McpPatchReq rq = req[i];
+  McpPatchRes out;
+  out.template_bad = 1; out.found = 0; out.did_subpix = 0; out.score = 0; out.coarse_x = 0; out.coarse_y = 0;
+  out.found_x = 0; out.found_y = 0; out.n_candidates = 0; out.pad_ = 0;
+  const int max_ssd = 8 * 8 * 250;                                  // src/PatchFinder.cc:44,61
+  const bool args_ok = rq.src_kf >= 0 && rq.src_kf < fe.n_slots && rq.src_level >= 0 && rq.src_level < MCP_LEVELS &&
+                       rq.search_level >= 0 && rq.search_level < MCP_LEVELS;
+  if (!args_ok) { if (lane == 0) res[i] = out; return; }
+  // ---- the window of the target level: issued first, it lands while the template is being warped --------------------------
+  const FeLevel T = fe.kf[target_slot].lv[rq.search_level];
+  const int lsc = 1 << rq.search_level;
+  const int ipx = rq.exhaustive == 2 ? rq.pred_x : rq.pred_x / lsc, ipy = rq.exhaustive == 2 ? rq.pred_y : rq.pred_y / lsc;
+  const unsigned nRange = ((unsigned)rq.range + lsc - 1) / lsc;
+  PsWin W;
+  W.win = s_win[wid]; W.x0 = ipx - PSW_W / 2; W.y0 = ipy - PSW_H / 2; W.img = T.img; W.pitch = T.pitch;
+  if (lane == 0) {
+    const unsigned bar = ps_smem_u32(&s_bar[wid]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PSW_W * PSW_H) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(ps_smem_u32(s_win[wid])), "l"(tmaps + target_slot * MCP_LEVELS + rq.search_level), "r"(W.x0), "r"(W.y0), "r"(bar) : "memory");
+  }
+  __syncwarp();
+  // ---- template: MakeTemplateCoarseCont (unchanged arithmetic) -------------------------------------------------------------
+  const FeLevel S = fe.kf[rq.src_kf].lv[rq.src_level];
+  const double wi0 = rq.warp_inv[0], wi1 = rq.warp_inv[1], wi2 = rq.warp_inv[2], wi3 = rq.warp_inv[3];
+  const double det = __dsub_rn(__dmul_rn(wi0, wi3), __dmul_rn(wi1, wi2));
+  const double idet = __ddiv_rn(1.0, det);
+  const double ls = (double)lsc;
+  const double M0 = __dmul_rn(__dmul_rn(wi3, idet), ls), M1 = __dmul_rn(__dmul_rn(-wi1, idet), ls);
+  const double M2 = __dmul_rn(__dmul_rn(-wi2, idet), ls), M3 = __dmul_rn(__dmul_rn(wi0, idet), ls);
+  const double ax = M0, ay = M2, dx = M1, dy = M3;
+  const double p0x = __dsub_rn((double)rq.src_cx, __dadd_rn(__dmul_rn(M0, 4.0), __dmul_rn(M1, 4.0)));
+  const double p0y = __dsub_rn((double)rq.src_cy, __dadd_rn(__dmul_rn(M2, 4.0), __dmul_rn(M3, 4.0)));
+  double min_x = p0x, min_y = p0y, max_x = p0x, max_y = p0y;
+  if (ax < 0) min_x = __dadd_rn(min_x, __dmul_rn(8.0, ax)); else max_x = __dadd_rn(max_x, __dmul_rn(8.0, ax));
+  if (dx < 0) min_x = __dadd_rn(min_x, __dmul_rn(8.0, dx)); else max_x = __dadd_rn(max_x, __dmul_rn(8.0, dx));
+  if (ay < 0) min_y = __dadd_rn(min_y, __dmul_rn(8.0, ay)); else max_y = __dadd_rn(max_y, __dmul_rn(8.0, ay));
+  if (dy < 0) min_y = __dadd_rn(min_y, __dmul_rn(8.0, dy)); else max_y = __dadd_rn(max_y, __dmul_rn(8.0, dy));
+  const bool all_in = (min_x >= 0 && min_y >= 0 && max_x < S.w - 1 && max_y < S.h - 1);
+  const double crx = __dsub_rn(dx, __dmul_rn(8.0, ax)), cry = __dsub_rn(dy, __dmul_rn(8.0, ay));
+  const double xb = S.w - 1, yb = S.h - 1;
+  double px = p0x, py = p0y;
+  int n_out = 0;
+  uint8_t mine[2] = { 0, 0 };
+  for (int ii = 0; ii < 8; ++ii) {
+    for (int jj = 0; jj < 8; ++jj) {
+      const int k = ii * 8 + jj;
+      if ((k & 31) == lane) {
+        uint8_t v = 0;
+        if (all_in || (0 <= px && 0 <= py && px < xb && py < yb)) v = sample_u8(S, px, py, fe.transform_round);
+        else n_out++;
+        mine[k >> 5] = v;
+      }
+      px = __dadd_rn(px, ax); py = __dadd_rn(py, ay);
+    }
+    px = __dadd_rn(px, crx); py = __dadd_rn(py, cry);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
+  s_t[wid][lane] = mine[0]; s_t[wid][lane + 32] = mine[1];
+  __syncwarp();
+  if (templ_out) { templ_out[(size_t)i * 64 + lane] = mine[0]; templ_out[(size_t)i * 64 + 32 + lane] = mine[1]; }
+  const bool det_ok = isfinite(idet);
+  out.template_bad = (n_out > 0 || !det_ok) ? 1 : 0;
+  // (every lane must consume the TMA completion before the warp may leave: the copy targets this CTA's shared memory)
+  {
+    const unsigned bar = ps_smem_u32(&s_bar[wid]);
+    unsigned done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+  if (out.template_bad) { if (lane == 0) res[i] = out; return; }
+  int tsum = mine[0] + mine[1], tsq = mine[0] * mine[0] + mine[1] * mine[1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { tsum += __shfl_xor_sync(0xffffffffu, tsum, o); tsq += __shfl_xor_sync(0xffffffffu, tsq, o); }
+
+  // ---- FindPatchCoarse -----------------------------------------------------------------------------------------------------
+  const int n_corners = min(fe.kf[target_slot].meta->lv[rq.search_level].n_corners, fe.kf[target_slot].corner_cap);
+  int nTop = ipy - (int)nRange, nBottomPlusOne = ipy + (int)nRange + 1, nLeft = ipx - (int)nRange;
+  const int nRight = ipx + (int)nRange;
+  bool early = false;
+  if (nTop < 0) nTop = 0;
+  if (nTop >= T.h) early = true;
+  if (nBottomPlusOne <= 0) early = true;
+  if (nLeft < 0) nLeft = 0;
+  if (nLeft >= T.w) early = true;
+  int best_ssd = max_ssd + 1, best_idx = 0x7fffffff, best_x = 0, best_y = 0, n_valid = 0;
+  const int sub = lane & 7, grp = lane >> 3;
+  // eight lanes score one candidate (lane `sub` = template row), four candidates per pass; k = position in the reference's visiting order
+  auto score4 = [&](int cx, int cy, int k, bool valid) {
+    int isum = 0, isq = 0, cross = 0;
+    const bool inb = valid && (cx >= 4 && cy >= 4 && cx < T.w - 4 && cy < T.h - 4);
+    if (inb) {
+      const uint8_t* trow = s_t[wid] + 8 * sub;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int nn = ps_pix(W, cx - 4 + c, cy - 4 + sub), t = trow[c];
+        isum += nn; isq += nn * nn; cross += nn * t;
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { isum += __shfl_xor_sync(0xffffffffu, isum, o); isq += __shfl_xor_sync(0xffffffffu, isq, o); cross += __shfl_xor_sync(0xffffffffu, cross, o); }
+    if (valid && sub == 0) {
+      const int SA = tsum, SB = isum;
+      const int sc = inb ? ((2 * SA * SB - SA * SA - SB * SB) / 64 + isq + tsq - 2 * cross) : max_ssd + 1;
+      if (sc < best_ssd || (sc == best_ssd && k < best_idx)) { best_ssd = sc; best_idx = k; best_x = cx; best_y = cy; }
+    }
+  };
+  if (rq.exhaustive == 2) {
+    early = false; best_ssd = 0; best_x = rq.pred_x; best_y = rq.pred_y;
+  } else if (!early) {
+    if (rq.exhaustive) {
+      const int y_end = min(nBottomPlusOne, T.h), x_end = min(nRight + 1, T.w);
+      const int bw = x_end - nLeft, bh = y_end - nTop;
+      const int total = (bw > 0 && bh > 0) ? bw * bh : 0;
+      for (int k0 = 0; k0 < total; k0 += 4) {
+        const int k = k0 + grp;
+        const int y = nTop + k / max(bw, 1), x = nLeft + k % max(bw, 1);
+        const bool valid = k < total && !((unsigned)((ipx - x) * (ipx - x) + (ipy - y) * (ipy - y)) > nRange * nRange);
+        if (valid && sub == 0) n_valid++;
+        score4(x, y, k, valid);
+      }
+    } else {
+      const int i0 = T.row_lut[nTop];
+      const int i1 = nBottomPlusOne >= T.h ? n_corners : min(T.row_lut[nBottomPlusOne], n_corners);
+      // 32 corners of the list per step; the ones inside the disc are scored four at a time (group g takes the g-th of them)
+      for (int k0 = i0; k0 < i1; k0 += 32) {
+        const int k = k0 + lane;
+        int2 c = make_int2(0, 0);
+        bool ok = false;
+        if (k < i1) {
+          c = T.corners[k];
+          ok = !(c.x < nLeft || c.x > nRight) && !((unsigned)((ipx - c.x) * (ipx - c.x) + (ipy - c.y) * (ipy - c.y)) > nRange * nRange);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) n_valid += __popc(m);
+        while (m) {
+          const unsigned srcl = __fns(m, 0, grp + 1);               // lane holding this group's candidate, or ~0u
+          const bool valid = srcl != 0xffffffffu;
+          const int cx = __shfl_sync(0xffffffffu, c.x, valid ? srcl : 0), cy = __shfl_sync(0xffffffffu, c.y, valid ? srcl : 0);
+          score4(cx, cy, k0 + (int)srcl, valid);
+          for (int q = 0; q < 4 && m; q++) m &= m - 1;              // the four lowest are done
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int os = __shfl_xor_sync(0xffffffffu, best_ssd, o), oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+      const int ox = __shfl_xor_sync(0xffffffffu, best_x, o), oy = __shfl_xor_sync(0xffffffffu, best_y, o);
+      if (os < best_ssd || (os == best_ssd && oi < best_idx)) { best_ssd = os; best_idx = oi; best_x = ox; best_y = oy; }
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    }
+  }
+  out.score = best_ssd;
+  out.n_candidates = n_valid;
+  const bool found = !early && best_ssd < max_ssd;
+  if (!found) { if (early) out.score = max_ssd + 1; if (lane == 0) res[i] = out; return; }
+  out.found = 1;
+  out.coarse_x = best_x; out.coarse_y = best_y;
+  double posx = __dsub_rn(__dmul_rn(__dadd_rn((double)best_x, 0.5), (double)lsc), 0.5);
+  double posy = __dsub_rn(__dmul_rn(__dadd_rn((double)best_y, 0.5), (double)lsc), 0.5);
+  out.found_x = posx; out.found_y = posy;
+  if (rq.subpix_its <= 0) { if (lane == 0) res[i] = out; return; }
+  // ---- MakeSubPixTemplate + IterateSubPixToConvergence (mixed fp32/fp64, no contraction), pixels from the window -------------
+  out.did_subpix = 1;
+  float jxv[2] = { 0.f, 0.f }, jyv[2] = { 0.f, 0.f };
+  int tv[2] = { 0, 0 };
+  double H[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+  for (int h2 = 0; h2 < 2; h2++) {
+    const int k = lane + 32 * h2;
+    if (k < 36) {
+      const int yy = 1 + k / 6, xx = 1 + k % 6;
+      const uint8_t* t = s_t[wid];
+      const double gx = __dmul_rn(0.5, (double)((int)t[yy * 8 + xx + 1] - (int)t[yy * 8 + xx - 1]));
+      const double gy = __dmul_rn(0.5, (double)((int)t[(yy + 1) * 8 + xx] - (int)t[(yy - 1) * 8 + xx]));
+      jxv[h2] = (float)gx; jyv[h2] = (float)gy; tv[h2] = t[yy * 8 + xx];
+      const double g[3] = { gx, gy, 1.0 };
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) H[r * 3 + c] += g[r] * g[c];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; q++) { for (int o = 16; o > 0; o >>= 1) H[q] += __shfl_xor_sync(0xffffffffu, H[q], o); }
+  double Hinv[9];
+  toon_chol3_inverse(H, Hinv);
+  double mean_diff = 0.0;
+  int converged = 0;
+  for (int it = 0; it < rq.subpix_its; it++) {
+    const double cxl = __dsub_rn(__ddiv_rn(__dadd_rn(posx, 0.5), (double)lsc), 0.5);
+    const double cyl = __dsub_rn(__ddiv_rn(__dadd_rn(posy, 0.5), (double)lsc), 0.5);
+    const int rx = (int)(cxl > 0.0 ? __dadd_rn(cxl, 0.5) : __dsub_rn(cxl, 0.5));
+    const int ry = (int)(cyl > 0.0 ? __dadd_rn(cyl, 0.5) : __dsub_rn(cyl, 0.5));
+    if (!(rx >= 5 && ry >= 5 && rx < T.w - 5 && ry < T.h - 5)) { converged = 0; break; }
+    const double bx = __dsub_rn(cxl, 4.0), by = __dsub_rn(cyl, 4.0);
+    const double dX = __dsub_rn(bx, floor(bx)), dY = __dsub_rn(by, floor(by));
+    const float fMixTL = (float)__dmul_rn(__dsub_rn(1.0, dX), __dsub_rn(1.0, dY));
+    const float fMixTR = (float)__dmul_rn(dX, __dsub_rn(1.0, dY));
+    const float fMixBL = (float)__dmul_rn(__dsub_rn(1.0, dX), dY);
+    const float fMixBR = (float)__dmul_rn(dX, dY);
+    const int ibx = (int)bx, iby = (int)by;
+    double dd[2] = { 0, 0 };
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+      const int k = lane + 32 * h2;
+      if (k < 36) {
+        const int yy = 1 + k / 6, xx = 1 + k % 6;
+        const int X = ibx + xx, Y = iby + yy;
+        const float p00 = (float)ps_pix(W, X, Y), p01 = (float)ps_pix(W, X + 1, Y), p10 = (float)ps_pix(W, X, Y + 1), p11 = (float)ps_pix(W, X + 1, Y + 1);
+        const float fPixel = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fMixTL, p00), __fmul_rn(fMixTR, p01)), __fmul_rn(fMixBL, p10)), __fmul_rn(fMixBR, p11));
+        dd[h2] = __dadd_rn((double)__fsub_rn(fPixel, (float)tv[h2]), mean_diff);
+      }
+    }
+    double acc0 = 0, acc1 = 0, acc2 = 0;
+    for (int k = 0; k < 36; k++) {
+      const double dk = __shfl_sync(0xffffffffu, dd[k >> 5], k & 31);
+      const float jxk = __shfl_sync(0xffffffffu, jxv[k >> 5], k & 31), jyk = __shfl_sync(0xffffffffu, jyv[k >> 5], k & 31);
+      acc0 = __dadd_rn(acc0, __dmul_rn(dk, (double)jxk));
+      acc1 = __dadd_rn(acc1, __dmul_rn(dk, (double)jyk));
+      acc2 = __dadd_rn(acc2, dk);
+    }
+    double upd[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      upd[r] = __dadd_rn(__dadd_rn(__dmul_rn(Hinv[r * 3], acc0), __dmul_rn(Hinv[r * 3 + 1], acc1)), __dmul_rn(Hinv[r * 3 + 2], acc2));
+    posx = __dsub_rn(posx, __dmul_rn(upd[0], (double)lsc));
+    posy = __dsub_rn(posy, __dmul_rn(upd[1], (double)lsc));
+    mean_diff = __dsub_rn(mean_diff, upd[2]);
+    const double u2 = __dadd_rn(__dmul_rn(upd[0], upd[0]), __dmul_rn(upd[1], upd[1]));
+    if (u2 < 0.03 * 0.03) { converged = 1; break; }
+  }
+  if (!converged) out.found = 0;
+  else { out.found_x = posx; out.found_y = posy; }
+  if (lane == 0) res[i] = out;
+}
+
 // FindShiTomasiScoreAtPoint (src/ShiTomasi.cc:34-63, half box 3)
 __device__ __forceinline__ double shitomasi_at(const FeLevel& L, int cx, int cy)
 {
@@ -911,10 +1181,13 @@ int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s)
   k_fast_compact<<<(rows + 7) / 8, 256, 0, s>>>(kf, adaptive);
   return 4;
 }
-void fe_launch_patch_search(const FeDev& fe, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s)
+void fe_launch_patch_search(const FeDev& fe, const void* tmaps, bool all_fit_window, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s)
 {
   if (n <= 0) return;
-  k_patch_search<<<(n + 3) / 4, 128, 0, s>>>(fe, target, n, req, res, templ);
+  // tmaps: one CUtensorMap per (slot, level) or NULL (MCP_FE_TMA=0 / descriptor creation failed); all_fit_window: every request's
+  // footprint fits the 64 x 48 TMA box (decided on the host from the ranges)
+  if (tmaps && all_fit_window) k_patch_search_tma<<<(n + 3) / 4, 128, 0, s>>>(fe, reinterpret_cast<const CUtensorMap*>(tmaps), target, n, req, res, templ);
+  else k_patch_search<<<(n + 3) / 4, 128, 0, s>>>(fe, target, n, req, res, templ);
 }
 void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s)
 {
