@@ -41,7 +41,7 @@ struct McpFe {
   size_t out_block_bytes = 0;      // per slot: meta + luts + corners (contiguous, copied to the host in one go)
   std::vector<uint8_t*> out_block_dev;
   uint8_t* mask_dev[MCP_LEVELS] = { nullptr, nullptr, nullptr, nullptr };
-  void* tmaps_dev = nullptr;       // one CUtensorMap per (slot, level): 2-D tile descriptors of the level images (TMA window loads)
+  std::vector<CUtensorMap> tmaps;  // one per (slot, level): 2-D tile descriptors of the level images (TMA window loads); empty: not available
   uint8_t* gmask_dev[MCP_LEVELS] = { nullptr, nullptr, nullptr, nullptr };   // internal mask AND glare mask of the last frame (Level::lastMask)
   bool has_mask = false, glare = false;
   uint8_t* stage_img = nullptr;    // pinned
@@ -165,7 +165,7 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
   h->kf_dev = reinterpret_cast<FeKf*>(h->pool + o_kf);
   MCP_CUDA_CHECK(cudaMemcpyAsync(h->kf_dev, h->kf_host.data(), sizeof(FeKf) * S, cudaMemcpyHostToDevice, h->stream));
   {
-    // 2-D TMA descriptors (64 x 48 byte boxes) of every resident level image: the patch search fetches a patch's whole
+    // 2-D TMA descriptors (80 x 48 byte boxes) of every resident level image: the patch search fetches a patch's whole
     // footprint with one tile copy.  The encoder is a driver entry point (no libcuda link); MCP_FE_TMA=0 or any failure keeps
     // the global-memory kernel.
     static const bool off = [] { const char* e = getenv("MCP_FE_TMA"); return e && e[0] == '0'; }();
@@ -180,15 +180,12 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
         for (int l = 0; l < MCP_LEVELS && ok; l++) {
           const FeLevel& L = h->kf_host[s].lv[l];
           const cuuint64_t dims[2] = { (cuuint64_t)L.w, (cuuint64_t)L.h }, strides[1] = { (cuuint64_t)L.pitch };
-          const cuuint32_t box[2] = { 64, 48 }, estr[2] = { 1, 1 };
+          const cuuint32_t box[2] = { 80, 48 }, estr[2] = { 1, 1 };
           ok = reinterpret_cast<EncodeFn>(fn)(&maps[(size_t)s * MCP_LEVELS + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, L.img, dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
-      if (ok) {
-        MCP_CUDA_CHECK(cudaMalloc(&h->tmaps_dev, sizeof(CUtensorMap) * maps.size()));
-        MCP_CUDA_CHECK(cudaMemcpy(h->tmaps_dev, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
-      }
+      if (ok) h->tmaps.swap(maps);
     } else (void)cudaGetLastError();
   }
   h->req_dev = reinterpret_cast<McpPatchReq*>(h->pool + o_req);
@@ -214,7 +211,6 @@ int mcp_fe_destroy(McpFe* h)
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->pool) cudaFree(h->pool);
-  if (h->tmaps_dev) cudaFree(h->tmaps_dev);
   if (h->stage_img) cudaFreeHost(h->stage_img);
   if (h->stage_out) cudaFreeHost(h->stage_out);
   if (h->req_host) cudaFreeHost(h->req_host);
@@ -350,7 +346,7 @@ int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatch
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
   FeDev fe;
   fe.kf = h->kf_dev; fe.n_slots = (int)h->kf_host.size(); fe.transform_round = h->cfg.transform_round;
-  // the TMA kernel stages a 64 x 48 window around the prediction: disc radius + half patch + sub-pixel drift must fit 24 rows
+  // the TMA kernel stages an 80 x 48 window around the prediction: disc radius + half patch + sub-pixel drift must fit 24 rows
   bool fits = true;
   for (int i = 0; i < n && fits; i++) {
     const int lv = req[i].search_level;
@@ -358,7 +354,7 @@ int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatch
     const int nr = (req[i].range + (1 << lv) - 1) >> lv;
     fits = req[i].exhaustive == 2 || (req[i].range >= 0 && nr + 4 + 3 <= 24);
   }
-  fe_launch_patch_search(fe, h->tmaps_dev, fits, target_kf, n, h->req_dev, h->res_dev, h->templ_dev, s);
+  fe_launch_patch_search(fe, h->tmaps.empty() ? nullptr : h->tmaps.data(), fits, target_kf, n, h->req_dev, h->res_dev, h->templ_dev, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
   MCP_CUDA_CHECK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(McpPatchRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
 // ---------------------------------------------------------------------------------------------
 // k_patch_search_tma: the same search, B200 data path.
 //   * The part of the target level a patch can touch -- the search disc plus the 8x8 patch plus the sub-pixel drift -- is ONE
-//     64 x 48 byte box.  Lane 0 fetches it with a 2-D TMA tile copy (cp.async.bulk.tensor.2d, SASS UTMALDG; pixels outside the
+//     80 x 48 byte box (x origin rounded down to 16 bytes).  Lane 0 fetches it with a 2-D TMA tile copy (cp.async.bulk.tensor.2d, SASS UTMALDG; pixels outside the
 //     image arrive as zeros) into the warp's shared-memory window and the warp waits on an mbarrier.  Candidate scoring and all
 //     sub-pixel iterations then read shared memory: no per-candidate unaligned global loads, no global round trip per iteration.
 //   * Candidates are first compacted (ballot) and then scored FOUR AT A TIME, eight lanes per candidate, one template row per
@@ -541,10 +541,11 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
 //   Arithmetic, candidate order and tie-breaks are those of k_patch_search (bit-identical results); a request whose footprint
 //   does not fit the box (search range > 17 level pixels) is handled by that kernel's global-memory path.
 // ---------------------------------------------------------------------------------------------
-constexpr int PSW_W = 64, PSW_H = 48;
+constexpr int PSW_W = 80, PSW_H = 48;        // the box: its x origin must be 16-byte aligned (TMA tiled mode), hence 80 = 2 * 24 + 8 + 16 + 8 wide
 
 __device__ __forceinline__ unsigned ps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+struct PsMaps { CUtensorMap lv[MCP_LEVELS]; };       // the target slot's four level descriptors, passed as a __grid_constant__ parameter
 struct PsWin { const uint8_t* win; int x0, y0; const uint8_t* img; int pitch; };
 __device__ __forceinline__ int ps_pix(const PsWin& W, int x, int y)
 {
@@ -553,7 +554,7 @@ __device__ __forceinline__ int ps_pix(const PsWin& W, int x, int y)
   return W.img[(size_t)y * W.pitch + x];                     // (a sub-pixel walk that left the window: never in practice)
 }
 
-__global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const CUtensorMap* __restrict__ tmaps, int target_slot, int n,
+__global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid_constant__ PsMaps tmaps, int target_slot, int n,
                                                          const McpPatchReq* __restrict__ req, McpPatchRes* __restrict__ res, uint8_t* __restrict__ templ_out)
 {
   __shared__ __align__(128) uint8_t s_win[4][PSW_W * PSW_H];
@@ -576,14 +577,14 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const CUtens
   const int ipx = rq.exhaustive == 2 ? rq.pred_x : rq.pred_x / lsc, ipy = rq.exhaustive == 2 ? rq.pred_y : rq.pred_y / lsc;
   const unsigned nRange = ((unsigned)rq.range + lsc - 1) / lsc;
   PsWin W;
-  W.win = s_win[wid]; W.x0 = ipx - PSW_W / 2; W.y0 = ipy - PSW_H / 2; W.img = T.img; W.pitch = T.pitch;
+  W.win = s_win[wid]; W.x0 = ((ipx - 24) >> 4) << 4; W.y0 = ipy - PSW_H / 2; W.img = T.img; W.pitch = T.pitch;   // covers x in [ipx - 24, ipx + 24]
   if (lane == 0) {
     const unsigned bar = ps_smem_u32(&s_bar[wid]);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(PSW_W * PSW_H) : "memory");
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(ps_smem_u32(s_win[wid])), "l"(tmaps + target_slot * MCP_LEVELS + rq.search_level), "r"(W.x0), "r"(W.y0), "r"(bar) : "memory");
+                 ::"r"(ps_smem_u32(s_win[wid])), "l"(&tmaps.lv[rq.search_level]), "r"(W.x0), "r"(W.y0), "r"(bar) : "memory");
   }
   __syncwarp();
   // ---- template: MakeTemplateCoarseCont (unchanged arithmetic) -------------------------------------------------------------
@@ -1184,9 +1185,13 @@ int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s)
 void fe_launch_patch_search(const FeDev& fe, const void* tmaps, bool all_fit_window, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s)
 {
   if (n <= 0) return;
-  // tmaps: one CUtensorMap per (slot, level) or NULL (MCP_FE_TMA=0 / descriptor creation failed); all_fit_window: every request's
+  // tmaps: one CUtensorMap per (slot, level) in HOST memory or NULL (MCP_FE_TMA=0 / descriptor creation failed); all_fit_window: every request's
   // footprint fits the 64 x 48 TMA box (decided on the host from the ranges)
-  if (tmaps && all_fit_window) k_patch_search_tma<<<(n + 3) / 4, 128, 0, s>>>(fe, reinterpret_cast<const CUtensorMap*>(tmaps), target, n, req, res, templ);
+  if (tmaps && all_fit_window) {
+    PsMaps m;
+    memcpy(&m, reinterpret_cast<const CUtensorMap*>(tmaps) + (size_t)target * MCP_LEVELS, sizeof(m));     // tmaps: HOST array, [slot][level]
+    k_patch_search_tma<<<(n + 3) / 4, 128, 0, s>>>(fe, m, target, n, req, res, templ);
+  }
   else k_patch_search<<<(n + 3) / 4, 128, 0, s>>>(fe, target, n, req, res, templ);
 }
 void fe_launch_project(const DevCam& cam, const Se3& T, int n, const double* pw, const double* rw, const double* dw, McpProjRes* out, cudaStream_t s)
