@@ -68,7 +68,9 @@ void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, 
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
 void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
-void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s);
+void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s, int pick_sigma = 0);
+bool select_spec_possible(const BaDev& d);
+void launch_select_spec(const BaDev& d, int which, cudaStream_t s);
 void launch_tri_pack(double* const* full, int count, double* packed, int n, int tail, bool unpack, cudaStream_t s);
 struct P2pPeers { uint4* base[8]; };
 static inline size_t p2p_slice(size_t cnt, int world) { return (cnt + world - 1) / world; }   // as in ba_p2p.cu
@@ -132,6 +134,8 @@ struct McpBa {
     int chol_epoch = 0, chol_task_base = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
   cudaEvent_t ev_ready = nullptr, ev_red = nullptr, ev_ctrl = nullptr;
+  cudaStream_t sel_stream[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr };   // speculative sigma of every candidate's trial state
+  cudaEvent_t ev_bs[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr }, ev_sel[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr };
   cudaStream_t copy_stream = nullptr;   // control-block read-back that does not queue behind look-ahead kernels
   int n_spec_multi = 3;           // candidates per round when sharded over several GPUs (one grouped all-reduce per round)
   int n_spec = 3;                 // candidates per round (1 = no speculation)
@@ -204,6 +208,11 @@ static int ba_create_impl(const McpBaConfig* cfg, McpBa* h)
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ctrl, cudaEventDisableTiming));
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int q = 0; q < MAX_CAND; q++) {
+    MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->sel_stream[q], cudaStreamNonBlocking));
+    MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_bs[q], cudaEventDisableTiming));
+    MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_sel[q], cudaEventDisableTiming));
+  }
   for (int q = 1; q < MAX_CAND; q++) {
     MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cand[q].stream, cudaStreamNonBlocking));
     MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->cand[q].ev_done, cudaEventDisableTiming));
@@ -272,6 +281,11 @@ int mcp_ba_destroy(McpBa* h)
   if (h->ev_red) cudaEventDestroy(h->ev_red);
   if (h->ev_ctrl) cudaEventDestroy(h->ev_ctrl);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int q = 0; q < MAX_CAND; q++) {
+    if (h->sel_stream[q]) { cudaStreamSynchronize(h->sel_stream[q]); cudaStreamDestroy(h->sel_stream[q]); }
+    if (h->ev_bs[q]) cudaEventDestroy(h->ev_bs[q]);
+    if (h->ev_sel[q]) cudaEventDestroy(h->ev_sel[q]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MCP_OK;
@@ -419,7 +433,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   MCP_CUDA_CHECK(cudaMemsetAsync(h->b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
   h->chol_epoch = 0; h->chol_task_base = 0;
   {
-    const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1);
+    const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1) + sizeof(double) * MAX_CAND;
     if ((rc = h->b_sel.ensure(sel_bytes))) return rc;
     MCP_CUDA_CHECK(cudaMemsetAsync(h->b_sel.p, 0, sel_bytes, h->stream));
   }
@@ -459,6 +473,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.sel_state = h->b_sel.as<unsigned long long>();
   d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
   d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();
+  d.spec_sigma = reinterpret_cast<double*>(d.sel_done + 16);
   d.ctrl = h->b_ctrl.as<BaCtrl>(); d.outlier_flags = h->b_flags.as<int>();
 
   for (int q = 1; q < MAX_CAND; q++) {
@@ -751,6 +766,11 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   // host is still reading the control block back.  (Single GPU only: the multi-GPU path has collectives in between.)
   static const bool ahead_env = [] { const char* e = getenv("MCP_BA_LOOKAHEAD"); return !(e && e[0] == '0'); }();
   const bool can_look_ahead = ahead_env && !multi && !single_step && !h->profiling;
+  // Speculative sigma: the Huber sigma^2 of every candidate's trial state is computed next to the trial (own stream), so the
+  // next outer iteration does not start with a median selection on its critical path.  MCP_BA_SPEC_SIGMA=0 disables.
+  static const bool spec_env = [] { const char* e = getenv("MCP_BA_SPEC_SIGMA"); return !(e && e[0] == '0'); }();
+  const bool spec_sigma = spec_env && can_look_ahead && h->cfg.use_robust && select_spec_possible(d);
+  int spec_pending = 0;                                   // candidates whose speculative selection is in flight
   bool next_iteration_started = false;
   BaDev d_ahead = d;
   d_ahead.ahead = 1;
@@ -797,6 +817,8 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       // 2 or 3 candidates: ONE pass over the co-visibility lists reduces every candidate's camera system
       // (k_schur_pairs_multi); otherwise one reduction per candidate on its own stream
       const bool fused = h->fuse_schur && d.schur_mode == 1 && n_cand >= 2 && n_cand <= 3;
+      for (int q = 0; q < spec_pending; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));   // (their chi2 buffers are about to be rewritten)
+      spec_pending = 0;
       if (!first && !fused) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
       if (n_cand > 1 && !fused) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
       if (fused) {
@@ -840,6 +862,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       }
       { Prof p(h, C_SOLVE); TlScope t(h, "solve", 0, s); launch_chol_solve(d, ++h->chol_epoch, h->n_sms / n_cand, &h->chol_task_base, s); }
       { Prof p(h, C_BACKSUB); TlScope t(h, "backsub", 0, s); n_bs = launch_backsub_eval(d, 1, -1, nullptr, s); }
+      if (spec_sigma) {
+        MCP_CUDA_CHECK(cudaEventRecord(h->ev_bs[0], s));
+        MCP_CUDA_CHECK(cudaStreamWaitEvent(h->sel_stream[0], h->ev_bs[0], 0));
+        { TlScope t(h, "spec_select", 4, h->sel_stream[0]); launch_select_spec(d, (c.cur + 1) % N_STATE, h->sel_stream[0]); }
+        MCP_CUDA_CHECK(cudaEventRecord(h->ev_sel[0], h->sel_stream[0]));
+        h->launches++;
+      }
       for (int q = 1; q < n_cand; q++) {
         McpBa::Cand& cq = h->cand[q];
         parts.p[q] = cq.d.part;
@@ -856,6 +885,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         { TlScope t(h, "solve", q, cq.stream); launch_chol_solve(cq.d, ++cq.chol_epoch, h->n_sms / n_cand, &cq.chol_task_base, cq.stream); }
         { TlScope t(h, "backsub", q, cq.stream); launch_backsub_eval(cq.d, 1, -1, nullptr, cq.stream); }
         h->launches += 2;
+        if (spec_sigma) {
+          MCP_CUDA_CHECK(cudaEventRecord(h->ev_bs[q], cq.stream));
+          MCP_CUDA_CHECK(cudaStreamWaitEvent(h->sel_stream[q], h->ev_bs[q], 0));
+          { TlScope t(h, "spec_select", 4 + q, h->sel_stream[q]); launch_select_spec(cq.d, (c.cur + 1 + q) % N_STATE, h->sel_stream[q]); }
+          MCP_CUDA_CHECK(cudaEventRecord(h->ev_sel[q], h->sel_stream[q]));
+          h->launches++;
+        }
         if (multi) { launch_reduce_partials(cq.d, 0, n_bs, red + 3 * q, cq.stream); h->launches++; }
         MCP_CUDA_CHECK(cudaEventRecord(cq.ev_done, cq.stream));
         h->spec_rounds++;
@@ -870,6 +906,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       }
       { Prof p(h, C_CONTROL); TlScope t(h, "control", 0, s); launch_lm_control(d, parts, n_cand, n_lin, n_bs, multi ? red : nullptr, first ? 1 : 0, s); }
       first = false;
+      if (spec_sigma) spec_pending = n_cand;
       const bool ahead = can_look_ahead && it + 1 < n_iter;
       if (ahead) {
         // the control block is read back on a side stream so that the copy does not queue behind the look-ahead kernels
@@ -877,7 +914,11 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         MCP_CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_ctrl, 0));
         MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->copy_stream));
         // the sigma selection also clears the accumulators of the next linearisation
-        if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s, acc, h->acc_doubles); }
+        if (spec_sigma) {
+          for (int q = 0; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));
+          { TlScope t(h, "zero+sigma", 0, s); launch_zero_acc(d_ahead, acc, h->acc_doubles, s, 1); }
+          h->launches++;
+        } else if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s, acc, h->acc_doubles); }
         else { launch_zero_acc(d_ahead, acc, h->acc_doubles, s); h->launches++; }
         { TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s); }
         h->launches += 2;
@@ -899,6 +940,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     if (c.terminate) ok = false;
     if (c.conv_mag || c.conv_res) local_abort = true;
   }
+  for (int q = 0; q < spec_pending; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));
   MCP_CUDA_CHECK(cudaEventRecord(h->ev1, s));
   if (h->timeline) {
     cudaDeviceSynchronize();

@@ -717,7 +717,9 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   BaCtrl* ctrl = d.ctrl;
-  const int which = which_in < 0 ? ctrl->cur : which_in;
+  // which_in -2: the trial state of this launch's candidate (speculative sigma of the state that becomes current if the
+  // candidate is accepted; the control kernel has not run yet, so ctrl->cur is still the linearisation point)
+  const int which = which_in == -2 ? trial_buffer(d, ctrl->cur) : (which_in < 0 ? ctrl->cur : which_in);
   const double* __restrict__ v = d.chi2[which];
   const int n = d.n_meas;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -814,6 +816,7 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
     const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
     double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
     if (mode == 2) ctrl->median_out = med;                      // plain upper median (src/ChainBundle.cc:1434)
+    else if (mode == 3) { s = 1.345 * s; d.spec_sigma[d.cand] = s * s; }
     else if (mode == 0) {
       s = 1.345 * s;
       ctrl->sigma_sq_raw = s * s;
@@ -1070,6 +1073,7 @@ __global__ void __launch_bounds__(256) k_lm_control(BaDev d, CandParts parts, in
       c->current_chi = temp_chi;
       c->cur = (cur0 + 1 + cnd) % N_STATE;
       c->accepted = 1;
+      c->acc_cand = cnd;
     } else {
       c->lambda *= c->ni;
       c->ni *= 2;
@@ -1230,13 +1234,24 @@ static int lin_variant()
   return v;
 }
 // zeroes the linearisation accumulators [H0 | gc | red] (a memset that honours the look-ahead predicate)
-__global__ void k_zero_acc(BaDev d, double* acc, size_t n)
+__global__ void k_zero_acc(BaDev d, double* acc, size_t n, int pick_sigma)
 {
   pdl_prologue();
   if (lookahead_skip(d)) return;
+  if (pick_sigma && blockIdx.x == 0 && threadIdx.x == 0) {
+    // the outer iteration ended by accepting candidate acc_cand: its trial state is the new linearisation point and the
+    // Huber sigma^2 of that state was computed next to the trial (k_select_cluster mode 3).  RobustKernelData::RecomputeNow.
+    BaCtrl* c = d.ctrl;
+    if (c->accepted) {
+      const double raw = d.spec_sigma[c->acc_cand];
+      c->sigma_sq_raw = raw;
+      c->sigma_sq_lim = raw < c->min_sigma_sq ? c->min_sigma_sq : raw;
+      c->sigma_lim = sqrt(c->sigma_sq_lim);
+    }
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = 0.0;
 }
-void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s) { launch_chain(k_zero_acc, dim3(148), dim3(512), 0, s, d, acc, n); }
+void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s, int pick_sigma) { launch_chain(k_zero_acc, dim3(148), dim3(512), 0, s, d, acc, n, pick_sigma); }
 static void launch_pose_blocks(const BaDev& d, cudaStream_t s)
 {
   if (d.n_pb_items <= 0) return;
@@ -1279,12 +1294,18 @@ int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, dou
       (void)cudaGetLastError();                      // fall back to the multi-launch path
     }
   }
-  if (zero_n) launch_zero_acc(d, zero_ptr, zero_n, s);
+  if (zero_n) launch_zero_acc(d, zero_ptr, zero_n, s, 0);
   int grid = (d.n_meas + 2047) / 2048;
   if (grid < 1) grid = 1;
   if (grid > 148) grid = 148;
   for (int pass = 0; pass < SEL_PASSES; pass++) k_sel_pass<<<grid, 256, 0, s>>>(d, which, pass, mode);
   return SEL_PASSES;
+}
+// Huber sigma^2 of state buffer `which` (candidate d.cand's trial state) into d.spec_sigma[d.cand]; one-launch kernel only
+bool select_spec_possible(const BaDev& d) { return d.n_meas > 0 && d.n_meas <= SELC_CAP; }
+void launch_select_spec(const BaDev& d, int which, cudaStream_t s)
+{
+  launch_chain(k_select_cluster, dim3(SELC_CTAS), dim3(SELC_THREADS), SELC_SMEM, s, d, which, 3, (double*)nullptr, (size_t)0);
 }
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
 void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }

@@ -45,6 +45,8 @@ struct BaCtrl {
   int sel_n;          // number of values in the selection (global measurement count)
   int sel_rank;       // n/2
   int cand_used;      // candidates consumed by the last k_lm_control
+  int acc_cand;       // index of the candidate the last k_lm_control accepted (valid if accepted)
+  int pad_acc;
   int marg_fail;      // computeMarginals() failed (singular block)
   double median_out;  // plain upper median of the last mode-2 selection (point-depth covariances)
   double abort_agreed; // multi-GPU: sum over the ranks of their abort flags as of the last trial round (> 0: everybody stops)
@@ -104,6 +106,7 @@ struct BaDev {
   unsigned* sel_hist;            // [SEL_PASSES][SEL_BINS] radix-select histograms (self re-arming)
   unsigned* sel_done;            // [SEL_PASSES] ticket counters
   unsigned long long* sel_state; // [SEL_PASSES][2] prefix, rank
+  double* spec_sigma;            // [MAX_CAND] Huber sigma^2 (raw) of every candidate's trial state, computed speculatively (mode 3)
   BaCtrl* ctrl;
   int* outlier_flags;            // [n_meas] (sorted order)
   double* dbg;                   // optional debug output
