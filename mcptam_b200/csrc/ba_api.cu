@@ -44,7 +44,7 @@ bool pdl_enabled()
 }
 
 // launchers defined in ba_kernels.cu
-int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s);
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc = nullptr);
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr = nullptr, size_t zero_n = 0);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
@@ -66,7 +66,8 @@ void launch_pair_count(const BaDev& d, int* cnt, cudaStream_t s);
 void launch_pair_fill(const BaDev& d, int* cursor, int2* inc, cudaStream_t s);
 void launch_pair_items(const BaDev& d, int* cnt, int4* items, int* n_items_out, cudaStream_t s);
 void launch_schur_gather(const BaDev& d, cudaStream_t s);
-void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s);
+void launch_schur_multi(const BaDev& d, const SchurMulti& mc, cudaStream_t s, bool records_ready = false);
+void schur_multi_prepare(const BaDev& d, SchurMulti& mc);
 void launch_marginals(const BaDev& d, double* cov, cudaStream_t s);
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s, int pick_sigma = 0);
 bool select_spec_possible(const BaDev& d);
@@ -774,6 +775,28 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   bool next_iteration_started = false;
   BaDev d_ahead = d;
   d_ahead.ahead = 1;
+  // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
+  // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
+  const int n_cand = (single_step || h->profiling) ? 1 : (multi ? std::min(h->n_spec, h->n_spec_multi) : h->n_spec);
+  // 2 or 3 candidates: ONE pass over the co-visibility lists reduces every candidate's camera system
+  // (k_schur_pairs_multi); otherwise one reduction per candidate on its own stream
+  const bool fused = h->fuse_schur && d.schur_mode == 1 && n_cand >= 2 && n_cand <= 3;
+  const size_t sm_doubles = h->acc_doubles - h->off_Sm;
+  auto schur_args = [&](bool first_round) {
+    SchurMulti mc;
+    memset(&mc, 0, sizeof(mc));
+    mc.n_cand = n_cand; mc.R = h->b_R.as<double>(); mc.sm_doubles = sm_doubles;
+    mc.next_item = reinterpret_cast<int*>(mc.R + 36 * (size_t)std::max(d.n_pt, 1));
+    mc.Sm[0] = d.Sm; mc.rm[0] = d.rm;
+    mc.zero_mask = first_round ? 0 : 1;                  // candidate 0 shares the accumulator zeroed before the linearisation
+    for (int q = 1; q < n_cand; q++) { mc.Sm[q] = h->cand[q].d.Sm; mc.rm[q] = h->cand[q].d.rm; mc.zero_mask |= 1 << q; }
+    schur_multi_prepare(d, mc);
+    return mc;
+  };
+  // Fold: when lambda is already valid on the device (every linearisation but the first), the point records of the first
+  // trial round are formed by extra blocks of k_pose_blocks and k_schur_vinv_multi leaves the critical path.
+  static const bool fold_env = [] { const char* e = getenv("MCP_BA_FOLD_VINV"); return !(e && e[0] == '0'); }();
+  bool records_ready = false;
   for (int it = 0; it < n_iter && !local_abort && !aborted() && ok; it++) {
     if (!next_iteration_started) {
       if (it > 0) {
@@ -781,7 +804,10 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         if (h->cfg.use_robust) { Prof p(h, C_SELECT); TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
       }
       MCP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * h->acc_doubles, s));
-      { Prof p(h, C_LIN); TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s); h->launches++; }
+      const bool fold = fold_env && fused && !c.need_lambda_init;
+      const SchurMulti mcf = schur_args(true);
+      { Prof p(h, C_LIN); TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d, h->lin_warps, h->lin_smem, s, fold ? &mcf : nullptr); h->launches++; }
+      records_ready = fold;
     }
     next_iteration_started = false;
     if (multi) {
@@ -807,29 +833,18 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
       c.need_lambda_init = 0;
     }
     bool first = true;
-    const size_t sm_doubles = h->acc_doubles - h->off_Sm;
     for (;;) {
-      // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
-      // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
-      const int n_cand = (single_step || h->profiling) ? 1 : (multi ? std::min(h->n_spec, h->n_spec_multi) : h->n_spec);
       CandParts parts;
       for (int q = 0; q < MAX_CAND; q++) parts.p[q] = d.part;
-      // 2 or 3 candidates: ONE pass over the co-visibility lists reduces every candidate's camera system
-      // (k_schur_pairs_multi); otherwise one reduction per candidate on its own stream
-      const bool fused = h->fuse_schur && d.schur_mode == 1 && n_cand >= 2 && n_cand <= 3;
       for (int q = 0; q < spec_pending; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));   // (their chi2 buffers are about to be rewritten)
       spec_pending = 0;
       if (!first && !fused) MCP_CUDA_CHECK(cudaMemsetAsync(d.Sm, 0, sizeof(double) * sm_doubles, s));
       if (n_cand > 1 && !fused) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
       if (fused) {
-        SchurMulti mc;
-        memset(&mc, 0, sizeof(mc));
-        mc.n_cand = n_cand; mc.R = h->b_R.as<double>(); mc.sm_doubles = sm_doubles;
-        mc.next_item = reinterpret_cast<int*>(mc.R + 36 * (size_t)std::max(d.n_pt, 1));
-        mc.Sm[0] = d.Sm; mc.rm[0] = d.rm;
-        mc.zero_mask = first ? 0 : 1;                    // candidate 0 shares the accumulator zeroed before the linearisation
-        for (int q = 1; q < n_cand; q++) { mc.Sm[q] = h->cand[q].d.Sm; mc.rm[q] = h->cand[q].d.rm; mc.zero_mask |= 1 << q; }
-        { Prof p(h, C_SCHUR); TlScope t(h, "schur", 0, s); launch_schur_multi(d, mc, s); h->launches += 2; }
+        const SchurMulti mc = schur_args(first);
+        const bool ready = first && records_ready;
+        records_ready = false;
+        { Prof p(h, C_SCHUR); TlScope t(h, "schur", 0, s); launch_schur_multi(d, mc, s, ready); h->launches += ready ? 1 : 2; }
         if (!multi) MCP_CUDA_CHECK(cudaEventRecord(h->ev_ready, s));
       } else {
         Prof p(h, C_SCHUR); TlScope t(h, "schur", 0, s); launch_schur_gather(d, s); h->launches++;
@@ -920,7 +935,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
           h->launches++;
         } else if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s, acc, h->acc_doubles); }
         else { launch_zero_acc(d_ahead, acc, h->acc_doubles, s); h->launches++; }
-        { TlScope t(h, "linearize", 0, s); n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s); }
+        {
+          const bool fold = fold_env && fused;
+          const SchurMulti mcf = schur_args(true);
+          TlScope t(h, "linearize", 0, s);
+          n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s, fold ? &mcf : nullptr);
+          records_ready = fold;
+        }
         h->launches += 2;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
       } else if ((rc = sync_ctrl(h))) return rc;

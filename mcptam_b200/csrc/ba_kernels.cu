@@ -12,8 +12,10 @@
 //                       error evaluation.
 //   k_lm_control        accept / reject, lambda schedule, convergence actions (:1009-1118).
 #include "ba_types.cuh"
+#include "ba_vinv.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mcp {
 
@@ -432,12 +434,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 // observer/source cross block of one pose pair.  Lane = measurement; the 27 / 36 sums are warp-reduced and added
 // with one atomic per entry per item (items of one block are <= 128 measurements each).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pose_blocks(BaDev d)
+__global__ void __launch_bounds__(128) k_pose_blocks(BaDev d, SchurMulti mc, int n_pb_blocks)
 {
   pdl_prologue();
   if (lookahead_skip(d)) return;
+  if ((int)blockIdx.x >= n_pb_blocks) {
+    // extra blocks: the point records of the trial round that follows this linearisation (ba_vinv.cuh)
+    if (mc.n_cand == 2) schur_vinv_body<2>(d, mc, blockIdx.x - n_pb_blocks, gridDim.x - n_pb_blocks);
+    else schur_vinv_body<3>(d, mc, blockIdx.x - n_pb_blocks, gridDim.x - n_pb_blocks);
+    return;
+  }
   const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (n_pb_blocks * blockDim.x) >> 5;
   const int nc = d.nc;
   for (int it = gw; it < d.n_pb_items; it += nw) {
     const int4 item = d.pb_items[it];
@@ -1252,26 +1260,37 @@ __global__ void k_zero_acc(BaDev d, double* acc, size_t n, int pick_sigma)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = 0.0;
 }
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s, int pick_sigma) { launch_chain(k_zero_acc, dim3(148), dim3(512), 0, s, d, acc, n, pick_sigma); }
-static void launch_pose_blocks(const BaDev& d, cudaStream_t s)
+// mc != nullptr: the launch also forms the point records of the next trial round (lambda must already be valid on the device)
+static void launch_pose_blocks(const BaDev& d, cudaStream_t s, const SchurMulti* mc)
 {
-  if (d.n_pb_items <= 0) return;
+  if (d.n_pb_items <= 0 && !mc) return;
   int g = (d.n_pb_items + 3) / 4;
   if (g > 148 * 16) g = 148 * 16;
-  launch_chain(k_pose_blocks, dim3(g), dim3(128), 0, s, d);
+  if (g < 0) g = 0;
+  SchurMulti m;
+  memset(&m, 0, sizeof(m));
+  int extra = 0;
+  if (mc) {
+    m = *mc;
+    extra = (d.p_hi - d.p_lo + 127) / 128;
+    if (extra < 148) extra = 148;
+    if (extra > 148 * 4) extra = 148 * 4;
+  }
+  launch_chain(k_pose_blocks, dim3(g + extra), dim3(128), 0, s, d, m, g);
 }
-int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s)
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc)
 {
   const size_t stage = sizeof(double) * d.stage_doubles;
   if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
     const int g = per_point_grid(d, 4);
     launch_chain(k_linearize<128, 3>, dim3(g), dim3(128), smem / warps * 4 + stage, s, d);
-    launch_pose_blocks(d, s);
+    launch_pose_blocks(d, s, mc);
     return g;
   }
   const int g = per_point_grid(d, warps);
   if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) launch_chain(k_linearize<256, 2>, dim3(g), dim3(256), smem + stage, s, d);
   else launch_chain(k_linearize<256, 1>, dim3(g), dim3(warps * 32), smem + stage, s, d);
-  launch_pose_blocks(d, s);
+  launch_pose_blocks(d, s, mc);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)

@@ -12,22 +12,11 @@
 #include <cstdlib>
 
 #include "ba_types.cuh"
+#include "ba_vinv.cuh"
 
 namespace mcp {
 
 __device__ __forceinline__ int pair_id(int a, int b, int npv) { return a * npv - (a * (a - 1)) / 2 + (b - a); }
-
-__device__ __forceinline__ bool inv3_sym_s(const double* V6, double lambda, double* Vi)
-{
-  const double a = V6[0] + lambda, b = V6[1], c = V6[2], dd = V6[3] + lambda, e = V6[4], f = V6[5] + lambda;
-  const double c00 = dd * f - e * e, c01 = c * e - b * f, c02 = b * e - c * dd;
-  const double det = a * c00 + b * c01 + c * c02;
-  const double id = 1.0 / det;
-  Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id;
-  Vi[3] = Vi[1]; Vi[4] = (a * f - c * c) * id; Vi[5] = (b * c - a * e) * id;
-  Vi[6] = Vi[2]; Vi[7] = Vi[5]; Vi[8] = (a * dd - b * b) * id;
-  return (a > 0) && (a * dd - b * b > 0) && (det > 0) && isfinite(id);
-}
 
 // ---- load-time construction of the co-visibility lists ------------------------------------------------
 // one thread per (point, slot) entry x: the incidences (x, y >= x) of its point
@@ -306,53 +295,12 @@ __global__ void __launch_bounds__(TW * 32) k_schur_pairs_tma(BaDev d)
 // ---------------------------------------------------------------------------------------------
 constexpr int MG_CA = 16;                    // incidences per group of the cp.async variant
 constexpr int MRECD = 72;                    // doubles per staged incidence: W_A(18) W_B(18) R(36)
-constexpr int RPD = 36;                      // doubles per point record
 
 template <int NC>
 __global__ void __launch_bounds__(256) k_schur_vinv_multi(BaDev d, SchurMulti mc)
 {
   pdl_prologue();
-  double lam[NC];
-  {
-    double l = d.ctrl->lambda, ni = d.ctrl->ni;
-#pragma unroll
-    for (int c = 0; c < NC; c++) { lam[c] = l; l *= ni; ni *= 2; }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *mc.next_item = mc.first_dynamic_item;
-  // the reduced systems accumulate by atomics: clear them here instead of one memset per candidate in the stream
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-    if (mc.zero_mask & (1 << c))
-      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < mc.sm_doubles; i += (size_t)gridDim.x * blockDim.x) mc.Sm[c][i] = 0.0;
-  int fail = 0;
-  for (int p = d.p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < d.p_hi; p += gridDim.x * blockDim.x) {
-    if (d.pt_var[p] < 0) continue;
-    double V6[6], gp[3];
-#pragma unroll
-    for (int i = 0; i < 6; i++) V6[i] = d.V[6 * (size_t)p + i];
-#pragma unroll
-    for (int i = 0; i < 3; i++) gp[i] = d.gp[3 * (size_t)p + i];
-    double* R = mc.R + RPD * (size_t)p;
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      double Vi[9];
-      if (!inv3_sym_s(V6, lam[c], Vi)) fail |= 1 << c;
-#pragma unroll
-      for (int i = 0; i < 9; i++) R[9 * c + i] = Vi[i];
-#pragma unroll
-      for (int r = 0; r < 3; r++) R[27 + 3 * c + r] = Vi[3 * r] * gp[0] + Vi[3 * r + 1] * gp[1] + Vi[3 * r + 2] * gp[2];
-    }
-#pragma unroll
-    for (int c = NC; c < 3; c++) {
-#pragma unroll
-      for (int i = 0; i < 9; i++) R[9 * c + i] = 0.0;
-#pragma unroll
-      for (int r = 0; r < 3; r++) R[27 + 3 * c + r] = 0.0;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-    if (fail & (1 << c)) atomicExch(&d.ctrl->solve_ok[c], 0);
+  schur_vinv_body<NC>(d, mc, blockIdx.x, gridDim.x);
 }
 
 template <int NC, int MG>
@@ -845,7 +793,17 @@ static void launch_pairs_multi_tma(const BaDev& d, const SchurMulti& mc, cudaStr
   k_schur_pairs_multi<NC, MGT><<<g2, TW * 32, smem, s>>>(d, mc);
 }
 
-void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s)
+static int pairs_multi_grid(const BaDev& d)
+{
+  int g2 = (d.max_items + TW - 1) / TW;
+  if (g2 < 1) g2 = 1;
+  if (g2 > 148 * 3) g2 = 148 * 3;
+  return g2;
+}
+// first_dynamic_item of the cp.async pair kernel (every warp starts on its own index): needed by whoever forms the point records
+void schur_multi_prepare(const BaDev& d, SchurMulti& mc) { mc.first_dynamic_item = pairs_multi_grid(d) * TW; }
+
+void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s, bool records_ready)
 {
   // MCP_BA_SCHUR_STAGE: "ca" (default) = 16-byte cp.async pieces through the LSU; "tma8" / "tma16" = three bulk
   // copies per incidence, groups of 8 / 16 incidences (measured slower: profiles/README.md)
@@ -855,14 +813,15 @@ void launch_schur_multi(const BaDev& d, const SchurMulti& mc_in, cudaStream_t s)
     return (e[1] && e[2] && e[3] == '1') ? 1 : 0;
   }();
   SchurMulti mc = mc_in;
-  int g2 = (d.max_items + TW - 1) / TW;
-  if (g2 < 1) g2 = 1;
-  if (g2 > 148 * 3) g2 = 148 * 3;
+  const int g2 = pairs_multi_grid(d);
   mc.first_dynamic_item = g2 * TW;
-  int g1 = (d.p_hi - d.p_lo + 255) / 256;
-  if (g1 < 148) g1 = 148;
-  if (mc.n_cand == 2) launch_chain(k_schur_vinv_multi<2>, dim3(g1), dim3(256), 0, s, d, mc);
-  else launch_chain(k_schur_vinv_multi<3>, dim3(g1), dim3(256), 0, s, d, mc);
+  if (stage_mode != 2) records_ready = false;          // the bulk-copy variants do not use the work counter: keep their own launch
+  if (!records_ready) {
+    int g1 = (d.p_hi - d.p_lo + 255) / 256;
+    if (g1 < 148) g1 = 148;
+    if (mc.n_cand == 2) launch_chain(k_schur_vinv_multi<2>, dim3(g1), dim3(256), 0, s, d, mc);
+    else launch_chain(k_schur_vinv_multi<3>, dim3(g1), dim3(256), 0, s, d, mc);
+  }
   if (stage_mode == 0) {
     if (mc.n_cand == 2) launch_pairs_multi_tma<2, 8>(d, mc, s); else launch_pairs_multi_tma<3, 8>(d, mc, s);
     return;
