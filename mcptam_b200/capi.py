@@ -431,9 +431,10 @@ class FeHandle:
         cap = self.cfg.max_corners_per_level
         keep = []
         w, h = self.cfg.width, self.cfg.height
+        if getattr(self, "_kf_bufs", None) is None:          # corner / LUT landing buffers, allocated once per handle
+            self._kf_bufs = [(np.zeros((cap, 2), np.int32), np.zeros(h >> l, np.int32)) for l in range(4)]
         for l in range(4):
-            cor = np.zeros((cap, 2), np.int32)
-            lut = np.zeros(h, np.int32)
+            cor, lut = self._kf_bufs[l]
             im = np.zeros((h, w), np.uint8) if want_images else None
             mk = np.zeros((h, w), np.uint8) if want_masks else None
             keep.append((cor, lut, im, mk))
@@ -450,7 +451,7 @@ class FeHandle:
             cor, lut, im, mk = keep[l]
             n = outs[l].n_corners
             res.append({"width": outs[l].width, "height": outs[l].height, "n_corners": n, "corners": cor[:n].copy(),
-                        "row_lut": lut, "n_corners_total": outs[l].n_corners_total, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
+                        "row_lut": lut.copy(), "n_corners_total": outs[l].n_corners_total, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
                         "image": im, "last_mask": mk})
         return res
 

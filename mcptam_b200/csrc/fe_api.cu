@@ -13,6 +13,8 @@
 namespace mcp {
 void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s);
 int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s);
+bool fe_fast_fused();
+bool fe_zero_copy();
 void fe_launch_glare_mask(const FeKf& kf, const FeMasks& out, cudaStream_t s);
 void fe_launch_patch_search(const FeDev& fe, const void* tmaps, bool all_fit_window, int target, int n, const McpPatchReq* req, McpPatchRes* res, uint8_t* templ, cudaStream_t s);
 void fe_launch_shitomasi(const FeLevel& L, int n, const int2* xy, double* out, cudaStream_t s);
@@ -112,7 +114,7 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
     for (int l = 0; l < MCP_LEVELS; l++) {
       o_img[s * MCP_LEVELS + l] = take((size_t)h->lp[l] * (h->lh[l] + 2) + 64);
       o_score[s * MCP_LEVELS + l] = take((size_t)h->lp[l] * h->lh[l]);
-      o_rowcount[s * MCP_LEVELS + l] = take(sizeof(int) * h->lh[l]);
+      o_rowcount[s * MCP_LEVELS + l] = take(sizeof(int) * (32 * (size_t)h->lh[l] + 32));
     }
     o_hist[s] = take(sizeof(unsigned) * 32 * MCP_LEVELS);
     o_out[s] = take(h->out_block_bytes);
@@ -148,6 +150,7 @@ int mcp_fe_create(const McpFeConfig* cfg, McpFe** out)
       L.img = h->pool + o_img[s * MCP_LEVELS + l];
       L.score = h->pool + o_score[s * MCP_LEVELS + l];
       L.rowcount = reinterpret_cast<int*>(h->pool + o_rowcount[s * MCP_LEVELS + l]);
+      L.rowhist = L.rowcount;
       L.hist = reinterpret_cast<unsigned*>(h->pool + o_hist[s]) + 32 * l;
       L.mask = nullptr;
       L.row_lut = reinterpret_cast<int*>(ob + oo);
@@ -265,25 +268,34 @@ int mcp_fe_make_keyframe(McpFe* h, int32_t slot, const uint8_t* img, int32_t str
   cudaStream_t s = h->stream;
   const FeKf& kf = h->kf_host[slot];
   const int w = h->lw[0], hh = h->lh[0];
-  if (stride == w) memcpy(h->stage_img, img, (size_t)w * hh);
-  else for (int y = 0; y < hh; y++) memcpy(h->stage_img + (size_t)y * w, img + (size_t)y * stride, w);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[0], s));
-  MCP_CUDA_CHECK(cudaMemcpy2DAsync(kf.lv[0].img, kf.lv[0].pitch, h->stage_img, w, w, hh, cudaMemcpyHostToDevice, s));
-  MCP_CUDA_CHECK(cudaMemsetAsync(kf.lv[0].hist, 0, sizeof(unsigned) * 32 * MCP_LEVELS, s));
+  {
+    // the image goes through the pinned staging buffer in four bands: the upload of a band overlaps the host copy of the next
+    const int bands = hh >= 64 ? 4 : 1;
+    for (int b = 0; b < bands; b++) {
+      const int y0 = (int)((long long)hh * b / bands), y1 = (int)((long long)hh * (b + 1) / bands);
+      if (stride == w) memcpy(h->stage_img + (size_t)y0 * w, img + (size_t)y0 * w, (size_t)w * (y1 - y0));
+      else for (int y = y0; y < y1; y++) memcpy(h->stage_img + (size_t)y * w, img + (size_t)y * stride, w);
+      MCP_CUDA_CHECK(cudaMemcpy2DAsync(kf.lv[0].img + (size_t)y0 * kf.lv[0].pitch, kf.lv[0].pitch, h->stage_img + (size_t)y0 * w, w, w, y1 - y0, cudaMemcpyHostToDevice, s));
+    }
+  }
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
   fe_launch_pyramid(kf, h->cfg.halfsample_round, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
   int nl = 0;
+  // two-launch FAST: the kernels write meta / row LUT / corners to the device block AND to its pinned host mirror
+  const bool mirrored = fe_fast_fused() && fe_zero_copy();
+  FeKf kl = kf;
+  if (mirrored) kl.host_delta = (long long)(reinterpret_cast<char*>(h->stage_out) - reinterpret_cast<char*>(h->out_block_dev[slot]));
   if (h->glare) {
     // the frame's effective mask = internal mask AND (no pixel > 245 within the dilation footprint); FAST filters against it
     FeMasks gm;
-    FeKf kg = kf;
-    for (int l = 0; l < MCP_LEVELS; l++) { gm.m[l] = h->gmask_dev[l]; kg.lv[l].mask = h->gmask_dev[l]; }
+    for (int l = 0; l < MCP_LEVELS; l++) { gm.m[l] = h->gmask_dev[l]; kl.lv[l].mask = h->gmask_dev[l]; }
     fe_launch_glare_mask(kf, gm, s);
-    nl = 1 + fe_launch_fast(kg, h->cfg.adaptive_thresh, s);
-  } else nl = fe_launch_fast(kf, h->cfg.adaptive_thresh, s);
+    nl = 1 + fe_launch_fast(kl, h->cfg.adaptive_thresh, s);
+  } else nl = fe_launch_fast(kl, h->cfg.adaptive_thresh, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[3], s));
-  MCP_CUDA_CHECK(cudaMemcpyAsync(h->stage_out, h->out_block_dev[slot], h->out_block_bytes, cudaMemcpyDeviceToHost, s));
+  if (!mirrored) MCP_CUDA_CHECK(cudaMemcpyAsync(h->stage_out, h->out_block_dev[slot], h->out_block_bytes, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[4], s));
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));
   h->kf_valid[slot] = true;
@@ -342,7 +354,10 @@ int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatch
   cudaStream_t s = h->stream;
   memcpy(h->req_host, req, sizeof(McpPatchReq) * (size_t)n);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[0], s));
-  MCP_CUDA_CHECK(cudaMemcpyAsync(h->req_dev, h->req_host, sizeof(McpPatchReq) * (size_t)n, cudaMemcpyHostToDevice, s));
+  // the kernel reads the requests from the pinned host array (one uniform read per warp) and writes its results there:
+  // no copy-engine hop on either side of the launch (MCP_FE_ZEROCOPY=0: staged copies)
+  const bool req_direct = fe_zero_copy();
+  if (!req_direct) MCP_CUDA_CHECK(cudaMemcpyAsync(h->req_dev, h->req_host, sizeof(McpPatchReq) * (size_t)n, cudaMemcpyHostToDevice, s));
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[1], s));
   FeDev fe;
   fe.kf = h->kf_dev; fe.n_slots = (int)h->kf_host.size(); fe.transform_round = h->cfg.transform_round;
@@ -354,9 +369,11 @@ int mcp_fe_search_patches(McpFe* h, int32_t target_kf, int32_t n, const McpPatch
     const int nr = (req[i].range + (1 << lv) - 1) >> lv;
     fits = req[i].exhaustive == 2 || (req[i].range >= 0 && nr + 4 + 3 <= 24);
   }
-  fe_launch_patch_search(fe, h->tmaps.empty() ? nullptr : h->tmaps.data(), fits, target_kf, n, h->req_dev, h->res_dev, h->templ_dev, s);
+  // the kernel writes its results straight into the pinned (mapped) host array: no device->host copy behind it
+  const bool direct = fe_zero_copy();
+  fe_launch_patch_search(fe, h->tmaps.empty() ? nullptr : h->tmaps.data(), fits, target_kf, n, req_direct ? h->req_host : h->req_dev, direct ? h->res_host : h->res_dev, h->templ_dev, s);
   MCP_CUDA_CHECK(cudaEventRecord(h->ev[2], s));
-  MCP_CUDA_CHECK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(McpPatchRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (!direct) MCP_CUDA_CHECK(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(McpPatchRes) * (size_t)n, cudaMemcpyDeviceToHost, s));
   MCP_CUDA_CHECK(cudaStreamSynchronize(s));
   memcpy(res, h->res_host, sizeof(McpPatchRes) * (size_t)n);
   float t;

@@ -250,6 +250,217 @@ __global__ void __launch_bounds__(256) k_fast_compact(FeKf kf, int adaptive)
 }
 
 // ---------------------------------------------------------------------------------------------
+// FAST-10 in two launches (default; MCP_FE_FAST_FUSED=0 keeps the four-kernel path above).
+//   k_fast_score_rows  per 32x8 tile: the 38x14 footprint is staged with 16-byte loads (aligned 64-byte rows), the
+//                      FAST-10 test runs on compare masks, and the score of a corner -- the largest t at which it still is
+//                      one, libCVD's fast_corner_score_10 bisection -- is evaluated directly as
+//                          max over the 16 arcs of (min over the 10 ring pixels of the arc of +-(p - c)) - 1
+//                      (the criterion is monotone in t, so this is what the bisection converges to) with the 16-bit SIMD
+//                      min3/max3 instructions, bright and dark arcs side by side in one register.  Besides the level
+//                      histogram of capped scores (adaptive threshold, src/KeyFrame.cc:264-300) every tile adds its
+//                      corners that pass the mask to a per-ROW histogram; the last tile of a level (ticket counter) turns
+//                      the histogram into the threshold, the row histograms into row counts for that threshold, scans
+//                      them into Level::vCornerRowLUT and re-arms histogram, row histograms and ticket for the next frame.
+//   k_fast_compact4    one warp per row, four pixels per lane: ordered compaction into the raster-ordered corner list.
+// Both are launched with programmatic stream serialisation behind the pyramid kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT_LW = 64;                 // staged bytes per tile row: the aligned span [x0 - 16, x0 + 48)
+
+// the host mirror of a location in the slot's output block (pinned, mapped: the kernels write the results the host reads
+// straight into host memory, so no device->host copy follows them)
+template <typename T>
+__device__ __forceinline__ T* fe_mirror(const FeKf& kf, T* dev) { return reinterpret_cast<T*>(reinterpret_cast<char*>(dev) + kf.host_delta); }
+
+__device__ __forceinline__ unsigned pack_pm(int d) { return ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16); }   // (d, -d) as s16x2
+
+__device__ __forceinline__ int fast_score_direct(const int (&dv)[16])
+{
+  unsigned q[16], m3[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) q[i] = pack_pm(dv[i]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) m3[i] = __vimin3_s16x2(q[i], q[(i + 1) & 15], q[(i + 2) & 15]);
+  unsigned best = 0x80008000u;            // (-32768, -32768)
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const unsigned m9 = __vimin3_s16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+    const unsigned m10 = __vimin3_s16x2(m9, q[(i + 9) & 15], q[(i + 9) & 15]);
+    best = __vimax3_s16x2(best, m10, m10);
+  }
+  const int bright = (int)(short)(best & 0xffffu), dark = (int)(short)(best >> 16);
+  return max(bright, dark) - 1;
+}
+
+__global__ void __launch_bounds__(FT_W* FT_H) k_fast_score_rows(FeKf kf, int adaptive)
+{
+  pdl_prologue();
+  __shared__ __align__(16) uint8_t tile[FT_SH][FT_LW];
+  __shared__ unsigned hist[32];
+  __shared__ unsigned rowh[FT_H][32];
+  __shared__ int s_last, s_thr, carry;
+  __shared__ int wsum[8];
+  int l = 0;
+  while (l < MCP_LEVELS - 1 && (int)blockIdx.x >= kf.tile_off[l + 1]) l++;
+  const FeLevel L = kf.lv[l];
+  const int t = blockIdx.x - kf.tile_off[l];
+  const int tiles_x = (L.w + FT_W - 1) / FT_W;
+  const int x0 = (t % tiles_x) * FT_W, y0 = (t / tiles_x) * FT_H;
+  const int tid = threadIdx.y * FT_W + threadIdx.x;
+  if (tid < 32) hist[tid] = 0;
+  rowh[threadIdx.y][threadIdx.x] = 0;
+  if (tid < FT_SH * (FT_LW / 16)) {
+    const int sy = tid >> 2, ch = tid & 3;
+    const int gy = y0 + sy - 3, gx = x0 - 16 + 16 * ch;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch) v = *reinterpret_cast<const uint4*>(L.img + (size_t)gy * L.pitch + gx);
+    *reinterpret_cast<uint4*>(&tile[sy][16 * ch]) = v;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  const bool use_mask = adaptive && L.mask;
+  int score = 0;
+  if (x >= 3 && y >= 3 && x < L.w - 3 && y < L.h - 3) {
+    const int sx = threadIdx.x + 16, sy = threadIdx.y + 3;
+    const int c = tile[sy][sx];
+    const int b = MCP_MIN_FAST_THRESH;
+    const int cb = c + b, c_b = c - b;
+    int dv[16];
+    unsigned br = 0, dk = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int v = tile[sy + c_ring_dy[i]][sx + c_ring_dx[i]];
+      dv[i] = v - c;
+      br |= (unsigned)(v > cb) << i;
+      dk |= (unsigned)(v < c_b) << i;
+    }
+    if (has_run10(br) || has_run10(dk)) {
+      score = fast_score_direct(dv);                             // 5..254
+      atomicAdd(&hist[min(score, MCP_MAX_FAST_THRESH)], 1u);
+      if (!use_mask || L.mask[(size_t)y * L.pitch + x] == 255) {
+        // adaptive: binned by capped score (the threshold is not known yet); fixed threshold: bin 31 = kept
+        if (adaptive) atomicAdd(&rowh[threadIdx.y][min(score, MCP_MAX_FAST_THRESH)], 1u);
+        else if (score >= kf.fixed_thresh[l]) atomicAdd(&rowh[threadIdx.y][31], 1u);
+      }
+    }
+  }
+  if (x < L.w && y < L.h) L.score[(size_t)y * L.pitch + x] = (uint8_t)score;
+  __syncthreads();
+  if (tid < 32 && hist[tid]) atomicAdd(&L.hist[tid], hist[tid]);
+  {
+    const unsigned v = rowh[threadIdx.y][threadIdx.x];
+    if (v && y0 + (int)threadIdx.y < L.h) atomicAdd(reinterpret_cast<unsigned*>(L.rowhist) + (size_t)(y0 + threadIdx.y) * 32 + threadIdx.x, v);
+  }
+  __threadfence();
+  __syncthreads();
+  const int n_tiles = kf.tile_off[l + 1] - kf.tile_off[l];
+  if (tid == 0) s_last = (atomicAdd(L.rowhist + (size_t)L.h * 32, 1) == n_tiles - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last tile of the level: threshold, row counts, row LUT ---------------------------------------------------
+  __threadfence();
+  if (tid == 0) {
+    unsigned hh[32];
+    for (int i = 0; i < 32; i++) hh[i] = __ldcg(&L.hist[i]);
+    int thr;
+    if (adaptive) thr = fast_threshold(hh, L.w, L.h, kf.meta->lv[l].fast_freq);
+    else { thr = kf.fixed_thresh[l]; for (int i = 0; i <= 30; i++) kf.meta->lv[l].fast_freq[i] = 0; }
+    kf.meta->lv[l].fast_thresh = thr;
+    if (kf.host_delta) {
+      FeMetaLevel* mh = &fe_mirror(kf, kf.meta)->lv[l];
+      mh->fast_thresh = thr;
+      for (int i = 0; i <= 30; i++) mh->fast_freq[i] = kf.meta->lv[l].fast_freq[i];
+    }
+    s_thr = thr;
+    carry = 0;
+    L.rowhist[(size_t)L.h * 32] = 0;                             // ticket re-armed
+  }
+  __syncthreads();
+  if (tid < 32) L.hist[tid] = 0;
+  const int lo_bin = adaptive ? s_thr : 31;
+  for (int base = 0; base < L.h; base += FT_W * FT_H) {
+    const int yy = base + tid;
+    int v = 0;
+    if (yy < L.h) {
+      int4* rh = reinterpret_cast<int4*>(L.rowhist + (size_t)yy * 32);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int4 r = __ldcg(rh + k);
+        v += (4 * k + 0 >= lo_bin ? r.x : 0) + (4 * k + 1 >= lo_bin ? r.y : 0) + (4 * k + 2 >= lo_bin ? r.z : 0) + (4 * k + 3 >= lo_bin ? r.w : 0);
+        rh[k] = make_int4(0, 0, 0, 0);
+      }
+    }
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += u; }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < (tid >> 5); w++) off += wsum[w];
+    if (yy < L.h) {
+      L.row_lut[yy] = off + incl - v;
+      if (kf.host_delta) fe_mirror(kf, L.row_lut)[yy] = off + incl - v;
+    }
+    __syncthreads();
+    if (tid == FT_W * FT_H - 1) carry = off + incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    kf.meta->lv[l].n_corners = carry; kf.meta->lv[l].width = L.w; kf.meta->lv[l].height = L.h;
+    if (kf.host_delta) { FeMetaLevel* mh = &fe_mirror(kf, kf.meta)->lv[l]; mh->n_corners = carry; mh->width = L.w; mh->height = L.h; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fast_compact4(FeKf kf, int adaptive)
+{
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int l = 0;
+  while (l < MCP_LEVELS - 1 && row >= kf.row_off[l + 1]) l++;
+  const bool row_ok = row < kf.row_off[MCP_LEVELS];
+  const FeLevel L = kf.lv[l];
+  const int y = row_ok ? row - kf.row_off[l] : 0;
+  const int thr = kf.meta->lv[l].fast_thresh;
+  int pos = L.row_lut[y];
+  // empty rows are skipped (the LUT is an exclusive scan: equal neighbours = no corner in the row)
+  const bool work = row_ok && !(y + 1 < L.h && pos == L.row_lut[y + 1]);
+  const unsigned* sc = reinterpret_cast<const unsigned*>(L.score + (size_t)y * L.pitch);
+  const unsigned* mk = (adaptive && L.mask) ? reinterpret_cast<const unsigned*>(L.mask + (size_t)y * L.pitch) : nullptr;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int x0 = 0; work && x0 < L.w; x0 += 128) {
+    const int x = x0 + 4 * lane;
+    unsigned keep = 0;
+    if (x < L.w) {
+      const unsigned s4 = sc[x >> 2];
+      if (s4) {
+        const unsigned m4 = mk ? mk[x >> 2] : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int sv = (int)((s4 >> (8 * k)) & 255u);
+          const bool ok = sv >= thr && sv > 0 && ((m4 >> (8 * k)) & 255u) == 255u && x + k < L.w;
+          keep |= (unsigned)ok << k;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, keep != 0)) continue;
+    const unsigned b0 = __ballot_sync(0xffffffffu, keep & 1u), b1 = __ballot_sync(0xffffffffu, keep & 2u);
+    const unsigned b2 = __ballot_sync(0xffffffffu, keep & 4u), b3 = __ballot_sync(0xffffffffu, keep & 8u);
+    int idx = pos + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (keep & (1u << k)) { if (idx < kf.corner_cap) L.corners[idx] = make_int2(x + k, y); idx++; }
+    pos += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+  }
+  if (!kf.host_delta || !work) return;
+  // ---- host mirror: the warp ships its row's segment of the corner list to pinned host memory, 32 corners per store
+  // instruction (per-corner stores would cross PCIe as thousands of 8-byte writes) ---------------------------------------------
+  __syncwarp();
+  const int beg = L.row_lut[y], end = min(pos, kf.corner_cap);
+  int2* dst = fe_mirror(kf, L.corners);
+  for (int i = beg + lane; i < end; i += 32) dst[i] = __ldcg(&L.corners[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // patch search
 // ---------------------------------------------------------------------------------------------
 // 8 bytes at an arbitrary address via two aligned 8-byte loads
@@ -364,18 +575,26 @@ __global__ void __launch_bounds__(128) k_patch_search(FeDev fe, int target_slot,
   double px = p0x, py = p0y;
   int n_out = 0;
   uint8_t mine[2] = { 0, 0 };
+  // every lane replays the whole position sequence (the additions are order dependent) and keeps the positions of its two
+  // template pixels; the bilinear samples are then taken by all lanes at once (two global round trips per warp, not 64)
+  double qx[2] = { 0, 0 }, qy[2] = { 0, 0 };
+#pragma unroll
   for (int ii = 0; ii < 8; ++ii) {
+#pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int k = ii * 8 + jj;
-      if ((k & 31) == lane) {
-        uint8_t v = 0;
-        if (all_in || (0 <= px && 0 <= py && px < xb && py < yb)) v = sample_u8(S, px, py, fe.transform_round);
-        else n_out++;
-        mine[k >> 5] = v;
-      }
+      const bool me = (k & 31) == lane;
+      qx[k >> 5] = me ? px : qx[k >> 5]; qy[k >> 5] = me ? py : qy[k >> 5];
       px = __dadd_rn(px, ax); py = __dadd_rn(py, ay);
     }
     px = __dadd_rn(px, crx); py = __dadd_rn(py, cry);
+  }
+#pragma unroll
+  for (int h2 = 0; h2 < 2; h2++) {
+    uint8_t v = 0;
+    if (all_in || (0 <= qx[h2] && 0 <= qy[h2] && qx[h2] < xb && qy[h2] < yb)) v = sample_u8(S, qx[h2], qy[h2], fe.transform_round);
+    else n_out++;
+    mine[h2] = v;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
@@ -560,6 +779,7 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
   __shared__ __align__(128) uint8_t s_win[4][PSW_W * PSW_H];
   __shared__ __align__(8) unsigned long long s_bar[4];
   __shared__ __align__(8) uint8_t s_t[4][64];
+  __shared__ double s_terms[4][3][36];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = blockIdx.x * (blockDim.x >> 5) + wid;
   if (i >= n) return;
@@ -587,6 +807,21 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
                  ::"r"(ps_smem_u32(s_win[wid])), "l"(&tmaps.lv[rq.search_level]), "r"(W.x0), "r"(W.y0), "r"(bar) : "memory");
   }
   __syncwarp();
+  // ---- FindPatchCoarse bookkeeping: the corner-list range of the disc's rows and its first 32 corners are requested now
+  // (four dependent global round trips) and land while the template is being warped -------------------------------------------
+  const int n_corners = min(fe.kf[target_slot].meta->lv[rq.search_level].n_corners, fe.kf[target_slot].corner_cap);
+  int nTop = ipy - (int)nRange, nBottomPlusOne = ipy + (int)nRange + 1, nLeft = ipx - (int)nRange;
+  const int nRight = ipx + (int)nRange;
+  bool early = false;
+  if (nTop < 0) nTop = 0;
+  if (nTop >= T.h) early = true;
+  if (nBottomPlusOne <= 0) early = true;
+  if (nLeft < 0) nLeft = 0;
+  if (nLeft >= T.w) early = true;
+  const bool list_search = !early && rq.exhaustive == 0;
+  const int i0 = list_search ? T.row_lut[nTop] : 0;
+  const int i1 = list_search ? (nBottomPlusOne >= T.h ? n_corners : min(T.row_lut[nBottomPlusOne], n_corners)) : 0;
+  int2 c_next = (i0 + lane < i1) ? T.corners[i0 + lane] : make_int2(0, 0);
   // ---- template: MakeTemplateCoarseCont (unchanged arithmetic) -------------------------------------------------------------
   const FeLevel S = fe.kf[rq.src_kf].lv[rq.src_level];
   const double wi0 = rq.warp_inv[0], wi1 = rq.warp_inv[1], wi2 = rq.warp_inv[2], wi3 = rq.warp_inv[3];
@@ -609,18 +844,26 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
   double px = p0x, py = p0y;
   int n_out = 0;
   uint8_t mine[2] = { 0, 0 };
+  // every lane replays the whole position sequence (the additions are order dependent) and keeps the positions of its two
+  // template pixels; the bilinear samples are then taken by all lanes at once (two global round trips per warp, not 64)
+  double qx[2] = { 0, 0 }, qy[2] = { 0, 0 };
+#pragma unroll
   for (int ii = 0; ii < 8; ++ii) {
+#pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int k = ii * 8 + jj;
-      if ((k & 31) == lane) {
-        uint8_t v = 0;
-        if (all_in || (0 <= px && 0 <= py && px < xb && py < yb)) v = sample_u8(S, px, py, fe.transform_round);
-        else n_out++;
-        mine[k >> 5] = v;
-      }
+      const bool me = (k & 31) == lane;
+      qx[k >> 5] = me ? px : qx[k >> 5]; qy[k >> 5] = me ? py : qy[k >> 5];
       px = __dadd_rn(px, ax); py = __dadd_rn(py, ay);
     }
     px = __dadd_rn(px, crx); py = __dadd_rn(py, cry);
+  }
+#pragma unroll
+  for (int h2 = 0; h2 < 2; h2++) {
+    uint8_t v = 0;
+    if (all_in || (0 <= qx[h2] && 0 <= qy[h2] && qx[h2] < xb && qy[h2] < yb)) v = sample_u8(S, qx[h2], qy[h2], fe.transform_round);
+    else n_out++;
+    mine[h2] = v;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
@@ -641,15 +884,6 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
   for (int o = 16; o > 0; o >>= 1) { tsum += __shfl_xor_sync(0xffffffffu, tsum, o); tsq += __shfl_xor_sync(0xffffffffu, tsq, o); }
 
   // ---- FindPatchCoarse -----------------------------------------------------------------------------------------------------
-  const int n_corners = min(fe.kf[target_slot].meta->lv[rq.search_level].n_corners, fe.kf[target_slot].corner_cap);
-  int nTop = ipy - (int)nRange, nBottomPlusOne = ipy + (int)nRange + 1, nLeft = ipx - (int)nRange;
-  const int nRight = ipx + (int)nRange;
-  bool early = false;
-  if (nTop < 0) nTop = 0;
-  if (nTop >= T.h) early = true;
-  if (nBottomPlusOne <= 0) early = true;
-  if (nLeft < 0) nLeft = 0;
-  if (nLeft >= T.w) early = true;
   int best_ssd = max_ssd + 1, best_idx = 0x7fffffff, best_x = 0, best_y = 0, n_valid = 0;
   const int sub = lane & 7, grp = lane >> 3;
   // eight lanes score one candidate (lane `sub` = template row), four candidates per pass; k = position in the reference's visiting order
@@ -687,15 +921,14 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
         score4(x, y, k, valid);
       }
     } else {
-      const int i0 = T.row_lut[nTop];
-      const int i1 = nBottomPlusOne >= T.h ? n_corners : min(T.row_lut[nBottomPlusOne], n_corners);
-      // 32 corners of the list per step; the ones inside the disc are scored four at a time (group g takes the g-th of them)
+      // 32 corners of the list per step (the next 32 are already in flight); the ones inside the disc are scored four at a
+      // time (group g takes the g-th of them)
       for (int k0 = i0; k0 < i1; k0 += 32) {
         const int k = k0 + lane;
-        int2 c = make_int2(0, 0);
+        const int2 c = c_next;
+        if (k + 32 < i1) c_next = T.corners[k + 32];
         bool ok = false;
         if (k < i1) {
-          c = T.corners[k];
           ok = !(c.x < nLeft || c.x > nRight) && !((unsigned)((ipx - c.x) * (ipx - c.x) + (ipy - c.y) * (ipy - c.y)) > nRange * nRange);
         }
         unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -751,9 +984,11 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
   toon_chol3_inverse(H, Hinv);
   double mean_diff = 0.0;
   int converged = 0;
+  const double inv_lsc = 1.0 / (double)lsc;
   for (int it = 0; it < rq.subpix_its; it++) {
-    const double cxl = __dsub_rn(__ddiv_rn(__dadd_rn(posx, 0.5), (double)lsc), 0.5);
-    const double cyl = __dsub_rn(__ddiv_rn(__dadd_rn(posy, 0.5), (double)lsc), 0.5);
+    // LevelNPos: the division by the level scale (a power of two) is exact, so it is the multiplication by its reciprocal
+    const double cxl = __dsub_rn(__dmul_rn(__dadd_rn(posx, 0.5), inv_lsc), 0.5);
+    const double cyl = __dsub_rn(__dmul_rn(__dadd_rn(posy, 0.5), inv_lsc), 0.5);
     const int rx = (int)(cxl > 0.0 ? __dadd_rn(cxl, 0.5) : __dsub_rn(cxl, 0.5));
     const int ry = (int)(cyl > 0.0 ? __dadd_rn(cyl, 0.5) : __dsub_rn(cyl, 0.5));
     if (!(rx >= 5 && ry >= 5 && rx < T.w - 5 && ry < T.h - 5)) { converged = 0; break; }
@@ -776,14 +1011,26 @@ __global__ void __launch_bounds__(128) k_patch_search_tma(FeDev fe, const __grid
         dd[h2] = __dadd_rn((double)__fsub_rn(fPixel, (float)tv[h2]), mean_diff);
       }
     }
-    double acc0 = 0, acc1 = 0, acc2 = 0;
-    for (int k = 0; k < 36; k++) {
-      const double dk = __shfl_sync(0xffffffffu, dd[k >> 5], k & 31);
-      const float jxk = __shfl_sync(0xffffffffu, jxv[k >> 5], k & 31), jyk = __shfl_sync(0xffffffffu, jyv[k >> 5], k & 31);
-      acc0 = __dadd_rn(acc0, __dmul_rn(dk, (double)jxk));
-      acc1 = __dadd_rn(acc1, __dmul_rn(dk, (double)jyk));
-      acc2 = __dadd_rn(acc2, dk);
+    // v3Accum += diff * (jx, jy, 1) over the 36 pixels IN ORDER (fp64, order dependent): every lane forms its pixels' three
+    // terms, lanes 0..2 each add one component's 36 terms sequentially from shared memory, the sums are broadcast
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+      const int k = lane + 32 * h2;
+      if (k < 36) {
+        s_terms[wid][0][k] = __dmul_rn(dd[h2], (double)jxv[h2]);
+        s_terms[wid][1][k] = __dmul_rn(dd[h2], (double)jyv[h2]);
+        s_terms[wid][2][k] = dd[h2];
+      }
     }
+    __syncwarp();
+    double asum = 0;
+    if (lane < 3) {
+      const double* tr = s_terms[wid][lane];
+#pragma unroll
+      for (int k = 0; k < 36; k++) asum = __dadd_rn(asum, tr[k]);
+    }
+    __syncwarp();
+    const double acc0 = __shfl_sync(0xffffffffu, asum, 0), acc1 = __shfl_sync(0xffffffffu, asum, 1), acc2 = __shfl_sync(0xffffffffu, asum, 2);
     double upd[3];
 #pragma unroll
     for (int r = 0; r < 3; r++)
@@ -1172,9 +1419,27 @@ void fe_launch_pyramid(const FeKf& kf, int rnd, cudaStream_t s)
     }
   }
 }
+bool fe_fast_fused()
+{
+  static const bool on = [] { const char* e = getenv("MCP_FE_FAST_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+// MCP_FE_ZEROCOPY=0: results return through device->host copies instead of kernel stores into pinned host memory
+bool fe_zero_copy()
+{
+  static const bool on = [] { const char* e = getenv("MCP_FE_ZEROCOPY"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int fe_launch_fast(const FeKf& kf, int adaptive, cudaStream_t s)
 {
   dim3 blk(FT_W, FT_H);
+  if (fe_fast_fused()) {
+    const int rows = kf.row_off[MCP_LEVELS];
+    launch_chain(k_fast_score_rows, dim3(kf.tile_off[MCP_LEVELS]), blk, 0, s, kf, adaptive);
+    launch_chain(k_fast_compact4, dim3((rows + 7) / 8), dim3(256), 0, s, kf, adaptive);
+    return 2;
+  }
+  cudaMemsetAsync(kf.lv[0].hist, 0, sizeof(unsigned) * 32 * MCP_LEVELS, s);
   k_fast_score<<<kf.tile_off[MCP_LEVELS], blk, 0, s>>>(kf);
   const int rows = kf.row_off[MCP_LEVELS];
   k_fast_count<<<(rows + 7) / 8, 256, 0, s>>>(kf, adaptive);

@@ -11,7 +11,8 @@ struct FeLevel {
   const uint8_t* mask;   // [h][pitch] fixed mask pyramid (255 = usable) or nullptr
   int2* corners;         // [corner_cap] raster-ordered corners after threshold + mask
   int* row_lut;          // [h] Level::vCornerRowLUT
-  int* rowcount;         // [h]
+  int* rowcount;         // [h]   (four-kernel path; aliases rowhist)
+  int* rowhist;          // [h][32] per-row histogram of capped scores of the corners that pass the mask, + ticket at [h*32]; zero between frames
   unsigned* hist;        // [32] capped-score histogram
   int w, h, pitch, pad_;
 };
@@ -30,6 +31,7 @@ struct FeKf {
   int row_off[MCP_LEVELS + 1];    // prefix sums of image rows per level
   int fixed_thresh[MCP_LEVELS];
   int corner_cap, pad_;
+  long long host_delta;           // != 0: byte offset from this slot's device output block to its pinned host mirror (the two-launch FAST writes both)
 };
 
 struct FeMasks { unsigned char* m[MCP_LEVELS]; };   // per-level effective masks (pitch = the level's image pitch)
