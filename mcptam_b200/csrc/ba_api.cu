@@ -354,11 +354,12 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   const auto t_begin = std::chrono::steady_clock::now();
   BaPrep& pr = h->prep;
   {
-    // host threads for the marshalling passes: MCP_BA_HOST_THREADS, else half the cores shared between the ranks
+    // host threads for the marshalling passes: MCP_BA_HOST_THREADS, else three quarters of the cores (<= 12) shared between the ranks
     int want = 0;
     if (const char* e = getenv("MCP_BA_HOST_THREADS")) want = atoi(e);
-    if (want <= 0) want = std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / (2 * std::max(h->world, 1))));
+    if (want <= 0) want = std::min(12, std::max(1, (int)std::thread::hardware_concurrency() * 3 / (4 * std::max(h->world, 1))));
     if (!h->pool || h->pool->size() != want) h->pool.reset(new HostPool(want));
+    if (n_meas >= pr.par_min_meas) h->pool->prewake();            // (the workers are spinning by the time the first pass is dispatched)
   }
   int rc = MCP_OK;
 #define UP(buf, arr) if (rc == MCP_OK) rc = upload(h, buf, (arr).p, (arr).bytes())

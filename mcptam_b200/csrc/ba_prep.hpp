@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -46,15 +47,27 @@ class HostPool {
   void run(const std::function<void(int)>& f)
   {
     if (n_ == 1) { f(0); return; }
-    job_ = &f;
+    const unsigned long long next = gen_.load(std::memory_order_relaxed) + 1;
+    slot_[next & 1].store(&f, std::memory_order_release);
     remaining_.store(n_ - 1, std::memory_order_relaxed);
-    { std::lock_guard<std::mutex> lk(mu_); gen_.fetch_add(1, std::memory_order_release); }
+    { std::lock_guard<std::mutex> lk(mu_); gen_.store(next, std::memory_order_release); }
     cv_.notify_all();
     f(0);
     while (remaining_.load(std::memory_order_acquire) > 0) cpu_relax();
   }
+  // Takes the workers out of their sleep without giving them work: called at the start of a load, so that the first pass
+  // does not pay the wake-up latency of a condition variable (the workers then spin for kSpinUs waiting for the passes).
+  void prewake()
+  {
+    if (n_ == 1) return;
+    const unsigned long long next = gen_.load(std::memory_order_relaxed) + 1;
+    slot_[next & 1].store(nullptr, std::memory_order_release);
+    { std::lock_guard<std::mutex> lk(mu_); gen_.store(next, std::memory_order_release); }
+    cv_.notify_all();
+  }
 
  private:
+  static constexpr int kSpinUs = 500;       // longer than the serial stretches between two passes of one load
   static void cpu_relax()
   {
 #if defined(__x86_64__) || defined(__i386__)
@@ -68,18 +81,28 @@ class HostPool {
     unsigned long long last = 0;
     for (;;) {
       bool got = false;
-      for (int spin = 0; spin < 4000; spin++) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int spin = 0;; spin++) {
         if (gen_.load(std::memory_order_acquire) != last) { got = true; break; }
         cpu_relax();
+        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(kSpinUs)) break;
       }
       if (!got) {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != last; });
         if (stop_) return;
       }
-      last = gen_.load(std::memory_order_acquire);
-      (*job_)(tid);
-      remaining_.fetch_sub(1, std::memory_order_release);
+      // the job of generation g sits in slot g & 1, written before g is published and rewritten only while g + 2 is being
+      // prepared: the slot value is taken for g only if g is still the current generation after the read (otherwise retry
+      // with the newer one -- generations without a job, prewake(), can follow each other without waiting for the workers)
+      const unsigned long long cand = gen_.load(std::memory_order_acquire);
+      const std::function<void(int)>* job = slot_[cand & 1].load(std::memory_order_acquire);
+      if (gen_.load(std::memory_order_acquire) != cand) continue;
+      last = cand;
+      if (job) {
+        (*job)(tid);
+        remaining_.fetch_sub(1, std::memory_order_release);
+      }
     }
   }
   int n_;
@@ -88,7 +111,7 @@ class HostPool {
   std::condition_variable cv_;
   std::atomic<unsigned long long> gen_{ 0 };
   std::atomic<int> remaining_{ 0 };
-  const std::function<void(int)>* job_ = nullptr;
+  std::atomic<const std::function<void(int)>*> slot_[2] = { { nullptr }, { nullptr } };
   bool stop_ = false;
 };
 
@@ -149,6 +172,8 @@ struct BaPrep {
   PrepArr<PInt4> rs_items;
   // host-side results
   std::vector<int> meas_orig;     // sorted position -> original measurement index
+  std::vector<int> pb_cnt;        // pose-block key histograms / cursors, one row per thread
+  std::vector<int> thr_unsorted;  // per thread: its range of point indices is not non-decreasing
   std::vector<int> part_pt, part_meas;   // world+1 boundaries of the contiguous point partition
   int npv = 0, nptv = 0, n_slots = 0, max_slots = 1, rs_nblk = 1;
   long long n_inc = 0;            // co-visibility incidences of this rank: sum over its points of K(K+1)/2
@@ -193,6 +218,9 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
                       const std::function<void()>* after_points = nullptr)
 {
   o.err[0] = 0;
+  static const bool prep_trace = getenv("MCP_PREP_TRACE") != nullptr;
+  auto prep_t0 = std::chrono::steady_clock::now();
+#define PREP_TICK(name) do { if (prep_trace) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "PREP %-14s %8.1f us\n", name, std::chrono::duration<double, std::micro>(t1 - prep_t0).count()); prep_t0 = t1; } } while (0)
   const size_t np1 = (size_t)std::max(n_pt, 1), nm1 = (size_t)std::max(n_meas, 1);
   if (!o.pose_var.resize((size_t)n_pose, al) || !o.pt_var.resize(np1, al) || !o.pt_info.resize(np1, al) ||
       !o.pt_order.resize(np1, al) || !o.pt_meas_off.resize((size_t)n_pt + 1, al) || !o.pt_slot_off.resize((size_t)n_pt + 1, al) ||
@@ -210,16 +238,17 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     if (a < 0 || a >= n_pose || b >= n_pose) MCP_PREP_FAIL(PREP_INVALID, "point %d: chain index out of range", p);
     if (b >= 0 && !pose_fixed[b]) MCP_PREP_FAIL(PREP_UNSUPPORTED, "point %d: movable second chain link is not supported", p);
   }
-  // validation + histogram of measurements per point in one pass; the first offending measurement (in index order) is
-  // reported, as a sequential scan would.  Every thread histograms its own contiguous range of measurements into a
-  // private row (no atomics); the rows then turn into the cursors of a STABLE parallel counting sort: thread t's
-  // measurements of point p go behind those of threads < t.
+  // validation of the measurements in one parallel pass; the first offending measurement (in index order) is reported, as a
+  // sequential scan would.
   int* pmo = o.pt_meas_off.p;
   o.thr_bad.assign((size_t)T * 2, -1);
-  o.thr_hist.assign((size_t)T * ((size_t)n_pt + 1), 0);
+  o.thr_unsorted.assign((size_t)T, 0);
+  // Point-major input (what BundleAdjusterMulti::BundleAdjust produces: it walks the points and adds each point's
+  // measurements, src/BundleAdjusterMulti.cc:150-200) needs no sort at all.  The validation pass also finds out whether
+  // the point indices are non-decreasing; only if they are not does the counting sort below run.
   par([&](int t) {
-    int* hist = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
     const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+    int prev = lo > 0 ? meas_pt[lo - 1] : -1, unsorted = 0;
     for (int m = lo; m < hi; m++) {
       const int a = meas_chain[2 * m], b = meas_chain[2 * m + 1];
       int bad = 0;
@@ -229,8 +258,10 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       else if (meas_cam[m] < 0 || meas_cam[m] >= n_cam) bad = 4;
       else if (!(meas_noise[m] > 0)) bad = 5;
       if (bad) { o.thr_bad[2 * t] = m; o.thr_bad[2 * t + 1] = bad; return; }
-      hist[meas_pt[m]]++;
+      unsorted |= meas_pt[m] < prev;
+      prev = meas_pt[m];
     }
+    o.thr_unsorted[t] = unsorted;
   });
   for (int t = 0; t < T; t++) {
     const int m = o.thr_bad[2 * t];
@@ -243,26 +274,64 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       default: MCP_PREP_FAIL(PREP_INVALID, "measurement %d: noise must be > 0", m);
     }
   }
-  // offsets per point, and per (point, thread) the first position of that thread's measurements
-  {
-    int run = 0;
-    for (int p = 0; p < n_pt; p++) {
-      pmo[p] = run;
-      for (int t = 0; t < T; t++) { int& c = o.thr_hist[(size_t)t * ((size_t)n_pt + 1) + p]; const int v = c; c = run; run += v; }
-    }
-    pmo[n_pt] = run;
-  }
+  PREP_TICK("validate");
+  bool point_major = true;
+  for (int t = 0; t < T; t++) point_major = point_major && !o.thr_unsorted[t];
   o.meas_orig.resize((size_t)n_meas);
-  par([&](int t) {
-    int* cur = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
-    int* orig = o.meas_orig.data();
-    const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
-    for (int m = lo; m < hi; m++) orig[cur[meas_pt[m]]++] = m;
-  });
+  if (point_major) {
+    // pmo[p] = first measurement whose point index is >= p: every thread fills the offsets of the points that begin in its range
+    par([&](int t) {
+      const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+      int prev = lo > 0 ? meas_pt[lo - 1] : -1;
+      int* orig = o.meas_orig.data();
+      for (int m = lo; m < hi; m++) {
+        const int p = meas_pt[m];
+        for (int pp = prev + 1; pp <= p; pp++) pmo[pp] = m;
+        prev = p;
+        orig[m] = m;
+      }
+    });
+    for (int pp = (n_meas > 0 ? meas_pt[n_meas - 1] : -1) + 1; pp <= n_pt; pp++) pmo[pp] = n_meas;
+    PREP_TICK("offsets(sorted)");
+  } else {
+    // stable parallel counting sort by point: every thread histograms its own contiguous range of measurements into a
+    // private row (no atomics); the rows then turn into cursors: thread t's measurements of point p go behind those of threads < t
+    o.thr_hist.assign((size_t)T * ((size_t)n_pt + 1), 0);
+    par([&](int t) {
+      int* hist = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
+      const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+      for (int m = lo; m < hi; m++) hist[meas_pt[m]]++;
+    });
+    {
+      int run = 0;
+      for (int p = 0; p < n_pt; p++) {
+        pmo[p] = run;
+        for (int t = 0; t < T; t++) { int& c = o.thr_hist[(size_t)t * ((size_t)n_pt + 1) + p]; const int v = c; c = run; run += v; }
+      }
+      pmo[n_pt] = run;
+    }
+    PREP_TICK("offsets");
+    par([&](int t) {
+      int* cur = o.thr_hist.data() + (size_t)t * ((size_t)n_pt + 1);
+      int* orig = o.meas_orig.data();
+      const int lo = (int)((long long)n_meas * t / T), hi = (int)((long long)n_meas * (t + 1) / T);
+      for (int m = lo; m < hi; m++) orig[cur[meas_pt[m]]++] = m;
+    });
+  }
 
+  PREP_TICK("scatter");
   int nptv = 0;
   for (int p = 0; p < n_pt; p++) o.pt_var[p] = pt_fixed[p] ? -1 : nptv++;
   o.nptv = nptv;
+
+  o.part_pt.assign((size_t)world + 1, 0);
+  o.part_meas.assign((size_t)world + 1, 0);
+  partition_points(pmo, n_pt, world, o.part_pt.data());
+  for (int r = 0; r <= world; r++) o.part_meas[r] = pmo[o.part_pt[r]];
+  // pose-block keys of this rank's measurements are counted inside the per-point pass (one histogram row per thread)
+  const int pb_lo = o.part_meas[rank], pb_hi = o.part_meas[rank + 1];
+  const size_t pb_nv = (size_t)std::max(npv, 1), pb_keys = pb_nv * pb_nv;
+  o.pb_cnt.assign(pb_keys * (size_t)T, 0);
 
   // per point: the ascending list of movable poses that carry a Jacobian block of the point (its slots).  Threads take
   // measurement-balanced point ranges; the lists first go to a provisional place (point p at pmo[p] + p: a point has
@@ -294,6 +363,7 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     const int32_t* const in_cam = meas_cam;
     const int32_t* const in_ptchain = pt_chain;
     const int p_lo = o.thr_lo[t], p_hi = o.thr_lo[t + 1];
+    int* const kc = o.pb_cnt.data() + pb_keys * (size_t)t;
     int max_slots = 1;
     double last_noise = -1.0, last_info = 0.0;
     for (int p = p_lo; p < p_hi; p++) {
@@ -313,6 +383,10 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
         if (ov >= 0 && movable && stamp[ov] != p) { stamp[ov] = p; tmp.push_back(ov); }
         ma[q] = PInt4{ obs0, in_chain[2 * m + 1], in_cam[m], m };
         mb[q] = PInt4{ ov, -1, has_src ? 1 : 0, p };
+        if (ov >= 0 && q >= pb_lo && q < pb_hi) {
+          kc[(size_t)ov * pb_nv + ov]++;
+          if (has_src) kc[(size_t)std::min(ov, src_var) * pb_nv + std::max(ov, src_var)]++;
+        }
         mxy[q] = PDouble2{ in_xy[2 * m], in_xy[2 * m + 1] };
         const double nz = in_noise[m];
         if (nz != last_noise) { last_noise = nz; last_info = 1.0 / std::sqrt(nz); }
@@ -345,6 +419,7 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     }
     o.thr_max[t] = max_slots;
   });
+  PREP_TICK("per-point");
   o.pt_slot_off[0] = 0;
   for (int p = 0; p < n_pt; p++) o.pt_slot_off[p + 1] += o.pt_slot_off[p];
   const int n_slots = o.pt_slot_off[n_pt];
@@ -360,12 +435,9 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
   o.n_slots = n_slots; o.max_slots = max_slots;
   o.slot_var.n = o.slot_pt.n = (size_t)std::max(n_slots, 1);
   if (n_slots == 0) { o.slot_var[0] = 0; o.slot_pt[0] = 0; }
+  PREP_TICK("slots");
   if (after_points) (*after_points)();
-
-  o.part_pt.assign((size_t)world + 1, 0);
-  o.part_meas.assign((size_t)world + 1, 0);
-  partition_points(pmo, n_pt, world, o.part_pt.data());
-  for (int r = 0; r <= world; r++) o.part_meas[r] = pmo[o.part_pt[r]];
+  PREP_TICK("after_points");
 
   // visiting order of the per-point kernels: inside every rank's range, heaviest points first (stable counting sort
   // by descending measurement count)
@@ -393,52 +465,53 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     o.n_inc = n_inc;
   }
 
+  PREP_TICK("order+inc");
   // work lists of k_pose_blocks: this rank's measurements bucketed by the pose block they contribute to
   // ((v,v): observed from movable pose v; (lo,hi): observer / source pair), cut into items of <= 128 measurements.
-  // Counting sort over the npv^2 block keys; inside a block the measurements keep ascending position: every thread
-  // histograms a contiguous range of positions, the cursors are laid out key-major / thread-minor.
+  // Counting sort over the npv^2 block keys; inside a block the measurements keep ascending position: the per-point pass
+  // above left one histogram row per thread (thread t = the contiguous positions of its points), the cursors are laid out
+  // key-major / thread-minor and the fill pass walks the same ranges.
   {
-    const int m_lo = o.part_meas[rank], m_hi = o.part_meas[rank + 1];
-    const size_t nv = (size_t)std::max(npv, 1), n_keys = nv * nv;
-    const int TP = (T > 1 && m_hi - m_lo >= o.par_min_meas) ? T : 1;
-    std::vector<int>& cnt = o.key_cnt;
-    cnt.assign(n_keys * (size_t)TP, 0);
-    auto walk = [&](int t, auto&& emit) {
-      const int lo = m_lo + (int)((long long)(m_hi - m_lo) * t / TP), hi = m_lo + (int)((long long)(m_hi - m_lo) * (t + 1) / TP);
-      const PInt4* const mb = o.meas_b.p;
-      const PInt4* const pinfo = o.pt_info.p;
-      for (int q = lo; q < hi; q++) {
-        const int vo = mb[q].x;
-        if (vo < 0) continue;
-        emit((size_t)vo * nv + vo, q);
-        if (mb[q].z) {
-          const int vs = pinfo[mb[q].w].z;
-          emit((size_t)std::min(vo, vs) * nv + std::max(vo, vs), q);
-        }
-      }
-    };
-    auto count_pass = [&](int t) { if (t < TP) { int* c = cnt.data() + n_keys * (size_t)t; walk(t, [&](size_t key, int) { c[key]++; }); } };
-    if (TP > 1) pool->run(count_pass); else count_pass(0);
+    const size_t nv = pb_nv, n_keys = pb_keys;
+    std::vector<int>& cnt = o.pb_cnt;
     size_t n_ent = 0, n_items = 0;
     for (size_t k = 0; k < n_keys; k++) {
       const size_t b = n_ent;
-      for (int t = 0; t < TP; t++) { int& c = cnt[n_keys * (size_t)t + k]; const int v = c; c = (int)n_ent; n_ent += (size_t)v; }
+      for (int t = 0; t < T; t++) { int& c = cnt[n_keys * (size_t)t + k]; const int v = c; c = (int)n_ent; n_ent += (size_t)v; }
       n_items += (n_ent - b + PREP_PB_CHUNK - 1) / PREP_PB_CHUNK;
     }
     if (!o.pb_idx.resize(std::max(n_ent, (size_t)1), al) || !o.pb_items.resize(std::max(n_items, (size_t)1), al))
       MCP_PREP_FAIL(PREP_NOMEM, "mcp_ba_load: host staging allocation failed");
+    PREP_TICK("pb:cursors");
     size_t it = 0;
     for (size_t k = 0; k < n_keys; k++) {
       const int b = cnt[k], e = (k + 1 < n_keys) ? cnt[k + 1] : (int)n_ent;      // thread 0's cursor = start of the key
+      if (b == e) continue;
       const int lo = (int)(k / nv), hi = (int)(k % nv);
       for (int s2 = b; s2 < e; s2 += PREP_PB_CHUNK) o.pb_items[it++] = PInt4{ lo, hi, s2, std::min(s2 + PREP_PB_CHUNK, e) };
     }
     o.pb_items.n = it;                                     // 0 items is legal (nothing movable is observed)
-    auto fill_pass = [&](int t) { if (t < TP) { int* c = cnt.data() + n_keys * (size_t)t; int* const out = o.pb_idx.p; walk(t, [&](size_t key, int q) { out[c[key]++] = q; }); } };
-    if (TP > 1) pool->run(fill_pass); else fill_pass(0);
+    PREP_TICK("pb:items");
+    par([&](int t) {
+      int* c = cnt.data() + n_keys * (size_t)t;
+      int* const out = o.pb_idx.p;
+      const PInt4* const mb = o.meas_b.p;
+      const PInt4* const pinfo = o.pt_info.p;
+      const int lo = std::max(pmo[o.thr_lo[t]], pb_lo), hi = std::min(pmo[o.thr_lo[t + 1]], pb_hi);
+      for (int q = lo; q < hi; q++) {
+        const int vo = mb[q].x;
+        if (vo < 0) continue;
+        out[c[(size_t)vo * nv + vo]++] = q;
+        if (mb[q].z) {
+          const int vs = pinfo[mb[q].w].z;
+          out[c[(size_t)std::min(vo, vs) * nv + std::max(vo, vs)]++] = q;
+        }
+      }
+    });
     o.pb_idx.n = n_ent;
   }
 
+  PREP_TICK("pose-blocks");
   // work lists of k_schur_rows (MCP_BA_SCHUR=0): this rank's (point, slot) entries sorted by pose variable; entry =
   // {slot, number of slots from it to the end of its point}; groups of entries that fit one staging buffer; items =
   // runs of groups of one pose variable sized so that every resident warp gets about one item
@@ -489,5 +562,6 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
 }
 
 #undef MCP_PREP_FAIL
+#undef PREP_TICK
 
 }  // namespace mcp

@@ -35,6 +35,7 @@ int mcp_prep_run(int n_cam, int n_pose, const uint8_t* pose_fixed, int n_pt, con
   int rc = 0;
   double best = 1e300;
   for (int r = 0; r < (reps > 0 ? reps : 1); r++) {
+    g_pool->prewake();                                    // as mcp_ba_load does
     const auto t0 = std::chrono::steady_clock::now();
     rc = mcp::ba_prepare(g_prep, g_alloc, n_cam, n_pose, pose_fixed, n_pt, pt_chain, pt_fixed, n_meas, meas_xy, meas_chain,
                          meas_pt, meas_noise, meas_cam, rank, world, want_rows != 0, g_pool);

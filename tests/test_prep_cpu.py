@@ -79,13 +79,15 @@ def _restate(prob, rank, world):
                 pb_idx=np.asarray([q for _, q in keyed]), pb_items=np.asarray(items).reshape(-1, 4), n_inc=int((K * (K + 1) // 2).sum()))
 
 
+@pytest.mark.parametrize("shuffle", [True, False])
 @pytest.mark.parametrize("cfg,seed,world", [("tiny", 0, 1), ("tiny", 1, 2), ("cfg1", 0, 1), ("cfg1", 2, 3)])
-def test_layout_matches_restatement(cfg, seed, world):
+def test_layout_matches_restatement(cfg, seed, world, shuffle):
     prob = synth.make_ba_config(cfg, seed=seed)
-    # make the case less regular: shuffle the measurement order, fix a few points, fix a second pose
+    # make the case less regular: shuffle the measurement order (the counting-sort path; point-major input as
+    # BundleAdjusterMulti produces it takes the no-sort path), fix a few points, fix a second pose
     rng = np.random.default_rng(seed)
     prob = copy.copy(prob)
-    perm = rng.permutation(prob.n_meas)
+    perm = rng.permutation(prob.n_meas) if shuffle else np.arange(prob.n_meas)
     for k in ("meas_xy", "meas_chain", "meas_pt", "meas_noise", "meas_cam"):
         setattr(prob, k, np.ascontiguousarray(np.asarray(getattr(prob, k))[perm]))
     pf = np.array(prob.pt_fixed, copy=True)
@@ -106,13 +108,14 @@ def test_layout_matches_restatement(cfg, seed, world):
         assert np.array_equal(got["part_pt"], capi_partition(prob, world))
 
 
+@pytest.mark.parametrize("shuffle", [True, False])
 @pytest.mark.parametrize("threads", [2, 4, 7])
-def test_threaded_passes_give_identical_layout(threads):
+def test_threaded_passes_give_identical_layout(threads, shuffle):
     """the marshalling passes run on several host threads for large maps; the output does not depend on the count"""
     prob = synth.make_ba_config("cfg1", seed=1)
     rng = np.random.default_rng(5)
     prob = copy.copy(prob)
-    perm = rng.permutation(prob.n_meas)
+    perm = rng.permutation(prob.n_meas) if shuffle else np.arange(prob.n_meas)
     for k in ("meas_xy", "meas_chain", "meas_pt", "meas_noise", "meas_cam"):
         setattr(prob, k, np.ascontiguousarray(np.asarray(getattr(prob, k))[perm]))
     for world, rank in [(1, 0), (2, 1)]:
