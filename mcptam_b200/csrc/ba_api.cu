@@ -44,7 +44,7 @@ bool pdl_enabled()
 }
 
 // launchers defined in ba_kernels.cu
-int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc = nullptr);
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc = nullptr, double* zero_ptr = nullptr, size_t zero_n = 0);
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr = nullptr, size_t zero_n = 0);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
@@ -422,7 +422,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   const size_t ncp = (size_t)std::max(nc, 1);
   h->off_H0 = 0; h->off_gc = ncp * ncp; h->off_red = h->off_gc + ncp; h->off_Sm = h->off_red + 16; h->off_rm = h->off_Sm + ncp * ncp;
   h->acc_doubles = h->off_rm + ncp;
-  if ((rc = h->b_acc.ensure(sizeof(double) * h->acc_doubles))) return rc;
+  if ((rc = h->b_acc.ensure(sizeof(double) * 2 * h->acc_doubles))) return rc;          // two halves: see run_compute (double-buffered linearisation)
   if (h->world > 1 && (rc = h->b_pack.ensure(sizeof(double) * MAX_CAND * (ncp * (ncp + 1) / 2 + ncp + 16)))) return rc;
   if (h->world > 1 && (rc = p2p_setup(h, (size_t)n_meas, ncp))) return rc;
   if ((rc = h->b_dc.ensure(sizeof(double) * ncp))) return rc;
@@ -435,7 +435,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   MCP_CUDA_CHECK(cudaMemsetAsync(h->b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
   h->chol_epoch = 0; h->chol_task_base = 0;
   {
-    const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1) + sizeof(double) * MAX_CAND;
+    const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1) + sizeof(double) * 2 * MAX_CAND;
     if ((rc = h->b_sel.ensure(sel_bytes))) return rc;
     MCP_CUDA_CHECK(cudaMemsetAsync(h->b_sel.p, 0, sel_bytes, h->stream));
   }
@@ -448,7 +448,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     MCP_CUDA_CHECK(cudaMallocHost(&h->flags_host, sizeof(int) * (size_t)(n_meas + n_meas / 4 + 16)));
     h->flags_cap = (size_t)(n_meas + n_meas / 4 + 16);
   }
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_acc.p, 0, sizeof(double) * h->acc_doubles, h->stream));
+  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_acc.p, 0, sizeof(double) * 2 * h->acc_doubles, h->stream));
   MCP_CUDA_CHECK(cudaMemsetAsync(h->b_dc.p, 0, sizeof(double) * ncp, h->stream));
   MCP_CUDA_CHECK(cudaMemsetAsync(h->b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
 
@@ -476,6 +476,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   d.sel_hist = reinterpret_cast<unsigned*>(d.sel_state + 2 * (SEL_PASSES + 1));
   d.sel_done = d.sel_hist + SEL_PASSES * SEL_BINS; d.part = h->b_part.as<double>();
   d.spec_sigma = reinterpret_cast<double*>(d.sel_done + 16);
+  d.spec_med = d.spec_sigma + MAX_CAND;
   d.ctrl = h->b_ctrl.as<BaCtrl>(); d.outlier_flags = h->b_flags.as<int>();
 
   for (int q = 1; q < MAX_CAND; q++) {
@@ -706,10 +707,20 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   BaDev& d = h->d;
   BaCtrl& c = *h->ctrl_host;
   cudaStream_t s = h->stream;
-  double* acc = h->b_acc.as<double>();
-  double* red = acc + h->off_red;
+  double* const acc_base = h->b_acc.as<double>();
+  double* acc = acc_base;
+  double* red = acc_base + h->off_red;                 // (the scalar slots of half 0 serve both halves)
   const bool multi = h->world > 1;
   int rc;
+  // [H0 | gc | Sm | rm] exists twice.  With look-ahead the next outer iteration linearises into the other half, which
+  // k_pose_blocks cleared an iteration earlier: no clearing kernel between k_lm_control and k_linearize.
+  int ab = 0;
+  auto set_acc = [&](int b) {
+    acc = acc_base + (size_t)b * h->acc_doubles;
+    d.H0 = acc + h->off_H0; d.gc = acc + h->off_gc; d.Sm = acc + h->off_Sm; d.rm = acc + h->off_rm;
+    for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.H0 = d.H0; h->cand[q].d.gc = d.gc; }
+  };
+  set_acc(0);
   // Single GPU: the caller's flag is polled between trial rounds like the reference polls it between iterations.
   // Several ranks: every rank must take the same branch (each round issues collectives), so the flag is only ever acted
   // on through a value all ranks agreed on -- it rides on the per-round all-reduce of the trial sums (and on one
@@ -721,7 +732,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   { const char* e = getenv("MCP_BA_TIMELINE"); h->timeline = e && e[0] == '1'; }
   if ((rc = sync_ctrl(h))) return rc;
   c.need_lambda_init = 1; c.user_lambda = user_lambda; c.iter = 0; c.conv_mag = 0; c.conv_res = 0; c.total_trials = 0;
-  c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0; c.abort_agreed = 0;
+  c.terminate = 0; c.qmax = 0; for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1; c.stop_trials = 0; c.accepted = 0; c.n_outliers = 0; c.abort_agreed = 0; c.med_hint = 0;
   if ((rc = push_ctrl(h))) return rc;
   h->outliers.clear();
 
@@ -774,8 +785,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   const bool spec_sigma = spec_env && can_look_ahead && h->cfg.use_robust && select_spec_possible(d);
   int spec_pending = 0;                                   // candidates whose speculative selection is in flight
   bool next_iteration_started = false;
-  BaDev d_ahead = d;
-  d_ahead.ahead = 1;
+  if (can_look_ahead) MCP_CUDA_CHECK(cudaMemsetAsync(acc_base + h->acc_doubles, 0, sizeof(double) * h->acc_doubles, s));   // half 1 starts clean
   // speculate on the trials g2o would run after rejections of this one (lambda * ni, * 2ni, ...): most outer
   // iterations reject their first trial(s), so the candidates are evaluated concurrently on side streams
   const int n_cand = (single_step || h->profiling) ? 1 : (multi ? std::min(h->n_spec, h->n_spec_multi) : h->n_spec);
@@ -929,22 +939,28 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
         MCP_CUDA_CHECK(cudaEventRecord(h->ev_ctrl, s));
         MCP_CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_ctrl, 0));
         MCP_CUDA_CHECK(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(BaCtrl), cudaMemcpyDeviceToHost, h->copy_stream));
-        // the sigma selection also clears the accumulators of the next linearisation
+        // The next iteration linearises into the other accumulator half (clean since the iteration before this one) and its
+        // k_pose_blocks clears the half this iteration used.  With speculative sigma the linearisation itself adopts the
+        // accepted candidate's sigma^2: nothing runs between k_lm_control and k_linearize.
+        double* const used_half = acc;
+        set_acc(ab ^ 1);
+        BaDev d_ahead = d;
+        d_ahead.ahead = 1;
         if (spec_sigma) {
           for (int q = 0; q < n_cand; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));
-          { TlScope t(h, "zero+sigma", 0, s); launch_zero_acc(d_ahead, acc, h->acc_doubles, s, 1); }
-          h->launches++;
-        } else if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s, acc, h->acc_doubles); }
-        else { launch_zero_acc(d_ahead, acc, h->acc_doubles, s); h->launches++; }
+          d_ahead.pick_sigma = 1;
+        } else if (h->cfg.use_robust) { TlScope t(h, "select", 0, s); h->launches += launch_select_sigma(d_ahead, -1, 0, s); }
         {
           const bool fold = fold_env && fused;
           const SchurMulti mcf = schur_args(true);
           TlScope t(h, "linearize", 0, s);
-          n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s, fold ? &mcf : nullptr);
+          n_lin = launch_linearize(d_ahead, h->lin_warps, h->lin_smem, s, fold ? &mcf : nullptr, used_half, h->acc_doubles);
           records_ready = fold;
         }
         h->launches += 2;
         MCP_CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
+        // (the device skipped these launches unless this round closed the iteration by accepting a trial)
+        if (c.stop_trials && !c.terminate && !c.conv_mag && !c.conv_res) ab ^= 1; else set_acc(ab);
       } else if ((rc = sync_ctrl(h))) return rc;
       if (multi) agreed_abort = agreed_abort || c.abort_agreed > 0;
       if (c.cand_used > 1) h->spec_used++;

@@ -28,6 +28,13 @@ __device__ __forceinline__ void robustify(const BaCtrl* __restrict__ c, double e
   if (e2 <= c->sigma_sq_lim) { rho0 = fabs(e2); rho1 = 1.0; }
   else { const double e = sqrt(e2); rho0 = 2 * c->sigma_lim * e - c->sigma_sq_lim; rho1 = c->sigma_lim / e; }
 }
+// the same with the kernel's own copy of the Huber parameters (k_linearize may have picked them itself)
+__device__ __forceinline__ void robustify(bool use_robust, double sigma_sq_lim, double sigma_lim, double e2, double& rho0, double& rho1)
+{
+  if (!use_robust) { rho0 = e2; rho1 = 1.0; return; }
+  if (e2 <= sigma_sq_lim) { rho0 = fabs(e2); rho1 = 1.0; }
+  else { const double e = sqrt(e2); rho0 = 2 * sigma_lim * e - sigma_sq_lim; rho1 = sigma_lim / e; }
+}
 
 struct PtCtx {
   Se3 Bs;          // source MKF pose (base from world)
@@ -259,6 +266,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
   double* Wsm = smem + d.stage_doubles + (size_t)(wid * PPW + grp) * d.max_slots * 18;
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
+  // Huber parameters of this linearisation.  A look-ahead launch (d.pick_sigma) follows an accepted trial whose state is the
+  // new linearisation point: its sigma^2 was computed next to the trial (k_select_cluster mode 3) and is adopted here by
+  // every block for itself -- RobustKernelData::RecomputeNow -- block 0 also records it in the control block.
+  __shared__ double s_sig[2];
+  if (threadIdx.x == 0) {
+    double lim2 = ctrl->sigma_sq_lim, lim = ctrl->sigma_lim;
+    if (d.pick_sigma && ctrl->accepted) {
+      const double raw = d.spec_sigma[ctrl->acc_cand];
+      lim2 = raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : raw;
+      lim = sqrt(lim2);
+      if (blockIdx.x == 0) { BaCtrl* cw = d.ctrl; cw->sigma_sq_raw = raw; cw->sigma_sq_lim = lim2; cw->sigma_lim = lim; cw->med_hint = d.spec_med[ctrl->acc_cand]; }
+    }
+    s_sig[0] = lim2; s_sig[1] = lim;
+  }
+  __syncthreads();
+  const double sig_sq_lim = s_sig[0], sig_lim = s_sig[1];
+  const bool use_robust = ctrl->use_robust != 0;
   const double* pose;
   const DevCam* cams;
   stage_pose_cams(d, d.pose[cur], smem, pose, cams);
@@ -294,9 +318,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
       MeasGeom g;
       meas_geometry<true>(cams, pose, c, ma, z, g);
       double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
-      if (pvar < 0 && ctrl->use_robust) chi2 = -chi2;             // src/ChainBundle.cc:413-414
+      if (pvar < 0 && use_robust) chi2 = -chi2;                   // src/ChainBundle.cc:413-414
       double rho0, rho1;
-      robustify(ctrl, chi2, rho0, rho1);
+      robustify(use_robust, sig_sq_lim, sig_lim, chi2, rho0, rho1);
       chi_acc += rho0;
       const double w = rho1 * info;
       const double we0 = w * g.e[0], we1 = w * g.e[1];
@@ -434,10 +458,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
 // observer/source cross block of one pose pair.  Lane = measurement; the 27 / 36 sums are warp-reduced and added
 // with one atomic per entry per item (items of one block are <= 128 measurements each).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pose_blocks(BaDev d, SchurMulti mc, int n_pb_blocks)
+__global__ void __launch_bounds__(128) k_pose_blocks(BaDev d, SchurMulti mc, int n_pb_blocks, double* zero_ptr, size_t zero_n)
 {
   pdl_prologue();
   if (lookahead_skip(d)) return;
+  // the accumulators of the NEXT linearisation (the other half of the double-buffered [H0 | gc | Sm | rm]) are cleared here,
+  // off the critical path: nothing reads them any more once this linearisation has been accepted for execution
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += (size_t)gridDim.x * blockDim.x) zero_ptr[i] = 0.0;
   if ((int)blockIdx.x >= n_pb_blocks) {
     // extra blocks: the point records of the trial round that follows this linearisation (ba_vinv.cuh)
     if (mc.n_cand == 2) schur_vinv_body<2>(d, mc, blockIdx.x - n_pb_blocks, gridDim.x - n_pb_blocks);
@@ -742,7 +769,126 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   unsigned long long prefix = 0;
   unsigned rank = (unsigned)(n / 2);
   bool done = false;
-  for (int pass = 0; pass < SEL_PASSES && !done; pass++) {
+  // ---- bracket first ------------------------------------------------------------------------------------------------------
+  // The median moves little from one LM state to the next, so the one of the current state (ctrl->med_hint) brackets the
+  // wanted one: every CTA counts its keys below [0.9, 1.1) x hint and lists the keys inside (shared memory); after ONE
+  // cluster barrier CTA 0 pulls the few thousand listed keys into registers (distributed shared memory) and finishes the
+  // exact selection among them alone, on key - lo digits, with block barriers only.  If the wanted rank is not inside the
+  // bracket (or the lists overflow) nothing is lost: the keys are still in registers and the full passes below run.
+  bool fast_done = false;
+  unsigned long long fast_bits = 0;
+  {
+    const double hint = ctrl->med_hint;
+    if (mode != 2 && hint > 0.0 && hint < 1e300) {                   // uniform over the cluster (mode 2 selects over other data)
+      __shared__ unsigned s_cnt, s_below, s_fcount;
+      __shared__ unsigned long long s_fkey;
+      unsigned long long* list = reinterpret_cast<unsigned long long*>(copies);     // SELC_LIST keys (the replica area is idle now)
+      constexpr unsigned SELC_LIST = SELC_COPIES * SEL_BINS / 2;      // 8192
+      const unsigned long long lo_b = (unsigned long long)__double_as_longlong(hint * 0.9), hi_b = (unsigned long long)__double_as_longlong(hint * 1.1);
+      if (tid == 0) { s_cnt = 0; s_below = 0; }
+      __syncthreads();
+      unsigned below = 0, inb = 0;
+#pragma unroll
+      for (int k = 0; k < SELC_K; k++) { below += key[k] < lo_b; inb |= (unsigned)(key[k] >= lo_b && key[k] < hi_b) << k; }
+      // warp-aggregated append: one shared-memory atomic per warp
+      const unsigned mine = __popc(inb);
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned wbase = 0;
+      if (lane == 31 && wtot) wbase = atomicAdd(&s_cnt, wtot);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      unsigned at = wbase + incl - mine;
+#pragma unroll
+      for (int k = 0; k < SELC_K; k++)
+        if (inb & (1u << k)) { if (at < SELC_LIST) list[at] = key[k] - lo_b; at++; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+      if (lane == 0 && below) atomicAdd(&s_below, below);
+      cluster.sync();
+      // totals (every CTA reads the eight counter pairs: the verdict is uniform)
+      unsigned cnt_r[SELC_CTAS], tot = 0, bel = 0;
+      bool overflow = false;
+#pragma unroll
+      for (int r = 0; r < SELC_CTAS; r++) {
+        cnt_r[r] = *cluster.map_shared_rank(&s_cnt, r);
+        bel += *cluster.map_shared_rank(&s_below, r);
+        overflow |= cnt_r[r] > SELC_LIST;
+        tot += cnt_r[r];
+      }
+      const unsigned want = (unsigned)(n / 2);
+      const bool ok = !overflow && tot <= SELC_LIST && want >= bel && want - bel < tot;
+      if (ok) {
+        unsigned long long rel[SELC_LIST / SELC_THREADS];             // 8 listed keys per thread of CTA 0
+        if (crank == 0) {
+#pragma unroll
+          for (int j = 0; j < (int)(SELC_LIST / SELC_THREADS); j++) {
+            unsigned e = (unsigned)tid + (unsigned)j * SELC_THREADS;
+            rel[j] = ~0ull;
+            if (e < tot) {
+              int r = 0;
+              while (e >= cnt_r[r]) { e -= cnt_r[r]; r++; }
+              rel[j] = cluster.map_shared_rank(list, r)[e];
+            }
+          }
+        }
+        cluster.sync();                                             // the lists have been read: the other CTAs may leave
+        if (crank != 0) return;
+        // exact selection of rank (want - bel) among the listed keys, MSB first on the bits of (hi - lo)
+        const unsigned long long R = hi_b - lo_b;
+        const int nb = 64 - __clzll((long long)R);
+        unsigned long long fpre = 0;
+        unsigned frank = want - bel;
+        int consumed = 0;
+        bool single = false;
+        unsigned* fh = redh;
+        while (consumed < nb && !single) {
+          const int take = min(SEL_BITS, nb - consumed), shift = nb - consumed - take;
+          *reinterpret_cast<uint2*>(fh + 2 * tid) = make_uint2(0u, 0u);
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < (int)(SELC_LIST / SELC_THREADS); j++)
+            if (rel[j] != ~0ull && (rel[j] >> (shift + take)) == fpre) atomicAdd(&fh[(unsigned)(rel[j] >> shift) & ((1u << take) - 1u)], 1u);
+          __syncthreads();
+          const uint2 cc = *reinterpret_cast<const uint2*>(fh + 2 * tid);
+          const unsigned tsum = cc.x + cc.y;
+          unsigned inc2 = tsum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t; }
+          if (lane == 31) wsum[wid] = inc2;
+          __syncthreads();
+          unsigned wv = wsum[lane], winc = wv;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+          const unsigned woff = __shfl_sync(0xffffffffu, winc - wv, wid);
+          const unsigned excl = woff + inc2 - tsum;
+          if (frank >= excl && frank < excl + tsum) {
+            const bool first = frank < excl + cc.x;
+            s_fkey = (fpre << take) | (unsigned long long)(first ? 2 * tid : 2 * tid + 1);
+            s_rank = frank - (first ? excl : excl + cc.x);
+            s_fcount = first ? cc.x : cc.y;
+          }
+          __syncthreads();
+          fpre = s_fkey; frank = s_rank;
+          consumed += take;
+          single = s_fcount == 1u;
+          __syncthreads();
+        }
+        // fpre = the leading `consumed` bits of the wanted key - lo; all bits if the digits ran out, else exactly one listed key has them
+        if (consumed < nb) {
+#pragma unroll
+          for (int j = 0; j < (int)(SELC_LIST / SELC_THREADS); j++)
+            if (rel[j] != ~0ull && (rel[j] >> (nb - consumed)) == fpre) s_fkey = rel[j];
+          __syncthreads();
+          fpre = s_fkey;
+        }
+        fast_done = true;
+        fast_bits = fpre + lo_b;
+      }
+    }
+  }
+  for (int pass = 0; pass < SEL_PASSES && !done && !fast_done; pass++) {
     unsigned* h = redh + (pass & 1) * SEL_BINS;
     const int shift = 63 - SEL_BITS * (pass + 1);       // 52, 41, 30, 19, 8, -3
     if (pass == 0) {
@@ -808,9 +954,9 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
   }
   // `prefix` holds the leading bits of the wanted key.  If the passes ran to the end it is the whole key; otherwise
   // exactly one key in the cluster starts with it, and the thread that owns it finishes the job.
-  unsigned long long med_bits = prefix;
+  unsigned long long med_bits = fast_done ? fast_bits : prefix;
   bool owner = (crank == 0 && tid == 0);
-  if (done) {
+  if (done && !fast_done) {
     owner = false;
 #pragma unroll
     for (int k = 0; k < SELC_K; k++) {
@@ -818,9 +964,11 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
       if (key[k] != ~0ull && (key[k] >> s_prefix_shift) == prefix) { owner = true; med_bits = key[k]; }
     }
   }
-  cluster.sync();                                       // nobody leaves while its histogram may still be read
+  if (!fast_done) cluster.sync();                       // nobody leaves while its histogram may still be read
   if (owner) {
     const double med = __longlong_as_double((long long)med_bits);
+    if (mode == 0) ctrl->med_hint = med;
+    else if (mode == 3) d.spec_med[d.cand] = med;
     const size_t denom = (size_t)n * 2 - 6;                     // size_t arithmetic as in the reference
     double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
     if (mode == 2) ctrl->median_out = med;                      // plain upper median (src/ChainBundle.cc:1434)
@@ -1252,6 +1400,7 @@ __global__ void k_zero_acc(BaDev d, double* acc, size_t n, int pick_sigma)
     BaCtrl* c = d.ctrl;
     if (c->accepted) {
       const double raw = d.spec_sigma[c->acc_cand];
+      c->med_hint = d.spec_med[c->acc_cand];
       c->sigma_sq_raw = raw;
       c->sigma_sq_lim = raw < c->min_sigma_sq ? c->min_sigma_sq : raw;
       c->sigma_lim = sqrt(c->sigma_sq_lim);
@@ -1261,9 +1410,9 @@ __global__ void k_zero_acc(BaDev d, double* acc, size_t n, int pick_sigma)
 }
 void launch_zero_acc(const BaDev& d, double* acc, size_t n, cudaStream_t s, int pick_sigma) { launch_chain(k_zero_acc, dim3(148), dim3(512), 0, s, d, acc, n, pick_sigma); }
 // mc != nullptr: the launch also forms the point records of the next trial round (lambda must already be valid on the device)
-static void launch_pose_blocks(const BaDev& d, cudaStream_t s, const SchurMulti* mc)
+static void launch_pose_blocks(const BaDev& d, cudaStream_t s, const SchurMulti* mc, double* zero_ptr, size_t zero_n)
 {
-  if (d.n_pb_items <= 0 && !mc) return;
+  if (d.n_pb_items <= 0 && !mc && !zero_n) return;
   int g = (d.n_pb_items + 3) / 4;
   if (g > 148 * 16) g = 148 * 16;
   if (g < 0) g = 0;
@@ -1276,21 +1425,22 @@ static void launch_pose_blocks(const BaDev& d, cudaStream_t s, const SchurMulti*
     if (extra < 148) extra = 148;
     if (extra > 148 * 4) extra = 148 * 4;
   }
-  launch_chain(k_pose_blocks, dim3(g + extra), dim3(128), 0, s, d, m, g);
+  if (g + extra == 0) extra = 148;                     // (only the clearing to do)
+  launch_chain(k_pose_blocks, dim3(g + extra), dim3(128), 0, s, d, m, g, zero_ptr, zero_n);
 }
-int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc)
+int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc, double* zero_ptr, size_t zero_n)
 {
   const size_t stage = sizeof(double) * d.stage_doubles;
   if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
     const int g = per_point_grid(d, 4);
     launch_chain(k_linearize<128, 3>, dim3(g), dim3(128), smem / warps * 4 + stage, s, d);
-    launch_pose_blocks(d, s, mc);
+    launch_pose_blocks(d, s, mc, zero_ptr, zero_n);
     return g;
   }
   const int g = per_point_grid(d, warps);
   if (lin_variant() == 2 && warps == 8 && smem + stage <= 100 * 1024) launch_chain(k_linearize<256, 2>, dim3(g), dim3(256), smem + stage, s, d);
   else launch_chain(k_linearize<256, 1>, dim3(g), dim3(warps * 32), smem + stage, s, d);
-  launch_pose_blocks(d, s, mc);
+  launch_pose_blocks(d, s, mc, zero_ptr, zero_n);
   return g;
 }
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s)

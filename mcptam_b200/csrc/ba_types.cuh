@@ -49,6 +49,7 @@ struct BaCtrl {
   int pad_acc;
   int marg_fail;      // computeMarginals() failed (singular block)
   double median_out;  // plain upper median of the last mode-2 selection (point-depth covariances)
+  double med_hint;     // median |chi2| of the current state (0: unknown): centre of the bracket k_select_cluster tries first
   double abort_agreed; // multi-GPU: sum over the ranks of their abort flags as of the last trial round (> 0: everybody stops)
 };
 
@@ -74,6 +75,7 @@ struct BaDev {
   double* chi2[N_STATE];              // [n_meas] signed as EdgeChainMeas::chi2
   int cand, ahead;               // speculative candidate index of this launch (c: lambda after c rejections); ahead = 1: this launch
                                  // was enqueued before the host knew the trial loop ended (see next_iteration_started)
+  int pick_sigma, pad_pick;      // look-ahead linearisation: take the Huber sigma^2 of the accepted candidate from spec_sigma (k_linearize prologue)
   double* V;                     // [n_pt*6]  upper triangle of J_pt^T W J_pt
   double* gp;                    // [n_pt*3]
   double* W;                     // [n_slots*18] 6x3 row-major
@@ -107,6 +109,7 @@ struct BaDev {
   unsigned* sel_done;            // [SEL_PASSES] ticket counters
   unsigned long long* sel_state; // [SEL_PASSES][2] prefix, rank
   double* spec_sigma;            // [MAX_CAND] Huber sigma^2 (raw) of every candidate's trial state, computed speculatively (mode 3)
+  double* spec_med;              // [MAX_CAND] the medians they come from
   BaCtrl* ctrl;
   int* outlier_flags;            // [n_meas] (sorted order)
   double* dbg;                   // optional debug output
