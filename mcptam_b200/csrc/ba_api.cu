@@ -48,6 +48,7 @@ int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, con
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr = nullptr, size_t zero_n = 0);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
+int launch_robust_sum(const BaDev& d, int which, cudaStream_t s);
 void launch_lambda_init(const BaDev& d, cudaStream_t s);
 void launch_lambda_apply(const BaDev& d, cudaStream_t s);
 void launch_chol_solve(const BaDev& d, int epoch, int max_ctas, int* task_base, cudaStream_t s);
@@ -145,7 +146,7 @@ struct McpBa {
   int chol_epoch = 0, chol_task_base = 0, n_sms = 148;
   size_t acc_doubles = 0, off_H0 = 0, off_gc = 0, off_red = 0, off_Sm = 0, off_rm = 0;
   BaCtrl* ctrl_host = nullptr;   // pinned
-  double* abort_word = nullptr;  // pinned [2]: this rank's abort flag for the next round, the all-reduced one of the last round
+  double* abort_word = nullptr;  // pinned [4]: this rank's abort flag for the next round, the all-reduced one of the last round, chi2 before / after
   int* flags_host = nullptr;     // pinned, n_meas
   size_t flags_cap = 0;
   BaPrep prep;                   // host marshalling output in pinned memory, pooled across loads
@@ -227,8 +228,8 @@ static int ba_create_impl(const McpBaConfig* cfg, McpBa* h)
   MCP_CUDA_CHECK(cudaEventCreate(&h->ev1));
   MCP_CUDA_CHECK(cudaMallocHost(&h->ctrl_host, sizeof(BaCtrl)));
   memset(h->ctrl_host, 0, sizeof(BaCtrl));
-  MCP_CUDA_CHECK(cudaMallocHost(&h->abort_word, 2 * sizeof(double)));
-  h->abort_word[0] = h->abort_word[1] = 0;
+  MCP_CUDA_CHECK(cudaMallocHost(&h->abort_word, 4 * sizeof(double)));
+  h->abort_word[0] = h->abort_word[1] = h->abort_word[2] = h->abort_word[3] = 0;
   memset(&h->d, 0, sizeof(h->d));
   memset(&h->timing, 0, sizeof(h->timing));
   return MCP_OK;
@@ -441,7 +442,7 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   }
   if ((rc = h->b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
   if ((rc = h->b_ctrl.ensure(sizeof(BaCtrl)))) return rc;
-  if ((rc = h->b_flags.ensure(sizeof(int) * (size_t)std::max(n_meas, 1)))) return rc;
+  if ((rc = h->b_flags.ensure(sizeof(int) * ((size_t)std::max(n_meas, 1) + 16)))) return rc;
   if ((size_t)n_meas > h->flags_cap) {
     if (h->flags_host) cudaFreeHost(h->flags_host);
     h->flags_host = nullptr;
@@ -753,13 +754,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     if ((rc = push_ctrl(h))) return rc;
   }
   int n_bs = 0, n_lin = 0;
-  n_bs = launch_backsub_eval(d, 0, -1, nullptr, s); h->launches++;
+  // (the errors are in d.chi2 already: the robust sum is a pass over them, not a second reprojection)
+  n_bs = launch_robust_sum(d, -1, s); h->launches++;
   { Prof p(h, C_OTHER); launch_reduce_partials(d, 0, n_bs, red, s); }
   if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 1, ncclDouble, ncclSum, h->comm, s));
-  double chi_before = 0;
-  MCP_CUDA_CHECK(cudaMemcpyAsync(&chi_before, red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-  MCP_CUDA_CHECK(cudaStreamSynchronize(s));
-  if (st) st->chi2_before = chi_before;
+  // the figure is only reported: it travels to pinned memory in stream order and is read when the Compute ends
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&h->abort_word[2], red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (single_step) { MCP_CUDA_CHECK(cudaStreamSynchronize(s)); if (st) st->chi2_before = h->abort_word[2]; }
 
   if (multi) {
     // red[15] is free between rounds
@@ -995,13 +996,25 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   eval_state(h, -1, nullptr);
   if ((rc = allgather_ranges(h, d.chi2[c.cur], h->part_meas, 1))) return rc;
   if (h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 0, s) - 1; }
-  n_bs = launch_backsub_eval(d, 0, -1, nullptr, s); h->launches++;
+  n_bs = launch_robust_sum(d, -1, s); h->launches++;
   launch_reduce_partials(d, 0, n_bs, red, s); h->launches++;
   if (multi) NCCL_CHECK(ncclAllReduce(red + 1, red + 1, 1, ncclDouble, ncclSum, h->comm, s));
-  double chi_after = 0;
-  MCP_CUDA_CHECK(cudaMemcpyAsync(&chi_after, red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  MCP_CUDA_CHECK(cudaMemcpyAsync(&h->abort_word[3], red + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
   if ((rc = allgather_ranges(h, d.pt[c.cur], h->part_pt, 3))) return rc;
+  // Tukey outliers (src/ChainBundle.cc:1368-1399) are flagged before the one host synchronisation of this block.  With the
+  // Huber kernel on, the selection above already left the Tukey sigma^2 (same values, same median); the flags come back as
+  // a compact list of original indices -- its head rides in the same copy as a count, the tail follows only if it is long
+  const bool want_tukey = h->cfg.use_tukey && d.n_meas > 0;
+  const int head = std::min(d.n_meas, 4095);
+  if (want_tukey) {
+    if (!h->cfg.use_robust) { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 1, s) - 1; }
+    MCP_CUDA_CHECK(cudaMemsetAsync(d.outlier_flags, 0, sizeof(int), s));
+    { Prof p(h, C_OTHER); launch_tukey_flags(d, s); }
+    MCP_CUDA_CHECK(cudaMemcpyAsync(h->flags_host, d.outlier_flags, sizeof(int) * (size_t)(1 + head), cudaMemcpyDeviceToHost, s));
+  }
   if ((rc = sync_ctrl(h))) return rc;
+  const double chi_after = h->abort_word[3];
+  if (st) st->chi2_before = h->abort_word[2];
 
   const bool converged = c.conv_mag || c.conv_res;
   const bool abort_now = local_abort || aborted();
@@ -1017,12 +1030,13 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
   if (counter == 0 && !external_abort) return -1;
   if (counter == 0 && abort_now) return 0;
 
-  if (h->cfg.use_tukey && d.n_meas > 0) {        // src/ChainBundle.cc:1368-1399
-    { Prof p(h, C_SELECT); h->launches += launch_select_sigma(d, -1, 1, s) - 1; }
-    { Prof p(h, C_OTHER); launch_tukey_flags(d, s); }
-    MCP_CUDA_CHECK(cudaMemcpyAsync(h->flags_host, d.outlier_flags, sizeof(int) * (size_t)d.n_meas, cudaMemcpyDeviceToHost, s));
-    MCP_CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int q = 0; q < d.n_meas; q++) if (h->flags_host[q]) h->outliers.push_back(h->meas_orig[q]);
+  if (want_tukey) {
+    const int n_out = h->flags_host[0];
+    if (n_out > head) {
+      MCP_CUDA_CHECK(cudaMemcpyAsync(h->flags_host + 1 + head, d.outlier_flags + 1 + head, sizeof(int) * (size_t)(n_out - head), cudaMemcpyDeviceToHost, s));
+      MCP_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    h->outliers.assign(h->flags_host + 1, h->flags_host + 1 + n_out);
     std::sort(h->outliers.begin(), h->outliers.end());
   }
   // median point-depth covariance (src/ChainBundle.cc:1401-1448): attempted only with < 3 movable poses

@@ -704,6 +704,7 @@ __global__ void __launch_bounds__(256) k_sel_pass(BaDev d, int which_in, int pas
       double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
       if (mode == 2) ctrl->median_out = med;
       else if (mode == 0) {
+        { const double st = 4.6851 * s; double t = st * st; if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq; ctrl->tukey_sigma_sq = t; }   // same median: the Tukey sigma^2 comes along
         s = 1.345 * s;
         ctrl->sigma_sq_raw = s * s;
         ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
@@ -974,6 +975,7 @@ __global__ void __cluster_dims__(SELC_CTAS, 1, 1) __launch_bounds__(SELC_THREADS
     if (mode == 2) ctrl->median_out = med;                      // plain upper median (src/ChainBundle.cc:1434)
     else if (mode == 3) { s = 1.345 * s; d.spec_sigma[d.cand] = s * s; }
     else if (mode == 0) {
+      { const double st = 4.6851 * s; double t = st * st; if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq; ctrl->tukey_sigma_sq = t; }   // same median: the Tukey sigma^2 comes along
       s = 1.345 * s;
       ctrl->sigma_sq_raw = s * s;
       ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
@@ -1081,6 +1083,7 @@ __global__ void __launch_bounds__(SELG_THREADS, 1) k_select_grid(BaDev d, int wh
     double s = 1.4826 * (1 + 5.0 / (double)denom) * sqrt(med);
     if (mode == 2) ctrl->median_out = med;
     else if (mode == 0) {
+      { const double st = 4.6851 * s; double t = st * st; if (t < ctrl->min_sigma_sq) t = ctrl->min_sigma_sq; ctrl->tukey_sigma_sq = t; }   // same median: the Tukey sigma^2 comes along
       s = 1.345 * s;
       ctrl->sigma_sq_raw = s * s;
       ctrl->sigma_sq_lim = ctrl->sigma_sq_raw < ctrl->min_sigma_sq ? ctrl->min_sigma_sq : ctrl->sigma_sq_raw;
@@ -1095,6 +1098,8 @@ __global__ void __launch_bounds__(SELG_THREADS, 1) k_select_grid(BaDev d, int wh
 }
 
 // Tukey outlier flags (src/ChainBundle.cc:1385-1398)
+// Tukey outliers (src/ChainBundle.cc:1384-1399) as a compact list: outlier_flags[0] = count (cleared by the caller),
+// outlier_flags[1..] = the ORIGINAL indices of the flagged measurements, in no particular order (the host sorts them)
 __global__ void k_tukey_flags(BaDev d)
 {
   const double ts = d.ctrl->tukey_sigma_sq;
@@ -1102,7 +1107,29 @@ __global__ void k_tukey_flags(BaDev d)
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < d.n_meas; m += gridDim.x * blockDim.x) {
     const double a = fabs(v[m]);
     const double sq = a > ts ? 0.0 : 1.0 - (a / ts);
-    d.outlier_flags[m] = (sq * sq == 0.0) ? 1 : 0;
+    if (sq * sq == 0.0) d.outlier_flags[1 + atomicAdd(&d.outlier_flags[0], 1)] = d.meas_a[m].w;
+  }
+}
+
+// sum of the robustified chi2 of a state whose errors are already in d.chi2[which] (this rank's measurement range): the
+// "BEFORE" / "AFTER" figures of a Compute (src/ChainBundle.cc:1317-1345) need the errors for the sigma selection first and
+// the robust sum afterwards -- a pass over the stored values instead of a second reprojection of every measurement
+__global__ void __launch_bounds__(256) k_robust_sum(BaDev d, int which_in)
+{
+  __shared__ double red[32];
+  const BaCtrl* ctrl = d.ctrl;
+  const double* __restrict__ v = d.chi2[which_in < 0 ? ctrl->cur : which_in];
+  double acc = 0;
+  for (int m = d.m_lo + blockIdx.x * blockDim.x + threadIdx.x; m < d.m_hi; m += gridDim.x * blockDim.x) {
+    double rho0, rho1;
+    robustify(ctrl, v[m], rho0, rho1);
+    acc += rho0;
+  }
+  const double a = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    d.part[PART_TMP_CHI * MAX_PARTIALS + blockIdx.x] = a;
+    d.part[PART_SCALE * MAX_PARTIALS + blockIdx.x] = 0.0;
+    d.part[PART_SUMSQ * MAX_PARTIALS + blockIdx.x] = 0.0;
   }
 }
 
@@ -1477,6 +1504,12 @@ void launch_select_spec(const BaDev& d, int which, cudaStream_t s)
   launch_chain(k_select_cluster, dim3(SELC_CTAS), dim3(SELC_THREADS), SELC_SMEM, s, d, which, 3, (double*)nullptr, (size_t)0);
 }
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
+int launch_robust_sum(const BaDev& d, int which, cudaStream_t s)
+{
+  const int g = 148 < MAX_PARTIALS ? 148 : MAX_PARTIALS;
+  k_robust_sum<<<g, 256, 0, s>>>(d, which);
+  return g;
+}
 void launch_lambda_init(const BaDev& d, cudaStream_t s) { k_lambda_init<<<1, 1024, 0, s>>>(d); }
 void launch_lambda_apply(const BaDev& d, cudaStream_t s) { k_lambda_apply<<<1, 1, 0, s>>>(d); }
 void launch_lm_control(const BaDev& d, const CandParts& parts, int n_cand, int n_lin, int n_bs, const double* red_in, int first_trial, cudaStream_t s)

@@ -11,10 +11,15 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 prob = synth.make_ba_config(cfg, 0)
 g = capi.BaHandle()
 g.load(prob)
+import time
+wall = []
 for _ in range(reps):
     g.reset_state()
+    t0 = time.perf_counter()
     rc, st = g.compute(iters)
-print("rc", rc, "trials", st.total_trials, "launches", st.kernel_launches, "gpu_ms", st.gpu_ms)
+    wall.append(time.perf_counter() - t0)
+print("rc", rc, "trials", st.total_trials, "launches", st.kernel_launches, "gpu_ms", st.gpu_ms, "call_ms(min)", 1e3 * min(wall),
+      "n_outliers", st.n_outliers, "chi2", st.chi2_before, st.chi2_after)
 if len(sys.argv) > 4 and sys.argv[4] == "fe":
     f = capi.FeHandle(640, 480, max_corners_per_level=16384)
     a = synth.make_frame(seed=100); b = synth.make_frame(seed=100, shift=(3.0, -2.0))
