@@ -173,6 +173,58 @@ __device__ __forceinline__ void meas_geometry(const DevCam* cams, const double* 
   }
 }
 
+// The same for k_linearize with the per-point context in shared memory (one copy per 8-lane group): 33 doubles that would
+// otherwise stay in registers across the whole measurement loop next to 30 accumulators (the kernel sat at the 255-register
+// limit with spills; with the context in shared memory it fits 168 registers = 12 warps per SM).
+//   cs[0..2] point in the world frame, cs[3..11] R of the source MKF pose, cs[12..20] R of the source cam-from-base link,
+//   cs[21..23] point in the source MKF frame, cs[24..32] tangent basis M (point_tangent)
+constexpr int CTXD = 33;
+__device__ __forceinline__ void meas_geometry_s(const DevCam* cams, const double* pose, const double* cs, const int4 ma, const double2 z, MeasGeom& g)
+{
+  Se3 Bm;
+  se3_load(pose + 12 * (size_t)ma.x, Bm);
+  {
+    const double pw[3] = { cs[0], cs[1], cs[2] };
+    se3_apply(Bm, pw, g.q);
+  }
+  double v[3];
+  double RC[9];
+  if (ma.y >= 0) {
+    Se3 C;
+    se3_load(pose + 12 * (size_t)ma.y, C);
+    se3_apply(C, g.q, v);
+#pragma unroll
+    for (int i = 0; i < 9; i++) RC[i] = C.R[i];
+  } else {
+    v[0] = g.q[0]; v[1] = g.q[1]; v[2] = g.q[2];
+#pragma unroll
+    for (int i = 0; i < 9; i++) RC[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  double px[2], G[6];
+  cam_project(cams[ma.z], v, px, G);
+  g.e[0] = z.x - px[0];
+  g.e[1] = z.y - px[1];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) g.A[r * 3 + k] = G[r * 3] * RC[k] + G[r * 3 + 1] * RC[3 + k] + G[r * 3 + 2] * RC[6 + k];
+  double T[6];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) T[r * 3 + k] = g.A[r * 3] * Bm.R[k] + g.A[r * 3 + 1] * Bm.R[3 + k] + g.A[r * 3 + 2] * Bm.R[6 + k];
+  const double* BsR = cs + 3;
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) g.A2[r * 3 + k] = T[r * 3] * BsR[k * 3] + T[r * 3 + 1] * BsR[k * 3 + 1] + T[r * 3 + 2] * BsR[k * 3 + 2];
+  const double* RCcs = cs + 12;
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) g.A3[r * 3 + k] = g.A2[r * 3] * RCcs[k * 3] + g.A2[r * 3 + 1] * RCcs[k * 3 + 1] + g.A2[r * 3 + 2] * RCcs[k * 3 + 2];
+}
+
 // J (2x6, row-major) = sign * A * Gamma(q),  Gamma(q) = [ I3 | e_k x q ]  (TooN SE3 generator field)
 __device__ __forceinline__ void pose_jac(const double* A, const double* q, double sign, double* J)
 {
@@ -263,7 +315,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
   const int gl = lane & (LG - 1), grp = lane / LG;
   const unsigned gmask = ((1u << LG) - 1u) << (grp * LG);
   if (lookahead_skip(d)) return;
-  double* Wsm = smem + d.stage_doubles + (size_t)(wid * PPW + grp) * d.max_slots * 18;
+  double* Wsm = smem + d.stage_doubles + (size_t)(wid * PPW + grp) * ((size_t)d.max_slots * 18 + CTXD);
+  double* cs = Wsm + (size_t)d.max_slots * 18;             // this group's point context
   const BaCtrl* ctrl = d.ctrl;
   const int cur = ctrl->cur;
   // Huber parameters of this linearisation.  A look-ahead launch (d.pick_sigma) follows an accepted trial whose state is the
@@ -298,10 +351,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
     const int4 pi = d.pt_info[p];
     const int pvar = d.pt_var[p];
     const double prel[3] = { ptv[3 * (size_t)p], ptv[3 * (size_t)p + 1], ptv[3 * (size_t)p + 2] };
-    PtCtx c;
-    load_pt_ctx(d, pose, pi, prel, c);
-    double M[9];
-    point_tangent(prel, M);
+    {
+      PtCtx c;
+      load_pt_ctx(d, pose, pi, prel, c);
+      double M[9];
+      point_tangent(prel, M);
+      if (gl == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { cs[i] = c.pw[i]; cs[21 + i] = c.qs[i]; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) { cs[3 + i] = c.Bs.R[i]; cs[12 + i] = c.RCcs[i]; cs[24 + i] = M[i]; }
+      }
+    }
+    const double* M = cs + 24;
     const int s0 = d.pt_slot_off[p], K = d.pt_slot_off[p + 1] - s0;
     for (int i = gl; i < K * 18; i += LG) Wsm[i] = 0.0;
     __syncwarp(gmask);
@@ -316,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
       const double2 z = d.meas_xy[m];
       const double info = d.meas_info[m];
       MeasGeom g;
-      meas_geometry<true>(cams, pose, c, ma, z, g);
+      meas_geometry_s(cams, pose, cs, ma, z, g);
       double chi2 = info * (g.e[0] * g.e[0] + g.e[1] * g.e[1]);
       if (pvar < 0 && use_robust) chi2 = -chi2;                   // src/ChainBundle.cc:413-414
       double rho0, rho1;
@@ -362,7 +424,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
         rec[3] = make_double2(g.q[0], g.q[1]); rec[4] = make_double2(g.q[2], w); rec[5] = make_double2(we0, we1);
         if (has_src) {
           rec[6] = make_double2(g.A2[0], g.A2[1]); rec[7] = make_double2(g.A2[2], g.A2[3]); rec[8] = make_double2(g.A2[4], g.A2[5]);
-          rec[9] = make_double2(c.qs[0], c.qs[1]); rec[10] = make_double2(c.qs[2], (double)vo);
+          rec[9] = make_double2(cs[21], cs[22]); rec[10] = make_double2(cs[23], (double)vo);
         }
         if (pvar >= 0) {
           double Jo[12];
@@ -408,7 +470,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_linearize(BaDev d)
     const bool any_src = (P2[0] != 0.0) || (P2[3] != 0.0) || (P2[5] != 0.0);
     if (vs >= 0 && any_src) {
       // Gs (3x6) = [I | o_k(qs)], o_0=(0,-q2,q1) o_1=(q2,0,-q0) o_2=(-q1,q0,0)
-      const double q0 = c.qs[0], q1 = c.qs[1], q2 = c.qs[2];
+      const double q0 = cs[21], q1 = cs[22], q2 = cs[23];
       const double Gs[18] = { 1, 0, 0, 0, q2, -q1, 0, 1, 0, -q2, 0, q0, 0, 0, 1, q1, -q0, 0 };
       const double P[9] = { P2[0], P2[1], P2[2], P2[1], P2[3], P2[4], P2[2], P2[4], P2[5] };
       for (int e = gl; e < 27; e += LG) {
@@ -1408,12 +1470,12 @@ static int per_point_grid(const BaDev& d, int warps)
   return g;
 }
 
-// Register-allocation variants of k_linearize (the kernel is latency bound; fewer registers = more resident warps
-// but spills).  MCP_BA_LIN_VARIANT: 0 = 256 threads, 1 block/SM (no cap), 1 = 128 threads x 3 blocks/SM (<= 168 regs),
-// 2 = 256 threads x 2 blocks/SM (<= 128 regs).
+// Register-allocation variants of k_linearize (the kernel is latency bound; fewer registers = more resident warps).
+// MCP_BA_LIN_VARIANT: 1 (default) = 128 threads x 3 blocks/SM (168 registers; used when three blocks' shared memory fit,
+// else variant 0), 0 = 256 threads, 1 block/SM (214 registers), 2 = 256 threads x 2 blocks/SM (128 registers, spills).
 static int lin_variant()
 {
-  static const int v = [] { const char* e = getenv("MCP_BA_LIN_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
+  static const int v = [] { const char* e = getenv("MCP_BA_LIN_VARIANT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
   return v;
 }
 // zeroes the linearisation accumulators [H0 | gc | red] (a memset that honours the look-ahead predicate)
@@ -1458,7 +1520,7 @@ static void launch_pose_blocks(const BaDev& d, cudaStream_t s, const SchurMulti*
 int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, const SchurMulti* mc, double* zero_ptr, size_t zero_n)
 {
   const size_t stage = sizeof(double) * d.stage_doubles;
-  if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 72 * 1024) {
+  if (lin_variant() == 1 && warps >= 4 && smem / warps * 4 + stage <= 74 * 1024) {
     const int g = per_point_grid(d, 4);
     launch_chain(k_linearize<128, 3>, dim3(g), dim3(128), smem / warps * 4 + stage, s, d);
     launch_pose_blocks(d, s, mc, zero_ptr, zero_n);
@@ -1531,8 +1593,8 @@ int stage_doubles_for(int n_pose, int n_cam)
 
 int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* smem_out)
 {
-  // shared memory per warp: the W blocks of its PPW points, max_slots x 18 doubles each
-  const size_t per_warp = (size_t)max_slots * 18 * sizeof(double) * PPW;
+  // shared memory per warp: the W blocks of its PPW points, max_slots x 18 doubles each, plus their contexts
+  const size_t per_warp = ((size_t)max_slots * 18 + CTXD) * sizeof(double) * PPW;
   int warps = 8;
   const size_t stage = sizeof(double) * (size_t)stage_doubles;
   while (warps > 1 && per_warp * warps + stage > 200 * 1024) warps >>= 1;
@@ -1541,7 +1603,7 @@ int configure_kernels(int max_slots, int stage_doubles, int* warps_out, size_t* 
   if (cudaFuncSetAttribute(k_select_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELC_SMEM) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(k_linearize<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) return -2;
   if (cudaFuncSetAttribute(k_linearize<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)) != cudaSuccess) return -2;
-  if (cudaFuncSetAttribute(k_linearize<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(72 * 1024)) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_linearize<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(74 * 1024)) != cudaSuccess) return -2;
   *warps_out = warps;
   *smem_out = smem;
   return 0;
