@@ -197,9 +197,9 @@ def frontend_report(parts, n_gpus, peak):
            "pyramid_ms_device": parts[0]["pyramid_ms_device"], "fast_ms_device": parts[0]["fast_ms_device"],
            "algorithmic_bytes_per_camera_frame": frame_bytes, "patch_bytes_each": patch_bytes,
            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
-                        "keyframe": {"kernel": "k_halfsample_fused + k_fast_*", "achieved": frame_bytes / (kf_dev_ms * 1e-3) / 1e9 if kf_dev_ms > 0 else None,
+                        "keyframe": {"kernel": "k_halfsample_fused + k_fast_score_rows + k_fast_compact4", "achieved": frame_bytes / (kf_dev_ms * 1e-3) / 1e9 if kf_dev_ms > 0 else None,
                                      "frac": frame_bytes / (kf_dev_ms * 1e-3) / 1e9 / peak if kf_dev_ms > 0 else None},
-                        "patch_search": {"kernel": "k_patch_search", "achieved": patch_bytes * n_patches / (ps_dev_ms * 1e-3) / 1e9 if ps_dev_ms > 0 else None,
+                        "patch_search": {"kernel": "k_patch_search_tma", "achieved": patch_bytes * n_patches / (ps_dev_ms * 1e-3) / 1e9 if ps_dev_ms > 0 else None,
                                          "frac": patch_bytes * n_patches / (ps_dev_ms * 1e-3) / 1e9 / peak if ps_dev_ms > 0 else None},
                         "note": "one 640x480 frame is 0.5 MB: launch / dependency latency bound, not HBM bound"},
            "result_checksum_per_camera_set": sum(p["checksum"] for p in parts)}

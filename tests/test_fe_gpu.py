@@ -78,6 +78,28 @@ def test_odd_size_and_edge_images(capi, ora):
     _check_levels(ora, sat, f.make_keyframe(2, sat))
 
 
+@pytest.mark.parametrize("kind", ["frame", "noise", "saturated"])
+def test_score_map_exact(capi, ora, kind):
+    """every pixel of the FAST score map (0 = no corner at b = 5, else libCVD's fast_corner_score_10) against the oracle's
+    bisection: the kernel evaluates the score in closed form with 16-bit SIMD min3/max3"""
+    if kind == "frame":
+        img = synth.make_frame(seed=7)
+    elif kind == "noise":
+        img = np.random.default_rng(3).integers(0, 256, (480, 640), dtype=np.uint8)
+    else:
+        img = np.zeros((480, 640), np.uint8); img[::2, ::2] = 255; img[1::3, 1::2] = 128
+    f = capi.FeHandle(640, 480, max_corners_per_level=1 << 17)
+    f.make_keyframe(0, img)
+    pyr = ora.pyramid(img)
+    for l in range(4):
+        sm = f.debug_scores(0, l)
+        xy = ora.fast10_detect(pyr[l], 5)
+        ref = np.zeros_like(sm)
+        if len(xy):
+            ref[xy[:, 1], xy[:, 0]] = np.minimum(ora.fast10_score(pyr[l], xy, 5), 255)
+        assert np.array_equal(sm, ref), (kind, l, int((sm != ref).sum()))
+
+
 def _make_requests(capi, rng, lv_src, n, shift, src_slot=0, subpix=True, exhaustive_frac=0.05):
     req = np.zeros(n, capi.PATCH_REQ_DTYPE)
     k = 0
