@@ -180,7 +180,8 @@ struct BaPrep {
   char err[256] = "";
   int par_min_meas = 16384;       // below this many measurements the passes run on the calling thread only
   // scratch, kept between calls
-  std::vector<int> key_cnt, order, slot_tmp, thr_bad, thr_max, thr_lo, thr_hist;
+  std::vector<int> key_cnt, order, slot_tmp, thr_bad, thr_max, thr_maxcnt, thr_lo, thr_hist, thr_keysum, thr_itemsum, key_tot;
+  std::vector<long long> thr_inc;
 
   void free_all(const PrepAlloc& a)
   {
@@ -338,6 +339,9 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
   // at most one slot per measurement plus its source pose), then an exclusive scan of the list lengths places them.
   o.slot_tmp.resize((size_t)n_meas + n_pt + 1);
   o.thr_max.assign((size_t)T, 1);
+  o.thr_maxcnt.assign((size_t)T, 0);
+  o.thr_inc.assign((size_t)T, 0);
+  const int inc_lo = o.part_pt[rank], inc_hi = o.part_pt[rank + 1];
   o.thr_lo.assign((size_t)T + 1, n_pt);
   for (int t = 0; t < T; t++)
     o.thr_lo[t] = (int)(std::lower_bound(pmo, pmo + n_pt, (int)((long long)n_meas * t / T)) - pmo);
@@ -364,13 +368,15 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
     const int32_t* const in_ptchain = pt_chain;
     const int p_lo = o.thr_lo[t], p_hi = o.thr_lo[t + 1];
     int* const kc = o.pb_cnt.data() + pb_keys * (size_t)t;
-    int max_slots = 1;
+    int max_slots = 1, max_cnt_t = 0;
+    long long inc_t = 0;
     double last_noise = -1.0, last_info = 0.0;
     for (int p = p_lo; p < p_hi; p++) {
       const int src0 = in_ptchain[2 * p], src1 = in_ptchain[2 * p + 1];
       const int src_var = pose_var_[src0];
       const bool movable = pt_var_[p] >= 0;
       const int q_lo = off_[p], q_hi = off_[p + 1];
+      max_cnt_t = std::max(max_cnt_t, q_hi - q_lo);
       bool any_src = false;
       tmp.clear();
       for (int q = q_lo; q < q_hi; q++) {
@@ -410,6 +416,7 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
         int* dst = slot_tmp + q_lo + p;
         for (int i = 0; i < K; i++) { dst[i] = tv[i]; pos[tv[i]] = i; }
         max_slots = std::max(max_slots, K);
+        if (p >= inc_lo && p < inc_hi) inc_t += (long long)K * (K + 1) / 2;     // co-visibility incidences of this rank
         for (int q = q_lo; q < q_hi; q++)
           if (mb[q].x >= 0) mb[q].y = pos[mb[q].x];
         if (any_src) src_slot = pos[src_var];
@@ -418,6 +425,8 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
       pinfo[p] = PInt4{ src0, src1, src_var, src_slot };
     }
     o.thr_max[t] = max_slots;
+    o.thr_maxcnt[t] = max_cnt_t;
+    o.thr_inc[t] = inc_t;
   });
   PREP_TICK("per-point");
   o.pt_slot_off[0] = 0;
@@ -443,25 +452,35 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
   // by descending measurement count)
   {
     int max_cnt = 0;
-    for (int p = 0; p < n_pt; p++) max_cnt = std::max(max_cnt, pmo[p + 1] - pmo[p]);
+    for (int t = 0; t < T; t++) max_cnt = std::max(max_cnt, o.thr_maxcnt[t]);
     std::vector<int>& cnt = o.key_cnt;
     if (n_pt == 0) o.pt_order[0] = 0;
+    const size_t nb = (size_t)max_cnt + 1;               // bins: descending measurement count
     for (int r = 0; r < world; r++) {
       const int lo = o.part_pt[r], hi = o.part_pt[r + 1];
-      cnt.assign((size_t)max_cnt + 2, 0);
-      for (int p = lo; p < hi; p++) cnt[(size_t)(max_cnt - (pmo[p + 1] - pmo[p])) + 1]++;
-      for (int c = 0; c <= max_cnt; c++) cnt[c + 1] += cnt[c];
-      for (int p = lo; p < hi; p++) o.pt_order[lo + cnt[(size_t)(max_cnt - (pmo[p + 1] - pmo[p]))]++] = p;
+      // stable parallel counting sort: one histogram row per thread over its contiguous share of the rank's points
+      cnt.assign(nb * (size_t)T, 0);
+      par([&](int t) {
+        int* c = cnt.data() + nb * (size_t)t;
+        const int a = lo + (int)((long long)(hi - lo) * t / T), b = lo + (int)((long long)(hi - lo) * (t + 1) / T);
+        for (int p = a; p < b; p++) c[max_cnt - (pmo[p + 1] - pmo[p])]++;
+      });
+      int run = lo;
+      for (size_t bin = 0; bin < nb; bin++)
+        for (int t = 0; t < T; t++) { int& c = cnt[nb * (size_t)t + bin]; const int v = c; c = run; run += v; }
+      par([&](int t) {
+        int* c = cnt.data() + nb * (size_t)t;
+        int* const out = o.pt_order.p;
+        const int a = lo + (int)((long long)(hi - lo) * t / T), b = lo + (int)((long long)(hi - lo) * (t + 1) / T);
+        for (int p = a; p < b; p++) out[c[max_cnt - (pmo[p + 1] - pmo[p])]++] = p;
+      });
     }
   }
 
-  // co-visibility incidences of this rank (sizes the pair lists built on the device)
+  // co-visibility incidences of this rank (sizes the pair lists built on the device): summed in the per-point pass
   {
     long long n_inc = 0;
-    for (int p = o.part_pt[rank]; p < o.part_pt[rank + 1]; p++) {
-      const long long K = o.pt_slot_off[p + 1] - o.pt_slot_off[p];
-      n_inc += K * (K + 1) / 2;
-    }
+    for (int t = 0; t < T; t++) n_inc += o.thr_inc[t];
     o.n_inc = n_inc;
   }
 
@@ -474,23 +493,43 @@ inline int ba_prepare(BaPrep& o, const PrepAlloc& al, int n_cam, int n_pose, con
   {
     const size_t nv = pb_nv, n_keys = pb_keys;
     std::vector<int>& cnt = o.pb_cnt;
+    // (key x thread) exclusive scan in two parallel passes over key ranges: totals per key and per range, then the cursors
+    // and the work items of every range from the range's base
+    o.key_tot.resize(n_keys);
+    o.thr_keysum.assign((size_t)T, 0);
+    o.thr_itemsum.assign((size_t)T, 0);
+    par([&](int t) {
+      const size_t k0 = n_keys * (size_t)t / T, k1 = n_keys * (size_t)(t + 1) / T;
+      int ents = 0, items = 0;
+      for (size_t k = k0; k < k1; k++) {
+        int tot = 0;
+        for (int u = 0; u < T; u++) tot += cnt[n_keys * (size_t)u + k];
+        o.key_tot[k] = tot;
+        ents += tot; items += (tot + PREP_PB_CHUNK - 1) / PREP_PB_CHUNK;
+      }
+      o.thr_keysum[t] = ents; o.thr_itemsum[t] = items;
+    });
     size_t n_ent = 0, n_items = 0;
-    for (size_t k = 0; k < n_keys; k++) {
-      const size_t b = n_ent;
-      for (int t = 0; t < T; t++) { int& c = cnt[n_keys * (size_t)t + k]; const int v = c; c = (int)n_ent; n_ent += (size_t)v; }
-      n_items += (n_ent - b + PREP_PB_CHUNK - 1) / PREP_PB_CHUNK;
+    for (int t = 0; t < T; t++) {
+      const int e = o.thr_keysum[t], i2 = o.thr_itemsum[t];
+      o.thr_keysum[t] = (int)n_ent; o.thr_itemsum[t] = (int)n_items;
+      n_ent += (size_t)e; n_items += (size_t)i2;
     }
     if (!o.pb_idx.resize(std::max(n_ent, (size_t)1), al) || !o.pb_items.resize(std::max(n_items, (size_t)1), al))
       MCP_PREP_FAIL(PREP_NOMEM, "mcp_ba_load: host staging allocation failed");
     PREP_TICK("pb:cursors");
-    size_t it = 0;
-    for (size_t k = 0; k < n_keys; k++) {
-      const int b = cnt[k], e = (k + 1 < n_keys) ? cnt[k + 1] : (int)n_ent;      // thread 0's cursor = start of the key
-      if (b == e) continue;
-      const int lo = (int)(k / nv), hi = (int)(k % nv);
-      for (int s2 = b; s2 < e; s2 += PREP_PB_CHUNK) o.pb_items[it++] = PInt4{ lo, hi, s2, std::min(s2 + PREP_PB_CHUNK, e) };
-    }
-    o.pb_items.n = it;                                     // 0 items is legal (nothing movable is observed)
+    par([&](int t) {
+      const size_t k0 = n_keys * (size_t)t / T, k1 = n_keys * (size_t)(t + 1) / T;
+      int run = o.thr_keysum[t];
+      size_t it = (size_t)o.thr_itemsum[t];
+      for (size_t k = k0; k < k1; k++) {
+        const int b = run, e = run + o.key_tot[k];
+        for (int u = 0; u < T; u++) { int& c = cnt[n_keys * (size_t)u + k]; const int v = c; c = run; run += v; }
+        const int lo = (int)(k / nv), hi = (int)(k % nv);
+        for (int s2 = b; s2 < e; s2 += PREP_PB_CHUNK) o.pb_items[it++] = PInt4{ lo, hi, s2, std::min(s2 + PREP_PB_CHUNK, e) };
+      }
+    });
+    o.pb_items.n = n_items;                                // 0 items is legal (nothing movable is observed)
     PREP_TICK("pb:items");
     par([&](int t) {
       int* c = cnt.data() + n_keys * (size_t)t;
