@@ -136,6 +136,11 @@ struct McpBa {
     int chol_epoch = 0, chol_task_base = 0;
   } cand[MAX_CAND];               // [0] unused (candidate 0 lives in the handle's own buffers)
   cudaEvent_t ev_ready = nullptr, ev_red = nullptr, ev_ctrl = nullptr;
+  // the co-visibility lists of a load are built on aux_stream next to the first evaluation / selection / linearisation of the
+  // Compute that follows; the first Schur reduction waits for ev_pairs
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_pairs = nullptr;
+  bool pairs_pending = false;
   cudaStream_t sel_stream[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr };   // speculative sigma of every candidate's trial state
   cudaEvent_t ev_bs[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr }, ev_sel[MAX_CAND] = { nullptr, nullptr, nullptr, nullptr };
   cudaStream_t copy_stream = nullptr;   // control-block read-back that does not queue behind look-ahead kernels
@@ -210,6 +215,9 @@ static int ba_create_impl(const McpBaConfig* cfg, McpBa* h)
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_red, cudaEventDisableTiming));
   MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ctrl, cudaEventDisableTiming));
   MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
+  MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pairs, cudaEventDisableTiming));
   for (int q = 0; q < MAX_CAND; q++) {
     MCP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->sel_stream[q], cudaStreamNonBlocking));
     MCP_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_bs[q], cudaEventDisableTiming));
@@ -283,6 +291,9 @@ int mcp_ba_destroy(McpBa* h)
   if (h->ev_red) cudaEventDestroy(h->ev_red);
   if (h->ev_ctrl) cudaEventDestroy(h->ev_ctrl);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
+  if (h->ev_pairs) cudaEventDestroy(h->ev_pairs);
   for (int q = 0; q < MAX_CAND; q++) {
     if (h->sel_stream[q]) { cudaStreamSynchronize(h->sel_stream[q]); cudaStreamDestroy(h->sel_stream[q]); }
     if (h->ev_bs[q]) cudaEventDestroy(h->ev_bs[q]);
@@ -342,6 +353,10 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     return MCP_ERR_INVALID;
   }
   h->loaded = false;
+  // mcp_ba_load returns without waiting for the device: whatever an earlier load / compute left in flight must be over before
+  // the pooled staging arrays are rewritten (normally nothing is: every Compute ends synchronised)
+  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (h->pairs_pending) { MCP_CUDA_CHECK(cudaStreamSynchronize(h->aux_stream)); h->pairs_pending = false; }
   const int n_cam = (int)h->cams.size();
   cudaSetDevice(h->device);
   // MCP_BA_SCHUR: 1 (default) pair gathers with TMA, 2 staged pair gathers, 0 row-wise (k_schur_rows; measured slower
@@ -523,16 +538,25 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     if ((rc = h->b_paircnt.ensure(sizeof(int) * (size_t)(n_pairs + 2)))) return rc;
     if ((rc = h->b_inc.ensure(sizeof(int2) * (size_t)std::max<long long>(pr.n_inc, 1)))) return rc;
     if ((rc = h->b_items.ensure(sizeof(int4) * max_items + 16))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 2), h->stream));
+    // on aux_stream, behind everything uploaded so far: ≈ 0.1 ms of device work that overlaps the start of the next Compute
+    MCP_CUDA_CHECK(cudaEventRecord(h->ev_up, h->stream));
+    MCP_CUDA_CHECK(cudaStreamWaitEvent(h->aux_stream, h->ev_up, 0));
+    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_paircnt.p, 0, sizeof(int) * (size_t)(n_pairs + 2), h->aux_stream));
     int* n_items_dev = reinterpret_cast<int*>(h->b_items.as<int4>() + max_items);
-    launch_pair_count(d, h->b_paircnt.as<int>(), h->stream);
-    launch_pair_items(d, h->b_paircnt.as<int>(), h->b_items.as<int4>(), n_items_dev, h->stream);
-    launch_pair_fill(d, h->b_paircnt.as<int>(), h->b_inc.as<int2>(), h->stream);
+    launch_pair_count(d, h->b_paircnt.as<int>(), h->aux_stream);
+    launch_pair_items(d, h->b_paircnt.as<int>(), h->b_items.as<int4>(), n_items_dev, h->aux_stream);
+    launch_pair_fill(d, h->b_paircnt.as<int>(), h->b_inc.as<int2>(), h->aux_stream);
+    MCP_CUDA_CHECK(cudaEventRecord(h->ev_pairs, h->aux_stream));
+    h->pairs_pending = true;
     d.inc = h->b_inc.as<int2>(); d.items = h->b_items.as<int4>(); d.n_items_dev = n_items_dev; d.max_items = (int)max_items;
     for (int q = 1; q < MAX_CAND; q++) { h->cand[q].d.inc = d.inc; h->cand[q].d.items = d.items; h->cand[q].d.n_items_dev = d.n_items_dev; h->cand[q].d.max_items = d.max_items; }
   }
   const auto t_enq = std::chrono::steady_clock::now();
-  MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  // no wait for the device here (MCP_BA_LOAD_SYNC=1 / the trace restore it): the uploads come from pinned staging owned by the
+  // handle, the caller's arrays have been consumed, and every later call is ordered behind this work on the handle's stream
+  static const bool load_sync = getenv("MCP_BA_LOAD_SYNC") && getenv("MCP_BA_LOAD_SYNC")[0] == '1';
+  if (trace || load_sync) { MCP_CUDA_CHECK(cudaStreamSynchronize(h->stream)); MCP_CUDA_CHECK(cudaStreamSynchronize(h->aux_stream)); }
+  MCP_CUDA_CHECK(cudaGetLastError());
   if (trace) {
     const auto t_end = std::chrono::steady_clock::now();
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -846,6 +870,7 @@ static int run_compute(McpBa* h, volatile const uint8_t* abort_flag, int n_iter,
     }
     bool first = true;
     for (;;) {
+      if (h->pairs_pending) { MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_pairs, 0)); h->pairs_pending = false; }   // (lists of this load)
       CandParts parts;
       for (int q = 0; q < MAX_CAND; q++) parts.p[q] = d.part;
       for (int q = 0; q < spec_pending; q++) MCP_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_sel[q], 0));   // (their chi2 buffers are about to be rewritten)
