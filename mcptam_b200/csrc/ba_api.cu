@@ -48,6 +48,7 @@ int launch_linearize(const BaDev& d, int warps, size_t smem, cudaStream_t s, con
 int launch_backsub_eval(const BaDev& d, int apply, int which, double* err_out, cudaStream_t s);
 int launch_select_sigma(const BaDev& d, int which, int mode, cudaStream_t s, double* zero_ptr = nullptr, size_t zero_n = 0);
 void launch_tukey_flags(const BaDev& d, cudaStream_t s);
+void launch_load_init(const LoadInit& li, cudaStream_t s);
 int launch_robust_sum(const BaDev& d, int which, cudaStream_t s);
 void launch_lambda_init(const BaDev& d, cudaStream_t s);
 void launch_lambda_apply(const BaDev& d, cudaStream_t s);
@@ -422,13 +423,19 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   const size_t pose_bytes = sizeof(double) * 12 * (size_t)n_pose, pt_bytes = sizeof(double) * 3 * (size_t)n_pt;
   if ((rc = upload(h, h->b_pose0, pose_Rt, pose_bytes))) return rc;
   if ((rc = upload(h, h->b_pt0, pt_xyz, pt_bytes))) return rc;
+  // (everything that has to be cleared or replicated on the device is collected here and done by ONE kernel, k_load_init)
+  LoadInit li;
+  memset(&li, 0, sizeof(li));
+  auto zero = [&](void* ptr, size_t bytes) { if (bytes && li.n_zero < LOAD_ZERO_MAX) { li.zero_ptr[li.n_zero] = ptr; li.zero_bytes[li.n_zero] = bytes; li.n_zero++; return true; } return bytes == 0; };
+  bool zok = true;
   for (int k = 0; k < N_STATE; k++) {
     if ((rc = h->b_pose[k].ensure(pose_bytes))) return rc;
     if ((rc = h->b_pt[k].ensure(pt_bytes ? pt_bytes : 16))) return rc;
     if ((rc = h->b_chi2[k].ensure(sizeof(double) * (size_t)std::max(n_meas, 1)))) return rc;
-    MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_pose[k].p, h->b_pose0.p, pose_bytes, cudaMemcpyDeviceToDevice, h->stream));
-    if (pt_bytes) MCP_CUDA_CHECK(cudaMemcpyAsync(h->b_pt[k].p, h->b_pt0.p, pt_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    li.pose[k] = h->b_pose[k].as<double>(); li.pt[k] = h->b_pt[k].as<double>();
   }
+  li.pose0 = h->b_pose0.as<double>(); li.pt0 = h->b_pt0.as<double>();
+  li.pose_doubles = 12 * (size_t)n_pose; li.pt_doubles = 3 * (size_t)n_pt;
   if ((rc = h->b_V.ensure(sizeof(double) * 6 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_gp.ensure(sizeof(double) * 3 * (size_t)std::max(n_pt, 1)))) return rc;
   if ((rc = h->b_W.ensure(sizeof(double) * 18 * (size_t)std::max(n_slots, 1)))) return rc;
@@ -445,15 +452,15 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   if ((rc = h->b_L.ensure(sizeof(double) * chol_tiles_doubles(nc)))) return rc;
   if ((rc = h->b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
   if ((rc = h->b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
+  zok = zok && zero(h->b_cflags.p, sizeof(int) * chol_flag_ints(nc));
   // LL tiles are tagged with the launch number (chol_epoch restarts at 1): stale tags of an earlier problem must go
   if ((rc = h->b_Lll.ensure(chol_ll_bytes(nc)))) return rc;
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
+  zok = zok && zero(h->b_Lll.p, chol_ll_bytes(nc));
   h->chol_epoch = 0; h->chol_task_base = 0;
   {
     const size_t sel_bytes = sizeof(unsigned) * (SEL_PASSES * SEL_BINS + 16) + sizeof(unsigned long long) * 2 * (SEL_PASSES + 1) + sizeof(double) * 2 * MAX_CAND;
     if ((rc = h->b_sel.ensure(sel_bytes))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(h->b_sel.p, 0, sel_bytes, h->stream));
+    zok = zok && zero(h->b_sel.p, sel_bytes);
   }
   if ((rc = h->b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
   if ((rc = h->b_ctrl.ensure(sizeof(BaCtrl)))) return rc;
@@ -464,9 +471,9 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     MCP_CUDA_CHECK(cudaMallocHost(&h->flags_host, sizeof(int) * (size_t)(n_meas + n_meas / 4 + 16)));
     h->flags_cap = (size_t)(n_meas + n_meas / 4 + 16);
   }
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_acc.p, 0, sizeof(double) * 2 * h->acc_doubles, h->stream));
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_dc.p, 0, sizeof(double) * ncp, h->stream));
-  MCP_CUDA_CHECK(cudaMemsetAsync(h->b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
+  zok = zok && zero(h->b_acc.p, sizeof(double) * 2 * h->acc_doubles);
+  zok = zok && zero(h->b_dc.p, sizeof(double) * ncp);
+  zok = zok && zero(h->b_part.p, sizeof(double) * 8 * MAX_PARTIALS);
 
   BaDev& d = h->d;
   memset(&d, 0, sizeof(d));
@@ -508,12 +515,12 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
     if ((rc = cq.b_Linv.ensure(sizeof(double) * chol_inv_doubles(nc)))) return rc;
     if ((rc = cq.b_cflags.ensure(sizeof(int) * chol_flag_ints(nc)))) return rc;
     if ((rc = cq.b_Lll.ensure(chol_ll_bytes(nc)))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_Lll.p, 0, chol_ll_bytes(nc), h->stream));
+    zok = zok && zero(cq.b_Lll.p, chol_ll_bytes(nc));
     if ((rc = cq.b_part.ensure(sizeof(double) * 8 * MAX_PARTIALS))) return rc;
     if ((rc = cq.b_Y.ensure(sizeof(double) * 24 * (size_t)std::max(n_slots, 1)))) return rc;
-    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_cflags.p, 0, sizeof(int) * chol_flag_ints(nc), h->stream));
-    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_dc.p, 0, sizeof(double) * ncp, h->stream));
-    MCP_CUDA_CHECK(cudaMemsetAsync(cq.b_part.p, 0, sizeof(double) * 8 * MAX_PARTIALS, h->stream));
+    zok = zok && zero(cq.b_cflags.p, sizeof(int) * chol_flag_ints(nc));
+    zok = zok && zero(cq.b_dc.p, sizeof(double) * ncp);
+    zok = zok && zero(cq.b_part.p, sizeof(double) * 8 * MAX_PARTIALS);
     cq.d.Sm = cq.b_acc.as<double>(); cq.d.rm = cq.d.Sm + (h->off_rm - h->off_Sm);
     cq.d.dc = cq.b_dc.as<double>(); cq.d.L = cq.b_L.as<double>(); cq.d.Linv = cq.b_Linv.as<double>(); cq.d.Lll = cq.b_Lll.as<uint4>();
     cq.d.flags = cq.b_cflags.as<int>(); cq.d.part = cq.b_part.as<double>(); cq.d.Y = cq.b_Y.as<double>();
@@ -530,6 +537,8 @@ int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* 
   for (int q = 0; q < MAX_CAND; q++) c.solve_ok[q] = 1;
   c.sel_n = n_meas; c.sel_rank = n_meas / 2;
   MCP_CUDA_CHECK(cudaMemcpyAsync(d.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+  if (!zok) { set_last_error("mcp_ba_load: internal: too many clear ranges"); return MCP_ERR_CUDA; }
+  launch_load_init(li, h->stream);
   if (schur_mode != 0) {
     // co-visibility lists for the pair-gather Schur kernels (ba_schur.cu), built entirely on the device: count per
     // block pair, scan + work items (k_pair_items), fill.  Only their sizes (upper bounds) are known to the host.

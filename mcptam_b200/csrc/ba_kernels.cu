@@ -1565,6 +1565,28 @@ void launch_select_spec(const BaDev& d, int which, cudaStream_t s)
 {
   launch_chain(k_select_cluster, dim3(SELC_CTAS), dim3(SELC_THREADS), SELC_SMEM, s, d, which, 3, (double*)nullptr, (size_t)0);
 }
+__global__ void __launch_bounds__(512) k_load_init(LoadInit li)
+{
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < li.n_zero; r++) {
+    const size_t n16 = li.zero_bytes[r] / 16, tail = (li.zero_bytes[r] - 16 * n16) / 4;
+    uint4* p16 = reinterpret_cast<uint4*>(li.zero_ptr[r]);
+    for (size_t i = gtid; i < n16; i += gsz) p16[i] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned* p4 = reinterpret_cast<unsigned*>(p16 + n16);
+    if (gtid < tail) p4[gtid] = 0u;
+  }
+  for (size_t i = gtid; i < li.pose_doubles; i += gsz) {
+    const double v = li.pose0[i];
+#pragma unroll
+    for (int k = 0; k < N_STATE; k++) li.pose[k][i] = v;
+  }
+  for (size_t i = gtid; i < li.pt_doubles; i += gsz) {
+    const double v = li.pt0[i];
+#pragma unroll
+    for (int k = 0; k < N_STATE; k++) li.pt[k][i] = v;
+  }
+}
+void launch_load_init(const LoadInit& li, cudaStream_t s) { k_load_init<<<148, 512, 0, s>>>(li); }
 void launch_tukey_flags(const BaDev& d, cudaStream_t s) { k_tukey_flags<<<148, 256, 0, s>>>(d); }
 int launch_robust_sum(const BaDev& d, int which, cudaStream_t s)
 {

@@ -143,7 +143,19 @@ struct SchurMulti {
   int first_dynamic_item, pad;    // = number of warps of the pair kernel (every warp starts on its own index)
 };
 
-struct CandParts { const double* p[MAX_CAND]; };   // per-candidate partial-sum arrays handed to k_lm_control
+struct CandParts { const double* p[MAX_CAND]; };
+
+// one launch at the end of mcp_ba_load instead of ~25 memset / device-to-device copy calls: ranges to clear (16-byte aligned
+// buffers, sizes in bytes, multiples of 4) and the initial state to replicate into the N_STATE state buffers
+constexpr int LOAD_ZERO_MAX = 20;
+struct LoadInit {
+  void* zero_ptr[LOAD_ZERO_MAX];
+  unsigned long long zero_bytes[LOAD_ZERO_MAX];
+  int n_zero, pad;
+  const double* pose0; const double* pt0;
+  double* pose[N_STATE]; double* pt[N_STATE];
+  unsigned long long pose_doubles, pt_doubles;
+};   // per-candidate partial-sum arrays handed to k_lm_control
 
 enum PartialRow { PART_CUR_CHI = 0, PART_MAXDIAG = 1, PART_TMP_CHI = 2, PART_SCALE = 3, PART_SUMSQ = 4 };
 
