@@ -112,7 +112,10 @@ int mcp_ba_set_cameras(McpBa* h, int32_t n_cam, const McpTaylorCam* cams);
  *   meas_noise  n_meas: dNoiseSigmaSquared (= LevelScale^2, src/BundleAdjusterMulti.cc:196)
  *   meas_cam    n_meas: index into the camera array (the reference's camera-name string)
  * Only chain link 0 may be movable (the hot path: BundleAdjusterMulti/Single); a movable link 1
- * (BundleAdjusterCalib) returns MCP_ERR_UNSUPPORTED. */
+ * (BundleAdjusterCalib) returns MCP_ERR_UNSUPPORTED.
+ * The caller's arrays have been consumed when the call returns (they may be reused at once), but the
+ * device may still be working on the load: every later call on the handle is ordered behind it, and a
+ * device-side failure of the load surfaces from that later call (MCP_BA_LOAD_SYNC=1 makes the load wait). */
 int mcp_ba_load(McpBa* h, int32_t n_pose, const double* pose_Rt, const uint8_t* pose_fixed,
                 int32_t n_pt, const double* pt_xyz, const int32_t* pt_chain, const uint8_t* pt_fixed,
                 int32_t n_meas, const double* meas_xy, const int32_t* meas_chain,
