@@ -10,7 +10,7 @@
  * (aharmat/mcptam @ ae54e1b) ships no tests, golden vectors or fixtures, and its build (ROS, TooN, libCVD, g2o,
  * SuiteSparse) is not available here -- but its hot-path translation units compile, UNMODIFIED and where they lie under
  * /root/reference, against minimal stand-ins for the third-party headers (oracle/ref_shim/, oracle/build_ref.py ->
- * oracle/_ref/*.so): include/mcptam/MEstimator.h, LevelHelpers.h, SmallMatrixOpts.h, src/ShiTomasi.cc, src/MiniPatch.cc,
+ * the .so files under oracle/_ref): include/mcptam/MEstimator.h, LevelHelpers.h, SmallMatrixOpts.h, src/ShiTomasi.cc, src/MiniPatch.cc,
  * src/TaylorCamera.cc, src/PatchFinder.cc (SSE and scalar ZMSSD) and src/ChainBundle.cc (vertices, edges, pose-chain
  * helpers, adaptive Huber kernel, convergence actions, Compute with its Tukey pass).  tests/test_oracle_vs_ref.py holds
  * the oracle to them: integers and same-order fp64 bit-for-bit, the rest to 1e-12 .. 1e-7 (stated per test).
