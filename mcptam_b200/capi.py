@@ -427,32 +427,39 @@ class FeHandle:
         if not outputs:
             check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], None))
             return None
-        outs = (LevelOut * 4)()
         cap = self.cfg.max_corners_per_level
-        keep = []
         w, h = self.cfg.width, self.cfg.height
-        if getattr(self, "_kf_bufs", None) is None:          # corner / LUT landing buffers, allocated once per handle
-            self._kf_bufs = [(np.zeros((cap, 2), np.int32), np.zeros(h >> l, np.int32)) for l in range(4)]
+        st = getattr(self, "_kf_state", None)
+        if st is None:
+            # the McpLevelOut array, the corner / LUT landing buffers and a numpy view of the scalar fields are made once per
+            # handle: a call then costs the C call plus the copies of what it returns
+            outs = (LevelOut * 4)()
+            bufs = [(np.zeros((cap, 2), np.int32), np.zeros(h >> l, np.int32)) for l in range(4)]
+            for l in range(4):
+                outs[l].corners_xy = bufs[l][0].ctypes.data
+                outs[l].corners_cap = cap
+                outs[l].row_lut = bufs[l][1].ctypes.data
+            ints = np.frombuffer(outs, dtype=np.int32).reshape(4, C.sizeof(LevelOut) // 4)
+            f = {k: getattr(LevelOut, k).offset // 4 for k in ("width", "height", "n_corners", "fast_thresh", "fast_freq", "n_corners_total")}
+            st = self._kf_state = (outs, bufs, ints, f, C.cast(outs, C.c_void_p))
+        outs, bufs, ints, f, outs_p = st
+        keep = []
         for l in range(4):
-            cor, lut = self._kf_bufs[l]
-            im = np.zeros((h, w), np.uint8) if want_images else None
-            mk = np.zeros((h, w), np.uint8) if want_masks else None
-            keep.append((cor, lut, im, mk))
-            outs[l].last_mask = mk.ctypes.data if mk is not None else None
-            outs[l].corners_xy = cor.ctypes.data
-            outs[l].corners_cap = cap
-            outs[l].row_lut = lut.ctypes.data
+            im = np.zeros((h >> l, w >> l), np.uint8) if want_images else None
+            mk = np.zeros((h >> l, w >> l), np.uint8) if want_masks else None
+            keep.append((im, mk))
             outs[l].image = im.ctypes.data if im is not None else None
-            w //= 2
-            h //= 2
-        check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], C.cast(outs, C.c_void_p)))
+            outs[l].last_mask = mk.ctypes.data if mk is not None else None
+        check(self.L.mcp_fe_make_keyframe(self.h, slot, _p(img), img.shape[1], outs_p))
         res = []
         for l in range(4):
-            cor, lut, im, mk = keep[l]
-            n = outs[l].n_corners
-            res.append({"width": outs[l].width, "height": outs[l].height, "n_corners": n, "corners": cor[:n].copy(),
-                        "row_lut": lut.copy(), "n_corners_total": outs[l].n_corners_total, "fast_thresh": outs[l].fast_thresh, "fast_freq": np.array(outs[l].fast_freq[:]),
-                        "image": im, "last_mask": mk})
+            cor, lut = bufs[l]
+            im, mk = keep[l]
+            row = ints[l]
+            n = int(row[f["n_corners"]])
+            res.append({"width": int(row[f["width"]]), "height": int(row[f["height"]]), "n_corners": n, "corners": cor[:n].copy(),
+                        "row_lut": lut.copy(), "n_corners_total": int(row[f["n_corners_total"]]), "fast_thresh": int(row[f["fast_thresh"]]),
+                        "fast_freq": row[f["fast_freq"]: f["fast_freq"] + 31].copy(), "image": im, "last_mask": mk})
         return res
 
     def search_patches(self, target_kf, req: np.ndarray) -> np.ndarray:
