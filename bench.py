@@ -98,9 +98,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "scope": scope}
 
 
-def cpu_reference_run(prob, steps, warmup, lm_iters_cpu):
+FULL_SYSTEM_NOTE = ("the FULL non-marginalised system as the reference configures g2o (BlockSolverX + CHOLMOD, points not marginalised, "
+                    "src/ChainBundle.cc:1150-1158,1218): general block-sparse Cholesky with a minimum-degree order on the block graph "
+                    "(oracle/ba_oracle.c solve_mode 3; CHOLMOD itself is not in the image), 1 thread")
+
+
+def cpu_reference_run(prob, steps, warmup, lm_iters_cpu, solve_mode=0):
     """Times the CPU restatement (oracle) on the host: one thread, as the reference runs BA on the single
-    MapMaker thread (no `#pragma omp` in the reference tree)."""
+    MapMaker thread (no `#pragma omp` in the reference tree).  solve_mode 0: points eliminated by an explicit
+    Schur complement; 3: the full system through a general block-sparse Cholesky."""
     from oracle.oracle import OracleBA
     o = OracleBA(prob)
     p0, x0 = np.array(prob.pose_Rt), np.array(prob.pt_xyz)
@@ -108,7 +114,7 @@ def cpu_reference_run(prob, steps, warmup, lm_iters_cpu):
     for s in range(warmup + steps):
         o.set_state(p0, x0)
         t = time.perf_counter()
-        rc, st = o.compute(lm_iters_cpu)
+        rc, st = o.compute(lm_iters_cpu, solve_mode=solve_mode)
         dt = time.perf_counter() - t
         if s >= warmup:
             total_it += max(rc, 0); total_t += dt; per_step.append(dt)
@@ -361,6 +367,7 @@ def main():
         # the same step as the GPU arm (--lm-iters outer iterations from the same initial estimate); one step is ~2 s of
         # CPU work at cfg2, so the driver's K and W stay as they are
         val, ms, n_it = cpu_reference_run(prob, args.steps, args.warmup, args.lm_iters)
+        val_full, _, _ = cpu_reference_run(prob, 1, 0, args.lm_iters, solve_mode=3)
         line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "reference",
@@ -369,7 +376,8 @@ def main():
                                  "sample": "%d steps x %d LM iterations of the same map, CPU restatement (oracle/ba_oracle.c, "
                                            "-O3 -march=native; points eliminated first = the order a fill-reducing sparse Cholesky of the "
                                            "full system takes), 1 thread like the reference's MapMaker thread; reference binary "
-                                           "unavailable (no ROS/TooN/g2o/SuiteSparse)" % (args.steps, args.lm_iters)},
+                                           "unavailable (no ROS/TooN/g2o/SuiteSparse)" % (args.steps, args.lm_iters),
+                                 "full_system": {"value": val_full, "unit": UNIT, "sample": "1 step x %d LM iterations; %s" % (args.lm_iters, FULL_SYSTEM_NOTE)}},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -618,6 +626,8 @@ def main():
                "sample": "1 step (%d LM iterations) of the same map on the host, CPU restatement (oracle/ba_oracle.c, -O3 -march=native; points "
                          "eliminated first = the order a fill-reducing sparse Cholesky of the full system takes), 1 thread; reference binary unavailable"
                          % args.lm_iters}
+        val_full, _, _ = cpu_reference_run(prob, 1, 0, args.lm_iters, solve_mode=3)
+        cpu["full_system"] = {"value": val_full, "unit": UNIT, "sample": "1 step x %d LM iterations; %s" % (args.lm_iters, FULL_SYSTEM_NOTE)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",

@@ -707,6 +707,177 @@ static int inv3_sym(const double* V, double* Vi)
   return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+   solve_mode 3: the FULL non-marginalised system, as the reference configures g2o (BlockSolverX + LinearSolverCholmod with
+   every point vertex setMarginalized(false), src/ChainBundle.cc:1150-1158, 1218).  CHOLMOD is not in this image; this is
+   a general block-sparse right-looking Cholesky with a minimum-degree elimination order chosen on the block graph (what
+   CHOLMOD's AMD does on this matrix up to tie-breaking): nothing in it knows about "points" and "poses" -- blocks of size
+   3 and 6 live in a hash map keyed by (row block, column block), fill blocks are created as they arise, the order comes
+   from a degree-bucket queue.  On a bundle-adjustment matrix minimum degree eliminates the point blocks first (their degree
+   is the handful of poses they touch, a pose's degree is hundreds of points until they are gone and then the whole pose
+   clique), i.e. it performs the Schur complement -- which is why the default restatement (solve_mode 0) is the same
+   arithmetic without the bookkeeping.  Used as the second CPU baseline of bench.py and as an independent check of the
+   Schur path (tests/test_oracle_cpu.py). */
+typedef struct { long long key; double* v; } fs_slot_t;
+typedef struct {
+  int nb;                 /* blocks */
+  const int* bdim;        /* 3 or 6 */
+  fs_slot_t* tab; size_t cap, used;
+  int** adj; int* nadj; int* capadj;    /* neighbour lists (may hold eliminated nodes; filtered on use) */
+} fs_t;
+static size_t fs_hash(long long k, size_t cap) { unsigned long long x = (unsigned long long)k * 0x9E3779B97F4A7C15ull; return (size_t)(x >> 20) & (cap - 1); }
+static double* fs_get(fs_t* f, int i, int j, int create)
+{
+  const long long key = (long long)i * f->nb + j;
+  size_t h = fs_hash(key, f->cap);
+  for (;;) {
+    if (f->tab[h].v == NULL) break;
+    if (f->tab[h].key == key) return f->tab[h].v;
+    h = (h + 1) & (f->cap - 1);
+  }
+  if (!create) return NULL;
+  f->tab[h].key = key;
+  f->tab[h].v = (double*)calloc((size_t)f->bdim[i] * f->bdim[j], sizeof(double));
+  f->used++;
+  return f->tab[h].v;
+}
+static void fs_link(fs_t* f, int i, int j)
+{
+  if (f->nadj[i] == f->capadj[i]) { f->capadj[i] = f->capadj[i] ? 2 * f->capadj[i] : 8; f->adj[i] = (int*)realloc(f->adj[i], sizeof(int) * (size_t)f->capadj[i]); }
+  f->adj[i][f->nadj[i]++] = j;
+}
+/* block (i,j) with i != j is stored once, under (min, max), as a bdim[min] x bdim[max] row-major matrix */
+static double* fs_off(fs_t* f, int i, int j, int create, int* transposed)
+{
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  *transposed = i > j;
+  double* v = fs_get(f, a, b, 0);
+  if (!v && create) { v = fs_get(f, a, b, 1); fs_link(f, a, b); fs_link(f, b, a); }
+  return v;
+}
+static int full_sparse_solve(int nb, const int* bdim, const int* boff, fs_t* f, const double* rhs, double* x)
+{
+  int rc = 0;
+  char* gone = (char*)calloc((size_t)nb + 1, 1);
+  int* order = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+  int* deg = (int*)calloc((size_t)nb + 1, sizeof(int));
+  /* factor storage per eliminated block: its Cholesky factor and the column blocks L_ik */
+  double** Lkk = (double**)calloc((size_t)nb + 1, sizeof(double*));
+  int** col_i = (int**)calloc((size_t)nb + 1, sizeof(int*));
+  double*** col_L = (double***)calloc((size_t)nb + 1, sizeof(double**));
+  int* col_n = (int*)calloc((size_t)nb + 1, sizeof(int));
+  /* degree buckets (degree = number of remaining neighbours): doubly linked lists */
+  int* head = (int*)malloc(sizeof(int) * (size_t)(nb + 2));
+  int* nxt = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+  int* prv = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+  for (int d = 0; d <= nb; d++) head[d] = -1;
+#define FS_UNLINK(i) do { if (prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[deg[i]] = nxt[i]; if (nxt[i] >= 0) prv[nxt[i]] = prv[i]; } while (0)
+#define FS_PUSH(i) do { prv[i] = -1; nxt[i] = head[deg[i]]; if (head[deg[i]] >= 0) prv[head[deg[i]]] = i; head[deg[i]] = i; } while (0)
+  for (int i = nb - 1; i >= 0; i--) { deg[i] = f->nadj[i]; FS_PUSH(i); }       /* (pushed in reverse: ties resolve to the lowest index) */
+  int* nbr = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+  char* mark = (char*)calloc((size_t)nb + 1, 1);
+  int dmin = 0;
+  for (int step = 0; step < nb && !rc; step++) {
+    while (dmin <= nb && head[dmin] < 0) dmin++;
+    const int k = head[dmin];
+    FS_UNLINK(k);
+    gone[k] = 1; order[step] = k;
+    /* remaining neighbours of k (the lists may repeat a node or hold eliminated ones) */
+    int d = 0;
+    for (int t = 0; t < f->nadj[k]; t++) { const int i = f->adj[k][t]; if (!gone[i] && !mark[i]) { mark[i] = 1; nbr[d++] = i; } }
+    for (int t = 0; t < d; t++) mark[nbr[t]] = 0;
+    const int dk = bdim[k];
+    double* Akk = fs_get(f, k, k, 0);
+    Lkk[k] = (double*)malloc(sizeof(double) * (size_t)dk * dk);
+    memcpy(Lkk[k], Akk, sizeof(double) * (size_t)dk * dk);
+    if (chol_dense(Lkk[k], dk)) { rc = -1; break; }
+    col_n[k] = d;
+    col_i[k] = (int*)malloc(sizeof(int) * (size_t)(d + 1));
+    col_L[k] = (double**)malloc(sizeof(double*) * (size_t)(d + 1));
+    for (int t = 0; t < d; t++) {
+      const int i = nbr[t], di = bdim[i];
+      int tr;
+      const double* Aik = fs_off(f, i, k, 0, &tr);               /* A_ik (di x dk); stored under (min,max) */
+      double* L = (double*)malloc(sizeof(double) * (size_t)di * dk);
+      for (int r = 0; r < di; r++) {
+        /* row r of L_ik solves  L_ik Lkk^T = A_ik  (forward substitution along the row) */
+        for (int c = 0; c < dk; c++) {
+          double sacc = tr ? Aik[(size_t)c * di + r] : Aik[(size_t)r * dk + c];
+          for (int q = 0; q < c; q++) sacc -= L[(size_t)r * dk + q] * Lkk[k][(size_t)c * dk + q];
+          L[(size_t)r * dk + c] = sacc / Lkk[k][(size_t)c * dk + c];
+        }
+      }
+      col_i[k][t] = i; col_L[k][t] = L;
+    }
+    /* Schur update of the remaining sub-matrix: A_ij -= L_ik L_jk^T for every pair of neighbours (fill where absent) */
+    for (int t = 0; t < d; t++) {
+      const int i = nbr[t], di = bdim[i];
+      const double* Li = col_L[k][t];
+      double* Aii = fs_get(f, i, i, 0);
+      for (int r = 0; r < di; r++)
+        for (int c = 0; c < di; c++) {
+          double sacc = 0;
+          for (int q = 0; q < dk; q++) sacc += Li[(size_t)r * dk + q] * Li[(size_t)c * dk + q];
+          Aii[(size_t)r * di + c] -= sacc;
+        }
+      for (int u = t + 1; u < d; u++) {
+        const int j = nbr[u], dj = bdim[j];
+        const double* Lj = col_L[k][u];
+        int tr;
+        const int before = f->nadj[i];
+        double* Aij = fs_off(f, i, j, 1, &tr);
+        if (f->nadj[i] != before) {                                /* a fill block: both degrees grow */
+          FS_UNLINK(i); deg[i]++; FS_PUSH(i);
+          FS_UNLINK(j); deg[j]++; FS_PUSH(j);
+        }
+        for (int r = 0; r < di; r++)
+          for (int c = 0; c < dj; c++) {
+            double sacc = 0;
+            for (int q = 0; q < dk; q++) sacc += Li[(size_t)r * dk + q] * Lj[(size_t)c * dk + q];
+            if (tr) Aij[(size_t)c * di + r] -= sacc; else Aij[(size_t)r * dj + c] -= sacc;
+          }
+      }
+      /* i lost the neighbour k */
+      FS_UNLINK(i); deg[i]--; FS_PUSH(i);
+      if (deg[i] < dmin) dmin = deg[i];
+    }
+  }
+  if (!rc) {
+    /* forward: y_k = Lkk^-1 b_k, b_i -= L_ik y_k; backward in reverse order */
+    double* y = (double*)malloc(sizeof(double) * (size_t)(boff[nb] + 1));
+    memcpy(y, rhs, sizeof(double) * (size_t)boff[nb]);
+    for (int step = 0; step < nb; step++) {
+      const int k = order[step], dk = bdim[k];
+      double* yk = y + boff[k];
+      for (int r = 0; r < dk; r++) { double sacc = yk[r]; for (int q = 0; q < r; q++) sacc -= Lkk[k][(size_t)r * dk + q] * yk[q]; yk[r] = sacc / Lkk[k][(size_t)r * dk + r]; }
+      for (int t = 0; t < col_n[k]; t++) {
+        const int i = col_i[k][t], di = bdim[i];
+        const double* L = col_L[k][t];
+        double* yi = y + boff[i];
+        for (int r = 0; r < di; r++) { double sacc = 0; for (int q = 0; q < dk; q++) sacc += L[(size_t)r * dk + q] * yk[q]; yi[r] -= sacc; }
+      }
+    }
+    for (int step = nb - 1; step >= 0; step--) {
+      const int k = order[step], dk = bdim[k];
+      double* yk = y + boff[k];
+      for (int t = 0; t < col_n[k]; t++) {
+        const int i = col_i[k][t], di = bdim[i];
+        const double* L = col_L[k][t];
+        const double* xi = y + boff[i];
+        for (int q = 0; q < dk; q++) { double sacc = 0; for (int r = 0; r < di; r++) sacc += L[(size_t)r * dk + q] * xi[r]; yk[q] -= sacc; }
+      }
+      for (int r = dk - 1; r >= 0; r--) { double sacc = yk[r]; for (int q = r + 1; q < dk; q++) sacc -= Lkk[k][(size_t)q * dk + r] * yk[q]; yk[r] = sacc / Lkk[k][(size_t)r * dk + r]; }
+    }
+    memcpy(x, y, sizeof(double) * (size_t)boff[nb]);
+    free(y);
+  }
+#undef FS_UNLINK
+#undef FS_PUSH
+  for (int k = 0; k < nb; k++) { free(Lkk[k]); for (int t = 0; t < col_n[k]; t++) free(col_L[k][t]); free(col_i[k]); free(col_L[k]); }
+  free(gone); free(order); free(deg); free(Lkk); free(col_i); free(col_L); free(col_n); free(head); free(nxt); free(prv); free(nbr); free(mark);
+  return rc;
+}
+
 #define MAXSLOT 256
 typedef struct { int nslot; int var[MAXSLOT]; double W[MAXSLOT][18]; double V[9]; double bp[3]; } ptblk_t;
 
@@ -723,7 +894,8 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
   memset(h->b, 0, sizeof(double) * (size_t)dim);
   ptblk_t* blk = (ptblk_t*)malloc(sizeof(ptblk_t));
   double* Hfull = NULL;
-  if (solve_mode >= 1) Hfull = (double*)calloc((size_t)dim * (size_t)dim + 1, sizeof(double));
+  if (solve_mode == 1 || solve_mode == 2) Hfull = (double*)calloc((size_t)dim * (size_t)dim + 1, sizeof(double));
+  double* V_all = solve_mode == 3 ? (double*)calloc((size_t)nptv * 9 + 1, sizeof(double)) : NULL;   /* point blocks of the full system */
   /* per-point storage for Schur back-substitution */
   double* Vinv_all = (double*)calloc((size_t)nptv * 9 + 1, sizeof(double));
   int* slot_off = (int*)calloc((size_t)h->n_pt + 1, sizeof(int));
@@ -796,7 +968,9 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
       slot_var[slot_off[p] + s] = blk->var[s];
       memcpy(slot_W + (size_t)(slot_off[p] + s) * 18, blk->W[s], sizeof(blk->W[s]));
     }
-    if (solve_mode >= 1) {
+    if (solve_mode == 3) {
+      memcpy(V_all + 9 * (size_t)pv, blk->V, sizeof(blk->V));
+    } else if (solve_mode >= 1) {
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Hfull[(size_t)(nc + 3 * pv + r) * dim + nc + 3 * pv + c] = blk->V[r * 3 + c];
       for (int s = 0; s < blk->nslot; s++)
@@ -854,6 +1028,49 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
       h->max_cov = nptv > 0 ? cov[nptv / 2] : DBL_MAX;
       free(cov); free(y);
     }
+  } else if (!rc && solve_mode == 3) {
+    /* block graph of the full damped system: npv pose blocks (6) then nptv point blocks (3) */
+    const int nb = npv + nptv;
+    int* bdim = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
+    int* boff = (int*)malloc(sizeof(int) * (size_t)(nb + 2));
+    for (int b = 0; b < nb; b++) { bdim[b] = b < npv ? 6 : 3; boff[b] = b < npv ? 6 * b : nc + 3 * (b - npv); }
+    boff[nb] = dim;
+    fs_t f;
+    memset(&f, 0, sizeof(f));
+    f.nb = nb; f.bdim = bdim;
+    size_t want = 4 * ((size_t)nb + (size_t)cap + (size_t)npv * npv) + 64;
+    f.cap = 1; while (f.cap < want) f.cap <<= 1;
+    f.tab = (fs_slot_t*)calloc(f.cap, sizeof(fs_slot_t));
+    f.adj = (int**)calloc((size_t)nb + 1, sizeof(int*)); f.nadj = (int*)calloc((size_t)nb + 1, sizeof(int)); f.capadj = (int*)calloc((size_t)nb + 1, sizeof(int));
+    for (int a = 0; a < npv; a++) {
+      double* D = fs_get(&f, a, a, 1);
+      for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) D[r * 6 + c] = Hcc[(size_t)(6 * a + r) * nc + 6 * a + c];
+      for (int r = 0; r < 6; r++) D[r * 6 + r] += lambda;
+      for (int b2 = a + 1; b2 < npv; b2++) {
+        int any = 0;
+        for (int r = 0; r < 6 && !any; r++) for (int c = 0; c < 6; c++) if (Hcc[(size_t)(6 * a + r) * nc + 6 * b2 + c] != 0.0) { any = 1; break; }
+        if (!any) continue;
+        int tr;
+        double* O = fs_off(&f, a, b2, 1, &tr);
+        for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) O[r * 6 + c] = Hcc[(size_t)(6 * a + r) * nc + 6 * b2 + c];
+      }
+    }
+    for (int p = 0; p < h->n_pt; p++) {
+      if (h->pt_var[p] < 0) continue;
+      const int pv = h->pt_var[p], node = npv + pv;
+      double* D = fs_get(&f, node, node, 1);
+      memcpy(D, V_all + 9 * (size_t)pv, sizeof(double) * 9);
+      D[0] += lambda; D[4] += lambda; D[8] += lambda;
+      for (int s2 = 0; s2 < slot_cnt[p]; s2++) {
+        int tr;
+        double* O = fs_off(&f, slot_var[slot_off[p] + s2], node, 1, &tr);      /* pose index < point index: stored 6 x 3 as W */
+        memcpy(O, slot_W + (size_t)(slot_off[p] + s2) * 18, sizeof(double) * 18);
+      }
+    }
+    rc = full_sparse_solve(nb, bdim, boff, &f, h->b, h->x);
+    for (size_t i = 0; i < f.cap; i++) free(f.tab[i].v);
+    for (int b = 0; b < nb; b++) free(f.adj[b]);
+    free(f.tab); free(f.adj); free(f.nadj); free(f.capadj); free(bdim); free(boff);
   } else if (!rc && solve_mode == 1) {
     for (int r = 0; r < nc; r++)
       for (int c = 0; c < nc; c++) Hfull[(size_t)r * dim + c] = Hcc[(size_t)r * nc + c];
@@ -900,7 +1117,7 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
     free(red);
   }
   if (rc) memset(h->x, 0, sizeof(double) * (size_t)dim);
-  free(Hcc); free(blk); free(Hfull); free(Vinv_all); free(slot_off); free(slot_var); free(slot_W); free(slot_cnt);
+  free(Hcc); free(blk); free(Hfull); free(V_all); free(Vinv_all); free(slot_off); free(slot_var); free(slot_W); free(slot_cnt);
   return rc;
 }
 

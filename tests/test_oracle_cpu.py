@@ -103,6 +103,28 @@ def test_schur_equals_full_system(tiny):
         assert np.linalg.norm(d0 - d1) <= 1e-9 * np.linalg.norm(d1)
 
 
+@pytest.mark.parametrize("cfg", ["tiny", "cfg1"])
+def test_full_system_block_sparse_cholesky(cfg):
+    """solve_mode 3 -- the reference's configuration (no marginalised points) through a general block-sparse Cholesky with a
+    minimum-degree order (bench.py's second CPU baseline) -- gives the step of the Schur restatement and, on the small map,
+    of the dense natural-order factorisation; a whole Compute follows the same iterates."""
+    prob = synth.make_ba_config(cfg, seed=1)
+    o = OracleBA(prob)
+    for lam in (1e-3, 1.0, 100.0):
+        rc0, d0, s0, _ = o.lm_step(lam, -1, 0)
+        rc3, d3, s3, _ = o.lm_step(lam, -1, 3)
+        assert rc0 == 0 and rc3 == 0 and s0 == s3
+        assert np.linalg.norm(d0 - d3) <= 1e-6 * np.linalg.norm(d0)          # (elimination orders differ: rounding at small lambda)
+        if cfg == "tiny":
+            rc1, d1, _, _ = o.lm_step(lam, -1, 1)
+            assert rc1 == 0 and np.linalg.norm(d1 - d3) <= 1e-6 * np.linalg.norm(d1)
+    a, b = OracleBA(prob), OracleBA(prob)
+    ra, sa = a.compute(6)
+    rb, sb = b.compute(6, solve_mode=3)
+    assert ra == rb and sa.total_trials == sb.total_trials
+    assert np.abs(a.poses() - b.poses()).max() < 1e-8 and np.abs(a.points() - b.points()).max() < 1e-8
+
+
 def test_huber_tukey_sigma():
     v = np.random.default_rng(3).uniform(0, 10, 101)
     srt = np.sort(v)
