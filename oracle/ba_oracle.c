@@ -724,7 +724,20 @@ typedef struct {
   const int* bdim;        /* 3 or 6 */
   fs_slot_t* tab; size_t cap, used;
   int** adj; int* nadj; int* capadj;    /* neighbour lists (may hold eliminated nodes; filtered on use) */
+  double** chunk; int n_chunk; size_t chunk_used;   /* bump allocator for the blocks (zeroed chunks of FS_CHUNK doubles) */
 } fs_t;
+#define FS_CHUNK (1u << 20)
+static double* fs_alloc(fs_t* f, size_t n)
+{
+  if (f->n_chunk == 0 || f->chunk_used + n > FS_CHUNK) {
+    f->chunk = (double**)realloc(f->chunk, sizeof(double*) * (size_t)(f->n_chunk + 1));
+    f->chunk[f->n_chunk++] = (double*)calloc(FS_CHUNK, sizeof(double));
+    f->chunk_used = 0;
+  }
+  double* p = f->chunk[f->n_chunk - 1] + f->chunk_used;
+  f->chunk_used += n;
+  return p;
+}
 static size_t fs_hash(long long k, size_t cap) { unsigned long long x = (unsigned long long)k * 0x9E3779B97F4A7C15ull; return (size_t)(x >> 20) & (cap - 1); }
 static double* fs_get(fs_t* f, int i, int j, int create)
 {
@@ -737,7 +750,7 @@ static double* fs_get(fs_t* f, int i, int j, int create)
   }
   if (!create) return NULL;
   f->tab[h].key = key;
-  f->tab[h].v = (double*)calloc((size_t)f->bdim[i] * f->bdim[j], sizeof(double));
+  f->tab[h].v = fs_alloc(f, (size_t)f->bdim[i] * f->bdim[j]);
   f->used++;
   return f->tab[h].v;
 }
@@ -788,7 +801,7 @@ static int full_sparse_solve(int nb, const int* bdim, const int* boff, fs_t* f, 
     for (int t = 0; t < d; t++) mark[nbr[t]] = 0;
     const int dk = bdim[k];
     double* Akk = fs_get(f, k, k, 0);
-    Lkk[k] = (double*)malloc(sizeof(double) * (size_t)dk * dk);
+    Lkk[k] = fs_alloc(f, (size_t)dk * dk);
     memcpy(Lkk[k], Akk, sizeof(double) * (size_t)dk * dk);
     if (chol_dense(Lkk[k], dk)) { rc = -1; break; }
     col_n[k] = d;
@@ -798,7 +811,7 @@ static int full_sparse_solve(int nb, const int* bdim, const int* boff, fs_t* f, 
       const int i = nbr[t], di = bdim[i];
       int tr;
       const double* Aik = fs_off(f, i, k, 0, &tr);               /* A_ik (di x dk); stored under (min,max) */
-      double* L = (double*)malloc(sizeof(double) * (size_t)di * dk);
+      double* L = fs_alloc(f, (size_t)di * dk);
       for (int r = 0; r < di; r++) {
         /* row r of L_ik solves  L_ik Lkk^T = A_ik  (forward substitution along the row) */
         for (int c = 0; c < dk; c++) {
@@ -873,7 +886,7 @@ static int full_sparse_solve(int nb, const int* bdim, const int* boff, fs_t* f, 
   }
 #undef FS_UNLINK
 #undef FS_PUSH
-  for (int k = 0; k < nb; k++) { free(Lkk[k]); for (int t = 0; t < col_n[k]; t++) free(col_L[k][t]); free(col_i[k]); free(col_L[k]); }
+  for (int k = 0; k < nb; k++) { free(col_i[k]); free(col_L[k]); }
   free(gone); free(order); free(deg); free(Lkk); free(col_i); free(col_L); free(col_n); free(head); free(nxt); free(prv); free(nbr); free(mark);
   return rc;
 }
@@ -1068,7 +1081,8 @@ static int build_and_solve(OraBa* h, double lambda, int solve_mode)
       }
     }
     rc = full_sparse_solve(nb, bdim, boff, &f, h->b, h->x);
-    for (size_t i = 0; i < f.cap; i++) free(f.tab[i].v);
+    for (int i = 0; i < f.n_chunk; i++) free(f.chunk[i]);
+    free(f.chunk);
     for (int b = 0; b < nb; b++) free(f.adj[b]);
     free(f.tab); free(f.adj); free(f.nadj); free(f.capadj); free(bdim); free(boff);
   } else if (!rc && solve_mode == 1) {
