@@ -83,8 +83,8 @@ def _restate(prob, rank, world):
 @pytest.mark.parametrize("cfg,seed,world", [("tiny", 0, 1), ("tiny", 1, 2), ("cfg1", 0, 1), ("cfg1", 2, 3)])
 def test_layout_matches_restatement(cfg, seed, world, shuffle):
     prob = synth.make_ba_config(cfg, seed=seed)
-    # make the case less regular: shuffle the measurement order (the counting-sort path; point-major input as
-    # BundleAdjusterMulti produces it takes the no-sort path), fix a few points, fix a second pose
+    # make the case less regular: shuffle the measurement order (the two-level sort path; point-major input takes the
+    # no-sort path), fix a few points, fix a second pose
     rng = np.random.default_rng(seed)
     prob = copy.copy(prob)
     perm = rng.permutation(prob.n_meas) if shuffle else np.arange(prob.n_meas)
