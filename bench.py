@@ -304,13 +304,14 @@ def bench_config(workload, prob, lm_iters, world):
             "parallelism": "points sharded x%d, NCCL allreduce of the Schur system" % world if world > 1 else "1 GPU"}
 
 
-def csrc_digest(prefixes=("ba_", "mcp_common")):
-    """Content hash of the bundle-adjuster kernel sources: a committed ncu capture is only quoted if it was taken from them."""
+def csrc_digest(prefixes=("ba_", "mcp_common"), host_only=("ba_prep.hpp", "ba_prep_cpu.cpp")):
+    """Content hash of the bundle-adjuster kernel sources and their launcher: a committed ncu capture is only quoted if it
+    was taken from them.  The host marshalling (ba_prep.*: no device code, no launch parameter) is not part of it."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "mcptam_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.startswith(prefixes):
+        if f.startswith(prefixes) and f not in host_only:
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]

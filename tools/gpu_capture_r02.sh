@@ -1,7 +1,7 @@
 # gpurun command list behind profiles/r02_*: bench (both arms), launch list of the bench command, ncu --set full of every BA
 # kernel of a trial round (cfg2), stream timeline.  usage: gpurun --timeout 1500 -- 'bash tools/gpu_capture_r02.sh'
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-DIGEST=$(python -c "import bench; print(bench.csrc_digest())")
+DIGEST=$(python -c "import bench; print(bench.csrc_digest())")   # kernel + launcher sources (not the host marshalling)
 timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r02_gputests.txt
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-frontend > gpurun_out/r02_launches.log 2>&1
