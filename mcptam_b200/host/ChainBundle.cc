@@ -1,5 +1,7 @@
 #include "ChainBundle.h"
 
+#include <algorithm>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -22,16 +24,45 @@ struct PooledHandle {
   ~PooledHandle() { if (h) mcp_ba_destroy(h); }            // released when the thread ends
 };
 static thread_local PooledHandle tl_pool;
+
+// ... and so do the flat host arrays: a ChainBundle hands its vectors (cleared, capacity kept) to the next one built on the
+// thread.  Freshly allocated megabyte vectors cost their first-touch page faults on every BundleAdjust call otherwise
+// (~2 ms of the ~7 ms marshalling of a 200 KF map).
+struct PooledArrays {
+  std::vector<int> idKind, idIndex, ptId;
+  std::vector<double> poseRt, ptXyz, measXy, measNoise;
+  std::vector<uint8_t> poseFixed, ptFixed;
+  std::vector<int32_t> ptChain, measChain, measPt, measCam, measFirstId;
+};
+static thread_local std::vector<PooledArrays> tl_arrays;      // at most two sets are kept
 #define tl_pooled tl_pool.h
 #define tl_pooled_cfg tl_pool.cfg
 
 ChainBundle::ChainBundle(TaylorCameraMap& cams, bool bUseRobust, bool bUseTukey, bool bVerbose)
     : mmCameraModels(cams), mbUseRobust(bUseRobust), mbUseTukey(bUseTukey), mbVerbose(bVerbose)
 {
+  if (!tl_arrays.empty()) {
+    PooledArrays& a = tl_arrays.back();
+    mvIdKind.swap(a.idKind); mvIdIndex.swap(a.idIndex); mvPtId.swap(a.ptId);
+    mvPoseRt.swap(a.poseRt); mvPtXyz.swap(a.ptXyz); mvMeasXy.swap(a.measXy); mvMeasNoise.swap(a.measNoise);
+    mvPoseFixed.swap(a.poseFixed); mvPtFixed.swap(a.ptFixed);
+    mvPtChain.swap(a.ptChain); mvMeasChain.swap(a.measChain); mvMeasPt.swap(a.measPt); mvMeasCam.swap(a.measCam); mvMeasFirstId.swap(a.measFirstId);
+    tl_arrays.pop_back();
+  }
   mvIdKind.push_back(-1); mvIdIndex.push_back(-1);     // id 0 unused
 }
 ChainBundle::~ChainBundle()
 {
+  if (tl_arrays.size() < 2) {
+    tl_arrays.emplace_back();
+    PooledArrays& a = tl_arrays.back();
+    mvIdKind.clear(); mvIdIndex.clear(); mvPtId.clear(); mvPoseRt.clear(); mvPtXyz.clear(); mvMeasXy.clear(); mvMeasNoise.clear();
+    mvPoseFixed.clear(); mvPtFixed.clear(); mvPtChain.clear(); mvMeasChain.clear(); mvMeasPt.clear(); mvMeasCam.clear(); mvMeasFirstId.clear();
+    mvIdKind.swap(a.idKind); mvIdIndex.swap(a.idIndex); mvPtId.swap(a.ptId);
+    mvPoseRt.swap(a.poseRt); mvPtXyz.swap(a.ptXyz); mvMeasXy.swap(a.measXy); mvMeasNoise.swap(a.measNoise);
+    mvPoseFixed.swap(a.poseFixed); mvPtFixed.swap(a.ptFixed);
+    mvPtChain.swap(a.ptChain); mvMeasChain.swap(a.measChain); mvMeasPt.swap(a.measPt); mvMeasCam.swap(a.measCam); mvMeasFirstId.swap(a.measFirstId);
+  }
   if (mpHandle) {
     // a handle whose last call failed (CUDA error state) or that joined a communicator is not worth keeping
     if (!tl_pooled && !mbHandleFailed) { tl_pooled = mpHandle; tl_pooled_cfg = mConfig; } else mcp_ba_destroy(mpHandle);
@@ -52,6 +83,16 @@ int ChainBundle::AddPoint(Vector<3> p, std::vector<int> vCams, bool bFixed)
   if (vCams.empty() || vCams.size() > 2) throw std::invalid_argument("ChainBundle::AddPoint: chains of 1 or 2 poses are supported");
   for (int k = 0; k < 3; k++) mvPtXyz.push_back(p[k]);
   for (int k = 0; k < 2; k++) mvPtChain.push_back(k < (int)vCams.size() ? mvIdIndex.at(vCams[k]) : -1);
+  mvPtFixed.push_back(bFixed ? 1 : 0);
+  mvIdKind.push_back(1); mvIdIndex.push_back((int)mvPtFixed.size() - 1);
+  mvPtId.push_back(mnCurrId);
+  return mnCurrId++;
+}
+int ChainBundle::AddPoint(const Vector<3>& p, int nPose0, int nPose1, bool bFixed)
+{
+  for (int k = 0; k < 3; k++) mvPtXyz.push_back(p[k]);
+  mvPtChain.push_back(mvIdIndex.at(nPose0));
+  mvPtChain.push_back(nPose1 >= 0 ? mvIdIndex.at(nPose1) : -1);
   mvPtFixed.push_back(bFixed ? 1 : 0);
   mvIdKind.push_back(1); mvIdIndex.push_back((int)mvPtFixed.size() - 1);
   mvPtId.push_back(mnCurrId);
@@ -85,6 +126,39 @@ void ChainBundle::AddMeas(int nBasePoseId, int nCamPoseId, int nPointIdx, const 
   mvMeasNoise.push_back(dNoiseSigmaSquared);
   mvMeasFirstId.push_back(nBasePoseId);
   mvMeasCam.push_back(nCameraIndex);
+}
+
+void ChainBundle::AddMeasBlock(int nBasePoseId, int nCamPoseId, int nCameraIndex, size_t n, const int* pPointIds, const double* pXy, const double* pNoise)
+{
+  const int32_t nBase = mvIdIndex.at(nBasePoseId), nCam = nCamPoseId >= 0 ? mvIdIndex.at(nCamPoseId) : -1;
+  mvMeasXy.insert(mvMeasXy.end(), pXy, pXy + 2 * n);
+  mvMeasNoise.insert(mvMeasNoise.end(), pNoise, pNoise + n);
+  for (size_t i = 0; i < n; i++) {
+    mvMeasChain.push_back(nBase); mvMeasChain.push_back(nCam);
+    mvMeasPt.push_back(mvIdIndex.at(pPointIds[i]));
+  }
+  mvMeasFirstId.insert(mvMeasFirstId.end(), n, nBasePoseId);
+  mvMeasCam.insert(mvMeasCam.end(), n, nCameraIndex);
+}
+
+size_t ChainBundle::GrowMeas(size_t n)
+{
+  const size_t at = mvMeasPt.size();
+  mvMeasXy.resize(2 * (at + n)); mvMeasNoise.resize(at + n); mvMeasChain.resize(2 * (at + n)); mvMeasPt.resize(at + n);
+  mvMeasFirstId.resize(at + n); mvMeasCam.resize(at + n);
+  return at;
+}
+void ChainBundle::FillMeasBlock(size_t nAt, int nBasePoseId, int nCamPoseId, int nCameraIndex, size_t n, const int* pPointIds, const double* pXy, const double* pNoise)
+{
+  const int32_t nBase = mvIdIndex.at(nBasePoseId), nCam = nCamPoseId >= 0 ? mvIdIndex.at(nCamPoseId) : -1;
+  std::copy(pXy, pXy + 2 * n, mvMeasXy.begin() + 2 * nAt);
+  std::copy(pNoise, pNoise + n, mvMeasNoise.begin() + nAt);
+  for (size_t i = 0; i < n; i++) {
+    mvMeasChain[2 * (nAt + i)] = nBase; mvMeasChain[2 * (nAt + i) + 1] = nCam;
+    mvMeasPt[nAt + i] = mvIdIndex.at(pPointIds[i]);
+    mvMeasFirstId[nAt + i] = nBasePoseId;
+    mvMeasCam[nAt + i] = nCameraIndex;
+  }
 }
 
 void ChainBundle::Reserve(size_t nPoses, size_t nPoints, size_t nMeas)

@@ -24,7 +24,14 @@ class ChainBundle {
   // The same measurement without the per-call vector / string copies of the reference signature: the two pose ids of the
   // observing chain and the index CameraIndex(name) returned for the camera.  BundleAdjusterCuda marshals through these.
   int CameraIndex(const std::string& cameraName);
+  int AddPoint(const Vector<3>& v3Pos, int nPose0, int nPose1, bool bFixed);      // chain {nPose0[, nPose1]} (nPose1 = -1: one link), no vector argument
   void AddMeas(int nBasePoseId, int nCamPoseId, int nPointIdx, const Vector<2>& v2Pos, double dNoiseSigmaSquared, int nCameraIndex);
+  // n measurements of one keyframe (same chain, same camera) in one call: what BundleAdjusterCuda::Marshal's parallel pass hands over
+  void AddMeasBlock(int nBasePoseId, int nCamPoseId, int nCameraIndex, size_t n, const int* pPointIds, const double* pXy, const double* pNoise);
+  // the same in two steps, for callers that fill disjoint blocks from several threads: GrowMeas(n) makes room for n more
+  // measurements and returns the position of the first, FillMeasBlock writes one keyframe's block at a position inside it
+  size_t GrowMeas(size_t n);
+  void FillMeasBlock(size_t nAt, int nBasePoseId, int nCamPoseId, int nCameraIndex, size_t n, const int* pPointIds, const double* pXy, const double* pNoise);
   void Reserve(size_t nPoses, size_t nPoints, size_t nMeas);
   int Compute(bool* pAbortSignal, int nNumIter = snMaxIterations, double dUserLambda = -1);   // :1305
   bool Converged() { return mbConverged; }

@@ -96,13 +96,13 @@ def test_bad_camera_is_rejected(host):
 
 
 def test_bundle_adjuster_marshalling_equals_the_reference_loop(host, tmp_path):
-    """BundleAdjusterCuda::Marshal (hash-map lookups, allocation-free AddMeas) hands mcp_ba_load exactly the arrays of
+    """BundleAdjusterCuda::Marshal (parallel per-keyframe gather, hash-map lookups, pooled arrays) hands mcp_ba_load exactly the arrays of
     the loop as src/BundleAdjusterMulti.cc:83-203 writes it (host/test_marshal_cpu.cc; no device call involved)."""
     import subprocess
     build = os.path.join(ROOT, "mcptam_b200", "_build")
     exe = str(tmp_path / "test_marshal")
     subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-Wno-unused-function", "-o", exe,
                            os.path.join(ROOT, "mcptam_b200", "host", "test_marshal_cpu.cc"), "-L" + build, "-lmcptam_host", "-lmcptam_b200",
-                           "-Wl,-rpath," + build])
+                           "-Wl,-rpath," + build, "-lpthread"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "MARSHAL_TEST OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
