@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <map>
 #include <random>
+#include <thread>
+#include <cstdlib>
 
 #include "BundleAdjusterCuda.h"
 
@@ -19,6 +21,7 @@ struct ProbeBundle : ChainBundle {
 struct ProbeAdjuster : BundleAdjusterCuda {
   using BundleAdjusterCuda::BundleAdjusterCuda;
   using BundleAdjusterCuda::Marshal;
+  void Reset() { mmPoint_BundleID.clear(); mmBundleID_Point.clear(); mmBase_BundleID.clear(); mmBundleID_Base.clear(); mmCamName_BundleID.clear(); }   // as BundleAdjust() does
 };
 
 static inline int LevelScale(int l) { return 1 << l; }
@@ -132,6 +135,25 @@ int main()
               a.mvPtFixed == b.mvPtFixed && a.mvMeasXy == b.mvMeasXy && a.mvMeasChain == b.mvMeasChain && a.mvMeasPt == b.mvMeasPt &&
               a.mvMeasNoise == b.mvMeasNoise && a.mvMeasCam == b.mvMeasCam && a.mvMeasFirstId == b.mvMeasFirstId && a.mvCamNames == b.mvCamNames);
     if (rep == 0) std::printf("marshalled %zu poses, %zu points, %zu measurements (map holds %zu)\n", b.mvPoseFixed.size(), b.mvPtFixed.size(), b.mvMeasPt.size(), nMeas);
+  }
+  {
+    // the worker pool under churn: 150 more calls with the thread count changing from call to call (pool growth, threads that
+    // sit out a pass, wake-ups from sleep), one adapter object as in production
+    ProbeBundle ref(cams, true, true, false);
+    MarshalReferenceStyle(ref, adjust, fixed, points);
+    ProbeAdjuster adj(cams);
+    for (int rep = 0; rep < 150; rep++) {
+      char buf[8];
+      std::snprintf(buf, sizeof(buf), "%d", 1 + (rep * 5) % 8);
+      setenv("MCP_HOST_THREADS", buf, 1);
+      ProbeBundle b(cams, true, true, false);
+      adj.Reset();
+      adj.Marshal(b, adjust, fixed, points);
+      fail += !(ref.mvMeasXy == b.mvMeasXy && ref.mvMeasChain == b.mvMeasChain && ref.mvMeasPt == b.mvMeasPt && ref.mvMeasNoise == b.mvMeasNoise &&
+                ref.mvMeasCam == b.mvMeasCam && ref.mvMeasFirstId == b.mvMeasFirstId && ref.mvPtXyz == b.mvPtXyz && ref.mvPtChain == b.mvPtChain);
+      if (rep % 37 == 0) std::this_thread::sleep_for(std::chrono::milliseconds(2));      // lets the workers fall asleep
+    }
+    unsetenv("MCP_HOST_THREADS");
   }
   std::printf("reference-style %.2f ms, Marshal %.2f ms\n", tRef, tNew);
   std::printf(fail ? "MARSHAL_TEST FAILED\n" : "MARSHAL_TEST OK\n");
